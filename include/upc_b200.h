@@ -1,0 +1,238 @@
+/*
+ * upc_b200.h - C ABI of the B200-native particle hot path of uncertainty_planning_core.
+ *
+ * The entry points below are what a reference-side plugin binds:
+ *
+ *   upc_forward_simulate*      replaces a concrete SimulatorInterface::ForwardSimulateRobots
+ *                              (pure virtual at include/uncertainty_planning_core/simple_simulator_interface.hpp:623,
+ *                               called at uncertainty_contact_planning.hpp:2065 and :1826)
+ *   upc_check_config_collision replaces SimulatorInterface::CheckConfigCollision (simple_simulator_interface.hpp:617)
+ *   upc_cluster_particles*     replaces UncertaintyPlanningSpace::ClusterParticles index clustering
+ *                              (uncertainty_contact_planning.hpp:1986-2034: PerformSpatialFeatureClustering :1915 +
+ *                               RunDistanceClusteringOnInitialClusters :1947) and PolicyParticleClusteringFn (:1558)
+ *   upc_get_stats/reset_stats  back SimulatorInterface::GetStatistics / ResetStatistics (simple_simulator_interface.hpp:613-615)
+ *
+ * Everything is POD: plain pointers and sizes, int32 status codes, no C++ or torch types.
+ * All floating-point data is IEEE double unless stated; configurations cross the boundary as
+ * structure-of-arrays [C][n] (component-major, particle-minor) with C = upc_config_width(kind, dof).
+ */
+#ifndef UPC_B200_H
+#define UPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UPC_MAX_DOF 16
+#define UPC_MAX_JOINTS 16
+#define UPC_MAX_LINKS 17
+
+/* status codes */
+#define UPC_OK 0
+#define UPC_ERR_INVALID_ARGUMENT 1 /* maps to std::invalid_argument in the C++ shim */
+#define UPC_ERR_CUDA 2             /* maps to std::runtime_error */
+#define UPC_ERR_NO_ROBOT 3
+#define UPC_ERR_UNSUPPORTED 4
+
+/* robot kinds: the three instantiations fixed by uncertainty_planning_core.hpp:130-166 */
+#define UPC_ROBOT_SE2 0
+#define UPC_ROBOT_SE3 1
+#define UPC_ROBOT_LINKED 2
+
+/* SimpleJointModel::JOINT_TYPE values (simple_robot_models.hpp:881) */
+#define UPC_JOINT_FIXED 0
+#define UPC_JOINT_REVOLUTE 1
+#define UPC_JOINT_CONTINUOUS 2
+#define UPC_JOINT_PRISMATIC 4
+
+/* SPATIAL_FEATURE_CLUSTERING_TYPE (uncertainty_contact_planning.hpp:52-99), plus NONE = distance pass only */
+#define UPC_FEATURE_NONE 0
+#define UPC_FEATURE_CONVEX_REGION_SIGNATURE 1
+#define UPC_FEATURE_ACTUATION_CENTER_CONNECTIVITY 2
+#define UPC_FEATURE_POINT_TO_POINT_MOVEMENT 3
+
+typedef struct upc_handle upc_handle;
+
+/*
+ * Environment: dense voxel grids in the sdf_tools layout index = (x*ny + y)*nz + z.
+ * grid_from_world is the inverse of the grids' origin transform (row-major 3x4), so that
+ * p_grid = grid_from_world * p_world and voxel (ix,iy,iz) covers [ix,ix+1)*resolution etc.
+ * A world point is in bounds iff 0 <= floor(p_grid/resolution) < n on every axis.
+ */
+typedef struct upc_env_desc
+{
+    int32_t nx, ny, nz;
+    int32_t reserved0;
+    double resolution;
+    double grid_from_world[12];
+    const float* sdf;               /* nx*ny*nz signed distances (metres), host memory */
+    const uint32_t* convex_segment; /* nx*ny*nz convex-segment bitmasks, may be NULL (CRS clustering unavailable) */
+    const float* occupancy;         /* nx*ny*nz occupancies, may be NULL (AC clustering unavailable) */
+    float sdf_oob_value;            /* distance reported for out-of-bounds points */
+    float occupancy_oob_value;      /* occupancy of the default cell returned for out-of-bounds lookups */
+} upc_env_desc;
+
+/* Per-axis controller / sensor / actuator parameters (SE2_ROBOT_CONFIG, SE3_ROBOT_CONFIG, LINKED_ROBOT_CONFIG
+ * fields at simple_robot_models.hpp:38-90, :453-505, :1183-1214, expanded per axis). */
+typedef struct upc_axis_params
+{
+    double kp, ki, kd, integral_clamp;
+    double velocity_limit;
+    double max_sensor_noise;
+    double max_actuator_noise;
+} upc_axis_params;
+
+typedef struct upc_joint_desc
+{
+    int32_t type;         /* UPC_JOINT_* */
+    int32_t parent_link;  /* index into links */
+    int32_t child_link;
+    int32_t reserved0;
+    double axis[3];
+    double lower_limit, upper_limit; /* ignored for continuous joints */
+    double transform[12];            /* parent link origin -> joint, row-major 3x4 */
+} upc_joint_desc;
+
+/*
+ * Robot model. Body points are (x, y, z, radius) in their link's frame, grouped by link:
+ * link l owns points [link_point_offset[l], link_point_offset[l+1]). radius = 0 reproduces the reference's
+ * point model (EigenHelpers::VectorVector4d with w = 1); radius > 0 gives sphere-approximated links.
+ * SE2/SE3 robots have one link ("robot"), dof 3 / 6, and ignore the joint table.
+ */
+typedef struct upc_robot_desc
+{
+    int32_t kind; /* UPC_ROBOT_* */
+    int32_t dof;  /* active degrees of freedom: 3, 6, or number of non-fixed joints */
+    int32_t num_links;
+    int32_t num_joints; /* linked only, fixed joints included, parents before children (simple_robot_models.hpp:1299-1343) */
+    int32_t num_points;
+    int32_t reserved0;
+    int32_t link_point_offset[UPC_MAX_LINKS + 1];
+    const double* points;                 /* num_points * 4 doubles, host memory */
+    upc_axis_params axis[UPC_MAX_DOF];    /* SE2: x, y, zr; SE3: x, y, z, xr, yr, zr; linked: active joints in order */
+    double distance_weights[UPC_MAX_DOF]; /* linked only (simple_robot_models.hpp:2191-2217) */
+    double base_transform[12];            /* linked only */
+    upc_joint_desc joints[UPC_MAX_JOINTS];
+} upc_robot_desc;
+
+/*
+ * Simulation parameters: the ForwardSimulateRobots arguments (simple_simulator_interface.hpp:623) plus the
+ * solver settings the concrete simulator owns (normative spec in DESIGN.md section 3).
+ */
+typedef struct upc_sim_params
+{
+    int32_t num_steps;        /* controller intervals per edge: max(1, (uint32)(forward_simulation_time * controller_frequency)) */
+    int32_t max_microsteps;   /* M_max: actuator-draw slots per controller interval present on the tape (>= 1) */
+    int32_t allow_contacts;
+    int32_t use_individual_jacobians;
+    int32_t max_resolver_iterations;   /* default 25 */
+    int32_t resolver_decay_iterations; /* default 5 */
+    int32_t reserved0, reserved1;
+    double controller_interval;          /* seconds */
+    double simulation_shortcut_distance; /* early exit when distance(config, target) < this; <= 0 disables */
+    double contact_distance;             /* a body point collides iff sdf(p) - radius < contact_distance */
+    double resolve_distance;             /* corrections push points out to this distance (>= contact_distance) */
+    double microstep_distance;           /* max workspace motion per microstep (metres) */
+    double resolver_initial_scale;       /* default 1.0 */
+    double resolver_decay_rate;          /* default 0.5 */
+    double resolver_damping;             /* lambda of the damped normal equations, default 1e-6 */
+} upc_sim_params;
+
+typedef struct upc_cluster_params
+{
+    int32_t feature_type; /* UPC_FEATURE_* */
+    int32_t reserved0;
+    double signature_matching_threshold;
+    double distance_clustering_threshold;
+    /* POINT_TO_POINT_MOVEMENT only (uncertainty_contact_planning.hpp:1801-1863) */
+    double goal_distance_threshold;
+    const upc_sim_params* ptpm_sim;
+    const double* ptpm_tape; /* tape for the n*(n-1) pair simulations, same layout as upc_forward_simulate */
+} upc_cluster_params;
+
+/* counters surfaced through GetStatistics() */
+typedef struct upc_stats
+{
+    int64_t kernel_launches;
+    int64_t particles_simulated;
+    int64_t particle_steps;         /* controller intervals actually executed (early exits excluded) */
+    int64_t collided_particles;
+    int64_t resolver_iterations;    /* total contact-resolver iterations */
+    int64_t failed_resolves;        /* microsteps reverted because the resolver did not clear the contact */
+    int64_t cluster_calls;
+    int64_t cluster_fallback_calls; /* particle sets that needed the exact complete-link path */
+    int64_t h2d_bytes;
+    int64_t d2h_bytes;
+} upc_stats;
+
+/* number of doubles per configuration: SE2 3 (x, y, theta); SE3 12 (R row-major, then t); linked dof */
+int32_t upc_config_width(int32_t kind, int32_t dof);
+
+/* doubles per particle on the noise tape: num_steps * (1 + max_microsteps) * dof */
+int64_t upc_tape_doubles_per_particle(const upc_sim_params* params, int32_t dof);
+
+const char* upc_last_error(void);
+const char* upc_version(void);
+
+int32_t upc_create(const upc_env_desc* env, int32_t device, upc_handle** out);
+int32_t upc_destroy(upc_handle* h);
+int32_t upc_set_robot(upc_handle* h, const upc_robot_desc* robot);
+int32_t upc_get_stats(upc_handle* h, upc_stats* out);
+int32_t upc_reset_stats(upc_handle* h);
+/* tuning: lanes cooperating on one particle (1, 2, 4, 8, 16 or 32); 0 restores the built-in choice. Results do not depend on it. */
+int32_t upc_set_lanes_per_particle(upc_handle* h, int32_t lanes);
+
+/* pinned host memory helpers for callers that want the fast H2D/D2H path */
+int32_t upc_host_alloc(void** ptr, int64_t bytes);
+int32_t upc_host_free(void* ptr);
+
+/*
+ * Batched forward simulation. starts: [C][n]; targets: [C][n_targets] with n_targets == 1 or n;
+ * tape: [num_steps][1 + max_microsteps][dof][n] pre-truncated draws (slot 0 of each step = sensor draws in
+ * [-max_sensor_noise, +max_sensor_noise]; slots 1.. = actuator draws in [-1, 1]); out_configs: [C][n];
+ * out_collided: n bytes, 1 iff the particle touched the environment during the edge.
+ * Host-pointer form: copies inputs to the device, runs, copies results back, synchronises.
+ */
+int32_t upc_forward_simulate(upc_handle* h, const upc_sim_params* params, int64_t n, const double* starts,
+                             int64_t n_targets, const double* targets, const double* tape, double* out_configs,
+                             uint8_t* out_collided);
+/* Device-pointer form: all buffers in device memory, asynchronous on stream (a cudaStream_t, or NULL for the handle's stream). */
+int32_t upc_forward_simulate_device(upc_handle* h, const upc_sim_params* params, int64_t n, const double* d_starts,
+                                    int64_t n_targets, const double* d_targets, const double* d_tape,
+                                    double* d_out_configs, uint8_t* d_out_collided, void* stream);
+
+/* CheckConfigCollision: 1 iff any body point of `config` has sdf - radius < contact_distance + inflation */
+int32_t upc_check_config_collision(upc_handle* h, const double* config, double contact_distance, double inflation,
+                                   int32_t* out_in_collision);
+
+/*
+ * Outcome clustering of n_sets independent particle sets of set_size particles each
+ * (configs: [C][n_sets*set_size], set s owns particles [s*set_size, (s+1)*set_size)).
+ * labels[i] = cluster of particle i within its set, clusters numbered by increasing smallest member;
+ * n_clusters[s] = cluster count of set s. Collided particles take part in clustering
+ * (uncertainty_contact_planning.hpp:2000-2025 drops them afterwards, in the shim).
+ */
+int32_t upc_cluster_particles(upc_handle* h, const upc_cluster_params* params, int64_t n_sets, int64_t set_size,
+                              const double* configs, int32_t* labels, int32_t* n_clusters);
+int32_t upc_cluster_particles_device(upc_handle* h, const upc_cluster_params* params, int64_t n_sets, int64_t set_size,
+                                     const double* d_configs, int32_t* d_labels, int32_t* d_n_clusters, void* stream);
+
+/*
+ * Host-side noise tape generator: fills tape[.][first..first+n) for particles
+ * first_particle .. first_particle+n-1 of a batch whose tape has `tape_stride` particles per row
+ * (tape_stride >= n; pass tape + offset to fill a shard).  Particle i always draws from its own
+ * std::mt19937_64 stream keyed by (seed, i): tapes do not depend on thread count or GPU sharding.
+ */
+int32_t upc_fill_noise_tape(uint64_t seed, const upc_robot_desc* robot, const upc_sim_params* params, int64_t first_particle,
+                            int64_t n, int64_t tape_stride, double* tape);
+
+/* blocks until everything queued on the handle's stream has finished */
+int32_t upc_synchronize(upc_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* UPC_B200_H */

@@ -1,0 +1,237 @@
+/*
+ * upc_math.h - deterministic elementary functions shared by the CUDA kernels and the CPU oracle.
+ *
+ * Why this exists: the reference computes angle wraps, SE(3) log/exp and quaternion distances through
+ * libm / Eigen / arc_utilities (EnforceContinuousRevoluteBounds at simple_robot_models.hpp:115,1083;
+ * ContinuousRevoluteSignedDistance :415,1112; TwistBetweenTransforms / ExpTwist :657-666,759;
+ * EigenHelpers::Distance :873).  glibc and the CUDA math library do not round sin/cos/atan2 identically,
+ * so cluster memberships and collision flags could not be bit-exact between a CPU oracle and the GPU.
+ * Everything here is built only from IEEE-754 exact operations (+ - * / sqrt fma floor rint fmod), which
+ * round identically on x86-64 and sm_100a when contraction is disabled (nvcc -fmad=false,
+ * g++ -ffp-contract=off) and fused multiply-adds are written explicitly.
+ *
+ * Polynomial kernels follow the classic published minimax forms for sin/cos on [-pi/4,pi/4] and atan with
+ * four break points; coefficients are checked against mpmath in tests/test_math.py.
+ */
+#ifndef UPC_MATH_H
+#define UPC_MATH_H
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define UPC_HD __host__ __device__ __forceinline__
+#else
+#define UPC_HD inline
+#endif
+
+#define UPC_PI 3.14159265358979323846
+#define UPC_TWO_PI 6.28318530717958647692
+#define UPC_HALF_PI 1.57079632679489661923
+
+UPC_HD double upc_fma(double a, double b, double c)
+{
+#if defined(__CUDA_ARCH__)
+    return __fma_rn(a, b, c);
+#else
+    return __builtin_fma(a, b, c);
+#endif
+}
+
+UPC_HD double upc_rint(double x)
+{
+#if defined(__CUDA_ARCH__)
+    return rint(x);
+#else
+    return __builtin_rint(x);
+#endif
+}
+
+UPC_HD double upc_abs(double x) { return fabs(x); }
+
+/* min/max written as selects so that host and device agree on every input (no NaN inputs by contract). */
+UPC_HD double upc_min(double a, double b) { return (b < a) ? b : a; }
+UPC_HD double upc_max(double a, double b) { return (a < b) ? b : a; }
+
+/* sin and cos kernels on |r| <= pi/4 */
+UPC_HD double upc_ksin(double r)
+{
+    const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03,
+                 S3 = -1.98412698298579493134e-04, S4 = 2.75573137070700676789e-06,
+                 S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+    const double z = r * r;
+    double p = upc_fma(z, S6, S5);
+    p = upc_fma(z, p, S4);
+    p = upc_fma(z, p, S3);
+    p = upc_fma(z, p, S2);
+    p = upc_fma(z, p, S1);
+    return upc_fma(r * z, p, r);
+}
+
+UPC_HD double upc_kcos(double r)
+{
+    const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03,
+                 C3 = 2.48015872894767294178e-05, C4 = -2.75573143513906633035e-07,
+                 C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+    const double z = r * r;
+    double p = upc_fma(z, C6, C5);
+    p = upc_fma(z, p, C4);
+    p = upc_fma(z, p, C3);
+    p = upc_fma(z, p, C2);
+    p = upc_fma(z, p, C1);
+    /* 1 - z/2 + z^2 * p */
+    return upc_fma(z * z, p, upc_fma(-0.5, z, 1.0));
+}
+
+/* Simultaneous sine and cosine. Accurate (about 1 ulp) for |x| up to about 1e5; beyond that the two-term
+ * Cody-Waite reduction degrades gracefully. Angles on this path are bounded by a few pi. */
+UPC_HD void upc_sincos(double x, double* s, double* c)
+{
+    const double TWO_OVER_PI = 6.36619772367581382433e-01;
+    const double PIO2_HI = 1.57079632673412561417e+00; /* first 33 bits of pi/2 */
+    const double PIO2_LO = 6.07710050650619224932e-11; /* pi/2 - PIO2_HI */
+    const double k = upc_rint(x * TWO_OVER_PI);
+    double r = upc_fma(-k, PIO2_HI, x);
+    r = upc_fma(-k, PIO2_LO, r);
+    const long long q = (long long)k;
+    const double sr = upc_ksin(r);
+    const double cr = upc_kcos(r);
+    switch ((int)(q & 3LL))
+    {
+        case 0: *s = sr; *c = cr; break;
+        case 1: *s = cr; *c = -sr; break;
+        case 2: *s = -sr; *c = -cr; break;
+        default: *s = -cr; *c = sr; break;
+    }
+}
+
+UPC_HD double upc_sin(double x) { double s, c; upc_sincos(x, &s, &c); return s; }
+UPC_HD double upc_cos(double x) { double s, c; upc_sincos(x, &s, &c); return c; }
+
+/* arctangent, four-interval argument reduction + odd/even split polynomial */
+UPC_HD double upc_atan(double xin)
+{
+    const double aT0 = 3.33333333333329318027e-01, aT1 = -1.99999999998764832476e-01,
+                 aT2 = 1.42857142725034663711e-01, aT3 = -1.11111104054623557880e-01,
+                 aT4 = 9.09088713343650656196e-02, aT5 = -7.69187620504482999495e-02,
+                 aT6 = 6.66107313738753120669e-02, aT7 = -5.83357013379057348645e-02,
+                 aT8 = 4.97687799461593236017e-02, aT9 = -3.65315727442169155270e-02,
+                 aT10 = 1.62858201153657823623e-02;
+    const bool neg = xin < 0.0;
+    double x = fabs(xin);
+    double hi = 0.0, lo = 0.0;
+    bool reduced = true;
+    if (x < 0.4375)
+    {
+        reduced = false;
+    }
+    else if (x < 0.6875)
+    {
+        hi = 4.63647609000806093515e-01; lo = 2.26987774529616870924e-17;
+        x = (2.0 * x - 1.0) / (2.0 + x);
+    }
+    else if (x < 1.1875)
+    {
+        hi = 7.85398163397448278999e-01; lo = 3.06161699786838301793e-17;
+        x = (x - 1.0) / (x + 1.0);
+    }
+    else if (x < 2.4375)
+    {
+        hi = 9.82793723247329054082e-01; lo = 1.39033110312309984516e-17;
+        x = (x - 1.5) / upc_fma(1.5, x, 1.0);
+    }
+    else
+    {
+        hi = 1.57079632679489655800e+00; lo = 6.12323399573676603587e-17;
+        x = -1.0 / x;
+    }
+    const double z = x * x;
+    const double w = z * z;
+    double s1 = upc_fma(w, aT10, aT8);
+    s1 = upc_fma(w, s1, aT6);
+    s1 = upc_fma(w, s1, aT4);
+    s1 = upc_fma(w, s1, aT2);
+    s1 = upc_fma(w, s1, aT0);
+    s1 = z * s1;
+    double s2 = upc_fma(w, aT9, aT7);
+    s2 = upc_fma(w, s2, aT5);
+    s2 = upc_fma(w, s2, aT3);
+    s2 = upc_fma(w, s2, aT1);
+    s2 = w * s2;
+    double res;
+    if (!reduced)
+    {
+        res = x - x * (s1 + s2);
+    }
+    else
+    {
+        res = hi - ((x * (s1 + s2) - lo) - x);
+    }
+    return neg ? -res : res;
+}
+
+/* atan2 restricted to finite inputs. atan2(0,0) = 0. */
+UPC_HD double upc_atan2(double y, double x)
+{
+    const double ay = fabs(y);
+    const double ax = fabs(x);
+    double a;
+    if (ax == 0.0)
+    {
+        a = (ay == 0.0) ? 0.0 : UPC_HALF_PI;
+    }
+    else
+    {
+        a = upc_atan(ay / ax);
+        if (x < 0.0)
+        {
+            a = UPC_PI - a;
+        }
+    }
+    return (y < 0.0) ? -a : a;
+}
+
+/* arccosine for |x| <= 1 through atan2(sqrt((1-x)(1+x)), x) */
+UPC_HD double upc_acos(double x)
+{
+    const double sn = sqrt((1.0 - x) * (1.0 + x));
+    return upc_atan2(sn, x);
+}
+
+/* Angle wrap into (-pi, pi]; restates EigenHelpers::EnforceContinuousRevoluteBounds as used at
+ * simple_robot_models.hpp:115 and :1083 (source un-vendored; this is the normative form here). */
+UPC_HD double upc_wrap_angle(double v)
+{
+    if ((v <= -UPC_PI) || (v > UPC_PI))
+    {
+        const double r = fmod(v, UPC_TWO_PI);
+        if (r <= -UPC_PI)
+        {
+            return r + UPC_TWO_PI;
+        }
+        else if (r > UPC_PI)
+        {
+            return r - UPC_TWO_PI;
+        }
+        return r;
+    }
+    return v;
+}
+
+/* Shortest signed rotation from a to b, in (-pi, pi]; restates ContinuousRevoluteSignedDistance as used
+ * at simple_robot_models.hpp:415 and :1112. */
+UPC_HD double upc_angle_signed_distance(double a, double b)
+{
+    const double raw = upc_wrap_angle(b) - upc_wrap_angle(a);
+    if (raw <= -UPC_PI)
+    {
+        return raw + UPC_TWO_PI;
+    }
+    else if (raw > UPC_PI)
+    {
+        return raw - UPC_TWO_PI;
+    }
+    return raw;
+}
+
+#endif /* UPC_MATH_H */

@@ -1,0 +1,200 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle.so) and of oracle/_ref/libref_pid.so.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  The product package never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from uncertainty_planning_core_b200 import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+_REF = None
+
+
+def build(force=False):
+    """Compile liboracle.so (and oracle/_ref when the reference tree is present)."""
+    so = os.path.join(_HERE, "liboracle.so")
+    if force or not os.path.exists(so):
+        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"])
+    if os.path.isdir("/root/reference"):
+        subprocess.check_call(["make", "-C", _HERE, "ref"])
+    return so
+
+
+def load():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    so = os.path.join(_HERE, "liboracle.so")
+    if not os.path.exists(so):
+        build()
+    lib = C.CDLL(so)
+    vp, i32, i64, dp = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    lib.oracle_last_error.restype = C.c_char_p
+    lib.oracle_num_threads.restype = i32
+    lib.oracle_set_num_threads.argtypes = [i32]
+    lib.oracle_pid_sequence.argtypes = [dp, dp, dp, dp, vp, vp, i32, vp]
+    lib.oracle_pid_sequence.restype = dp
+    lib.oracle_math.argtypes = [i32, i64, vp, vp, vp]
+    lib.oracle_se3_log.argtypes = [vp, vp]
+    lib.oracle_se3_exp.argtypes = [vp, vp]
+    lib.oracle_forward_simulate.argtypes = [C.POINTER(abi.EnvDesc), C.POINTER(abi.RobotDesc), C.POINTER(abi.SimParams),
+                                            i64, vp, i64, vp, vp, vp, vp, C.POINTER(abi.Stats)]
+    lib.oracle_check_config_collision.argtypes = [C.POINTER(abi.EnvDesc), C.POINTER(abi.RobotDesc), vp, dp, dp, C.POINTER(i32)]
+    lib.oracle_cluster_particles.argtypes = [C.POINTER(abi.EnvDesc), C.POINTER(abi.RobotDesc), C.POINTER(abi.ClusterParams),
+                                             i64, i64, vp, vp, vp, C.POINTER(abi.Stats)]
+    lib.oracle_pair_distances.argtypes = [C.POINTER(abi.RobotDesc), i64, vp, vp]
+    lib.oracle_pair_distances_reference_style.argtypes = [C.POINTER(abi.RobotDesc), i64, vp, vp]
+    lib.oracle_region_signatures.argtypes = [C.POINTER(abi.EnvDesc), C.POINTER(abi.RobotDesc), i64, vp, vp]
+    lib.oracle_sdf_lookup.argtypes = [C.POINTER(abi.EnvDesc), i64, vp, vp, vp]
+    lib.oracle_complete_link.argtypes = [vp, i64, dp, vp, vp]
+    for name in ("oracle_forward_simulate", "oracle_check_config_collision", "oracle_cluster_particles",
+                 "oracle_pair_distances", "oracle_pair_distances_reference_style", "oracle_region_signatures",
+                 "oracle_sdf_lookup", "oracle_complete_link"):
+        getattr(lib, name).restype = i32
+    _LIB = lib
+    return lib
+
+
+def load_ref_pid():
+    """The reference's own PID controller compiled unmodified (None when oracle/_ref was never built)."""
+    global _REF
+    if _REF is not None:
+        return _REF
+    so = os.path.join(_HERE, "_ref", "libref_pid.so")
+    if not os.path.exists(so):
+        return None
+    lib = C.CDLL(so)
+    lib.ref_pid_sequence.argtypes = [C.c_double] * 4 + [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.ref_pid_sequence.restype = C.c_double
+    _REF = lib
+    return lib
+
+
+def _check(code):
+    if code != 0:
+        raise RuntimeError("oracle error %d: %s" % (code, load().oracle_last_error().decode()))
+
+
+def num_threads():
+    return int(load().oracle_num_threads())
+
+
+def set_num_threads(n):
+    load().oracle_set_num_threads(int(n))
+
+
+def pid_sequence(kp, ki, kd, clamp, errors, dts, lib=None, fn="oracle_pid_sequence"):
+    errors = np.ascontiguousarray(errors, dtype=np.float64)
+    dts = np.ascontiguousarray(dts, dtype=np.float64)
+    out = np.zeros_like(errors)
+    f = getattr(lib or load(), fn)
+    f(kp, ki, kd, clamp, errors.ctypes.data, dts.ctypes.data, len(errors), out.ctypes.data)
+    return out
+
+
+def ref_pid_sequence(kp, ki, kd, clamp, errors, dts):
+    return pid_sequence(kp, ki, kd, clamp, errors, dts, lib=load_ref_pid(), fn="ref_pid_sequence")
+
+
+def math_fn(which, a, b=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(a if b is None else b, dtype=np.float64)
+    out = np.zeros_like(a)
+    load().oracle_math(which, a.size, a.ctypes.data, b.ctypes.data, out.ctypes.data)
+    return out
+
+
+def se3_log(cfg12):
+    cfg12 = np.ascontiguousarray(cfg12, dtype=np.float64)
+    out = np.zeros(6)
+    load().oracle_se3_log(cfg12.ctypes.data, out.ctypes.data)
+    return out
+
+
+def se3_exp(twist6):
+    twist6 = np.ascontiguousarray(twist6, dtype=np.float64)
+    out = np.zeros(12)
+    load().oracle_se3_exp(twist6.ctypes.data, out.ctypes.data)
+    return out
+
+
+def forward_simulate(env, robot, params, starts, targets, tape):
+    """starts [n, C], targets [1 or n, C], tape [S, 1+M, dof, n] -> (configs [n, C], collided [n] bool, stats dict)"""
+    starts = np.asarray(starts, dtype=np.float64)
+    targets = np.asarray(targets, dtype=np.float64)
+    n = starts.shape[0]
+    s_soa = np.ascontiguousarray(starts.T)
+    t_soa = np.ascontiguousarray(targets.T)
+    tape = np.ascontiguousarray(tape, dtype=np.float64)
+    assert tape.shape == abi.tape_shape(params, robot.dof, n)
+    out = np.zeros_like(s_soa)
+    coll = np.zeros(n, dtype=np.uint8)
+    stats = abi.Stats()
+    _check(load().oracle_forward_simulate(C.byref(env.desc), C.byref(robot.desc), C.byref(params), n, s_soa.ctypes.data,
+                                          targets.shape[0], t_soa.ctypes.data, tape.ctypes.data, out.ctypes.data,
+                                          coll.ctypes.data, C.byref(stats)))
+    return np.ascontiguousarray(out.T), coll.astype(bool), stats.as_dict()
+
+
+def check_config_collision(env, robot, config, contact_distance=0.0, inflation=0.0):
+    cfg = np.ascontiguousarray(config, dtype=np.float64)
+    out = C.c_int32(0)
+    _check(load().oracle_check_config_collision(C.byref(env.desc), C.byref(robot.desc), cfg.ctypes.data, contact_distance,
+                                                inflation, C.byref(out)))
+    return bool(out.value)
+
+
+def cluster_particles(env, robot, cparams, configs, n_sets=1):
+    cfg = np.asarray(configs, dtype=np.float64)
+    total = cfg.shape[0]
+    set_size = total // n_sets
+    soa = np.ascontiguousarray(cfg.T)
+    labels = np.zeros(total, dtype=np.int32)
+    ncl = np.zeros(n_sets, dtype=np.int32)
+    stats = abi.Stats()
+    _check(load().oracle_cluster_particles(C.byref(env.desc), C.byref(robot.desc), C.byref(cparams), n_sets, set_size,
+                                           soa.ctypes.data, labels.ctypes.data, ncl.ctypes.data, C.byref(stats)))
+    return labels, ncl, stats.as_dict()
+
+
+def pair_distances(robot, configs, reference_style=False):
+    cfg = np.asarray(configs, dtype=np.float64)
+    n = cfg.shape[0]
+    soa = np.ascontiguousarray(cfg.T)
+    out = np.zeros((n, n))
+    fn = load().oracle_pair_distances_reference_style if reference_style else load().oracle_pair_distances
+    _check(fn(C.byref(robot.desc), n, soa.ctypes.data, out.ctypes.data))
+    return out
+
+
+def region_signatures(env, robot, configs):
+    cfg = np.asarray(configs, dtype=np.float64)
+    n = cfg.shape[0]
+    soa = np.ascontiguousarray(cfg.T)
+    out = np.zeros((n, robot.num_points), dtype=np.uint32)
+    _check(load().oracle_region_signatures(C.byref(env.desc), C.byref(robot.desc), n, soa.ctypes.data, out.ctypes.data))
+    return out
+
+
+def sdf_lookup(env, points):
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    n = pts.shape[0]
+    d = np.zeros(n)
+    g = np.zeros((n, 3))
+    _check(load().oracle_sdf_lookup(C.byref(env.desc), n, pts.ctypes.data, d.ctypes.data, g.ctypes.data))
+    return d, g
+
+
+def complete_link(matrix, threshold):
+    m = np.ascontiguousarray(matrix, dtype=np.float64)
+    n = m.shape[0]
+    labels = np.zeros(n, dtype=np.int32)
+    ncl = C.c_int32(0)
+    _check(load().oracle_complete_link(m.ctypes.data, n, threshold, labels.ctypes.data, C.byref(ncl)))
+    return labels, int(ncl.value)

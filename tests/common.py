@@ -1,0 +1,76 @@
+"""Shared helpers for the test suite: emulation binding, partition canonicalisation, small scenario variants."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from uncertainty_planning_core_b200 import abi  # noqa: E402
+
+_EMU = None
+
+
+def build_emulation(force=False):
+    here = os.path.join(ROOT, "tests", "emulation")
+    so = os.path.join(here, "libupc_emulation.so")
+    src = os.path.join(here, "emulate.cpp")
+    deps = [src] + [os.path.join(ROOT, "uncertainty_planning_core_b200", "csrc", f) for f in ("upc_sim.cuh", "upc_device.cuh")] + \
+           [os.path.join(ROOT, "include", f) for f in ("upc_math.h", "upc_b200.h")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-mfma",
+                               "-I" + os.path.join(ROOT, "include"),
+                               "-I" + os.path.join(ROOT, "uncertainty_planning_core_b200", "csrc"), src, "-o", so])
+    return so
+
+
+def emulation():
+    global _EMU
+    if _EMU is None:
+        lib = C.CDLL(build_emulation())
+        vp, i64 = C.c_void_p, C.c_int64
+        lib.emulate_forward_simulate.argtypes = [C.POINTER(abi.EnvDesc), C.POINTER(abi.RobotDesc), C.POINTER(abi.SimParams),
+                                                 i64, vp, i64, vp, vp, vp, vp, vp]
+        lib.emulate_forward_simulate.restype = C.c_int
+        _EMU = lib
+    return _EMU
+
+
+def emulate_forward_simulate(env, robot, params, starts, targets, tape):
+    """The product's per-thread program run on the CPU with one lane per particle."""
+    starts = np.asarray(starts, dtype=np.float64)
+    targets = np.asarray(targets, dtype=np.float64)
+    n = starts.shape[0]
+    s_soa = np.ascontiguousarray(starts.T)
+    t_soa = np.ascontiguousarray(targets.T)
+    tape = np.ascontiguousarray(tape, dtype=np.float64)
+    out = np.zeros_like(s_soa)
+    coll = np.zeros(n, dtype=np.uint8)
+    counters = np.zeros(4, dtype=np.int64)
+    emulation().emulate_forward_simulate(C.byref(env.desc), C.byref(robot.desc), C.byref(params), n, s_soa.ctypes.data,
+                                         targets.shape[0], t_soa.ctypes.data, tape.ctypes.data, out.ctypes.data,
+                                         coll.ctypes.data, counters.ctypes.data)
+    stats = dict(particle_steps=int(counters[0]), collided_particles=int(counters[1]),
+                 resolver_iterations=int(counters[2]), failed_resolves=int(counters[3]))
+    return np.ascontiguousarray(out.T), coll.astype(bool), stats
+
+
+def canonical_partition(labels):
+    """Partition as a sorted list of sorted member tuples, for order-free comparison."""
+    groups = {}
+    for i, l in enumerate(np.asarray(labels).tolist()):
+        groups.setdefault(l, []).append(i)
+    return sorted(tuple(v) for v in groups.values())
+
+
+def max_ulp_diff(a, b):
+    a = np.ascontiguousarray(a, dtype=np.float64).view(np.int64)
+    b = np.ascontiguousarray(b, dtype=np.float64).view(np.int64)
+    # map the sign-magnitude float ordering onto a monotone integer line
+    a = np.where(a < 0, np.int64(-2 ** 63) - a, a)
+    b = np.where(b < 0, np.int64(-2 ** 63) - b, b)
+    return int(np.max(np.abs(a - b))) if a.size else 0

@@ -1,0 +1,89 @@
+/*
+ * emulate.cpp - runs the product's per-particle device program (uncertainty_planning_core_b200/csrc/upc_sim.cuh,
+ * one lane per particle, G = 1) on the CPU.  DEVELOPMENT / TEST AID ONLY: it lets the CPU test suite compare the
+ * very code the CUDA kernels execute against the independent oracle in a container without a GPU.  It is built
+ * into tests/emulation/libupc_emulation.so by tests/conftest.py and never loaded by the product package.
+ */
+#include <string.h>
+#include <math.h>
+#include <vector>
+#include "upc_sim.cuh"
+
+using namespace upc;
+
+static void fill_env(const upc_env_desc* e, DevEnv* d)
+{
+    d->nx = e->nx; d->ny = e->ny; d->nz = e->nz;
+    d->sdf_oob = e->sdf_oob_value; d->occ_oob = e->occupancy_oob_value;
+    d->res = e->resolution; d->inv_res = 1.0 / e->resolution;
+    for (int k = 0; k < 12; k++) d->G[k] = e->grid_from_world[k];
+    d->sdf = e->sdf; d->seg = e->convex_segment; d->occ = e->occupancy;
+}
+
+/* same conversion as upc_set_robot in upc_capi.cu (validation omitted) */
+static void fill_robot(const upc_robot_desc* r, DevRobot* d)
+{
+    memset(d, 0, sizeof(*d));
+    d->kind = r->kind; d->dof = r->dof; d->num_links = r->num_links;
+    d->num_joints = (r->kind == UPC_ROBOT_LINKED) ? r->num_joints : 0;
+    d->num_points = r->num_points;
+    for (int l = 0; l <= r->num_links; l++) d->link_off[l] = r->link_point_offset[l];
+    for (int l = 0; l < UPC_MAX_LINKS; l++) d->parent_joint_of_link[l] = -1;
+    for (int a = 0; a < r->dof; a++)
+    {
+        d->axis[a].kp = fabs(r->axis[a].kp); d->axis[a].ki = fabs(r->axis[a].ki); d->axis[a].kd = fabs(r->axis[a].kd);
+        d->axis[a].clamp = fabs(r->axis[a].integral_clamp); d->axis[a].vlim = fabs(r->axis[a].velocity_limit);
+        d->axis[a].nb = fabs(r->axis[a].max_actuator_noise); d->weights[a] = fabs(r->distance_weights[a]);
+    }
+    d->pts = r->points;
+    if (r->kind == UPC_ROBOT_LINKED)
+    {
+        for (int k = 0; k < 12; k++) d->base[k] = r->base_transform[k];
+        int active = 0;
+        for (int j = 0; j < r->num_joints; j++)
+        {
+            const upc_joint_desc& jd = r->joints[j];
+            DevJoint& dj = d->joints[j];
+            dj.type = jd.type; dj.parent = jd.parent_link; dj.child = jd.child_link; dj.active = -1;
+            for (int k = 0; k < 3; k++) dj.axis[k] = jd.axis[k];
+            for (int k = 0; k < 12; k++) dj.T[k] = jd.transform[k];
+            if (jd.type == UPC_JOINT_CONTINUOUS) { dj.lo = -INFINITY; dj.hi = INFINITY; }
+            else { dj.lo = jd.lower_limit; dj.hi = jd.upper_limit; }
+            if (jd.type != UPC_JOINT_FIXED) dj.active = active++;
+            d->parent_joint_of_link[jd.child_link] = j;
+        }
+    }
+}
+
+template <class M>
+static void run(const DevEnv& env, const DevRobot& rob, const DevSim& sp, int64_t n, const double* starts, int64_t n_targets,
+                const double* targets, const double* tape, double* out, uint8_t* coll, int64_t* counters)
+{
+    Group<1> g; g.mask = 1u; g.base = 0; g.sub = 0;
+    std::vector<double> f0((size_t)rob.num_links * 12), f1((size_t)rob.num_links * 12);
+    for (int64_t i = 0; i < n; i++)
+    {
+        LocalCounters lc = {0u, 0u, 0u};
+        bool c = false;
+        simulate_particle<M, 1>(env, rob, sp, g, i, n, starts, n_targets, targets, tape, out, coll, rob.pts, f0.data(), f1.data(), lc, c);
+        counters[0] += lc.particle_steps; counters[1] += c ? 1 : 0; counters[2] += lc.resolver_iterations; counters[3] += lc.failed_resolves;
+    }
+}
+
+extern "C" int emulate_forward_simulate(const upc_env_desc* e, const upc_robot_desc* r, const upc_sim_params* p, int64_t n,
+                                        const double* starts, int64_t n_targets, const double* targets, const double* tape,
+                                        double* out, uint8_t* coll, int64_t* counters)
+{
+    DevEnv env; DevRobot rob; DevSim sp;
+    fill_env(e, &env); fill_robot(r, &rob);
+    sp.num_steps = p->num_steps; sp.max_microsteps = p->max_microsteps; sp.allow_contacts = p->allow_contacts;
+    sp.individual_jacobians = p->use_individual_jacobians; sp.max_resolver_iterations = p->max_resolver_iterations;
+    sp.decay_iterations = p->resolver_decay_iterations; sp.dt = p->controller_interval; sp.shortcut = p->simulation_shortcut_distance;
+    sp.contact_distance = p->contact_distance; sp.resolve_distance = p->resolve_distance; sp.microstep_distance = p->microstep_distance;
+    sp.initial_scale = p->resolver_initial_scale; sp.decay_rate = p->resolver_decay_rate; sp.damping = p->resolver_damping;
+    for (int k = 0; k < 4; k++) counters[k] = 0;
+    if (r->kind == UPC_ROBOT_SE2) run<Se2Model>(env, rob, sp, n, starts, n_targets, targets, tape, out, coll, counters);
+    else if (r->kind == UPC_ROBOT_SE3) run<Se3Model>(env, rob, sp, n, starts, n_targets, targets, tape, out, coll, counters);
+    else run<LinkedModel>(env, rob, sp, n, starts, n_targets, targets, tape, out, coll, counters);
+    return 0;
+}

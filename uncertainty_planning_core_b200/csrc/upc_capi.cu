@@ -1,0 +1,546 @@
+/*
+ * upc_capi.cu - the C ABI declared in include/upc_b200.h: handle life cycle, uploads, the host- and
+ * device-pointer entry points, statistics and the host-side noise-tape generator.
+ */
+#include "upc_internal.h"
+
+#include <math.h>
+#include <string.h>
+#include <random>
+
+namespace upc
+{
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+cudaError_t DeviceBuffer::reserve(size_t want)
+{
+    if (want <= bytes && ptr) return cudaSuccess;
+    if (ptr)
+    {
+        cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+    }
+    if (want == 0) want = 256;
+    /* round up so that slowly growing requests do not reallocate every call */
+    size_t cap = 256;
+    while (cap < want) cap *= 2;
+    if (cap > want + (size_t(1) << 30)) cap = want;
+    cudaError_t e = cudaMalloc(&ptr, cap);
+    if (e != cudaSuccess)
+    {
+        ptr = nullptr;
+        return e;
+    }
+    bytes = cap;
+    return cudaSuccess;
+}
+
+void DeviceBuffer::release()
+{
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+}
+
+static bool finite_all(const double* v, int n)
+{
+    for (int i = 0; i < n; i++)
+        if (!isfinite(v[i])) return false;
+    return true;
+}
+
+static int32_t fail_arg(const std::string& msg)
+{
+    set_error(msg);
+    return UPC_ERR_INVALID_ARGUMENT;
+}
+
+static int32_t to_dev_sim(const upc_sim_params* p, DevSim* out)
+{
+    if (!p) return fail_arg("null sim params");
+    if (p->num_steps < 1) return fail_arg("num_steps must be >= 1");
+    if (p->max_microsteps < 1) return fail_arg("max_microsteps must be >= 1");
+    if (!(p->controller_interval > 0.0)) return fail_arg("controller_interval must be > 0");
+    if (!(p->microstep_distance > 0.0)) return fail_arg("microstep_distance must be > 0");
+    if (p->max_resolver_iterations < 1 || p->resolver_decay_iterations < 1) return fail_arg("resolver iteration counts must be >= 1");
+    if (!(p->resolve_distance >= p->contact_distance)) return fail_arg("resolve_distance must be >= contact_distance");
+    if (!(p->resolver_damping > 0.0)) return fail_arg("resolver_damping must be > 0");
+    out->num_steps = p->num_steps;
+    out->max_microsteps = p->max_microsteps;
+    out->allow_contacts = p->allow_contacts;
+    out->individual_jacobians = p->use_individual_jacobians;
+    out->max_resolver_iterations = p->max_resolver_iterations;
+    out->decay_iterations = p->resolver_decay_iterations;
+    out->dt = p->controller_interval;
+    out->shortcut = p->simulation_shortcut_distance;
+    out->contact_distance = p->contact_distance;
+    out->resolve_distance = p->resolve_distance;
+    out->microstep_distance = p->microstep_distance;
+    out->initial_scale = p->resolver_initial_scale;
+    out->decay_rate = p->resolver_decay_rate;
+    out->damping = p->resolver_damping;
+    return UPC_OK;
+}
+
+/* fold the device-side counters into the host-side totals */
+static int32_t pull_counters(upc_handle* h)
+{
+    DevCounters c;
+    UPC_CUDA_TRY(cudaMemcpyAsync(&c, h->d_counters, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+    UPC_CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(c), h->stream));
+    UPC_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->stats.particle_steps += (int64_t)c.particle_steps;
+    h->stats.collided_particles += (int64_t)c.collided;
+    h->stats.resolver_iterations += (int64_t)c.resolver_iterations;
+    h->stats.failed_resolves += (int64_t)c.failed_resolves;
+    return UPC_OK;
+}
+} /* namespace upc */
+
+using namespace upc;
+
+extern "C" {
+
+int32_t upc_config_width(int32_t kind, int32_t dof)
+{
+    if (kind == UPC_ROBOT_SE2) return 3;
+    if (kind == UPC_ROBOT_SE3) return 12;
+    return dof;
+}
+
+int64_t upc_tape_doubles_per_particle(const upc_sim_params* p, int32_t dof)
+{
+    return (int64_t)p->num_steps * (int64_t)(1 + p->max_microsteps) * (int64_t)dof;
+}
+
+const char* upc_last_error(void) { return g_last_error.c_str(); }
+const char* upc_version(void) { return "upc_b200 0.1 (sm_100a)"; }
+
+int32_t upc_create(const upc_env_desc* env, int32_t device, upc_handle** out)
+{
+    if (!env || !out) return fail_arg("null argument");
+    if (env->nx < 1 || env->ny < 1 || env->nz < 1) return fail_arg("grid dimensions must be >= 1");
+    if (!(env->resolution > 0.0) || !isfinite(env->resolution)) return fail_arg("resolution must be > 0");
+    if (!env->sdf) return fail_arg("sdf grid is required");
+    if (!finite_all(env->grid_from_world, 12)) return fail_arg("grid_from_world must be finite");
+    int count = 0;
+    UPC_CUDA_TRY(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail_arg("no such CUDA device");
+    UPC_CUDA_TRY(cudaSetDevice(device));
+    upc_handle* h = new upc_handle();
+    h->device = device;
+    cudaDeviceProp prop;
+    UPC_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    UPC_CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    const size_t cells = (size_t)env->nx * (size_t)env->ny * (size_t)env->nz;
+    UPC_CUDA_TRY(cudaMalloc(&h->d_sdf, cells * sizeof(float)));
+    UPC_CUDA_TRY(cudaMemcpyAsync(h->d_sdf, env->sdf, cells * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    h->stats.h2d_bytes += (int64_t)(cells * sizeof(float));
+    if (env->convex_segment)
+    {
+        UPC_CUDA_TRY(cudaMalloc(&h->d_seg, cells * sizeof(uint32_t)));
+        UPC_CUDA_TRY(cudaMemcpyAsync(h->d_seg, env->convex_segment, cells * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+        h->stats.h2d_bytes += (int64_t)(cells * sizeof(uint32_t));
+    }
+    if (env->occupancy)
+    {
+        UPC_CUDA_TRY(cudaMalloc(&h->d_occ, cells * sizeof(float)));
+        UPC_CUDA_TRY(cudaMemcpyAsync(h->d_occ, env->occupancy, cells * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        h->stats.h2d_bytes += (int64_t)(cells * sizeof(float));
+    }
+    UPC_CUDA_TRY(cudaMalloc(&h->d_counters, sizeof(DevCounters)));
+    UPC_CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(DevCounters), h->stream));
+    UPC_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    DevEnv& e = h->env;
+    e.nx = env->nx; e.ny = env->ny; e.nz = env->nz;
+    e.sdf_oob = env->sdf_oob_value;
+    e.occ_oob = env->occupancy_oob_value;
+    e.res = env->resolution;
+    e.inv_res = 1.0 / env->resolution;
+    for (int k = 0; k < 12; k++) e.G[k] = env->grid_from_world[k];
+    e.sdf = h->d_sdf;
+    e.seg = h->d_seg;
+    e.occ = h->d_occ;
+    *out = h;
+    return UPC_OK;
+}
+
+int32_t upc_destroy(upc_handle* h)
+{
+    if (!h) return UPC_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_sdf);
+    cudaFree(h->d_seg);
+    cudaFree(h->d_occ);
+    cudaFree(h->d_points);
+    cudaFree(h->d_counters);
+    DeviceBuffer* bufs[] = {&h->st_starts, &h->st_targets, &h->st_tape, &h->st_out, &h->st_coll, &h->st_labels, &h->st_ncl,
+                            &h->cw.features, &h->cw.adjacency, &h->cw.roots, &h->cw.comp, &h->cw.flags, &h->cw.signatures,
+                            &h->cw.frames, &h->cw.dist_matrix, &h->cw.members, &h->cw.link_scratch, &h->cw.misc};
+    for (DeviceBuffer* b : bufs) b->release();
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return UPC_OK;
+}
+
+int32_t upc_set_robot(upc_handle* h, const upc_robot_desc* r)
+{
+    if (!h || !r) return fail_arg("null argument");
+    if (r->kind != UPC_ROBOT_SE2 && r->kind != UPC_ROBOT_SE3 && r->kind != UPC_ROBOT_LINKED) return fail_arg("unknown robot kind");
+    if (r->kind == UPC_ROBOT_SE2 && r->dof != 3) return fail_arg("SE2 robots have 3 degrees of freedom");
+    if (r->kind == UPC_ROBOT_SE3 && r->dof != 6) return fail_arg("SE3 robots have 6 degrees of freedom");
+    if (r->dof < 1 || r->dof > UPC_MAX_DOF) return fail_arg("dof out of range");
+    if (r->num_links < 1 || r->num_links > UPC_MAX_LINKS) return fail_arg("num_links out of range");
+    if (r->kind != UPC_ROBOT_LINKED && r->num_links != 1) return fail_arg("SE2/SE3 robots have exactly one link");
+    if (r->num_points < 1 || !r->points) return fail_arg("robot needs body points");
+    if (r->link_point_offset[0] != 0 || r->link_point_offset[r->num_links] != r->num_points) return fail_arg("link_point_offset must span all points");
+    for (int l = 0; l < r->num_links; l++)
+        if (r->link_point_offset[l + 1] < r->link_point_offset[l]) return fail_arg("link_point_offset must be non-decreasing");
+    DevRobot d;
+    memset(&d, 0, sizeof(d));
+    d.kind = r->kind;
+    d.dof = r->dof;
+    d.num_links = r->num_links;
+    d.num_joints = (r->kind == UPC_ROBOT_LINKED) ? r->num_joints : 0;
+    d.num_points = r->num_points;
+    for (int l = 0; l <= r->num_links; l++) d.link_off[l] = r->link_point_offset[l];
+    for (int l = 0; l < UPC_MAX_LINKS; l++) d.parent_joint_of_link[l] = -1;
+    for (int a = 0; a < r->dof; a++)
+    {
+        d.axis[a].kp = fabs(r->axis[a].kp);
+        d.axis[a].ki = fabs(r->axis[a].ki);
+        d.axis[a].kd = fabs(r->axis[a].kd);
+        d.axis[a].clamp = fabs(r->axis[a].integral_clamp);
+        d.axis[a].vlim = fabs(r->axis[a].velocity_limit);
+        d.axis[a].nb = fabs(r->axis[a].max_actuator_noise);
+        d.weights[a] = fabs(r->distance_weights[a]);
+    }
+    if (r->kind == UPC_ROBOT_LINKED)
+    {
+        if (r->num_joints < 1 || r->num_joints > UPC_MAX_JOINTS) return fail_arg("num_joints out of range");
+        for (int k = 0; k < 12; k++) d.base[k] = r->base_transform[k];
+        int active = 0;
+        std::vector<bool> placed((size_t)r->num_links, false);
+        placed[0] = true;
+        for (int j = 0; j < r->num_joints; j++)
+        {
+            const upc_joint_desc& jd = r->joints[j];
+            if (jd.parent_link < 0 || jd.parent_link >= r->num_links || jd.child_link < 1 || jd.child_link >= r->num_links)
+                return fail_arg("joint refers to a link that does not exist");
+            /* UpdateTransforms (simple_robot_models.hpp:1299-1343) relies on parents being placed first */
+            if (!placed[(size_t)jd.parent_link]) return fail_arg("joints must be ordered parents before children");
+            if (placed[(size_t)jd.child_link]) return fail_arg("link has more than one parent joint");
+            placed[(size_t)jd.child_link] = true;
+            DevJoint& dj = d.joints[j];
+            dj.type = jd.type;
+            dj.parent = jd.parent_link;
+            dj.child = jd.child_link;
+            dj.active = -1;
+            for (int k = 0; k < 3; k++) dj.axis[k] = jd.axis[k];
+            for (int k = 0; k < 12; k++) dj.T[k] = jd.transform[k];
+            if (jd.type == UPC_JOINT_CONTINUOUS)
+            {
+                dj.lo = -INFINITY; dj.hi = INFINITY;
+            }
+            else if (jd.type == UPC_JOINT_REVOLUTE || jd.type == UPC_JOINT_PRISMATIC)
+            {
+                if (!(jd.lower_limit <= jd.upper_limit)) return fail_arg("joint limits must satisfy lower <= upper");
+                dj.lo = jd.lower_limit; dj.hi = jd.upper_limit;
+            }
+            else if (jd.type != UPC_JOINT_FIXED)
+            {
+                return fail_arg("unknown joint type");
+            }
+            if (jd.type != UPC_JOINT_FIXED) dj.active = active++;
+            d.parent_joint_of_link[jd.child_link] = j;
+        }
+        if (active != r->dof) return fail_arg("dof must equal the number of non-fixed joints");
+        for (int l = 1; l < r->num_links; l++)
+            if (!placed[(size_t)l]) return fail_arg("every link except the root needs a parent joint");
+    }
+    UPC_CUDA_TRY(cudaSetDevice(h->device));
+    if (h->d_points) cudaFree(h->d_points);
+    h->d_points = nullptr;
+    UPC_CUDA_TRY(cudaMalloc(&h->d_points, (size_t)r->num_points * 4 * sizeof(double)));
+    UPC_CUDA_TRY(cudaMemcpyAsync(h->d_points, r->points, (size_t)r->num_points * 4 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    UPC_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    d.pts = h->d_points;
+    h->robot = d;
+    h->has_robot = true;
+    return UPC_OK;
+}
+
+int32_t upc_get_stats(upc_handle* h, upc_stats* out)
+{
+    if (!h || !out) return fail_arg("null argument");
+    UPC_CUDA_TRY(cudaSetDevice(h->device));
+    const int32_t rc = pull_counters(h);
+    if (rc != UPC_OK) return rc;
+    *out = h->stats;
+    return UPC_OK;
+}
+
+int32_t upc_reset_stats(upc_handle* h)
+{
+    if (!h) return fail_arg("null argument");
+    UPC_CUDA_TRY(cudaSetDevice(h->device));
+    const int32_t rc = pull_counters(h);
+    if (rc != UPC_OK) return rc;
+    memset(&h->stats, 0, sizeof(h->stats));
+    return UPC_OK;
+}
+
+int32_t upc_set_lanes_per_particle(upc_handle* h, int32_t lanes)
+{
+    if (!h) return fail_arg("null argument");
+    if (lanes != 0 && lanes != 1 && lanes != 2 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32)
+        return fail_arg("lanes must be 0, 1, 2, 4, 8, 16 or 32");
+    h->lanes_override = lanes;
+    return UPC_OK;
+}
+
+int32_t upc_host_alloc(void** ptr, int64_t bytes)
+{
+    if (!ptr || bytes < 0) return fail_arg("bad argument");
+    UPC_CUDA_TRY(cudaMallocHost(ptr, (size_t)(bytes > 0 ? bytes : 1)));
+    return UPC_OK;
+}
+
+int32_t upc_host_free(void* ptr)
+{
+    if (ptr) UPC_CUDA_TRY(cudaFreeHost(ptr));
+    return UPC_OK;
+}
+
+int32_t upc_synchronize(upc_handle* h)
+{
+    if (!h) return fail_arg("null argument");
+    UPC_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return UPC_OK;
+}
+
+int32_t upc_forward_simulate_device(upc_handle* h, const upc_sim_params* params, int64_t n, const double* d_starts,
+                                    int64_t n_targets, const double* d_targets, const double* d_tape,
+                                    double* d_out_configs, uint8_t* d_out_collided, void* stream)
+{
+    if (!h) return fail_arg("null handle");
+    if (!h->has_robot)
+    {
+        set_error("upc_set_robot has not been called");
+        return UPC_ERR_NO_ROBOT;
+    }
+    DevSim sp;
+    const int32_t rc = to_dev_sim(params, &sp);
+    if (rc != UPC_OK) return rc;
+    if (n < 0) return fail_arg("n must be >= 0");
+    if (n == 0) return UPC_OK;
+    if (!(n_targets == 1 || n_targets == n)) return fail_arg("target_positions must have size 1 or size start_positions.size()");
+    if (!d_starts || !d_targets || !d_tape || !d_out_configs || !d_out_collided) return fail_arg("null buffer");
+    UPC_CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+    UPC_CUDA_TRY(launch_forward_simulate(h, sp, n, d_starts, n_targets, d_targets, d_tape, d_out_configs, d_out_collided, s));
+    h->stats.kernel_launches++;
+    h->stats.particles_simulated += n;
+    return UPC_OK;
+}
+
+int32_t upc_forward_simulate(upc_handle* h, const upc_sim_params* params, int64_t n, const double* starts,
+                             int64_t n_targets, const double* targets, const double* tape, double* out_configs,
+                             uint8_t* out_collided)
+{
+    if (!h) return fail_arg("null handle");
+    if (!h->has_robot)
+    {
+        set_error("upc_set_robot has not been called");
+        return UPC_ERR_NO_ROBOT;
+    }
+    if (n < 0) return fail_arg("n must be >= 0");
+    if (n == 0) return UPC_OK;
+    if (!params) return fail_arg("null sim params");
+    if (!(n_targets == 1 || n_targets == n)) return fail_arg("target_positions must have size 1 or size start_positions.size()");
+    if (!starts || !targets || !tape || !out_configs || !out_collided) return fail_arg("null buffer");
+    UPC_CUDA_TRY(cudaSetDevice(h->device));
+    const int width = upc_config_width(h->robot.kind, h->robot.dof);
+    const size_t cfg_bytes = (size_t)width * (size_t)n * sizeof(double);
+    const size_t tgt_bytes = (size_t)width * (size_t)n_targets * sizeof(double);
+    if (params->num_steps < 1 || params->max_microsteps < 1) return fail_arg("bad step counts");
+    const size_t tape_bytes = (size_t)upc_tape_doubles_per_particle(params, h->robot.dof) * (size_t)n * sizeof(double);
+    UPC_CUDA_TRY(h->st_starts.reserve(cfg_bytes));
+    UPC_CUDA_TRY(h->st_targets.reserve(tgt_bytes));
+    UPC_CUDA_TRY(h->st_tape.reserve(tape_bytes));
+    UPC_CUDA_TRY(h->st_out.reserve(cfg_bytes));
+    UPC_CUDA_TRY(h->st_coll.reserve((size_t)n));
+    UPC_CUDA_TRY(cudaMemcpyAsync(h->st_starts.ptr, starts, cfg_bytes, cudaMemcpyHostToDevice, h->stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(h->st_targets.ptr, targets, tgt_bytes, cudaMemcpyHostToDevice, h->stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(h->st_tape.ptr, tape, tape_bytes, cudaMemcpyHostToDevice, h->stream));
+    h->stats.h2d_bytes += (int64_t)(cfg_bytes + tgt_bytes + tape_bytes);
+    const int32_t rc = upc_forward_simulate_device(h, params, n, (const double*)h->st_starts.ptr, n_targets, (const double*)h->st_targets.ptr,
+                                                   (const double*)h->st_tape.ptr, (double*)h->st_out.ptr, (uint8_t*)h->st_coll.ptr, h->stream);
+    if (rc != UPC_OK) return rc;
+    UPC_CUDA_TRY(cudaMemcpyAsync(out_configs, h->st_out.ptr, cfg_bytes, cudaMemcpyDeviceToHost, h->stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(out_collided, h->st_coll.ptr, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    h->stats.d2h_bytes += (int64_t)(cfg_bytes + (size_t)n);
+    UPC_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return UPC_OK;
+}
+
+int32_t upc_check_config_collision(upc_handle* h, const double* config, double contact_distance, double inflation,
+                                   int32_t* out_in_collision)
+{
+    if (!h || !config || !out_in_collision) return fail_arg("null argument");
+    if (!h->has_robot)
+    {
+        set_error("upc_set_robot has not been called");
+        return UPC_ERR_NO_ROBOT;
+    }
+    UPC_CUDA_TRY(cudaSetDevice(h->device));
+    const int width = upc_config_width(h->robot.kind, h->robot.dof);
+    UPC_CUDA_TRY(h->st_starts.reserve((size_t)width * sizeof(double) + 64));
+    UPC_CUDA_TRY(h->st_ncl.reserve(64));
+    UPC_CUDA_TRY(cudaMemcpyAsync(h->st_starts.ptr, config, (size_t)width * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    UPC_CUDA_TRY(launch_check_collision(h, (const double*)h->st_starts.ptr, contact_distance + inflation, (int*)h->st_ncl.ptr, h->stream));
+    h->stats.kernel_launches++;
+    int result = 0;
+    UPC_CUDA_TRY(cudaMemcpyAsync(&result, h->st_ncl.ptr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    UPC_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    *out_in_collision = result;
+    return UPC_OK;
+}
+
+int32_t upc_cluster_particles_device(upc_handle* h, const upc_cluster_params* params, int64_t n_sets, int64_t set_size,
+                                     const double* d_configs, int32_t* d_labels, int32_t* d_n_clusters, void* stream)
+{
+    if (!h || !params) return fail_arg("null argument");
+    if (!h->has_robot)
+    {
+        set_error("upc_set_robot has not been called");
+        return UPC_ERR_NO_ROBOT;
+    }
+    if (n_sets < 0 || set_size < 0) return fail_arg("negative size");
+    if (n_sets > 65535) return fail_arg("at most 65535 particle sets per call");
+    if (set_size > (int64_t)1 << 20) return fail_arg("at most 2^20 particles per set");
+    if (n_sets == 0) return UPC_OK;
+    if (!d_n_clusters) return fail_arg("null buffer");
+    UPC_CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+    if (set_size == 0)
+    {
+        UPC_CUDA_TRY(cudaMemsetAsync(d_n_clusters, 0, (size_t)n_sets * sizeof(int32_t), s));
+        return UPC_OK;
+    }
+    if (!d_configs || !d_labels) return fail_arg("null buffer");
+    if (!isfinite(params->distance_clustering_threshold)) return fail_arg("distance_clustering_threshold must be finite");
+    return run_cluster(h, *params, n_sets, set_size, d_configs, d_labels, d_n_clusters, s);
+}
+
+int32_t upc_cluster_particles(upc_handle* h, const upc_cluster_params* params, int64_t n_sets, int64_t set_size,
+                              const double* configs, int32_t* labels, int32_t* n_clusters)
+{
+    if (!h || !params) return fail_arg("null argument");
+    if (!h->has_robot)
+    {
+        set_error("upc_set_robot has not been called");
+        return UPC_ERR_NO_ROBOT;
+    }
+    if (n_sets < 0 || set_size < 0) return fail_arg("negative size");
+    if (n_sets == 0) return UPC_OK;
+    if (!n_clusters) return fail_arg("null buffer");
+    if (set_size == 0)
+    {
+        for (int64_t s = 0; s < n_sets; s++) n_clusters[s] = 0;
+        return UPC_OK;
+    }
+    if (!configs || !labels) return fail_arg("null buffer");
+    UPC_CUDA_TRY(cudaSetDevice(h->device));
+    const int64_t total = n_sets * set_size;
+    const int width = upc_config_width(h->robot.kind, h->robot.dof);
+    const size_t cfg_bytes = (size_t)width * (size_t)total * sizeof(double);
+    UPC_CUDA_TRY(h->st_starts.reserve(cfg_bytes));
+    UPC_CUDA_TRY(h->st_labels.reserve((size_t)total * sizeof(int32_t)));
+    UPC_CUDA_TRY(h->st_ncl.reserve((size_t)n_sets * sizeof(int32_t) + 64));
+    UPC_CUDA_TRY(cudaMemcpyAsync(h->st_starts.ptr, configs, cfg_bytes, cudaMemcpyHostToDevice, h->stream));
+    h->stats.h2d_bytes += (int64_t)cfg_bytes;
+    const int32_t rc = upc_cluster_particles_device(h, params, n_sets, set_size, (const double*)h->st_starts.ptr, (int32_t*)h->st_labels.ptr,
+                                                    (int32_t*)h->st_ncl.ptr, h->stream);
+    if (rc != UPC_OK) return rc;
+    UPC_CUDA_TRY(cudaMemcpyAsync(labels, h->st_labels.ptr, (size_t)total * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(n_clusters, h->st_ncl.ptr, (size_t)n_sets * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    h->stats.d2h_bytes += (int64_t)((size_t)total * sizeof(int32_t) + (size_t)n_sets * sizeof(int32_t));
+    UPC_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return UPC_OK;
+}
+
+/*
+ * Noise tape: replaces the per-thread PRNG fan-out of
+ * uncertainty_contact_planning.hpp:343-356 + the truncated-normal draws of simple_uncertainty_models.hpp:38-45, 77-88.
+ * Particle i draws from its own std::mt19937_64 seeded with SplitMix64(seed + i), so the tape - and therefore
+ * every result - is independent of thread counts and of how particles are sharded across GPUs.
+ * Standard normals come from the Marsaglia polar method on 53-bit uniforms, rejected outside [-2, 2]
+ * (the reference's distributions are all mean 0, bounds +-2 sigma): sensor draws are z * max_sensor_noise / 2,
+ * actuator draws z / 2.  A zero noise bound yields exact zeros without consuming random numbers.
+ */
+static inline uint64_t splitmix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+static inline double truncated_standard_normal(std::mt19937_64& rng)
+{
+    while (true)
+    {
+        const double u = ((double)(rng() >> 11) * (1.0 / 9007199254740992.0)) * 2.0 - 1.0;
+        const double v = ((double)(rng() >> 11) * (1.0 / 9007199254740992.0)) * 2.0 - 1.0;
+        const double s = u * u + v * v;
+        if (s >= 1.0 || s == 0.0) continue;
+        const double z = u * sqrt(-2.0 * log(s) / s);
+        if (z >= -2.0 && z <= 2.0) return z;
+    }
+}
+
+int32_t upc_fill_noise_tape(uint64_t seed, const upc_robot_desc* robot, const upc_sim_params* params, int64_t first_particle,
+                            int64_t n, int64_t tape_stride, double* tape)
+{
+    if (!robot || !params || !tape) return fail_arg("null argument");
+    if (robot->dof < 1 || robot->dof > UPC_MAX_DOF) return fail_arg("dof out of range");
+    if (params->num_steps < 1 || params->max_microsteps < 1) return fail_arg("bad step counts");
+    if (tape_stride < n) return fail_arg("tape_stride must be >= n");
+    const int dof = robot->dof;
+    const int slots = 1 + params->max_microsteps;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++)
+    {
+        std::mt19937_64 rng(splitmix64(seed + (uint64_t)(first_particle + i)));
+        for (int step = 0; step < params->num_steps; step++)
+        {
+            for (int slot = 0; slot < slots; slot++)
+            {
+                for (int d = 0; d < dof; d++)
+                {
+                    double value;
+                    if (slot == 0)
+                    {
+                        const double bound = fabs(robot->axis[d].max_sensor_noise);
+                        value = (bound > 0.0) ? truncated_standard_normal(rng) * (bound * 0.5) : 0.0;
+                    }
+                    else
+                    {
+                        const double bound = fabs(robot->axis[d].max_actuator_noise);
+                        value = (bound > 0.0) ? truncated_standard_normal(rng) * 0.5 : 0.0;
+                    }
+                    tape[(((int64_t)step * slots + slot) * dof + d) * tape_stride + i] = value;
+                }
+            }
+        }
+    }
+    return UPC_OK;
+}
+
+} /* extern "C" */

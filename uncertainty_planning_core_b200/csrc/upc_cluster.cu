@@ -1,0 +1,855 @@
+/*
+ * upc_cluster.cu - outcome clustering on the GPU.
+ *
+ * Replaces the index-clustering half of UncertaintyPlanningSpace::ClusterParticles
+ * (uncertainty_contact_planning.hpp:1986-2034): PerformSpatialFeatureClustering (:1915) followed by
+ * RunDistanceClusteringOnInitialClusters (:1947), whose heavy callees are arc_helpers::BuildDistanceMatrix
+ * (:1674, :1960) and SimpleHierarchicalClustering::Cluster (:1684, :1974).
+ *
+ * The reference materialises an N x N FP64 matrix per pass.  Here each pass is fused into a 1-bit
+ * threshold-adjacency matrix (N^2/8 bytes) built by a tiled pair kernel; the partition is then read off it:
+ *   - if every row equals the row of its smallest neighbour, the threshold graph is a disjoint union of
+ *     cliques and complete-link clustering cut at the threshold returns exactly those cliques
+ *      - this also covers the reference's own "max <= threshold" shortcut;
+ *   - otherwise the affected connected components are clustered exactly (Lance-Williams complete link with
+ *     the deterministic tie-break of DESIGN.md 5.2) from their FP64 distance sub-matrices, on the GPU.
+ * Labels are canonical: clusters numbered by increasing smallest member.
+ */
+#include "upc_internal.h"
+#include "upc_sim.cuh"
+
+#include <algorithm>
+#include <map>
+
+namespace upc
+{
+constexpr int kTileRows = 64;
+constexpr int kTileCols = 256;
+
+/* ------------------------------------------------------------------ pair distances on per-particle features */
+
+/* features: SE2 (x, y, theta); SE3 (tx, ty, tz, qx, qy, qz, qw); linked (joint values) */
+template <int KIND>
+struct PairDistance;
+
+template <>
+struct PairDistance<UPC_ROBOT_SE2>
+{
+    static constexpr int MAXF = 3;
+    __device__ __forceinline__ static double eval(const DevRobot& r, const double* a, const double* b)
+    {
+        return Se2Model::distance(r, a, b);
+    }
+};
+
+template <>
+struct PairDistance<UPC_ROBOT_SE3>
+{
+    static constexpr int MAXF = 7;
+    __device__ __forceinline__ static double eval(const DevRobot&, const double* a, const double* b)
+    {
+        /* simple_robot_models.hpp:871-874 with the quaternions extracted once per particle */
+        const double dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+        const double tdist = sqrt(((dx * dx) + (dy * dy)) + (dz * dz));
+        const double dq = fabs((((a[3] * b[3]) + (a[4] * b[4])) + (a[5] * b[5])) + (a[6] * b[6]));
+        double rdist = 0.0;
+        if (dq < (1.0 - 2.220446049250313e-16))
+        {
+            rdist = upc_acos(((2.0 * dq) * dq) - 1.0);
+        }
+        return (((1.0 - 0.5) * tdist) + (0.5 * rdist)) * 2.0;
+    }
+};
+
+template <>
+struct PairDistance<UPC_ROBOT_LINKED>
+{
+    static constexpr int MAXF = UPC_MAX_DOF;
+    __device__ __forceinline__ static double eval(const DevRobot& r, const double* a, const double* b)
+    {
+        return LinkedModel::distance(r, a, b);
+    }
+};
+
+__global__ void se3_features_kernel(const double* __restrict__ cfg, double* __restrict__ feat, int64_t total)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    double T[12];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+    {
+#pragma unroll
+        for (int k = 0; k < 3; k++) T[r * 4 + k] = cfg[(int64_t)(r * 3 + k) * total + i];
+        T[r * 4 + 3] = cfg[(int64_t)(9 + r) * total + i];
+    }
+    double q[4];
+    quat_from_xf(T, q);
+    feat[0 * total + i] = T[3];
+    feat[1 * total + i] = T[7];
+    feat[2 * total + i] = T[11];
+    feat[3 * total + i] = q[0];
+    feat[4 * total + i] = q[1];
+    feat[5 * total + i] = q[2];
+    feat[6 * total + i] = q[3];
+}
+
+struct AdjArgs
+{
+    DevRobot robot;
+    const double* feat; /* [F][total] */
+    int nfeat;
+    int64_t total, set_size;
+    int wpr; /* 32-bit words per adjacency row */
+    const int32_t* group; /* optional first-pass cluster id per particle (pairs in different groups are never adjacent) */
+    uint32_t* adj;        /* [total][wpr] */
+    double threshold;
+};
+
+/*
+ * Threshold adjacency, one CTA per 64-row x 256-column tile of one particle set.
+ * Thread = column; the 64 row feature vectors sit in shared memory; one warp ballot per row yields a packed
+ * 32-column word; the 64x8 words of the tile are staged in shared memory and written as full 32-byte sectors.
+ */
+template <int KIND>
+__global__ void __launch_bounds__(kTileCols) adjacency_kernel(const __grid_constant__ AdjArgs a)
+{
+    constexpr int MAXF = PairDistance<KIND>::MAXF;
+    __shared__ double s_row[MAXF][kTileRows];
+    __shared__ int32_t s_grp[kTileRows];
+    __shared__ uint32_t s_words[kTileRows][kTileCols / 32];
+    const int64_t set_base = (int64_t)blockIdx.z * a.set_size;
+    const int64_t row0 = (int64_t)blockIdx.y * kTileRows;
+    const int64_t col = (int64_t)blockIdx.x * kTileCols + threadIdx.x;
+    const int F = a.nfeat;
+    for (int k = threadIdx.x; k < F * kTileRows; k += kTileCols)
+    {
+        const int f = k / kTileRows, r = k % kTileRows;
+        const int64_t i = row0 + r;
+        s_row[f][r] = (i < a.set_size) ? a.feat[(int64_t)f * a.total + set_base + i] : 0.0;
+    }
+    if (threadIdx.x < kTileRows)
+    {
+        const int64_t i = row0 + threadIdx.x;
+        s_grp[threadIdx.x] = (a.group && i < a.set_size) ? a.group[set_base + i] : 0;
+    }
+    double cf[MAXF];
+    const bool col_ok = col < a.set_size;
+#pragma unroll
+    for (int f = 0; f < MAXF; f++) cf[f] = (col_ok && f < F) ? a.feat[(int64_t)f * a.total + set_base + col] : 0.0;
+    const int32_t cgrp = (a.group && col_ok) ? a.group[set_base + col] : 0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = 0; r < kTileRows; r++)
+    {
+        bool adjacent = false;
+        if (col_ok && (row0 + r) < a.set_size && s_grp[r] == cgrp)
+        {
+            double rf[MAXF];
+#pragma unroll
+            for (int f = 0; f < MAXF; f++) rf[f] = s_row[f][r];
+            adjacent = PairDistance<KIND>::eval(a.robot, rf, cf) <= a.threshold;
+        }
+        const unsigned word = __ballot_sync(0xffffffffu, adjacent);
+        if (lane == 0) s_words[r][warp] = word;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < kTileRows * (kTileCols / 32); k += kTileCols)
+    {
+        const int r = k / (kTileCols / 32), w = k % (kTileCols / 32);
+        const int64_t i = row0 + r;
+        const int64_t word_index = (int64_t)blockIdx.x * (kTileCols / 32) + w;
+        if (i < a.set_size && word_index < a.wpr) a.adj[(set_base + i) * a.wpr + word_index] = s_words[r][w];
+    }
+}
+
+/* ------------------------------------------------------------------ convex-region signatures (CRS first pass) */
+
+struct SigArgs
+{
+    DevEnv env;
+    DevRobot robot;
+    const double* cfg;
+    int64_t total;
+    uint32_t* sig; /* [P][total] */
+    double* frames; /* linked only: total * num_links * 12 scratch */
+};
+
+/* uncertainty_contact_planning.hpp:1597-1635: one thread per particle, signatures stored point-major */
+template <class M>
+__global__ void __launch_bounds__(128) signature_kernel(const __grid_constant__ SigArgs a)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.total) return;
+    M m;
+    if constexpr (M::HAS_FRAMES)
+    {
+        m.frames = a.frames + i * (int64_t)a.robot.num_links * 12;
+    }
+    m.load(a.robot, a.cfg, a.total, i);
+    if constexpr (M::HAS_FRAMES) m.fk(a.robot, m.frames);
+    for (int l = 0; l < a.robot.num_links; l++)
+    {
+        const int beg = a.robot.link_off[l], end = a.robot.link_off[l + 1];
+        if (beg == end) continue;
+        double T[12], V[12];
+        m.frame(a.robot, l, T);
+        voxel_from_link(a.env, T, V);
+        for (int k = beg; k < end; k++)
+        {
+            double u[3];
+            xf_point(V, a.robot.pts[4 * k + 0], a.robot.pts[4 * k + 1], a.robot.pts[4 * k + 2], u);
+            uint32_t s = 0u;
+            if (voxel_in_bounds(a.env, u))
+            {
+                s = ldg(a.env.seg + cell_index(a.env, (int)floor(u[0]), (int)floor(u[1]), (int)floor(u[2])));
+            }
+            a.sig[(int64_t)k * a.total + i] = s;
+        }
+    }
+}
+
+struct SigAdjArgs
+{
+    const uint32_t* sig; /* [P][total] */
+    int num_points;
+    int64_t total, set_size;
+    int wpr;
+    uint32_t* adj;
+    int max_mismatch; /* largest count m with (double)m / (double)P <= signature_matching_threshold */
+};
+
+/*
+ * Signature-mismatch adjacency (uncertainty_contact_planning.hpp:1637-1661 + the threshold at :1677-1685):
+ * a 64x64 tile of pairs per CTA, 4x4 pairs per thread, 32 body points per shared-memory stage.
+ */
+__global__ void __launch_bounds__(256) signature_adjacency_kernel(const __grid_constant__ SigAdjArgs a)
+{
+    __shared__ uint32_t s_a[32][64];
+    __shared__ uint32_t s_b[32][64];
+    __shared__ uint32_t s_bits[64][2];
+    const int64_t set_base = (int64_t)blockIdx.z * a.set_size;
+    const int64_t row0 = (int64_t)blockIdx.y * 64;
+    const int64_t col0 = (int64_t)blockIdx.x * 64;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    int acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[r][c] = 0;
+    if (threadIdx.x < 128) s_bits[threadIdx.x >> 1][threadIdx.x & 1] = 0u;
+    for (int k0 = 0; k0 < a.num_points; k0 += 32)
+    {
+        __syncthreads();
+        for (int e = threadIdx.x; e < 32 * 64; e += 256)
+        {
+            const int kk = e >> 6, r = e & 63;
+            const int k = k0 + kk;
+            const int64_t ri = row0 + r, ci = col0 + r;
+            s_a[kk][r] = (k < a.num_points && ri < a.set_size) ? a.sig[(int64_t)k * a.total + set_base + ri] : 0u;
+            s_b[kk][r] = (k < a.num_points && ci < a.set_size) ? a.sig[(int64_t)k * a.total + set_base + ci] : 0u;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int kk = 0; kk < 32; kk++)
+        {
+            uint32_t av[4], bv[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) av[r] = s_a[kk][ty + 16 * r];
+#pragma unroll
+            for (int c = 0; c < 4; c++) bv[c] = s_b[kk][tx + 16 * c];
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                {
+                    acc[r][c] += ((av[r] != 0u) && (bv[c] != 0u) && ((av[r] & bv[c]) == 0u)) ? 1 : 0;
+                }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+        {
+            const int rr = ty + 16 * r, cc = tx + 16 * c;
+            if ((row0 + rr) < a.set_size && (col0 + cc) < a.set_size && acc[r][c] <= a.max_mismatch)
+            {
+                atomicOr(&s_bits[rr][cc >> 5], 1u << (cc & 31));
+            }
+        }
+    __syncthreads();
+    if (threadIdx.x < 128)
+    {
+        const int rr = threadIdx.x >> 1, w = threadIdx.x & 1;
+        const int64_t word_index = (int64_t)blockIdx.x * 2 + w;
+        if ((row0 + rr) < a.set_size && word_index < a.wpr) a.adj[(set_base + row0 + rr) * a.wpr + word_index] = s_bits[rr][w];
+    }
+}
+
+/* ------------------------------------------------------------------ reading the partition off the adjacency */
+
+/* One warp per row: root = smallest neighbour; row_ok = (row == row of root). */
+__global__ void __launch_bounds__(256) root_check_kernel(const uint32_t* __restrict__ adj, int64_t total, int64_t set_size, int wpr,
+                                                         int32_t* __restrict__ root, uint8_t* __restrict__ row_ok,
+                                                         int32_t* __restrict__ set_bad)
+{
+    const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (p >= total) return;
+    const int64_t set = p / set_size;
+    const uint32_t* row = adj + p * wpr;
+    /* first set bit */
+    int first = -1;
+    for (int w0 = 0; w0 < wpr && first < 0; w0 += 32)
+    {
+        const int w = w0 + lane;
+        const uint32_t v = (w < wpr) ? row[w] : 0u;
+        const unsigned nz = __ballot_sync(0xffffffffu, v != 0u);
+        if (nz)
+        {
+            const int src = __ffs((int)nz) - 1;
+            const uint32_t word = __shfl_sync(0xffffffffu, v, src);
+            first = (w0 + src) * 32 + (__ffs((int)word) - 1);
+        }
+    }
+    /* the diagonal guarantees a set bit; keep a defined value anyway */
+    if (first < 0) first = (int)(p - set * set_size);
+    const uint32_t* rrow = adj + (set * set_size + first) * wpr;
+    bool same = true;
+    for (int w = lane; w < wpr; w += 32) same = same && (row[w] == rrow[w]);
+    same = __all_sync(0xffffffffu, same);
+    if (lane == 0)
+    {
+        root[p] = first;
+        row_ok[p] = same ? 1 : 0;
+        if (!same) atomicOr(&set_bad[set], 1);
+    }
+}
+
+/* connected components of the threshold graph by min-label propagation + pointer jumping (fallback path only) */
+__global__ void __launch_bounds__(256) propagate_kernel(const uint32_t* __restrict__ adj, int64_t total, int64_t set_size, int wpr,
+                                                        const int32_t* __restrict__ set_bad, int32_t* __restrict__ comp,
+                                                        int* __restrict__ changed)
+{
+    const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (p >= total) return;
+    const int64_t set = p / set_size;
+    if (!set_bad[set]) return;
+    const uint32_t* row = adj + p * wpr;
+    const int32_t* sc = comp + set * set_size;
+    int32_t best = sc[p - set * set_size];
+    for (int w = lane; w < wpr; w += 32)
+    {
+        uint32_t v = row[w];
+        while (v)
+        {
+            const int b = __ffs((int)v) - 1;
+            v &= v - 1u;
+            const int32_t c = sc[w * 32 + b];
+            best = min(best, c);
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, off));
+    if (lane == 0)
+    {
+        /* pointer jumping */
+        int32_t r = best;
+        while (sc[r] < r) r = sc[r];
+        if (r < comp[p])
+        {
+            comp[p] = r;
+            *changed = 1;
+        }
+    }
+}
+
+__global__ void iota_in_set_kernel(int32_t* out, int64_t total, int64_t set_size)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < total) out[p] = (int32_t)(p % set_size);
+}
+
+/* canonical labels: one CTA per set; clusters numbered by increasing representative */
+__global__ void __launch_bounds__(1024) label_kernel(const int32_t* __restrict__ root, int64_t set_size, int32_t* __restrict__ rank_scratch,
+                                                     int32_t* __restrict__ labels, int32_t* __restrict__ n_clusters)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_running;
+    const int64_t base = (int64_t)blockIdx.x * set_size;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_running = 0;
+    __syncthreads();
+    for (int64_t c0 = 0; c0 < set_size; c0 += 1024)
+    {
+        const int64_t i = c0 + threadIdx.x;
+        const bool is_root = (i < set_size) && (root[base + i] == (int32_t)i);
+        const unsigned b = __ballot_sync(0xffffffffu, is_root);
+        if (lane == 0) s_warp[warp] = __popc(b);
+        __syncthreads();
+        int before = s_running;
+        for (int w = 0; w < warp; w++) before += s_warp[w];
+        if (is_root) rank_scratch[base + i] = before + __popc(b & ((1u << lane) - 1u));
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            int tot = 0;
+            for (int w = 0; w < 32; w++) tot += s_warp[w];
+            s_running += tot;
+        }
+        __syncthreads();
+    }
+    for (int64_t i = threadIdx.x; i < set_size; i += 1024) labels[base + i] = rank_scratch[base + root[base + i]];
+    if (threadIdx.x == 0) n_clusters[blockIdx.x] = s_running;
+}
+
+/* ------------------------------------------------------------------ exact complete link on non-clique components */
+
+struct MatrixArgs
+{
+    DevRobot robot;
+    const double* feat;   /* config features [F][total] or null */
+    const uint32_t* sig;  /* signatures [P][total] or null */
+    int nfeat, num_points;
+    int64_t total;
+    const int64_t* members;    /* global particle index of every member, components concatenated */
+    const int64_t* comp_off;   /* per component: offset into members */
+    const int64_t* matrix_off; /* per component: offset into matrices */
+    double* matrices;
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(256) component_matrix_kernel(const __grid_constant__ MatrixArgs a)
+{
+    constexpr int MAXF = PairDistance<KIND>::MAXF;
+    const int comp = blockIdx.y;
+    const int64_t off = a.comp_off[comp];
+    const int64_t m = a.comp_off[comp + 1] - off;
+    double* D = a.matrices + a.matrix_off[comp];
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < m * m; e += (int64_t)gridDim.x * blockDim.x)
+    {
+        const int64_t i = e / m, j = e % m;
+        double d = 0.0;
+        if (i != j)
+        {
+            const int64_t pi = a.members[off + i], pj = a.members[off + j];
+            if (a.sig)
+            {
+                int mism = 0;
+                for (int k = 0; k < a.num_points; k++)
+                {
+                    const uint32_t x = a.sig[(int64_t)k * a.total + pi], y = a.sig[(int64_t)k * a.total + pj];
+                    mism += ((x != 0u) && (y != 0u) && ((x & y) == 0u)) ? 1 : 0;
+                }
+                d = (double)mism / (double)a.num_points;
+            }
+            else
+            {
+                double fa[MAXF], fb[MAXF];
+#pragma unroll
+                for (int f = 0; f < MAXF; f++)
+                {
+                    fa[f] = (f < a.nfeat) ? a.feat[(int64_t)f * a.total + pi] : 0.0;
+                    fb[f] = (f < a.nfeat) ? a.feat[(int64_t)f * a.total + pj] : 0.0;
+                }
+                d = PairDistance<KIND>::eval(a.robot, fa, fb);
+            }
+        }
+        D[e] = d;
+    }
+}
+
+struct LinkArgs
+{
+    const int64_t* comp_off;
+    const int64_t* matrix_off;
+    double* matrices;
+    double threshold;
+    /* per-member scratch, concatenated like members */
+    double* rmin;
+    int32_t* rarg;
+    int32_t* parent;
+    uint8_t* active;
+    uint8_t* valid;
+    int32_t* rep; /* out: representative (position within the component) of every member */
+};
+
+/*
+ * Complete-link agglomeration cut at `threshold`, one CTA per component.
+ * D is updated in place with the Lance-Williams rule d(k, a U b) = max(d(k,a), d(k,b)); each row keeps its
+ * nearest later active row; ties resolve to the smallest (a, b) lexicographically.
+ */
+__global__ void __launch_bounds__(256) complete_link_kernel(const __grid_constant__ LinkArgs a)
+{
+    const int comp = blockIdx.x;
+    const int64_t off = a.comp_off[comp];
+    const int m = (int)(a.comp_off[comp + 1] - off);
+    double* D = a.matrices + a.matrix_off[comp];
+    double* rmin = a.rmin + off;
+    int32_t* rarg = a.rarg + off;
+    int32_t* parent = a.parent + off;
+    uint8_t* active = a.active + off;
+    uint8_t* valid = a.valid + off;
+    __shared__ double s_val[8];
+    __shared__ int s_idx[8];
+    __shared__ double s_best;
+    __shared__ int s_a, s_b;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = threadIdx.x; k < m; k += 256)
+    {
+        active[k] = 1; valid[k] = 0; parent[k] = k;
+    }
+    __syncthreads();
+    while (true)
+    {
+        /* refresh nearest-later-neighbour of invalid rows, one warp per row */
+        for (int r = warp; r < m; r += 8)
+        {
+            if (!active[r] || valid[r]) continue;
+            double bv = INFINITY;
+            int bi = -1;
+            for (int c = r + 1 + lane; c < m; c += 32)
+            {
+                if (!active[c]) continue;
+                const double d = D[(int64_t)r * m + c];
+                if (d < bv) { bv = d; bi = c; }
+            }
+            for (int o = 16; o > 0; o >>= 1)
+            {
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (oi >= 0 && (bi < 0 || ov < bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+            }
+            if (lane == 0) { rmin[r] = bv; rarg[r] = bi; valid[r] = 1; }
+        }
+        __syncthreads();
+        /* global minimum over rows, ties to the smallest row */
+        double bv = INFINITY;
+        int bi = -1;
+        for (int r = threadIdx.x; r < m; r += 256)
+        {
+            if (!active[r] || rarg[r] < 0) continue;
+            const double d = rmin[r];
+            if (bi < 0 || d < bv) { bv = d; bi = r; }
+        }
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (oi >= 0 && (bi < 0 || ov < bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { s_val[warp] = bv; s_idx[warp] = bi; }
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            double v = INFINITY;
+            int idx = -1;
+            for (int w = 0; w < 8; w++)
+            {
+                if (s_idx[w] >= 0 && (idx < 0 || s_val[w] < v || (s_val[w] == v && s_idx[w] < idx))) { v = s_val[w]; idx = s_idx[w]; }
+            }
+            s_best = v;
+            s_a = idx;
+            s_b = (idx >= 0) ? rarg[idx] : -1;
+        }
+        __syncthreads();
+        const int ra = s_a, rb = s_b;
+        if (ra < 0 || !(s_best <= a.threshold)) break;
+        /* merge rb into ra */
+        for (int k = threadIdx.x; k < m; k += 256)
+        {
+            if (!active[k] || k == ra || k == rb) continue;
+            const double da = D[(int64_t)ra * m + k], db = D[(int64_t)rb * m + k];
+            const double nd = (da < db) ? db : da;
+            D[(int64_t)ra * m + k] = nd;
+            D[(int64_t)k * m + ra] = nd;
+            if (rarg[k] == ra || rarg[k] == rb) valid[k] = 0;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            active[rb] = 0;
+            parent[rb] = ra;
+            valid[ra] = 0;
+        }
+        __syncthreads();
+    }
+    for (int k = threadIdx.x; k < m; k += 256)
+    {
+        int r = k;
+        while (parent[r] != r) r = parent[r];
+        a.rep[off + k] = r;
+    }
+}
+
+__global__ void scatter_roots_kernel(const int64_t* members, const int64_t* comp_off, int ncomp, const int32_t* rep, int64_t set_size,
+                                     int32_t* root)
+{
+    const int comp = blockIdx.x;
+    const int64_t off = comp_off[comp];
+    const int64_t m = comp_off[comp + 1] - off;
+    for (int64_t k = threadIdx.x; k < m; k += blockDim.x)
+    {
+        const int64_t p = members[off + k];
+        const int64_t rp = members[off + rep[off + k]];
+        root[p] = (int32_t)(rp % set_size);
+    }
+    (void)ncomp;
+}
+
+/* ------------------------------------------------------------------ host orchestration */
+
+struct PassInput
+{
+    const double* feat = nullptr;
+    int nfeat = 0;
+    const uint32_t* sig = nullptr;
+    int max_mismatch = 0;
+    const int32_t* group = nullptr;
+    double threshold = 0.0;
+};
+
+template <typename T>
+static T* buf(DeviceBuffer& b, size_t count)
+{
+    if (b.reserve(count * sizeof(T)) != cudaSuccess) return nullptr;
+    return (T*)b.ptr;
+}
+
+#define UPC_NULLCHECK(p)                            \
+    if (!(p))                                       \
+    {                                               \
+        set_error("device allocation failed");      \
+        return UPC_ERR_CUDA;                        \
+    }
+
+/* one clustering pass: adjacency -> roots (+ exact fallback). roots[p] = representative index within the set. */
+static int32_t cluster_pass(upc_handle* h, const PassInput& in, int64_t n_sets, int64_t set_size, int32_t* d_root, cudaStream_t stream,
+                            int64_t* fallback_sets)
+{
+    const int64_t total = n_sets * set_size;
+    const int wpr = (int)((set_size + 31) / 32);
+    uint32_t* adj = buf<uint32_t>(h->cw.adjacency, (size_t)total * wpr);
+    UPC_NULLCHECK(adj);
+    uint8_t* row_ok = buf<uint8_t>(h->cw.flags, (size_t)total + (size_t)n_sets * sizeof(int32_t) + 64);
+    UPC_NULLCHECK(row_ok);
+    int32_t* set_bad = (int32_t*)(row_ok + ((total + 15) / 16) * 16);
+    UPC_CUDA_TRY(cudaMemsetAsync(set_bad, 0, (size_t)n_sets * sizeof(int32_t), stream));
+    const int kind = h->robot.kind;
+    if (in.sig)
+    {
+        SigAdjArgs sa;
+        sa.sig = in.sig; sa.num_points = h->robot.num_points; sa.total = total; sa.set_size = set_size; sa.wpr = wpr; sa.adj = adj;
+        sa.max_mismatch = in.max_mismatch;
+        dim3 grid((unsigned)((set_size + 63) / 64), (unsigned)((set_size + 63) / 64), (unsigned)n_sets);
+        signature_adjacency_kernel<<<grid, 256, 0, stream>>>(sa);
+    }
+    else
+    {
+        AdjArgs aa;
+        aa.robot = h->robot; aa.feat = in.feat; aa.nfeat = in.nfeat; aa.total = total; aa.set_size = set_size; aa.wpr = wpr;
+        aa.group = in.group; aa.adj = adj; aa.threshold = in.threshold;
+        dim3 grid((unsigned)((set_size + kTileCols - 1) / kTileCols), (unsigned)((set_size + kTileRows - 1) / kTileRows), (unsigned)n_sets);
+        if (kind == UPC_ROBOT_SE2) adjacency_kernel<UPC_ROBOT_SE2><<<grid, kTileCols, 0, stream>>>(aa);
+        else if (kind == UPC_ROBOT_SE3) adjacency_kernel<UPC_ROBOT_SE3><<<grid, kTileCols, 0, stream>>>(aa);
+        else adjacency_kernel<UPC_ROBOT_LINKED><<<grid, kTileCols, 0, stream>>>(aa);
+    }
+    h->stats.kernel_launches++;
+    UPC_CUDA_TRY(cudaGetLastError());
+    {
+        const int64_t threads = total * 32;
+        root_check_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(adj, total, set_size, wpr, d_root, row_ok, set_bad);
+        h->stats.kernel_launches++;
+        UPC_CUDA_TRY(cudaGetLastError());
+    }
+    /* did every set come out as a union of cliques? */
+    std::vector<int32_t> bad((size_t)n_sets);
+    UPC_CUDA_TRY(cudaMemcpyAsync(bad.data(), set_bad, (size_t)n_sets * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    UPC_CUDA_TRY(cudaStreamSynchronize(stream));
+    h->stats.d2h_bytes += n_sets * (int64_t)sizeof(int32_t);
+    int64_t nbad = 0;
+    for (int32_t b : bad) nbad += b ? 1 : 0;
+    if (fallback_sets) *fallback_sets = nbad;
+    if (nbad == 0) return UPC_OK;
+
+    /* ---- exact path for the sets whose threshold graph is not a union of cliques ---- */
+    int32_t* comp = buf<int32_t>(h->cw.comp, (size_t)total);
+    UPC_NULLCHECK(comp);
+    iota_in_set_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(comp, total, set_size);
+    int* d_changed = (int*)buf<int>(h->cw.misc, 16);
+    UPC_NULLCHECK(d_changed);
+    for (int iter = 0; iter < 100000; iter++)
+    {
+        UPC_CUDA_TRY(cudaMemsetAsync(d_changed, 0, sizeof(int), stream));
+        propagate_kernel<<<(unsigned)((total * 32 + 255) / 256), 256, 0, stream>>>(adj, total, set_size, wpr, set_bad, comp, d_changed);
+        h->stats.kernel_launches++;
+        int changed = 0;
+        UPC_CUDA_TRY(cudaMemcpyAsync(&changed, d_changed, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        UPC_CUDA_TRY(cudaStreamSynchronize(stream));
+        if (!changed) break;
+    }
+    std::vector<int32_t> h_comp((size_t)total);
+    std::vector<uint8_t> h_ok((size_t)total);
+    UPC_CUDA_TRY(cudaMemcpyAsync(h_comp.data(), comp, (size_t)total * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(h_ok.data(), row_ok, (size_t)total, cudaMemcpyDeviceToHost, stream));
+    UPC_CUDA_TRY(cudaStreamSynchronize(stream));
+    h->stats.d2h_bytes += total * 5;
+    /* components that contain a row differing from its root's row */
+    std::vector<int64_t> members, comp_off(1, 0), matrix_off(1, 0);
+    for (int64_t s = 0; s < n_sets; s++)
+    {
+        if (!bad[(size_t)s]) continue;
+        std::map<int32_t, std::vector<int64_t>> groups;
+        std::map<int32_t, bool> dirty;
+        for (int64_t i = 0; i < set_size; i++)
+        {
+            const int64_t p = s * set_size + i;
+            groups[h_comp[(size_t)p]].push_back(p);
+            if (!h_ok[(size_t)p]) dirty[h_comp[(size_t)p]] = true;
+        }
+        for (auto& kv : groups)
+        {
+            if (!dirty.count(kv.first)) continue;
+            members.insert(members.end(), kv.second.begin(), kv.second.end());
+            comp_off.push_back((int64_t)members.size());
+            matrix_off.push_back(matrix_off.back() + (int64_t)(kv.second.size() * kv.second.size()));
+        }
+    }
+    const int ncomp = (int)comp_off.size() - 1;
+    if (ncomp == 0) return UPC_OK;
+    const size_t nm = members.size();
+    int64_t* d_members = buf<int64_t>(h->cw.members, nm + comp_off.size() + matrix_off.size());
+    UPC_NULLCHECK(d_members);
+    int64_t* d_comp_off = d_members + nm;
+    int64_t* d_matrix_off = d_comp_off + comp_off.size();
+    UPC_CUDA_TRY(cudaMemcpyAsync(d_members, members.data(), nm * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(d_comp_off, comp_off.data(), comp_off.size() * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(d_matrix_off, matrix_off.data(), matrix_off.size() * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+    h->stats.h2d_bytes += (int64_t)((nm + comp_off.size() + matrix_off.size()) * sizeof(int64_t));
+    double* d_mat = buf<double>(h->cw.dist_matrix, (size_t)matrix_off.back());
+    UPC_NULLCHECK(d_mat);
+    /* per-member scratch: rmin (8) + rarg, parent, rep (4 each) + active, valid (1 each) */
+    uint8_t* scratch = buf<uint8_t>(h->cw.link_scratch, nm * 24 + 64);
+    UPC_NULLCHECK(scratch);
+    MatrixArgs ma;
+    ma.robot = h->robot; ma.feat = in.feat; ma.sig = in.sig; ma.nfeat = in.nfeat; ma.num_points = h->robot.num_points; ma.total = total;
+    ma.members = d_members; ma.comp_off = d_comp_off; ma.matrix_off = d_matrix_off; ma.matrices = d_mat;
+    {
+        dim3 grid(64, (unsigned)ncomp);
+        if (kind == UPC_ROBOT_SE2) component_matrix_kernel<UPC_ROBOT_SE2><<<grid, 256, 0, stream>>>(ma);
+        else if (kind == UPC_ROBOT_SE3) component_matrix_kernel<UPC_ROBOT_SE3><<<grid, 256, 0, stream>>>(ma);
+        else component_matrix_kernel<UPC_ROBOT_LINKED><<<grid, 256, 0, stream>>>(ma);
+        h->stats.kernel_launches++;
+        UPC_CUDA_TRY(cudaGetLastError());
+    }
+    LinkArgs la;
+    la.comp_off = d_comp_off; la.matrix_off = d_matrix_off; la.matrices = d_mat; la.threshold = in.threshold;
+    la.rmin = (double*)scratch;
+    la.rarg = (int32_t*)(scratch + nm * 8);
+    la.parent = (int32_t*)(scratch + nm * 12);
+    la.rep = (int32_t*)(scratch + nm * 16);
+    la.active = scratch + nm * 20;
+    la.valid = scratch + nm * 21;
+    complete_link_kernel<<<(unsigned)ncomp, 256, 0, stream>>>(la);
+    h->stats.kernel_launches++;
+    UPC_CUDA_TRY(cudaGetLastError());
+    scatter_roots_kernel<<<(unsigned)ncomp, 256, 0, stream>>>(d_members, d_comp_off, ncomp, la.rep, set_size, d_root);
+    h->stats.kernel_launches++;
+    UPC_CUDA_TRY(cudaGetLastError());
+    return UPC_OK;
+}
+
+template <class M>
+static cudaError_t launch_signatures(upc_handle* h, const double* cfg, int64_t total, uint32_t* sig, double* frames, cudaStream_t stream)
+{
+    SigArgs sa;
+    sa.env = h->env; sa.robot = h->robot; sa.cfg = cfg; sa.total = total; sa.sig = sig; sa.frames = frames;
+    signature_kernel<M><<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(sa);
+    return cudaGetLastError();
+}
+
+int32_t run_cluster(upc_handle* h, const upc_cluster_params& cp, int64_t n_sets, int64_t set_size, const double* d_configs,
+                    int32_t* d_labels, int32_t* d_n_clusters, cudaStream_t stream)
+{
+    const int64_t total = n_sets * set_size;
+    if (total == 0) return UPC_OK;
+    const int kind = h->robot.kind;
+    /* distance features */
+    const double* feat = d_configs;
+    int nfeat = (kind == UPC_ROBOT_SE2) ? 3 : h->robot.dof;
+    if (kind == UPC_ROBOT_SE3)
+    {
+        double* f = buf<double>(h->cw.features, (size_t)total * 7);
+        UPC_NULLCHECK(f);
+        se3_features_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_configs, f, total);
+        h->stats.kernel_launches++;
+        UPC_CUDA_TRY(cudaGetLastError());
+        feat = f;
+        nfeat = 7;
+    }
+    /* [first-pass roots | final roots | rank scratch] */
+    int32_t* roots = buf<int32_t>(h->cw.roots, (size_t)total * 3);
+    UPC_NULLCHECK(roots);
+    int32_t* root1 = roots;
+    int32_t* root2 = roots + total;
+    int32_t* rank = roots + 2 * total;
+    const int32_t* group = nullptr;
+    if (set_size > 1) h->stats.cluster_calls += n_sets;
+    if (cp.feature_type == UPC_FEATURE_CONVEX_REGION_SIGNATURE)
+    {
+        if (!h->d_seg)
+        {
+            set_error("convex_segment grid required for CRS clustering");
+            return UPC_ERR_INVALID_ARGUMENT;
+        }
+        const int P = h->robot.num_points;
+        uint32_t* sig = buf<uint32_t>(h->cw.signatures, (size_t)total * P);
+        UPC_NULLCHECK(sig);
+        double* frames = nullptr;
+        if (kind == UPC_ROBOT_LINKED)
+        {
+            frames = buf<double>(h->cw.frames, (size_t)total * h->robot.num_links * 12);
+            UPC_NULLCHECK(frames);
+        }
+        cudaError_t e;
+        if (kind == UPC_ROBOT_SE2) e = launch_signatures<Se2Model>(h, d_configs, total, sig, frames, stream);
+        else if (kind == UPC_ROBOT_SE3) e = launch_signatures<Se3Model>(h, d_configs, total, sig, frames, stream);
+        else e = launch_signatures<LinkedModel>(h, d_configs, total, sig, frames, stream);
+        h->stats.kernel_launches++;
+        UPC_CUDA_TRY(e);
+        PassInput in;
+        in.sig = sig;
+        in.threshold = cp.signature_matching_threshold;
+        int mm = -1;
+        for (int m = 0; m <= P; m++)
+        {
+            if (((double)m / (double)P) <= cp.signature_matching_threshold) mm = m;
+            else break;
+        }
+        in.max_mismatch = mm;
+        const int32_t rc = cluster_pass(h, in, n_sets, set_size, root1, stream, nullptr);
+        if (rc != UPC_OK) return rc;
+        group = root1;
+    }
+    else if (cp.feature_type != UPC_FEATURE_NONE)
+    {
+        set_error("feature_type not supported by this build (ACTUATION_CENTER / POINT_TO_POINT are round-2 rows)");
+        return UPC_ERR_UNSUPPORTED;
+    }
+    PassInput in;
+    in.feat = feat;
+    in.nfeat = nfeat;
+    in.group = group;
+    in.threshold = cp.distance_clustering_threshold;
+    int64_t fallback = 0;
+    const int32_t rc = cluster_pass(h, in, n_sets, set_size, root2, stream, &fallback);
+    if (rc != UPC_OK) return rc;
+    h->stats.cluster_fallback_calls += fallback;
+    label_kernel<<<(unsigned)n_sets, 1024, 0, stream>>>(root2, set_size, rank, d_labels, d_n_clusters);
+    h->stats.kernel_launches++;
+    UPC_CUDA_TRY(cudaGetLastError());
+    return UPC_OK;
+}
+
+} /* namespace upc */

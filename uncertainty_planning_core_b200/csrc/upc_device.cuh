@@ -1,0 +1,901 @@
+/*
+ * upc_device.cuh - per-particle device code of the B200 particle hot path.
+ *
+ * Everything here is written once as __host__ __device__ so that tests/emulation can run the exact per-thread
+ * program on the CPU (one lane per particle) while developing without a GPU; the product only ever launches
+ * it through the __global__ kernels in upc_kernels.cu.  Arithmetic follows DESIGN.md operation by operation:
+ * reference formulas (PID, actuator, SE2 distance ...) keep the reference's separate multiplies and adds,
+ * the self-specified geometry (transform composition, trilinear SDF, normal equations) uses explicit fma.
+ * Compile with -fmad=false: contraction must never be left to the compiler.
+ */
+#ifndef UPC_DEVICE_CUH
+#define UPC_DEVICE_CUH
+
+#include <stdint.h>
+#include "upc_b200.h"
+#include "upc_math.h"
+
+#if defined(__CUDACC__)
+#define UPC_D __host__ __device__ __forceinline__
+#define UPC_DNI __host__ __device__ __noinline__
+#else
+#define UPC_D inline
+#define UPC_DNI inline
+#endif
+
+namespace upc
+{
+struct DevEnv
+{
+    int nx, ny, nz;
+    float sdf_oob, occ_oob;
+    double res, inv_res;
+    double G[12]; /* grid_from_world, row-major 3x4 */
+    const float* sdf;
+    const uint32_t* seg;
+    const float* occ;
+};
+
+struct DevAxis
+{
+    double kp, ki, kd, clamp; /* already abs()'d, simple_pid_controller.hpp:104-112 */
+    double vlim, nb;          /* |actuator limit|, |noise bound|, simple_uncertainty_models.hpp:59 */
+};
+
+struct DevJoint
+{
+    int type, parent, child, active;
+    double axis[3];
+    double lo, hi;
+    double T[12];
+};
+
+struct DevRobot
+{
+    int kind, dof, num_links, num_joints, num_points;
+    int link_off[UPC_MAX_LINKS + 1];
+    int parent_joint_of_link[UPC_MAX_LINKS];
+    const double* pts; /* num_points * 4: x, y, z, radius */
+    DevAxis axis[UPC_MAX_DOF];
+    double weights[UPC_MAX_DOF];
+    double base[12];
+    DevJoint joints[UPC_MAX_JOINTS];
+};
+
+struct DevSim
+{
+    int num_steps, max_microsteps, allow_contacts, individual_jacobians, max_resolver_iterations, decay_iterations;
+    double dt, shortcut, contact_distance, resolve_distance, microstep_distance, initial_scale, decay_rate, damping;
+};
+
+/* per-launch counters, reduced per block then added to the handle's totals */
+struct DevCounters
+{
+    unsigned long long particle_steps, collided, resolver_iterations, failed_resolves;
+};
+
+template <typename T>
+UPC_D T ldg(const T* p)
+{
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+/* ------------------------------------------------------------------ rigid transforms, row-major 3x4 in 12 doubles */
+
+UPC_D void xf_compose(const double* a, const double* b, double* c)
+{
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+    {
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+        {
+            c[i * 4 + j] = upc_fma(a[i * 4 + 2], b[8 + j], upc_fma(a[i * 4 + 1], b[4 + j], a[i * 4 + 0] * b[j]));
+        }
+        c[i * 4 + 3] = upc_fma(a[i * 4 + 2], b[11], upc_fma(a[i * 4 + 1], b[7], upc_fma(a[i * 4 + 0], b[3], a[i * 4 + 3])));
+    }
+}
+
+UPC_D void xf_point(const double* a, double px, double py, double pz, double* out)
+{
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+    {
+        out[i] = upc_fma(a[i * 4 + 2], pz, upc_fma(a[i * 4 + 1], py, upc_fma(a[i * 4 + 0], px, a[i * 4 + 3])));
+    }
+}
+
+UPC_D void cross3(const double* a, const double* b, double* out)
+{
+    out[0] = upc_fma(a[1], b[2], -(a[2] * b[1]));
+    out[1] = upc_fma(a[2], b[0], -(a[0] * b[2]));
+    out[2] = upc_fma(a[0], b[1], -(a[1] * b[0]));
+}
+
+UPC_D double dot3(const double* a, const double* b) { return upc_fma(a[2], b[2], upc_fma(a[1], b[1], a[0] * b[0])); }
+
+/* V = inv_res * (grid_from_world o link) : link frame -> continuous voxel coordinates */
+UPC_D void voxel_from_link(const DevEnv& env, const double* link, double* V)
+{
+    xf_compose(env.G, link, V);
+#pragma unroll
+    for (int k = 0; k < 12; k++) V[k] = V[k] * env.inv_res;
+}
+
+/* ------------------------------------------------------------------ SE(3) closed forms */
+
+UPC_D void se3_log(const double* T, double* twist)
+{
+    const double trace = (T[0] + T[5]) + T[10];
+    double s[3];
+    s[0] = 0.5 * (T[9] - T[6]);
+    s[1] = 0.5 * (T[2] - T[8]);
+    s[2] = 0.5 * (T[4] - T[1]);
+    const double sn = sqrt(dot3(s, s));
+    const double ct = 0.5 * (trace - 1.0);
+    const double theta = upc_atan2(sn, ct);
+    double w[3];
+    if (theta < 1.0e-8)
+    {
+        w[0] = s[0]; w[1] = s[1]; w[2] = s[2];
+    }
+    else if ((UPC_PI - theta) > 1.0e-3)
+    {
+        const double k = theta / sn;
+        w[0] = s[0] * k; w[1] = s[1] * k; w[2] = s[2] * k;
+    }
+    else
+    {
+        const double omc = 1.0 - ct;
+        const double a20 = (T[0] - ct) / omc;
+        const double a21 = (T[5] - ct) / omc;
+        const double a22 = (T[10] - ct) / omc;
+        int k = 0;
+        double best = a20;
+        if (a21 > best) { k = 1; best = a21; }
+        if (a22 > best) { k = 2; best = a22; }
+        const double akm = sqrt(upc_max(best, 0.0));
+        const double sk = (k == 0) ? s[0] : ((k == 1) ? s[1] : s[2]);
+        const double ak = (sk < 0.0) ? -akm : akm;
+        const double denom = (2.0 * omc) * ak;
+        double a[3];
+        /* (R[k][j] + R[j][k]) / denom for j != k */
+        a[0] = (k == 0) ? ak : ((T[k * 4 + 0] + T[0 * 4 + k]) / denom);
+        a[1] = (k == 1) ? ak : ((T[k * 4 + 1] + T[1 * 4 + k]) / denom);
+        a[2] = (k == 2) ? ak : ((T[k * 4 + 2] + T[2 * 4 + k]) / denom);
+        w[0] = a[0] * theta; w[1] = a[1] * theta; w[2] = a[2] * theta;
+    }
+    double k2;
+    if (theta < 1.0e-3)
+    {
+        k2 = upc_fma(theta * theta, 1.0 / 720.0, 1.0 / 12.0);
+    }
+    else
+    {
+        k2 = (1.0 - (theta * sn) / (2.0 * (1.0 - ct))) / (theta * theta);
+    }
+    const double tr[3] = {T[3], T[7], T[11]};
+    double wxt[3], wxwxt[3];
+    cross3(w, tr, wxt);
+    cross3(w, wxt, wxwxt);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+    {
+        twist[i] = upc_fma(k2, wxwxt[i], upc_fma(-0.5, wxt[i], tr[i]));
+        twist[3 + i] = w[i];
+    }
+}
+
+UPC_D void se3_exp(const double* twist, double* T)
+{
+    const double* v = twist;
+    const double* w = twist + 3;
+    const double th2 = dot3(w, w);
+    const double theta = sqrt(th2);
+    double A, B, C;
+    if (theta < 1.0e-3)
+    {
+        A = upc_fma(th2, -1.0 / 6.0, 1.0);
+        B = upc_fma(th2, -1.0 / 24.0, 0.5);
+        C = upc_fma(th2, -1.0 / 120.0, 1.0 / 6.0);
+    }
+    else
+    {
+        double sn, cs;
+        upc_sincos(theta, &sn, &cs);
+        A = sn / theta;
+        B = (1.0 - cs) / th2;
+        C = (1.0 - A) / th2;
+    }
+    const double wx = w[0], wy = w[1], wz = w[2];
+    T[0] = upc_fma(B, upc_fma(wx, wx, -th2), 1.0);
+    T[5] = upc_fma(B, upc_fma(wy, wy, -th2), 1.0);
+    T[10] = upc_fma(B, upc_fma(wz, wz, -th2), 1.0);
+    T[1] = upc_fma(B, wx * wy, -(A * wz));
+    T[4] = upc_fma(B, wx * wy, A * wz);
+    T[2] = upc_fma(B, wx * wz, A * wy);
+    T[8] = upc_fma(B, wx * wz, -(A * wy));
+    T[6] = upc_fma(B, wy * wz, -(A * wx));
+    T[9] = upc_fma(B, wy * wz, A * wx);
+    double wxv[3], wxwxv[3];
+    cross3(w, v, wxv);
+    cross3(w, wxv, wxwxv);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+    {
+        T[i * 4 + 3] = upc_fma(C, wxwxv[i], upc_fma(B, wxv[i], v[i]));
+    }
+}
+
+/* a^-1 o b */
+UPC_D void se3_between(const double* a, const double* b, double* r)
+{
+    const double d0 = b[3] - a[3], d1 = b[7] - a[7], d2 = b[11] - a[11];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+    {
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+        {
+            r[i * 4 + j] = upc_fma(a[8 + i], b[8 + j], upc_fma(a[4 + i], b[4 + j], a[i] * b[j]));
+        }
+        r[i * 4 + 3] = upc_fma(a[8 + i], d2, upc_fma(a[4 + i], d1, a[i] * d0));
+    }
+}
+
+/* rotation -> quaternion (x, y, z, w) with Eigen's branch structure */
+UPC_D void quat_from_xf(const double* T, double* q)
+{
+    double t = (T[0] + T[5]) + T[10];
+    if (t > 0.0)
+    {
+        t = sqrt(t + 1.0);
+        q[3] = 0.5 * t;
+        t = 0.5 / t;
+        q[0] = (T[9] - T[6]) * t;
+        q[1] = (T[2] - T[8]) * t;
+        q[2] = (T[4] - T[1]) * t;
+    }
+    else
+    {
+        int i = 0;
+        if (T[5] > T[0]) i = 1;
+        if (T[10] > T[i * 5]) i = 2;
+        const int j = (i + 1) % 3;
+        const int k = (j + 1) % 3;
+        t = sqrt(((T[i * 5] - T[j * 5]) - T[k * 5]) + 1.0);
+        const double qi = 0.5 * t;
+        t = 0.5 / t;
+        const double qw = (T[k * 4 + j] - T[j * 4 + k]) * t;
+        const double qj = (T[j * 4 + i] + T[i * 4 + j]) * t;
+        const double qk = (T[k * 4 + i] + T[i * 4 + k]) * t;
+        q[3] = qw;
+        q[0] = (i == 0) ? qi : ((j == 0) ? qj : qk);
+        q[1] = (i == 1) ? qi : ((j == 1) ? qj : qk);
+        q[2] = (i == 2) ? qi : ((j == 2) ? qj : qk);
+    }
+}
+
+/* ------------------------------------------------------------------ PID / actuator (reference arithmetic, no fma) */
+
+UPC_D double pid_step(const DevAxis& ax, double& integral, double& last_error, double e, double dt)
+{
+    const double step_integral = ((e * 0.5) + (last_error * 0.5)) * dt;
+    const double new_integral = integral + step_integral;
+    integral = upc_max(-ax.clamp, upc_min(ax.clamp, new_integral));
+    const double derivative = (e - last_error) / dt;
+    last_error = e;
+    return ((e * ax.kp) + (integral * ax.ki)) + (derivative * ax.kd);
+}
+
+UPC_D double actuator_clamp(const DevAxis& ax, double u)
+{
+    double r = upc_min(ax.vlim, u);
+    r = upc_max(-ax.vlim, r);
+    return r;
+}
+
+UPC_D double actuator_noisy(const DevAxis& ax, double u, double draw)
+{
+    const double r = actuator_clamp(ax, u);
+    const double noise = draw * (ax.nb * r);
+    return r + noise;
+}
+
+/* ------------------------------------------------------------------ SDF sampling */
+
+UPC_D bool voxel_in_bounds(const DevEnv& env, const double* u)
+{
+    return (u[0] >= 0.0) && (u[0] < (double)env.nx) && (u[1] >= 0.0) && (u[1] < (double)env.ny) && (u[2] >= 0.0) &&
+           (u[2] < (double)env.nz);
+}
+
+UPC_D int64_t cell_index(const DevEnv& env, int ix, int iy, int iz)
+{
+    return ((int64_t)ix * (int64_t)env.ny + (int64_t)iy) * (int64_t)env.nz + (int64_t)iz;
+}
+
+/* distance only */
+UPC_D double sdf_distance(const DevEnv& env, const double* u)
+{
+    if (!voxel_in_bounds(env, u)) return (double)env.sdf_oob;
+    const double cx = u[0] - 0.5, cy = u[1] - 0.5, cz = u[2] - 0.5;
+    const double flx = floor(cx), fly = floor(cy), flz = floor(cz);
+    const double fx = cx - flx, fy = cy - fly, fz = cz - flz;
+    const int ix = (int)flx, iy = (int)fly, iz = (int)flz;
+    const int x0 = (ix < 0) ? 0 : ix, x1 = (ix + 1 > env.nx - 1) ? env.nx - 1 : ix + 1;
+    const int y0 = (iy < 0) ? 0 : iy, y1 = (iy + 1 > env.ny - 1) ? env.ny - 1 : iy + 1;
+    const int z0 = (iz < 0) ? 0 : iz, z1 = (iz + 1 > env.nz - 1) ? env.nz - 1 : iz + 1;
+    const int64_t r00 = ((int64_t)x0 * env.ny + y0) * env.nz;
+    const int64_t r01 = ((int64_t)x0 * env.ny + y1) * env.nz;
+    const int64_t r10 = ((int64_t)x1 * env.ny + y0) * env.nz;
+    const int64_t r11 = ((int64_t)x1 * env.ny + y1) * env.nz;
+    const double v000 = (double)ldg(env.sdf + r00 + z0), v001 = (double)ldg(env.sdf + r00 + z1);
+    const double v010 = (double)ldg(env.sdf + r01 + z0), v011 = (double)ldg(env.sdf + r01 + z1);
+    const double v100 = (double)ldg(env.sdf + r10 + z0), v101 = (double)ldg(env.sdf + r10 + z1);
+    const double v110 = (double)ldg(env.sdf + r11 + z0), v111 = (double)ldg(env.sdf + r11 + z1);
+    const double c00 = upc_fma(fz, v001 - v000, v000);
+    const double c01 = upc_fma(fz, v011 - v010, v010);
+    const double c10 = upc_fma(fz, v101 - v100, v100);
+    const double c11 = upc_fma(fz, v111 - v110, v110);
+    const double c0 = upc_fma(fy, c01 - c00, c00);
+    const double c1 = upc_fma(fy, c11 - c10, c10);
+    return upc_fma(fx, c1 - c0, c0);
+}
+
+/* distance and world-frame gradient */
+UPC_D double sdf_distance_gradient(const DevEnv& env, const double* u, double* grad)
+{
+    if (!voxel_in_bounds(env, u))
+    {
+        grad[0] = 0.0; grad[1] = 0.0; grad[2] = 0.0;
+        return (double)env.sdf_oob;
+    }
+    const double cx = u[0] - 0.5, cy = u[1] - 0.5, cz = u[2] - 0.5;
+    const double flx = floor(cx), fly = floor(cy), flz = floor(cz);
+    const double fx = cx - flx, fy = cy - fly, fz = cz - flz;
+    const int ix = (int)flx, iy = (int)fly, iz = (int)flz;
+    const int x0 = (ix < 0) ? 0 : ix, x1 = (ix + 1 > env.nx - 1) ? env.nx - 1 : ix + 1;
+    const int y0 = (iy < 0) ? 0 : iy, y1 = (iy + 1 > env.ny - 1) ? env.ny - 1 : iy + 1;
+    const int z0 = (iz < 0) ? 0 : iz, z1 = (iz + 1 > env.nz - 1) ? env.nz - 1 : iz + 1;
+    const int64_t r00 = ((int64_t)x0 * env.ny + y0) * env.nz;
+    const int64_t r01 = ((int64_t)x0 * env.ny + y1) * env.nz;
+    const int64_t r10 = ((int64_t)x1 * env.ny + y0) * env.nz;
+    const int64_t r11 = ((int64_t)x1 * env.ny + y1) * env.nz;
+    const double v000 = (double)ldg(env.sdf + r00 + z0), v001 = (double)ldg(env.sdf + r00 + z1);
+    const double v010 = (double)ldg(env.sdf + r01 + z0), v011 = (double)ldg(env.sdf + r01 + z1);
+    const double v100 = (double)ldg(env.sdf + r10 + z0), v101 = (double)ldg(env.sdf + r10 + z1);
+    const double v110 = (double)ldg(env.sdf + r11 + z0), v111 = (double)ldg(env.sdf + r11 + z1);
+    const double dz00 = v001 - v000, dz01 = v011 - v010, dz10 = v101 - v100, dz11 = v111 - v110;
+    const double c00 = upc_fma(fz, dz00, v000);
+    const double c01 = upc_fma(fz, dz01, v010);
+    const double c10 = upc_fma(fz, dz10, v100);
+    const double c11 = upc_fma(fz, dz11, v110);
+    const double dy0 = c01 - c00, dy1 = c11 - c10;
+    const double c0 = upc_fma(fy, dy0, c00);
+    const double c1 = upc_fma(fy, dy1, c10);
+    const double dzv0 = upc_fma(fy, dz01 - dz00, dz00);
+    const double dzv1 = upc_fma(fy, dz11 - dz10, dz10);
+    const double ddx = c1 - c0;
+    const double dist = upc_fma(fx, ddx, c0);
+    const double ddy = upc_fma(fx, dy1 - dy0, dy0);
+    const double ddz = upc_fma(fx, dzv1 - dzv0, dzv0);
+    const double g0 = ddx * env.inv_res, g1 = ddy * env.inv_res, g2 = ddz * env.inv_res;
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+    {
+        grad[j] = upc_fma(env.G[8 + j], g2, upc_fma(env.G[4 + j], g1, env.G[j] * g0));
+    }
+    return dist;
+}
+
+/* ------------------------------------------------------------------ damped normal equations */
+
+template <int N>
+UPC_D void solve_damped(double (&H)[N][N], const double* g, double lambda, double* x, int n)
+{
+    /* Cholesky in place in the lower triangle of H (upper triangle holds the input) */
+#pragma unroll
+    for (int j = 0; j < N; j++)
+    {
+        if (j < n)
+        {
+            double s = H[j][j] + lambda;
+#pragma unroll
+            for (int k = 0; k < N; k++)
+                if (k < j) s = upc_fma(-H[j][k], H[j][k], s);
+            if (s < lambda) s = lambda;
+            const double ljj = sqrt(s);
+#pragma unroll
+            for (int i = 0; i < N; i++)
+            {
+                if (i > j && i < n)
+                {
+                    double t = H[j][i]; /* input H[i][j] read from the symmetric upper triangle */
+#pragma unroll
+                    for (int k = 0; k < N; k++)
+                        if (k < j) t = upc_fma(-H[i][k], H[j][k], t);
+                    H[i][j] = t / ljj;
+                }
+            }
+            H[j][j] = ljj;
+        }
+    }
+    double y[N];
+#pragma unroll
+    for (int i = 0; i < N; i++)
+    {
+        if (i < n)
+        {
+            double s = g[i];
+#pragma unroll
+            for (int k = 0; k < N; k++)
+                if (k < i) s = upc_fma(-H[i][k], y[k], s);
+            y[i] = s / H[i][i];
+        }
+    }
+#pragma unroll
+    for (int ii = 0; ii < N; ii++)
+    {
+        const int i = N - 1 - ii;
+        if (i < n)
+        {
+            double s = y[i];
+#pragma unroll
+            for (int k = 0; k < N; k++)
+                if (k > i && k < n) s = upc_fma(-H[k][i], x[k], s);
+            x[i] = s / H[i][i];
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ robot models */
+
+/*
+ * Each model keeps the particle's configuration, the PID state of every axis and whatever pose cache it needs.
+ * Common interface used by the simulation program:
+ *   load(cfg_soa, stride, i) / store(...)   boundary layout <-> registers
+ *   reset_controllers()
+ *   control(robot, target, dt, draws, u)    GenerateControlAction(target, dt, rng)
+ *   apply(robot, input, draws|nullptr)      ApplyControlInput(input[, rng])
+ *   frame(robot, l, T)                      current transform of link l
+ *   jacobian(robot, l, local, world, J)     3 x dof translational point Jacobian
+ *   distance_to(robot, target)              ComputeConfigurationDistance(config, target)
+ */
+struct Se2Model
+{
+    static constexpr int DOF = 3;
+    static constexpr int WIDTH = 3;
+    double x, y, th, sn, cs;
+    double pid_i[3], pid_e[3];
+
+    UPC_D int dof(const DevRobot&) const { return 3; }
+    UPC_D void set_config(double nx, double ny, double nth) /* simple_robot_models.hpp:110-119 */
+    {
+        x = nx;
+        y = ny;
+        th = upc_wrap_angle(nth);
+        upc_sincos(th, &sn, &cs);
+    }
+    UPC_D void load(const DevRobot&, const double* c, int64_t stride, int64_t i) { set_config(c[i], c[stride + i], c[2 * stride + i]); }
+    UPC_D void store(const DevRobot&, double* c, int64_t stride, int64_t i) const
+    {
+        c[i] = x; c[stride + i] = y; c[2 * stride + i] = th;
+    }
+    UPC_D void get(const DevRobot&, double* c) const { c[0] = x; c[1] = y; c[2] = th; }
+    UPC_D void set(const DevRobot&, const double* c) { set_config(c[0], c[1], c[2]); }
+    UPC_D void reset_controllers()
+    {
+#pragma unroll
+        for (int i = 0; i < 3; i++) { pid_i[i] = 0.0; pid_e[i] = 0.0; }
+    }
+    UPC_D static double distance(const DevRobot&, const double* a, const double* b) /* :424-430 */
+    {
+        const double dx = b[0] - a[0];
+        const double dy = b[1] - a[1];
+        const double dth = upc_angle_signed_distance(a[2], b[2]);
+        const double trans = sqrt((dx * dx) + (dy * dy));
+        return trans + fabs(dth);
+    }
+    UPC_D double distance_to(const DevRobot& r, const double* target) const
+    {
+        const double c[3] = {x, y, th};
+        return distance(r, c, target);
+    }
+    UPC_D void control(const DevRobot& r, const double* target, double dt, const double* draws, double* u) /* :239-259 */
+    {
+        const double sx = x + draws[0];
+        const double sy = y + draws[1];
+        const double sth = th + draws[2];
+        const double e0 = target[0] - sx;
+        const double e1 = target[1] - sy;
+        const double e2 = upc_angle_signed_distance(sth, target[2]);
+        u[0] = actuator_clamp(r.axis[0], pid_step(r.axis[0], pid_i[0], pid_e[0], e0, dt));
+        u[1] = actuator_clamp(r.axis[1], pid_step(r.axis[1], pid_i[1], pid_e[1], e1, dt));
+        u[2] = actuator_clamp(r.axis[2], pid_step(r.axis[2], pid_i[2], pid_e[2], e2, dt));
+    }
+    UPC_D void apply(const DevRobot& r, const double* in, const double* draws) /* :282-308 */
+    {
+        double n0, n1, n2;
+        if (draws)
+        {
+            n0 = actuator_noisy(r.axis[0], in[0], draws[0]);
+            n1 = actuator_noisy(r.axis[1], in[1], draws[1]);
+            n2 = actuator_noisy(r.axis[2], in[2], draws[2]);
+        }
+        else
+        {
+            n0 = actuator_clamp(r.axis[0], in[0]);
+            n1 = actuator_clamp(r.axis[1], in[1]);
+            n2 = actuator_clamp(r.axis[2], in[2]);
+        }
+        set_config(x + n0, y + n1, th + n2);
+    }
+    static constexpr bool HAS_FRAMES = false;
+    UPC_D void frame(const DevRobot&, int, double* T) const /* :363-371 */
+    {
+        T[0] = cs;  T[1] = -sn; T[2] = 0.0;  T[3] = x;
+        T[4] = sn;  T[5] = cs;  T[6] = 0.0;  T[7] = y;
+        T[8] = 0.0; T[9] = 0.0; T[10] = 1.0; T[11] = 0.0;
+    }
+    UPC_D void jacobian(const DevRobot&, int, const double*, const double* world, double (&J)[3][DOF]) const /* :334-361 */
+    {
+        J[0][0] = 1.0; J[1][0] = 0.0; J[2][0] = 0.0;
+        J[0][1] = 0.0; J[1][1] = 1.0; J[2][1] = 0.0;
+        const double rx = world[0] - x;
+        const double ry = world[1] - y;
+        J[0][2] = -ry; J[1][2] = rx; J[2][2] = 0.0;
+    }
+};
+
+struct Se3Model
+{
+    static constexpr int DOF = 6;
+    static constexpr int WIDTH = 12;
+    double T[12];
+    double pid_i[6], pid_e[6];
+
+    UPC_D int dof(const DevRobot&) const { return 6; }
+    UPC_D void load(const DevRobot&, const double* c, int64_t stride, int64_t i)
+    {
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+        {
+#pragma unroll
+            for (int k = 0; k < 3; k++) T[r * 4 + k] = c[(int64_t)(r * 3 + k) * stride + i];
+            T[r * 4 + 3] = c[(int64_t)(9 + r) * stride + i];
+        }
+    }
+    UPC_D void store(const DevRobot&, double* c, int64_t stride, int64_t i) const
+    {
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+        {
+#pragma unroll
+            for (int k = 0; k < 3; k++) c[(int64_t)(r * 3 + k) * stride + i] = T[r * 4 + k];
+            c[(int64_t)(9 + r) * stride + i] = T[r * 4 + 3];
+        }
+    }
+    UPC_D void get(const DevRobot&, double* c) const
+    {
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+        {
+#pragma unroll
+            for (int k = 0; k < 3; k++) c[r * 3 + k] = T[r * 4 + k];
+            c[9 + r] = T[r * 4 + 3];
+        }
+    }
+    UPC_D void set(const DevRobot&, const double* c)
+    {
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+        {
+#pragma unroll
+            for (int k = 0; k < 3; k++) T[r * 4 + k] = c[r * 3 + k];
+            T[r * 4 + 3] = c[9 + r];
+        }
+    }
+    UPC_D void reset_controllers()
+    {
+#pragma unroll
+        for (int i = 0; i < 6; i++) { pid_i[i] = 0.0; pid_e[i] = 0.0; }
+    }
+    /* a, b in the boundary layout (R row-major, then t) */
+    UPC_D static double distance(const DevRobot&, const double* a, const double* b) /* :871-874 */
+    {
+        double ta[12], tb[12];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+        {
+#pragma unroll
+            for (int k = 0; k < 3; k++) { ta[r * 4 + k] = a[r * 3 + k]; tb[r * 4 + k] = b[r * 3 + k]; }
+            ta[r * 4 + 3] = a[9 + r]; tb[r * 4 + 3] = b[9 + r];
+        }
+        return distance_xf(ta, tb);
+    }
+    UPC_D static double distance_xf(const double* ta, const double* tb)
+    {
+        const double dx = ta[3] - tb[3], dy = ta[7] - tb[7], dz = ta[11] - tb[11];
+        const double tdist = sqrt(((dx * dx) + (dy * dy)) + (dz * dz));
+        double q1[4], q2[4];
+        quat_from_xf(ta, q1);
+        quat_from_xf(tb, q2);
+        const double dq = fabs((((q1[0] * q2[0]) + (q1[1] * q2[1])) + (q1[2] * q2[2])) + (q1[3] * q2[3]));
+        double rdist = 0.0;
+        if (dq < (1.0 - 2.220446049250313e-16))
+        {
+            rdist = upc_acos(((2.0 * dq) * dq) - 1.0);
+        }
+        return (((1.0 - 0.5) * tdist) + (0.5 * rdist)) * 2.0;
+    }
+    UPC_D double distance_to(const DevRobot&, const double* target) const
+    {
+        double tb[12];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+        {
+#pragma unroll
+            for (int k = 0; k < 3; k++) tb[r * 4 + k] = target[r * 3 + k];
+            tb[r * 4 + 3] = target[9 + r];
+        }
+        return distance_xf(T, tb);
+    }
+    UPC_D void control(const DevRobot& r, const double* target, double dt, const double* draws, double* u) /* :685-714 */
+    {
+        double tw[6];
+        se3_log(T, tw); /* GetPosition(rng) :654-668 */
+#pragma unroll
+        for (int i = 0; i < 6; i++) tw[i] = tw[i] + draws[i];
+        double sensed[12];
+        se3_exp(tw, sensed);
+        double tgt[12];
+#pragma unroll
+        for (int rr = 0; rr < 3; rr++)
+        {
+#pragma unroll
+            for (int k = 0; k < 3; k++) tgt[rr * 4 + k] = target[rr * 3 + k];
+            tgt[rr * 4 + 3] = target[9 + rr];
+        }
+        double rel[12];
+        se3_between(sensed, tgt, rel);
+        double err[6];
+        se3_log(rel, err);
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+        {
+            u[i] = actuator_clamp(r.axis[i], pid_step(r.axis[i], pid_i[i], pid_e[i], err[i], dt));
+        }
+    }
+    UPC_D void apply(const DevRobot& r, const double* in, const double* draws) /* :746-789 */
+    {
+        double tw[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+        {
+            tw[i] = draws ? actuator_noisy(r.axis[i], in[i], draws[i]) : actuator_clamp(r.axis[i], in[i]);
+        }
+        double motion[12], next[12];
+        se3_exp(tw, motion);
+        xf_compose(T, motion, next);
+#pragma unroll
+        for (int k = 0; k < 12; k++) T[k] = next[k];
+    }
+    static constexpr bool HAS_FRAMES = false;
+    UPC_D void frame(const DevRobot&, int, double* out) const
+    {
+#pragma unroll
+        for (int k = 0; k < 12; k++) out[k] = T[k];
+    }
+    UPC_D void jacobian(const DevRobot&, int, const double* local, const double*, double (&J)[3][DOF]) const /* :813-832 */
+    {
+        const double px = local[0], py = local[1], pz = local[2];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+        {
+            J[i][0] = T[i * 4 + 0];
+            J[i][1] = T[i * 4 + 1];
+            J[i][2] = T[i * 4 + 2];
+            J[i][3] = upc_fma(T[i * 4 + 2], py, -(T[i * 4 + 1] * pz));
+            J[i][4] = upc_fma(T[i * 4 + 0], pz, -(T[i * 4 + 2] * px));
+            J[i][5] = upc_fma(T[i * 4 + 1], px, -(T[i * 4 + 0] * py));
+        }
+    }
+};
+
+/*
+ * Linked robot: joint values and PID state live in registers/local memory; link transforms are recomputed
+ * into a caller-provided frame buffer (shared memory on the GPU) by fk().
+ */
+struct LinkedModel
+{
+    static constexpr int DOF = UPC_MAX_DOF;
+    static constexpr int WIDTH = UPC_MAX_DOF;
+    double q[UPC_MAX_DOF];
+    double pid_i[UPC_MAX_DOF], pid_e[UPC_MAX_DOF];
+    double* frames; /* num_links * 12 doubles, current link transforms */
+    static constexpr bool HAS_FRAMES = true;
+    UPC_D void frame(const DevRobot&, int l, double* out) const
+    {
+#pragma unroll
+        for (int k = 0; k < 12; k++) out[k] = frames[l * 12 + k];
+    }
+
+    UPC_D int dof(const DevRobot& r) const { return r.dof; }
+    UPC_D static double enforce_limits(const DevJoint& j, double v) /* :1077-1100 */
+    {
+        if (j.type == UPC_JOINT_CONTINUOUS) return upc_wrap_angle(v);
+        if (v < j.lo) return j.lo;
+        if (v > j.hi) return j.hi;
+        return v;
+    }
+    UPC_D static double signed_distance(const DevJoint& j, double v1, double v2) /* :1108-1118 */
+    {
+        if (j.type == UPC_JOINT_CONTINUOUS) return upc_angle_signed_distance(v1, v2);
+        return (v2 - v1);
+    }
+    /* forward kinematics into out (num_links*12), :1299-1343 */
+    UPC_D void fk(const DevRobot& r, double* out) const
+    {
+        for (int k = 0; k < 12; k++) out[k] = r.base[k];
+        for (int idx = 0; idx < r.num_joints; idx++)
+        {
+            const DevJoint& j = r.joints[idx];
+            double parent[12], complete[12];
+            for (int k = 0; k < 12; k++) parent[k] = out[j.parent * 12 + k];
+            xf_compose(parent, j.T, complete);
+            double* child = out + j.child * 12;
+            if ((j.type == UPC_JOINT_REVOLUTE) || (j.type == UPC_JOINT_CONTINUOUS))
+            {
+                double s, c;
+                upc_sincos(q[j.active], &s, &c);
+                const double t = 1.0 - c;
+                const double ax = j.axis[0], ay = j.axis[1], az = j.axis[2];
+                double Rj[9];
+                Rj[0] = upc_fma(t * ax, ax, c);
+                Rj[1] = upc_fma(t * ax, ay, -(s * az));
+                Rj[2] = upc_fma(t * ax, az, s * ay);
+                Rj[3] = upc_fma(t * ay, ax, s * az);
+                Rj[4] = upc_fma(t * ay, ay, c);
+                Rj[5] = upc_fma(t * ay, az, -(s * ax));
+                Rj[6] = upc_fma(t * az, ax, -(s * ay));
+                Rj[7] = upc_fma(t * az, ay, s * ax);
+                Rj[8] = upc_fma(t * az, az, c);
+#pragma unroll
+                for (int rr = 0; rr < 3; rr++)
+                {
+#pragma unroll
+                    for (int cc = 0; cc < 3; cc++)
+                    {
+                        child[rr * 4 + cc] = upc_fma(complete[rr * 4 + 2], Rj[6 + cc],
+                                                     upc_fma(complete[rr * 4 + 1], Rj[3 + cc], complete[rr * 4 + 0] * Rj[cc]));
+                    }
+                    child[rr * 4 + 3] = complete[rr * 4 + 3];
+                }
+            }
+            else if (j.type == UPC_JOINT_PRISMATIC)
+            {
+                const double v = q[j.active];
+                const double d0 = j.axis[0] * v, d1 = j.axis[1] * v, d2 = j.axis[2] * v;
+#pragma unroll
+                for (int rr = 0; rr < 3; rr++)
+                {
+                    child[rr * 4 + 0] = complete[rr * 4 + 0];
+                    child[rr * 4 + 1] = complete[rr * 4 + 1];
+                    child[rr * 4 + 2] = complete[rr * 4 + 2];
+                    child[rr * 4 + 3] = upc_fma(complete[rr * 4 + 2], d2,
+                                                upc_fma(complete[rr * 4 + 1], d1, upc_fma(complete[rr * 4 + 0], d0, complete[rr * 4 + 3])));
+                }
+            }
+            else
+            {
+                for (int k = 0; k < 12; k++) child[k] = complete[k];
+            }
+        }
+    }
+    UPC_D void set_values(const DevRobot& r, const double* c) /* :1345-1369 */
+    {
+        for (int idx = 0; idx < r.num_joints; idx++)
+        {
+            const DevJoint& j = r.joints[idx];
+            if (j.type == UPC_JOINT_FIXED) continue;
+            q[j.active] = enforce_limits(j, c[j.active]);
+        }
+    }
+    UPC_D void load(const DevRobot& r, const double* c, int64_t stride, int64_t i)
+    {
+        double v[UPC_MAX_DOF];
+        for (int a = 0; a < r.dof; a++) v[a] = c[(int64_t)a * stride + i];
+        set_values(r, v);
+    }
+    UPC_D void store(const DevRobot& r, double* c, int64_t stride, int64_t i) const
+    {
+        for (int a = 0; a < r.dof; a++) c[(int64_t)a * stride + i] = q[a];
+    }
+    UPC_D void get(const DevRobot& r, double* c) const
+    {
+        for (int a = 0; a < r.dof; a++) c[a] = q[a];
+    }
+    UPC_D void set(const DevRobot& r, const double* c) { set_values(r, c); }
+    UPC_D void reset_controllers()
+    {
+        for (int i = 0; i < UPC_MAX_DOF; i++) { pid_i[i] = 0.0; pid_e[i] = 0.0; }
+    }
+    UPC_D static double distance(const DevRobot& r, const double* a, const double* b) /* :2191-2217 */
+    {
+        double sum = 0.0;
+        for (int idx = 0; idx < r.num_joints; idx++)
+        {
+            const DevJoint& j = r.joints[idx];
+            if (j.type == UPC_JOINT_FIXED) continue;
+            const double raw = signed_distance(j, a[j.active], b[j.active]);
+            const double wd = raw * r.weights[j.active];
+            sum = sum + (wd * wd);
+        }
+        return sqrt(sum);
+    }
+    UPC_D double distance_to(const DevRobot& r, const double* target) const { return distance(r, q, target); }
+    UPC_D void control(const DevRobot& r, const double* target, double dt, const double* draws, double* u) /* :1823-1851 */
+    {
+        for (int idx = 0; idx < r.num_joints; idx++)
+        {
+            const DevJoint& j = r.joints[idx];
+            if (j.type == UPC_JOINT_FIXED) continue;
+            const int a = j.active;
+            const double sensed = enforce_limits(j, q[a] + draws[a]); /* :1784-1806 */
+            const double err = signed_distance(j, sensed, target[a]);
+            u[a] = actuator_clamp(r.axis[a], pid_step(r.axis[a], pid_i[a], pid_e[a], err, dt));
+        }
+    }
+    UPC_D void apply(const DevRobot& r, const double* in, const double* draws) /* :1882-1940 */
+    {
+        for (int idx = 0; idx < r.num_joints; idx++)
+        {
+            const DevJoint& j = r.joints[idx];
+            if (j.type == UPC_JOINT_FIXED) continue;
+            const int a = j.active;
+            const double n = draws ? actuator_noisy(r.axis[a], in[a], draws[a]) : actuator_clamp(r.axis[a], in[a]);
+            q[a] = enforce_limits(j, q[a] + n);
+        }
+    }
+    /* :2011-2084 using the frames computed by the last fk() into `frames` */
+    UPC_D void jacobian(const DevRobot& r, int link, const double*, const double* world, double (&J)[3][DOF]) const
+    {
+        for (int rr = 0; rr < 3; rr++)
+            for (int a = 0; a < r.dof; a++) J[rr][a] = 0.0;
+        int current = link;
+        while (current > 0)
+        {
+            const DevJoint& j = r.joints[r.parent_joint_of_link[current]];
+            const double* Tc = frames + j.child * 12;
+            if ((j.type == UPC_JOINT_REVOLUTE) || (j.type == UPC_JOINT_CONTINUOUS))
+            {
+                double aw[3];
+#pragma unroll
+                for (int rr = 0; rr < 3; rr++)
+                {
+                    aw[rr] = upc_fma(Tc[rr * 4 + 2], j.axis[2], upc_fma(Tc[rr * 4 + 1], j.axis[1], Tc[rr * 4 + 0] * j.axis[0]));
+                }
+                const double rel[3] = {world[0] - Tc[3], world[1] - Tc[7], world[2] - Tc[11]};
+                double c[3];
+                cross3(aw, rel, c);
+                J[0][j.active] = c[0]; J[1][j.active] = c[1]; J[2][j.active] = c[2];
+            }
+            else if (j.type == UPC_JOINT_PRISMATIC)
+            {
+                double aw[3];
+                xf_point(Tc, j.axis[0], j.axis[1], j.axis[2], aw); /* full isometry, :2064 */
+                J[0][j.active] = aw[0]; J[1][j.active] = aw[1]; J[2][j.active] = aw[2];
+            }
+            current = j.parent;
+        }
+    }
+};
+
+} /* namespace upc */
+
+#endif /* UPC_DEVICE_CUH */

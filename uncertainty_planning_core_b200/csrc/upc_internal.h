@@ -1,0 +1,86 @@
+/*
+ * upc_internal.h - host-side state behind the C ABI (include/upc_b200.h) and the launcher prototypes.
+ */
+#ifndef UPC_INTERNAL_H
+#define UPC_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "upc_device.cuh"
+
+namespace upc
+{
+void set_error(const std::string& msg);
+
+struct DeviceBuffer
+{
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    /* grow-only scratch; contents are not preserved */
+    cudaError_t reserve(size_t want);
+    void release();
+};
+
+struct ClusterWorkspace
+{
+    DeviceBuffer features;     /* per-particle distance features */
+    DeviceBuffer adjacency;    /* bit matrix rows */
+    DeviceBuffer roots;        /* first-pass roots | final roots | rank scratch */
+    DeviceBuffer comp;         /* connected-component labels (exact path) */
+    DeviceBuffer flags;        /* per-row ok flags + per-set bad flags */
+    DeviceBuffer signatures;   /* convex-region signatures, point-major */
+    DeviceBuffer frames;       /* link frames for linked-robot signatures */
+    DeviceBuffer dist_matrix;  /* FP64 sub-matrices of non-clique components */
+    DeviceBuffer members;      /* member lists + offsets of those components */
+    DeviceBuffer link_scratch; /* per-member state of the complete-link kernel */
+    DeviceBuffer misc;
+};
+
+} /* namespace upc */
+
+struct upc_handle
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    upc::DevEnv env{};
+    upc::DevRobot robot{};
+    bool has_robot = false;
+    int lanes_override = 0;
+    int sm_count = 148;
+    float* d_sdf = nullptr;
+    uint32_t* d_seg = nullptr;
+    float* d_occ = nullptr;
+    double* d_points = nullptr;
+    upc::DevCounters* d_counters = nullptr; /* device-side running totals */
+    upc_stats stats{};
+    /* staging for the host-pointer entry points */
+    upc::DeviceBuffer st_starts, st_targets, st_tape, st_out, st_coll, st_labels, st_ncl;
+    upc::ClusterWorkspace cw;
+};
+
+namespace upc
+{
+/* launchers; all asynchronous on `stream`, return cudaGetLastError() */
+int choose_lanes(const upc_handle* h, int64_t n);
+cudaError_t launch_forward_simulate(upc_handle* h, const DevSim& sp, int64_t n, const double* starts, int64_t n_targets,
+                                    const double* targets, const double* tape, double* out_configs, uint8_t* out_collided,
+                                    cudaStream_t stream);
+cudaError_t launch_check_collision(upc_handle* h, const double* d_config, double threshold, int* d_out, cudaStream_t stream);
+int32_t run_cluster(upc_handle* h, const upc_cluster_params& cp, int64_t n_sets, int64_t set_size, const double* d_configs,
+                    int32_t* d_labels, int32_t* d_n_clusters, cudaStream_t stream);
+}
+
+#define UPC_CUDA_TRY(expr)                                                                    \
+    do                                                                                        \
+    {                                                                                         \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+        {                                                                                     \
+            upc::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));               \
+            return UPC_ERR_CUDA;                                                              \
+        }                                                                                     \
+    } while (0)
+
+#endif

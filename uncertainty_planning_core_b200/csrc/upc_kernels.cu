@@ -1,0 +1,210 @@
+/*
+ * upc_kernels.cu - forward-simulation + SDF-collision kernels for sm_100a.
+ *
+ * One launch advances every particle of a batch along its planner edge: the GPU replacement for the body of
+ * SimulatorInterface::ForwardSimulateRobots (simple_simulator_interface.hpp:623).
+ *
+ * Mapping: G lanes (1..32, a power of two) cooperate on one particle, 128 threads per CTA.  Body points live
+ * in shared memory; the SDF is read through the read-only path and stays L2-resident (8 MiB for 128^3,
+ * 64 MiB for 256^3 against 126 MB of L2); the noise tape is streamed once from HBM with particle-minor
+ * (coalesced) layout.  FP64 throughout, -fmad=false, explicit fma only where DESIGN.md says so.
+ */
+#include "upc_internal.h"
+#include "upc_sim.cuh"
+
+namespace upc
+{
+constexpr int kBlock = 128;
+
+struct SimArgs
+{
+    DevEnv env;
+    DevRobot robot;
+    DevSim sp;
+    int64_t n, n_targets;
+    const double* starts;
+    const double* targets;
+    const double* tape;
+    double* out_configs;
+    uint8_t* out_collided;
+    DevCounters* counters;
+};
+
+template <class M, int G>
+__global__ void __launch_bounds__(kBlock) forward_simulate_kernel(const __grid_constant__ SimArgs a)
+{
+    extern __shared__ double smem[];
+    __shared__ unsigned int s_cnt[4];
+    double* pts = smem;
+    const int npd = a.robot.num_points * 4;
+    for (int k = threadIdx.x; k < npd; k += kBlock) pts[k] = a.robot.pts[k];
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0u;
+    __syncthreads();
+
+    const int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    const int64_t i = t / G;
+    LocalCounters lc = {0u, 0u, 0u};
+    bool collided = false;
+    Group<G> g;
+    g.sub = (int)(threadIdx.x % G);
+    g.base = (int)((threadIdx.x & 31) - g.sub);
+    g.mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << g.base);
+    if (i < a.n)
+    {
+        double* frames0 = nullptr;
+        double* frames1 = nullptr;
+        if constexpr (M::HAS_FRAMES)
+        {
+            const int per = a.robot.num_links * 12;
+            double* fb = smem + npd + (size_t)(threadIdx.x / G) * (size_t)(2 * per);
+            frames0 = fb;
+            frames1 = fb + per;
+        }
+        simulate_particle<M, G>(a.env, a.robot, a.sp, g, i, a.n, a.starts, a.n_targets, a.targets, a.tape, a.out_configs,
+                                a.out_collided, pts, frames0, frames1, lc, collided);
+        if (g.sub == 0)
+        {
+            atomicAdd(&s_cnt[0], lc.particle_steps);
+            atomicAdd(&s_cnt[1], collided ? 1u : 0u);
+            atomicAdd(&s_cnt[2], lc.resolver_iterations);
+            atomicAdd(&s_cnt[3], lc.failed_resolves);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        atomicAdd(&a.counters->particle_steps, (unsigned long long)s_cnt[0]);
+        atomicAdd(&a.counters->collided, (unsigned long long)s_cnt[1]);
+        atomicAdd(&a.counters->resolver_iterations, (unsigned long long)s_cnt[2]);
+        atomicAdd(&a.counters->failed_resolves, (unsigned long long)s_cnt[3]);
+    }
+}
+
+template <class M, int G>
+static cudaError_t launch_sim_impl(const SimArgs& a, cudaStream_t stream)
+{
+    const int64_t threads = a.n * G;
+    const int64_t blocks = (threads + kBlock - 1) / kBlock;
+    size_t smem = (size_t)a.robot.num_points * 4 * sizeof(double);
+    if (M::HAS_FRAMES) smem += (size_t)(kBlock / G) * 2 * (size_t)a.robot.num_links * 12 * sizeof(double);
+    if (smem > 48 * 1024)
+    {
+        cudaError_t e = cudaFuncSetAttribute(forward_simulate_kernel<M, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    forward_simulate_kernel<M, G><<<(unsigned)blocks, kBlock, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+template <class M>
+static cudaError_t launch_sim_lanes(const SimArgs& a, int lanes, cudaStream_t stream)
+{
+    switch (lanes)
+    {
+        case 1: return launch_sim_impl<M, 1>(a, stream);
+        case 2: return launch_sim_impl<M, 2>(a, stream);
+        case 4: return launch_sim_impl<M, 4>(a, stream);
+        case 8: return launch_sim_impl<M, 8>(a, stream);
+        case 16: return launch_sim_impl<M, 16>(a, stream);
+        default: return launch_sim_impl<M, 32>(a, stream);
+    }
+}
+
+/* Built-in choice of lanes per particle: enough threads for about two full waves of the 148 SMs,
+ * never more lanes than a link has points to hand out. */
+int choose_lanes(const upc_handle* h, int64_t n)
+{
+    int lanes;
+    if (h->lanes_override > 0)
+    {
+        lanes = h->lanes_override;
+    }
+    else
+    {
+        const int64_t want_threads = (int64_t)h->sm_count * 2048;
+        lanes = 1;
+        while (lanes < 32 && n * lanes * 2 <= want_threads) lanes *= 2;
+        int max_pts = 1;
+        for (int l = 0; l < h->robot.num_links; l++)
+        {
+            const int c = h->robot.link_off[l + 1] - h->robot.link_off[l];
+            if (c > max_pts) max_pts = c;
+        }
+        while (lanes > 1 && lanes > max_pts) lanes /= 2;
+    }
+    if (h->robot.kind == UPC_ROBOT_LINKED && lanes < 4) lanes = 4; /* frame scratch is per particle in shared memory */
+    return lanes;
+}
+
+cudaError_t launch_forward_simulate(upc_handle* h, const DevSim& sp, int64_t n, const double* starts, int64_t n_targets,
+                                    const double* targets, const double* tape, double* out_configs, uint8_t* out_collided,
+                                    cudaStream_t stream)
+{
+    SimArgs a;
+    a.env = h->env;
+    a.robot = h->robot;
+    a.sp = sp;
+    a.n = n;
+    a.n_targets = n_targets;
+    a.starts = starts;
+    a.targets = targets;
+    a.tape = tape;
+    a.out_configs = out_configs;
+    a.out_collided = out_collided;
+    a.counters = h->d_counters;
+    const int lanes = choose_lanes(h, n);
+    switch (h->robot.kind)
+    {
+        case UPC_ROBOT_SE2: return launch_sim_lanes<Se2Model>(a, lanes, stream);
+        case UPC_ROBOT_SE3: return launch_sim_lanes<Se3Model>(a, lanes, stream);
+        default: return launch_sim_lanes<LinkedModel>(a, lanes < 4 ? 4 : lanes, stream);
+    }
+}
+
+/* ------------------------------------------------------------------ CheckConfigCollision (single configuration) */
+
+struct CheckArgs
+{
+    DevEnv env;
+    DevRobot robot;
+    const double* config;
+    double threshold;
+    int* out;
+};
+
+template <class M>
+__global__ void __launch_bounds__(32) check_collision_kernel(const __grid_constant__ CheckArgs a)
+{
+    extern __shared__ double smem[];
+    double* frames = smem;
+    Group<32> g;
+    g.sub = (int)threadIdx.x;
+    g.base = 0;
+    g.mask = 0xffffffffu;
+    M m;
+    if constexpr (M::HAS_FRAMES) m.frames = frames;
+    m.load(a.robot, a.config, 1, 0);
+    refresh_frames(a.robot, m, g);
+    const bool hit = check_collision<M, 32>(a.env, a.robot, m, g, a.robot.pts, a.threshold);
+    if (threadIdx.x == 0) *a.out = hit ? 1 : 0;
+}
+
+cudaError_t launch_check_collision(upc_handle* h, const double* d_config, double threshold, int* d_out, cudaStream_t stream)
+{
+    CheckArgs a;
+    a.env = h->env;
+    a.robot = h->robot;
+    a.config = d_config;
+    a.threshold = threshold;
+    a.out = d_out;
+    const size_t smem = (size_t)h->robot.num_links * 12 * sizeof(double);
+    switch (h->robot.kind)
+    {
+        case UPC_ROBOT_SE2: check_collision_kernel<Se2Model><<<1, 32, smem, stream>>>(a); break;
+        case UPC_ROBOT_SE3: check_collision_kernel<Se3Model><<<1, 32, smem, stream>>>(a); break;
+        default: check_collision_kernel<LinkedModel><<<1, 32, smem, stream>>>(a); break;
+    }
+    return cudaGetLastError();
+}
+
+} /* namespace upc */

@@ -1,0 +1,378 @@
+/*
+ * upc_sim.cuh - the per-particle forward-simulation program, shared by the CUDA kernel
+ * (G cooperating lanes per particle) and the CPU emulation used by tests (G = 1).
+ *
+ * Replaces the body of a concrete SimulatorInterface::ForwardSimulateRobots
+ * (include/uncertainty_planning_core/simple_simulator_interface.hpp:623; per-step building blocks at
+ * simple_robot_models.hpp:239-259, 282-295 etc.).
+ *
+ * Lane cooperation: every lane of a group holds an identical copy of the particle state and executes the
+ * state update redundantly (a warp instruction costs the same for 1 or 32 active lanes); the body points of
+ * each link are dealt round-robin to the lanes, which is where the SDF gathers - the dominant cost - are
+ * parallelised.  Reductions over points are either order-free (any / max) or replayed in ascending point
+ * order by every lane from ballot masks and shuffles, so results do not depend on G and equal the
+ * sequential oracle bit for bit.
+ */
+#ifndef UPC_SIM_CUH
+#define UPC_SIM_CUH
+
+#include "upc_device.cuh"
+
+namespace upc
+{
+template <int G>
+struct Group
+{
+    unsigned mask; /* lanes of this group inside the warp */
+    int base;      /* first lane of the group */
+    int sub;       /* this lane's rank in the group */
+
+    UPC_D bool any(bool p) const
+    {
+#if defined(__CUDA_ARCH__)
+        if (G > 1) return (__ballot_sync(mask, p) & mask) != 0u;
+#endif
+        return p;
+    }
+    /* group-relative ballot: bit k = predicate of lane k of the group */
+    UPC_D unsigned ballot(bool p) const
+    {
+#if defined(__CUDA_ARCH__)
+        if (G > 1) return (__ballot_sync(mask, p) & mask) >> base;
+#endif
+        return p ? 1u : 0u;
+    }
+    UPC_D double bcast(double v, int src) const
+    {
+#if defined(__CUDA_ARCH__)
+        if (G > 1) return __shfl_sync(mask, v, base + src);
+#endif
+        (void)src;
+        return v;
+    }
+    UPC_D double max(double v) const
+    {
+#if defined(__CUDA_ARCH__)
+        if (G > 1)
+        {
+#pragma unroll
+            for (int off = G / 2; off > 0; off >>= 1)
+            {
+                const double o = __shfl_xor_sync(mask, v, off);
+                v = upc_max(v, o);
+            }
+        }
+#endif
+        return v;
+    }
+    UPC_D void sync() const
+    {
+#if defined(__CUDA_ARCH__)
+        if (G > 1) __syncwarp(mask);
+#endif
+    }
+};
+
+struct LocalCounters
+{
+    unsigned int particle_steps, resolver_iterations, failed_resolves;
+};
+
+/* recompute cached link frames after a configuration change (linked robots only) */
+template <class M, int G>
+UPC_D void refresh_frames(const DevRobot& r, M& m, const Group<G>& g)
+{
+    if constexpr (M::HAS_FRAMES)
+    {
+        g.sync();
+        if (g.sub == 0) m.fk(r, m.frames);
+        g.sync();
+    }
+}
+
+template <class M, int G>
+UPC_D bool check_collision(const DevEnv& env, const DevRobot& r, const M& m, const Group<G>& g, const double* pts, double threshold)
+{
+    bool hit = false;
+    for (int l = 0; l < r.num_links; l++)
+    {
+        const int beg = r.link_off[l], end = r.link_off[l + 1];
+        if (beg == end) continue;
+        double T[12], V[12];
+        m.frame(r, l, T);
+        voxel_from_link(env, T, V);
+        for (int k = beg + g.sub; k < end; k += G)
+        {
+            double u[3];
+            xf_point(V, pts[4 * k + 0], pts[4 * k + 1], pts[4 * k + 2], u);
+            const double d = sdf_distance(env, u);
+            hit = hit || ((d - pts[4 * k + 3]) < threshold);
+        }
+    }
+    return g.any(hit);
+}
+
+/* EstimateMaxControlInputWorkspaceMotion: largest body-point displacement caused by a noise-free input */
+template <class M, int G>
+UPC_D double estimate_motion(const DevRobot& r, const M& m, const Group<G>& g, const double* pts, const double* input, double* scratch_frames)
+{
+    M moved = m;
+    if constexpr (M::HAS_FRAMES) moved.frames = scratch_frames;
+    moved.apply(r, input, nullptr);
+    refresh_frames(r, moved, g);
+    double max_sq = 0.0;
+    for (int l = 0; l < r.num_links; l++)
+    {
+        const int beg = r.link_off[l], end = r.link_off[l + 1];
+        if (beg == end) continue;
+        double Ta[12], Tb[12];
+        m.frame(r, l, Ta);
+        moved.frame(r, l, Tb);
+#pragma unroll
+        for (int k = 0; k < 12; k++) Tb[k] = Tb[k] - Ta[k];
+        for (int k = beg + g.sub; k < end; k += G)
+        {
+            double disp[3];
+            xf_point(Tb, pts[4 * k + 0], pts[4 * k + 1], pts[4 * k + 2], disp);
+            max_sq = upc_max(max_sq, dot3(disp, disp));
+        }
+    }
+    max_sq = g.max(max_sq);
+    return sqrt(max_sq);
+}
+
+/* one resolver pass: raw correction step x from the body points closer than resolve_distance. Returns #contributing points. */
+template <class M, int G>
+UPC_D int resolver_correction(const DevEnv& env, const DevRobot& r, const DevSim& sp, const M& m, const Group<G>& g,
+                              const double* pts, double* x)
+{
+    constexpr int N = M::DOF;
+    const int n = m.dof(r);
+    double H[N][N];
+    double gv[N], xs[N];
+#pragma unroll
+    for (int a = 0; a < N; a++)
+    {
+        gv[a] = 0.0; xs[a] = 0.0;
+#pragma unroll
+        for (int b = 0; b < N; b++) H[a][b] = 0.0;
+    }
+    int count = 0;
+    for (int l = 0; l < r.num_links; l++)
+    {
+        const int beg = r.link_off[l], end = r.link_off[l + 1];
+        if (beg == end) continue;
+        double T[12], V[12];
+        m.frame(r, l, T);
+        voxel_from_link(env, T, V);
+        for (int k0 = beg; k0 < end; k0 += G)
+        {
+            const int k = k0 + g.sub;
+            bool contrib = false;
+            double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+            if (k < end)
+            {
+                double u[3], grad[3];
+                xf_point(V, pts[4 * k + 0], pts[4 * k + 1], pts[4 * k + 2], u);
+                const double d = sdf_distance_gradient(env, u, grad);
+                const double de = d - pts[4 * k + 3];
+                if (de < sp.resolve_distance)
+                {
+                    const double gn2 = dot3(grad, grad);
+                    if (gn2 > 1.0e-24)
+                    {
+                        const double gn = sqrt(gn2);
+                        const double pen = sp.resolve_distance - de;
+                        c0 = (grad[0] / gn) * pen;
+                        c1 = (grad[1] / gn) * pen;
+                        c2 = (grad[2] / gn) * pen;
+                        contrib = true;
+                    }
+                }
+            }
+            unsigned todo = g.ballot(contrib);
+            while (todo)
+            {
+#if defined(__CUDA_ARCH__)
+                const int src = __ffs((int)todo) - 1;
+#else
+                const int src = 0;
+#endif
+                todo &= todo - 1u;
+                const double b0 = g.bcast(c0, src), b1 = g.bcast(c1, src), b2 = g.bcast(c2, src);
+                const int kk = k0 + src;
+                const double local[3] = {pts[4 * kk + 0], pts[4 * kk + 1], pts[4 * kk + 2]};
+                double world[3];
+                xf_point(T, local[0], local[1], local[2], world);
+                double J[3][N];
+                m.jacobian(r, l, local, world, J);
+                count++;
+                if (sp.individual_jacobians)
+                {
+                    double A[3][3];
+#pragma unroll
+                    for (int rr = 0; rr < 3; rr++)
+#pragma unroll
+                        for (int qq = 0; qq < 3; qq++)
+                        {
+                            double s = 0.0;
+#pragma unroll
+                            for (int a = 0; a < N; a++)
+                                if (a < n) s = upc_fma(J[rr][a], J[qq][a], s);
+                            A[rr][qq] = s;
+                        }
+                    const double cv[3] = {b0, b1, b2};
+                    double yv[3];
+                    solve_damped<3>(A, cv, sp.damping, yv, 3);
+#pragma unroll
+                    for (int a = 0; a < N; a++)
+                        if (a < n) xs[a] = upc_fma(J[2][a], yv[2], upc_fma(J[1][a], yv[1], upc_fma(J[0][a], yv[0], xs[a])));
+                }
+                else
+                {
+#pragma unroll
+                    for (int a = 0; a < N; a++)
+                    {
+                        if (a < n)
+                        {
+#pragma unroll
+                            for (int b = 0; b < N; b++)
+                            {
+                                if (b >= a && b < n)
+                                    H[a][b] = upc_fma(J[2][a], J[2][b], upc_fma(J[1][a], J[1][b], upc_fma(J[0][a], J[0][b], H[a][b])));
+                            }
+                            gv[a] = upc_fma(J[2][a], b2, upc_fma(J[1][a], b1, upc_fma(J[0][a], b0, gv[a])));
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (count == 0) return 0;
+    if (sp.individual_jacobians)
+    {
+        const double inv = 1.0 / (double)count;
+#pragma unroll
+        for (int a = 0; a < N; a++)
+            if (a < n) x[a] = xs[a] * inv;
+    }
+    else
+    {
+        solve_damped<N>(H, gv, sp.damping, x, n);
+    }
+    return count;
+}
+
+/*
+ * Simulate particle i for one planner edge. `pts` are the robot's body points (shared memory on the GPU),
+ * frames0/frames1 are per-particle scratch for link transforms (linked robots only).
+ * Writes the final configuration and the collided flag from lane 0 of the group.
+ */
+template <class M, int G>
+UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim& sp, const Group<G>& g, int64_t i, int64_t n,
+                             const double* starts, int64_t n_targets, const double* targets, const double* tape,
+                             double* out_configs, uint8_t* out_collided, const double* pts, double* frames0,
+                             double* frames1, LocalCounters& cnt, bool& collided_out)
+{
+    constexpr int N = M::DOF;
+    const int dof = r.dof;
+    M m;
+    if constexpr (M::HAS_FRAMES) m.frames = frames0;
+    m.load(r, starts, n, i);
+    m.reset_controllers();
+    refresh_frames(r, m, g);
+    double target[M::WIDTH];
+    {
+        const int64_t ti = (n_targets == 1) ? 0 : i;
+        const int width = (M::HAS_FRAMES) ? dof : M::WIDTH;
+#pragma unroll
+        for (int c = 0; c < M::WIDTH; c++)
+            if (c < width) target[c] = targets[(int64_t)c * n_targets + ti];
+    }
+    const int slots = 1 + sp.max_microsteps;
+    bool collided = false;
+    for (int step = 0; step < sp.num_steps; step++)
+    {
+        cnt.particle_steps++;
+        double draws[N];
+#pragma unroll
+        for (int d = 0; d < N; d++)
+            if (d < dof) draws[d] = tape[(((int64_t)step * slots) * dof + d) * n + i];
+        double u[N];
+        m.control(r, target, sp.dt, draws, u);
+        double real[N];
+#pragma unroll
+        for (int d = 0; d < N; d++)
+            if (d < dof) real[d] = u[d] * sp.dt;
+        const double motion = estimate_motion(r, m, g, pts, real, frames1);
+        unsigned microsteps = (unsigned)ceil(motion / sp.microstep_distance);
+        if (microsteps < 1u) microsteps = 1u;
+        if (microsteps > (unsigned)sp.max_microsteps) microsteps = (unsigned)sp.max_microsteps;
+        const double inv_micro = 1.0 / (double)microsteps;
+        double ustep[N];
+#pragma unroll
+        for (int d = 0; d < N; d++)
+            if (d < dof) ustep[d] = real[d] * inv_micro;
+        for (unsigned ms = 0; ms < microsteps; ms++)
+        {
+            double previous[M::WIDTH];
+            m.get(r, previous);
+#pragma unroll
+            for (int d = 0; d < N; d++)
+                if (d < dof) draws[d] = tape[(((int64_t)step * slots + 1 + ms) * dof + d) * n + i];
+            m.apply(r, ustep, draws);
+            refresh_frames(r, m, g);
+            bool in_collision = check_collision(env, r, m, g, pts, sp.contact_distance);
+            if (in_collision) collided = true;
+            if (in_collision && sp.allow_contacts)
+            {
+                int iterations = 0;
+                double scaling = sp.initial_scale;
+                while (in_collision)
+                {
+                    double raw[N];
+                    const int contributing = resolver_correction(env, r, sp, m, g, pts, raw);
+                    if (contributing == 0) break;
+                    const double est = estimate_motion(r, m, g, pts, raw, frames1);
+                    const double limit_scale = (est > sp.microstep_distance) ? (sp.microstep_distance / est) : 1.0;
+                    const double total_scale = limit_scale * fabs(scaling);
+                    double corr[N];
+#pragma unroll
+                    for (int d = 0; d < N; d++)
+                        if (d < dof) corr[d] = raw[d] * total_scale;
+                    m.apply(r, corr, nullptr);
+                    refresh_frames(r, m, g);
+                    in_collision = check_collision(env, r, m, g, pts, sp.contact_distance);
+                    iterations++;
+                    cnt.resolver_iterations++;
+                    if (iterations >= sp.max_resolver_iterations) break;
+                    if ((iterations % sp.decay_iterations) == 0) scaling = scaling * sp.decay_rate;
+                }
+                if (in_collision)
+                {
+                    m.set(r, previous);
+                    refresh_frames(r, m, g);
+                    cnt.failed_resolves++;
+                    break;
+                }
+            }
+            else if (in_collision)
+            {
+                m.set(r, previous);
+                refresh_frames(r, m, g);
+                break;
+            }
+        }
+        if (m.distance_to(r, target) < sp.shortcut) break;
+    }
+    if (g.sub == 0)
+    {
+        m.store(r, out_configs, n, i);
+        out_collided[i] = collided ? 1 : 0;
+    }
+    collided_out = collided;
+}
+
+} /* namespace upc */
+
+#endif /* UPC_SIM_CUH */

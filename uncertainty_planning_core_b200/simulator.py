@@ -1,0 +1,160 @@
+"""Host-side mirror of the reference's plugin interfaces over the C ABI.
+
+B200Simulator mirrors simple_simulator_interface::SimulatorInterface
+(include/uncertainty_planning_core/simple_simulator_interface.hpp:383-624): same method names, argument
+meaning and error behaviour (ValueError where the reference throws std::invalid_argument).
+OutcomeClustering mirrors UncertaintyPlanningSpace::ClusterParticles / PolicyParticleClusteringFn
+(uncertainty_contact_planning.hpp:1986-2034, :1558-1578).
+
+Configurations are numpy arrays [n, C] on this side (one row per particle, C = 3 for SE2 (x, y, theta),
+12 for SE3 (R row-major then t), dof for linked robots) and are transposed to the ABI's [C][n] layout here.
+The production host shim is the C++ header include/upc_b200_shim.hpp; this Python mirror exists for the
+parity tests and the benchmark.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+
+
+class B200Simulator:
+    def __init__(self, environment, robot, debug_level=0, device=0):
+        self._lib = abi.load_library()
+        self.environment = environment
+        self.robot = robot
+        self.debug_level = debug_level
+        self._h = C.c_void_p()
+        abi.check(self._lib.upc_create(C.byref(environment.desc), device, C.byref(self._h)))
+        abi.check(self._lib.upc_set_robot(self._h, C.byref(robot.desc)))
+
+    # -- life cycle -------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.upc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def SetLanesPerParticle(self, lanes):
+        abi.check(self._lib.upc_set_lanes_per_particle(self._h, lanes))
+
+    # -- SimulatorInterface ---------------------------------------------------------------------------------
+    def GetStatistics(self):
+        s = abi.Stats()
+        abi.check(self._lib.upc_get_stats(self._h, C.byref(s)))
+        return {k: float(v) for k, v in s.as_dict().items()}
+
+    def ResetStatistics(self):
+        abi.check(self._lib.upc_reset_stats(self._h))
+
+    def GetResolution(self):
+        return self.environment.resolution
+
+    def CheckConfigCollision(self, config, inflation_ratio=0.0, contact_distance=0.0):
+        cfg = np.ascontiguousarray(config, dtype=np.float64).reshape(-1)
+        if cfg.shape[0] != self.robot.width:
+            raise ValueError("configuration has %d values, robot needs %d" % (cfg.shape[0], self.robot.width))
+        out = C.c_int32(0)
+        inflation = inflation_ratio * self.environment.resolution
+        abi.check(self._lib.upc_check_config_collision(self._h, cfg.ctypes.data, contact_distance, inflation, C.byref(out)))
+        return bool(out.value)
+
+    def ForwardSimulateRobots(self, start_positions, target_positions, noise_tape, params):
+        """Batched forward simulation.  Returns (configs [n, C], collided [n] bool).
+
+        start_positions [n, C]; target_positions [1, C] or [n, C]; noise_tape
+        [num_steps, 1 + max_microsteps, dof, n] (abi.fill_noise_tape or the caller's own draws);
+        params: abi.SimParams carrying forward_simulation_time (as num_steps * controller_interval),
+        simulation_shortcut_distance, use_individual_jacobians and allow_contacts.
+        """
+        starts = np.asarray(start_positions, dtype=np.float64)
+        targets = np.asarray(target_positions, dtype=np.float64)
+        if starts.ndim != 2 or starts.shape[1] != self.robot.width:
+            raise ValueError("start_positions must be [n, %d]" % self.robot.width)
+        n = starts.shape[0]
+        if targets.ndim != 2 or targets.shape[1] != self.robot.width or targets.shape[0] not in (1, n):
+            raise ValueError("target_positions must have size 1 or size start_positions.size()")
+        tape = np.ascontiguousarray(noise_tape, dtype=np.float64)
+        if tape.shape != abi.tape_shape(params, self.robot.dof, n):
+            raise ValueError("noise tape has shape %s, expected %s" % (tape.shape, abi.tape_shape(params, self.robot.dof, n)))
+        starts_soa = np.ascontiguousarray(starts.T)
+        targets_soa = np.ascontiguousarray(targets.T)
+        out = np.zeros_like(starts_soa)
+        collided = np.zeros(n, dtype=np.uint8)
+        abi.check(self._lib.upc_forward_simulate(self._h, C.byref(params), n, starts_soa.ctypes.data, targets.shape[0],
+                                                 targets_soa.ctypes.data, tape.ctypes.data, out.ctypes.data,
+                                                 collided.ctypes.data))
+        return np.ascontiguousarray(out.T), collided.astype(bool)
+
+    def ForwardSimulateRobot(self, start_position, target_position, noise_tape, params):
+        cfg, coll = self.ForwardSimulateRobots(np.asarray(start_position, dtype=np.float64).reshape(1, -1),
+                                               np.asarray(target_position, dtype=np.float64).reshape(1, -1),
+                                               noise_tape, params)
+        return cfg[0], bool(coll[0])
+
+
+class OutcomeClustering:
+    """ClusterParticles / PolicyParticleClusteringFn over a B200Simulator's handle."""
+
+    def __init__(self, simulator, clustering_type=abi.FEATURE_CRS, signature_matching_threshold=0.125,
+                 distance_clustering_threshold=0.1):
+        self.sim = simulator
+        self._lib = simulator._lib
+        self.params = abi.ClusterParams()
+        self.params.feature_type = clustering_type
+        self.params.signature_matching_threshold = signature_matching_threshold
+        self.params.distance_clustering_threshold = distance_clustering_threshold
+
+    def ClusterIndices(self, configs, n_sets=1):
+        """Index clustering of n_sets equally sized particle sets stacked in configs [n_sets*set_size, C].
+        Returns (labels [total] int32, n_clusters [n_sets] int32)."""
+        cfg = np.asarray(configs, dtype=np.float64)
+        if cfg.ndim != 2 or cfg.shape[1] != self.sim.robot.width:
+            raise ValueError("configs must be [n, %d]" % self.sim.robot.width)
+        total = cfg.shape[0]
+        if n_sets < 1 or total % n_sets:
+            raise ValueError("configs must hold n_sets equally sized sets")
+        set_size = total // n_sets
+        soa = np.ascontiguousarray(cfg.T)
+        labels = np.zeros(total, dtype=np.int32)
+        ncl = np.zeros(n_sets, dtype=np.int32)
+        abi.check(self._lib.upc_cluster_particles(self.sim.handle, C.byref(self.params), n_sets, set_size,
+                                                  soa.ctypes.data, labels.ctypes.data, ncl.ctypes.data))
+        return labels, ncl
+
+    def ClusterParticles(self, particles, allow_contacts):
+        """particles: (configs [n, C], collided [n] bool).  Returns a list of clusters, each a
+        (configs, collided) pair; collided particles are dropped from the clusters when contacts are not
+        allowed, and clusters emptied that way are still emitted (uncertainty_contact_planning.hpp:2008-2026)."""
+        configs, collided = particles
+        configs = np.asarray(configs, dtype=np.float64)
+        collided = np.asarray(collided, dtype=bool)
+        n = configs.shape[0]
+        if n == 0:
+            return []
+        if n == 1:
+            return [(configs.copy(), collided.copy())]
+        labels, ncl = self.ClusterIndices(configs)
+        clusters = []
+        for k in range(int(ncl[0])):
+            keep = (labels == k) & (allow_contacts | ~collided)
+            clusters.append((configs[keep], collided[keep]))
+        return clusters
+
+    def PolicyParticleClusteringFn(self, particles, current_config):
+        """Index clusters of (particles + [current_config]) as lists of indices (:1558-1578)."""
+        allp = np.concatenate([np.asarray(particles, dtype=np.float64),
+                               np.asarray(current_config, dtype=np.float64).reshape(1, -1)], axis=0)
+        if allp.shape[0] == 1:
+            return [[0]]
+        labels, ncl = self.ClusterIndices(allp)
+        return [np.nonzero(labels == k)[0].tolist() for k in range(int(ncl[0]))]
