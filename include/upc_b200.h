@@ -228,6 +228,11 @@ int32_t upc_cluster_particles_device(upc_handle* h, const upc_cluster_params* pa
 int32_t upc_fill_noise_tape(uint64_t seed, const upc_robot_desc* robot, const upc_sim_params* params, int64_t first_particle,
                             int64_t n, int64_t tape_stride, double* tape);
 
+/* Roofline denominators measured on the device the handle lives on (diagnostics, not on the hot path):
+ * random 32-byte-sector gather bandwidth over a buffer of `buffer_bytes` (L2-resident when it fits), and the FP64 FMA rate. */
+int32_t upc_measure_l2_gather_gbs(upc_handle* h, int64_t buffer_bytes, double* out_gbs);
+int32_t upc_measure_fp64_tflops(upc_handle* h, double* out_tflops);
+
 /* blocks until everything queued on the handle's stream has finished */
 int32_t upc_synchronize(upc_handle* h);
 

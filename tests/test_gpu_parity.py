@@ -1,0 +1,227 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded
+inputs and against the committed golden fixtures.
+
+Stated bar: collision flags, solver counters and cluster labels bit-exact; configurations within 0 ulp
+(FP64 everywhere, nvcc -fmad=false vs g++ -ffp-contract=off, shared elementary functions)."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from common import canonical_partition, max_ulp_diff
+from uncertainty_planning_core_b200 import abi, scenarios
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+CONFIG_ULP_TOLERANCE = 0
+
+
+@pytest.fixture(scope="module")
+def simulators():
+    from uncertainty_planning_core_b200 import B200Simulator
+    cache = {}
+
+    def get(key, env, robot):
+        if key not in cache:
+            cache[key] = B200Simulator(env, robot)
+        return cache[key]
+    yield get
+    for s in cache.values():
+        s.close()
+
+
+@pytest.mark.parametrize("name", sorted(cases.GOLDEN_SIM_CASES))
+def test_forward_simulation_matches_oracle_for_every_lane_count(oracle, simulators, name):
+    sc = cases.GOLDEN_SIM_CASES[name]()
+    n = sc["starts"].shape[0]
+    tape = abi.fill_noise_tape(sc["seed"], sc["robot"], sc["params"], n)
+    ocfg, ocoll, ostats = oracle.forward_simulate(sc["env"], sc["robot"], sc["params"], sc["starts"], sc["targets"], tape)
+    g = np.load(os.path.join(HERE, "golden", "sim_%s.npz" % name))
+    assert np.array_equal(ocfg, g["configs"]) and np.array_equal(ocoll, g["collided"])
+    sim = simulators(name, sc["env"], sc["robot"])
+    for lanes in (0, 1, 2, 4, 8, 16, 32):
+        if sc["robot"].kind == abi.ROBOT_LINKED and lanes in (1, 2):
+            continue
+        sim.SetLanesPerParticle(lanes)
+        sim.ResetStatistics()
+        cfg, coll = sim.ForwardSimulateRobots(sc["starts"], sc["targets"], tape, sc["params"])
+        assert np.array_equal(coll, ocoll), (name, lanes)
+        assert max_ulp_diff(cfg, ocfg) <= CONFIG_ULP_TOLERANCE, (name, lanes, np.abs(cfg - ocfg).max())
+        stats = sim.GetStatistics()
+        for k in cases.SIM_STAT_KEYS:
+            assert int(stats[k]) == ostats[k], (name, lanes, k)
+        assert int(stats["particles_simulated"]) == n and stats["kernel_launches"] >= 1
+    sim.SetLanesPerParticle(0)
+
+
+@pytest.mark.parametrize("name", sorted(cases.GOLDEN_CLUSTER_CASES))
+def test_clustering_matches_oracle(oracle, simulators, name):
+    from uncertainty_planning_core_b200 import OutcomeClustering
+    c = cases.GOLDEN_CLUSTER_CASES[name]()
+    n_sets = c.get("n_sets", 1)
+    olabels, oncl, ostats = oracle.cluster_particles(c["env"], c["robot"], c["cparams"], c["configs"], n_sets)
+    g = np.load(os.path.join(HERE, "golden", "cluster_%s.npz" % name))
+    assert np.array_equal(olabels, g["labels"]) and np.array_equal(oncl, g["n_clusters"])
+    sim = simulators("cl_" + name, c["env"], c["robot"])
+    oc = OutcomeClustering(sim, c["cparams"].feature_type, c["cparams"].signature_matching_threshold,
+                           c["cparams"].distance_clustering_threshold)
+    labels, ncl = oc.ClusterIndices(c["configs"], n_sets)
+    assert np.array_equal(ncl, oncl), name
+    assert np.array_equal(labels, olabels), name
+
+
+def test_cluster_particles_assembly_and_edge_cases(oracle, simulators):
+    from uncertainty_planning_core_b200 import OutcomeClustering
+    c = cases.cl_se2_blobs()
+    sim = simulators("cl_edge", c["env"], c["robot"])
+    oc = OutcomeClustering(sim, abi.FEATURE_NONE, 0.125, 0.1)
+    cfg = c["configs"]
+    collided = np.zeros(len(cfg), dtype=bool)
+    collided[::3] = True
+    assert oc.ClusterParticles((cfg[:0], collided[:0]), True) == []
+    one = oc.ClusterParticles((cfg[:1], collided[:1]), False)
+    assert len(one) == 1 and len(one[0][0]) == 1            # a single particle is returned as is, collided or not
+    with_contacts = oc.ClusterParticles((cfg, collided), True)
+    without = oc.ClusterParticles((cfg, collided), False)
+    assert len(with_contacts) == len(without) == 5
+    assert sum(len(k[0]) for k in with_contacts) == len(cfg)
+    assert sum(len(k[0]) for k in without) == int((~collided).sum())
+    # all members collided: the cluster is emitted empty (uncertainty_contact_planning.hpp:2025)
+    labels, _ = oc.ClusterIndices(cfg)
+    coll2 = labels == 2
+    emptied = oc.ClusterParticles((cfg, coll2), False)
+    assert len(emptied) == 5 and len(emptied[2][0]) == 0
+    # PolicyParticleClusteringFn: the current configuration joins as the last index
+    idx = oc.PolicyParticleClusteringFn(cfg[:40], cfg[41])
+    assert sorted(i for grp in idx for i in grp) == list(range(41))
+    # two-particle and size-one sets in a batch
+    labels, ncl = oc.ClusterIndices(cfg[:6], n_sets=6)
+    assert labels.tolist() == [0] * 6 and ncl.tolist() == [1] * 6
+    far = np.array([[1.0, 1.0, 0.0], [3.0, 1.0, 0.0]])
+    labels, ncl = oc.ClusterIndices(far)
+    assert labels.tolist() == [0, 1] and ncl.tolist() == [2]
+
+
+def test_check_config_collision_matches_oracle(oracle, simulators):
+    for make in (cases.se2_contact, cases.se3_contact, cases.linked_contact):
+        sc = make()
+        sim = simulators("chk_" + sc["name"], sc["env"], sc["robot"])
+        rng = np.random.default_rng(3)
+        hits = 0
+        for i in range(40):
+            cfg = sc["starts"][0] + (sc["targets"][0] - sc["starts"][0]) * rng.uniform(0, 1.6)
+            if sc["robot"].kind == abi.ROBOT_SE3:
+                cfg[:9] = sc["starts"][0][:9]
+            want = oracle.check_config_collision(sc["env"], sc["robot"], cfg, 0.0, 0.0)
+            assert sim.CheckConfigCollision(cfg) == want
+            infl = oracle.check_config_collision(sc["env"], sc["robot"], cfg, 0.0, 2.0 * sc["env"].resolution)
+            assert sim.CheckConfigCollision(cfg, inflation_ratio=2.0) == infl
+            hits += int(want)
+        assert 0 < hits < 40
+
+
+def test_device_pointer_entry_points_on_the_torch_stream(oracle, simulators):
+    import ctypes as C
+    import torch
+    sc = cases.se3_contact()
+    n = sc["starts"].shape[0]
+    tape = abi.fill_noise_tape(sc["seed"], sc["robot"], sc["params"], n)
+    ocfg, ocoll, _ = oracle.forward_simulate(sc["env"], sc["robot"], sc["params"], sc["starts"], sc["targets"], tape)
+    sim = simulators("dev_ptr", sc["env"], sc["robot"])
+    dev = torch.device("cuda:0")
+    d_starts = torch.from_numpy(np.ascontiguousarray(sc["starts"].T)).to(dev)
+    d_targets = torch.from_numpy(np.ascontiguousarray(sc["targets"].T)).to(dev)
+    d_tape = torch.from_numpy(tape).to(dev)
+    d_out = torch.zeros_like(d_starts)
+    d_coll = torch.zeros(n, dtype=torch.uint8, device=dev)
+    lib = abi.load_library()
+    stream = torch.cuda.current_stream().cuda_stream
+    abi.check(lib.upc_forward_simulate_device(sim.handle, C.byref(sc["params"]), n, d_starts.data_ptr(), 1, d_targets.data_ptr(),
+                                              d_tape.data_ptr(), d_out.data_ptr(), d_coll.data_ptr(), stream))
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy().T, ocfg) and np.array_equal(d_coll.cpu().numpy().astype(bool), ocoll)
+    cp = cases._cparams(abi.FEATURE_CRS, 0.125, 0.05)
+    d_labels = torch.zeros(n, dtype=torch.int32, device=dev)
+    d_ncl = torch.zeros(1, dtype=torch.int32, device=dev)
+    abi.check(lib.upc_cluster_particles_device(sim.handle, C.byref(cp), 1, n, d_out.data_ptr(), d_labels.data_ptr(), d_ncl.data_ptr(), stream))
+    torch.cuda.synchronize()
+    olabels, oncl, _ = oracle.cluster_particles(sc["env"], sc["robot"], cp, ocfg)
+    assert np.array_equal(d_labels.cpu().numpy(), olabels) and int(d_ncl.item()) == int(oncl[0])
+
+
+def test_errors_mirror_the_reference_interface(simulators):
+    sc = cases.se2_contact()
+    sim = simulators("errs", sc["env"], sc["robot"])
+    tape = abi.fill_noise_tape(1, sc["robot"], sc["params"], 96)
+    with pytest.raises(ValueError):
+        sim.ForwardSimulateRobots(sc["starts"], np.zeros((5, 3)), tape, sc["params"])      # targets neither 1 nor n
+    with pytest.raises(ValueError):
+        sim.ForwardSimulateRobots(sc["starts"][:, :2], sc["targets"], tape, sc["params"])
+    with pytest.raises(ValueError):
+        sim.ForwardSimulateRobots(sc["starts"], sc["targets"], tape[:10], sc["params"])
+    bad = abi.make_sim_params(0, 0.01, 0.08)
+    with pytest.raises(ValueError):
+        sim.ForwardSimulateRobots(sc["starts"], sc["targets"], tape, bad)
+    from uncertainty_planning_core_b200 import OutcomeClustering
+    oc = OutcomeClustering(sim, abi.FEATURE_AC)
+    with pytest.raises(abi.UpcError):
+        oc.ClusterIndices(sc["starts"])
+    cfg, coll = sim.ForwardSimulateRobots(sc["starts"][:0], sc["targets"], tape[..., :0], sc["params"])  # empty batch
+    assert cfg.shape == (0, 3) and coll.shape == (0,)
+
+
+# ------------------------------------------------------------------ BASELINE.json sizes: size-independent properties
+
+def test_full_size_c2_properties(oracle, simulators):
+    """10,000 SE(3) particles / 128^3 SDF (BASELINE config 2): lane-count invariance, shard invariance,
+    oracle agreement on a subsample of the very same run, resolved contacts are collision free."""
+    sc = scenarios.c2_se3()
+    n = sc["starts"].shape[0]
+    tape = abi.fill_noise_tape(sc["seed"], sc["robot"], sc["params"], n)
+    sim = simulators("c2_full", sc["env"], sc["robot"])
+    results = {}
+    for lanes in (1, 8, 32):
+        sim.SetLanesPerParticle(lanes)
+        results[lanes] = sim.ForwardSimulateRobots(sc["starts"], sc["targets"], tape, sc["params"])
+    sim.SetLanesPerParticle(0)
+    for lanes in (8, 32):
+        assert np.array_equal(results[1][0], results[lanes][0]) and np.array_equal(results[1][1], results[lanes][1])
+    cfg, coll = results[1]
+    # particles are independent: any shard with its tape slice reproduces the full run
+    lo, hi = 3000, 3700
+    part_cfg, part_coll = sim.ForwardSimulateRobots(sc["starts"][lo:hi], sc["targets"], np.ascontiguousarray(tape[..., lo:hi]), sc["params"])
+    assert np.array_equal(part_cfg, cfg[lo:hi]) and np.array_equal(part_coll, coll[lo:hi])
+    # the oracle on a subsample of the same run
+    pick = np.arange(0, n, 97)
+    ocfg, ocoll, _ = oracle.forward_simulate(sc["env"], sc["robot"], sc["params"], sc["starts"][pick], sc["targets"], np.ascontiguousarray(tape[..., pick]))
+    assert np.array_equal(ocoll, coll[pick]) and max_ulp_diff(ocfg, cfg[pick]) <= CONFIG_ULP_TOLERANCE
+    assert coll.any()
+    for i in pick[:30]:
+        assert not sim.CheckConfigCollision(cfg[i])
+    R = cfg[:, :9].reshape(-1, 3, 3)
+    assert np.max(np.abs(R @ np.transpose(R, (0, 2, 1)) - np.eye(3))) < 1e-9
+
+
+def test_full_size_clustering_properties(oracle, simulators):
+    """16,384 particles: blobs come back as blobs, permuting the input permutes the partition, the single-blob
+    case takes the no-fallback path, and a 2,048-particle subsample agrees with the oracle."""
+    from uncertainty_planning_core_b200 import OutcomeClustering
+    for kind, case in ((abi.ROBOT_SE2, cases.cl_se2_blobs), (abi.ROBOT_SE3, cases.cl_se3_blobs), (abi.ROBOT_LINKED, cases.cl_linked_blobs)):
+        c = case()
+        sim = simulators("cl_full_%d" % kind, c["env"], c["robot"])
+        oc = OutcomeClustering(sim, abi.FEATURE_NONE, 0.125, 0.1)
+        n = 16384 if kind != abi.ROBOT_SE3 else 4096
+        cfg, owner = scenarios.c4_blobs(kind, n, k=8, seed=77)
+        sim.ResetStatistics()
+        labels, ncl = oc.ClusterIndices(cfg)
+        assert int(ncl[0]) == 8
+        assert canonical_partition(labels) == canonical_partition(owner)
+        assert sim.GetStatistics()["cluster_fallback_calls"] == 0
+        perm = np.random.default_rng(5).permutation(n)
+        plabels, _ = oc.ClusterIndices(cfg[perm])
+        assert canonical_partition(plabels) == canonical_partition(owner[perm])
+        sub = np.arange(0, n, n // 1024)[:1024]
+        olabels, oncl, _ = oracle.cluster_particles(c["env"], c["robot"], oc.params, cfg[sub])
+        slabels, sncl = oc.ClusterIndices(cfg[sub])
+        assert np.array_equal(olabels, slabels)

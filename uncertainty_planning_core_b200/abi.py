@@ -264,7 +264,9 @@ def load_library():
     lib.upc_cluster_particles.argtypes = [vp, C.POINTER(ClusterParams), i64, i64, vp, vp, vp]
     lib.upc_cluster_particles_device.argtypes = [vp, C.POINTER(ClusterParams), i64, i64, vp, vp, vp, vp]
     lib.upc_fill_noise_tape.argtypes = [C.c_uint64, C.POINTER(RobotDesc), C.POINTER(SimParams), i64, i64, i64, vp]
-    for name in ("upc_create", "upc_destroy", "upc_set_robot", "upc_get_stats", "upc_reset_stats",
+    lib.upc_measure_l2_gather_gbs.argtypes = [vp, i64, C.POINTER(dp)]
+    lib.upc_measure_fp64_tflops.argtypes = [vp, C.POINTER(dp)]
+    for name in ("upc_measure_l2_gather_gbs", "upc_measure_fp64_tflops", "upc_create", "upc_destroy", "upc_set_robot", "upc_get_stats", "upc_reset_stats",
                  "upc_set_lanes_per_particle", "upc_host_alloc", "upc_host_free", "upc_synchronize",
                  "upc_forward_simulate", "upc_forward_simulate_device", "upc_check_config_collision",
                  "upc_cluster_particles", "upc_cluster_particles_device", "upc_fill_noise_tape"):
@@ -277,7 +279,8 @@ EXPORTED_SYMBOLS = (
     "upc_config_width", "upc_tape_doubles_per_particle", "upc_last_error", "upc_version", "upc_create", "upc_destroy",
     "upc_set_robot", "upc_get_stats", "upc_reset_stats", "upc_set_lanes_per_particle", "upc_host_alloc", "upc_host_free",
     "upc_forward_simulate", "upc_forward_simulate_device", "upc_check_config_collision", "upc_cluster_particles",
-    "upc_cluster_particles_device", "upc_fill_noise_tape", "upc_synchronize",
+    "upc_cluster_particles_device", "upc_fill_noise_tape", "upc_synchronize", "upc_measure_l2_gather_gbs",
+    "upc_measure_fp64_tflops",
 )
 
 
