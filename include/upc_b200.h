@@ -198,7 +198,8 @@ int32_t upc_host_free(void* ptr);
 int32_t upc_forward_simulate(upc_handle* h, const upc_sim_params* params, int64_t n, const double* starts,
                              int64_t n_targets, const double* targets, const double* tape, double* out_configs,
                              uint8_t* out_collided);
-/* Device-pointer form: all buffers in device memory, asynchronous on stream (a cudaStream_t, or NULL for the handle's stream). */
+/* Device-pointer form: all buffers in device memory, asynchronous on `stream` (a cudaStream_t; NULL selects the handle's own
+ * non-blocking stream - pass cudaStreamLegacy (0x1) to name the legacy default stream explicitly). */
 int32_t upc_forward_simulate_device(upc_handle* h, const upc_sim_params* params, int64_t n, const double* d_starts,
                                     int64_t n_targets, const double* d_targets, const double* d_tape,
                                     double* d_out_configs, uint8_t* d_out_collided, void* stream);

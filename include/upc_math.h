@@ -21,8 +21,11 @@
 
 #if defined(__CUDACC__)
 #define UPC_HD __host__ __device__ __forceinline__
+/* larger leaf functions: one out-of-line copy per kernel keeps code size (instruction-cache pressure) and registers down */
+#define UPC_HD_CALL inline __host__ __device__ __noinline__
 #else
 #define UPC_HD inline
+#define UPC_HD_CALL inline
 #endif
 
 #define UPC_PI 3.14159265358979323846
@@ -85,7 +88,7 @@ UPC_HD double upc_kcos(double r)
 
 /* Simultaneous sine and cosine. Accurate (about 1 ulp) for |x| up to about 1e5; beyond that the two-term
  * Cody-Waite reduction degrades gracefully. Angles on this path are bounded by a few pi. */
-UPC_HD void upc_sincos(double x, double* s, double* c)
+UPC_HD_CALL void upc_sincos(double x, double* s, double* c)
 {
     const double TWO_OVER_PI = 6.36619772367581382433e-01;
     const double PIO2_HI = 1.57079632673412561417e+00; /* first 33 bits of pi/2 */
@@ -109,7 +112,7 @@ UPC_HD double upc_sin(double x) { double s, c; upc_sincos(x, &s, &c); return s; 
 UPC_HD double upc_cos(double x) { double s, c; upc_sincos(x, &s, &c); return c; }
 
 /* arctangent, four-interval argument reduction + odd/even split polynomial */
-UPC_HD double upc_atan(double xin)
+UPC_HD_CALL double upc_atan(double xin)
 {
     const double aT0 = 3.33333333333329318027e-01, aT1 = -1.99999999998764832476e-01,
                  aT2 = 1.42857142725034663711e-01, aT3 = -1.11111104054623557880e-01,

@@ -6,6 +6,7 @@ TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.
 import ctypes as C
 import os
 import subprocess
+import sys
 
 import numpy as np
 
@@ -20,9 +21,9 @@ def build(force=False):
     """Compile liboracle.so (and oracle/_ref when the reference tree is present)."""
     so = os.path.join(_HERE, "liboracle.so")
     if force or not os.path.exists(so):
-        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"])
+        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=sys.stderr)
     if os.path.isdir("/root/reference"):
-        subprocess.check_call(["make", "-C", _HERE, "ref"])
+        subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=sys.stderr)
     return so
 
 

@@ -60,12 +60,12 @@ static void run(const DevEnv& env, const DevRobot& rob, const DevSim& sp, int64_
                 const double* targets, const double* tape, double* out, uint8_t* coll, int64_t* counters)
 {
     Group<1> g; g.mask = 1u; g.base = 0; g.sub = 0;
-    std::vector<double> f0((size_t)rob.num_links * 12), f1((size_t)rob.num_links * 12);
+    std::vector<double> f0((size_t)rob.num_links * 12), f1((size_t)rob.num_links * 12), park((size_t)2 * M::WIDTH);
     for (int64_t i = 0; i < n; i++)
     {
         LocalCounters lc = {0u, 0u, 0u};
         bool c = false;
-        simulate_particle<M, 1>(env, rob, sp, g, i, n, starts, n_targets, targets, tape, out, coll, rob.pts, f0.data(), f1.data(), lc, c);
+        simulate_particle<M, 1>(env, rob, sp, g, i, n, starts, n_targets, targets, tape, out, coll, rob.pts, f0.data(), f1.data(), park.data(), lc, c);
         counters[0] += lc.particle_steps; counters[1] += c ? 1 : 0; counters[2] += lc.resolver_iterations; counters[3] += lc.failed_resolves;
     }
 }

@@ -228,6 +228,10 @@ _LIB = None
 
 
 def library_path():
+    """In-tree library; UPC_B200_LIBRARY names an alternative build of the same sources (kernel tuning experiments)."""
+    override = os.environ.get("UPC_B200_LIBRARY")
+    if override:
+        return override
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libupc_b200.so")
 
 

@@ -125,6 +125,7 @@ int32_t upc_create(const upc_env_desc* env, int32_t device, upc_handle** out)
     if (env->nx < 1 || env->ny < 1 || env->nz < 1) return fail_arg("grid dimensions must be >= 1");
     if (!(env->resolution > 0.0) || !isfinite(env->resolution)) return fail_arg("resolution must be > 0");
     if (!env->sdf) return fail_arg("sdf grid is required");
+    if ((int64_t)env->nx * (int64_t)env->ny * (int64_t)env->nz >= ((int64_t)1 << 31)) return fail_arg("grids are limited to 2^31 cells");
     if (!finite_all(env->grid_from_world, 12)) return fail_arg("grid_from_world must be finite");
     int count = 0;
     UPC_CUDA_TRY(cudaGetDeviceCount(&count));

@@ -17,7 +17,7 @@
 
 #if defined(__CUDACC__)
 #define UPC_D __host__ __device__ __forceinline__
-#define UPC_DNI __host__ __device__ __noinline__
+#define UPC_DNI inline __host__ __device__ __noinline__
 #else
 #define UPC_D inline
 #define UPC_DNI inline
@@ -128,7 +128,7 @@ UPC_D void voxel_from_link(const DevEnv& env, const double* link, double* V)
 
 /* ------------------------------------------------------------------ SE(3) closed forms */
 
-UPC_D void se3_log(const double* T, double* twist)
+UPC_DNI void se3_log(const double* T, double* twist)
 {
     const double trace = (T[0] + T[5]) + T[10];
     double s[3];
@@ -190,7 +190,7 @@ UPC_D void se3_log(const double* T, double* twist)
     }
 }
 
-UPC_D void se3_exp(const double* twist, double* T)
+UPC_DNI void se3_exp(const double* twist, double* T)
 {
     const double* v = twist;
     const double* w = twist + 3;
@@ -330,10 +330,11 @@ UPC_D double sdf_distance(const DevEnv& env, const double* u)
     const int x0 = (ix < 0) ? 0 : ix, x1 = (ix + 1 > env.nx - 1) ? env.nx - 1 : ix + 1;
     const int y0 = (iy < 0) ? 0 : iy, y1 = (iy + 1 > env.ny - 1) ? env.ny - 1 : iy + 1;
     const int z0 = (iz < 0) ? 0 : iz, z1 = (iz + 1 > env.nz - 1) ? env.nz - 1 : iz + 1;
-    const int64_t r00 = ((int64_t)x0 * env.ny + y0) * env.nz;
-    const int64_t r01 = ((int64_t)x0 * env.ny + y1) * env.nz;
-    const int64_t r10 = ((int64_t)x1 * env.ny + y0) * env.nz;
-    const int64_t r11 = ((int64_t)x1 * env.ny + y1) * env.nz;
+    /* grids are limited to 2^31 cells (checked in upc_create): 32-bit index arithmetic */
+    const int r00 = (x0 * env.ny + y0) * env.nz;
+    const int r01 = (x0 * env.ny + y1) * env.nz;
+    const int r10 = (x1 * env.ny + y0) * env.nz;
+    const int r11 = (x1 * env.ny + y1) * env.nz;
     const double v000 = (double)ldg(env.sdf + r00 + z0), v001 = (double)ldg(env.sdf + r00 + z1);
     const double v010 = (double)ldg(env.sdf + r01 + z0), v011 = (double)ldg(env.sdf + r01 + z1);
     const double v100 = (double)ldg(env.sdf + r10 + z0), v101 = (double)ldg(env.sdf + r10 + z1);
@@ -362,10 +363,11 @@ UPC_D double sdf_distance_gradient(const DevEnv& env, const double* u, double* g
     const int x0 = (ix < 0) ? 0 : ix, x1 = (ix + 1 > env.nx - 1) ? env.nx - 1 : ix + 1;
     const int y0 = (iy < 0) ? 0 : iy, y1 = (iy + 1 > env.ny - 1) ? env.ny - 1 : iy + 1;
     const int z0 = (iz < 0) ? 0 : iz, z1 = (iz + 1 > env.nz - 1) ? env.nz - 1 : iz + 1;
-    const int64_t r00 = ((int64_t)x0 * env.ny + y0) * env.nz;
-    const int64_t r01 = ((int64_t)x0 * env.ny + y1) * env.nz;
-    const int64_t r10 = ((int64_t)x1 * env.ny + y0) * env.nz;
-    const int64_t r11 = ((int64_t)x1 * env.ny + y1) * env.nz;
+    /* grids are limited to 2^31 cells (checked in upc_create): 32-bit index arithmetic */
+    const int r00 = (x0 * env.ny + y0) * env.nz;
+    const int r01 = (x0 * env.ny + y1) * env.nz;
+    const int r10 = (x1 * env.ny + y0) * env.nz;
+    const int r11 = (x1 * env.ny + y1) * env.nz;
     const double v000 = (double)ldg(env.sdf + r00 + z0), v001 = (double)ldg(env.sdf + r00 + z1);
     const double v010 = (double)ldg(env.sdf + r01 + z0), v011 = (double)ldg(env.sdf + r01 + z1);
     const double v100 = (double)ldg(env.sdf + r10 + z0), v101 = (double)ldg(env.sdf + r10 + z1);
@@ -396,7 +398,7 @@ UPC_D double sdf_distance_gradient(const DevEnv& env, const double* u, double* g
 /* ------------------------------------------------------------------ damped normal equations */
 
 template <int N>
-UPC_D void solve_damped(double (&H)[N][N], const double* g, double lambda, double* x, int n)
+UPC_DNI void solve_damped(double (&H)[N][N], const double* g, double lambda, double* x, int n)
 {
     /* Cholesky in place in the lower triangle of H (upper triangle holds the input) */
 #pragma unroll
@@ -618,7 +620,7 @@ struct Se3Model
         }
         return distance_xf(ta, tb);
     }
-    UPC_D static double distance_xf(const double* ta, const double* tb)
+    UPC_DNI static double distance_xf(const double* ta, const double* tb)
     {
         const double dx = ta[3] - tb[3], dy = ta[7] - tb[7], dz = ta[11] - tb[11];
         const double tdist = sqrt(((dx * dx) + (dy * dy)) + (dz * dz));

@@ -15,6 +15,9 @@
 namespace upc
 {
 constexpr int kBlock = 128;
+#ifndef UPC_SIM_MIN_BLOCKS
+#define UPC_SIM_MIN_BLOCKS 1
+#endif
 
 struct SimArgs
 {
@@ -31,7 +34,7 @@ struct SimArgs
 };
 
 template <class M, int G>
-__global__ void __launch_bounds__(kBlock) forward_simulate_kernel(const __grid_constant__ SimArgs a)
+__global__ void __launch_bounds__(kBlock, UPC_SIM_MIN_BLOCKS) forward_simulate_kernel(const __grid_constant__ SimArgs a)
 {
     extern __shared__ double smem[];
     __shared__ unsigned int s_cnt[4];
@@ -53,15 +56,16 @@ __global__ void __launch_bounds__(kBlock) forward_simulate_kernel(const __grid_c
     {
         double* frames0 = nullptr;
         double* frames1 = nullptr;
+        /* per-particle scratch: [target | previous] then (linked robots) two sets of link frames */
+        const int per = M::HAS_FRAMES ? a.robot.num_links * 12 : 0;
+        double* park = smem + npd + (size_t)(threadIdx.x / G) * (size_t)(2 * M::WIDTH + 2 * per);
         if constexpr (M::HAS_FRAMES)
         {
-            const int per = a.robot.num_links * 12;
-            double* fb = smem + npd + (size_t)(threadIdx.x / G) * (size_t)(2 * per);
-            frames0 = fb;
-            frames1 = fb + per;
+            frames0 = park + 2 * M::WIDTH;
+            frames1 = frames0 + per;
         }
         simulate_particle<M, G>(a.env, a.robot, a.sp, g, i, a.n, a.starts, a.n_targets, a.targets, a.tape, a.out_configs,
-                                a.out_collided, pts, frames0, frames1, lc, collided);
+                                a.out_collided, pts, frames0, frames1, park, lc, collided);
         if (g.sub == 0)
         {
             atomicAdd(&s_cnt[0], lc.particle_steps);
@@ -86,7 +90,7 @@ static cudaError_t launch_sim_impl(const SimArgs& a, cudaStream_t stream)
     const int64_t threads = a.n * G;
     const int64_t blocks = (threads + kBlock - 1) / kBlock;
     size_t smem = (size_t)a.robot.num_points * 4 * sizeof(double);
-    if (M::HAS_FRAMES) smem += (size_t)(kBlock / G) * 2 * (size_t)a.robot.num_links * 12 * sizeof(double);
+    smem += (size_t)(kBlock / G) * (2 * M::WIDTH + (M::HAS_FRAMES ? 2 * (size_t)a.robot.num_links * 12 : 0)) * sizeof(double);
     if (smem > 48 * 1024)
     {
         cudaError_t e = cudaFuncSetAttribute(forward_simulate_kernel<M, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -101,7 +101,18 @@ UPC_D bool check_collision(const DevEnv& env, const DevRobot& r, const M& m, con
         double T[12], V[12];
         m.frame(r, l, T);
         voxel_from_link(env, T, V);
-        for (int k = beg + g.sub; k < end; k += G)
+        /* two independent points per trip: the second hides the first one's load and dependent-FMA latency */
+        int k = beg + g.sub;
+        for (; k + G < end; k += 2 * G)
+        {
+            double ua[3], ub[3];
+            xf_point(V, pts[4 * k + 0], pts[4 * k + 1], pts[4 * k + 2], ua);
+            xf_point(V, pts[4 * (k + G) + 0], pts[4 * (k + G) + 1], pts[4 * (k + G) + 2], ub);
+            const double da = sdf_distance(env, ua);
+            const double db = sdf_distance(env, ub);
+            hit = hit || ((da - pts[4 * k + 3]) < threshold) || ((db - pts[4 * (k + G) + 3]) < threshold);
+        }
+        if (k < end)
         {
             double u[3];
             xf_point(V, pts[4 * k + 0], pts[4 * k + 1], pts[4 * k + 2], u);
@@ -143,7 +154,7 @@ UPC_D double estimate_motion(const DevRobot& r, const M& m, const Group<G>& g, c
 
 /* one resolver pass: raw correction step x from the body points closer than resolve_distance. Returns #contributing points. */
 template <class M, int G>
-UPC_D int resolver_correction(const DevEnv& env, const DevRobot& r, const DevSim& sp, const M& m, const Group<G>& g,
+UPC_DNI int resolver_correction(const DevEnv& env, const DevRobot& r, const DevSim& sp, const M& m, const Group<G>& g,
                               const double* pts, double* x)
 {
     constexpr int N = M::DOF;
@@ -265,102 +276,176 @@ UPC_D int resolver_correction(const DevEnv& env, const DevRobot& r, const DevSim
 
 /*
  * Simulate particle i for one planner edge. `pts` are the robot's body points (shared memory on the GPU),
- * frames0/frames1 are per-particle scratch for link transforms (linked robots only).
+ * frames0/frames1 are per-particle scratch for link transforms (linked robots only), `park` is per-particle
+ * scratch of 2*WIDTH doubles (shared memory on the GPU) holding the target and the pre-microstep configuration,
+ * which are read once per controller interval / only when a microstep is reverted and would otherwise
+ * occupy registers for the whole edge.
  * Writes the final configuration and the collided flag from lane 0 of the group.
+ *
+ * Control flow: one loop body = "apply an input, then collision-check", used both for noisy microsteps and for
+ * noise-free resolver corrections, so that the model's apply / the motion estimate / the collision check are
+ * each instantiated once (code size is instruction-cache pressure here).  The sequence of operations per
+ * particle is exactly the sequential program of DESIGN.md section 3.
  */
 template <class M, int G>
 UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim& sp, const Group<G>& g, int64_t i, int64_t n,
                              const double* starts, int64_t n_targets, const double* targets, const double* tape,
                              double* out_configs, uint8_t* out_collided, const double* pts, double* frames0,
-                             double* frames1, LocalCounters& cnt, bool& collided_out)
+                             double* frames1, double* park, LocalCounters& cnt, bool& collided_out)
 {
     constexpr int N = M::DOF;
     const int dof = r.dof;
+    const int width = (M::HAS_FRAMES) ? dof : M::WIDTH;
     M m;
     if constexpr (M::HAS_FRAMES) m.frames = frames0;
     m.load(r, starts, n, i);
     m.reset_controllers();
     refresh_frames(r, m, g);
-    double target[M::WIDTH];
+    double* target = park;
+    double* previous = park + M::WIDTH;
     {
         const int64_t ti = (n_targets == 1) ? 0 : i;
-        const int width = (M::HAS_FRAMES) ? dof : M::WIDTH;
-#pragma unroll
-        for (int c = 0; c < M::WIDTH; c++)
-            if (c < width) target[c] = targets[(int64_t)c * n_targets + ti];
+        if (g.sub == 0)
+        {
+            for (int c = 0; c < width; c++) target[c] = targets[(int64_t)c * n_targets + ti];
+        }
+        g.sync();
     }
     const int slots = 1 + sp.max_microsteps;
     bool collided = false;
     for (int step = 0; step < sp.num_steps; step++)
     {
         cnt.particle_steps++;
-        double draws[N];
-#pragma unroll
-        for (int d = 0; d < N; d++)
-            if (d < dof) draws[d] = tape[(((int64_t)step * slots) * dof + d) * n + i];
-        double u[N];
-        m.control(r, target, sp.dt, draws, u);
-        double real[N];
-#pragma unroll
-        for (int d = 0; d < N; d++)
-            if (d < dof) real[d] = u[d] * sp.dt;
-        const double motion = estimate_motion(r, m, g, pts, real, frames1);
-        unsigned microsteps = (unsigned)ceil(motion / sp.microstep_distance);
-        if (microsteps < 1u) microsteps = 1u;
-        if (microsteps > (unsigned)sp.max_microsteps) microsteps = (unsigned)sp.max_microsteps;
-        const double inv_micro = 1.0 / (double)microsteps;
-        double ustep[N];
-#pragma unroll
-        for (int d = 0; d < N; d++)
-            if (d < dof) ustep[d] = real[d] * inv_micro;
-        for (unsigned ms = 0; ms < microsteps; ms++)
+        double vec[N];   /* the input about to be estimated / applied: control step, then resolver corrections */
+        double ustep[N]; /* control input per microstep */
         {
-            double previous[M::WIDTH];
-            m.get(r, previous);
+            double draws[N];
 #pragma unroll
             for (int d = 0; d < N; d++)
-                if (d < dof) draws[d] = tape[(((int64_t)step * slots + 1 + ms) * dof + d) * n + i];
-            m.apply(r, ustep, draws);
-            refresh_frames(r, m, g);
-            bool in_collision = check_collision(env, r, m, g, pts, sp.contact_distance);
-            if (in_collision) collided = true;
-            if (in_collision && sp.allow_contacts)
+                if (d < dof) draws[d] = tape[(((int64_t)step * slots) * dof + d) * n + i];
+            double u[N];
+            m.control(r, target, sp.dt, draws, u);
+#pragma unroll
+            for (int d = 0; d < N; d++)
+                if (d < dof) vec[d] = u[d] * sp.dt;
+        }
+        unsigned microsteps = 1u, ms = 0u;
+        bool resolving = false;    /* false: next action is a (noisy) microstep; true: a resolver correction */
+        bool need_estimate = true; /* the control step and every resolver correction are measured first */
+        int iterations = 0;
+        double scaling = sp.initial_scale;
+        bool step_done = false;
+        while (!step_done)
+        {
+            double apply_in[N];
+            const double* noise = nullptr;
+            double draws[N];
+            if (need_estimate)
             {
-                int iterations = 0;
-                double scaling = sp.initial_scale;
-                while (in_collision)
+                const double est = estimate_motion(r, m, g, pts, vec, frames1);
+                if (!resolving)
                 {
-                    double raw[N];
-                    const int contributing = resolver_correction(env, r, sp, m, g, pts, raw);
-                    if (contributing == 0) break;
-                    const double est = estimate_motion(r, m, g, pts, raw, frames1);
-                    const double limit_scale = (est > sp.microstep_distance) ? (sp.microstep_distance / est) : 1.0;
-                    const double total_scale = limit_scale * fabs(scaling);
-                    double corr[N];
+                    microsteps = (unsigned)ceil(est / sp.microstep_distance);
+                    if (microsteps < 1u) microsteps = 1u;
+                    if (microsteps > (unsigned)sp.max_microsteps) microsteps = (unsigned)sp.max_microsteps;
+                    const double inv_micro = 1.0 / (double)microsteps;
 #pragma unroll
                     for (int d = 0; d < N; d++)
-                        if (d < dof) corr[d] = raw[d] * total_scale;
-                    m.apply(r, corr, nullptr);
-                    refresh_frames(r, m, g);
-                    in_collision = check_collision(env, r, m, g, pts, sp.contact_distance);
-                    iterations++;
-                    cnt.resolver_iterations++;
-                    if (iterations >= sp.max_resolver_iterations) break;
-                    if ((iterations % sp.decay_iterations) == 0) scaling = scaling * sp.decay_rate;
+                        if (d < dof) ustep[d] = vec[d] * inv_micro;
                 }
+                else
+                {
+                    const double limit_scale = (est > sp.microstep_distance) ? (sp.microstep_distance / est) : 1.0;
+                    const double total_scale = limit_scale * fabs(scaling);
+#pragma unroll
+                    for (int d = 0; d < N; d++)
+                        if (d < dof) apply_in[d] = vec[d] * total_scale;
+                }
+                need_estimate = false;
+            }
+            if (!resolving)
+            {
+                /* noisy microstep `ms` */
+                g.sync();
+                if (g.sub == 0) m.get(r, previous);
+                g.sync();
+#pragma unroll
+                for (int d = 0; d < N; d++)
+                    if (d < dof)
+                    {
+                        draws[d] = tape[(((int64_t)step * slots + 1 + ms) * dof + d) * n + i];
+                        apply_in[d] = ustep[d];
+                    }
+                noise = draws;
+            }
+            m.apply(r, apply_in, noise);
+            refresh_frames(r, m, g);
+            bool in_collision = check_collision(env, r, m, g, pts, sp.contact_distance);
+            bool revert = false;
+            if (!resolving)
+            {
                 if (in_collision)
                 {
-                    m.set(r, previous);
-                    refresh_frames(r, m, g);
-                    cnt.failed_resolves++;
-                    break;
+                    collided = true;
+                    if (sp.allow_contacts)
+                    {
+                        resolving = true;
+                        iterations = 0;
+                        scaling = sp.initial_scale;
+                    }
+                    else
+                    {
+                        revert = true;
+                    }
                 }
             }
-            else if (in_collision)
+            else
             {
-                m.set(r, previous);
+                iterations++;
+                cnt.resolver_iterations++;
+                if (in_collision)
+                {
+                    if (iterations >= sp.max_resolver_iterations)
+                    {
+                        revert = true;
+                        cnt.failed_resolves++;
+                    }
+                    else if ((iterations % sp.decay_iterations) == 0)
+                    {
+                        scaling = scaling * sp.decay_rate;
+                    }
+                }
+            }
+            if (resolving && in_collision && !revert)
+            {
+                /* next action: a resolver correction from the current configuration */
+                const int contributing = resolver_correction(env, r, sp, m, g, pts, vec);
+                if (contributing == 0)
+                {
+                    revert = true;
+                    cnt.failed_resolves++;
+                }
+                else
+                {
+                    need_estimate = true;
+                }
+            }
+            if (revert)
+            {
+                double prev[M::WIDTH];
+#pragma unroll
+                for (int c = 0; c < M::WIDTH; c++)
+                    if (c < width) prev[c] = previous[c];
+                m.set(r, prev);
                 refresh_frames(r, m, g);
-                break;
+                step_done = true; /* a reverted microstep ends the controller interval */
+            }
+            else if (!in_collision)
+            {
+                /* microstep finished (directly, or after a successful resolve) */
+                resolving = false;
+                ms++;
+                if (ms >= microsteps) step_done = true;
             }
         }
         if (m.distance_to(r, target) < sp.shortcut) break;

@@ -201,12 +201,15 @@ def c1_se2(seed=1, n=1000, num_steps=64, max_microsteps=1, shape=(256, 256, 1), 
     return dict(name="c1_se2", env=env, robot=robot, starts=starts, targets=targets, params=params, seed=seed, boxes=boxes)
 
 
-def c2_se3(seed=2, n=10000, num_steps=64, max_microsteps=1, shape=(128, 128, 128), resolution=0.03125, num_boxes=24):
+def c2_se3(seed=2, n=10000, num_steps=64, max_microsteps=1, shape=(128, 128, 128), resolution=0.03125, num_boxes=24, edge=0):
+    """`edge` > 0 picks another planner edge (start, target) in the same environment (multi-GPU edge sharding)."""
     rng = np.random.default_rng(seed)
     extent = shape[0] * resolution
     boxes = random_boxes(rng, num_boxes, extent, 0.2, 0.5)
     env = make_environment(shape, resolution, boxes)
     robot = se3_robot()
+    if edge:
+        rng = np.random.default_rng([seed, 1000 + edge])
     start, target = _pick_contact_edge(rng, boxes, env, clearance=0.35, travel=0.35, push=0.05, planar=False)
     R0 = rotation_from_axis_angle(rng.normal(size=3), rng.uniform(0.2, 1.0))
     R1 = rotation_from_axis_angle(rng.normal(size=3), rng.uniform(0.2, 1.0))
