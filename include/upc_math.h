@@ -111,8 +111,13 @@ UPC_HD_CALL void upc_sincos(double x, double* s, double* c)
 UPC_HD double upc_sin(double x) { double s, c; upc_sincos(x, &s, &c); return s; }
 UPC_HD double upc_cos(double x) { double s, c; upc_sincos(x, &s, &c); return c; }
 
-/* arctangent, four-interval argument reduction + odd/even split polynomial */
-UPC_HD_CALL double upc_atan(double xin)
+/*
+ * atan2 for finite inputs, atan2(0,0) = 0.  The classic four-break-point reduction of atan is applied to the
+ * pair (|y|, |x|) directly, so the whole function costs ONE division (an FP64 division is ~130 dependent
+ * cycles on sm_100a): t = (|y| - c|x|) / (|x| + c|y|) for c in {0, 1/2, 1, 3/2, inf}, then the odd/even split
+ * minimax polynomial in t.
+ */
+UPC_HD_CALL double upc_atan2(double y, double x)
 {
     const double aT0 = 3.33333333333329318027e-01, aT1 = -1.99999999998764832476e-01,
                  aT2 = 1.42857142725034663711e-01, aT3 = -1.11111104054623557880e-01,
@@ -120,72 +125,59 @@ UPC_HD_CALL double upc_atan(double xin)
                  aT6 = 6.66107313738753120669e-02, aT7 = -5.83357013379057348645e-02,
                  aT8 = 4.97687799461593236017e-02, aT9 = -3.65315727442169155270e-02,
                  aT10 = 1.62858201153657823623e-02;
-    const bool neg = xin < 0.0;
-    double x = fabs(xin);
-    double hi = 0.0, lo = 0.0;
-    bool reduced = true;
-    if (x < 0.4375)
-    {
-        reduced = false;
-    }
-    else if (x < 0.6875)
-    {
-        hi = 4.63647609000806093515e-01; lo = 2.26987774529616870924e-17;
-        x = (2.0 * x - 1.0) / (2.0 + x);
-    }
-    else if (x < 1.1875)
-    {
-        hi = 7.85398163397448278999e-01; lo = 3.06161699786838301793e-17;
-        x = (x - 1.0) / (x + 1.0);
-    }
-    else if (x < 2.4375)
-    {
-        hi = 9.82793723247329054082e-01; lo = 1.39033110312309984516e-17;
-        x = (x - 1.5) / upc_fma(1.5, x, 1.0);
-    }
-    else
-    {
-        hi = 1.57079632679489655800e+00; lo = 6.12323399573676603587e-17;
-        x = -1.0 / x;
-    }
-    const double z = x * x;
-    const double w = z * z;
-    double s1 = upc_fma(w, aT10, aT8);
-    s1 = upc_fma(w, s1, aT6);
-    s1 = upc_fma(w, s1, aT4);
-    s1 = upc_fma(w, s1, aT2);
-    s1 = upc_fma(w, s1, aT0);
-    s1 = z * s1;
-    double s2 = upc_fma(w, aT9, aT7);
-    s2 = upc_fma(w, s2, aT5);
-    s2 = upc_fma(w, s2, aT3);
-    s2 = upc_fma(w, s2, aT1);
-    s2 = w * s2;
-    double res;
-    if (!reduced)
-    {
-        res = x - x * (s1 + s2);
-    }
-    else
-    {
-        res = hi - ((x * (s1 + s2) - lo) - x);
-    }
-    return neg ? -res : res;
-}
-
-/* atan2 restricted to finite inputs. atan2(0,0) = 0. */
-UPC_HD double upc_atan2(double y, double x)
-{
     const double ay = fabs(y);
     const double ax = fabs(x);
-    double a;
-    if (ax == 0.0)
+    double a = 0.0;
+    if (!((ax == 0.0) && (ay == 0.0)))
     {
-        a = (ay == 0.0) ? 0.0 : UPC_HALF_PI;
-    }
-    else
-    {
-        a = upc_atan(ay / ax);
+        double num, den, hi = 0.0, lo = 0.0;
+        bool reduced = true;
+        if (ay < 0.4375 * ax)
+        {
+            num = ay; den = ax; reduced = false;
+        }
+        else if (ay < 0.6875 * ax)
+        {
+            hi = 4.63647609000806093515e-01; lo = 2.26987774529616870924e-17;
+            num = 2.0 * ay - ax; den = 2.0 * ax + ay;
+        }
+        else if (ay < 1.1875 * ax)
+        {
+            hi = 7.85398163397448278999e-01; lo = 3.06161699786838301793e-17;
+            num = ay - ax; den = ay + ax;
+        }
+        else if (ay < 2.4375 * ax)
+        {
+            hi = 9.82793723247329054082e-01; lo = 1.39033110312309984516e-17;
+            num = upc_fma(-1.5, ax, ay); den = upc_fma(1.5, ay, ax);
+        }
+        else
+        {
+            hi = 1.57079632679489655800e+00; lo = 6.12323399573676603587e-17;
+            num = -ax; den = ay;
+        }
+        const double t = num / den;
+        const double z = t * t;
+        const double w = z * z;
+        double s1 = upc_fma(w, aT10, aT8);
+        s1 = upc_fma(w, s1, aT6);
+        s1 = upc_fma(w, s1, aT4);
+        s1 = upc_fma(w, s1, aT2);
+        s1 = upc_fma(w, s1, aT0);
+        s1 = z * s1;
+        double s2 = upc_fma(w, aT9, aT7);
+        s2 = upc_fma(w, s2, aT5);
+        s2 = upc_fma(w, s2, aT3);
+        s2 = upc_fma(w, s2, aT1);
+        s2 = w * s2;
+        if (!reduced)
+        {
+            a = t - t * (s1 + s2);
+        }
+        else
+        {
+            a = hi - ((t * (s1 + s2) - lo) - t);
+        }
         if (x < 0.0)
         {
             a = UPC_PI - a;
@@ -193,6 +185,8 @@ UPC_HD double upc_atan2(double y, double x)
     }
     return (y < 0.0) ? -a : a;
 }
+
+UPC_HD double upc_atan(double x) { return upc_atan2(x, 1.0); }
 
 /* arccosine for |x| <= 1 through atan2(sqrt((1-x)(1+x)), x) */
 UPC_HD double upc_acos(double x)

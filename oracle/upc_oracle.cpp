@@ -195,13 +195,18 @@ void Se3Log(const Mat34& t, double twist[6])
     }
     /* v = t - 0.5 w x t + k2 w x (w x t) */
     double k2;
-    if (theta < 1.0e-3)
+    const double th2 = theta * theta;
+    if (theta < 0.05)
     {
-        k2 = upc_fma(theta * theta, 1.0 / 720.0, 1.0 / 12.0);
+        k2 = upc_fma(th2, 1.0 / 47900160.0, 1.0 / 1209600.0);
+        k2 = upc_fma(th2, k2, 1.0 / 30240.0);
+        k2 = upc_fma(th2, k2, 1.0 / 720.0);
+        k2 = upc_fma(th2, k2, 1.0 / 12.0);
     }
     else
     {
-        k2 = (1.0 - (theta * sn) / (2.0 * (1.0 - ct))) / (theta * theta);
+        const double two_omc = 2.0 * (1.0 - ct);
+        k2 = (two_omc - theta * sn) / (two_omc * th2);
     }
     const double tr[3] = {R[0][3], R[1][3], R[2][3]};
     double wxt[3], wxwxt[3];
@@ -231,9 +236,10 @@ Mat34 Se3Exp(const double twist[6])
     {
         double sn, cs;
         upc_sincos(theta, &sn, &cs);
-        A = sn / theta;
-        B = (1.0 - cs) / th2;
-        C = (1.0 - A) / th2;
+        const double inv = 1.0 / theta;
+        A = sn * inv;
+        B = ((1.0 - cs) * inv) * inv;
+        C = ((1.0 - A) * inv) * inv;
     }
     Mat34 out;
     /* R = I + A [w]x + B [w]x^2 ;  [w]x^2 = w w^T - |w|^2 I */
@@ -538,13 +544,16 @@ public:
     Pid controllers_[6];
     Actuator actuators_[6];
     std::shared_ptr<PointSet> points_;
+    bool sensor_noise_free_;
 
     explicit Se3Robot(const upc_robot_desc& d) : points_(MakePointSet(d))
     {
+        sensor_noise_free_ = true;
         for (int i = 0; i < 6; i++)
         {
             controllers_[i].Initialize(d.axis[i].kp, d.axis[i].ki, d.axis[i].kd, d.axis[i].integral_clamp);
             actuators_[i].Initialize(d.axis[i].max_actuator_noise, d.axis[i].velocity_limit);
+            if (d.axis[i].max_sensor_noise != 0.0) sensor_noise_free_ = false;
         }
         config_ = Identity34();
     }
@@ -582,12 +591,17 @@ public:
     }
     void GenerateControlAction(const double* target, double interval, const double* sensor_draws, double* u) /* :685-714 */
     {
-        /* GetPosition(rng), :654-668 */
-        double twist[6];
-        Se3Log(config_, twist);
-        double noisy[6];
-        for (int i = 0; i < 6; i++) noisy[i] = SensorValue(twist[i], sensor_draws[i]);
-        const Mat34 current = Se3Exp(noisy);
+        /* GetPosition(rng), :654-668.  With every sensor noise bound zero the draws are exact zeros and
+         * Exp(Log(T) + 0) is T up to rounding: the round trip is skipped. */
+        Mat34 current = config_;
+        if (!sensor_noise_free_)
+        {
+            double twist[6];
+            Se3Log(config_, twist);
+            double noisy[6];
+            for (int i = 0; i < 6; i++) noisy[i] = SensorValue(twist[i], sensor_draws[i]);
+            current = Se3Exp(noisy);
+        }
         const Mat34 tgt = FromRows12(target);
         double err[6];
         Se3Log(Se3Between(current, tgt), err);
@@ -885,35 +899,38 @@ static double EstimateMaxWorkspaceMotion(const Robot& robot, const double* input
     return sqrt(max_sq);
 }
 
-/* damped normal equations (H + lambda I) x = g by Cholesky, DESIGN.md 3.5 */
+/* damped normal equations (H + lambda I) x = g by LDL^T with reciprocal pivots, DESIGN.md 3.5 */
 static void SolveDamped(int n, double H[UPC_MAX_DOF][UPC_MAX_DOF], const double* g, double lambda, double* x)
 {
     double L[UPC_MAX_DOF][UPC_MAX_DOF];
+    double D[UPC_MAX_DOF], R[UPC_MAX_DOF];
     for (int j = 0; j < n; j++)
     {
-        double s = H[j][j] + lambda;
-        for (int k = 0; k < j; k++) s = upc_fma(-L[j][k], L[j][k], s);
-        if (s < lambda) s = lambda;
-        L[j][j] = sqrt(s);
+        double d = H[j][j] + lambda;
+        for (int k = 0; k < j; k++) d = upc_fma(-(L[j][k] * L[j][k]), D[k], d);
+        if (d < lambda) d = lambda;
+        const double r = 1.0 / d;
         for (int i = j + 1; i < n; i++)
         {
             double t = H[i][j];
-            for (int k = 0; k < j; k++) t = upc_fma(-L[i][k], L[j][k], t);
-            L[i][j] = t / L[j][j];
+            for (int k = 0; k < j; k++) t = upc_fma(-(L[i][k] * L[j][k]), D[k], t);
+            L[i][j] = t * r;
         }
+        D[j] = d;
+        R[j] = r;
     }
     double y[UPC_MAX_DOF];
     for (int i = 0; i < n; i++)
     {
         double s = g[i];
         for (int k = 0; k < i; k++) s = upc_fma(-L[i][k], y[k], s);
-        y[i] = s / L[i][i];
+        y[i] = s;
     }
     for (int i = n - 1; i >= 0; i--)
     {
-        double s = y[i];
+        double s = y[i] * R[i];
         for (int k = i + 1; k < n; k++) s = upc_fma(-L[k][i], x[k], s);
-        x[i] = s / L[i][i];
+        x[i] = s;
     }
 }
 

@@ -19,7 +19,7 @@ def build_emulation(force=False):
     here = os.path.join(ROOT, "tests", "emulation")
     so = os.path.join(here, "libupc_emulation.so")
     src = os.path.join(here, "emulate.cpp")
-    deps = [src] + [os.path.join(ROOT, "uncertainty_planning_core_b200", "csrc", f) for f in ("upc_sim.cuh", "upc_device.cuh")] + \
+    deps = [src] + [os.path.join(ROOT, "uncertainty_planning_core_b200", "csrc", f) for f in ("upc_sim.cuh", "upc_device.cuh", "upc_host_prep.h")] + \
            [os.path.join(ROOT, "include", f) for f in ("upc_math.h", "upc_b200.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-mfma",

@@ -8,6 +8,7 @@
 #include <math.h>
 #include <vector>
 #include "upc_sim.cuh"
+#include "upc_host_prep.h"
 
 using namespace upc;
 
@@ -17,7 +18,7 @@ static void fill_env(const upc_env_desc* e, DevEnv* d)
     d->sdf_oob = e->sdf_oob_value; d->occ_oob = e->occupancy_oob_value;
     d->res = e->resolution; d->inv_res = 1.0 / e->resolution;
     for (int k = 0; k < 12; k++) d->G[k] = e->grid_from_world[k];
-    d->sdf = e->sdf; d->seg = e->convex_segment; d->occ = e->occupancy;
+    d->sdf = e->sdf; d->seg = e->convex_segment; d->occ = e->occupancy; d->cellmin = nullptr;
 }
 
 /* same conversion as upc_set_robot in upc_capi.cu (validation omitted) */
@@ -27,6 +28,9 @@ static void fill_robot(const upc_robot_desc* r, DevRobot* d)
     d->kind = r->kind; d->dof = r->dof; d->num_links = r->num_links;
     d->num_joints = (r->kind == UPC_ROBOT_LINKED) ? r->num_joints : 0;
     d->num_points = r->num_points;
+    d->sensor_noise_free = 1;
+    for (int a = 0; a < r->dof; a++)
+        if (r->axis[a].max_sensor_noise != 0.0) d->sensor_noise_free = 0;
     for (int l = 0; l <= r->num_links; l++) d->link_off[l] = r->link_point_offset[l];
     for (int l = 0; l < UPC_MAX_LINKS; l++) d->parent_joint_of_link[l] = -1;
     for (int a = 0; a < r->dof; a++)
@@ -36,6 +40,7 @@ static void fill_robot(const upc_robot_desc* r, DevRobot* d)
         d->axis[a].nb = fabs(r->axis[a].max_actuator_noise); d->weights[a] = fabs(r->distance_weights[a]);
     }
     d->pts = r->points;
+    compute_reach(r, d->reach);
     if (r->kind == UPC_ROBOT_LINKED)
     {
         for (int k = 0; k < 12; k++) d->base[k] = r->base_transform[k];
@@ -76,6 +81,9 @@ extern "C" int emulate_forward_simulate(const upc_env_desc* e, const upc_robot_d
 {
     DevEnv env; DevRobot rob; DevSim sp;
     fill_env(e, &env); fill_robot(r, &rob);
+    std::vector<float> cellmin((size_t)(e->nx + 1) * (size_t)(e->ny + 1) * (size_t)(e->nz + 1));
+    build_cellmin(e->sdf, e->nx, e->ny, e->nz, cellmin.data());
+    env.cellmin = cellmin.data();
     sp.num_steps = p->num_steps; sp.max_microsteps = p->max_microsteps; sp.allow_contacts = p->allow_contacts;
     sp.individual_jacobians = p->use_individual_jacobians; sp.max_resolver_iterations = p->max_resolver_iterations;
     sp.decay_iterations = p->resolver_decay_iterations; sp.dt = p->controller_interval; sp.shortcut = p->simulation_shortcut_distance;

@@ -3,6 +3,7 @@
  * device-pointer entry points, statistics and the host-side noise-tape generator.
  */
 #include "upc_internal.h"
+#include "upc_host_prep.h"
 
 #include <math.h>
 #include <string.h>
@@ -153,6 +154,16 @@ int32_t upc_create(const upc_env_desc* env, int32_t device, upc_handle** out)
         UPC_CUDA_TRY(cudaMemcpyAsync(h->d_occ, env->occupancy, cells * sizeof(float), cudaMemcpyHostToDevice, h->stream));
         h->stats.h2d_bytes += (int64_t)(cells * sizeof(float));
     }
+    {
+        /* cell-minimum grid for the conservative SDF cull */
+        const size_t mcells = (size_t)(env->nx + 1) * (size_t)(env->ny + 1) * (size_t)(env->nz + 1);
+        std::vector<float> cellmin(mcells);
+        build_cellmin(env->sdf, env->nx, env->ny, env->nz, cellmin.data());
+        UPC_CUDA_TRY(cudaMalloc(&h->d_cellmin, mcells * sizeof(float)));
+        UPC_CUDA_TRY(cudaMemcpyAsync(h->d_cellmin, cellmin.data(), mcells * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        UPC_CUDA_TRY(cudaStreamSynchronize(h->stream));
+        h->stats.h2d_bytes += (int64_t)(mcells * sizeof(float));
+    }
     UPC_CUDA_TRY(cudaMalloc(&h->d_counters, sizeof(DevCounters)));
     UPC_CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(DevCounters), h->stream));
     UPC_CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -166,6 +177,7 @@ int32_t upc_create(const upc_env_desc* env, int32_t device, upc_handle** out)
     e.sdf = h->d_sdf;
     e.seg = h->d_seg;
     e.occ = h->d_occ;
+    e.cellmin = h->d_cellmin;
     *out = h;
     return UPC_OK;
 }
@@ -178,11 +190,12 @@ int32_t upc_destroy(upc_handle* h)
     cudaFree(h->d_sdf);
     cudaFree(h->d_seg);
     cudaFree(h->d_occ);
+    cudaFree(h->d_cellmin);
     cudaFree(h->d_points);
     cudaFree(h->d_counters);
     DeviceBuffer* bufs[] = {&h->st_starts, &h->st_targets, &h->st_tape, &h->st_out, &h->st_coll, &h->st_labels, &h->st_ncl,
                             &h->cw.features, &h->cw.adjacency, &h->cw.roots, &h->cw.comp, &h->cw.flags, &h->cw.signatures,
-                            &h->cw.frames, &h->cw.dist_matrix, &h->cw.members, &h->cw.link_scratch, &h->cw.misc};
+                            &h->cw.frames, &h->cw.dist_matrix, &h->cw.members, &h->cw.link_scratch, &h->cw.misc, &h->cw.hash, &h->cw.dedupe, &h->cw.usig, &h->cw.uroot};
     for (DeviceBuffer* b : bufs) b->release();
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -209,6 +222,9 @@ int32_t upc_set_robot(upc_handle* h, const upc_robot_desc* r)
     d.num_links = r->num_links;
     d.num_joints = (r->kind == UPC_ROBOT_LINKED) ? r->num_joints : 0;
     d.num_points = r->num_points;
+    d.sensor_noise_free = 1;
+    for (int a = 0; a < r->dof; a++)
+        if (r->axis[a].max_sensor_noise != 0.0) d.sensor_noise_free = 0;
     for (int l = 0; l <= r->num_links; l++) d.link_off[l] = r->link_point_offset[l];
     for (int l = 0; l < UPC_MAX_LINKS; l++) d.parent_joint_of_link[l] = -1;
     for (int a = 0; a < r->dof; a++)
@@ -264,6 +280,7 @@ int32_t upc_set_robot(upc_handle* h, const upc_robot_desc* r)
         for (int l = 1; l < r->num_links; l++)
             if (!placed[(size_t)l]) return fail_arg("every link except the root needs a parent joint");
     }
+    compute_reach(r, d.reach);
     UPC_CUDA_TRY(cudaSetDevice(h->device));
     if (h->d_points) cudaFree(h->d_points);
     h->d_points = nullptr;

@@ -40,6 +40,7 @@ struct PairDistance<UPC_ROBOT_SE2>
     {
         return Se2Model::distance(r, a, b);
     }
+    __device__ __forceinline__ static bool within(const DevRobot& r, const double* a, const double* b, double thr) { return eval(r, a, b) <= thr; }
 };
 
 template <>
@@ -59,6 +60,21 @@ struct PairDistance<UPC_ROBOT_SE3>
         }
         return (((1.0 - 0.5) * tdist) + (0.5 * rdist)) * 2.0;
     }
+    /* eval(a, b) <= thr, decided without the arccosine whenever rigorous bounds allow:
+     * the distance is |dt| + angle with angle = acos(c) >= 0, and sqrt(2(1-c)) <= acos(c) <= pi*sqrt((1-c)/2). */
+    __device__ __forceinline__ static bool within(const DevRobot& r, const double* a, const double* b, double thr)
+    {
+        const double dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+        const double tdist = sqrt(((dx * dx) + (dy * dy)) + (dz * dz));
+        if (tdist > thr) return false;
+        const double dq = fabs((((a[3] * b[3]) + (a[4] * b[4])) + (a[5] * b[5])) + (a[6] * b[6]));
+        if (!(dq < (1.0 - 2.220446049250313e-16))) return tdist <= thr;
+        const double c = ((2.0 * dq) * dq) - 1.0;
+        const double sq = sqrt(1.0 - c);
+        if ((tdist + (sq * 1.4142135623730951) * (1.0 - 1.0e-9)) > thr * (1.0 + 1.0e-9)) return false;
+        if ((tdist + (sq * 2.2214414690791831) * (1.0 + 1.0e-9)) <= thr * (1.0 - 1.0e-9)) return true;
+        return eval(r, a, b) <= thr;
+    }
 };
 
 template <>
@@ -69,6 +85,7 @@ struct PairDistance<UPC_ROBOT_LINKED>
     {
         return LinkedModel::distance(r, a, b);
     }
+    __device__ __forceinline__ static bool within(const DevRobot& r, const double* a, const double* b, double thr) { return eval(r, a, b) <= thr; }
 };
 
 __global__ void se3_features_kernel(const double* __restrict__ cfg, double* __restrict__ feat, int64_t total)
@@ -148,7 +165,7 @@ __global__ void __launch_bounds__(kTileCols) adjacency_kernel(const __grid_const
             double rf[MAXF];
 #pragma unroll
             for (int f = 0; f < MAXF; f++) rf[f] = s_row[f][r];
-            adjacent = PairDistance<KIND>::eval(a.robot, rf, cf) <= a.threshold;
+            adjacent = PairDistance<KIND>::within(a.robot, rf, cf, a.threshold);
         }
         const unsigned word = __ballot_sync(0xffffffffu, adjacent);
         if (lane == 0) s_words[r][warp] = word;
@@ -172,6 +189,7 @@ struct SigArgs
     const double* cfg;
     int64_t total;
     uint32_t* sig; /* [P][total] */
+    unsigned long long* hash; /* [total] 64-bit mix of the particle's signature vector */
     double* frames; /* linked only: total * num_links * 12 scratch */
 };
 
@@ -188,6 +206,7 @@ __global__ void __launch_bounds__(128) signature_kernel(const __grid_constant__ 
     }
     m.load(a.robot, a.cfg, a.total, i);
     if constexpr (M::HAS_FRAMES) m.fk(a.robot, m.frames);
+    unsigned long long h = 0x243F6A8885A308D3ull;
     for (int l = 0; l < a.robot.num_links; l++)
     {
         const int beg = a.robot.link_off[l], end = a.robot.link_off[l + 1];
@@ -202,11 +221,116 @@ __global__ void __launch_bounds__(128) signature_kernel(const __grid_constant__ 
             uint32_t s = 0u;
             if (voxel_in_bounds(a.env, u))
             {
-                s = ldg(a.env.seg + cell_index(a.env, (int)floor(u[0]), (int)floor(u[1]), (int)floor(u[2])));
+                s = ldg(a.env.seg + cell_index(a.env, floor_to_int(u[0]), floor_to_int(u[1]), floor_to_int(u[2])));
             }
             a.sig[(int64_t)k * a.total + i] = s;
+            h = (h ^ (unsigned long long)s) * 0x9E3779B97F4A7C15ull;
+            h ^= h >> 29;
         }
     }
+    if (h == ~0ull) h = 0ull; /* ~0 marks an empty hash-table slot */
+    a.hash[i] = h;
+}
+
+/* ---- duplicate-signature elimination: particles of one outcome usually share a handful of
+ * distinct signature vectors, and the signature pass only needs one row/column per distinct vector ---- */
+
+struct DedupeArgs
+{
+    const uint32_t* sig;
+    const unsigned long long* hash;
+    int num_points;
+    int64_t total, set_size;
+    int table_size; /* per set, power of two >= 2*set_size */
+    unsigned long long* keys; /* [n_sets][table_size], ~0 = empty */
+    int32_t* reps;            /* [n_sets][table_size], smallest particle (index within the set) seen with the key */
+    int32_t* urep;            /* [total] representative (index within the set) with an identical signature vector */
+    int32_t* ucount;          /* [n_sets] number of distinct vectors */
+    int32_t* ulist;           /* [n_sets][set_size] representatives, in arrival order */
+    int32_t* uid;             /* [total] position of the particle's representative in ulist */
+};
+
+__global__ void dedupe_insert_kernel(const __grid_constant__ DedupeArgs a)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.total) return;
+    const int64_t set = p / a.set_size;
+    const int i = (int)(p - set * a.set_size);
+    const unsigned long long h = a.hash[p];
+    unsigned long long* keys = a.keys + set * a.table_size;
+    int32_t* reps = a.reps + set * a.table_size;
+    unsigned slot = (unsigned)(h >> 17) & (unsigned)(a.table_size - 1);
+    while (true)
+    {
+        const unsigned long long old = atomicCAS(&keys[slot], ~0ull, h);
+        if (old == ~0ull || old == h)
+        {
+            atomicMin(&reps[slot], i);
+            break;
+        }
+        slot = (slot + 1u) & (unsigned)(a.table_size - 1);
+    }
+}
+
+__global__ void dedupe_resolve_kernel(const __grid_constant__ DedupeArgs a)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.total) return;
+    const int64_t set = p / a.set_size;
+    const int64_t base = set * a.set_size;
+    const int i = (int)(p - base);
+    const unsigned long long h = a.hash[p];
+    const unsigned long long* keys = a.keys + set * a.table_size;
+    const int32_t* reps = a.reps + set * a.table_size;
+    unsigned slot = (unsigned)(h >> 17) & (unsigned)(a.table_size - 1);
+    while (keys[slot] != h) slot = (slot + 1u) & (unsigned)(a.table_size - 1);
+    int r = reps[slot];
+    /* equal hashes are only a hint: the vectors themselves decide */
+    bool same = true;
+    for (int k = 0; k < a.num_points && same; k++) same = a.sig[(int64_t)k * a.total + base + i] == a.sig[(int64_t)k * a.total + base + r];
+    if (!same) r = i;
+    a.urep[p] = r;
+    if (r == i)
+    {
+        const int pos = atomicAdd(&a.ucount[set], 1);
+        a.ulist[base + pos] = i;
+        a.uid[p] = pos;
+    }
+}
+
+__global__ void dedupe_uid_kernel(const __grid_constant__ DedupeArgs a)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.total) return;
+    const int64_t base = (p / a.set_size) * a.set_size;
+    const int r = a.urep[p];
+    if (r != (int)(p - base)) a.uid[p] = a.uid[base + r];
+}
+
+/* compact signature matrix of the distinct vectors: usig[k][set*umax + u] */
+__global__ void dedupe_gather_kernel(const uint32_t* __restrict__ sig, int num_points, int64_t total, int64_t set_size,
+                                     const int32_t* __restrict__ ucount, const int32_t* __restrict__ ulist, int umax, uint32_t* __restrict__ usig)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n_sets = total / set_size;
+    const int64_t utotal = n_sets * umax;
+    if (e >= utotal * num_points) return;
+    const int k = (int)(e / utotal);
+    const int64_t q = e - (int64_t)k * utotal;
+    const int64_t set = q / umax;
+    const int u = (int)(q - set * umax);
+    uint32_t v = 0u;
+    if (u < ucount[set]) v = sig[(int64_t)k * total + set * set_size + ulist[set * set_size + u]];
+    usig[e] = v;
+}
+
+__global__ void dedupe_expand_kernel(const int32_t* __restrict__ uroot, const int32_t* __restrict__ uid, int64_t total, int64_t set_size, int umax,
+                                     int32_t* __restrict__ group)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total) return;
+    const int64_t set = p / set_size;
+    group[p] = uroot[set * umax + uid[p]];
 }
 
 struct SigAdjArgs
@@ -217,6 +341,7 @@ struct SigAdjArgs
     int wpr;
     uint32_t* adj;
     int max_mismatch; /* largest count m with (double)m / (double)P <= signature_matching_threshold */
+    const int32_t* set_count; /* optional: valid rows/columns per set (padded compact matrices) */
 };
 
 /*
@@ -231,6 +356,18 @@ __global__ void __launch_bounds__(256) signature_adjacency_kernel(const __grid_c
     const int64_t set_base = (int64_t)blockIdx.z * a.set_size;
     const int64_t row0 = (int64_t)blockIdx.y * 64;
     const int64_t col0 = (int64_t)blockIdx.x * 64;
+    const int64_t valid = a.set_count ? (int64_t)a.set_count[blockIdx.z] : a.set_size;
+    if (row0 >= valid && col0 >= valid)
+    {
+        /* tile entirely in the padding: rows stay empty */
+        if (threadIdx.x < 128)
+        {
+            const int rr = threadIdx.x >> 1, w = threadIdx.x & 1;
+            const int64_t word_index = (int64_t)blockIdx.x * 2 + w;
+            if ((row0 + rr) < a.set_size && word_index < a.wpr) a.adj[(set_base + row0 + rr) * a.wpr + word_index] = 0u;
+        }
+        return;
+    }
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     int acc[4][4];
 #pragma unroll
@@ -273,7 +410,7 @@ __global__ void __launch_bounds__(256) signature_adjacency_kernel(const __grid_c
         for (int c = 0; c < 4; c++)
         {
             const int rr = ty + 16 * r, cc = tx + 16 * c;
-            if ((row0 + rr) < a.set_size && (col0 + cc) < a.set_size && acc[r][c] <= a.max_mismatch)
+            if ((row0 + rr) < valid && (col0 + cc) < valid && acc[r][c] <= a.max_mismatch)
             {
                 atomicOr(&s_bits[rr][cc >> 5], 1u << (cc & 31));
             }
@@ -608,6 +745,8 @@ struct PassInput
     int max_mismatch = 0;
     const int32_t* group = nullptr;
     double threshold = 0.0;
+    const int32_t* set_count = nullptr; /* valid items per set when the sets are padded to a common size */
+    bool allow_exact = true;            /* false: only report whether every set is a union of cliques */
 };
 
 template <typename T>
@@ -642,6 +781,7 @@ static int32_t cluster_pass(upc_handle* h, const PassInput& in, int64_t n_sets, 
         SigAdjArgs sa;
         sa.sig = in.sig; sa.num_points = h->robot.num_points; sa.total = total; sa.set_size = set_size; sa.wpr = wpr; sa.adj = adj;
         sa.max_mismatch = in.max_mismatch;
+        sa.set_count = in.set_count;
         dim3 grid((unsigned)((set_size + 63) / 64), (unsigned)((set_size + 63) / 64), (unsigned)n_sets);
         signature_adjacency_kernel<<<grid, 256, 0, stream>>>(sa);
     }
@@ -671,7 +811,7 @@ static int32_t cluster_pass(upc_handle* h, const PassInput& in, int64_t n_sets, 
     int64_t nbad = 0;
     for (int32_t b : bad) nbad += b ? 1 : 0;
     if (fallback_sets) *fallback_sets = nbad;
-    if (nbad == 0) return UPC_OK;
+    if (nbad == 0 || !in.allow_exact) return UPC_OK;
 
     /* ---- exact path for the sets whose threshold graph is not a union of cliques ---- */
     int32_t* comp = buf<int32_t>(h->cw.comp, (size_t)total);
@@ -761,10 +901,11 @@ static int32_t cluster_pass(upc_handle* h, const PassInput& in, int64_t n_sets, 
 }
 
 template <class M>
-static cudaError_t launch_signatures(upc_handle* h, const double* cfg, int64_t total, uint32_t* sig, double* frames, cudaStream_t stream)
+static cudaError_t launch_signatures(upc_handle* h, const double* cfg, int64_t total, uint32_t* sig, unsigned long long* hash, double* frames,
+                                     cudaStream_t stream)
 {
     SigArgs sa;
-    sa.env = h->env; sa.robot = h->robot; sa.cfg = cfg; sa.total = total; sa.sig = sig; sa.frames = frames;
+    sa.env = h->env; sa.robot = h->robot; sa.cfg = cfg; sa.total = total; sa.sig = sig; sa.hash = hash; sa.frames = frames;
     signature_kernel<M><<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(sa);
     return cudaGetLastError();
 }
@@ -812,14 +953,15 @@ int32_t run_cluster(upc_handle* h, const upc_cluster_params& cp, int64_t n_sets,
             frames = buf<double>(h->cw.frames, (size_t)total * h->robot.num_links * 12);
             UPC_NULLCHECK(frames);
         }
+        unsigned long long* hash = buf<unsigned long long>(h->cw.hash, (size_t)total);
+        UPC_NULLCHECK(hash);
         cudaError_t e;
-        if (kind == UPC_ROBOT_SE2) e = launch_signatures<Se2Model>(h, d_configs, total, sig, frames, stream);
-        else if (kind == UPC_ROBOT_SE3) e = launch_signatures<Se3Model>(h, d_configs, total, sig, frames, stream);
-        else e = launch_signatures<LinkedModel>(h, d_configs, total, sig, frames, stream);
+        if (kind == UPC_ROBOT_SE2) e = launch_signatures<Se2Model>(h, d_configs, total, sig, hash, frames, stream);
+        else if (kind == UPC_ROBOT_SE3) e = launch_signatures<Se3Model>(h, d_configs, total, sig, hash, frames, stream);
+        else e = launch_signatures<LinkedModel>(h, d_configs, total, sig, hash, frames, stream);
         h->stats.kernel_launches++;
         UPC_CUDA_TRY(e);
         PassInput in;
-        in.sig = sig;
         in.threshold = cp.signature_matching_threshold;
         int mm = -1;
         for (int m = 0; m <= P; m++)
@@ -828,8 +970,73 @@ int32_t run_cluster(upc_handle* h, const upc_cluster_params& cp, int64_t n_sets,
             else break;
         }
         in.max_mismatch = mm;
-        const int32_t rc = cluster_pass(h, in, n_sets, set_size, root1, stream, nullptr);
-        if (rc != UPC_OK) return rc;
+        bool done = false;
+        if (mm >= 0 && set_size >= 64)
+        {
+            /* ---- fast path: cluster the distinct signature vectors only (exact whenever their threshold graph is a
+             * union of cliques, which is then also true of the full graph; otherwise fall through to the full pass) ---- */
+            int table = 64;
+            while (table < 2 * set_size) table *= 2;
+            const size_t tcells = (size_t)n_sets * (size_t)table;
+            /* [keys u64 | reps i32 | urep | uid | ulist (i32 each, total) | ucount (n_sets)] */
+            const size_t bytes = tcells * 12 + (size_t)total * 12 + (size_t)n_sets * 4 + 64;
+            uint8_t* base = buf<uint8_t>(h->cw.dedupe, bytes);
+            UPC_NULLCHECK(base);
+            DedupeArgs da;
+            da.sig = sig; da.hash = hash; da.num_points = P; da.total = total; da.set_size = set_size; da.table_size = table;
+            da.keys = (unsigned long long*)base;
+            da.reps = (int32_t*)(base + tcells * 8);
+            da.urep = da.reps + tcells;
+            da.uid = da.urep + total;
+            da.ulist = da.uid + total;
+            da.ucount = da.ulist + total;
+            UPC_CUDA_TRY(cudaMemsetAsync(da.keys, 0xFF, tcells * 8, stream));
+            UPC_CUDA_TRY(cudaMemsetAsync(da.reps, 0x7F, tcells * 4, stream));
+            UPC_CUDA_TRY(cudaMemsetAsync(da.ucount, 0, (size_t)n_sets * 4, stream));
+            const unsigned blocks = (unsigned)((total + 255) / 256);
+            dedupe_insert_kernel<<<blocks, 256, 0, stream>>>(da);
+            dedupe_resolve_kernel<<<blocks, 256, 0, stream>>>(da);
+            dedupe_uid_kernel<<<blocks, 256, 0, stream>>>(da);
+            h->stats.kernel_launches += 3;
+            UPC_CUDA_TRY(cudaGetLastError());
+            std::vector<int32_t> ucount((size_t)n_sets);
+            UPC_CUDA_TRY(cudaMemcpyAsync(ucount.data(), da.ucount, (size_t)n_sets * 4, cudaMemcpyDeviceToHost, stream));
+            UPC_CUDA_TRY(cudaStreamSynchronize(stream));
+            h->stats.d2h_bytes += n_sets * 4;
+            int umax = 1;
+            for (int32_t c : ucount) umax = std::max(umax, (int)c);
+            if ((int64_t)umax * 2 <= set_size)
+            {
+                const int64_t utotal = n_sets * (int64_t)umax;
+                uint32_t* usig = buf<uint32_t>(h->cw.usig, (size_t)utotal * P);
+                UPC_NULLCHECK(usig);
+                int32_t* uroot = buf<int32_t>(h->cw.uroot, (size_t)utotal);
+                UPC_NULLCHECK(uroot);
+                dedupe_gather_kernel<<<(unsigned)((utotal * P + 255) / 256), 256, 0, stream>>>(sig, P, total, set_size, da.ucount, da.ulist, umax, usig);
+                h->stats.kernel_launches++;
+                UPC_CUDA_TRY(cudaGetLastError());
+                PassInput uin = in;
+                uin.sig = usig;
+                uin.set_count = da.ucount;
+                uin.allow_exact = false;
+                int64_t ubad = 0;
+                const int32_t urc = cluster_pass(h, uin, n_sets, umax, uroot, stream, &ubad);
+                if (urc != UPC_OK) return urc;
+                if (ubad == 0)
+                {
+                    dedupe_expand_kernel<<<blocks, 256, 0, stream>>>(uroot, da.uid, total, set_size, umax, root1);
+                    h->stats.kernel_launches++;
+                    UPC_CUDA_TRY(cudaGetLastError());
+                    done = true;
+                }
+            }
+        }
+        if (!done)
+        {
+            in.sig = sig;
+            const int32_t rc = cluster_pass(h, in, n_sets, set_size, root1, stream, nullptr);
+            if (rc != UPC_OK) return rc;
+        }
         group = root1;
     }
     else if (cp.feature_type != UPC_FEATURE_NONE)

@@ -34,6 +34,10 @@ struct DevEnv
     const float* sdf;
     const uint32_t* seg;
     const float* occ;
+    /* (nx+1)(ny+1)(nz+1) floats: minimum of the 8 (border-clamped) corners of every trilinear interpolation cell,
+     * indexed by the cell's low corner + 1.  A conservative lower bound of the interpolated distance used to skip
+     * the 8-corner fetch for points that are provably clear; may be NULL (no culling). */
+    const float* cellmin;
 };
 
 struct DevAxis
@@ -53,12 +57,16 @@ struct DevJoint
 struct DevRobot
 {
     int kind, dof, num_links, num_joints, num_points;
+    int sensor_noise_free; /* every max_sensor_noise is zero: the sensed configuration is the configuration */
     int link_off[UPC_MAX_LINKS + 1];
     int parent_joint_of_link[UPC_MAX_LINKS];
     const double* pts; /* num_points * 4: x, y, z, radius */
     DevAxis axis[UPC_MAX_DOF];
     double weights[UPC_MAX_DOF];
     double base[12];
+    /* static bounds on how far a body point can be from the axis that moves it:
+     * reach[a] for active axis a of a linked robot; reach[0] = largest |p| of the single link of SE2/SE3 robots */
+    double reach[UPC_MAX_DOF];
     DevJoint joints[UPC_MAX_JOINTS];
 };
 
@@ -73,6 +81,16 @@ struct DevCounters
 {
     unsigned long long particle_steps, collided, resolver_iterations, failed_resolves;
 };
+
+/* floor(x) as a 32-bit integer in one conversion instruction (|x| < 2^31 by the grid-size limit) */
+UPC_D int floor_to_int(double x)
+{
+#if defined(__CUDA_ARCH__)
+    return __double2int_rd(x);
+#else
+    return (int)floor(x);
+#endif
+}
 
 template <typename T>
 UPC_D T ldg(const T* p)
@@ -170,13 +188,19 @@ UPC_DNI void se3_log(const double* T, double* twist)
         w[0] = a[0] * theta; w[1] = a[1] * theta; w[2] = a[2] * theta;
     }
     double k2;
-    if (theta < 1.0e-3)
+    const double th2 = theta * theta;
+    if (theta < 0.05)
     {
-        k2 = upc_fma(theta * theta, 1.0 / 720.0, 1.0 / 12.0);
+        /* 1/12 + th^2/720 + th^4/30240 + th^6/1209600 + th^8/47900160 */
+        k2 = upc_fma(th2, 1.0 / 47900160.0, 1.0 / 1209600.0);
+        k2 = upc_fma(th2, k2, 1.0 / 30240.0);
+        k2 = upc_fma(th2, k2, 1.0 / 720.0);
+        k2 = upc_fma(th2, k2, 1.0 / 12.0);
     }
     else
     {
-        k2 = (1.0 - (theta * sn) / (2.0 * (1.0 - ct))) / (theta * theta);
+        const double two_omc = 2.0 * (1.0 - ct);
+        k2 = (two_omc - theta * sn) / (two_omc * th2);
     }
     const double tr[3] = {T[3], T[7], T[11]};
     double wxt[3], wxwxt[3];
@@ -207,9 +231,10 @@ UPC_DNI void se3_exp(const double* twist, double* T)
     {
         double sn, cs;
         upc_sincos(theta, &sn, &cs);
-        A = sn / theta;
-        B = (1.0 - cs) / th2;
-        C = (1.0 - A) / th2;
+        const double inv = 1.0 / theta; /* the only division of the exponential */
+        A = sn * inv;
+        B = ((1.0 - cs) * inv) * inv;
+        C = ((1.0 - A) * inv) * inv;
     }
     const double wx = w[0], wy = w[1], wz = w[2];
     T[0] = upc_fma(B, upc_fma(wx, wx, -th2), 1.0);
@@ -324,9 +349,8 @@ UPC_D double sdf_distance(const DevEnv& env, const double* u)
 {
     if (!voxel_in_bounds(env, u)) return (double)env.sdf_oob;
     const double cx = u[0] - 0.5, cy = u[1] - 0.5, cz = u[2] - 0.5;
-    const double flx = floor(cx), fly = floor(cy), flz = floor(cz);
-    const double fx = cx - flx, fy = cy - fly, fz = cz - flz;
-    const int ix = (int)flx, iy = (int)fly, iz = (int)flz;
+    const int ix = floor_to_int(cx), iy = floor_to_int(cy), iz = floor_to_int(cz);
+    const double fx = cx - (double)ix, fy = cy - (double)iy, fz = cz - (double)iz;
     const int x0 = (ix < 0) ? 0 : ix, x1 = (ix + 1 > env.nx - 1) ? env.nx - 1 : ix + 1;
     const int y0 = (iy < 0) ? 0 : iy, y1 = (iy + 1 > env.ny - 1) ? env.ny - 1 : iy + 1;
     const int z0 = (iz < 0) ? 0 : iz, z1 = (iz + 1 > env.nz - 1) ? env.nz - 1 : iz + 1;
@@ -348,6 +372,21 @@ UPC_D double sdf_distance(const DevEnv& env, const double* u)
     return upc_fma(fx, c1 - c0, c0);
 }
 
+/* margin (metres) by which the cell-minimum bound must clear a threshold before the exact interpolation is skipped;
+ * the interpolant can undershoot the smallest corner only by a few ulps of the corner values */
+#define UPC_CULL_MARGIN 1.0e-9
+
+/* true when the point at voxel coordinate u is certainly at distance >= limit + radius (so the exact test
+ * "distance - radius < limit" is false); false means "unknown, evaluate exactly". */
+UPC_D bool sdf_certainly_clear(const DevEnv& env, const double* u, double radius, double limit)
+{
+    if (!voxel_in_bounds(env, u)) return (((double)env.sdf_oob - radius) - limit) > UPC_CULL_MARGIN;
+    if (env.cellmin == nullptr) return false;
+    const int ix = floor_to_int(u[0] - 0.5) + 1, iy = floor_to_int(u[1] - 0.5) + 1, iz = floor_to_int(u[2] - 0.5) + 1;
+    const double m = (double)ldg(env.cellmin + ((ix * (env.ny + 1) + iy) * (env.nz + 1) + iz));
+    return ((m - radius) - limit) > UPC_CULL_MARGIN;
+}
+
 /* distance and world-frame gradient */
 UPC_D double sdf_distance_gradient(const DevEnv& env, const double* u, double* grad)
 {
@@ -357,9 +396,8 @@ UPC_D double sdf_distance_gradient(const DevEnv& env, const double* u, double* g
         return (double)env.sdf_oob;
     }
     const double cx = u[0] - 0.5, cy = u[1] - 0.5, cz = u[2] - 0.5;
-    const double flx = floor(cx), fly = floor(cy), flz = floor(cz);
-    const double fx = cx - flx, fy = cy - fly, fz = cz - flz;
-    const int ix = (int)flx, iy = (int)fly, iz = (int)flz;
+    const int ix = floor_to_int(cx), iy = floor_to_int(cy), iz = floor_to_int(cz);
+    const double fx = cx - (double)ix, fy = cy - (double)iy, fz = cz - (double)iz;
     const int x0 = (ix < 0) ? 0 : ix, x1 = (ix + 1 > env.nx - 1) ? env.nx - 1 : ix + 1;
     const int y0 = (iy < 0) ? 0 : iy, y1 = (iy + 1 > env.ny - 1) ? env.ny - 1 : iy + 1;
     const int z0 = (iz < 0) ? 0 : iz, z1 = (iz + 1 > env.nz - 1) ? env.nz - 1 : iz + 1;
@@ -400,31 +438,34 @@ UPC_D double sdf_distance_gradient(const DevEnv& env, const double* u, double* g
 template <int N>
 UPC_DNI void solve_damped(double (&H)[N][N], const double* g, double lambda, double* x, int n)
 {
-    /* Cholesky in place in the lower triangle of H (upper triangle holds the input) */
+    /* (H + lambda I) x = g by an LDL^T factorisation without square roots: unit-lower L in the strict lower
+     * triangle of H (the upper triangle holds the input), reciprocal pivots in rd[] - one division per column. */
+    double rd[N];
 #pragma unroll
     for (int j = 0; j < N; j++)
     {
         if (j < n)
         {
-            double s = H[j][j] + lambda;
+            double d = H[j][j] + lambda;
 #pragma unroll
             for (int k = 0; k < N; k++)
-                if (k < j) s = upc_fma(-H[j][k], H[j][k], s);
-            if (s < lambda) s = lambda;
-            const double ljj = sqrt(s);
+                if (k < j) d = upc_fma(-(H[j][k] * H[j][k]), H[k][k], d); /* H[k][k] holds pivot d_k once column k is done */
+            if (d < lambda) d = lambda;
+            const double r = 1.0 / d;
 #pragma unroll
             for (int i = 0; i < N; i++)
             {
                 if (i > j && i < n)
                 {
-                    double t = H[j][i]; /* input H[i][j] read from the symmetric upper triangle */
+                    double t = H[j][i]; /* input H[i][j], read from the symmetric upper triangle */
 #pragma unroll
                     for (int k = 0; k < N; k++)
-                        if (k < j) t = upc_fma(-H[i][k], H[j][k], t);
-                    H[i][j] = t / ljj;
+                        if (k < j) t = upc_fma(-(H[i][k] * H[j][k]), H[k][k], t);
+                    H[i][j] = t * r;
                 }
             }
-            H[j][j] = ljj;
+            H[j][j] = d;
+            rd[j] = r;
         }
     }
     double y[N];
@@ -437,7 +478,7 @@ UPC_DNI void solve_damped(double (&H)[N][N], const double* g, double lambda, dou
 #pragma unroll
             for (int k = 0; k < N; k++)
                 if (k < i) s = upc_fma(-H[i][k], y[k], s);
-            y[i] = s / H[i][i];
+            y[i] = s;
         }
     }
 #pragma unroll
@@ -446,11 +487,11 @@ UPC_DNI void solve_damped(double (&H)[N][N], const double* g, double lambda, dou
         const int i = N - 1 - ii;
         if (i < n)
         {
-            double s = y[i];
+            double s = y[i] * rd[i];
 #pragma unroll
             for (int k = 0; k < N; k++)
                 if (k > i && k < n) s = upc_fma(-H[k][i], x[k], s);
-            x[i] = s / H[i][i];
+            x[i] = s;
         }
     }
 }
@@ -507,6 +548,14 @@ struct Se2Model
     {
         const double c[3] = {x, y, th};
         return distance(r, c, target);
+    }
+    /* ComputeConfigurationDistance(config, target) < shortcut */
+    UPC_D bool reached(const DevRobot& r, const double* target, double shortcut) const { return distance_to(r, target) < shortcut; }
+    /* upper bound of the body-point displacement caused by a noise-free input */
+    UPC_D double motion_bound(const DevRobot& r, const double* in) const
+    {
+        const double c0 = actuator_clamp(r.axis[0], in[0]), c1 = actuator_clamp(r.axis[1], in[1]), c2 = actuator_clamp(r.axis[2], in[2]);
+        return sqrt((c0 * c0) + (c1 * c1)) + fabs(c2) * r.reach[0];
     }
     UPC_D void control(const DevRobot& r, const double* target, double dt, const double* draws, double* u) /* :239-259 */
     {
@@ -647,14 +696,41 @@ struct Se3Model
         }
         return distance_xf(T, tb);
     }
+    /* ComputeConfigurationDistance(config, target) < shortcut.  The distance is |dt| + angle with angle >= 0 and
+     * monotone rounding, so |dt| >= shortcut already decides "no" without the quaternion / acos work. */
+    UPC_D bool reached(const DevRobot& r, const double* target, double shortcut) const
+    {
+        const double dx = T[3] - target[9], dy = T[7] - target[10], dz = T[11] - target[11];
+        const double tdist = sqrt(((dx * dx) + (dy * dy)) + (dz * dz));
+        if (!(tdist < shortcut)) return false;
+        return distance_to(r, target) < shortcut;
+    }
+    UPC_D double motion_bound(const DevRobot& r, const double* in) const
+    {
+        double c[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) c[i] = actuator_clamp(r.axis[i], in[i]);
+        const double v = sqrt(((c[0] * c[0]) + (c[1] * c[1])) + (c[2] * c[2]));
+        const double w = sqrt(((c[3] * c[3]) + (c[4] * c[4])) + (c[5] * c[5]));
+        return v + w * r.reach[0];
+    }
     UPC_D void control(const DevRobot& r, const double* target, double dt, const double* draws, double* u) /* :685-714 */
     {
-        double tw[6];
-        se3_log(T, tw); /* GetPosition(rng) :654-668 */
-#pragma unroll
-        for (int i = 0; i < 6; i++) tw[i] = tw[i] + draws[i];
         double sensed[12];
-        se3_exp(tw, sensed);
+        if (r.sensor_noise_free)
+        {
+            /* Exp(Log(T) + 0) is T up to rounding: with no sensor noise the round trip is skipped */
+#pragma unroll
+            for (int k = 0; k < 12; k++) sensed[k] = T[k];
+        }
+        else
+        {
+            double tw[6];
+            se3_log(T, tw); /* GetPosition(rng) :654-668 */
+#pragma unroll
+            for (int i = 0; i < 6; i++) tw[i] = tw[i] + draws[i];
+            se3_exp(tw, sensed);
+        }
         double tgt[12];
 #pragma unroll
         for (int rr = 0; rr < 3; rr++)
@@ -841,6 +917,13 @@ struct LinkedModel
         return sqrt(sum);
     }
     UPC_D double distance_to(const DevRobot& r, const double* target) const { return distance(r, q, target); }
+    UPC_D bool reached(const DevRobot& r, const double* target, double shortcut) const { return distance_to(r, target) < shortcut; }
+    UPC_D double motion_bound(const DevRobot& r, const double* in) const
+    {
+        double b = 0.0;
+        for (int a = 0; a < r.dof; a++) b = b + fabs(actuator_clamp(r.axis[a], in[a])) * r.reach[a];
+        return b;
+    }
     UPC_D void control(const DevRobot& r, const double* target, double dt, const double* draws, double* u) /* :1823-1851 */
     {
         for (int idx = 0; idx < r.num_joints; idx++)

@@ -1,0 +1,106 @@
+/*
+ * upc_host_prep.h - host-side precomputation shared by the C ABI (upc_capi.cu) and the CPU emulation of the
+ * device program (tests/emulation): the cell-minimum grid behind the SDF cull and the static reach bounds
+ * behind the motion bound.  Both only ever make the kernels skip work whose outcome is
+ * already certain; they never change a result.
+ */
+#ifndef UPC_HOST_PREP_H
+#define UPC_HOST_PREP_H
+
+#include <math.h>
+#include <stdint.h>
+#include <algorithm>
+#include <vector>
+#include "upc_b200.h"
+
+namespace upc
+{
+/* out[(ix*(ny+1)+iy)*(nz+1)+iz] = min of the 8 border-clamped SDF corners of the interpolation cell whose low
+ * corner is (ix-1, iy-1, iz-1) */
+inline void build_cellmin(const float* sdf, int nx, int ny, int nz, float* out)
+{
+#pragma omp parallel for schedule(static)
+    for (int ix = 0; ix <= nx; ix++)
+    {
+        const int x0 = std::max(ix - 1, 0), x1 = std::min(ix, nx - 1);
+        for (int iy = 0; iy <= ny; iy++)
+        {
+            const int y0 = std::max(iy - 1, 0), y1 = std::min(iy, ny - 1);
+            for (int iz = 0; iz <= nz; iz++)
+            {
+                const int z0 = std::max(iz - 1, 0), z1 = std::min(iz, nz - 1);
+                float m = sdf[((int64_t)x0 * ny + y0) * nz + z0];
+                m = std::min(m, sdf[((int64_t)x0 * ny + y0) * nz + z1]);
+                m = std::min(m, sdf[((int64_t)x0 * ny + y1) * nz + z0]);
+                m = std::min(m, sdf[((int64_t)x0 * ny + y1) * nz + z1]);
+                m = std::min(m, sdf[((int64_t)x1 * ny + y0) * nz + z0]);
+                m = std::min(m, sdf[((int64_t)x1 * ny + y0) * nz + z1]);
+                m = std::min(m, sdf[((int64_t)x1 * ny + y1) * nz + z0]);
+                m = std::min(m, sdf[((int64_t)x1 * ny + y1) * nz + z1]);
+                out[((int64_t)ix * (ny + 1) + iy) * (nz + 1) + iz] = m;
+            }
+        }
+    }
+}
+
+/*
+ * reach[a]: an upper bound of |d(point)/d(axis a)| over all body points and all configurations.
+ * SE2 / SE3: reach[0] = largest |p| of the body points (rotation about the body origin).
+ * Linked: for active joint a, the largest distance any point of a descendant link can have from the joint's
+ * frame origin: sum over the joints further down the chain of (|translation of the joint transform| + the
+ * largest prismatic extension) plus the largest |p| of the link; prismatic joints move points by |axis| per unit.
+ */
+inline void compute_reach(const upc_robot_desc* r, double* reach)
+{
+    for (int a = 0; a < UPC_MAX_DOF; a++) reach[a] = 0.0;
+    std::vector<double> link_radius((size_t)r->num_links, 0.0);
+    for (int l = 0; l < r->num_links; l++)
+    {
+        for (int k = r->link_point_offset[l]; k < r->link_point_offset[l + 1]; k++)
+        {
+            const double* p = r->points + 4 * k;
+            link_radius[(size_t)l] = std::max(link_radius[(size_t)l], sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]));
+        }
+    }
+    if (r->kind != UPC_ROBOT_LINKED)
+    {
+        reach[0] = link_radius[0];
+        return;
+    }
+    /* offset_below[j]: how far the child-link frame origin of joint j can be from joint j's own frame origin is 0
+     * (revolute) or its prismatic extension; distances accumulate down the tree */
+    const int nj = r->num_joints;
+    std::vector<double> extent((size_t)r->num_links, 0.0); /* largest distance of any descendant point from the link's frame origin */
+    for (int l = 0; l < r->num_links; l++) extent[(size_t)l] = link_radius[(size_t)l];
+    for (int j = nj - 1; j >= 0; j--) /* parents precede children, so walking backwards sees children first */
+    {
+        const upc_joint_desc& jd = r->joints[j];
+        const double* t = jd.transform;
+        double hop = sqrt(t[3] * t[3] + t[7] * t[7] + t[11] * t[11]);
+        if (jd.type == UPC_JOINT_PRISMATIC)
+        {
+            const double an = sqrt(jd.axis[0] * jd.axis[0] + jd.axis[1] * jd.axis[1] + jd.axis[2] * jd.axis[2]);
+            hop += an * std::max(fabs(jd.lower_limit), fabs(jd.upper_limit));
+        }
+        extent[(size_t)jd.parent_link] = std::max(extent[(size_t)jd.parent_link], hop + extent[(size_t)jd.child_link]);
+    }
+    int active = 0;
+    for (int j = 0; j < nj; j++)
+    {
+        const upc_joint_desc& jd = r->joints[j];
+        if (jd.type == UPC_JOINT_FIXED) continue;
+        if (jd.type == UPC_JOINT_PRISMATIC)
+        {
+            reach[active] = sqrt(jd.axis[0] * jd.axis[0] + jd.axis[1] * jd.axis[1] + jd.axis[2] * jd.axis[2]);
+        }
+        else
+        {
+            const double an = sqrt(jd.axis[0] * jd.axis[0] + jd.axis[1] * jd.axis[1] + jd.axis[2] * jd.axis[2]);
+            reach[active] = std::max(an, 1.0) * extent[(size_t)jd.child_link];
+        }
+        active++;
+    }
+}
+} /* namespace upc */
+
+#endif

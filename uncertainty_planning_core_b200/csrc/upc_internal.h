@@ -36,6 +36,10 @@ struct ClusterWorkspace
     DeviceBuffer members;      /* member lists + offsets of those components */
     DeviceBuffer link_scratch; /* per-member state of the complete-link kernel */
     DeviceBuffer misc;
+    DeviceBuffer hash;         /* per-particle signature hashes */
+    DeviceBuffer dedupe;       /* hash table + representative bookkeeping */
+    DeviceBuffer usig;         /* compact signatures of the distinct vectors */
+    DeviceBuffer uroot;        /* roots of the distinct vectors */
 };
 
 } /* namespace upc */
@@ -52,6 +56,7 @@ struct upc_handle
     float* d_sdf = nullptr;
     uint32_t* d_seg = nullptr;
     float* d_occ = nullptr;
+    float* d_cellmin = nullptr;
     double* d_points = nullptr;
     upc::DevCounters* d_counters = nullptr; /* device-side running totals */
     upc_stats stats{};

@@ -14,9 +14,13 @@
 
 namespace upc
 {
-constexpr int kBlock = 128;
+#ifndef UPC_SIM_BLOCK
+#define UPC_SIM_BLOCK 128
+#endif
+constexpr int kBlock = UPC_SIM_BLOCK;
+/* 3 CTAs of 128 threads per SM (<= 168 registers): measured best on B200 for the latency-bound per-particle program */
 #ifndef UPC_SIM_MIN_BLOCKS
-#define UPC_SIM_MIN_BLOCKS 1
+#define UPC_SIM_MIN_BLOCKS 3
 #endif
 
 struct SimArgs
@@ -114,8 +118,10 @@ static cudaError_t launch_sim_lanes(const SimArgs& a, int lanes, cudaStream_t st
     }
 }
 
-/* Built-in choice of lanes per particle: enough threads for about two full waves of the 148 SMs,
- * never more lanes than a link has points to hand out. */
+/* Built-in choice of lanes per particle.  The per-particle program is a long dependent FP64 chain, so a batch is
+ * fastest when all of it is resident at once: take the most lanes (shortest per-lane point loop) for which
+ * n * lanes threads still fit in one wave (sm_count * UPC_SIM_MIN_BLOCKS CTAs); big batches get one lane per
+ * particle, which is also the most instruction-efficient mapping (no replicated state math). */
 int choose_lanes(const upc_handle* h, int64_t n)
 {
     int lanes;
@@ -125,9 +131,9 @@ int choose_lanes(const upc_handle* h, int64_t n)
     }
     else
     {
-        const int64_t want_threads = (int64_t)h->sm_count * 2048;
+        const int64_t one_wave_threads = (int64_t)h->sm_count * UPC_SIM_MIN_BLOCKS * kBlock;
         lanes = 1;
-        while (lanes < 32 && n * lanes * 2 <= want_threads) lanes *= 2;
+        while (lanes < 32 && n * lanes * 2 <= one_wave_threads) lanes *= 2;
         int max_pts = 1;
         for (int l = 0; l < h->robot.num_links; l++)
         {

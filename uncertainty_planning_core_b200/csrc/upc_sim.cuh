@@ -108,16 +108,18 @@ UPC_D bool check_collision(const DevEnv& env, const DevRobot& r, const M& m, con
             double ua[3], ub[3];
             xf_point(V, pts[4 * k + 0], pts[4 * k + 1], pts[4 * k + 2], ua);
             xf_point(V, pts[4 * (k + G) + 0], pts[4 * (k + G) + 1], pts[4 * (k + G) + 2], ub);
-            const double da = sdf_distance(env, ua);
-            const double db = sdf_distance(env, ub);
-            hit = hit || ((da - pts[4 * k + 3]) < threshold) || ((db - pts[4 * (k + G) + 3]) < threshold);
+            const double ra = pts[4 * k + 3], rb = pts[4 * (k + G) + 3];
+            const bool clear_a = sdf_certainly_clear(env, ua, ra, threshold);
+            const bool clear_b = sdf_certainly_clear(env, ub, rb, threshold);
+            if (!clear_a) hit = hit || ((sdf_distance(env, ua) - ra) < threshold);
+            if (!clear_b) hit = hit || ((sdf_distance(env, ub) - rb) < threshold);
         }
         if (k < end)
         {
             double u[3];
             xf_point(V, pts[4 * k + 0], pts[4 * k + 1], pts[4 * k + 2], u);
-            const double d = sdf_distance(env, u);
-            hit = hit || ((d - pts[4 * k + 3]) < threshold);
+            const double rk = pts[4 * k + 3];
+            if (!sdf_certainly_clear(env, u, rk, threshold)) hit = hit || ((sdf_distance(env, u) - rk) < threshold);
         }
     }
     return g.any(hit);
@@ -185,8 +187,11 @@ UPC_DNI int resolver_correction(const DevEnv& env, const DevRobot& r, const DevS
             {
                 double u[3], grad[3];
                 xf_point(V, pts[4 * k + 0], pts[4 * k + 1], pts[4 * k + 2], u);
-                const double d = sdf_distance_gradient(env, u, grad);
-                const double de = d - pts[4 * k + 3];
+                double de = sp.resolve_distance;
+                if (!sdf_certainly_clear(env, u, pts[4 * k + 3], sp.resolve_distance))
+                {
+                    de = sdf_distance_gradient(env, u, grad) - pts[4 * k + 3];
+                }
                 if (de < sp.resolve_distance)
                 {
                     const double gn2 = dot3(grad, grad);
@@ -342,10 +347,14 @@ UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim&
             double draws[N];
             if (need_estimate)
             {
-                const double est = estimate_motion(r, m, g, pts, vec, frames1);
+                /* a static upper bound decides the common case (motion <= microstep_distance => one microstep, no
+                 * down-scaling) without touching the body points; otherwise the exact estimate runs */
+                const bool small = (m.motion_bound(r, vec) * 1.000001) <= sp.microstep_distance;
+                double est = 0.0;
+                if (!small) est = estimate_motion(r, m, g, pts, vec, frames1);
                 if (!resolving)
                 {
-                    microsteps = (unsigned)ceil(est / sp.microstep_distance);
+                    microsteps = small ? 1u : (unsigned)ceil(est / sp.microstep_distance);
                     if (microsteps < 1u) microsteps = 1u;
                     if (microsteps > (unsigned)sp.max_microsteps) microsteps = (unsigned)sp.max_microsteps;
                     const double inv_micro = 1.0 / (double)microsteps;
@@ -355,7 +364,7 @@ UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim&
                 }
                 else
                 {
-                    const double limit_scale = (est > sp.microstep_distance) ? (sp.microstep_distance / est) : 1.0;
+                    const double limit_scale = (!small && est > sp.microstep_distance) ? (sp.microstep_distance / est) : 1.0;
                     const double total_scale = limit_scale * fabs(scaling);
 #pragma unroll
                     for (int d = 0; d < N; d++)
@@ -448,7 +457,7 @@ UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim&
                 if (ms >= microsteps) step_done = true;
             }
         }
-        if (m.distance_to(r, target) < sp.shortcut) break;
+        if (m.reached(r, target, sp.shortcut)) break;
     }
     if (g.sub == 0)
     {
