@@ -88,7 +88,7 @@ UPC_HD double upc_kcos(double r)
 
 /* Simultaneous sine and cosine. Accurate (about 1 ulp) for |x| up to about 1e5; beyond that the two-term
  * Cody-Waite reduction degrades gracefully. Angles on this path are bounded by a few pi. */
-UPC_HD_CALL void upc_sincos(double x, double* s, double* c)
+UPC_HD void upc_sincos(double x, double* s, double* c)
 {
     const double TWO_OVER_PI = 6.36619772367581382433e-01;
     const double PIO2_HI = 1.57079632673412561417e+00; /* first 33 bits of pi/2 */
@@ -117,7 +117,7 @@ UPC_HD double upc_cos(double x) { double s, c; upc_sincos(x, &s, &c); return c; 
  * cycles on sm_100a): t = (|y| - c|x|) / (|x| + c|y|) for c in {0, 1/2, 1, 3/2, inf}, then the odd/even split
  * minimax polynomial in t.
  */
-UPC_HD_CALL double upc_atan2(double y, double x)
+UPC_HD double upc_atan2(double y, double x)
 {
     const double aT0 = 3.33333333333329318027e-01, aT1 = -1.99999999998764832476e-01,
                  aT2 = 1.42857142725034663711e-01, aT3 = -1.11111104054623557880e-01,

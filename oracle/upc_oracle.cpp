@@ -962,9 +962,8 @@ static int ComputeResolverCorrection(const Environment& env, const Robot& robot,
             if (!(de < sp.resolve_distance)) continue;
             const double gn2 = Dot3(grad, grad);
             if (!(gn2 > 1.0e-24)) continue;
-            const double gn = sqrt(gn2);
-            const double pen = sp.resolve_distance - de;
-            const double c[3] = {(grad[0] / gn) * pen, (grad[1] / gn) * pen, (grad[2] / gn) * pen};
+            const double scale = (sp.resolve_distance - de) / sqrt(gn2);
+            const double c[3] = {grad[0] * scale, grad[1] * scale, grad[2] * scale};
             double world[3];
             TransformPoint(T, pt.data(), world);
             double J[3][UPC_MAX_DOF];

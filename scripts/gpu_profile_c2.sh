@@ -4,4 +4,4 @@ CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline"
 $CMD > gpurun_out/prof_plain.json 2> gpurun_out/prof_plain.err && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_c2.csv $CMD > gpurun_out/ncu_list.log 2>&1
 $CMD > gpurun_out/prof_plain2.json 2>> gpurun_out/prof_plain.err && \
-ncu --set full --clock-control none --import-source on -k regex:forward_simulate -s 3 -c 2 -o gpurun_out/prof_sim_c2 -f $CMD > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:forward_simulate -s 3 -c 1 -o gpurun_out/prof_sim_c2 -f $CMD > gpurun_out/ncu_full.log 2>&1

@@ -17,6 +17,7 @@ static void fill_env(const upc_env_desc* e, DevEnv* d)
     d->nx = e->nx; d->ny = e->ny; d->nz = e->nz;
     d->sdf_oob = e->sdf_oob_value; d->occ_oob = e->occupancy_oob_value;
     d->res = e->resolution; d->inv_res = 1.0 / e->resolution;
+    d->dnx = (double)e->nx; d->dny = (double)e->ny; d->dnz = (double)e->nz;
     for (int k = 0; k < 12; k++) d->G[k] = e->grid_from_world[k];
     d->sdf = e->sdf; d->seg = e->convex_segment; d->occ = e->occupancy; d->cellmin = nullptr;
 }
@@ -65,10 +66,10 @@ static void run(const DevEnv& env, const DevRobot& rob, const DevSim& sp, int64_
                 const double* targets, const double* tape, double* out, uint8_t* coll, int64_t* counters)
 {
     Group<1> g; g.mask = 1u; g.base = 0; g.sub = 0;
-    std::vector<double> f0((size_t)rob.num_links * 12), f1((size_t)rob.num_links * 12), park((size_t)2 * M::WIDTH);
+    std::vector<double> f0((size_t)rob.num_links * 12), f1((size_t)rob.num_links * 12), park((size_t)2 * M::WIDTH + 2 * M::DOF);
     for (int64_t i = 0; i < n; i++)
     {
-        LocalCounters lc = {0u, 0u, 0u};
+        LocalCounters lc = {};
         bool c = false;
         simulate_particle<M, 1>(env, rob, sp, g, i, n, starts, n_targets, targets, tape, out, coll, rob.pts, f0.data(), f1.data(), park.data(), lc, c);
         counters[0] += lc.particle_steps; counters[1] += c ? 1 : 0; counters[2] += lc.resolver_iterations; counters[3] += lc.failed_resolves;

@@ -97,6 +97,7 @@ static int32_t pull_counters(upc_handle* h)
     h->stats.collided_particles += (int64_t)c.collided;
     h->stats.resolver_iterations += (int64_t)c.resolver_iterations;
     h->stats.failed_resolves += (int64_t)c.failed_resolves;
+    for (int k = 0; k < 12; k++) h->phase_cycles[k] += (int64_t)c.phase[k];
     return UPC_OK;
 }
 } /* namespace upc */
@@ -173,6 +174,7 @@ int32_t upc_create(const upc_env_desc* env, int32_t device, upc_handle** out)
     e.occ_oob = env->occupancy_oob_value;
     e.res = env->resolution;
     e.inv_res = 1.0 / env->resolution;
+    e.dnx = (double)env->nx; e.dny = (double)env->ny; e.dnz = (double)env->nz;
     for (int k = 0; k < 12; k++) e.G[k] = env->grid_from_world[k];
     e.sdf = h->d_sdf;
     e.seg = h->d_seg;
@@ -300,6 +302,16 @@ int32_t upc_get_stats(upc_handle* h, upc_stats* out)
     const int32_t rc = pull_counters(h);
     if (rc != UPC_OK) return rc;
     *out = h->stats;
+    return UPC_OK;
+}
+
+/* development aid (UPC_PHASE_TIMING builds): cycles per phase of the simulation program, summed over particles */
+int32_t upc_debug_phase_cycles(upc_handle* h, int64_t* out8)
+{
+    if (!h || !out8) return fail_arg("null argument");
+    const int32_t rc = pull_counters(h);
+    if (rc != UPC_OK) return rc;
+    for (int k = 0; k < 12; k++) { out8[k] = h->phase_cycles[k]; h->phase_cycles[k] = 0; }
     return UPC_OK;
 }
 

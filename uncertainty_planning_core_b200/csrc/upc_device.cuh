@@ -30,6 +30,7 @@ struct DevEnv
     int nx, ny, nz;
     float sdf_oob, occ_oob;
     double res, inv_res;
+    double dnx, dny, dnz; /* grid dimensions as doubles (bounds tests) */
     double G[12]; /* grid_from_world, row-major 3x4 */
     const float* sdf;
     const uint32_t* seg;
@@ -80,6 +81,7 @@ struct DevSim
 struct DevCounters
 {
     unsigned long long particle_steps, collided, resolver_iterations, failed_resolves;
+    unsigned long long phase[12]; /* UPC_PHASE_TIMING builds only: cycles per phase, summed over particles */
 };
 
 /* floor(x) as a 32-bit integer in one conversion instruction (|x| < 2^31 by the grid-size limit) */
@@ -146,7 +148,7 @@ UPC_D void voxel_from_link(const DevEnv& env, const double* link, double* V)
 
 /* ------------------------------------------------------------------ SE(3) closed forms */
 
-UPC_DNI void se3_log(const double* T, double* twist)
+UPC_D void se3_log(const double* T, double* twist)
 {
     const double trace = (T[0] + T[5]) + T[10];
     double s[3];
@@ -214,7 +216,7 @@ UPC_DNI void se3_log(const double* T, double* twist)
     }
 }
 
-UPC_DNI void se3_exp(const double* twist, double* T)
+UPC_D void se3_exp(const double* twist, double* T)
 {
     const double* v = twist;
     const double* w = twist + 3;
@@ -335,8 +337,7 @@ UPC_D double actuator_noisy(const DevAxis& ax, double u, double draw)
 
 UPC_D bool voxel_in_bounds(const DevEnv& env, const double* u)
 {
-    return (u[0] >= 0.0) && (u[0] < (double)env.nx) && (u[1] >= 0.0) && (u[1] < (double)env.ny) && (u[2] >= 0.0) &&
-           (u[2] < (double)env.nz);
+    return (u[0] >= 0.0) && (u[0] < env.dnx) && (u[1] >= 0.0) && (u[1] < env.dny) && (u[2] >= 0.0) && (u[2] < env.dnz);
 }
 
 UPC_D int64_t cell_index(const DevEnv& env, int ix, int iy, int iz)
@@ -514,7 +515,8 @@ struct Se2Model
     static constexpr int DOF = 3;
     static constexpr int WIDTH = 3;
     double x, y, th, sn, cs;
-    double pid_i[3], pid_e[3];
+    double* pid_i; /* per-particle PID state (integral, last error), parked in shared memory on the GPU */
+    double* pid_e;
 
     UPC_D int dof(const DevRobot&) const { return 3; }
     UPC_D void set_config(double nx, double ny, double nth) /* simple_robot_models.hpp:110-119 */
@@ -533,7 +535,6 @@ struct Se2Model
     UPC_D void set(const DevRobot&, const double* c) { set_config(c[0], c[1], c[2]); }
     UPC_D void reset_controllers()
     {
-#pragma unroll
         for (int i = 0; i < 3; i++) { pid_i[i] = 0.0; pid_e[i] = 0.0; }
     }
     UPC_D static double distance(const DevRobot&, const double* a, const double* b) /* :424-430 */
@@ -608,7 +609,8 @@ struct Se3Model
     static constexpr int DOF = 6;
     static constexpr int WIDTH = 12;
     double T[12];
-    double pid_i[6], pid_e[6];
+    double* pid_i; /* per-particle PID state (integral, last error), parked in shared memory on the GPU */
+    double* pid_e;
 
     UPC_D int dof(const DevRobot&) const { return 6; }
     UPC_D void load(const DevRobot&, const double* c, int64_t stride, int64_t i)
@@ -653,7 +655,6 @@ struct Se3Model
     }
     UPC_D void reset_controllers()
     {
-#pragma unroll
         for (int i = 0; i < 6; i++) { pid_i[i] = 0.0; pid_e[i] = 0.0; }
     }
     /* a, b in the boundary layout (R row-major, then t) */
@@ -714,23 +715,22 @@ struct Se3Model
         const double w = sqrt(((c[3] * c[3]) + (c[4] * c[4])) + (c[5] * c[5]));
         return v + w * r.reach[0];
     }
+    /* GetPosition(rng) :654-668; out of line: benchmarks and most planner setups run without sensor noise */
+    UPC_DNI static void sense_noisy(const double* T, const double* draws, double* sensed)
+    {
+        double tw[6];
+        se3_log(T, tw);
+#pragma unroll
+        for (int i = 0; i < 6; i++) tw[i] = tw[i] + draws[i];
+        se3_exp(tw, sensed);
+    }
     UPC_D void control(const DevRobot& r, const double* target, double dt, const double* draws, double* u) /* :685-714 */
     {
         double sensed[12];
-        if (r.sensor_noise_free)
-        {
-            /* Exp(Log(T) + 0) is T up to rounding: with no sensor noise the round trip is skipped */
 #pragma unroll
-            for (int k = 0; k < 12; k++) sensed[k] = T[k];
-        }
-        else
-        {
-            double tw[6];
-            se3_log(T, tw); /* GetPosition(rng) :654-668 */
-#pragma unroll
-            for (int i = 0; i < 6; i++) tw[i] = tw[i] + draws[i];
-            se3_exp(tw, sensed);
-        }
+        for (int k = 0; k < 12; k++) sensed[k] = T[k];
+        /* Exp(Log(T) + 0) is T up to rounding: with no sensor noise the round trip is skipped */
+        if (!r.sensor_noise_free) sense_noisy(T, draws, sensed);
         double tgt[12];
 #pragma unroll
         for (int rr = 0; rr < 3; rr++)
@@ -794,7 +794,8 @@ struct LinkedModel
     static constexpr int DOF = UPC_MAX_DOF;
     static constexpr int WIDTH = UPC_MAX_DOF;
     double q[UPC_MAX_DOF];
-    double pid_i[UPC_MAX_DOF], pid_e[UPC_MAX_DOF];
+    double* pid_i;
+    double* pid_e;
     double* frames; /* num_links * 12 doubles, current link transforms */
     static constexpr bool HAS_FRAMES = true;
     UPC_D void frame(const DevRobot&, int l, double* out) const

@@ -60,6 +60,7 @@ struct upc_handle
     double* d_points = nullptr;
     upc::DevCounters* d_counters = nullptr; /* device-side running totals */
     upc_stats stats{};
+    int64_t phase_cycles[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     /* staging for the host-pointer entry points */
     upc::DeviceBuffer st_starts, st_targets, st_tape, st_out, st_coll, st_labels, st_ncl;
     upc::ClusterWorkspace cw;

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(kBlock, UPC_SIM_MIN_BLOCKS) forward_simulate_k
 
     const int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     const int64_t i = t / G;
-    LocalCounters lc = {0u, 0u, 0u};
+    LocalCounters lc = {};
     bool collided = false;
     Group<G> g;
     g.sub = (int)(threadIdx.x % G);
@@ -62,10 +62,10 @@ __global__ void __launch_bounds__(kBlock, UPC_SIM_MIN_BLOCKS) forward_simulate_k
         double* frames1 = nullptr;
         /* per-particle scratch: [target | previous] then (linked robots) two sets of link frames */
         const int per = M::HAS_FRAMES ? a.robot.num_links * 12 : 0;
-        double* park = smem + npd + (size_t)(threadIdx.x / G) * (size_t)(2 * M::WIDTH + 2 * per);
+        double* park = smem + npd + (size_t)(threadIdx.x / G) * (size_t)(2 * M::WIDTH + 2 * M::DOF + 2 * per);
         if constexpr (M::HAS_FRAMES)
         {
-            frames0 = park + 2 * M::WIDTH;
+            frames0 = park + 2 * M::WIDTH + 2 * M::DOF;
             frames1 = frames0 + per;
         }
         simulate_particle<M, G>(a.env, a.robot, a.sp, g, i, a.n, a.starts, a.n_targets, a.targets, a.tape, a.out_configs,
@@ -76,6 +76,9 @@ __global__ void __launch_bounds__(kBlock, UPC_SIM_MIN_BLOCKS) forward_simulate_k
             atomicAdd(&s_cnt[1], collided ? 1u : 0u);
             atomicAdd(&s_cnt[2], lc.resolver_iterations);
             atomicAdd(&s_cnt[3], lc.failed_resolves);
+#ifdef UPC_PHASE_TIMING
+            for (int k = 0; k < 12; k++) atomicAdd((unsigned long long*)&a.counters->phase[k], (unsigned long long)lc.cyc[k]);
+#endif
         }
     }
     __syncthreads();
@@ -94,7 +97,7 @@ static cudaError_t launch_sim_impl(const SimArgs& a, cudaStream_t stream)
     const int64_t threads = a.n * G;
     const int64_t blocks = (threads + kBlock - 1) / kBlock;
     size_t smem = (size_t)a.robot.num_points * 4 * sizeof(double);
-    smem += (size_t)(kBlock / G) * (2 * M::WIDTH + (M::HAS_FRAMES ? 2 * (size_t)a.robot.num_links * 12 : 0)) * sizeof(double);
+    smem += (size_t)(kBlock / G) * (2 * M::WIDTH + 2 * M::DOF + (M::HAS_FRAMES ? 2 * (size_t)a.robot.num_links * 12 : 0)) * sizeof(double);
     if (smem > 48 * 1024)
     {
         cudaError_t e = cudaFuncSetAttribute(forward_simulate_kernel<M, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -76,7 +76,18 @@ struct Group
 struct LocalCounters
 {
     unsigned int particle_steps, resolver_iterations, failed_resolves;
+#ifdef UPC_PHASE_TIMING
+    long long cyc[12]; /* control, estimate, apply, check, resolver pass, reached, tape loads, -, resolver: points, replay, solve, - */
+#endif
 };
+
+#if defined(UPC_PHASE_TIMING) && defined(__CUDA_ARCH__)
+#define UPC_T0 long long _t0 = clock64();
+#define UPC_T1(slot) { const long long _t1 = clock64(); cnt.cyc[slot] += _t1 - _t0; _t0 = _t1; }
+#else
+#define UPC_T0
+#define UPC_T1(slot)
+#endif
 
 /* recompute cached link frames after a configuration change (linked robots only) */
 template <class M, int G>
@@ -90,6 +101,12 @@ UPC_D void refresh_frames(const DevRobot& r, M& m, const Group<G>& g)
     }
 }
 
+/*
+ * Collision check of the current configuration.  Per link, each lane first runs the cheap conservative test
+ * (one cell-minimum load) over all of its points - independent iterations, so the loads of several points are in
+ * flight together - and records the undecided ones in a bit mask; only those get the exact trilinear evaluation,
+ * two at a time.  The result (an OR over points) does not depend on the order.
+ */
 template <class M, int G>
 UPC_D bool check_collision(const DevEnv& env, const DevRobot& r, const M& m, const Group<G>& g, const double* pts, double threshold)
 {
@@ -101,25 +118,53 @@ UPC_D bool check_collision(const DevEnv& env, const DevRobot& r, const M& m, con
         double T[12], V[12];
         m.frame(r, l, T);
         voxel_from_link(env, T, V);
-        /* two independent points per trip: the second hides the first one's load and dependent-FMA latency */
-        int k = beg + g.sub;
-        for (; k + G < end; k += 2 * G)
+        for (int chunk = beg; chunk < end; chunk += 32 * G)
         {
-            double ua[3], ub[3];
-            xf_point(V, pts[4 * k + 0], pts[4 * k + 1], pts[4 * k + 2], ua);
-            xf_point(V, pts[4 * (k + G) + 0], pts[4 * (k + G) + 1], pts[4 * (k + G) + 2], ub);
-            const double ra = pts[4 * k + 3], rb = pts[4 * (k + G) + 3];
-            const bool clear_a = sdf_certainly_clear(env, ua, ra, threshold);
-            const bool clear_b = sdf_certainly_clear(env, ub, rb, threshold);
-            if (!clear_a) hit = hit || ((sdf_distance(env, ua) - ra) < threshold);
-            if (!clear_b) hit = hit || ((sdf_distance(env, ub) - rb) < threshold);
-        }
-        if (k < end)
-        {
-            double u[3];
-            xf_point(V, pts[4 * k + 0], pts[4 * k + 1], pts[4 * k + 2], u);
-            const double rk = pts[4 * k + 3];
-            if (!sdf_certainly_clear(env, u, rk, threshold)) hit = hit || ((sdf_distance(env, u) - rk) < threshold);
+            const int first = chunk + g.sub;
+            const int lim = (end < chunk + 32 * G) ? end : (chunk + 32 * G);
+            unsigned undecided = 0u;
+#pragma unroll 4
+            for (int j = 0; j < 32; j++)
+            {
+                const int k = first + j * G;
+                if (k < lim)
+                {
+                    double u[3];
+                    xf_point(V, pts[4 * k + 0], pts[4 * k + 1], pts[4 * k + 2], u);
+                    if (!sdf_certainly_clear(env, u, pts[4 * k + 3], threshold)) undecided |= (1u << j);
+                }
+            }
+            while (undecided)
+            {
+#if defined(__CUDA_ARCH__)
+                const int ja = __ffs((int)undecided) - 1;
+#else
+                const int ja = __builtin_ctz(undecided);
+#endif
+                undecided &= undecided - 1u;
+                const int ka = first + ja * G;
+                double ua[3];
+                xf_point(V, pts[4 * ka + 0], pts[4 * ka + 1], pts[4 * ka + 2], ua);
+                if (undecided)
+                {
+#if defined(__CUDA_ARCH__)
+                    const int jb = __ffs((int)undecided) - 1;
+#else
+                    const int jb = __builtin_ctz(undecided);
+#endif
+                    undecided &= undecided - 1u;
+                    const int kb = first + jb * G;
+                    double ub[3];
+                    xf_point(V, pts[4 * kb + 0], pts[4 * kb + 1], pts[4 * kb + 2], ub);
+                    const double da = sdf_distance(env, ua);
+                    const double db = sdf_distance(env, ub);
+                    hit = hit || ((da - pts[4 * ka + 3]) < threshold) || ((db - pts[4 * kb + 3]) < threshold);
+                }
+                else
+                {
+                    hit = hit || ((sdf_distance(env, ua) - pts[4 * ka + 3]) < threshold);
+                }
+            }
         }
     }
     return g.any(hit);
@@ -127,7 +172,7 @@ UPC_D bool check_collision(const DevEnv& env, const DevRobot& r, const M& m, con
 
 /* EstimateMaxControlInputWorkspaceMotion: largest body-point displacement caused by a noise-free input */
 template <class M, int G>
-UPC_D double estimate_motion(const DevRobot& r, const M& m, const Group<G>& g, const double* pts, const double* input, double* scratch_frames)
+UPC_DNI double estimate_motion(const DevRobot& r, const M& m, const Group<G>& g, const double* pts, const double* input, double* scratch_frames)
 {
     M moved = m;
     if constexpr (M::HAS_FRAMES) moved.frames = scratch_frames;
@@ -154,14 +199,24 @@ UPC_D double estimate_motion(const DevRobot& r, const M& m, const Group<G>& g, c
     return sqrt(max_sq);
 }
 
-/* one resolver pass: raw correction step x from the body points closer than resolve_distance. Returns #contributing points. */
+/*
+ * One resolver pass: raw correction step x from the body points closer than resolve_distance.  Returns the number
+ * of contributing points.
+ *   phase A  per lane, all its points of the link: conservative test, undecided points into a bit mask;
+ *   phase B  per lane, its undecided points: exact distance + gradient -> correction vector, kept in a small
+ *            per-thread buffer (independent evaluations, so their latencies overlap);
+ *   phase C  the contributing points are replayed in ascending point order by every lane of the group
+ *            (ballot + shuffles), accumulating J^T J and J^T c in registers - the same sequence of operations as
+ *            the sequential oracle, whatever the number of lanes.
+ */
 template <class M, int G>
 UPC_DNI int resolver_correction(const DevEnv& env, const DevRobot& r, const DevSim& sp, const M& m, const Group<G>& g,
-                              const double* pts, double* x)
+                              const double* pts, double* x, LocalCounters& cnt)
 {
+    UPC_T0
     constexpr int N = M::DOF;
     const int n = m.dof(r);
-    double H[N][N];
+    double H[N][N]; /* accumulators: never passed by address, so they can live in registers */
     double gv[N], xs[N];
 #pragma unroll
     for (int a = 0; a < N; a++)
@@ -171,6 +226,7 @@ UPC_DNI int resolver_correction(const DevEnv& env, const DevRobot& r, const DevS
         for (int b = 0; b < N; b++) H[a][b] = 0.0;
     }
     int count = 0;
+    double cbuf[32][3];
     for (int l = 0; l < r.num_links; l++)
     {
         const int beg = r.link_off[l], end = r.link_off[l + 1];
@@ -178,90 +234,130 @@ UPC_DNI int resolver_correction(const DevEnv& env, const DevRobot& r, const DevS
         double T[12], V[12];
         m.frame(r, l, T);
         voxel_from_link(env, T, V);
-        for (int k0 = beg; k0 < end; k0 += G)
+        for (int chunk = beg; chunk < end; chunk += 32 * G)
         {
-            const int k = k0 + g.sub;
-            bool contrib = false;
-            double c0 = 0.0, c1 = 0.0, c2 = 0.0;
-            if (k < end)
+            const int first = chunk + g.sub;
+            const int lim = (end < chunk + 32 * G) ? end : (chunk + 32 * G);
+            /* phase A */
+            unsigned undecided = 0u;
+#pragma unroll 4
+            for (int j = 0; j < 32; j++)
             {
+                const int k = first + j * G;
+                if (k < lim)
+                {
+                    double u[3];
+                    xf_point(V, pts[4 * k + 0], pts[4 * k + 1], pts[4 * k + 2], u);
+                    if (!sdf_certainly_clear(env, u, pts[4 * k + 3], sp.resolve_distance)) undecided |= (1u << j);
+                }
+            }
+            /* phase B */
+            unsigned contributing = 0u;
+            unsigned todo_b = undecided;
+            while (todo_b)
+            {
+#if defined(__CUDA_ARCH__)
+                const int j = __ffs((int)todo_b) - 1;
+#else
+                const int j = __builtin_ctz(todo_b);
+#endif
+                todo_b &= todo_b - 1u;
+                const int k = first + j * G;
                 double u[3], grad[3];
                 xf_point(V, pts[4 * k + 0], pts[4 * k + 1], pts[4 * k + 2], u);
-                double de = sp.resolve_distance;
-                if (!sdf_certainly_clear(env, u, pts[4 * k + 3], sp.resolve_distance))
-                {
-                    de = sdf_distance_gradient(env, u, grad) - pts[4 * k + 3];
-                }
+                const double de = sdf_distance_gradient(env, u, grad) - pts[4 * k + 3];
                 if (de < sp.resolve_distance)
                 {
                     const double gn2 = dot3(grad, grad);
                     if (gn2 > 1.0e-24)
                     {
-                        const double gn = sqrt(gn2);
-                        const double pen = sp.resolve_distance - de;
-                        c0 = (grad[0] / gn) * pen;
-                        c1 = (grad[1] / gn) * pen;
-                        c2 = (grad[2] / gn) * pen;
-                        contrib = true;
+                        const double scale = (sp.resolve_distance - de) / sqrt(gn2);
+                        cbuf[j][0] = grad[0] * scale;
+                        cbuf[j][1] = grad[1] * scale;
+                        cbuf[j][2] = grad[2] * scale;
+                        contributing |= (1u << j);
                     }
                 }
             }
-            unsigned todo = g.ballot(contrib);
-            while (todo)
+            UPC_T1(8)
+            /* phase C: rounds in ascending j, lanes in ascending rank = ascending point index */
+            unsigned rounds = contributing;
+#if defined(__CUDA_ARCH__)
+            if (G > 1)
+            {
+#pragma unroll
+                for (int off = G / 2; off > 0; off >>= 1) rounds |= __shfl_xor_sync(g.mask, rounds, off);
+            }
+#endif
+            while (rounds)
             {
 #if defined(__CUDA_ARCH__)
-                const int src = __ffs((int)todo) - 1;
+                const int j = __ffs((int)rounds) - 1;
 #else
-                const int src = 0;
+                const int j = __builtin_ctz(rounds);
 #endif
-                todo &= todo - 1u;
-                const double b0 = g.bcast(c0, src), b1 = g.bcast(c1, src), b2 = g.bcast(c2, src);
-                const int kk = k0 + src;
-                const double local[3] = {pts[4 * kk + 0], pts[4 * kk + 1], pts[4 * kk + 2]};
-                double world[3];
-                xf_point(T, local[0], local[1], local[2], world);
-                double J[3][N];
-                m.jacobian(r, l, local, world, J);
-                count++;
-                if (sp.individual_jacobians)
+                rounds &= rounds - 1u;
+                const bool mine = ((contributing >> j) & 1u) != 0u;
+                double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+                if (mine) { c0 = cbuf[j][0]; c1 = cbuf[j][1]; c2 = cbuf[j][2]; }
+                unsigned todo = g.ballot(mine);
+                while (todo)
                 {
-                    double A[3][3];
-#pragma unroll
-                    for (int rr = 0; rr < 3; rr++)
-#pragma unroll
-                        for (int qq = 0; qq < 3; qq++)
-                        {
-                            double s = 0.0;
-#pragma unroll
-                            for (int a = 0; a < N; a++)
-                                if (a < n) s = upc_fma(J[rr][a], J[qq][a], s);
-                            A[rr][qq] = s;
-                        }
-                    const double cv[3] = {b0, b1, b2};
-                    double yv[3];
-                    solve_damped<3>(A, cv, sp.damping, yv, 3);
-#pragma unroll
-                    for (int a = 0; a < N; a++)
-                        if (a < n) xs[a] = upc_fma(J[2][a], yv[2], upc_fma(J[1][a], yv[1], upc_fma(J[0][a], yv[0], xs[a])));
-                }
-                else
-                {
-#pragma unroll
-                    for (int a = 0; a < N; a++)
+#if defined(__CUDA_ARCH__)
+                    const int src = __ffs((int)todo) - 1;
+#else
+                    const int src = 0;
+#endif
+                    todo &= todo - 1u;
+                    const double b0 = g.bcast(c0, src), b1 = g.bcast(c1, src), b2 = g.bcast(c2, src);
+                    const int kk = chunk + src + j * G;
+                    const double local[3] = {pts[4 * kk + 0], pts[4 * kk + 1], pts[4 * kk + 2]};
+                    double world[3];
+                    xf_point(T, local[0], local[1], local[2], world);
+                    double J[3][N];
+                    m.jacobian(r, l, local, world, J);
+                    count++;
+                    if (sp.individual_jacobians)
                     {
-                        if (a < n)
-                        {
+                        double A[3][3];
 #pragma unroll
-                            for (int b = 0; b < N; b++)
+                        for (int rr = 0; rr < 3; rr++)
+#pragma unroll
+                            for (int qq = 0; qq < 3; qq++)
                             {
-                                if (b >= a && b < n)
-                                    H[a][b] = upc_fma(J[2][a], J[2][b], upc_fma(J[1][a], J[1][b], upc_fma(J[0][a], J[0][b], H[a][b])));
+                                double s = 0.0;
+#pragma unroll
+                                for (int a = 0; a < N; a++)
+                                    if (a < n) s = upc_fma(J[rr][a], J[qq][a], s);
+                                A[rr][qq] = s;
                             }
-                            gv[a] = upc_fma(J[2][a], b2, upc_fma(J[1][a], b1, upc_fma(J[0][a], b0, gv[a])));
+                        const double cv[3] = {b0, b1, b2};
+                        double yv[3];
+                        solve_damped<3>(A, cv, sp.damping, yv, 3);
+#pragma unroll
+                        for (int a = 0; a < N; a++)
+                            if (a < n) xs[a] = upc_fma(J[2][a], yv[2], upc_fma(J[1][a], yv[1], upc_fma(J[0][a], yv[0], xs[a])));
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int a = 0; a < N; a++)
+                        {
+                            if (a < n)
+                            {
+#pragma unroll
+                                for (int b = 0; b < N; b++)
+                                {
+                                    if (b >= a && b < n)
+                                        H[a][b] = upc_fma(J[2][a], J[2][b], upc_fma(J[1][a], J[1][b], upc_fma(J[0][a], J[0][b], H[a][b])));
+                                }
+                                gv[a] = upc_fma(J[2][a], b2, upc_fma(J[1][a], b1, upc_fma(J[0][a], b0, gv[a])));
+                            }
                         }
                     }
                 }
             }
+            UPC_T1(9)
         }
     }
     if (count == 0) return 0;
@@ -274,17 +370,24 @@ UPC_DNI int resolver_correction(const DevEnv& env, const DevRobot& r, const DevS
     }
     else
     {
-        solve_damped<N>(H, gv, sp.damping, x, n);
+        double Hs[N][N]; /* the out-of-line solver works on its own copy */
+#pragma unroll
+        for (int a = 0; a < N; a++)
+#pragma unroll
+            for (int b = 0; b < N; b++) Hs[a][b] = H[a][b];
+        solve_damped<N>(Hs, gv, sp.damping, x, n);
     }
+    UPC_T1(10)
     return count;
 }
 
 /*
  * Simulate particle i for one planner edge. `pts` are the robot's body points (shared memory on the GPU),
  * frames0/frames1 are per-particle scratch for link transforms (linked robots only), `park` is per-particle
- * scratch of 2*WIDTH doubles (shared memory on the GPU) holding the target and the pre-microstep configuration,
- * which are read once per controller interval / only when a microstep is reverted and would otherwise
- * occupy registers for the whole edge.
+ * scratch of 2*WIDTH + 2*DOF doubles (shared memory on the GPU) holding the target, the pre-microstep
+ * configuration and the PID state - values touched once per controller interval (or only when a microstep is
+ * reverted) that would otherwise occupy registers for the whole edge.  Every lane of a group writes identical
+ * values there.
  * Writes the final configuration and the collided flag from lane 0 of the group.
  *
  * Control flow: one loop body = "apply an input, then collision-check", used both for noisy microsteps and for
@@ -303,11 +406,13 @@ UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim&
     const int width = (M::HAS_FRAMES) ? dof : M::WIDTH;
     M m;
     if constexpr (M::HAS_FRAMES) m.frames = frames0;
+    double* target = park;
+    double* previous = park + M::WIDTH;
+    m.pid_i = park + 2 * M::WIDTH;
+    m.pid_e = park + 2 * M::WIDTH + M::DOF;
     m.load(r, starts, n, i);
     m.reset_controllers();
     refresh_frames(r, m, g);
-    double* target = park;
-    double* previous = park + M::WIDTH;
     {
         const int64_t ti = (n_targets == 1) ? 0 : i;
         if (g.sub == 0)
@@ -321,6 +426,7 @@ UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim&
     for (int step = 0; step < sp.num_steps; step++)
     {
         cnt.particle_steps++;
+        UPC_T0
         double vec[N];   /* the input about to be estimated / applied: control step, then resolver corrections */
         double ustep[N]; /* control input per microstep */
         {
@@ -328,11 +434,16 @@ UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim&
 #pragma unroll
             for (int d = 0; d < N; d++)
                 if (d < dof) draws[d] = tape[(((int64_t)step * slots) * dof + d) * n + i];
+#ifdef UPC_PHASE_TIMING
+            if (draws[0] == 123.456) cnt.particle_steps++; /* force the loads to complete inside this phase */
+#endif
+            UPC_T1(6)
             double u[N];
             m.control(r, target, sp.dt, draws, u);
 #pragma unroll
             for (int d = 0; d < N; d++)
                 if (d < dof) vec[d] = u[d] * sp.dt;
+            UPC_T1(0)
         }
         unsigned microsteps = 1u, ms = 0u;
         bool resolving = false;    /* false: next action is a (noisy) microstep; true: a resolver correction */
@@ -371,6 +482,7 @@ UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim&
                         if (d < dof) apply_in[d] = vec[d] * total_scale;
                 }
                 need_estimate = false;
+                UPC_T1(1)
             }
             if (!resolving)
             {
@@ -387,9 +499,12 @@ UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim&
                     }
                 noise = draws;
             }
+            UPC_T1(6)
             m.apply(r, apply_in, noise);
             refresh_frames(r, m, g);
+            UPC_T1(2)
             bool in_collision = check_collision(env, r, m, g, pts, sp.contact_distance);
+            UPC_T1(3)
             bool revert = false;
             if (!resolving)
             {
@@ -428,7 +543,8 @@ UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim&
             if (resolving && in_collision && !revert)
             {
                 /* next action: a resolver correction from the current configuration */
-                const int contributing = resolver_correction(env, r, sp, m, g, pts, vec);
+                const int contributing = resolver_correction(env, r, sp, m, g, pts, vec, cnt);
+                UPC_T1(4)
                 if (contributing == 0)
                 {
                     revert = true;
@@ -457,7 +573,9 @@ UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim&
                 if (ms >= microsteps) step_done = true;
             }
         }
-        if (m.reached(r, target, sp.shortcut)) break;
+        const bool arrived = m.reached(r, target, sp.shortcut);
+        UPC_T1(5)
+        if (arrived) break;
     }
     if (g.sub == 0)
     {
