@@ -173,6 +173,7 @@ def run_reference(args):
     from oracle import binding as oracle
     from uncertainty_planning_core_b200 import abi
     oracle.build()
+    oracle.set_num_threads(os.cpu_count() or 1)
     sc = make_workload(args, 0)
     cp = cluster_params()
     cores = oracle.num_threads()
@@ -219,7 +220,9 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    sc = make_workload(args, edge=rank)
+    # every rank runs its own attempt of the same planner edge (the planner repeats an edge `edge_attempt_count` times,
+    # uncertainty_planning_core.hpp:61): same endpoints, independent noise, equal work per GPU
+    sc = make_workload(args, edge=0)
     cp = cluster_params()
     params = sc["params"]
     robot, env = sc["robot"], sc["env"]
@@ -357,6 +360,7 @@ def run_b200(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             from oracle import binding as oracle
+            oracle.set_num_threads(os.cpu_count() or 1)
             sample = args.cpu_sample or auto_cpu_sample(sc, cp)
             ctape = abi.fill_noise_tape(sc["seed"], robot, params, sample)
             t_sim, t_cl, steps_done, ncl = cpu_path(sc, cp, sample, ctape)
@@ -370,6 +374,7 @@ def run_b200(args):
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic (seeded boxes SDF, replicated start, truncated-normal noise tape)",
             "config": {"workload": sc["label"], "edges_per_step": world, "particles_per_gpu": n,
+                       "sharding": "one attempt of the edge per GPU (same endpoints, independent noise), SDF replicated, one all-gather of outcome records",
                        "clustering": "CRS signatures (thr 0.125) + distance pass (thr 0.1)",
                        "lanes_per_particle": args.lanes or "auto",
                        "l2": "ring of %d distinct %.0f MB noise tapes (%.0f MB > 126 MB L2) so the streamed input is never cached; the %.0f MiB SDF is "
@@ -392,6 +397,11 @@ def run_b200(args):
 
 if __name__ == "__main__":
     a = parse_args()
+    # torchrun exports OMP_NUM_THREADS=1; the host-side pieces (tape generation, the CPU arm) are OpenMP code and the
+    # CPU arm is meant to use every host core ("with all the host threads it can use")
+    _world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+    _cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(_cores if a.impl == "reference" else max(1, _cores // max(1, _world)))
     if a.impl == "reference":
         run_reference(a)
     else:

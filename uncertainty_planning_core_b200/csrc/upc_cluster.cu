@@ -464,44 +464,6 @@ __global__ void __launch_bounds__(256) root_check_kernel(const uint32_t* __restr
     }
 }
 
-/* connected components of the threshold graph by min-label propagation + pointer jumping (fallback path only) */
-__global__ void __launch_bounds__(256) propagate_kernel(const uint32_t* __restrict__ adj, int64_t total, int64_t set_size, int wpr,
-                                                        const int32_t* __restrict__ set_bad, int32_t* __restrict__ comp,
-                                                        int* __restrict__ changed)
-{
-    const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (p >= total) return;
-    const int64_t set = p / set_size;
-    if (!set_bad[set]) return;
-    const uint32_t* row = adj + p * wpr;
-    const int32_t* sc = comp + set * set_size;
-    int32_t best = sc[p - set * set_size];
-    for (int w = lane; w < wpr; w += 32)
-    {
-        uint32_t v = row[w];
-        while (v)
-        {
-            const int b = __ffs((int)v) - 1;
-            v &= v - 1u;
-            const int32_t c = sc[w * 32 + b];
-            best = min(best, c);
-        }
-    }
-    for (int off = 16; off > 0; off >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, off));
-    if (lane == 0)
-    {
-        /* pointer jumping */
-        int32_t r = best;
-        while (sc[r] < r) r = sc[r];
-        if (r < comp[p])
-        {
-            comp[p] = r;
-            *changed = 1;
-        }
-    }
-}
-
 __global__ void iota_in_set_kernel(int32_t* out, int64_t total, int64_t set_size)
 {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -541,37 +503,56 @@ __global__ void __launch_bounds__(1024) label_kernel(const int32_t* __restrict__
     if (threadIdx.x == 0) n_clusters[blockIdx.x] = s_running;
 }
 
-/* ------------------------------------------------------------------ exact complete link on non-clique components */
+/* ------------------------------------------------------------------ exact complete link for sets that are not unions of cliques */
 
-struct MatrixArgs
+/*
+ * Complete-link agglomeration cut at the threshold, parallel form.  Order all cluster pairs by the
+ * key (distance, smaller representative, larger representative).  Complete linkage is reducible
+ * (d(k, a U b) = max(d(k,a), d(k,b)) never undercuts d(k,a) or d(k,b)), so a pair whose members are each other's
+ * nearest neighbour under that order stays so until it is merged: all such reciprocal pairs within the threshold
+ * can be merged in the same round, and the partition reached when no pair is left within the threshold is the one
+ * the sequential rule produces.  Each round is a handful of fully parallel passes over the FP64 distance matrices
+ * of the affected sets; the number of rounds is logarithmic for blob-like data.
+ */
+struct ExactArgs
 {
     DevRobot robot;
     const double* feat;   /* config features [F][total] or null */
     const uint32_t* sig;  /* signatures [P][total] or null */
+    const int32_t* group; /* optional first-pass groups: pairs across groups never merge */
     int nfeat, num_points;
-    int64_t total;
-    const int64_t* members;    /* global particle index of every member, components concatenated */
-    const int64_t* comp_off;   /* per component: offset into members */
-    const int64_t* matrix_off; /* per component: offset into matrices */
-    double* matrices;
+    int64_t total, set_size;
+    const int32_t* bad_sets; /* indices of the sets being clustered exactly */
+    int nbad;
+    double* D;        /* [nbad][m][m] */
+    uint8_t* active;  /* [nbad][m] */
+    int32_t* nn;      /* [nbad][m] nearest active neighbour under the key order */
+    int32_t* partner; /* [nbad][m] b if row a absorbs b this round, else -1 */
+    int32_t* into;    /* [nbad][m] representative chain */
+    double threshold;
+    int* merged_flag;
 };
 
 template <int KIND>
-__global__ void __launch_bounds__(256) component_matrix_kernel(const __grid_constant__ MatrixArgs a)
+__global__ void __launch_bounds__(256) exact_matrix_kernel(const __grid_constant__ ExactArgs a)
 {
     constexpr int MAXF = PairDistance<KIND>::MAXF;
-    const int comp = blockIdx.y;
-    const int64_t off = a.comp_off[comp];
-    const int64_t m = a.comp_off[comp + 1] - off;
-    double* D = a.matrices + a.matrix_off[comp];
+    const int s = blockIdx.y;
+    const int64_t m = a.set_size;
+    const int64_t base = (int64_t)a.bad_sets[s] * m;
+    double* D = a.D + (int64_t)s * m * m;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < m * m; e += (int64_t)gridDim.x * blockDim.x)
     {
         const int64_t i = e / m, j = e % m;
         double d = 0.0;
         if (i != j)
         {
-            const int64_t pi = a.members[off + i], pj = a.members[off + j];
-            if (a.sig)
+            const int64_t pi = base + i, pj = base + j;
+            if (a.group && a.group[pi] != a.group[pj])
+            {
+                d = INFINITY;
+            }
+            else if (a.sig)
             {
                 int mism = 0;
                 for (int k = 0; k < a.num_points; k++)
@@ -590,149 +571,158 @@ __global__ void __launch_bounds__(256) component_matrix_kernel(const __grid_cons
                     fa[f] = (f < a.nfeat) ? a.feat[(int64_t)f * a.total + pi] : 0.0;
                     fb[f] = (f < a.nfeat) ? a.feat[(int64_t)f * a.total + pj] : 0.0;
                 }
-                d = PairDistance<KIND>::eval(a.robot, fa, fb);
+                /* evaluate with the smaller index first, like BuildDistanceMatrix does for the upper triangle */
+                d = (i < j) ? PairDistance<KIND>::eval(a.robot, fa, fb) : PairDistance<KIND>::eval(a.robot, fb, fa);
             }
         }
         D[e] = d;
     }
-}
-
-struct LinkArgs
-{
-    const int64_t* comp_off;
-    const int64_t* matrix_off;
-    double* matrices;
-    double threshold;
-    /* per-member scratch, concatenated like members */
-    double* rmin;
-    int32_t* rarg;
-    int32_t* parent;
-    uint8_t* active;
-    uint8_t* valid;
-    int32_t* rep; /* out: representative (position within the component) of every member */
-};
-
-/*
- * Complete-link agglomeration cut at `threshold`, one CTA per component.
- * D is updated in place with the Lance-Williams rule d(k, a U b) = max(d(k,a), d(k,b)); each row keeps its
- * nearest later active row; ties resolve to the smallest (a, b) lexicographically.
- */
-__global__ void __launch_bounds__(256) complete_link_kernel(const __grid_constant__ LinkArgs a)
-{
-    const int comp = blockIdx.x;
-    const int64_t off = a.comp_off[comp];
-    const int m = (int)(a.comp_off[comp + 1] - off);
-    double* D = a.matrices + a.matrix_off[comp];
-    double* rmin = a.rmin + off;
-    int32_t* rarg = a.rarg + off;
-    int32_t* parent = a.parent + off;
-    uint8_t* active = a.active + off;
-    uint8_t* valid = a.valid + off;
-    __shared__ double s_val[8];
-    __shared__ int s_idx[8];
-    __shared__ double s_best;
-    __shared__ int s_a, s_b;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int k = threadIdx.x; k < m; k += 256)
+    if (blockIdx.x == 0)
     {
-        active[k] = 1; valid[k] = 0; parent[k] = k;
-    }
-    __syncthreads();
-    while (true)
-    {
-        /* refresh nearest-later-neighbour of invalid rows, one warp per row */
-        for (int r = warp; r < m; r += 8)
+        for (int64_t k = threadIdx.x; k < m; k += blockDim.x)
         {
-            if (!active[r] || valid[r]) continue;
-            double bv = INFINITY;
-            int bi = -1;
-            for (int c = r + 1 + lane; c < m; c += 32)
-            {
-                if (!active[c]) continue;
-                const double d = D[(int64_t)r * m + c];
-                if (d < bv) { bv = d; bi = c; }
-            }
-            for (int o = 16; o > 0; o >>= 1)
-            {
-                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (oi >= 0 && (bi < 0 || ov < bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
-            }
-            if (lane == 0) { rmin[r] = bv; rarg[r] = bi; valid[r] = 1; }
+            a.active[(int64_t)s * m + k] = 1;
+            a.into[(int64_t)s * m + k] = (int32_t)k;
+            a.partner[(int64_t)s * m + k] = -1;
         }
-        __syncthreads();
-        /* global minimum over rows, ties to the smallest row */
-        double bv = INFINITY;
-        int bi = -1;
-        for (int r = threadIdx.x; r < m; r += 256)
-        {
-            if (!active[r] || rarg[r] < 0) continue;
-            const double d = rmin[r];
-            if (bi < 0 || d < bv) { bv = d; bi = r; }
-        }
-        for (int o = 16; o > 0; o >>= 1)
-        {
-            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (oi >= 0 && (bi < 0 || ov < bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
-        }
-        if (lane == 0) { s_val[warp] = bv; s_idx[warp] = bi; }
-        __syncthreads();
-        if (threadIdx.x == 0)
-        {
-            double v = INFINITY;
-            int idx = -1;
-            for (int w = 0; w < 8; w++)
-            {
-                if (s_idx[w] >= 0 && (idx < 0 || s_val[w] < v || (s_val[w] == v && s_idx[w] < idx))) { v = s_val[w]; idx = s_idx[w]; }
-            }
-            s_best = v;
-            s_a = idx;
-            s_b = (idx >= 0) ? rarg[idx] : -1;
-        }
-        __syncthreads();
-        const int ra = s_a, rb = s_b;
-        if (ra < 0 || !(s_best <= a.threshold)) break;
-        /* merge rb into ra */
-        for (int k = threadIdx.x; k < m; k += 256)
-        {
-            if (!active[k] || k == ra || k == rb) continue;
-            const double da = D[(int64_t)ra * m + k], db = D[(int64_t)rb * m + k];
-            const double nd = (da < db) ? db : da;
-            D[(int64_t)ra * m + k] = nd;
-            D[(int64_t)k * m + ra] = nd;
-            if (rarg[k] == ra || rarg[k] == rb) valid[k] = 0;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0)
-        {
-            active[rb] = 0;
-            parent[rb] = ra;
-            valid[ra] = 0;
-        }
-        __syncthreads();
-    }
-    for (int k = threadIdx.x; k < m; k += 256)
-    {
-        int r = k;
-        while (parent[r] != r) r = parent[r];
-        a.rep[off + k] = r;
     }
 }
 
-__global__ void scatter_roots_kernel(const int64_t* members, const int64_t* comp_off, int ncomp, const int32_t* rep, int64_t set_size,
-                                     int32_t* root)
+/* nearest active neighbour of every active row: key (distance, min(row, col), max(row, col)); one warp per row */
+__global__ void __launch_bounds__(256) exact_nearest_kernel(const __grid_constant__ ExactArgs a)
 {
-    const int comp = blockIdx.x;
-    const int64_t off = comp_off[comp];
-    const int64_t m = comp_off[comp + 1] - off;
-    for (int64_t k = threadIdx.x; k < m; k += blockDim.x)
+    const int64_t m = a.set_size;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= (int64_t)a.nbad * m) return;
+    const int s = (int)(w / m);
+    const int row = (int)(w - (int64_t)s * m);
+    const uint8_t* active = a.active + (int64_t)s * m;
+    if (!active[row])
     {
-        const int64_t p = members[off + k];
-        const int64_t rp = members[off + rep[off + k]];
-        root[p] = (int32_t)(rp % set_size);
+        if (lane == 0) a.nn[w] = -1;
+        return;
     }
-    (void)ncomp;
+    const double* Drow = a.D + ((int64_t)s * m + row) * m;
+    double bv = INFINITY;
+    int bi = -1;
+    for (int c = lane; c < m; c += 32)
+    {
+        if (c == row || !active[c]) continue;
+        const double d = Drow[c];
+        bool better;
+        if (bi < 0) better = true;
+        else if (d != bv) better = d < bv;
+        else
+        {
+            const int lo1 = min(row, c), hi1 = max(row, c), lo0 = min(row, bi), hi0 = max(row, bi);
+            better = (lo1 < lo0) || (lo1 == lo0 && hi1 < hi0);
+        }
+        if (better) { bv = d; bi = c; }
+    }
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        bool better = false;
+        if (oi >= 0)
+        {
+            if (bi < 0) better = true;
+            else if (ov != bv) better = ov < bv;
+            else
+            {
+                const int lo1 = min(row, oi), hi1 = max(row, oi), lo0 = min(row, bi), hi0 = max(row, bi);
+                better = (lo1 < lo0) || (lo1 == lo0 && hi1 < hi0);
+            }
+        }
+        if (better) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) a.nn[w] = bi;
+}
+
+/* reciprocal nearest pairs within the threshold: the smaller representative absorbs the larger */
+__global__ void __launch_bounds__(256) exact_mark_kernel(const __grid_constant__ ExactArgs a)
+{
+    const int64_t m = a.set_size;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)a.nbad * m) return;
+    const int s = (int)(t / m);
+    const int row = (int)(t - (int64_t)s * m);
+    int partner = -1;
+    const int b = a.nn[t];
+    if (b > row && a.nn[(int64_t)s * m + b] == row)
+    {
+        const double d = a.D[((int64_t)s * m + row) * m + b];
+        if (d <= a.threshold)
+        {
+            partner = b;
+            *a.merged_flag = 1;
+        }
+    }
+    a.partner[t] = partner;
+}
+
+/* Lance-Williams, rows: D[a][k] = max(D[a][k], D[b][k]) for every absorbing row a */
+__global__ void __launch_bounds__(256) exact_row_merge_kernel(const __grid_constant__ ExactArgs a)
+{
+    const int64_t m = a.set_size;
+    const int s = blockIdx.z;
+    const int row = blockIdx.y;
+    const int b = a.partner[(int64_t)s * m + row];
+    if (b < 0) return;
+    double* Da = a.D + ((int64_t)s * m + row) * m;
+    const double* Db = a.D + ((int64_t)s * m + b) * m;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += (int64_t)gridDim.x * blockDim.x)
+    {
+        const double x = Da[k], y = Db[k];
+        Da[k] = (x < y) ? y : x;
+    }
+}
+
+/* Lance-Williams, columns: D[k][a] = max(D[k][a], D[k][b]) for every row k; then retire the absorbed rows */
+__global__ void __launch_bounds__(256) exact_col_merge_kernel(const __grid_constant__ ExactArgs a)
+{
+    const int64_t m = a.set_size;
+    const int s = blockIdx.z;
+    const int row = blockIdx.y;
+    if (!a.active[(int64_t)s * m + row]) return;
+    double* Dk = a.D + ((int64_t)s * m + row) * m;
+    const int32_t* partner = a.partner + (int64_t)s * m;
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < m; c += (int64_t)gridDim.x * blockDim.x)
+    {
+        const int b = partner[c];
+        if (b >= 0 && c != row)
+        {
+            const double x = Dk[c], y = Dk[b];
+            Dk[c] = (x < y) ? y : x;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) exact_retire_kernel(const __grid_constant__ ExactArgs a)
+{
+    const int64_t m = a.set_size;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)a.nbad * m) return;
+    const int b = a.partner[t];
+    if (b >= 0)
+    {
+        const int64_t s = t / m;
+        a.active[s * m + b] = 0;
+        a.into[s * m + b] = (int32_t)(t - s * m);
+    }
+}
+
+__global__ void __launch_bounds__(256) exact_roots_kernel(const __grid_constant__ ExactArgs a, int32_t* root)
+{
+    const int64_t m = a.set_size;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)a.nbad * m) return;
+    const int64_t s = t / m;
+    const int32_t* into = a.into + s * m;
+    int r = (int)(t - s * m);
+    while (into[r] != r) r = into[r];
+    root[(int64_t)a.bad_sets[s] * m + (t - s * m)] = r;
 }
 
 /* ------------------------------------------------------------------ host orchestration */
@@ -814,87 +804,59 @@ static int32_t cluster_pass(upc_handle* h, const PassInput& in, int64_t n_sets, 
     if (nbad == 0 || !in.allow_exact) return UPC_OK;
 
     /* ---- exact path for the sets whose threshold graph is not a union of cliques ---- */
-    int32_t* comp = buf<int32_t>(h->cw.comp, (size_t)total);
-    UPC_NULLCHECK(comp);
-    iota_in_set_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(comp, total, set_size);
-    int* d_changed = (int*)buf<int>(h->cw.misc, 16);
-    UPC_NULLCHECK(d_changed);
-    for (int iter = 0; iter < 100000; iter++)
-    {
-        UPC_CUDA_TRY(cudaMemsetAsync(d_changed, 0, sizeof(int), stream));
-        propagate_kernel<<<(unsigned)((total * 32 + 255) / 256), 256, 0, stream>>>(adj, total, set_size, wpr, set_bad, comp, d_changed);
-        h->stats.kernel_launches++;
-        int changed = 0;
-        UPC_CUDA_TRY(cudaMemcpyAsync(&changed, d_changed, sizeof(int), cudaMemcpyDeviceToHost, stream));
-        UPC_CUDA_TRY(cudaStreamSynchronize(stream));
-        if (!changed) break;
-    }
-    std::vector<int32_t> h_comp((size_t)total);
-    std::vector<uint8_t> h_ok((size_t)total);
-    UPC_CUDA_TRY(cudaMemcpyAsync(h_comp.data(), comp, (size_t)total * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-    UPC_CUDA_TRY(cudaMemcpyAsync(h_ok.data(), row_ok, (size_t)total, cudaMemcpyDeviceToHost, stream));
-    UPC_CUDA_TRY(cudaStreamSynchronize(stream));
-    h->stats.d2h_bytes += total * 5;
-    /* components that contain a row differing from its root's row */
-    std::vector<int64_t> members, comp_off(1, 0), matrix_off(1, 0);
+    std::vector<int32_t> bad_sets;
     for (int64_t s = 0; s < n_sets; s++)
-    {
-        if (!bad[(size_t)s]) continue;
-        std::map<int32_t, std::vector<int64_t>> groups;
-        std::map<int32_t, bool> dirty;
-        for (int64_t i = 0; i < set_size; i++)
-        {
-            const int64_t p = s * set_size + i;
-            groups[h_comp[(size_t)p]].push_back(p);
-            if (!h_ok[(size_t)p]) dirty[h_comp[(size_t)p]] = true;
-        }
-        for (auto& kv : groups)
-        {
-            if (!dirty.count(kv.first)) continue;
-            members.insert(members.end(), kv.second.begin(), kv.second.end());
-            comp_off.push_back((int64_t)members.size());
-            matrix_off.push_back(matrix_off.back() + (int64_t)(kv.second.size() * kv.second.size()));
-        }
-    }
-    const int ncomp = (int)comp_off.size() - 1;
-    if (ncomp == 0) return UPC_OK;
-    const size_t nm = members.size();
-    int64_t* d_members = buf<int64_t>(h->cw.members, nm + comp_off.size() + matrix_off.size());
-    UPC_NULLCHECK(d_members);
-    int64_t* d_comp_off = d_members + nm;
-    int64_t* d_matrix_off = d_comp_off + comp_off.size();
-    UPC_CUDA_TRY(cudaMemcpyAsync(d_members, members.data(), nm * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
-    UPC_CUDA_TRY(cudaMemcpyAsync(d_comp_off, comp_off.data(), comp_off.size() * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
-    UPC_CUDA_TRY(cudaMemcpyAsync(d_matrix_off, matrix_off.data(), matrix_off.size() * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
-    h->stats.h2d_bytes += (int64_t)((nm + comp_off.size() + matrix_off.size()) * sizeof(int64_t));
-    double* d_mat = buf<double>(h->cw.dist_matrix, (size_t)matrix_off.back());
+        if (bad[(size_t)s]) bad_sets.push_back((int32_t)s);
+    const int nb = (int)bad_sets.size();
+    const int64_t m = set_size;
+    ExactArgs ea;
+    ea.robot = h->robot; ea.feat = in.feat; ea.sig = in.sig; ea.group = in.group; ea.nfeat = in.nfeat; ea.num_points = h->robot.num_points;
+    ea.total = total; ea.set_size = set_size; ea.nbad = nb; ea.threshold = in.threshold;
+    double* d_mat = buf<double>(h->cw.dist_matrix, (size_t)nb * (size_t)m * (size_t)m);
     UPC_NULLCHECK(d_mat);
-    /* per-member scratch: rmin (8) + rarg, parent, rep (4 each) + active, valid (1 each) */
-    uint8_t* scratch = buf<uint8_t>(h->cw.link_scratch, nm * 24 + 64);
+    /* [bad_sets i32 nb | nn, partner, into i32 nb*m each | active u8 nb*m | flag] */
+    const size_t per = (size_t)nb * (size_t)m;
+    uint8_t* scratch = buf<uint8_t>(h->cw.link_scratch, (size_t)nb * 4 + per * 13 + 64);
     UPC_NULLCHECK(scratch);
-    MatrixArgs ma;
-    ma.robot = h->robot; ma.feat = in.feat; ma.sig = in.sig; ma.nfeat = in.nfeat; ma.num_points = h->robot.num_points; ma.total = total;
-    ma.members = d_members; ma.comp_off = d_comp_off; ma.matrix_off = d_matrix_off; ma.matrices = d_mat;
+    int32_t* d_bad = (int32_t*)scratch;
+    ea.bad_sets = d_bad;
+    ea.nn = d_bad + nb;
+    ea.partner = ea.nn + per;
+    ea.into = ea.partner + per;
+    ea.active = (uint8_t*)(ea.into + per);
+    ea.merged_flag = (int*)buf<int>(h->cw.misc, 16);
+    UPC_NULLCHECK(ea.merged_flag);
+    ea.D = d_mat;
+    UPC_CUDA_TRY(cudaMemcpyAsync(d_bad, bad_sets.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, stream));
+    h->stats.h2d_bytes += nb * 4;
     {
-        dim3 grid(64, (unsigned)ncomp);
-        if (kind == UPC_ROBOT_SE2) component_matrix_kernel<UPC_ROBOT_SE2><<<grid, 256, 0, stream>>>(ma);
-        else if (kind == UPC_ROBOT_SE3) component_matrix_kernel<UPC_ROBOT_SE3><<<grid, 256, 0, stream>>>(ma);
-        else component_matrix_kernel<UPC_ROBOT_LINKED><<<grid, 256, 0, stream>>>(ma);
+        dim3 grid((unsigned)std::min<int64_t>(2048, (m * m + 255) / 256), (unsigned)nb);
+        if (kind == UPC_ROBOT_SE2) exact_matrix_kernel<UPC_ROBOT_SE2><<<grid, 256, 0, stream>>>(ea);
+        else if (kind == UPC_ROBOT_SE3) exact_matrix_kernel<UPC_ROBOT_SE3><<<grid, 256, 0, stream>>>(ea);
+        else exact_matrix_kernel<UPC_ROBOT_LINKED><<<grid, 256, 0, stream>>>(ea);
         h->stats.kernel_launches++;
         UPC_CUDA_TRY(cudaGetLastError());
     }
-    LinkArgs la;
-    la.comp_off = d_comp_off; la.matrix_off = d_matrix_off; la.matrices = d_mat; la.threshold = in.threshold;
-    la.rmin = (double*)scratch;
-    la.rarg = (int32_t*)(scratch + nm * 8);
-    la.parent = (int32_t*)(scratch + nm * 12);
-    la.rep = (int32_t*)(scratch + nm * 16);
-    la.active = scratch + nm * 20;
-    la.valid = scratch + nm * 21;
-    complete_link_kernel<<<(unsigned)ncomp, 256, 0, stream>>>(la);
-    h->stats.kernel_launches++;
-    UPC_CUDA_TRY(cudaGetLastError());
-    scatter_roots_kernel<<<(unsigned)ncomp, 256, 0, stream>>>(d_members, d_comp_off, ncomp, la.rep, set_size, d_root);
+    const unsigned row_blocks = (unsigned)((per + 255) / 256);
+    const unsigned warp_blocks = (unsigned)((per * 32 + 255) / 256);
+    const dim3 merge_grid((unsigned)std::min<int64_t>(8, (m + 255) / 256), (unsigned)m, (unsigned)nb);
+    for (int round = 0; round < 1 << 20; round++)
+    {
+        UPC_CUDA_TRY(cudaMemsetAsync(ea.merged_flag, 0, sizeof(int), stream));
+        exact_nearest_kernel<<<warp_blocks, 256, 0, stream>>>(ea);
+        exact_mark_kernel<<<row_blocks, 256, 0, stream>>>(ea);
+        h->stats.kernel_launches += 2;
+        int merged = 0;
+        UPC_CUDA_TRY(cudaMemcpyAsync(&merged, ea.merged_flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        UPC_CUDA_TRY(cudaStreamSynchronize(stream));
+        if (!merged) break;
+        exact_row_merge_kernel<<<merge_grid, 256, 0, stream>>>(ea);
+        exact_col_merge_kernel<<<merge_grid, 256, 0, stream>>>(ea);
+        exact_retire_kernel<<<row_blocks, 256, 0, stream>>>(ea);
+        h->stats.kernel_launches += 3;
+        UPC_CUDA_TRY(cudaGetLastError());
+    }
+    exact_roots_kernel<<<row_blocks, 256, 0, stream>>>(ea, d_root);
     h->stats.kernel_launches++;
     UPC_CUDA_TRY(cudaGetLastError());
     return UPC_OK;
