@@ -288,7 +288,82 @@ def cl_linked_crs():
     return dict(env=env, robot=robot, configs=cfg, cparams=_cparams(feature=abi.FEATURE_CRS, sig_thr=0.05, dist_thr=0.1))
 
 
+def _with_ptpm(case, num_steps=30, goal=0.06, seed=71):
+    """attach POINT_TO_POINT_MOVEMENT inputs: simulation parameters and the tape of the n*(n-1) pair simulations"""
+    import ctypes as C
+    n = case["configs"].shape[0]
+    sp = abi.make_sim_params(num_steps, 0.01, case["env"].resolution, allow_contacts=True)
+    sp.simulation_shortcut_distance = goal * 0.5
+    tape = abi.fill_noise_tape(seed, case["robot"], sp, n * n - n)
+    cp = case["cparams"]
+    cp.feature_type = abi.FEATURE_PTPM
+    cp.goal_distance_threshold = goal
+    cp.ptpm_sim = C.pointer(sp)
+    cp.ptpm_tape = tape.ctypes.data
+    case["ptpm"] = (sp, tape, goal)  # keeps the buffers alive
+    return case
+
+
+def cl_se2_ac():
+    """two groups of particles on either side of an obstacle: the straight lines between them are blocked"""
+    sc = scenarios.c1_se2(seed=11, n=1, shape=(128, 128, 1), resolution=0.08)
+    env, robot, boxes = sc["env"], sc["robot"], sc["boxes"]
+    b = boxes[0]
+    rng = np.random.default_rng(48)
+    n = 90
+    side = np.where(rng.random(n) < 0.5, -1.0, 1.0)
+    x = b[0] + side * (b[3] + 0.35) + rng.uniform(-0.03, 0.03, n)
+    y = b[1] + rng.uniform(-0.03, 0.03, n)
+    cfg = np.stack([x, y, rng.uniform(-0.1, 0.1, n)], axis=1)
+    return dict(env=env, robot=robot, configs=cfg, cparams=_cparams(feature=abi.FEATURE_AC, dist_thr=0.2))
+
+
+def cl_se3_ac_messy():
+    sc = scenarios.c2_se3(seed=21, n=1, shape=(64, 64, 64), resolution=0.0625)
+    rng = np.random.default_rng(49)
+    n = 70
+    cfg = np.zeros((n, 12))
+    for i in range(n):
+        R = scenarios.rotation_from_axis_angle(rng.normal(size=3), rng.uniform(0.0, 0.3))
+        cfg[i] = scenarios.se3_config(R, rng.uniform(0.8, 3.2, size=3))
+    return dict(env=sc["env"], robot=sc["robot"], configs=cfg, cparams=_cparams(feature=abi.FEATURE_AC, dist_thr=1.5))
+
+
+def cl_linked_ac():
+    env, robot = _linked_env_robot()
+    rng = np.random.default_rng(50)
+    n = 48
+    cfg = rng.uniform(-0.05, 0.05, size=(n, 7))
+    cfg[:, 1] += np.where(rng.random(n) < 0.5, -0.5, 0.55)
+    return dict(env=env, robot=robot, configs=cfg, cparams=_cparams(feature=abi.FEATURE_AC, dist_thr=0.3))
+
+
+def cl_se2_ptpm():
+    """particles on two sides of a wall corner: moving between the groups fails, moving within succeeds"""
+    c = cl_se2_ac()
+    c["configs"] = c["configs"][:26]
+    c["cparams"] = _cparams(dist_thr=0.2)
+    return _with_ptpm(c, num_steps=40, goal=0.05)
+
+
+def cl_se3_ptpm():
+    env, robot = _se3_env_robot()
+    rng = np.random.default_rng(54)
+    n = 14
+    cfg = np.zeros((n, 12))
+    for i in range(n):
+        R = scenarios.rotation_from_axis_angle(rng.normal(size=3), rng.uniform(0.0, 0.05))
+        x = (1.7 if i % 2 == 0 else 2.0) + rng.uniform(-0.02, 0.02)
+        cfg[i] = scenarios.se3_config(R, [x, 1.5 + rng.uniform(-0.02, 0.02), 1.5])
+    return _with_ptpm(dict(env=env, robot=robot, configs=cfg, cparams=_cparams(dist_thr=0.1)), num_steps=25, goal=0.08)
+
+
 GOLDEN_CLUSTER_CASES = {
+    "se2_ac": cl_se2_ac,
+    "se3_ac_messy": cl_se3_ac_messy,
+    "linked_ac": cl_linked_ac,
+    "se2_ptpm": cl_se2_ptpm,
+    "se3_ptpm": cl_se3_ptpm,
     "se2_blobs": cl_se2_blobs,
     "se2_single_blob": cl_se2_single_blob,
     "se2_chain": cl_se2_chain,

@@ -64,8 +64,11 @@ def test_clustering_matches_oracle(oracle, simulators, name):
     g = np.load(os.path.join(HERE, "golden", "cluster_%s.npz" % name))
     assert np.array_equal(olabels, g["labels"]) and np.array_equal(oncl, g["n_clusters"])
     sim = simulators("cl_" + name, c["env"], c["robot"])
+    ptpm = c.get("ptpm")
     oc = OutcomeClustering(sim, c["cparams"].feature_type, c["cparams"].signature_matching_threshold,
-                           c["cparams"].distance_clustering_threshold)
+                           c["cparams"].distance_clustering_threshold,
+                           goal_distance_threshold=c["cparams"].goal_distance_threshold,
+                           ptpm_params=ptpm[0] if ptpm else None, ptpm_tape=ptpm[1] if ptpm else None)
     labels, ncl = oc.ClusterIndices(c["configs"], n_sets)
     assert np.array_equal(ncl, oncl), name
     assert np.array_equal(labels, olabels), name
@@ -164,8 +167,8 @@ def test_errors_mirror_the_reference_interface(simulators):
     with pytest.raises(ValueError):
         sim.ForwardSimulateRobots(sc["starts"], sc["targets"], tape, bad)
     from uncertainty_planning_core_b200 import OutcomeClustering
-    oc = OutcomeClustering(sim, abi.FEATURE_AC)
-    with pytest.raises(abi.UpcError):
+    oc = OutcomeClustering(sim, abi.FEATURE_PTPM)          # no simulation parameters / tape given
+    with pytest.raises(ValueError):
         oc.ClusterIndices(sc["starts"])
     cfg, coll = sim.ForwardSimulateRobots(sc["starts"][:0], sc["targets"], tape[..., :0], sc["params"])  # empty batch
     assert cfg.shape == (0, 3) and coll.shape == (0,)

@@ -495,7 +495,19 @@ int32_t upc_cluster_particles(upc_handle* h, const upc_cluster_params* params, i
     UPC_CUDA_TRY(h->st_ncl.reserve((size_t)n_sets * sizeof(int32_t) + 64));
     UPC_CUDA_TRY(cudaMemcpyAsync(h->st_starts.ptr, configs, cfg_bytes, cudaMemcpyHostToDevice, h->stream));
     h->stats.h2d_bytes += (int64_t)cfg_bytes;
-    const int32_t rc = upc_cluster_particles_device(h, params, n_sets, set_size, (const double*)h->st_starts.ptr, (int32_t*)h->st_labels.ptr,
+    upc_cluster_params local = *params;
+    if (params->feature_type == UPC_FEATURE_POINT_TO_POINT_MOVEMENT && params->ptpm_sim && params->ptpm_tape && set_size > 1)
+    {
+        /* the pair simulations' tape arrives in host memory here */
+        const int64_t sims = set_size * set_size - set_size;
+        if (params->ptpm_sim->num_steps < 1 || params->ptpm_sim->max_microsteps < 1) return fail_arg("bad step counts");
+        const size_t tape_bytes = (size_t)upc_tape_doubles_per_particle(params->ptpm_sim, h->robot.dof) * (size_t)sims * sizeof(double);
+        UPC_CUDA_TRY(h->st_tape.reserve(tape_bytes));
+        UPC_CUDA_TRY(cudaMemcpyAsync(h->st_tape.ptr, params->ptpm_tape, tape_bytes, cudaMemcpyHostToDevice, h->stream));
+        h->stats.h2d_bytes += (int64_t)tape_bytes;
+        local.ptpm_tape = (const double*)h->st_tape.ptr;
+    }
+    const int32_t rc = upc_cluster_particles_device(h, &local, n_sets, set_size, (const double*)h->st_starts.ptr, (int32_t*)h->st_labels.ptr,
                                                     (int32_t*)h->st_ncl.ptr, h->stream);
     if (rc != UPC_OK) return rc;
     UPC_CUDA_TRY(cudaMemcpyAsync(labels, h->st_labels.ptr, (size_t)total * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));

@@ -424,6 +424,185 @@ __global__ void __launch_bounds__(256) signature_adjacency_kernel(const __grid_c
     }
 }
 
+/* ------------------------------------------------------------------ actuation-centre connectivity (AC first pass) */
+
+struct CenterArgs
+{
+    DevRobot robot;
+    const double* cfg;
+    int64_t total;
+    double* centers; /* [num_links*3][total]: link frame origins */
+    double* frames;  /* linked only */
+};
+
+/* link origins of every particle (uncertainty_contact_planning.hpp:1718-1748) */
+template <class M>
+__global__ void __launch_bounds__(128) link_centers_kernel(const __grid_constant__ CenterArgs a)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.total) return;
+    M m;
+    if constexpr (M::HAS_FRAMES) m.frames = a.frames + i * (int64_t)a.robot.num_links * 12;
+    m.pid_i = nullptr;
+    m.pid_e = nullptr;
+    m.load(a.robot, a.cfg, a.total, i);
+    if constexpr (M::HAS_FRAMES) m.fk(a.robot, m.frames);
+    for (int l = 0; l < a.robot.num_links; l++)
+    {
+        double T[12];
+        m.frame(a.robot, l, T);
+        a.centers[(int64_t)(l * 3 + 0) * a.total + i] = T[3];
+        a.centers[(int64_t)(l * 3 + 1) * a.total + i] = T[7];
+        a.centers[(int64_t)(l * 3 + 2) * a.total + i] = T[11];
+    }
+}
+
+/* CheckStraightLine3DPath (uncertainty_contact_planning.hpp:1698-1716): occupancy sampled at `steps` points from a to b */
+__device__ __forceinline__ bool straight_line_free(const DevEnv& env, const double* V, const double* a, const double* b)
+{
+    const double d0 = b[0] - a[0], d1 = b[1] - a[1], d2 = b[2] - a[2];
+    const double distance = sqrt(((d0 * d0) + (d1 * d1)) + (d2 * d2));
+    unsigned steps = (unsigned)ceil(distance / env.res);
+    if (steps < 1u) steps = 1u;
+    for (unsigned step = 1u; step <= steps; step++)
+    {
+        const double percent = (double)step / (double)steps;
+        const double q0 = upc_fma(d0, percent, a[0]), q1 = upc_fma(d1, percent, a[1]), q2 = upc_fma(d2, percent, a[2]);
+        double u[3];
+        xf_point(V, q0, q1, q2, u);
+        float occupancy = env.occ_oob; /* the in-bounds flag is ignored at :1709: the default cell is used */
+        if (voxel_in_bounds(env, u)) occupancy = ldg(env.occ + cell_index(env, floor_to_int(u[0]), floor_to_int(u[1]), floor_to_int(u[2])));
+        if (occupancy > 0.5f) return false;
+    }
+    return true;
+}
+
+struct AcAdjArgs
+{
+    DevEnv env;
+    const double* centers; /* [L*3][total] */
+    int num_links;
+    int64_t total, set_size;
+    int wpr;
+    uint32_t* adj;
+};
+
+/* adjacency bit = every link origin of the lower-indexed particle sees the same link's origin of the other one */
+__global__ void __launch_bounds__(256) ac_adjacency_kernel(const __grid_constant__ AcAdjArgs a)
+{
+    __shared__ uint32_t s_words[kTileRows][kTileCols / 32];
+    const int64_t set_base = (int64_t)blockIdx.z * a.set_size;
+    const int64_t row0 = (int64_t)blockIdx.y * kTileRows;
+    const int64_t col = (int64_t)blockIdx.x * kTileCols + threadIdx.x;
+    const bool col_ok = col < a.set_size;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double V[12];
+    {
+        const double I[12] = {1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0};
+        voxel_from_link(a.env, I, V);
+    }
+    for (int r = 0; r < kTileRows; r++)
+    {
+        const int64_t row = row0 + r;
+        bool adjacent = false;
+        if (col_ok && row < a.set_size)
+        {
+            adjacent = true;
+            if (row != col)
+            {
+                const int64_t lo = (row < col) ? row : col, hi = (row < col) ? col : row;
+                for (int l = 0; l < a.num_links && adjacent; l++)
+                {
+                    double pa[3], pb[3];
+                    for (int c = 0; c < 3; c++)
+                    {
+                        pa[c] = a.centers[(int64_t)(l * 3 + c) * a.total + set_base + lo];
+                        pb[c] = a.centers[(int64_t)(l * 3 + c) * a.total + set_base + hi];
+                    }
+                    adjacent = straight_line_free(a.env, V, pa, pb);
+                }
+            }
+        }
+        const unsigned word = __ballot_sync(0xffffffffu, adjacent);
+        if (lane == 0) s_words[r][warp] = word;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < kTileRows * (kTileCols / 32); k += kTileCols)
+    {
+        const int r = k / (kTileCols / 32), w = k % (kTileCols / 32);
+        const int64_t i = row0 + r;
+        const int64_t word_index = (int64_t)blockIdx.x * (kTileCols / 32) + w;
+        if (i < a.set_size && word_index < a.wpr) a.adj[(set_base + i) * a.wpr + word_index] = s_words[r][w];
+    }
+}
+
+/* ------------------------------------------------------------------ point-to-point movement (PTPM first pass) */
+
+/* start/target pairs of uncertainty_contact_planning.hpp:1804-1825: for i < j the simulations (i -> j) then (j -> i) */
+__global__ void __launch_bounds__(256) ptpm_pairs_kernel(const double* __restrict__ cfg, int width, int64_t n, double* __restrict__ starts,
+                                                         double* __restrict__ targets)
+{
+    const int64_t sims = n * n - n;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (n * (n - 1)) / 2) return;
+    /* unrank e -> (i, j), i < j, row-major over the strict upper triangle */
+    int64_t i = (int64_t)floor(((double)(2 * n - 1) - sqrt((double)(2 * n - 1) * (double)(2 * n - 1) - 8.0 * (double)e)) * 0.5);
+    while (i * n - (i * (i + 1)) / 2 > e) i--;
+    while ((i + 1) * n - ((i + 1) * (i + 2)) / 2 <= e) i++;
+    const int64_t j = e - (i * n - (i * (i + 1)) / 2) + i + 1;
+    for (int c = 0; c < width; c++)
+    {
+        const double ci = cfg[(int64_t)c * n + i], cj = cfg[(int64_t)c * n + j];
+        starts[(int64_t)c * sims + 2 * e] = ci;
+        targets[(int64_t)c * sims + 2 * e] = cj;
+        starts[(int64_t)c * sims + 2 * e + 1] = cj;
+        targets[(int64_t)c * sims + 2 * e + 1] = ci;
+    }
+}
+
+struct PtpmAdjArgs
+{
+    DevRobot robot;
+    const double* cfg;     /* [C][n] */
+    const double* results; /* [C][n*n-n] */
+    int width;
+    int64_t n;
+    int wpr;
+    uint32_t* adj; /* zeroed; diagonal and feasible pairs are set */
+    double goal_distance_threshold;
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(256) ptpm_adjacency_kernel(const __grid_constant__ PtpmAdjArgs a)
+{
+    const int64_t n = a.n;
+    const int64_t sims = n * n - n;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) atomicOr(&a.adj[e * a.wpr + (e >> 5)], 1u << (e & 31));
+    if (e >= (n * (n - 1)) / 2) return;
+    int64_t i = (int64_t)floor(((double)(2 * n - 1) - sqrt((double)(2 * n - 1) * (double)(2 * n - 1) - 8.0 * (double)e)) * 0.5);
+    while (i * n - (i * (i + 1)) / 2 > e) i--;
+    while ((i + 1) * n - ((i + 1) * (i + 2)) / 2 <= e) i++;
+    const int64_t j = e - (i * n - (i * (i + 1)) / 2) + i + 1;
+    double fr[16], br[16], ci[16], cj[16];
+    for (int c = 0; c < a.width; c++)
+    {
+        fr[c] = a.results[(int64_t)c * sims + 2 * e];
+        br[c] = a.results[(int64_t)c * sims + 2 * e + 1];
+        ci[c] = a.cfg[(int64_t)c * n + i];
+        cj[c] = a.cfg[(int64_t)c * n + j];
+    }
+    double df, db;
+    if (KIND == UPC_ROBOT_SE2) { df = Se2Model::distance(a.robot, fr, cj); db = Se2Model::distance(a.robot, br, ci); }
+    else if (KIND == UPC_ROBOT_SE3) { df = Se3Model::distance(a.robot, fr, cj); db = Se3Model::distance(a.robot, br, ci); }
+    else { df = LinkedModel::distance(a.robot, fr, cj); db = LinkedModel::distance(a.robot, br, ci); }
+    if ((df <= a.goal_distance_threshold) && (db <= a.goal_distance_threshold))
+    {
+        atomicOr(&a.adj[i * a.wpr + (j >> 5)], 1u << (j & 31));
+        atomicOr(&a.adj[j * a.wpr + (i >> 5)], 1u << (i & 31));
+    }
+}
+
 /* ------------------------------------------------------------------ reading the partition off the adjacency */
 
 /* One warp per row: root = smallest neighbour; row_ok = (row == row of root). */
@@ -520,6 +699,8 @@ struct ExactArgs
     const double* feat;   /* config features [F][total] or null */
     const uint32_t* sig;  /* signatures [P][total] or null */
     const int32_t* group; /* optional first-pass groups: pairs across groups never merge */
+    const uint32_t* binary_adj; /* AC / PTPM: distances are 0 (bit set) or 1, read from the adjacency bits */
+    int wpr;
     int nfeat, num_points;
     int64_t total, set_size;
     const int32_t* bad_sets; /* indices of the sets being clustered exactly */
@@ -551,6 +732,10 @@ __global__ void __launch_bounds__(256) exact_matrix_kernel(const __grid_constant
             if (a.group && a.group[pi] != a.group[pj])
             {
                 d = INFINITY;
+            }
+            else if (a.binary_adj)
+            {
+                d = ((a.binary_adj[pi * a.wpr + (j >> 5)] >> (j & 31)) & 1u) ? 0.0 : 1.0;
             }
             else if (a.sig)
             {
@@ -737,6 +922,7 @@ struct PassInput
     double threshold = 0.0;
     const int32_t* set_count = nullptr; /* valid items per set when the sets are padded to a common size */
     bool allow_exact = true;            /* false: only report whether every set is a union of cliques */
+    bool binary = false;                /* the adjacency bits were already written by the caller (AC / PTPM) */
 };
 
 template <typename T>
@@ -766,7 +952,11 @@ static int32_t cluster_pass(upc_handle* h, const PassInput& in, int64_t n_sets, 
     int32_t* set_bad = (int32_t*)(row_ok + ((total + 15) / 16) * 16);
     UPC_CUDA_TRY(cudaMemsetAsync(set_bad, 0, (size_t)n_sets * sizeof(int32_t), stream));
     const int kind = h->robot.kind;
-    if (in.sig)
+    if (in.binary)
+    {
+        /* adjacency already in place */
+    }
+    else if (in.sig)
     {
         SigAdjArgs sa;
         sa.sig = in.sig; sa.num_points = h->robot.num_points; sa.total = total; sa.set_size = set_size; sa.wpr = wpr; sa.adj = adj;
@@ -785,7 +975,7 @@ static int32_t cluster_pass(upc_handle* h, const PassInput& in, int64_t n_sets, 
         else if (kind == UPC_ROBOT_SE3) adjacency_kernel<UPC_ROBOT_SE3><<<grid, kTileCols, 0, stream>>>(aa);
         else adjacency_kernel<UPC_ROBOT_LINKED><<<grid, kTileCols, 0, stream>>>(aa);
     }
-    h->stats.kernel_launches++;
+    if (!in.binary) h->stats.kernel_launches++;
     UPC_CUDA_TRY(cudaGetLastError());
     {
         const int64_t threads = total * 32;
@@ -811,6 +1001,7 @@ static int32_t cluster_pass(upc_handle* h, const PassInput& in, int64_t n_sets, 
     const int64_t m = set_size;
     ExactArgs ea;
     ea.robot = h->robot; ea.feat = in.feat; ea.sig = in.sig; ea.group = in.group; ea.nfeat = in.nfeat; ea.num_points = h->robot.num_points;
+    ea.binary_adj = in.binary ? adj : nullptr; ea.wpr = wpr;
     ea.total = total; ea.set_size = set_size; ea.nbad = nb; ea.threshold = in.threshold;
     double* d_mat = buf<double>(h->cw.dist_matrix, (size_t)nb * (size_t)m * (size_t)m);
     UPC_NULLCHECK(d_mat);
@@ -1001,10 +1192,102 @@ int32_t run_cluster(upc_handle* h, const upc_cluster_params& cp, int64_t n_sets,
         }
         group = root1;
     }
+    else if (cp.feature_type == UPC_FEATURE_ACTUATION_CENTER_CONNECTIVITY)
+    {
+        if (!h->d_occ)
+        {
+            set_error("occupancy grid required for actuation-centre clustering");
+            return UPC_ERR_INVALID_ARGUMENT;
+        }
+        const int L = h->robot.num_links;
+        double* centers = buf<double>(h->cw.usig, (size_t)total * L * 3);
+        UPC_NULLCHECK(centers);
+        double* frames = nullptr;
+        if (kind == UPC_ROBOT_LINKED)
+        {
+            frames = buf<double>(h->cw.frames, (size_t)total * L * 12);
+            UPC_NULLCHECK(frames);
+        }
+        CenterArgs ca;
+        ca.robot = h->robot; ca.cfg = d_configs; ca.total = total; ca.centers = centers; ca.frames = frames;
+        const unsigned cblocks = (unsigned)((total + 127) / 128);
+        if (kind == UPC_ROBOT_SE2) link_centers_kernel<Se2Model><<<cblocks, 128, 0, stream>>>(ca);
+        else if (kind == UPC_ROBOT_SE3) link_centers_kernel<Se3Model><<<cblocks, 128, 0, stream>>>(ca);
+        else link_centers_kernel<LinkedModel><<<cblocks, 128, 0, stream>>>(ca);
+        const int wpr = (int)((set_size + 31) / 32);
+        uint32_t* adj = buf<uint32_t>(h->cw.adjacency, (size_t)total * wpr);
+        UPC_NULLCHECK(adj);
+        AcAdjArgs aa;
+        aa.env = h->env; aa.centers = centers; aa.num_links = L; aa.total = total; aa.set_size = set_size; aa.wpr = wpr; aa.adj = adj;
+        dim3 grid((unsigned)((set_size + kTileCols - 1) / kTileCols), (unsigned)((set_size + kTileRows - 1) / kTileRows), (unsigned)n_sets);
+        ac_adjacency_kernel<<<grid, kTileCols, 0, stream>>>(aa);
+        h->stats.kernel_launches += 2;
+        UPC_CUDA_TRY(cudaGetLastError());
+        PassInput ain;
+        ain.binary = true;
+        ain.threshold = 0.0;
+        const int32_t rc = cluster_pass(h, ain, n_sets, set_size, root1, stream, nullptr);
+        if (rc != UPC_OK) return rc;
+        group = root1;
+    }
+    else if (cp.feature_type == UPC_FEATURE_POINT_TO_POINT_MOVEMENT)
+    {
+        if (n_sets != 1)
+        {
+            set_error("point-to-point-movement clustering handles one particle set per call");
+            return UPC_ERR_UNSUPPORTED;
+        }
+        if (!cp.ptpm_sim || !cp.ptpm_tape)
+        {
+            set_error("point-to-point-movement clustering needs simulation parameters and a noise tape");
+            return UPC_ERR_INVALID_ARGUMENT;
+        }
+        const int64_t n = set_size;
+        const int wpr = (int)((n + 31) / 32);
+        uint32_t* adj = buf<uint32_t>(h->cw.adjacency, (size_t)n * wpr);
+        UPC_NULLCHECK(adj);
+        UPC_CUDA_TRY(cudaMemsetAsync(adj, 0, (size_t)n * wpr * sizeof(uint32_t), stream));
+        const int width = upc_config_width(kind, h->robot.dof);
+        const int64_t sims = n * n - n;
+        if (sims > 0)
+        {
+            /* [starts | targets | results] and the collided flags */
+            double* work = buf<double>(h->cw.dist_matrix, (size_t)width * (size_t)sims * 3);
+            UPC_NULLCHECK(work);
+            uint8_t* coll = buf<uint8_t>(h->cw.link_scratch, (size_t)sims);
+            UPC_NULLCHECK(coll);
+            double* starts = work;
+            double* targets = work + (size_t)width * sims;
+            double* results = targets + (size_t)width * sims;
+            const unsigned pblocks = (unsigned)((sims / 2 + 255) / 256);
+            ptpm_pairs_kernel<<<pblocks, 256, 0, stream>>>(d_configs, width, n, starts, targets);
+            h->stats.kernel_launches++;
+            UPC_CUDA_TRY(cudaGetLastError());
+            upc_sim_params sp = *cp.ptpm_sim;
+            sp.allow_contacts = 1; /* :1826 */
+            const int32_t src = upc_forward_simulate_device(h, &sp, sims, starts, sims, targets, cp.ptpm_tape, results, coll, stream);
+            if (src != UPC_OK) return src;
+            PtpmAdjArgs pa;
+            pa.robot = h->robot; pa.cfg = d_configs; pa.results = results; pa.width = width; pa.n = n; pa.wpr = wpr; pa.adj = adj;
+            pa.goal_distance_threshold = cp.goal_distance_threshold;
+            const unsigned ablocks = (unsigned)((std::max<int64_t>(sims / 2, n) + 255) / 256);
+            if (kind == UPC_ROBOT_SE2) ptpm_adjacency_kernel<UPC_ROBOT_SE2><<<ablocks, 256, 0, stream>>>(pa);
+            else if (kind == UPC_ROBOT_SE3) ptpm_adjacency_kernel<UPC_ROBOT_SE3><<<ablocks, 256, 0, stream>>>(pa);
+            else ptpm_adjacency_kernel<UPC_ROBOT_LINKED><<<ablocks, 256, 0, stream>>>(pa);
+            h->stats.kernel_launches++;
+            UPC_CUDA_TRY(cudaGetLastError());
+        }
+        PassInput pin;
+        pin.binary = true;
+        pin.threshold = 0.0;
+        const int32_t rc = cluster_pass(h, pin, n_sets, set_size, root1, stream, nullptr);
+        if (rc != UPC_OK) return rc;
+        group = root1;
+    }
     else if (cp.feature_type != UPC_FEATURE_NONE)
     {
-        set_error("feature_type not supported by this build (ACTUATION_CENTER / POINT_TO_POINT are round-2 rows)");
-        return UPC_ERR_UNSUPPORTED;
+        set_error("unknown feature_type");
+        return UPC_ERR_INVALID_ARGUMENT;
     }
     PassInput in;
     in.feat = feat;

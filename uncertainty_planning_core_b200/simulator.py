@@ -106,13 +106,20 @@ class OutcomeClustering:
     """ClusterParticles / PolicyParticleClusteringFn over a B200Simulator's handle."""
 
     def __init__(self, simulator, clustering_type=abi.FEATURE_CRS, signature_matching_threshold=0.125,
-                 distance_clustering_threshold=0.1):
+                 distance_clustering_threshold=0.1, goal_distance_threshold=0.0, ptpm_params=None, ptpm_tape=None):
+        """ptpm_params / ptpm_tape: simulation parameters and noise tape [S, 1+M, dof, n*(n-1)] for the
+        POINT_TO_POINT_MOVEMENT first pass (uncertainty_contact_planning.hpp:1801-1863)."""
         self.sim = simulator
         self._lib = simulator._lib
         self.params = abi.ClusterParams()
         self.params.feature_type = clustering_type
         self.params.signature_matching_threshold = signature_matching_threshold
         self.params.distance_clustering_threshold = distance_clustering_threshold
+        self.params.goal_distance_threshold = goal_distance_threshold
+        self._keep = (ptpm_params, None if ptpm_tape is None else np.ascontiguousarray(ptpm_tape, dtype=np.float64))
+        if ptpm_params is not None:
+            self.params.ptpm_sim = C.pointer(ptpm_params)
+            self.params.ptpm_tape = self._keep[1].ctypes.data
 
     def ClusterIndices(self, configs, n_sets=1):
         """Index clustering of n_sets equally sized particle sets stacked in configs [n_sets*set_size, C].
