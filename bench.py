@@ -84,7 +84,7 @@ class ClockSampler:
         q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
@@ -156,14 +156,32 @@ def cpu_path(sc, cp, sample, tape, reps=1):
 
 
 def auto_cpu_sample(sc, cp, want_seconds=12.0):
-    """Size the CPU sample to roughly `want_seconds` of host work from a 256-particle probe."""
+    """Size the CPU sample to roughly `want_seconds` of host work.  Simulation time is linear in the particle count;
+    the clustering half is between quadratic (one blob) and cubic (hierarchical path), so its growth is fitted from
+    two probes."""
     from uncertainty_planning_core_b200 import abi
-    probe = min(256, sc["starts"].shape[0])
-    tape = abi.fill_noise_tape(sc["seed"], sc["robot"], sc["params"], probe)
-    t_sim, t_cl, _, _ = cpu_path(sc, cp, probe, tape)
-    per = max((t_sim + t_cl) / probe, 1e-7)
-    sample = int(min(sc["starts"].shape[0], max(probe, want_seconds / per)))
-    return min(sample, 8192)   # the clustering half is O(n^2) in time and memory
+    total = sc["starts"].shape[0]
+    p1, p2 = min(96, total), min(192, total)
+    tape = abi.fill_noise_tape(sc["seed"], sc["robot"], sc["params"], p2)
+    s1, c1, _, _ = cpu_path(sc, cp, p1, np.ascontiguousarray(tape[..., :p1]))
+    s2, c2, _, _ = cpu_path(sc, cp, p2, tape)
+    sim_per = max(s2 / p2, 1e-9)
+    power = 2.0
+    if p2 > p1 and c1 > 1e-5 and c2 > c1:
+        power = min(3.2, max(1.0, np.log(c2 / c1) / np.log(p2 / p1)))
+    coef = max(c2, 1e-7) / (p2 ** power)
+    cap = min(total, 8192)
+    n = p2
+    while n * 2 <= cap and sim_per * (n * 2) + coef * (n * 2) ** power <= want_seconds:
+        n *= 2
+    lo, hi = n, min(cap, n * 2)
+    while hi - lo > 16:
+        mid = (lo + hi) // 2
+        if sim_per * mid + coef * mid ** power <= want_seconds:
+            lo = mid
+        else:
+            hi = mid
+    return int(lo)
 
 
 def run_reference(args):
@@ -351,8 +369,12 @@ def run_b200(args):
         abi.check(lib.upc_measure_l2_gather_gbs(h, env.sdf.nbytes, C.byref(l2_gbs)))
         abi.check(lib.upc_measure_fp64_tflops(h, C.byref(fp64)))
         compulsory = (tape_bytes + 2 * width * n * 8 + n) / (sim_ms_launch * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_sim_kernel_traffic.json")
+        if args.workload == "c2" and not args.particles and os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("traffic")   # dram bytes of one launch of this kernel, from the committed ncu capture
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": None, "kernel": "forward_simulate_kernel", "kernel_ms": sim_ms_launch, "peak_source": peak_src,
+                    "traffic": traffic, "kernel": "forward_simulate_kernel", "kernel_ms": sim_ms_launch, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "l2_gather_peak_gbs": l2_gbs.value, "frac_of_l2_gather": achieved / max(l2_gbs.value, 1e-9),
                     "compulsory_hbm_gbs": compulsory, "fp64_fma_peak_tflops": fp64.value,
                     "note": "SDF (%.0f MiB) is L2/L1-resident by design, so the gather rate may exceed the HBM copy peak" % (env.sdf.nbytes / 2 ** 20)}

@@ -41,8 +41,6 @@ def test_forward_simulation_matches_oracle_for_every_lane_count(oracle, simulato
     assert np.array_equal(ocfg, g["configs"]) and np.array_equal(ocoll, g["collided"])
     sim = simulators(name, sc["env"], sc["robot"])
     for lanes in (0, 1, 2, 4, 8, 16, 32):
-        if sc["robot"].kind == abi.ROBOT_LINKED and lanes in (1, 2):
-            continue
         sim.SetLanesPerParticle(lanes)
         sim.ResetStatistics()
         cfg, coll = sim.ForwardSimulateRobots(sc["starts"], sc["targets"], tape, sc["params"])

@@ -703,72 +703,93 @@ struct ExactArgs
     int wpr;
     int nfeat, num_points;
     int64_t total, set_size;
-    const int32_t* bad_sets; /* indices of the sets being clustered exactly */
-    int nbad;
-    double* D;        /* [nbad][m][m] */
-    uint8_t* active;  /* [nbad][m] */
-    int32_t* nn;      /* [nbad][m] nearest active neighbour under the key order */
-    int32_t* partner; /* [nbad][m] b if row a absorbs b this round, else -1 */
-    int32_t* into;    /* [nbad][m] representative chain */
+    /* the non-clique connected components, concatenated: component c owns flat rows [comp_off[c], comp_off[c+1]) */
+    int64_t rows;               /* total number of flat rows */
+    const int64_t* members;     /* [rows] global particle index of every row */
+    const int32_t* comp_of_row; /* [rows] */
+    const int64_t* comp_off;    /* [ncomp+1] */
+    const int64_t* matrix_off;  /* [ncomp+1] offsets of the m_c x m_c FP64 matrices */
+    double* D;
+    uint8_t* active;  /* [rows] */
+    int32_t* nn;      /* [rows] nearest active neighbour (local index) under the key order */
+    int32_t* partner; /* [rows] local index b if this row absorbs b this round, else -1 */
+    int32_t* into;    /* [rows] representative chain (local indices) */
     double threshold;
     int* merged_flag;
 };
 
+struct RowRef
+{
+    int64_t base; /* first flat row of the component */
+    int i;        /* local index of the row */
+    int m;        /* component size */
+    double* D;    /* component matrix */
+};
+
+__device__ __forceinline__ RowRef row_ref(const ExactArgs& a, int64_t r)
+{
+    const int c = a.comp_of_row[r];
+    RowRef q;
+    q.base = a.comp_off[c];
+    q.i = (int)(r - q.base);
+    q.m = (int)(a.comp_off[c + 1] - q.base);
+    q.D = a.D + a.matrix_off[c];
+    return q;
+}
+
+/* one CTA per flat row: distances of the row's particle to every member of its component */
 template <int KIND>
 __global__ void __launch_bounds__(256) exact_matrix_kernel(const __grid_constant__ ExactArgs a)
 {
     constexpr int MAXF = PairDistance<KIND>::MAXF;
-    const int s = blockIdx.y;
-    const int64_t m = a.set_size;
-    const int64_t base = (int64_t)a.bad_sets[s] * m;
-    double* D = a.D + (int64_t)s * m * m;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < m * m; e += (int64_t)gridDim.x * blockDim.x)
+    for (int64_t r = blockIdx.x; r < a.rows; r += gridDim.x)
     {
-        const int64_t i = e / m, j = e % m;
-        double d = 0.0;
-        if (i != j)
-        {
-            const int64_t pi = base + i, pj = base + j;
-            if (a.group && a.group[pi] != a.group[pj])
-            {
-                d = INFINITY;
-            }
-            else if (a.binary_adj)
-            {
-                d = ((a.binary_adj[pi * a.wpr + (j >> 5)] >> (j & 31)) & 1u) ? 0.0 : 1.0;
-            }
-            else if (a.sig)
-            {
-                int mism = 0;
-                for (int k = 0; k < a.num_points; k++)
-                {
-                    const uint32_t x = a.sig[(int64_t)k * a.total + pi], y = a.sig[(int64_t)k * a.total + pj];
-                    mism += ((x != 0u) && (y != 0u) && ((x & y) == 0u)) ? 1 : 0;
-                }
-                d = (double)mism / (double)a.num_points;
-            }
-            else
-            {
-                double fa[MAXF], fb[MAXF];
+        const RowRef q = row_ref(a, r);
+        const int64_t pi = a.members[r];
+        double fa[MAXF];
 #pragma unroll
-                for (int f = 0; f < MAXF; f++)
-                {
-                    fa[f] = (f < a.nfeat) ? a.feat[(int64_t)f * a.total + pi] : 0.0;
-                    fb[f] = (f < a.nfeat) ? a.feat[(int64_t)f * a.total + pj] : 0.0;
-                }
-                /* evaluate with the smaller index first, like BuildDistanceMatrix does for the upper triangle */
-                d = (i < j) ? PairDistance<KIND>::eval(a.robot, fa, fb) : PairDistance<KIND>::eval(a.robot, fb, fa);
-            }
-        }
-        D[e] = d;
-    }
-    if (blockIdx.x == 0)
-    {
-        for (int64_t k = threadIdx.x; k < m; k += blockDim.x)
+        for (int f = 0; f < MAXF; f++) fa[f] = (a.feat && f < a.nfeat) ? a.feat[(int64_t)f * a.total + pi] : 0.0;
+        for (int j = threadIdx.x; j < q.m; j += blockDim.x)
         {
-            a.active[(int64_t)s * m + k] = 1;
-            a.into[(int64_t)s * m + k] = (int32_t)k;
-            a.partner[(int64_t)s * m + k] = -1;
+            double d = 0.0;
+            if (j != q.i)
+            {
+                const int64_t pj = a.members[q.base + j];
+                if (a.group && a.group[pi] != a.group[pj])
+                {
+                    d = INFINITY;
+                }
+                else if (a.binary_adj)
+                {
+                    const int64_t cj = pj % a.set_size;
+                    d = ((a.binary_adj[pi * a.wpr + (cj >> 5)] >> (cj & 31)) & 1u) ? 0.0 : 1.0;
+                }
+                else if (a.sig)
+                {
+                    int mism = 0;
+                    for (int k = 0; k < a.num_points; k++)
+                    {
+                        const uint32_t x = a.sig[(int64_t)k * a.total + pi], y = a.sig[(int64_t)k * a.total + pj];
+                        mism += ((x != 0u) && (y != 0u) && ((x & y) == 0u)) ? 1 : 0;
+                    }
+                    d = (double)mism / (double)a.num_points;
+                }
+                else
+                {
+                    double fb[MAXF];
+#pragma unroll
+                    for (int f = 0; f < MAXF; f++) fb[f] = (f < a.nfeat) ? a.feat[(int64_t)f * a.total + pj] : 0.0;
+                    /* smaller index first, like BuildDistanceMatrix evaluates the upper triangle */
+                    d = (q.i < j) ? PairDistance<KIND>::eval(a.robot, fa, fb) : PairDistance<KIND>::eval(a.robot, fb, fa);
+                }
+            }
+            q.D[(int64_t)q.i * q.m + j] = d;
+        }
+        if (threadIdx.x == 0)
+        {
+            a.active[r] = 1;
+            a.into[r] = q.i;
+            a.partner[r] = -1;
         }
     }
 }
@@ -776,22 +797,21 @@ __global__ void __launch_bounds__(256) exact_matrix_kernel(const __grid_constant
 /* nearest active neighbour of every active row: key (distance, min(row, col), max(row, col)); one warp per row */
 __global__ void __launch_bounds__(256) exact_nearest_kernel(const __grid_constant__ ExactArgs a)
 {
-    const int64_t m = a.set_size;
-    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (w >= (int64_t)a.nbad * m) return;
-    const int s = (int)(w / m);
-    const int row = (int)(w - (int64_t)s * m);
-    const uint8_t* active = a.active + (int64_t)s * m;
-    if (!active[row])
+    if (r >= a.rows) return;
+    if (!a.active[r])
     {
-        if (lane == 0) a.nn[w] = -1;
+        if (lane == 0) a.nn[r] = -1;
         return;
     }
-    const double* Drow = a.D + ((int64_t)s * m + row) * m;
+    const RowRef q = row_ref(a, r);
+    const uint8_t* active = a.active + q.base;
+    const double* Drow = q.D + (int64_t)q.i * q.m;
+    const int row = q.i;
     double bv = INFINITY;
     int bi = -1;
-    for (int c = lane; c < m; c += 32)
+    for (int c = lane; c < q.m; c += 32)
     {
         if (c == row || !active[c]) continue;
         const double d = Drow[c];
@@ -822,92 +842,129 @@ __global__ void __launch_bounds__(256) exact_nearest_kernel(const __grid_constan
         }
         if (better) { bv = ov; bi = oi; }
     }
-    if (lane == 0) a.nn[w] = bi;
+    if (lane == 0) a.nn[r] = bi;
 }
 
 /* reciprocal nearest pairs within the threshold: the smaller representative absorbs the larger */
 __global__ void __launch_bounds__(256) exact_mark_kernel(const __grid_constant__ ExactArgs a)
 {
-    const int64_t m = a.set_size;
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int64_t)a.nbad * m) return;
-    const int s = (int)(t / m);
-    const int row = (int)(t - (int64_t)s * m);
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.rows) return;
     int partner = -1;
-    const int b = a.nn[t];
-    if (b > row && a.nn[(int64_t)s * m + b] == row)
+    const int b = a.nn[r];
+    if (b >= 0)
     {
-        const double d = a.D[((int64_t)s * m + row) * m + b];
-        if (d <= a.threshold)
+        const RowRef q = row_ref(a, r);
+        if (b > q.i && a.nn[q.base + b] == q.i)
         {
-            partner = b;
-            *a.merged_flag = 1;
+            const double d = q.D[(int64_t)q.i * q.m + b];
+            if (d <= a.threshold)
+            {
+                partner = b;
+                *a.merged_flag = 1;
+            }
         }
     }
-    a.partner[t] = partner;
+    a.partner[r] = partner;
 }
 
-/* Lance-Williams, rows: D[a][k] = max(D[a][k], D[b][k]) for every absorbing row a */
+/* Lance-Williams, rows: D[a][k] = max(D[a][k], D[b][k]) for every absorbing row a; one CTA per flat row */
 __global__ void __launch_bounds__(256) exact_row_merge_kernel(const __grid_constant__ ExactArgs a)
 {
-    const int64_t m = a.set_size;
-    const int s = blockIdx.z;
-    const int row = blockIdx.y;
-    const int b = a.partner[(int64_t)s * m + row];
-    if (b < 0) return;
-    double* Da = a.D + ((int64_t)s * m + row) * m;
-    const double* Db = a.D + ((int64_t)s * m + b) * m;
-    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += (int64_t)gridDim.x * blockDim.x)
+    for (int64_t r = blockIdx.x; r < a.rows; r += gridDim.x)
     {
-        const double x = Da[k], y = Db[k];
-        Da[k] = (x < y) ? y : x;
+        const int b = a.partner[r];
+        if (b < 0) continue;
+        const RowRef q = row_ref(a, r);
+        double* Da = q.D + (int64_t)q.i * q.m;
+        const double* Db = q.D + (int64_t)b * q.m;
+        for (int k = threadIdx.x; k < q.m; k += blockDim.x)
+        {
+            const double x = Da[k], y = Db[k];
+            Da[k] = (x < y) ? y : x;
+        }
     }
 }
 
-/* Lance-Williams, columns: D[k][a] = max(D[k][a], D[k][b]) for every row k; then retire the absorbed rows */
+/* Lance-Williams, columns: D[k][a] = max(D[k][a], D[k][b]) for every active row k */
 __global__ void __launch_bounds__(256) exact_col_merge_kernel(const __grid_constant__ ExactArgs a)
 {
-    const int64_t m = a.set_size;
-    const int s = blockIdx.z;
-    const int row = blockIdx.y;
-    if (!a.active[(int64_t)s * m + row]) return;
-    double* Dk = a.D + ((int64_t)s * m + row) * m;
-    const int32_t* partner = a.partner + (int64_t)s * m;
-    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < m; c += (int64_t)gridDim.x * blockDim.x)
+    for (int64_t r = blockIdx.x; r < a.rows; r += gridDim.x)
     {
-        const int b = partner[c];
-        if (b >= 0 && c != row)
+        if (!a.active[r]) continue;
+        const RowRef q = row_ref(a, r);
+        double* Dk = q.D + (int64_t)q.i * q.m;
+        const int32_t* partner = a.partner + q.base;
+        for (int c = threadIdx.x; c < q.m; c += blockDim.x)
         {
-            const double x = Dk[c], y = Dk[b];
-            Dk[c] = (x < y) ? y : x;
+            const int b = partner[c];
+            if (b >= 0 && c != q.i)
+            {
+                const double x = Dk[c], y = Dk[b];
+                Dk[c] = (x < y) ? y : x;
+            }
         }
     }
 }
 
 __global__ void __launch_bounds__(256) exact_retire_kernel(const __grid_constant__ ExactArgs a)
 {
-    const int64_t m = a.set_size;
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int64_t)a.nbad * m) return;
-    const int b = a.partner[t];
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.rows) return;
+    const int b = a.partner[r];
     if (b >= 0)
     {
-        const int64_t s = t / m;
-        a.active[s * m + b] = 0;
-        a.into[s * m + b] = (int32_t)(t - s * m);
+        const RowRef q = row_ref(a, r);
+        a.active[q.base + b] = 0;
+        a.into[q.base + b] = q.i;
     }
 }
 
 __global__ void __launch_bounds__(256) exact_roots_kernel(const __grid_constant__ ExactArgs a, int32_t* root)
 {
-    const int64_t m = a.set_size;
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int64_t)a.nbad * m) return;
-    const int64_t s = t / m;
-    const int32_t* into = a.into + s * m;
-    int r = (int)(t - s * m);
-    while (into[r] != r) r = into[r];
-    root[(int64_t)a.bad_sets[s] * m + (t - s * m)] = r;
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.rows) return;
+    const RowRef q = row_ref(a, r);
+    const int32_t* into = a.into + q.base;
+    int k = q.i;
+    while (into[k] != k) k = into[k];
+    root[a.members[r]] = (int32_t)(a.members[q.base + k] % a.set_size);
+}
+
+/* connected components of the threshold graph by min-label propagation + pointer jumping (exact path only) */
+__global__ void __launch_bounds__(256) propagate_kernel(const uint32_t* __restrict__ adj, int64_t total, int64_t set_size, int wpr,
+                                                        const int32_t* __restrict__ set_bad, int32_t* __restrict__ comp,
+                                                        int* __restrict__ changed)
+{
+    const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (p >= total) return;
+    const int64_t set = p / set_size;
+    if (!set_bad[set]) return;
+    const uint32_t* row = adj + p * wpr;
+    int32_t* sc = comp + set * set_size;
+    int32_t best = sc[p - set * set_size];
+    for (int w = lane; w < wpr; w += 32)
+    {
+        uint32_t v = row[w];
+        while (v)
+        {
+            const int b = __ffs((int)v) - 1;
+            v &= v - 1u;
+            best = min(best, sc[w * 32 + b]);
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, off));
+    if (lane == 0)
+    {
+        int32_t rr = best;
+        while (sc[rr] < rr) rr = sc[rr];
+        if (rr < comp[p])
+        {
+            comp[p] = rr;
+            *changed = 1;
+        }
+    }
 }
 
 /* ------------------------------------------------------------------ host orchestration */
@@ -993,44 +1050,103 @@ static int32_t cluster_pass(upc_handle* h, const PassInput& in, int64_t n_sets, 
     if (fallback_sets) *fallback_sets = nbad;
     if (nbad == 0 || !in.allow_exact) return UPC_OK;
 
-    /* ---- exact path for the sets whose threshold graph is not a union of cliques ---- */
-    std::vector<int32_t> bad_sets;
+    /* ---- exact path: the connected components that are not cliques ---- */
+    int32_t* comp = buf<int32_t>(h->cw.comp, (size_t)total);
+    UPC_NULLCHECK(comp);
+    iota_in_set_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(comp, total, set_size);
+    int* d_flag = (int*)buf<int>(h->cw.misc, 16);
+    UPC_NULLCHECK(d_flag);
+    for (int iter = 0; iter < 1 << 20; iter++)
+    {
+        UPC_CUDA_TRY(cudaMemsetAsync(d_flag, 0, sizeof(int), stream));
+        propagate_kernel<<<(unsigned)((total * 32 + 255) / 256), 256, 0, stream>>>(adj, total, set_size, wpr, set_bad, comp, d_flag);
+        h->stats.kernel_launches++;
+        int changed = 0;
+        UPC_CUDA_TRY(cudaMemcpyAsync(&changed, d_flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        UPC_CUDA_TRY(cudaStreamSynchronize(stream));
+        if (!changed) break;
+    }
+    std::vector<int32_t> h_comp((size_t)total);
+    std::vector<uint8_t> h_ok((size_t)total);
+    UPC_CUDA_TRY(cudaMemcpyAsync(h_comp.data(), comp, (size_t)total * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(h_ok.data(), row_ok, (size_t)total, cudaMemcpyDeviceToHost, stream));
+    UPC_CUDA_TRY(cudaStreamSynchronize(stream));
+    h->stats.d2h_bytes += total * 5;
+    /* components containing a row that differs from its root's row, members in ascending order */
+    std::vector<int64_t> members, comp_off(1, 0), matrix_off(1, 0);
+    std::vector<int32_t> comp_of_row;
     for (int64_t s = 0; s < n_sets; s++)
-        if (bad[(size_t)s]) bad_sets.push_back((int32_t)s);
-    const int nb = (int)bad_sets.size();
-    const int64_t m = set_size;
+    {
+        if (!bad[(size_t)s]) continue;
+        const int64_t base = s * set_size;
+        std::vector<uint8_t> dirty((size_t)set_size, 0);
+        std::vector<int32_t> count((size_t)set_size, 0);
+        for (int64_t i = 0; i < set_size; i++)
+        {
+            const int32_t c = h_comp[(size_t)(base + i)];
+            count[(size_t)c]++;
+            if (!h_ok[(size_t)(base + i)]) dirty[(size_t)c] = 1;
+        }
+        std::vector<int64_t> slot((size_t)set_size, -1);
+        for (int64_t c = 0; c < set_size; c++)
+        {
+            if (!dirty[(size_t)c]) continue;
+            slot[(size_t)c] = (int64_t)members.size();
+            members.resize(members.size() + (size_t)count[(size_t)c]);
+            comp_of_row.insert(comp_of_row.end(), (size_t)count[(size_t)c], (int32_t)(comp_off.size() - 1));
+            comp_off.push_back((int64_t)members.size());
+            matrix_off.push_back(matrix_off.back() + (int64_t)count[(size_t)c] * (int64_t)count[(size_t)c]);
+        }
+        std::vector<int64_t> fill(slot);
+        for (int64_t i = 0; i < set_size; i++)
+        {
+            const int32_t c = h_comp[(size_t)(base + i)];
+            if (slot[(size_t)c] >= 0) members[(size_t)(fill[(size_t)c]++)] = base + i;
+        }
+    }
+    const int ncomp = (int)comp_off.size() - 1;
+    if (ncomp == 0) return UPC_OK;
+    const int64_t rows = (int64_t)members.size();
+    if ((double)matrix_off.back() * 8.0 > 100.0e9)
+    {
+        set_error("exact complete-link path: the non-clique components need more than 100 GB of distance matrices");
+        return UPC_ERR_UNSUPPORTED;
+    }
     ExactArgs ea;
     ea.robot = h->robot; ea.feat = in.feat; ea.sig = in.sig; ea.group = in.group; ea.nfeat = in.nfeat; ea.num_points = h->robot.num_points;
     ea.binary_adj = in.binary ? adj : nullptr; ea.wpr = wpr;
-    ea.total = total; ea.set_size = set_size; ea.nbad = nb; ea.threshold = in.threshold;
-    double* d_mat = buf<double>(h->cw.dist_matrix, (size_t)nb * (size_t)m * (size_t)m);
+    ea.total = total; ea.set_size = set_size; ea.rows = rows; ea.threshold = in.threshold;
+    double* d_mat = buf<double>(h->cw.dist_matrix, (size_t)matrix_off.back());
     UPC_NULLCHECK(d_mat);
-    /* [bad_sets i32 nb | nn, partner, into i32 nb*m each | active u8 nb*m | flag] */
-    const size_t per = (size_t)nb * (size_t)m;
-    uint8_t* scratch = buf<uint8_t>(h->cw.link_scratch, (size_t)nb * 4 + per * 13 + 64);
-    UPC_NULLCHECK(scratch);
-    int32_t* d_bad = (int32_t*)scratch;
-    ea.bad_sets = d_bad;
-    ea.nn = d_bad + nb;
-    ea.partner = ea.nn + per;
-    ea.into = ea.partner + per;
-    ea.active = (uint8_t*)(ea.into + per);
-    ea.merged_flag = (int*)buf<int>(h->cw.misc, 16);
-    UPC_NULLCHECK(ea.merged_flag);
     ea.D = d_mat;
-    UPC_CUDA_TRY(cudaMemcpyAsync(d_bad, bad_sets.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, stream));
-    h->stats.h2d_bytes += nb * 4;
-    {
-        dim3 grid((unsigned)std::min<int64_t>(2048, (m * m + 255) / 256), (unsigned)nb);
-        if (kind == UPC_ROBOT_SE2) exact_matrix_kernel<UPC_ROBOT_SE2><<<grid, 256, 0, stream>>>(ea);
-        else if (kind == UPC_ROBOT_SE3) exact_matrix_kernel<UPC_ROBOT_SE3><<<grid, 256, 0, stream>>>(ea);
-        else exact_matrix_kernel<UPC_ROBOT_LINKED><<<grid, 256, 0, stream>>>(ea);
-        h->stats.kernel_launches++;
-        UPC_CUDA_TRY(cudaGetLastError());
-    }
-    const unsigned row_blocks = (unsigned)((per + 255) / 256);
-    const unsigned warp_blocks = (unsigned)((per * 32 + 255) / 256);
-    const dim3 merge_grid((unsigned)std::min<int64_t>(8, (m + 255) / 256), (unsigned)m, (unsigned)nb);
+    /* [members i64 rows | comp_off i64 ncomp+1 | matrix_off i64 ncomp+1] */
+    int64_t* d_members = buf<int64_t>(h->cw.members, (size_t)rows + 2 * (size_t)(ncomp + 1));
+    UPC_NULLCHECK(d_members);
+    int64_t* d_comp_off = d_members + rows;
+    int64_t* d_matrix_off = d_comp_off + (ncomp + 1);
+    UPC_CUDA_TRY(cudaMemcpyAsync(d_members, members.data(), (size_t)rows * 8, cudaMemcpyHostToDevice, stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(d_comp_off, comp_off.data(), (size_t)(ncomp + 1) * 8, cudaMemcpyHostToDevice, stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(d_matrix_off, matrix_off.data(), (size_t)(ncomp + 1) * 8, cudaMemcpyHostToDevice, stream));
+    /* [comp_of_row, nn, partner, into i32 rows each | active u8 rows] */
+    uint8_t* scratch = buf<uint8_t>(h->cw.link_scratch, (size_t)rows * 17 + 64);
+    UPC_NULLCHECK(scratch);
+    int32_t* d_comp_of_row = (int32_t*)scratch;
+    UPC_CUDA_TRY(cudaMemcpyAsync(d_comp_of_row, comp_of_row.data(), (size_t)rows * 4, cudaMemcpyHostToDevice, stream));
+    h->stats.h2d_bytes += rows * 12 + (ncomp + 1) * 16;
+    ea.members = d_members; ea.comp_off = d_comp_off; ea.matrix_off = d_matrix_off; ea.comp_of_row = d_comp_of_row;
+    ea.nn = d_comp_of_row + rows;
+    ea.partner = ea.nn + rows;
+    ea.into = ea.partner + rows;
+    ea.active = (uint8_t*)(ea.into + rows);
+    ea.merged_flag = d_flag;
+    const unsigned cta_rows = (unsigned)std::min<int64_t>(rows, 1 << 20);
+    if (kind == UPC_ROBOT_SE2) exact_matrix_kernel<UPC_ROBOT_SE2><<<cta_rows, 256, 0, stream>>>(ea);
+    else if (kind == UPC_ROBOT_SE3) exact_matrix_kernel<UPC_ROBOT_SE3><<<cta_rows, 256, 0, stream>>>(ea);
+    else exact_matrix_kernel<UPC_ROBOT_LINKED><<<cta_rows, 256, 0, stream>>>(ea);
+    h->stats.kernel_launches++;
+    UPC_CUDA_TRY(cudaGetLastError());
+    const unsigned row_blocks = (unsigned)((rows + 255) / 256);
+    const unsigned warp_blocks = (unsigned)((rows * 32 + 255) / 256);
     for (int round = 0; round < 1 << 20; round++)
     {
         UPC_CUDA_TRY(cudaMemsetAsync(ea.merged_flag, 0, sizeof(int), stream));
@@ -1041,8 +1157,8 @@ static int32_t cluster_pass(upc_handle* h, const PassInput& in, int64_t n_sets, 
         UPC_CUDA_TRY(cudaMemcpyAsync(&merged, ea.merged_flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
         UPC_CUDA_TRY(cudaStreamSynchronize(stream));
         if (!merged) break;
-        exact_row_merge_kernel<<<merge_grid, 256, 0, stream>>>(ea);
-        exact_col_merge_kernel<<<merge_grid, 256, 0, stream>>>(ea);
+        exact_row_merge_kernel<<<cta_rows, 256, 0, stream>>>(ea);
+        exact_col_merge_kernel<<<cta_rows, 256, 0, stream>>>(ea);
         exact_retire_kernel<<<row_blocks, 256, 0, stream>>>(ea);
         h->stats.kernel_launches += 3;
         UPC_CUDA_TRY(cudaGetLastError());

@@ -60,13 +60,22 @@ __global__ void __launch_bounds__(kBlock, UPC_SIM_MIN_BLOCKS) forward_simulate_k
     {
         double* frames0 = nullptr;
         double* frames1 = nullptr;
-        /* per-particle scratch: [target | previous] then (linked robots) two sets of link frames */
-        const int per = M::HAS_FRAMES ? a.robot.num_links * 12 : 0;
+        /* per-particle scratch: [target | previous | PID state] then (linked robots, G >= 4) two sets of link frames.
+         * With 1 or 2 lanes per particle - the throughput mapping for big batches - the frames of a linked robot live in
+         * per-thread local memory instead: shared memory could not hold them for 64-128 particles per CTA. */
+        constexpr bool kFramesInShared = M::HAS_FRAMES && (G >= 4);
+        const int per = kFramesInShared ? a.robot.num_links * 12 : 0;
         double* park = smem + npd + (size_t)(threadIdx.x / G) * (size_t)(2 * M::WIDTH + 2 * M::DOF + 2 * per);
-        if constexpr (M::HAS_FRAMES)
+        double local_frames[(M::HAS_FRAMES && !kFramesInShared) ? 2 * UPC_MAX_LINKS * 12 : 1];
+        if constexpr (kFramesInShared)
         {
             frames0 = park + 2 * M::WIDTH + 2 * M::DOF;
             frames1 = frames0 + per;
+        }
+        else if constexpr (M::HAS_FRAMES)
+        {
+            frames0 = local_frames;
+            frames1 = local_frames + UPC_MAX_LINKS * 12;
         }
         simulate_particle<M, G>(a.env, a.robot, a.sp, g, i, a.n, a.starts, a.n_targets, a.targets, a.tape, a.out_configs,
                                 a.out_collided, pts, frames0, frames1, park, lc, collided);
@@ -97,7 +106,7 @@ static cudaError_t launch_sim_impl(const SimArgs& a, cudaStream_t stream)
     const int64_t threads = a.n * G;
     const int64_t blocks = (threads + kBlock - 1) / kBlock;
     size_t smem = (size_t)a.robot.num_points * 4 * sizeof(double);
-    smem += (size_t)(kBlock / G) * (2 * M::WIDTH + 2 * M::DOF + (M::HAS_FRAMES ? 2 * (size_t)a.robot.num_links * 12 : 0)) * sizeof(double);
+    smem += (size_t)(kBlock / G) * (2 * M::WIDTH + 2 * M::DOF + ((M::HAS_FRAMES && G >= 4) ? 2 * (size_t)a.robot.num_links * 12 : 0)) * sizeof(double);
     if (smem > 48 * 1024)
     {
         cudaError_t e = cudaFuncSetAttribute(forward_simulate_kernel<M, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -145,7 +154,6 @@ int choose_lanes(const upc_handle* h, int64_t n)
         }
         while (lanes > 1 && lanes > max_pts) lanes /= 2;
     }
-    if (h->robot.kind == UPC_ROBOT_LINKED && lanes < 4) lanes = 4; /* frame scratch is per particle in shared memory */
     return lanes;
 }
 
@@ -170,7 +178,7 @@ cudaError_t launch_forward_simulate(upc_handle* h, const DevSim& sp, int64_t n, 
     {
         case UPC_ROBOT_SE2: return launch_sim_lanes<Se2Model>(a, lanes, stream);
         case UPC_ROBOT_SE3: return launch_sim_lanes<Se3Model>(a, lanes, stream);
-        default: return launch_sim_lanes<LinkedModel>(a, lanes < 4 ? 4 : lanes, stream);
+        default: return launch_sim_lanes<LinkedModel>(a, lanes, stream);
     }
 }
 

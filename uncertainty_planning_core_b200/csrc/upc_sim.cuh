@@ -95,9 +95,17 @@ UPC_D void refresh_frames(const DevRobot& r, M& m, const Group<G>& g)
 {
     if constexpr (M::HAS_FRAMES)
     {
-        g.sync();
-        if (g.sub == 0) m.fk(r, m.frames);
-        g.sync();
+        if constexpr (G >= 4)
+        {
+            /* frames shared by the group: one lane writes them */
+            g.sync();
+            if (g.sub == 0) m.fk(r, m.frames);
+            g.sync();
+        }
+        else
+        {
+            m.fk(r, m.frames); /* per-lane frames */
+        }
     }
 }
 

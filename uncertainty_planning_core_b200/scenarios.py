@@ -223,13 +223,15 @@ def c3_linked(seed=3, n=100000, num_steps=64, max_microsteps=1, shape=(256, 256,
     rng = np.random.default_rng(seed)
     extent = shape[0] * resolution
     boxes = random_boxes(rng, num_boxes, extent, 0.15, 0.4)
-    # keep the base column free
+    # keep the base column free of the random clutter, then place three obstacles in the arm's sweep
     keep = np.linalg.norm(boxes[:, 0:2] - np.array([2.0, 2.0]), axis=1) > 0.9
-    boxes = boxes[keep]
+    boxes = np.concatenate([boxes[keep], np.array([[2.45, 2.0, 2.1, 0.2, 0.4, 0.25],
+                                                   [1.55, 2.0, 1.4, 0.15, 0.4, 0.2],
+                                                   [2.0, 2.5, 2.6, 0.4, 0.15, 0.2]])], axis=0)
     env = make_environment(shape, resolution, boxes)
     robot = linked_arm()
-    q0 = rng.uniform(-0.6, 0.6, size=7)
-    q1 = q0 + rng.uniform(-0.45, 0.45, size=7)
+    q0 = np.array([0.05, 0.02, -0.03, 0.04, 0.0, 0.02, 0.0]) + rng.uniform(-0.02, 0.02, size=7)
+    q1 = np.array([0.1, 0.2, 0.0, 0.0, 0.1, 0.0, 0.0]) + rng.uniform(-0.005, 0.005, size=7)
     starts = np.tile(q0, (n, 1))
     targets = q1[None, :]
     params = abi.make_sim_params(num_steps, 0.01, resolution, allow_contacts=True, max_microsteps=max_microsteps)
