@@ -36,12 +36,15 @@ def emulation():
         lib.emulate_forward_simulate.argtypes = [C.POINTER(abi.EnvDesc), C.POINTER(abi.RobotDesc), C.POINTER(abi.SimParams),
                                                  i64, vp, i64, vp, vp, vp, vp, vp]
         lib.emulate_forward_simulate.restype = C.c_int
+        lib.emulate_set_corner_cells.argtypes = [C.c_int]
         _EMU = lib
     return _EMU
 
 
-def emulate_forward_simulate(env, robot, params, starts, targets, tape):
-    """The product's per-thread program run on the CPU with one lane per particle."""
+def emulate_forward_simulate(env, robot, params, starts, targets, tape, corner_cells=True):
+    """The product's per-thread program run on the CPU with one lane per particle.
+    corner_cells selects the SDF layout the collision passes read (corner-cell table vs plain grid + cell-minimum cull)."""
+    emulation().emulate_set_corner_cells(1 if corner_cells else 0)
     starts = np.asarray(starts, dtype=np.float64)
     targets = np.asarray(targets, dtype=np.float64)
     n = starts.shape[0]

@@ -19,7 +19,7 @@ static void fill_env(const upc_env_desc* e, DevEnv* d)
     d->res = e->resolution; d->inv_res = 1.0 / e->resolution;
     d->dnx = (double)e->nx; d->dny = (double)e->ny; d->dnz = (double)e->nz;
     for (int k = 0; k < 12; k++) d->G[k] = e->grid_from_world[k];
-    d->sdf = e->sdf; d->seg = e->convex_segment; d->occ = e->occupancy; d->cellmin = nullptr;
+    d->sdf = e->sdf; d->seg = e->convex_segment; d->occ = e->occupancy; d->cellmin = nullptr; d->cells = nullptr;
 }
 
 /* same conversion as upc_set_robot in upc_capi.cu (validation omitted) */
@@ -42,6 +42,11 @@ static void fill_robot(const upc_robot_desc* r, DevRobot* d)
     }
     d->pts = r->points;
     compute_reach(r, d->reach);
+    for (int l = 0; l < r->num_links; l++)
+    {
+        d->link_radius[l] = 0.0;
+        for (int k = r->link_point_offset[l]; k < r->link_point_offset[l + 1]; k++) d->link_radius[l] = fmax(d->link_radius[l], r->points[4 * k + 3]);
+    }
     if (r->kind == UPC_ROBOT_LINKED)
     {
         for (int k = 0; k < 12; k++) d->base[k] = r->base_transform[k];
@@ -76,6 +81,9 @@ static void run(const DevEnv& env, const DevRobot& rob, const DevSim& sp, int64_
     }
 }
 
+static int g_use_cells = 1;
+extern "C" void emulate_set_corner_cells(int on) { g_use_cells = on; }
+
 extern "C" int emulate_forward_simulate(const upc_env_desc* e, const upc_robot_desc* r, const upc_sim_params* p, int64_t n,
                                         const double* starts, int64_t n_targets, const double* targets, const double* tape,
                                         double* out, uint8_t* coll, int64_t* counters)
@@ -85,6 +93,15 @@ extern "C" int emulate_forward_simulate(const upc_env_desc* e, const upc_robot_d
     std::vector<float> cellmin((size_t)(e->nx + 1) * (size_t)(e->ny + 1) * (size_t)(e->nz + 1));
     build_cellmin(e->sdf, e->nx, e->ny, e->nz, cellmin.data());
     env.cellmin = cellmin.data();
+    std::vector<float> cells;
+    if (g_use_cells)
+    {
+        cells.resize(cellmin.size() * 8 + 4);
+        float* aligned = cells.data();
+        while (((uintptr_t)aligned) & 15u) aligned++;
+        build_corner_cells(e->sdf, e->nx, e->ny, e->nz, aligned);
+        env.cells = aligned;
+    }
     sp.num_steps = p->num_steps; sp.max_microsteps = p->max_microsteps; sp.allow_contacts = p->allow_contacts;
     sp.individual_jacobians = p->use_individual_jacobians; sp.max_resolver_iterations = p->max_resolver_iterations;
     sp.decay_iterations = p->resolver_decay_iterations; sp.dt = p->controller_interval; sp.shortcut = p->simulation_shortcut_distance;

@@ -104,6 +104,26 @@ def test_cluster_particles_assembly_and_edge_cases(oracle, simulators):
     assert labels.tolist() == [0, 1] and ncl.tolist() == [2]
 
 
+def test_plain_grid_path_matches_oracle_too(oracle):
+    """Grids too large for the corner-cell table (e.g. 256^3) use the plain SDF + cell-minimum cull: force that path."""
+    from uncertainty_planning_core_b200 import B200Simulator
+    os.environ["UPC_B200_NO_CORNER_CELLS"] = "1"
+    try:
+        for make in (cases.se2_contact, cases.se3_contact, cases.linked_contact):
+            sc = make()
+            n = sc["starts"].shape[0]
+            tape = abi.fill_noise_tape(sc["seed"], sc["robot"], sc["params"], n)
+            ocfg, ocoll, ostats = oracle.forward_simulate(sc["env"], sc["robot"], sc["params"], sc["starts"], sc["targets"], tape)
+            sim = B200Simulator(sc["env"], sc["robot"])
+            for lanes in (1, 4, 32):
+                sim.SetLanesPerParticle(lanes)
+                cfg, coll = sim.ForwardSimulateRobots(sc["starts"], sc["targets"], tape, sc["params"])
+                assert np.array_equal(coll, ocoll) and max_ulp_diff(cfg, ocfg) <= CONFIG_ULP_TOLERANCE
+            sim.close()
+    finally:
+        del os.environ["UPC_B200_NO_CORNER_CELLS"]
+
+
 def test_check_config_collision_matches_oracle(oracle, simulators):
     for make in (cases.se2_contact, cases.se3_contact, cases.linked_contact):
         sc = make()

@@ -7,6 +7,7 @@
 
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 #include <random>
 
 namespace upc
@@ -165,6 +166,22 @@ int32_t upc_create(const upc_env_desc* env, int32_t device, upc_handle** out)
         UPC_CUDA_TRY(cudaStreamSynchronize(h->stream));
         h->stats.h2d_bytes += (int64_t)(mcells * sizeof(float));
     }
+    {
+        /* corner-cell table: 8x the SDF, kept only while it fits comfortably in the 126 MB L2 */
+        const size_t mcells = (size_t)(env->nx + 1) * (size_t)(env->ny + 1) * (size_t)(env->nz + 1);
+        const size_t bytes = mcells * 8 * sizeof(float);
+        /* UPC_B200_NO_CORNER_CELLS=1 forces the plain-grid path (tests exercise both) */
+        const char* off = getenv("UPC_B200_NO_CORNER_CELLS");
+        if (bytes <= (size_t)80 * 1024 * 1024 && !(off && off[0] == '1'))
+        {
+            std::vector<float> cells(mcells * 8);
+            build_corner_cells(env->sdf, env->nx, env->ny, env->nz, cells.data());
+            UPC_CUDA_TRY(cudaMalloc(&h->d_cells, bytes));
+            UPC_CUDA_TRY(cudaMemcpyAsync(h->d_cells, cells.data(), bytes, cudaMemcpyHostToDevice, h->stream));
+            UPC_CUDA_TRY(cudaStreamSynchronize(h->stream));
+            h->stats.h2d_bytes += (int64_t)bytes;
+        }
+    }
     UPC_CUDA_TRY(cudaMalloc(&h->d_counters, sizeof(DevCounters)));
     UPC_CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(DevCounters), h->stream));
     UPC_CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -180,6 +197,7 @@ int32_t upc_create(const upc_env_desc* env, int32_t device, upc_handle** out)
     e.seg = h->d_seg;
     e.occ = h->d_occ;
     e.cellmin = h->d_cellmin;
+    e.cells = h->d_cells;
     *out = h;
     return UPC_OK;
 }
@@ -193,6 +211,7 @@ int32_t upc_destroy(upc_handle* h)
     cudaFree(h->d_seg);
     cudaFree(h->d_occ);
     cudaFree(h->d_cellmin);
+    cudaFree(h->d_cells);
     cudaFree(h->d_points);
     cudaFree(h->d_counters);
     DeviceBuffer* bufs[] = {&h->st_starts, &h->st_targets, &h->st_tape, &h->st_out, &h->st_coll, &h->st_labels, &h->st_ncl,
@@ -283,6 +302,11 @@ int32_t upc_set_robot(upc_handle* h, const upc_robot_desc* r)
             if (!placed[(size_t)l]) return fail_arg("every link except the root needs a parent joint");
     }
     compute_reach(r, d.reach);
+    for (int l = 0; l < r->num_links; l++)
+    {
+        d.link_radius[l] = 0.0;
+        for (int k = r->link_point_offset[l]; k < r->link_point_offset[l + 1]; k++) d.link_radius[l] = fmax(d.link_radius[l], r->points[4 * k + 3]);
+    }
     UPC_CUDA_TRY(cudaSetDevice(h->device));
     if (h->d_points) cudaFree(h->d_points);
     h->d_points = nullptr;

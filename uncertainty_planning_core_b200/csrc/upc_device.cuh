@@ -12,6 +12,11 @@
 #define UPC_DEVICE_CUH
 
 #include <stdint.h>
+#if !defined(__CUDACC__)
+#include <algorithm>
+using std::max;
+using std::min;
+#endif
 #include "upc_b200.h"
 #include "upc_math.h"
 
@@ -39,6 +44,8 @@ struct DevEnv
      * indexed by the cell's low corner + 1.  A conservative lower bound of the interpolated distance used to skip
      * the 8-corner fetch for points that are provably clear; may be NULL (no culling). */
     const float* cellmin;
+    /* optional corner-cell table: 8 floats (one 32-byte sector) per interpolation cell, same indexing as cellmin */
+    const float* cells;
 };
 
 struct DevAxis
@@ -68,6 +75,7 @@ struct DevRobot
     /* static bounds on how far a body point can be from the axis that moves it:
      * reach[a] for active axis a of a linked robot; reach[0] = largest |p| of the single link of SE2/SE3 robots */
     double reach[UPC_MAX_DOF];
+    double link_radius[UPC_MAX_LINKS]; /* largest body-sphere radius of each link (conservative single-precision cull) */
     DevJoint joints[UPC_MAX_JOINTS];
 };
 
@@ -92,6 +100,32 @@ UPC_D int floor_to_int(double x)
 #else
     return (int)floor(x);
 #endif
+}
+
+/*
+ * floor(x) as a double and as a 32-bit integer WITHOUT the conversion unit (FP64 <-> integer conversions have a 45-cycle
+ * dependent latency and a quarter of the DFMA rate on sm_100a): adding 1.5 * 2^52 leaves round-to-nearest(x) in the low
+ * mantissa bits; one compare fixes the round-up cases.  Exact for |x| < 2^31, identical on host and device.
+ */
+UPC_D int floor_parts(double x, double* floor_x)
+{
+    const double magic = 6755399441055744.0;
+    const double t = x + magic;
+    double r = t - magic;
+#if defined(__CUDA_ARCH__)
+    int lo = __double2loint(t);
+#else
+    long long bits;
+    __builtin_memcpy(&bits, &t, sizeof(bits));
+    int lo = (int)(unsigned int)(bits & 0xffffffffLL);
+#endif
+    if (r > x)
+    {
+        r -= 1.0;
+        lo -= 1;
+    }
+    *floor_x = r;
+    return lo;
 }
 
 template <typename T>
@@ -386,6 +420,139 @@ UPC_D bool sdf_certainly_clear(const DevEnv& env, const double* u, double radius
     const int ix = floor_to_int(u[0] - 0.5) + 1, iy = floor_to_int(u[1] - 0.5) + 1, iz = floor_to_int(u[2] - 0.5) + 1;
     const double m = (double)ldg(env.cellmin + ((ix * (env.ny + 1) + iy) * (env.nz + 1) + iz));
     return ((m - radius) - limit) > UPC_CULL_MARGIN;
+}
+
+/* smallest float >= v (v finite): a single-precision value may be compared against it instead of against v */
+UPC_D float float_round_up(double v)
+{
+    float f = (float)v;
+    if ((double)f < v)
+    {
+#if defined(__CUDA_ARCH__)
+        f = __int_as_float(__float_as_int(f) + ((f >= 0.0f) ? 1 : -1));
+#else
+        f = __builtin_nextafterf(f, __builtin_inff());
+#endif
+    }
+    return f;
+}
+
+struct alignas(16) Corner4
+{
+    float x, y, z, w;
+};
+
+UPC_D Corner4 ldg4(const float* p)
+{
+#if defined(__CUDA_ARCH__)
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    Corner4 c;
+    c.x = v.x; c.y = v.y; c.z = v.z; c.w = v.w;
+    return c;
+#else
+    Corner4 c;
+    c.x = p[0]; c.y = p[1]; c.z = p[2]; c.w = p[3];
+    return c;
+#endif
+}
+
+UPC_D float fmin4(const Corner4& a, const Corner4& b)
+{
+    const float m0 = (a.y < a.x) ? a.y : a.x, m1 = (a.w < a.z) ? a.w : a.z;
+    const float m2 = (b.y < b.x) ? b.y : b.x, m3 = (b.w < b.z) ? b.w : b.z;
+    const float m01 = (m1 < m0) ? m1 : m0, m23 = (m3 < m2) ? m3 : m2;
+    return (m23 < m01) ? m23 : m01;
+}
+
+/*
+ * Corner-cell path, split so that callers can put several independent lookups in flight before the first use
+ * (the loads are the long pole: an L2 hit is ~300 cycles, and the compiler will not hoist them across the
+ * per-point branches on its own):
+ *   cell_locate  voxel coordinate -> address of the 32-byte corner record (always legal: clamped), fractions, in-bounds
+ *   cell_below   "sdf - radius < limit" from the loaded corners: single-precision minimum against a rounded-up
+ *                threshold decides the clear case, otherwise the exact trilinear value (same operations as sdf_distance)
+ */
+struct CellRef
+{
+    const float* cell;
+    double fx, fy, fz;
+    bool inb;
+};
+
+UPC_D CellRef cell_locate(const DevEnv& env, const double* u)
+{
+    CellRef c;
+    c.inb = voxel_in_bounds(env, u);
+    const double cx = u[0] - 0.5, cy = u[1] - 0.5, cz = u[2] - 0.5;
+    double flx, fly, flz;
+    int ix = floor_parts(cx, &flx), iy = floor_parts(cy, &fly), iz = floor_parts(cz, &flz);
+    c.fx = cx - flx; c.fy = cy - fly; c.fz = cz - flz;
+    ix = max(-1, min(ix, env.nx - 1));
+    iy = max(-1, min(iy, env.ny - 1));
+    iz = max(-1, min(iz, env.nz - 1));
+    c.cell = env.cells + (int64_t)(((ix + 1) * (env.ny + 1) + (iy + 1)) * (env.nz + 1) + (iz + 1)) * 8;
+    return c;
+}
+
+UPC_D bool cell_below(const DevEnv& env, const CellRef& c, const Corner4& a, const Corner4& b, double radius, double limit, float clear_above)
+{
+    if (!c.inb) return ((double)env.sdf_oob - radius) < limit;
+    if (fmin4(a, b) > clear_above) return false;
+    const double v000 = (double)a.x, v001 = (double)a.y, v010 = (double)a.z, v011 = (double)a.w;
+    const double v100 = (double)b.x, v101 = (double)b.y, v110 = (double)b.z, v111 = (double)b.w;
+    const double c00 = upc_fma(c.fz, v001 - v000, v000);
+    const double c01 = upc_fma(c.fz, v011 - v010, v010);
+    const double c10 = upc_fma(c.fz, v101 - v100, v100);
+    const double c11 = upc_fma(c.fz, v111 - v110, v110);
+    const double c0 = upc_fma(c.fy, c01 - c00, c00);
+    const double c1 = upc_fma(c.fy, c11 - c10, c10);
+    const double d = upc_fma(c.fx, c1 - c0, c0);
+    return (d - radius) < limit;
+}
+
+UPC_D bool sdf_below_cells(const DevEnv& env, const double* u, double radius, double limit, float clear_above)
+{
+    const CellRef c = cell_locate(env, u);
+    const Corner4 a = ldg4(c.cell), b = ldg4(c.cell + 4);
+    return cell_below(env, c, a, b, radius, limit, clear_above);
+}
+
+/* Corner-cell path of the resolver: distance and world gradient when the point is (possibly) closer than `limit`;
+ * returns false - nothing to do - when the corner minimum proves it is not. */
+UPC_D bool cell_gradient(const DevEnv& env, const CellRef& c, const Corner4& a, const Corner4& b, double radius, double limit, float clear_above,
+                         double* dist, double* grad)
+{
+    if (!c.inb)
+    {
+        *dist = (double)env.sdf_oob;
+        grad[0] = 0.0; grad[1] = 0.0; grad[2] = 0.0;
+        return !((((double)env.sdf_oob - radius) - limit) > UPC_CULL_MARGIN);
+    }
+    if (fmin4(a, b) > clear_above) return false;
+    const double fx = c.fx, fy = c.fy, fz = c.fz;
+    const double v000 = (double)a.x, v001 = (double)a.y, v010 = (double)a.z, v011 = (double)a.w;
+    const double v100 = (double)b.x, v101 = (double)b.y, v110 = (double)b.z, v111 = (double)b.w;
+    const double dz00 = v001 - v000, dz01 = v011 - v010, dz10 = v101 - v100, dz11 = v111 - v110;
+    const double c00 = upc_fma(fz, dz00, v000);
+    const double c01 = upc_fma(fz, dz01, v010);
+    const double c10 = upc_fma(fz, dz10, v100);
+    const double c11 = upc_fma(fz, dz11, v110);
+    const double dy0 = c01 - c00, dy1 = c11 - c10;
+    const double c0 = upc_fma(fy, dy0, c00);
+    const double c1 = upc_fma(fy, dy1, c10);
+    const double dzv0 = upc_fma(fy, dz01 - dz00, dz00);
+    const double dzv1 = upc_fma(fy, dz11 - dz10, dz10);
+    const double ddx = c1 - c0;
+    *dist = upc_fma(fx, ddx, c0);
+    const double ddy = upc_fma(fx, dy1 - dy0, dy0);
+    const double ddz = upc_fma(fx, dzv1 - dzv0, dzv0);
+    const double g0 = ddx * env.inv_res, g1 = ddy * env.inv_res, g2 = ddz * env.inv_res;
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+    {
+        grad[j] = upc_fma(env.G[8 + j], g2, upc_fma(env.G[4 + j], g1, env.G[j] * g0));
+    }
+    return true;
 }
 
 /* distance and world-frame gradient */

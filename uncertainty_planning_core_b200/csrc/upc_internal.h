@@ -57,6 +57,7 @@ struct upc_handle
     uint32_t* d_seg = nullptr;
     float* d_occ = nullptr;
     float* d_cellmin = nullptr;
+    float* d_cells = nullptr;
     double* d_points = nullptr;
     upc::DevCounters* d_counters = nullptr; /* device-side running totals */
     upc_stats stats{};

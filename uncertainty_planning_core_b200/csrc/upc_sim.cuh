@@ -126,6 +126,43 @@ UPC_D bool check_collision(const DevEnv& env, const DevRobot& r, const M& m, con
         double T[12], V[12];
         m.frame(r, l, T);
         voxel_from_link(env, T, V);
+        if (env.cells != nullptr)
+        {
+            /* corner-cell table: one sector per point decides (and, if needed, evaluates) it.  The clear test runs in
+             * single precision against (largest radius of the link + threshold + margin) rounded up - conservative for
+             * every point of the link, so it never changes a result. */
+            const float clear_above = float_round_up((r.link_radius[l] + threshold) + UPC_CULL_MARGIN);
+            int k = beg + g.sub;
+            /* four lookups in flight per trip: locate all, load all, then evaluate */
+            for (; k + 3 * G < end; k += 4 * G)
+            {
+                CellRef c[4];
+                Corner4 ca[4], cb[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                {
+                    const int kj = k + j * G;
+                    double u[3];
+                    xf_point(V, pts[4 * kj + 0], pts[4 * kj + 1], pts[4 * kj + 2], u);
+                    c[j] = cell_locate(env, u);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                {
+                    ca[j] = ldg4(c[j].cell);
+                    cb[j] = ldg4(c[j].cell + 4);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) hit |= cell_below(env, c[j], ca[j], cb[j], pts[4 * (k + j * G) + 3], threshold, clear_above);
+            }
+            for (; k < end; k += G)
+            {
+                double u[3];
+                xf_point(V, pts[4 * k + 0], pts[4 * k + 1], pts[4 * k + 2], u);
+                hit |= sdf_below_cells(env, u, pts[4 * k + 3], threshold, clear_above);
+            }
+            continue;
+        }
         for (int chunk = beg; chunk < end; chunk += 32 * G)
         {
             const int first = chunk + g.sub;
@@ -166,11 +203,11 @@ UPC_D bool check_collision(const DevEnv& env, const DevRobot& r, const M& m, con
                     xf_point(V, pts[4 * kb + 0], pts[4 * kb + 1], pts[4 * kb + 2], ub);
                     const double da = sdf_distance(env, ua);
                     const double db = sdf_distance(env, ub);
-                    hit = hit || ((da - pts[4 * ka + 3]) < threshold) || ((db - pts[4 * kb + 3]) < threshold);
+                    hit |= ((da - pts[4 * ka + 3]) < threshold) | ((db - pts[4 * kb + 3]) < threshold);
                 }
                 else
                 {
-                    hit = hit || ((sdf_distance(env, ua) - pts[4 * ka + 3]) < threshold);
+                    hit |= ((sdf_distance(env, ua) - pts[4 * ka + 3]) < threshold);
                 }
             }
         }
@@ -246,21 +283,75 @@ UPC_DNI int resolver_correction(const DevEnv& env, const DevRobot& r, const DevS
         {
             const int first = chunk + g.sub;
             const int lim = (end < chunk + 32 * G) ? end : (chunk + 32 * G);
-            /* phase A */
+            unsigned contributing = 0u;
             unsigned undecided = 0u;
-#pragma unroll 4
-            for (int j = 0; j < 32; j++)
+            if (env.cells != nullptr)
             {
-                const int k = first + j * G;
-                if (k < lim)
+                /* corner-cell table: phases A and B in one pass over the lane's points, two lookups in flight per trip */
+                const float clear_above = float_round_up((r.link_radius[l] + sp.resolve_distance) + UPC_CULL_MARGIN);
+                for (int j0 = 0; j0 < 32 && (first + j0 * G) < lim; j0 += 2)
                 {
-                    double u[3];
-                    xf_point(V, pts[4 * k + 0], pts[4 * k + 1], pts[4 * k + 2], u);
-                    if (!sdf_certainly_clear(env, u, pts[4 * k + 3], sp.resolve_distance)) undecided |= (1u << j);
+                    CellRef c[2];
+                    Corner4 ca[2], cb[2];
+#pragma unroll
+                    for (int jj = 0; jj < 2; jj++)
+                    {
+                        int k = first + (j0 + jj) * G;
+                        if (k >= lim) k = first; /* padding lanes of the last trip repeat a valid point and are ignored below */
+                        double u[3];
+                        xf_point(V, pts[4 * k + 0], pts[4 * k + 1], pts[4 * k + 2], u);
+                        c[jj] = cell_locate(env, u);
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < 2; jj++)
+                    {
+                        ca[jj] = ldg4(c[jj].cell);
+                        cb[jj] = ldg4(c[jj].cell + 4);
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < 2; jj++)
+                    {
+                        const int j = j0 + jj;
+                        const int k = first + j * G;
+                        if (k < lim)
+                        {
+                            double grad[3], dist;
+                            if (cell_gradient(env, c[jj], ca[jj], cb[jj], pts[4 * k + 3], sp.resolve_distance, clear_above, &dist, grad))
+                            {
+                                const double de = dist - pts[4 * k + 3];
+                                if (de < sp.resolve_distance)
+                                {
+                                    const double gn2 = dot3(grad, grad);
+                                    if (gn2 > 1.0e-24)
+                                    {
+                                        const double scale = (sp.resolve_distance - de) / sqrt(gn2);
+                                        cbuf[j][0] = grad[0] * scale;
+                                        cbuf[j][1] = grad[1] * scale;
+                                        cbuf[j][2] = grad[2] * scale;
+                                        contributing |= (1u << j);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            else
+            {
+                /* phase A */
+#pragma unroll 4
+                for (int j = 0; j < 32; j++)
+                {
+                    const int k = first + j * G;
+                    if (k < lim)
+                    {
+                        double u[3];
+                        xf_point(V, pts[4 * k + 0], pts[4 * k + 1], pts[4 * k + 2], u);
+                        if (!sdf_certainly_clear(env, u, pts[4 * k + 3], sp.resolve_distance)) undecided |= (1u << j);
+                    }
                 }
             }
             /* phase B */
-            unsigned contributing = 0u;
             unsigned todo_b = undecided;
             while (todo_b)
             {
