@@ -294,7 +294,11 @@ int32_t upc_set_robot(upc_handle* h, const upc_robot_desc* r)
             {
                 return fail_arg("unknown joint type");
             }
-            if (jd.type != UPC_JOINT_FIXED) dj.active = active++;
+            if (jd.type != UPC_JOINT_FIXED)
+            {
+                d.axis_continuous[active] = (jd.type == UPC_JOINT_CONTINUOUS) ? 1 : 0;
+                dj.active = active++;
+            }
             d.parent_joint_of_link[jd.child_link] = j;
         }
         if (active != r->dof) return fail_arg("dof must equal the number of non-fixed joints");

@@ -40,7 +40,24 @@ struct PairDistance<UPC_ROBOT_SE2>
     {
         return Se2Model::distance(r, a, b);
     }
-    __device__ __forceinline__ static bool within(const DevRobot& r, const double* a, const double* b, double thr) { return eval(r, a, b) <= thr; }
+    /* eval(a, b) <= thr; the square root is only taken inside a 1e-14-wide band around the threshold */
+    __device__ __forceinline__ static bool within(const DevRobot& r, const double* a, const double* b, double thr)
+    {
+        const double dx = b[0] - a[0];
+        const double dy = b[1] - a[1];
+        const double rot = fabs(upc_angle_signed_distance(a[2], b[2]));
+        if (rot > thr) return false; /* the translation part is >= 0 */
+        const double t2 = (dx * dx) + (dy * dy);
+        const double rem = thr - rot;
+        const double r2 = rem * rem;
+        if (rem > 0.1 * thr)
+        {
+            /* margins of 1e-14 relative to rem are then also > 4 ulp relative to thr */
+            if (t2 > r2 * (1.0 + 1.0e-14)) return false;
+            if (t2 <= r2 * (1.0 - 1.0e-14)) return true;
+        }
+        return (sqrt(t2) + rot) <= thr;
+    }
 };
 
 template <>
@@ -86,6 +103,24 @@ struct PairDistance<UPC_ROBOT_LINKED>
         return LinkedModel::distance(r, a, b);
     }
     __device__ __forceinline__ static bool within(const DevRobot& r, const double* a, const double* b, double thr) { return eval(r, a, b) <= thr; }
+    /* same test with the degree-of-freedom count known at compile time (fully unrolled, features stay in registers)
+     * and the square root only taken inside a 1e-14-wide band around the threshold */
+    template <int NF>
+    __device__ __forceinline__ static bool within_n(const DevRobot& r, const double* a, const double* b, double thr)
+    {
+        double sum = 0.0;
+#pragma unroll
+        for (int k = 0; k < NF; k++)
+        {
+            const double raw = r.axis_continuous[k] ? upc_angle_signed_distance(a[k], b[k]) : (b[k] - a[k]);
+            const double wd = raw * r.weights[k];
+            sum = sum + (wd * wd);
+        }
+        const double t2 = thr * thr;
+        if (thr < 0.0 || sum > t2 * (1.0 + 1.0e-14)) return false;
+        if (sum <= t2 * (1.0 - 1.0e-14)) return true;
+        return sqrt(sum) <= thr;
+    }
 };
 
 __global__ void se3_features_kernel(const double* __restrict__ cfg, double* __restrict__ feat, int64_t total)
@@ -127,18 +162,22 @@ struct AdjArgs
  * Threshold adjacency, one CTA per 64-row x 256-column tile of one particle set.
  * Thread = column; the 64 row feature vectors sit in shared memory; one warp ballot per row yields a packed
  * 32-column word; the 64x8 words of the tile are staged in shared memory and written as full 32-byte sectors.
+ * Distances are symmetric (bit for bit), so tiles lying entirely below the diagonal are skipped and filled in by
+ * mirror_lower_kernel.  NF > 0 fixes the feature count at compile time (linked robots: the degrees of freedom).
  */
-template <int KIND>
+template <int KIND, int NF>
 __global__ void __launch_bounds__(kTileCols) adjacency_kernel(const __grid_constant__ AdjArgs a)
 {
-    constexpr int MAXF = PairDistance<KIND>::MAXF;
+    constexpr int MAXF = (NF > 0) ? NF : PairDistance<KIND>::MAXF;
+    const int64_t row0 = (int64_t)blockIdx.y * kTileRows;
+    const int64_t col_first = (int64_t)blockIdx.x * kTileCols;
+    if (col_first + kTileCols - 1 < row0) return; /* whole tile below the diagonal: mirrored later */
     __shared__ double s_row[MAXF][kTileRows];
     __shared__ int32_t s_grp[kTileRows];
     __shared__ uint32_t s_words[kTileRows][kTileCols / 32];
     const int64_t set_base = (int64_t)blockIdx.z * a.set_size;
-    const int64_t row0 = (int64_t)blockIdx.y * kTileRows;
-    const int64_t col = (int64_t)blockIdx.x * kTileCols + threadIdx.x;
-    const int F = a.nfeat;
+    const int64_t col = col_first + threadIdx.x;
+    const int F = (NF > 0) ? NF : a.nfeat;
     for (int k = threadIdx.x; k < F * kTileRows; k += kTileCols)
     {
         const int f = k / kTileRows, r = k % kTileRows;
@@ -165,7 +204,8 @@ __global__ void __launch_bounds__(kTileCols) adjacency_kernel(const __grid_const
             double rf[MAXF];
 #pragma unroll
             for (int f = 0; f < MAXF; f++) rf[f] = s_row[f][r];
-            adjacent = PairDistance<KIND>::within(a.robot, rf, cf, a.threshold);
+            if constexpr (KIND == UPC_ROBOT_LINKED && NF > 0) adjacent = PairDistance<KIND>::template within_n<NF>(a.robot, rf, cf, a.threshold);
+            else adjacent = PairDistance<KIND>::within(a.robot, rf, cf, a.threshold);
         }
         const unsigned word = __ballot_sync(0xffffffffu, adjacent);
         if (lane == 0) s_words[r][warp] = word;
@@ -178,6 +218,37 @@ __global__ void __launch_bounds__(kTileCols) adjacency_kernel(const __grid_const
         const int64_t word_index = (int64_t)blockIdx.x * (kTileCols / 32) + w;
         if (i < a.set_size && word_index < a.wpr) a.adj[(set_base + i) * a.wpr + word_index] = s_words[r][w];
     }
+}
+
+/* fills the adjacency words of the tiles adjacency_kernel skipped from their transposes: one warp per 32x32 bit block */
+__global__ void __launch_bounds__(256) mirror_lower_kernel(uint32_t* __restrict__ adj, int64_t set_size, int wpr, int64_t n_sets)
+{
+    const int64_t blocks_per_row = wpr; /* 32-column blocks */
+    const int64_t row_blocks = (set_size + 31) / 32;
+    const int64_t per_set = row_blocks * blocks_per_row;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= per_set * n_sets) return;
+    const int64_t set = w / per_set;
+    const int64_t rb = (w - set * per_set) / blocks_per_row; /* rows rb*32 .. */
+    const int64_t cb = (w - set * per_set) % blocks_per_row; /* columns cb*32 .. */
+    /* was the tile containing this block skipped?  (tile = 64 rows x 256 columns) */
+    const int64_t tile_row0 = (rb * 32 / kTileRows) * kTileRows;
+    const int64_t tile_col_last = (cb * 32 / kTileCols) * kTileCols + kTileCols - 1;
+    if (!(tile_col_last < tile_row0)) return;
+    uint32_t* base = adj + set * set_size * wpr;
+    /* transposed source block: rows cb*32 + lane, word rb */
+    const int64_t src_row = cb * 32 + lane;
+    const uint32_t v = (src_row < set_size) ? base[src_row * wpr + rb] : 0u;
+    uint32_t mine = 0u;
+#pragma unroll
+    for (int b = 0; b < 32; b++)
+    {
+        const uint32_t t = __ballot_sync(0xffffffffu, (v >> b) & 1u);
+        if (lane == b) mine = t;
+    }
+    const int64_t dst_row = rb * 32 + lane;
+    if (dst_row < set_size) base[dst_row * wpr + cb] = mine;
 }
 
 /* ------------------------------------------------------------------ convex-region signatures (CRS first pass) */
@@ -1028,9 +1099,28 @@ static int32_t cluster_pass(upc_handle* h, const PassInput& in, int64_t n_sets, 
         aa.robot = h->robot; aa.feat = in.feat; aa.nfeat = in.nfeat; aa.total = total; aa.set_size = set_size; aa.wpr = wpr;
         aa.group = in.group; aa.adj = adj; aa.threshold = in.threshold;
         dim3 grid((unsigned)((set_size + kTileCols - 1) / kTileCols), (unsigned)((set_size + kTileRows - 1) / kTileRows), (unsigned)n_sets);
-        if (kind == UPC_ROBOT_SE2) adjacency_kernel<UPC_ROBOT_SE2><<<grid, kTileCols, 0, stream>>>(aa);
-        else if (kind == UPC_ROBOT_SE3) adjacency_kernel<UPC_ROBOT_SE3><<<grid, kTileCols, 0, stream>>>(aa);
-        else adjacency_kernel<UPC_ROBOT_LINKED><<<grid, kTileCols, 0, stream>>>(aa);
+        if (kind == UPC_ROBOT_SE2) adjacency_kernel<UPC_ROBOT_SE2, 0><<<grid, kTileCols, 0, stream>>>(aa);
+        else if (kind == UPC_ROBOT_SE3) adjacency_kernel<UPC_ROBOT_SE3, 0><<<grid, kTileCols, 0, stream>>>(aa);
+        else
+        {
+            switch (in.nfeat)
+            {
+                case 1: adjacency_kernel<UPC_ROBOT_LINKED, 1><<<grid, kTileCols, 0, stream>>>(aa); break;
+                case 2: adjacency_kernel<UPC_ROBOT_LINKED, 2><<<grid, kTileCols, 0, stream>>>(aa); break;
+                case 3: adjacency_kernel<UPC_ROBOT_LINKED, 3><<<grid, kTileCols, 0, stream>>>(aa); break;
+                case 4: adjacency_kernel<UPC_ROBOT_LINKED, 4><<<grid, kTileCols, 0, stream>>>(aa); break;
+                case 5: adjacency_kernel<UPC_ROBOT_LINKED, 5><<<grid, kTileCols, 0, stream>>>(aa); break;
+                case 6: adjacency_kernel<UPC_ROBOT_LINKED, 6><<<grid, kTileCols, 0, stream>>>(aa); break;
+                case 7: adjacency_kernel<UPC_ROBOT_LINKED, 7><<<grid, kTileCols, 0, stream>>>(aa); break;
+                case 8: adjacency_kernel<UPC_ROBOT_LINKED, 8><<<grid, kTileCols, 0, stream>>>(aa); break;
+                default: adjacency_kernel<UPC_ROBOT_LINKED, 0><<<grid, kTileCols, 0, stream>>>(aa); break;
+            }
+        }
+        {
+            const int64_t warps = ((set_size + 31) / 32) * (int64_t)wpr * n_sets;
+            mirror_lower_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(adj, set_size, wpr, n_sets);
+            h->stats.kernel_launches++;
+        }
     }
     if (!in.binary) h->stats.kernel_launches++;
     UPC_CUDA_TRY(cudaGetLastError());

@@ -76,6 +76,7 @@ struct DevRobot
      * reach[a] for active axis a of a linked robot; reach[0] = largest |p| of the single link of SE2/SE3 robots */
     double reach[UPC_MAX_DOF];
     double link_radius[UPC_MAX_LINKS]; /* largest body-sphere radius of each link (conservative single-precision cull) */
+    int axis_continuous[UPC_MAX_DOF];  /* linked robots: 1 when the active joint wraps (SimpleJointModel::IsContinuous) */
     DevJoint joints[UPC_MAX_JOINTS];
 };
 
