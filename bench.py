@@ -76,48 +76,62 @@ def sdf_bytes_per_point(sc):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs (B200_PROFILING.md recipe).
+    The sampler is started ahead of the warm-up (nvidia-smi needs ~0.2 s to come up); samples are kept when their
+    timestamp falls inside [mark_begin, mark_end], the timed region."""
 
     def __init__(self, index):
         self.path = tempfile.mktemp(suffix=".csv")
         self.proc = None
-        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+        self.t0 = self.t1 = None
+        q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "10"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
                 if len(f) < 9:
                     continue
                 try:
-                    sm.append(float(f[1]))
-                    mx.append(float(f[2]))
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    rows.append((ts, float(f[1]), float(f[2]), [nm for k, nm in enumerate(names) if f[5 + k].lower().startswith("active")]))
                 except ValueError:
                     continue
-                for k, nm in enumerate(names):
-                    if f[5 + k].lower().startswith("active"):
-                        reasons.add(nm)
             os.unlink(self.path)
         except OSError:
             pass
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        window = [r for r in rows if self.t0 is not None and self.t0 - 0.02 <= r[0] <= self.t1 + 0.02]
+        scope = "timed region"
+        if len(window) < 3:
+            window, scope = rows, "warm-up + timed region (the timed region is shorter than three sampling periods)"
+        if window:
+            reasons = sorted({nm for r in window for nm in r[3]})
+            out.update(sm_mhz=float(np.median([r[1] for r in window])), sm_max_mhz=float(max(r[2] for r in window)), reasons=reasons,
+                       samples=len(window), scope=scope)
         return out
 
 
@@ -305,19 +319,23 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput: W warm-up steps, then exactly K timed steps
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for k in range(args.warmup):
         device_step(k)
     barrier()
     sim.ResetStatistics()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if sampler:
+        sampler.mark_begin()
     t_begin.record()
     for k in range(args.steps):
         device_step(args.warmup + k, evs[k])
     t_end.record()
     barrier()
+    if sampler:
+        sampler.mark_end()
     total_ms = t_begin.elapsed_time(t_end)
     clocks = sampler.stop() if sampler else None
     sim_ms = sum(e[0].elapsed_time(e[1]) for e in evs)

@@ -107,6 +107,7 @@ extern "C" int emulate_forward_simulate(const upc_env_desc* e, const upc_robot_d
     sp.decay_iterations = p->resolver_decay_iterations; sp.dt = p->controller_interval; sp.shortcut = p->simulation_shortcut_distance;
     sp.contact_distance = p->contact_distance; sp.resolve_distance = p->resolve_distance; sp.microstep_distance = p->microstep_distance;
     sp.initial_scale = p->resolver_initial_scale; sp.decay_rate = p->resolver_decay_rate; sp.damping = p->resolver_damping;
+    sp.step_begin = 0; sp.step_end = p->num_steps; sp.carry_pid = nullptr; sp.carry_flags = nullptr;
     for (int k = 0; k < 4; k++) counters[k] = 0;
     if (r->kind == UPC_ROBOT_SE2) run<Se2Model>(env, rob, sp, n, starts, n_targets, targets, tape, out, coll, counters);
     else if (r->kind == UPC_ROBOT_SE3) run<Se3Model>(env, rob, sp, n, starts, n_targets, targets, tape, out, coll, counters);

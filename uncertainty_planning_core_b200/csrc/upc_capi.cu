@@ -84,6 +84,10 @@ static int32_t to_dev_sim(const upc_sim_params* p, DevSim* out)
     out->initial_scale = p->resolver_initial_scale;
     out->decay_rate = p->resolver_decay_rate;
     out->damping = p->resolver_damping;
+    out->step_begin = 0;
+    out->step_end = p->num_steps;
+    out->carry_pid = nullptr;
+    out->carry_flags = nullptr;
     return UPC_OK;
 }
 
@@ -214,10 +218,16 @@ int32_t upc_destroy(upc_handle* h)
     cudaFree(h->d_cells);
     cudaFree(h->d_points);
     cudaFree(h->d_counters);
-    DeviceBuffer* bufs[] = {&h->st_starts, &h->st_targets, &h->st_tape, &h->st_out, &h->st_coll, &h->st_labels, &h->st_ncl,
+    DeviceBuffer* bufs[] = {&h->st_starts, &h->st_targets, &h->st_tape, &h->st_out, &h->st_coll, &h->st_labels, &h->st_ncl, &h->st_carry,
                             &h->cw.features, &h->cw.adjacency, &h->cw.roots, &h->cw.comp, &h->cw.flags, &h->cw.signatures,
                             &h->cw.frames, &h->cw.dist_matrix, &h->cw.members, &h->cw.link_scratch, &h->cw.misc, &h->cw.hash, &h->cw.dedupe, &h->cw.usig, &h->cw.uroot};
     for (DeviceBuffer* b : bufs) b->release();
+    if (h->copy_stream)
+    {
+        cudaStreamDestroy(h->copy_stream);
+        for (int c = 0; c < 4; c++) cudaEventDestroy(h->copy_done[c]);
+        cudaEventDestroy(h->compute_done);
+    }
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return UPC_OK;
@@ -435,11 +445,50 @@ int32_t upc_forward_simulate(upc_handle* h, const upc_sim_params* params, int64_
     UPC_CUDA_TRY(h->st_coll.reserve((size_t)n));
     UPC_CUDA_TRY(cudaMemcpyAsync(h->st_starts.ptr, starts, cfg_bytes, cudaMemcpyHostToDevice, h->stream));
     UPC_CUDA_TRY(cudaMemcpyAsync(h->st_targets.ptr, targets, tgt_bytes, cudaMemcpyHostToDevice, h->stream));
-    UPC_CUDA_TRY(cudaMemcpyAsync(h->st_tape.ptr, tape, tape_bytes, cudaMemcpyHostToDevice, h->stream));
     h->stats.h2d_bytes += (int64_t)(cfg_bytes + tgt_bytes + tape_bytes);
-    const int32_t rc = upc_forward_simulate_device(h, params, n, (const double*)h->st_starts.ptr, n_targets, (const double*)h->st_targets.ptr,
-                                                   (const double*)h->st_tape.ptr, (double*)h->st_out.ptr, (uint8_t*)h->st_coll.ptr, h->stream);
-    if (rc != UPC_OK) return rc;
+    DevSim sp;
+    {
+        const int32_t prc = to_dev_sim(params, &sp);
+        if (prc != UPC_OK) return prc;
+    }
+    /* The tape dominates the upload (C2: 61 MB of 63 MB).  It is step-major, so the edge is simulated as up to four
+     * launches over consecutive step ranges while the next slices are still in flight on a second stream. */
+    int chunks = 1;
+    if (tape_bytes >= ((size_t)8 << 20) && params->num_steps >= 8) chunks = 4;
+    const size_t step_bytes = tape_bytes / (size_t)params->num_steps;
+    if (chunks > 1)
+    {
+        UPC_CUDA_TRY(h->st_carry.reserve((size_t)2 * h->robot.dof * (size_t)n * sizeof(double) + (size_t)2 * n + 64));
+        sp.carry_pid = (double*)h->st_carry.ptr;
+        sp.carry_flags = (uint8_t*)h->st_carry.ptr + (size_t)2 * h->robot.dof * (size_t)n * sizeof(double);
+        if (!h->copy_stream)
+        {
+            UPC_CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+            for (int c = 0; c < 4; c++) UPC_CUDA_TRY(cudaEventCreateWithFlags(&h->copy_done[c], cudaEventDisableTiming));
+            UPC_CUDA_TRY(cudaEventCreateWithFlags(&h->compute_done, cudaEventDisableTiming));
+        }
+        /* the previous call's kernels may still be reading the staging tape */
+        UPC_CUDA_TRY(cudaEventRecord(h->compute_done, h->stream));
+        UPC_CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->compute_done, 0));
+    }
+    for (int c = 0; c < chunks; c++)
+    {
+        const int s0 = (int)(((int64_t)params->num_steps * c) / chunks), s1 = (int)(((int64_t)params->num_steps * (c + 1)) / chunks);
+        const size_t off = (size_t)s0 * step_bytes, len = (size_t)(s1 - s0) * step_bytes;
+        cudaStream_t cs = (chunks > 1) ? h->copy_stream : h->stream;
+        UPC_CUDA_TRY(cudaMemcpyAsync((uint8_t*)h->st_tape.ptr + off, (const uint8_t*)tape + off, len, cudaMemcpyHostToDevice, cs));
+        if (chunks > 1)
+        {
+            UPC_CUDA_TRY(cudaEventRecord(h->copy_done[c], h->copy_stream));
+            UPC_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->copy_done[c], 0));
+        }
+        sp.step_begin = s0;
+        sp.step_end = s1;
+        UPC_CUDA_TRY(launch_forward_simulate(h, sp, n, (const double*)h->st_starts.ptr, n_targets, (const double*)h->st_targets.ptr,
+                                             (const double*)h->st_tape.ptr, (double*)h->st_out.ptr, (uint8_t*)h->st_coll.ptr, h->stream));
+        h->stats.kernel_launches++;
+    }
+    h->stats.particles_simulated += n;
     UPC_CUDA_TRY(cudaMemcpyAsync(out_configs, h->st_out.ptr, cfg_bytes, cudaMemcpyDeviceToHost, h->stream));
     UPC_CUDA_TRY(cudaMemcpyAsync(out_collided, h->st_coll.ptr, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
     h->stats.d2h_bytes += (int64_t)(cfg_bytes + (size_t)n);

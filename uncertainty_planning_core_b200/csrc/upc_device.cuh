@@ -84,6 +84,13 @@ struct DevSim
 {
     int num_steps, max_microsteps, allow_contacts, individual_jacobians, max_resolver_iterations, decay_iterations;
     double dt, shortcut, contact_distance, resolve_distance, microstep_distance, initial_scale, decay_rate, damping;
+    /* An edge may be simulated as several launches over consecutive step ranges (the host-pointer entry point does so
+     * to overlap the upload of later tape slices with the simulation of earlier ones).  The per-particle state that is
+     * not part of the configuration travels between launches in carry_pid ([2*dof][n]: integral, last error) and
+     * carry_flags ([2][n]: collided, finished early); both NULL for a single launch covering [0, num_steps). */
+    int step_begin, step_end;
+    double* carry_pid;
+    uint8_t* carry_flags;
 };
 
 /* per-launch counters, reduced per block then added to the handle's totals */

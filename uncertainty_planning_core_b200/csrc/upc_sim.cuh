@@ -509,8 +509,21 @@ UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim&
     double* previous = park + M::WIDTH;
     m.pid_i = park + 2 * M::WIDTH;
     m.pid_e = park + 2 * M::WIDTH + M::DOF;
-    m.load(r, starts, n, i);
+    const bool resumed = sp.step_begin > 0;
+    m.load(r, resumed ? out_configs : starts, n, i);
     m.reset_controllers();
+    bool collided = false;
+    bool finished = false;
+    if (resumed)
+    {
+        for (int d = 0; d < dof; d++)
+        {
+            m.pid_i[d] = sp.carry_pid[(int64_t)d * n + i];
+            m.pid_e[d] = sp.carry_pid[(int64_t)(dof + d) * n + i];
+        }
+        collided = sp.carry_flags[i] != 0;
+        finished = sp.carry_flags[n + i] != 0;
+    }
     refresh_frames(r, m, g);
     {
         const int64_t ti = (n_targets == 1) ? 0 : i;
@@ -521,8 +534,7 @@ UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim&
         g.sync();
     }
     const int slots = 1 + sp.max_microsteps;
-    bool collided = false;
-    for (int step = 0; step < sp.num_steps; step++)
+    for (int step = sp.step_begin; step < sp.step_end && !finished; step++)
     {
         cnt.particle_steps++;
         UPC_T0
@@ -674,14 +686,25 @@ UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim&
         }
         const bool arrived = m.reached(r, target, sp.shortcut);
         UPC_T1(5)
-        if (arrived) break;
+        if (arrived) finished = true;
     }
+    const bool last_launch = sp.step_end >= sp.num_steps;
     if (g.sub == 0)
     {
         m.store(r, out_configs, n, i);
         out_collided[i] = collided ? 1 : 0;
+        if (!last_launch)
+        {
+            for (int d = 0; d < dof; d++)
+            {
+                sp.carry_pid[(int64_t)d * n + i] = m.pid_i[d];
+                sp.carry_pid[(int64_t)(dof + d) * n + i] = m.pid_e[d];
+            }
+            sp.carry_flags[i] = collided ? 1 : 0;
+            sp.carry_flags[n + i] = finished ? 1 : 0;
+        }
     }
-    collided_out = collided;
+    collided_out = collided && last_launch; /* the collided-particle counter is bumped once per edge */
 }
 
 } /* namespace upc */
