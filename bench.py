@@ -407,6 +407,20 @@ def run_b200(args):
             cpu = {"value": sample * S / (t_sim + t_cl), "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
                    "sample": "first %d of %d particles of the same edge, %d controller intervals, sim + clustering, 1 pass" % (sample, n, S),
                    "sim_value": sample * S / t_sim, "clustered_per_sec": sample / max(t_cl, 1e-12)}
+            # SURVEY 8d extras: a 1-thread figure, and the distance pass in the reference's own shape (std::function per pair +
+            # a heap-allocated delta vector per pair, uncertainty_contact_planning.hpp:1955-1960) next to the plain loop
+            all_threads = oracle.num_threads()
+            oracle.set_num_threads(1)
+            small = min(256, sample)
+            t1 = time.perf_counter()
+            cfg1, _, _ = oracle.forward_simulate(env, robot, params, sc["starts"][:small], sc["targets"], np.ascontiguousarray(ctape[..., :small]))
+            cpu["sim_value_1_thread"] = small * S / (time.perf_counter() - t1)
+            oracle.set_num_threads(all_threads)
+            m = min(2048, sample)
+            fin = oracle.forward_simulate(env, robot, params, sc["starts"][:m], sc["targets"], np.ascontiguousarray(ctape[..., :m]))[0]
+            t1 = time.perf_counter(); oracle.pair_distances(robot, fin); t2 = time.perf_counter()
+            oracle.pair_distances(robot, fin, reference_style=True); t3 = time.perf_counter()
+            cpu["distance_matrix_pairs_per_sec"] = {"plain_loop": m * (m - 1) / 2 / (t2 - t1), "reference_style": m * (m - 1) / 2 / (t3 - t2), "n": m}
         h2d = e2e_stats["h2d_bytes"] / args.steps
         d2h = e2e_stats["d2h_bytes"] / args.steps
         line = {

@@ -229,6 +229,15 @@ int32_t upc_cluster_particles_device(upc_handle* h, const upc_cluster_params* pa
 int32_t upc_fill_noise_tape(uint64_t seed, const upc_robot_desc* robot, const upc_sim_params* params, int64_t first_particle,
                             int64_t n, int64_t tape_stride, double* tape);
 
+/*
+ * "Next" row: the count behind ComputeReverseEdgeProbability (uncertainty_contact_planning.hpp:2073-2090)
+ * and the goal-reached fraction: how many of n configurations ([C][n]) lie within `threshold` (<=) of their target
+ * (targets [C][n_targets], n_targets == 1 or n) under the robot's ComputeConfigurationDistance.  Also writes the
+ * per-particle flags when `within` is not NULL.  Host pointers; synchronises.
+ */
+int32_t upc_count_within(upc_handle* h, int64_t n, const double* configs, int64_t n_targets, const double* targets, double threshold,
+                         int64_t* out_count, uint8_t* within);
+
 /* Roofline denominators measured on the device the handle lives on (diagnostics, not on the hot path):
  * random 32-byte-sector gather bandwidth over a buffer of `buffer_bytes` (L2-resident when it fits), and the FP64 FMA rate. */
 int32_t upc_measure_l2_gather_gbs(upc_handle* h, int64_t buffer_bytes, double* out_gbs);

@@ -142,6 +142,29 @@ def test_check_config_collision_matches_oracle(oracle, simulators):
         assert 0 < hits < 40
 
 
+def test_count_within_and_reverse_edge_probability(oracle, simulators):
+    """next row 8f-2: counts are bit-exact against the oracle's distances (<= threshold, uncertainty_contact_planning.hpp:2083)"""
+    for make in (cases.se2_contact, cases.se3_contact, cases.linked_contact):
+        sc = make()
+        n = sc["starts"].shape[0]
+        tape = abi.fill_noise_tape(sc["seed"], sc["robot"], sc["params"], n)
+        sim = simulators("cnt_" + sc["name"], sc["env"], sc["robot"])
+        cfg, _ = sim.ForwardSimulateRobots(sc["starts"], sc["targets"], tape, sc["params"])
+        both = np.concatenate([cfg, sc["targets"]], axis=0)
+        D = oracle.pair_distances(sc["robot"], both)[:n, n]
+        thr = float(np.median(D))
+        count, flags = sim.CountWithin(cfg, sc["targets"], thr)
+        assert np.array_equal(flags, D <= thr) and count == int((D <= thr).sum()) and 0 < count < n
+        # per-particle targets
+        count2, flags2 = sim.CountWithin(cfg, np.roll(cfg, 1, axis=0), 1e-3)
+        Dp = np.array([oracle.pair_distances(sc["robot"], np.stack([cfg[i], cfg[i - 1]]))[0, 1] for i in range(n)])
+        assert np.array_equal(flags2, Dp <= 1e-3) and count2 == int((Dp <= 1e-3).sum())
+        attempts, reached = sim.ComputeReverseEdgeProbability(cfg, sc["starts"][0], tape, sc["params"], thr)
+        ocfg, _, _ = oracle.forward_simulate(sc["env"], sc["robot"], sc["params"], cfg, sc["starts"][:1], tape)
+        Dr = oracle.pair_distances(sc["robot"], np.concatenate([ocfg, sc["starts"][:1]], axis=0))[:n, n]
+        assert attempts == n and reached == int((Dr <= thr).sum())
+
+
 def test_device_pointer_entry_points_on_the_torch_stream(oracle, simulators):
     import ctypes as C
     import torch

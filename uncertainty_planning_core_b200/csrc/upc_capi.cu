@@ -519,6 +519,43 @@ int32_t upc_check_config_collision(upc_handle* h, const double* config, double c
     return UPC_OK;
 }
 
+int32_t upc_count_within(upc_handle* h, int64_t n, const double* configs, int64_t n_targets, const double* targets, double threshold,
+                         int64_t* out_count, uint8_t* within)
+{
+    if (!h || !out_count) return fail_arg("null argument");
+    if (!h->has_robot)
+    {
+        set_error("upc_set_robot has not been called");
+        return UPC_ERR_NO_ROBOT;
+    }
+    if (n < 0) return fail_arg("n must be >= 0");
+    *out_count = 0;
+    if (n == 0) return UPC_OK;
+    if (!(n_targets == 1 || n_targets == n)) return fail_arg("targets must have size 1 or n");
+    if (!configs || !targets) return fail_arg("null buffer");
+    UPC_CUDA_TRY(cudaSetDevice(h->device));
+    const int width = upc_config_width(h->robot.kind, h->robot.dof);
+    const size_t cfg_bytes = (size_t)width * (size_t)n * sizeof(double), tgt_bytes = (size_t)width * (size_t)n_targets * sizeof(double);
+    UPC_CUDA_TRY(h->st_starts.reserve(cfg_bytes));
+    UPC_CUDA_TRY(h->st_targets.reserve(tgt_bytes));
+    UPC_CUDA_TRY(h->st_coll.reserve((size_t)n));
+    UPC_CUDA_TRY(h->st_ncl.reserve(64));
+    UPC_CUDA_TRY(cudaMemcpyAsync(h->st_starts.ptr, configs, cfg_bytes, cudaMemcpyHostToDevice, h->stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(h->st_targets.ptr, targets, tgt_bytes, cudaMemcpyHostToDevice, h->stream));
+    UPC_CUDA_TRY(cudaMemsetAsync(h->st_ncl.ptr, 0, sizeof(unsigned long long), h->stream));
+    h->stats.h2d_bytes += (int64_t)(cfg_bytes + tgt_bytes);
+    UPC_CUDA_TRY(launch_count_within(h, n, (const double*)h->st_starts.ptr, n_targets, (const double*)h->st_targets.ptr, threshold,
+                                     (unsigned long long*)h->st_ncl.ptr, within ? (uint8_t*)h->st_coll.ptr : nullptr, h->stream));
+    h->stats.kernel_launches++;
+    unsigned long long count = 0;
+    UPC_CUDA_TRY(cudaMemcpyAsync(&count, h->st_ncl.ptr, sizeof(count), cudaMemcpyDeviceToHost, h->stream));
+    if (within) UPC_CUDA_TRY(cudaMemcpyAsync(within, h->st_coll.ptr, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    UPC_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->stats.d2h_bytes += 8 + (within ? n : 0);
+    *out_count = (int64_t)count;
+    return UPC_OK;
+}
+
 int32_t upc_cluster_particles_device(upc_handle* h, const upc_cluster_params* params, int64_t n_sets, int64_t set_size,
                                      const double* d_configs, int32_t* d_labels, int32_t* d_n_clusters, void* stream)
 {

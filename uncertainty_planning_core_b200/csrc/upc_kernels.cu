@@ -182,6 +182,58 @@ cudaError_t launch_forward_simulate(upc_handle* h, const DevSim& sp, int64_t n, 
     }
 }
 
+/* ------------------------------------------------------------------ distance-to-target count (reverse-edge / goal probabilities) */
+
+struct CountArgs
+{
+    DevRobot robot;
+    int64_t n, n_targets;
+    const double* configs;
+    const double* targets;
+    double threshold;
+    unsigned long long* count;
+    uint8_t* within;
+};
+
+/* uncertainty_contact_planning.hpp:2079-2088: particle_distance <= goal_distance_threshold_ */
+template <class M>
+__global__ void __launch_bounds__(256) count_within_kernel(const __grid_constant__ CountArgs a)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool ok = false;
+    if (i < a.n)
+    {
+        const int width = (M::HAS_FRAMES) ? a.robot.dof : M::WIDTH;
+        double c[M::WIDTH], t[M::WIDTH];
+        const int64_t ti = (a.n_targets == 1) ? 0 : i;
+        for (int k = 0; k < width; k++)
+        {
+            c[k] = a.configs[(int64_t)k * a.n + i];
+            t[k] = a.targets[(int64_t)k * a.n_targets + ti];
+        }
+        ok = M::distance(a.robot, c, t) <= a.threshold;
+        if (a.within) a.within[i] = ok ? 1 : 0;
+    }
+    const unsigned votes = __popc(__ballot_sync(0xffffffffu, ok));
+    if ((threadIdx.x & 31) == 0 && votes) atomicAdd(a.count, (unsigned long long)votes);
+}
+
+cudaError_t launch_count_within(upc_handle* h, int64_t n, const double* d_configs, int64_t n_targets, const double* d_targets, double threshold,
+                                unsigned long long* d_count, uint8_t* d_within, cudaStream_t stream)
+{
+    CountArgs a;
+    a.robot = h->robot; a.n = n; a.n_targets = n_targets; a.configs = d_configs; a.targets = d_targets; a.threshold = threshold;
+    a.count = d_count; a.within = d_within;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    switch (h->robot.kind)
+    {
+        case UPC_ROBOT_SE2: count_within_kernel<Se2Model><<<blocks, 256, 0, stream>>>(a); break;
+        case UPC_ROBOT_SE3: count_within_kernel<Se3Model><<<blocks, 256, 0, stream>>>(a); break;
+        default: count_within_kernel<LinkedModel><<<blocks, 256, 0, stream>>>(a); break;
+    }
+    return cudaGetLastError();
+}
+
 /* ------------------------------------------------------------------ CheckConfigCollision (single configuration) */
 
 struct CheckArgs

@@ -95,6 +95,30 @@ class B200Simulator:
                                                  collided.ctypes.data))
         return np.ascontiguousarray(out.T), collided.astype(bool)
 
+    def CountWithin(self, configs, targets, threshold):
+        """How many configurations lie within `threshold` (<=) of their target, and which: the count behind
+        ComputeReverseEdgeProbability / the goal-reached fraction (uncertainty_contact_planning.hpp:2079-2088)."""
+        cfg = np.asarray(configs, dtype=np.float64)
+        tgt = np.asarray(targets, dtype=np.float64).reshape(-1, self.robot.width)
+        n = cfg.shape[0]
+        if cfg.ndim != 2 or cfg.shape[1] != self.robot.width or tgt.shape[0] not in (1, n):
+            raise ValueError("configs must be [n, %d] and targets [1 or n, %d]" % (self.robot.width, self.robot.width))
+        soa, tsoa = np.ascontiguousarray(cfg.T), np.ascontiguousarray(tgt.T)
+        flags = np.zeros(n, dtype=np.uint8)
+        count = C.c_int64(0)
+        abi.check(self._lib.upc_count_within(self._h, n, soa.ctypes.data, tgt.shape[0], tsoa.ctypes.data, float(threshold),
+                                             C.byref(count), flags.ctypes.data))
+        return int(count.value), flags.astype(bool)
+
+    def ComputeReverseEdgeProbability(self, child_particles, parent_expectation, noise_tape, params, goal_distance_threshold):
+        """(attempts, reached): simulate the child's particles back towards the parent with contacts allowed and count those
+        that end within goal_distance_threshold of it (uncertainty_contact_planning.hpp:2073-2090)."""
+        p = abi.SimParams.from_buffer_copy(params)
+        p.allow_contacts = 1
+        cfg, _ = self.ForwardSimulateRobots(child_particles, np.asarray(parent_expectation, dtype=np.float64).reshape(1, -1), noise_tape, p)
+        reached, _ = self.CountWithin(cfg, parent_expectation, goal_distance_threshold)
+        return cfg.shape[0], reached
+
     def ForwardSimulateRobot(self, start_position, target_position, noise_tape, params):
         cfg, coll = self.ForwardSimulateRobots(np.asarray(start_position, dtype=np.float64).reshape(1, -1),
                                                np.asarray(target_position, dtype=np.float64).reshape(1, -1),
