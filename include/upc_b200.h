@@ -238,6 +238,23 @@ int32_t upc_fill_noise_tape(uint64_t seed, const upc_robot_desc* robot, const up
 int32_t upc_count_within(upc_handle* h, int64_t n, const double* configs, int64_t n_targets, const double* targets, double threshold,
                          int64_t* out_count, uint8_t* within);
 
+/*
+ * "Next" row: per-cluster statistics of an outcome, the reduction behind
+ * UncertaintyPlannerState::UpdateStatistics (uncertainty_planner_state.hpp:339-351, 591-714) and the counts of
+ * uncertainty_contact_planning.hpp:2105-2162.  For each cluster k in [0, n_clusters), over the particles with
+ * labels[i] == k that survive the contact filter (collided[i] == 0 || allow_contacts), in ascending particle order:
+ *   counts[k], any_collided[k]
+ *   expectations[k*C .. )          AverageConfigurations (arithmetic / circular means; SE(3): mean translation + sign-aligned
+ *                                  normalised quaternion mean - DESIGN.md section 6)
+ *   variance[k], si_variance[k]    sum of d(expectation, p)^2 / n  and  (d / step_size)^2 / n
+ *   variances[k*V .. ), si_variances[k*V .. )   per-dimension versions; V = upc_variance_width(kind, dof)
+ * A cluster with no surviving particle reports count 0 and zeros.  Host pointers; synchronises.
+ */
+int32_t upc_variance_width(int32_t kind, int32_t dof); /* SE2 3, SE3 4 (dx, dy, dz, rotation), linked dof */
+int32_t upc_cluster_statistics(upc_handle* h, int64_t n, const double* configs, const int32_t* labels, const uint8_t* collided,
+                               int32_t allow_contacts, double step_size, int32_t n_clusters, int64_t* counts, uint8_t* any_collided,
+                               double* expectations, double* variance, double* si_variance, double* variances, double* si_variances);
+
 /* Roofline denominators measured on the device the handle lives on (diagnostics, not on the hot path):
  * random 32-byte-sector gather bandwidth over a buffer of `buffer_bytes` (L2-resident when it fits), and the FP64 FMA rate. */
 int32_t upc_measure_l2_gather_gbs(upc_handle* h, int64_t buffer_bytes, double* out_gbs);

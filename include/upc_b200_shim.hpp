@@ -447,6 +447,48 @@ public:
         return ClusterIndices(ptrs);
     }
 
+    /* Flat per-cluster statistics: what UncertaintyPlannerState::UpdateStatistics (uncertainty_planner_state.hpp:339-351) computes
+     * for each child state the clusters become (uncertainty_contact_planning.hpp:2110-2160). */
+    struct ClusterStatisticsResult
+    {
+        int32_t width, variance_width;
+        std::vector<int64_t> counts;
+        std::vector<uint8_t> any_collided;
+        std::vector<double> expectations, variance, si_variance, variances, si_variances; /* [K][width] / [K] / [K][variance_width] */
+    };
+
+    ClusterStatisticsResult ClusterStatistics(const std::vector<std::pair<Configuration, bool>>& particles, const std::vector<std::vector<size_t>>& index_clusters,
+                                              const bool allow_contacts, const double step_size, const int32_t robot_kind, const int32_t dof) const
+    {
+        ClusterStatisticsResult r;
+        const size_t n = particles.size(), K = index_clusters.size();
+        r.width = (n > 0) ? Traits::width(particles[0].first) : 0;
+        r.variance_width = upc_variance_width(robot_kind, dof);
+        r.counts.assign(K, 0);
+        r.any_collided.assign(K, 0);
+        r.expectations.assign(K * (size_t)r.width, 0.0);
+        r.variance.assign(K, 0.0);
+        r.si_variance.assign(K, 0.0);
+        r.variances.assign(K * (size_t)r.variance_width, 0.0);
+        r.si_variances.assign(K * (size_t)r.variance_width, 0.0);
+        if (n == 0 || K == 0) return r;
+        std::vector<double> soa((size_t)r.width * n), tmp((size_t)r.width);
+        std::vector<int32_t> labels(n, -1);
+        std::vector<uint8_t> collided(n);
+        for (size_t i = 0; i < n; i++)
+        {
+            Traits::flatten(particles[i].first, tmp.data());
+            for (int c = 0; c < r.width; c++) soa[(size_t)c * n + i] = tmp[(size_t)c];
+            collided[i] = particles[i].second ? 1 : 0;
+        }
+        for (size_t k = 0; k < K; k++)
+            for (size_t e = 0; e < index_clusters[k].size(); e++) labels[index_clusters[k][e]] = (int32_t)k;
+        check(upc_cluster_statistics(handle_, (int64_t)n, soa.data(), labels.data(), collided.data(), allow_contacts ? 1 : 0, step_size, (int32_t)K,
+                                     r.counts.data(), r.any_collided.data(), r.expectations.data(), r.variance.data(), r.si_variance.data(),
+                                     r.variances.data(), r.si_variances.data()));
+        return r;
+    }
+
 private:
     upc_handle* handle_;
     upc_cluster_params params_;

@@ -54,6 +54,8 @@ def load():
     lib.oracle_region_signatures.argtypes = [C.POINTER(abi.EnvDesc), C.POINTER(abi.RobotDesc), i64, vp, vp]
     lib.oracle_sdf_lookup.argtypes = [C.POINTER(abi.EnvDesc), i64, vp, vp, vp]
     lib.oracle_complete_link.argtypes = [vp, i64, dp, vp, vp]
+    lib.oracle_cluster_statistics.argtypes = [C.POINTER(abi.RobotDesc), i64, vp, vp, vp, i32, dp, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.oracle_cluster_statistics.restype = i32
     for name in ("oracle_forward_simulate", "oracle_check_config_collision", "oracle_cluster_particles",
                  "oracle_pair_distances", "oracle_pair_distances_reference_style", "oracle_region_signatures",
                  "oracle_sdf_lookup", "oracle_complete_link"):
@@ -190,6 +192,23 @@ def sdf_lookup(env, points):
     g = np.zeros((n, 3))
     _check(load().oracle_sdf_lookup(C.byref(env.desc), n, pts.ctypes.data, d.ctypes.data, g.ctypes.data))
     return d, g
+
+
+def cluster_statistics(robot, configs, labels, collided, allow_contacts, step_size, n_clusters):
+    cfg = np.asarray(configs, dtype=np.float64)
+    n = cfg.shape[0]
+    K, W, V = int(n_clusters), robot.width, abi.variance_width(robot.kind, robot.dof)
+    soa = np.ascontiguousarray(cfg.T)
+    lab = np.ascontiguousarray(labels, dtype=np.int32)
+    col = np.ascontiguousarray(np.asarray(collided).astype(np.uint8))
+    out = dict(counts=np.zeros(K, dtype=np.int64), any_collided=np.zeros(K, dtype=np.uint8), expectations=np.zeros((K, W)),
+               variance=np.zeros(K), si_variance=np.zeros(K), variances=np.zeros((K, V)), si_variances=np.zeros((K, V)))
+    _check(load().oracle_cluster_statistics(C.byref(robot.desc), n, soa.ctypes.data, lab.ctypes.data, col.ctypes.data, 1 if allow_contacts else 0,
+                                            float(step_size), K, out["counts"].ctypes.data, out["any_collided"].ctypes.data,
+                                            out["expectations"].ctypes.data, out["variance"].ctypes.data, out["si_variance"].ctypes.data,
+                                            out["variances"].ctypes.data, out["si_variances"].ctypes.data))
+    out["any_collided"] = out["any_collided"].astype(bool)
+    return out
 
 
 def complete_link(matrix, threshold):

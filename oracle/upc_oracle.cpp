@@ -1413,6 +1413,197 @@ static void ClusterSets(const Environment& env, const upc_robot_desc& rd, const 
     }
 }
 
+/* ---------------------------------------------------------------- per-cluster statistics */
+
+static void QuaternionToRotation(const double q[4], Mat34& t)
+{
+    const double x = q[0], y = q[1], z = q[2], w = q[3];
+    t.m[0][0] = 1.0 - 2.0 * ((y * y) + (z * z));
+    t.m[0][1] = 2.0 * ((x * y) - (z * w));
+    t.m[0][2] = 2.0 * ((x * z) + (y * w));
+    t.m[1][0] = 2.0 * ((x * y) + (z * w));
+    t.m[1][1] = 1.0 - 2.0 * ((x * x) + (z * z));
+    t.m[1][2] = 2.0 * ((y * z) - (x * w));
+    t.m[2][0] = 2.0 * ((x * z) - (y * w));
+    t.m[2][1] = 2.0 * ((y * z) + (x * w));
+    t.m[2][2] = 1.0 - 2.0 * ((x * x) + (y * y));
+}
+
+/* AverageConfigurations: simple_robot_models.hpp:373-399 (SE2), :834-844 (SE3), :2093-2148 (linked) */
+static void AverageConfigurations(const upc_robot_desc& rd, const std::vector<const double*>& members, double* out)
+{
+    const double inv_guard = (double)members.size();
+    if (rd.kind == UPC_ROBOT_SE2)
+    {
+        double sx = 0.0, sy = 0.0, ss = 0.0, sc = 0.0;
+        for (const double* c : members)
+        {
+            sx = sx + c[0];
+            sy = sy + c[1];
+            double s, k;
+            upc_sincos(c[2], &s, &k);
+            ss = ss + s;
+            sc = sc + k;
+        }
+        out[0] = sx / inv_guard;
+        out[1] = sy / inv_guard;
+        out[2] = upc_atan2(ss, sc); /* circular mean (AverageContinuousRevolute) */
+    }
+    else if (rd.kind == UPC_ROBOT_SE3)
+    {
+        double st[3] = {0.0, 0.0, 0.0}, sq[4] = {0.0, 0.0, 0.0, 0.0}, qref[4] = {0.0, 0.0, 0.0, 1.0};
+        bool first = true;
+        for (const double* c : members)
+        {
+            const Mat34 t = FromRows12(c);
+            for (int a = 0; a < 3; a++) st[a] = st[a] + t.m[a][3];
+            double q[4];
+            QuaternionFromRotation(t, q);
+            if (first) { for (int a = 0; a < 4; a++) qref[a] = q[a]; first = false; }
+            const double dot = (((q[0] * qref[0]) + (q[1] * qref[1])) + (q[2] * qref[2])) + (q[3] * qref[3]);
+            const double sign = (dot < 0.0) ? -1.0 : 1.0;
+            for (int a = 0; a < 4; a++) sq[a] = sq[a] + (sign * q[a]);
+        }
+        const double norm = sqrt((((sq[0] * sq[0]) + (sq[1] * sq[1])) + (sq[2] * sq[2])) + (sq[3] * sq[3]));
+        double q[4];
+        for (int a = 0; a < 4; a++) q[a] = sq[a] / norm;
+        Mat34 e;
+        QuaternionToRotation(q, e);
+        for (int a = 0; a < 3; a++) e.m[a][3] = st[a] / inv_guard;
+        ToRows12(e, out);
+    }
+    else
+    {
+        int active = 0;
+        for (int j = 0; j < rd.num_joints; j++)
+        {
+            if (rd.joints[j].type == UPC_JOINT_FIXED) continue;
+            if (rd.joints[j].type == UPC_JOINT_CONTINUOUS)
+            {
+                double ss = 0.0, sc = 0.0;
+                for (const double* c : members)
+                {
+                    double s, k;
+                    upc_sincos(c[active], &s, &k);
+                    ss = ss + s;
+                    sc = sc + k;
+                }
+                out[active] = upc_atan2(ss, sc);
+            }
+            else
+            {
+                double sum = 0.0;
+                for (const double* c : members) sum = sum + c[active];
+                out[active] = sum / inv_guard;
+            }
+            active++;
+        }
+    }
+}
+
+/* ComputePerDimensionConfigurationDistance: simple_robot_models.hpp:419-422, :866-869, :2206-2209 (absolute values) */
+static void PerDimensionDistance(const upc_robot_desc& rd, const double* c1, const double* c2, double* out)
+{
+    if (rd.kind == UPC_ROBOT_SE2)
+    {
+        out[0] = fabs(c2[0] - c1[0]);
+        out[1] = fabs(c2[1] - c1[1]);
+        out[2] = fabs(upc_angle_signed_distance(c1[2], c2[2]));
+    }
+    else if (rd.kind == UPC_ROBOT_SE3)
+    {
+        const Mat34 t1 = FromRows12(c1), t2 = FromRows12(c2);
+        for (int a = 0; a < 3; a++) out[a] = fabs(t2.m[a][3] - t1.m[a][3]);
+        double q1[4], q2[4];
+        QuaternionFromRotation(t1, q1);
+        QuaternionFromRotation(t2, q2);
+        const double dq = fabs((((q1[0] * q2[0]) + (q1[1] * q2[1])) + (q1[2] * q2[2])) + (q1[3] * q2[3]));
+        out[3] = (dq < (1.0 - 2.220446049250313e-16)) ? fabs(upc_acos(((2.0 * dq) * dq) - 1.0)) : 0.0;
+    }
+    else
+    {
+        int active = 0;
+        for (int j = 0; j < rd.num_joints; j++)
+        {
+            if (rd.joints[j].type == UPC_JOINT_FIXED) continue;
+            const double raw = (rd.joints[j].type == UPC_JOINT_CONTINUOUS) ? upc_angle_signed_distance(c1[active], c2[active]) : (c2[active] - c1[active]);
+            out[active] = fabs(raw * fabs(rd.distance_weights[active]));
+            active++;
+        }
+    }
+}
+
+template <typename Robot>
+static void ClusterStatistics(const upc_robot_desc& rd, int64_t n, const double* configs, const int32_t* labels, const uint8_t* collided,
+                              int32_t allow_contacts, double step_size, int32_t n_clusters, int64_t* counts, uint8_t* any_collided,
+                              double* expectations, double* variance, double* si_variance, double* variances, double* si_variances)
+{
+    const Robot robot(rd);
+    const int width = upc_config_width(rd.kind, rd.dof);
+    const int vw = upc_variance_width(rd.kind, rd.dof);
+    std::vector<double> aos((size_t)(n * width));
+    for (int64_t i = 0; i < n; i++)
+        for (int c = 0; c < width; c++) aos[(size_t)(i * width + c)] = configs[(int64_t)c * n + i];
+    for (int32_t k = 0; k < n_clusters; k++)
+    {
+        std::vector<const double*> members;
+        bool any = false;
+        for (int64_t i = 0; i < n; i++)
+        {
+            if (labels[i] != k) continue;
+            if ((collided[i] == 0) || allow_contacts) /* uncertainty_contact_planning.hpp:2019 */
+            {
+                members.push_back(&aos[(size_t)(i * width)]);
+                if (collided[i]) any = true; /* :2132 */
+            }
+        }
+        counts[k] = (int64_t)members.size();
+        any_collided[k] = any ? 1 : 0;
+        double* e = expectations + (int64_t)k * width;
+        for (int c = 0; c < width; c++) e[c] = 0.0;
+        variance[k] = 0.0;
+        si_variance[k] = 0.0;
+        for (int v = 0; v < vw; v++) { variances[(int64_t)k * vw + v] = 0.0; si_variances[(int64_t)k * vw + v] = 0.0; }
+        if (members.empty()) continue;
+        /* ComputeExpectation, uncertainty_planner_state.hpp:591-607 */
+        if (members.size() == 1)
+        {
+            for (int c = 0; c < width; c++) e[c] = members[0][c];
+        }
+        else
+        {
+            AverageConfigurations(rd, members, e);
+        }
+        if (members.size() == 1)
+        {
+            /* :608-714: zero variances; the directional ones are dim_distance(p, p) */
+            double dd[UPC_MAX_DOF];
+            PerDimensionDistance(rd, members[0], members[0], dd);
+            for (int v = 0; v < vw; v++) { variances[(int64_t)k * vw + v] = dd[v]; si_variances[(int64_t)k * vw + v] = dd[v]; }
+            continue;
+        }
+        const double weight = 1.0 / (double)members.size();
+        double var_sum = 0.0, si_sum = 0.0;
+        for (const double* p : members)
+        {
+            const double raw = robot.ComputeConfigurationDistance(e, p);
+            var_sum = var_sum + ((raw * raw) * weight);
+            const double si = raw / step_size;
+            si_sum = si_sum + ((si * si) * weight);
+            double dd[UPC_MAX_DOF];
+            PerDimensionDistance(rd, e, p, dd);
+            for (int v = 0; v < vw; v++)
+            {
+                variances[(int64_t)k * vw + v] = variances[(int64_t)k * vw + v] + ((dd[v] * dd[v]) * weight);
+                const double sd = dd[v] / step_size;
+                si_variances[(int64_t)k * vw + v] = si_variances[(int64_t)k * vw + v] + ((sd * sd) * weight);
+            }
+        }
+        variance[k] = var_sum;
+        si_variance[k] = si_sum;
+    }
+}
+
 static void ValidateRobot(const upc_robot_desc* r)
 {
     if (!r) throw std::invalid_argument("null robot");
@@ -1453,6 +1644,12 @@ int32_t upc_config_width(int32_t kind, int32_t dof)
 int64_t upc_tape_doubles_per_particle(const upc_sim_params* p, int32_t dof)
 {
     return (int64_t)p->num_steps * (int64_t)(1 + p->max_microsteps) * (int64_t)dof;
+}
+int32_t upc_variance_width(int32_t kind, int32_t dof)
+{
+    if (kind == UPC_ROBOT_SE2) return 3;
+    if (kind == UPC_ROBOT_SE3) return 4;
+    return dof;
 }
 #endif
 
@@ -1682,6 +1879,22 @@ int32_t oracle_sdf_lookup(const upc_env_desc* env_desc, int64_t n, const double*
         double u[3];
         TransformPoint(V, world_points + 3 * i, u);
         SdfSample(env, u, dist + i, grad ? (grad + 3 * i) : nullptr);
+    }
+    return UPC_OK;
+    ORACLE_CATCH
+}
+
+int32_t oracle_cluster_statistics(const upc_robot_desc* robot, int64_t n, const double* configs, const int32_t* labels, const uint8_t* collided,
+                                  int32_t allow_contacts, double step_size, int32_t n_clusters, int64_t* counts, uint8_t* any_collided,
+                                  double* expectations, double* variance, double* si_variance, double* variances, double* si_variances)
+{
+    ORACLE_TRY
+    ValidateRobot(robot);
+    switch (robot->kind)
+    {
+        case UPC_ROBOT_SE2: ClusterStatistics<Se2Robot>(*robot, n, configs, labels, collided, allow_contacts, step_size, n_clusters, counts, any_collided, expectations, variance, si_variance, variances, si_variances); break;
+        case UPC_ROBOT_SE3: ClusterStatistics<Se3Robot>(*robot, n, configs, labels, collided, allow_contacts, step_size, n_clusters, counts, any_collided, expectations, variance, si_variance, variances, si_variances); break;
+        default: ClusterStatistics<LinkedRobot>(*robot, n, configs, labels, collided, allow_contacts, step_size, n_clusters, counts, any_collided, expectations, variance, si_variance, variances, si_variances); break;
     }
     return UPC_OK;
     ORACLE_CATCH

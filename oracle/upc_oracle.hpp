@@ -114,6 +114,9 @@ int32_t oracle_region_signatures(const upc_env_desc* env, const upc_robot_desc* 
                                  uint32_t* signatures);
 int32_t oracle_sdf_lookup(const upc_env_desc* env, int64_t n, const double* world_points, double* dist, double* grad);
 int32_t oracle_complete_link(const double* matrix, int64_t n, double threshold, int32_t* labels, int32_t* n_clusters);
+int32_t oracle_cluster_statistics(const upc_robot_desc* robot, int64_t n, const double* configs, const int32_t* labels, const uint8_t* collided,
+                                  int32_t allow_contacts, double step_size, int32_t n_clusters, int64_t* counts, uint8_t* any_collided,
+                                  double* expectations, double* variance, double* si_variance, double* variances, double* si_variances);
 /* reference-shaped distance pass (std::function per pair + heap-allocated delta vector per pair, as at
  * uncertainty_contact_planning.hpp:1955-1960 and simple_robot_models.hpp:412,2195), for the honest CPU baseline */
 int32_t oracle_pair_distances_reference_style(const upc_robot_desc* robot, int64_t n, const double* configs, double* matrix);

@@ -12,6 +12,8 @@
 
 extern "C" int32_t oracle_forward_simulate(const upc_env_desc*, const upc_robot_desc*, const upc_sim_params*, int64_t, const double*, int64_t,
                                            const double*, const double*, double*, uint8_t*, upc_stats*);
+extern "C" int32_t oracle_cluster_statistics(const upc_robot_desc*, int64_t, const double*, const int32_t*, const uint8_t*, int32_t, double, int32_t, int64_t*,
+                                             uint8_t*, double*, double*, double*, double*, double*);
 extern "C" int32_t oracle_cluster_particles(const upc_env_desc*, const upc_robot_desc*, const upc_cluster_params*, int64_t, int64_t, const double*,
                                             int32_t*, int32_t*, upc_stats*);
 
@@ -97,6 +99,19 @@ int main()
     size_t kept = 0;
     for (const auto& c : without) kept += c.size();
     if (kept != n - collided) { std::printf("allow_contacts=false kept %zu, expected %zu\n", kept, n - collided); return 8; }
+    {
+        /* per-cluster statistics through the shim vs the oracle */
+        const auto index_clusters = [&]() { std::vector<const SE2Config*> p; for (const auto& r : results) p.push_back(&r.first); return clustering.ClusterIndices(p); }();
+        const auto st = clustering.ClusterStatistics(results, index_clusters, true, 0.25, UPC_ROBOT_SE2, 3);
+        const size_t K = index_clusters.size();
+        std::vector<int64_t> counts(K);
+        std::vector<uint8_t> any(K);
+        std::vector<double> e(K * 3), v(K), si(K), vs(K * 3), sis(K * 3);
+        if (oracle_cluster_statistics(&robot.desc, (int64_t)n, out.data(), labels.data(), coll.data(), 1, 0.25, (int32_t)K, counts.data(), any.data(), e.data(),
+                                      v.data(), si.data(), vs.data(), sis.data()) != 0) return 12;
+        if (st.counts != counts || st.any_collided != any || st.expectations != e || st.variance != v || st.si_variance != si || st.variances != vs || st.si_variances != sis)
+        { std::printf("cluster statistics differ\n"); return 13; }
+    }
     const auto idx = clustering.PolicyParticleClusteringFn(std::vector<SE2Config>(starts.begin(), starts.begin() + 10), starts[0]);
     if (idx.size() != 1 || idx[0].size() != 11) { std::printf("policy clustering wrong\n"); return 9; }
     const bool in_collision = simulator.CheckConfigCollision(stub, SE2Config{3.2, 3.6, 0.0});

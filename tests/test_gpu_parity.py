@@ -142,6 +142,34 @@ def test_check_config_collision_matches_oracle(oracle, simulators):
         assert 0 < hits < 40
 
 
+def test_cluster_statistics_match_oracle(oracle, simulators):
+    """next row 8f-1: counts / any-collided bit-exact, expectations and variances 0 ulp (sequential sums replayed in order)"""
+    from uncertainty_planning_core_b200 import OutcomeClustering
+    for case in (cases.cl_se2_blobs, cases.cl_se2_wrap, cases.cl_se3_blobs, cases.cl_se3_random, cases.cl_linked_blobs, cases.cl_linked_random_mixed):
+        c = case()
+        sim = simulators("st_" + case.__name__, c["env"], c["robot"])
+        oc = OutcomeClustering(sim, abi.FEATURE_NONE, 0.125, c["cparams"].distance_clustering_threshold)
+        cfg = c["configs"]
+        labels, ncl = oc.ClusterIndices(cfg)
+        rng = np.random.default_rng(9)
+        collided = rng.random(len(cfg)) < 0.3
+        K = int(ncl[0])
+        if K >= 2:
+            collided[labels == 1] = True          # a cluster whose members all collided
+        for allow in (True, False):
+            got = oc.ClusterStatistics(cfg, labels, collided, allow, 0.25, K)
+            want = oracle.cluster_statistics(c["robot"], cfg, labels, collided, allow, 0.25, K)
+            assert np.array_equal(got["counts"], want["counts"]) and np.array_equal(got["any_collided"], want["any_collided"])
+            for key in ("expectations", "variance", "si_variance", "variances", "si_variances"):
+                assert max_ulp_diff(got[key], want[key]) == 0, (case.__name__, allow, key)
+            keep = allow | ~collided
+            assert int(got["counts"].sum()) == int(keep.sum())
+            if not allow:
+                assert not got["any_collided"].any()
+                if K >= 2:
+                    assert got["counts"][1] == 0
+
+
 def test_count_within_and_reverse_edge_probability(oracle, simulators):
     """next row 8f-2: counts are bit-exact against the oracle's distances (<= threshold, uncertainty_contact_planning.hpp:2083)"""
     for make in (cases.se2_contact, cases.se3_contact, cases.linked_contact):

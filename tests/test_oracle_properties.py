@@ -188,3 +188,37 @@ def test_results_do_not_depend_on_thread_count(oracle):
     # tapes are keyed by particle: a shard of the batch sees the same draws
     shard = abi.fill_noise_tape(sc["seed"], sc["robot"], sc["params"], 10, first_particle=20)
     assert np.array_equal(shard, tape[..., 20:30])
+
+
+def test_cluster_statistics_properties(oracle):
+    """per-cluster statistics (uncertainty_planner_state.hpp:591-714): means, contact filter, single-particle cases"""
+    c = cases.cl_se2_blobs()
+    cfg = c["configs"]
+    labels, ncl, _ = oracle.cluster_particles(c["env"], c["robot"], c["cparams"], cfg)
+    K = int(ncl[0])
+    assert K >= 2
+    collided = np.zeros(len(cfg), dtype=bool)
+    collided[labels == 1] = True
+    st = oracle.cluster_statistics(c["robot"], cfg, labels, collided, True, 0.25, K)
+    assert st["counts"].sum() == len(cfg) and st["any_collided"][1] and st["any_collided"].sum() == 1
+    for k in range(K):
+        m = cfg[labels == k]
+        assert np.allclose(st["expectations"][k][:2], m[:, :2].mean(axis=0), atol=1e-12)
+        assert abs(st["expectations"][k][2] - m[:, 2].mean()) < 1e-3           # circular mean of a tight blob
+        assert np.isclose(st["si_variance"][k], st["variance"][k] / 0.25 ** 2, rtol=1e-12)
+        assert np.allclose(st["variances"][k][:2], ((m[:, :2] - st["expectations"][k][:2]) ** 2).mean(axis=0), rtol=1e-9, atol=1e-15)
+    st2 = oracle.cluster_statistics(c["robot"], cfg, labels, collided, False, 0.25, K)
+    assert st2["counts"][1] == 0 and not st2["any_collided"].any() and np.all(st2["expectations"][1] == 0.0)
+    # one particle per cluster: expectation is the particle, variances vanish
+    one = oracle.cluster_statistics(c["robot"], cfg[:4], np.arange(4, dtype=np.int32), np.zeros(4, dtype=bool), True, 0.25, 4)
+    assert np.array_equal(one["expectations"], cfg[:4]) and not one["variance"].any() and not one["variances"].any()
+    # SE3: expectation of a cluster is a rotation matrix with the mean translation
+    c3 = cases.cl_se3_blobs()
+    l3, n3, _ = oracle.cluster_particles(c3["env"], c3["robot"], c3["cparams"], c3["configs"])
+    s3 = oracle.cluster_statistics(c3["robot"], c3["configs"], l3, np.zeros(len(l3), dtype=bool), True, 0.25, int(n3[0]))
+    for k in range(int(n3[0])):
+        if s3["counts"][k] < 2:
+            continue
+        R = s3["expectations"][k][:9].reshape(3, 3)
+        assert np.allclose(R @ R.T, np.eye(3), atol=1e-12) and np.linalg.det(R) > 0.999
+        assert np.allclose(s3["expectations"][k][9:], c3["configs"][l3 == k][:, 9:].mean(axis=0), atol=1e-12)

@@ -123,6 +123,13 @@ int64_t upc_tape_doubles_per_particle(const upc_sim_params* p, int32_t dof)
     return (int64_t)p->num_steps * (int64_t)(1 + p->max_microsteps) * (int64_t)dof;
 }
 
+int32_t upc_variance_width(int32_t kind, int32_t dof)
+{
+    if (kind == UPC_ROBOT_SE2) return 3;
+    if (kind == UPC_ROBOT_SE3) return 4;
+    return dof;
+}
+
 const char* upc_last_error(void) { return g_last_error.c_str(); }
 const char* upc_version(void) { return "upc_b200 0.1 (sm_100a)"; }
 
@@ -516,6 +523,62 @@ int32_t upc_check_config_collision(upc_handle* h, const double* config, double c
     UPC_CUDA_TRY(cudaMemcpyAsync(&result, h->st_ncl.ptr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     UPC_CUDA_TRY(cudaStreamSynchronize(h->stream));
     *out_in_collision = result;
+    return UPC_OK;
+}
+
+int32_t upc_cluster_statistics(upc_handle* h, int64_t n, const double* configs, const int32_t* labels, const uint8_t* collided,
+                               int32_t allow_contacts, double step_size, int32_t n_clusters, int64_t* counts, uint8_t* any_collided,
+                               double* expectations, double* variance, double* si_variance, double* variances, double* si_variances)
+{
+    if (!h) return fail_arg("null handle");
+    if (!h->has_robot)
+    {
+        set_error("upc_set_robot has not been called");
+        return UPC_ERR_NO_ROBOT;
+    }
+    if (n < 0 || n_clusters < 0) return fail_arg("negative size");
+    if (n_clusters == 0) return UPC_OK;
+    if (!configs || !labels || !collided || !counts || !any_collided || !expectations || !variance || !si_variance || !variances || !si_variances)
+        return fail_arg("null buffer");
+    if (!(step_size > 0.0)) return fail_arg("step_size must be > 0");
+    UPC_CUDA_TRY(cudaSetDevice(h->device));
+    const int width = upc_config_width(h->robot.kind, h->robot.dof);
+    const int vw = upc_variance_width(h->robot.kind, h->robot.dof);
+    const size_t cfg_bytes = (size_t)width * (size_t)n * sizeof(double);
+    UPC_CUDA_TRY(h->st_starts.reserve(cfg_bytes + 64));
+    UPC_CUDA_TRY(h->st_labels.reserve((size_t)n * sizeof(int32_t) + 64));
+    UPC_CUDA_TRY(h->st_coll.reserve((size_t)n + 64));
+    /* outputs: counts i64 | expectations | variance | si_variance | variances | si_variances (doubles) | any_collided u8 */
+    const size_t K = (size_t)n_clusters;
+    const size_t out_doubles = K * (size_t)(width + 2 + 2 * vw);
+    UPC_CUDA_TRY(h->st_out.reserve(K * 8 + out_doubles * 8 + K + 64));
+    uint8_t* base = (uint8_t*)h->st_out.ptr;
+    int64_t* d_counts = (int64_t*)base;
+    double* d_exp = (double*)(base + K * 8);
+    double* d_var = d_exp + K * width;
+    double* d_si = d_var + K;
+    double* d_vars = d_si + K;
+    double* d_sivars = d_vars + K * vw;
+    uint8_t* d_any = (uint8_t*)(d_sivars + K * vw);
+    if (n > 0)
+    {
+        UPC_CUDA_TRY(cudaMemcpyAsync(h->st_starts.ptr, configs, cfg_bytes, cudaMemcpyHostToDevice, h->stream));
+        UPC_CUDA_TRY(cudaMemcpyAsync(h->st_labels.ptr, labels, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        UPC_CUDA_TRY(cudaMemcpyAsync(h->st_coll.ptr, collided, (size_t)n, cudaMemcpyHostToDevice, h->stream));
+        h->stats.h2d_bytes += (int64_t)(cfg_bytes + (size_t)n * 5);
+    }
+    UPC_CUDA_TRY(launch_cluster_stats(h, n, (const double*)h->st_starts.ptr, (const int32_t*)h->st_labels.ptr, (const uint8_t*)h->st_coll.ptr,
+                                      allow_contacts, step_size, n_clusters, d_counts, d_any, d_exp, d_var, d_si, d_vars, d_sivars, h->stream));
+    h->stats.kernel_launches++;
+    UPC_CUDA_TRY(cudaMemcpyAsync(counts, d_counts, K * 8, cudaMemcpyDeviceToHost, h->stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(expectations, d_exp, K * width * 8, cudaMemcpyDeviceToHost, h->stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(variance, d_var, K * 8, cudaMemcpyDeviceToHost, h->stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(si_variance, d_si, K * 8, cudaMemcpyDeviceToHost, h->stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(variances, d_vars, K * vw * 8, cudaMemcpyDeviceToHost, h->stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(si_variances, d_sivars, K * vw * 8, cudaMemcpyDeviceToHost, h->stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(any_collided, d_any, K, cudaMemcpyDeviceToHost, h->stream));
+    UPC_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->stats.d2h_bytes += (int64_t)(K * 8 + out_doubles * 8 + K);
     return UPC_OK;
 }
 

@@ -1038,6 +1038,265 @@ __global__ void __launch_bounds__(256) propagate_kernel(const uint32_t* __restri
     }
 }
 
+/* ------------------------------------------------------------------ per-cluster statistics */
+
+struct StatsArgs
+{
+    DevRobot robot;
+    int64_t n;
+    const double* cfg; /* [C][n] */
+    const int32_t* labels;
+    const uint8_t* collided;
+    int allow_contacts;
+    double step_size;
+    int64_t* counts;
+    uint8_t* any_collided;
+    double* expectations; /* [K][C] */
+    double* variance;
+    double* si_variance;
+    double* variances;    /* [K][V] */
+    double* si_variances;
+};
+
+__device__ __forceinline__ void quat_to_rotation(const double* q, double* T)
+{
+    const double x = q[0], y = q[1], z = q[2], w = q[3];
+    T[0] = 1.0 - 2.0 * ((y * y) + (z * z));
+    T[1] = 2.0 * ((x * y) - (z * w));
+    T[2] = 2.0 * ((x * z) + (y * w));
+    T[4] = 2.0 * ((x * y) + (z * w));
+    T[5] = 1.0 - 2.0 * ((x * x) + (z * z));
+    T[6] = 2.0 * ((y * z) - (x * w));
+    T[8] = 2.0 * ((x * z) - (y * w));
+    T[9] = 2.0 * ((y * z) + (x * w));
+    T[10] = 1.0 - 2.0 * ((x * x) + (y * y));
+}
+
+template <int KIND>
+__device__ __forceinline__ void per_dimension_distance(const DevRobot& r, const double* c1, const double* c2, double* out)
+{
+    if (KIND == UPC_ROBOT_SE2)
+    {
+        out[0] = fabs(c2[0] - c1[0]);
+        out[1] = fabs(c2[1] - c1[1]);
+        out[2] = fabs(upc_angle_signed_distance(c1[2], c2[2]));
+    }
+    else if (KIND == UPC_ROBOT_SE3)
+    {
+        double t1[12], t2[12];
+        for (int rr = 0; rr < 3; rr++)
+        {
+            for (int k = 0; k < 3; k++) { t1[rr * 4 + k] = c1[rr * 3 + k]; t2[rr * 4 + k] = c2[rr * 3 + k]; }
+            t1[rr * 4 + 3] = c1[9 + rr]; t2[rr * 4 + 3] = c2[9 + rr];
+        }
+        out[0] = fabs(t2[3] - t1[3]);
+        out[1] = fabs(t2[7] - t1[7]);
+        out[2] = fabs(t2[11] - t1[11]);
+        double q1[4], q2[4];
+        quat_from_xf(t1, q1);
+        quat_from_xf(t2, q2);
+        const double dq = fabs((((q1[0] * q2[0]) + (q1[1] * q2[1])) + (q1[2] * q2[2])) + (q1[3] * q2[3]));
+        out[3] = (dq < (1.0 - 2.220446049250313e-16)) ? fabs(upc_acos(((2.0 * dq) * dq) - 1.0)) : 0.0;
+    }
+    else
+    {
+        for (int a = 0; a < r.dof; a++)
+        {
+            const double raw = r.axis_continuous[a] ? upc_angle_signed_distance(c1[a], c2[a]) : (c2[a] - c1[a]);
+            out[a] = fabs(raw * r.weights[a]);
+        }
+    }
+}
+
+/*
+ * One warp per cluster.  Members are visited in ascending particle order (32 candidates per ballot, then the set
+ * bits in order), every lane accumulating the same sequential sums, so the results are those of the serial loops of
+ * uncertainty_planner_state.hpp:591-714 bit for bit.
+ */
+template <int KIND>
+__global__ void __launch_bounds__(32) cluster_stats_kernel(const __grid_constant__ StatsArgs a)
+{
+    constexpr int W = (KIND == UPC_ROBOT_SE2) ? 3 : ((KIND == UPC_ROBOT_SE3) ? 12 : UPC_MAX_DOF);
+    constexpr int VW = (KIND == UPC_ROBOT_SE2) ? 3 : ((KIND == UPC_ROBOT_SE3) ? 4 : UPC_MAX_DOF);
+    const int k = blockIdx.x;
+    const int lane = threadIdx.x;
+    const int width = (KIND == UPC_ROBOT_LINKED) ? a.robot.dof : W;
+    const int vw = (KIND == UPC_ROBOT_LINKED) ? a.robot.dof : VW;
+    /* pass 1: count and sums */
+    int64_t count = 0;
+    bool any = false;
+    double acc[2 * UPC_MAX_DOF]; /* SE2: sx sy ss sc; SE3: st[3] sq[4]; linked: per joint (sum | sin, cos) */
+    for (int j = 0; j < 2 * UPC_MAX_DOF; j++) acc[j] = 0.0;
+    double qref[4] = {0.0, 0.0, 0.0, 1.0};
+    double first_cfg[W];
+    for (int c = 0; c < W; c++) first_cfg[c] = 0.0;
+    for (int64_t base = 0; base < a.n; base += 32)
+    {
+        const int64_t i = base + lane;
+        const bool member = (i < a.n) && (a.labels[i] == k) && ((a.collided[i] == 0) || a.allow_contacts);
+        unsigned todo = __ballot_sync(0xffffffffu, member);
+        while (todo)
+        {
+            const int src = __ffs((int)todo) - 1;
+            todo &= todo - 1u;
+            const int64_t p = base + src;
+            double c[W];
+            for (int x = 0; x < width; x++) c[x] = a.cfg[(int64_t)x * a.n + p];
+            if (count == 0)
+                for (int x = 0; x < width; x++) first_cfg[x] = c[x];
+            if (a.collided[p]) any = true;
+            if (KIND == UPC_ROBOT_SE2)
+            {
+                acc[0] = acc[0] + c[0];
+                acc[1] = acc[1] + c[1];
+                double sn, cs;
+                upc_sincos(c[2], &sn, &cs);
+                acc[2] = acc[2] + sn;
+                acc[3] = acc[3] + cs;
+            }
+            else if (KIND == UPC_ROBOT_SE3)
+            {
+                double T[12], q[4];
+                for (int rr = 0; rr < 3; rr++)
+                {
+                    for (int x = 0; x < 3; x++) T[rr * 4 + x] = c[rr * 3 + x];
+                    T[rr * 4 + 3] = c[9 + rr];
+                }
+                acc[0] = acc[0] + T[3];
+                acc[1] = acc[1] + T[7];
+                acc[2] = acc[2] + T[11];
+                quat_from_xf(T, q);
+                if (count == 0)
+                    for (int x = 0; x < 4; x++) qref[x] = q[x];
+                const double dot = (((q[0] * qref[0]) + (q[1] * qref[1])) + (q[2] * qref[2])) + (q[3] * qref[3]);
+                const double sign = (dot < 0.0) ? -1.0 : 1.0;
+                for (int x = 0; x < 4; x++) acc[3 + x] = acc[3 + x] + (sign * q[x]);
+            }
+            else
+            {
+                for (int x = 0; x < width; x++)
+                {
+                    if (a.robot.axis_continuous[x])
+                    {
+                        double sn, cs;
+                        upc_sincos(c[x], &sn, &cs);
+                        acc[2 * x] = acc[2 * x] + sn;
+                        acc[2 * x + 1] = acc[2 * x + 1] + cs;
+                    }
+                    else
+                    {
+                        acc[2 * x] = acc[2 * x] + c[x];
+                    }
+                }
+            }
+            count++;
+        }
+    }
+    /* expectation (ComputeExpectation: a single particle is returned as is) */
+    double e[W];
+    for (int c = 0; c < W; c++) e[c] = 0.0;
+    const double nd = (double)count;
+    if (count == 1)
+    {
+        for (int c = 0; c < width; c++) e[c] = first_cfg[c];
+    }
+    else if (count > 1)
+    {
+        if (KIND == UPC_ROBOT_SE2)
+        {
+            e[0] = acc[0] / nd;
+            e[1] = acc[1] / nd;
+            e[2] = upc_atan2(acc[2], acc[3]);
+        }
+        else if (KIND == UPC_ROBOT_SE3)
+        {
+            const double norm = sqrt((((acc[3] * acc[3]) + (acc[4] * acc[4])) + (acc[5] * acc[5])) + (acc[6] * acc[6]));
+            double q[4], T[12];
+            for (int x = 0; x < 4; x++) q[x] = acc[3 + x] / norm;
+            quat_to_rotation(q, T);
+            for (int rr = 0; rr < 3; rr++)
+                for (int x = 0; x < 3; x++) e[rr * 3 + x] = T[rr * 4 + x];
+            e[9] = acc[0] / nd;
+            e[10] = acc[1] / nd;
+            e[11] = acc[2] / nd;
+        }
+        else
+        {
+            for (int x = 0; x < width; x++) e[x] = a.robot.axis_continuous[x] ? upc_atan2(acc[2 * x], acc[2 * x + 1]) : (acc[2 * x] / nd);
+        }
+    }
+    /* pass 2: variances */
+    double var_sum = 0.0, si_sum = 0.0;
+    double dv[VW], dsi[VW];
+    for (int v = 0; v < VW; v++) { dv[v] = 0.0; dsi[v] = 0.0; }
+    if (count == 1)
+    {
+        double dd[VW];
+        per_dimension_distance<KIND>(a.robot, first_cfg, first_cfg, dd);
+        for (int v = 0; v < vw; v++) { dv[v] = dd[v]; dsi[v] = dd[v]; }
+    }
+    else if (count > 1)
+    {
+        const double weight = 1.0 / nd;
+        for (int64_t base = 0; base < a.n; base += 32)
+        {
+            const int64_t i = base + lane;
+            const bool member = (i < a.n) && (a.labels[i] == k) && ((a.collided[i] == 0) || a.allow_contacts);
+            unsigned todo = __ballot_sync(0xffffffffu, member);
+            while (todo)
+            {
+                const int src = __ffs((int)todo) - 1;
+                todo &= todo - 1u;
+                const int64_t p = base + src;
+                double c[W];
+                for (int x = 0; x < width; x++) c[x] = a.cfg[(int64_t)x * a.n + p];
+                double raw;
+                if (KIND == UPC_ROBOT_SE2) raw = Se2Model::distance(a.robot, e, c);
+                else if (KIND == UPC_ROBOT_SE3) raw = Se3Model::distance(a.robot, e, c);
+                else raw = LinkedModel::distance(a.robot, e, c);
+                var_sum = var_sum + ((raw * raw) * weight);
+                const double si = raw / a.step_size;
+                si_sum = si_sum + ((si * si) * weight);
+                double dd[VW];
+                per_dimension_distance<KIND>(a.robot, e, c, dd);
+                for (int v = 0; v < vw; v++)
+                {
+                    dv[v] = dv[v] + ((dd[v] * dd[v]) * weight);
+                    const double sd = dd[v] / a.step_size;
+                    dsi[v] = dsi[v] + ((sd * sd) * weight);
+                }
+            }
+        }
+    }
+    if (lane == 0)
+    {
+        a.counts[k] = count;
+        a.any_collided[k] = any ? 1 : 0;
+        for (int c = 0; c < width; c++) a.expectations[(int64_t)k * width + c] = e[c];
+        a.variance[k] = var_sum;
+        a.si_variance[k] = si_sum;
+        for (int v = 0; v < vw; v++)
+        {
+            a.variances[(int64_t)k * vw + v] = dv[v];
+            a.si_variances[(int64_t)k * vw + v] = dsi[v];
+        }
+    }
+}
+
+cudaError_t launch_cluster_stats(upc_handle* h, int64_t n, const double* cfg, const int32_t* labels, const uint8_t* collided, int allow_contacts,
+                                 double step_size, int n_clusters, int64_t* counts, uint8_t* any_collided, double* expectations, double* variance,
+                                 double* si_variance, double* variances, double* si_variances, cudaStream_t stream)
+{
+    StatsArgs a;
+    a.robot = h->robot; a.n = n; a.cfg = cfg; a.labels = labels; a.collided = collided; a.allow_contacts = allow_contacts; a.step_size = step_size;
+    a.counts = counts; a.any_collided = any_collided; a.expectations = expectations; a.variance = variance; a.si_variance = si_variance;
+    a.variances = variances; a.si_variances = si_variances;
+    if (h->robot.kind == UPC_ROBOT_SE2) cluster_stats_kernel<UPC_ROBOT_SE2><<<(unsigned)n_clusters, 32, 0, stream>>>(a);
+    else if (h->robot.kind == UPC_ROBOT_SE3) cluster_stats_kernel<UPC_ROBOT_SE3><<<(unsigned)n_clusters, 32, 0, stream>>>(a);
+    else cluster_stats_kernel<UPC_ROBOT_LINKED><<<(unsigned)n_clusters, 32, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
 /* ------------------------------------------------------------------ host orchestration */
 
 struct PassInput

@@ -80,6 +80,9 @@ cudaError_t launch_forward_simulate(upc_handle* h, const DevSim& sp, int64_t n, 
 cudaError_t launch_count_within(upc_handle* h, int64_t n, const double* d_configs, int64_t n_targets, const double* d_targets, double threshold,
                                 unsigned long long* d_count, uint8_t* d_within, cudaStream_t stream);
 cudaError_t launch_check_collision(upc_handle* h, const double* d_config, double threshold, int* d_out, cudaStream_t stream);
+cudaError_t launch_cluster_stats(upc_handle* h, int64_t n, const double* cfg, const int32_t* labels, const uint8_t* collided, int allow_contacts,
+                                 double step_size, int n_clusters, int64_t* counts, uint8_t* any_collided, double* expectations, double* variance,
+                                 double* si_variance, double* variances, double* si_variances, cudaStream_t stream);
 int32_t run_cluster(upc_handle* h, const upc_cluster_params& cp, int64_t n_sets, int64_t set_size, const double* d_configs,
                     int32_t* d_labels, int32_t* d_n_clusters, cudaStream_t stream);
 }

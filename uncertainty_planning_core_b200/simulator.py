@@ -181,6 +181,27 @@ class OutcomeClustering:
             clusters.append((configs[keep], collided[keep]))
         return clusters
 
+    def ClusterStatistics(self, configs, labels, collided, allow_contacts, step_size, n_clusters):
+        """Per-cluster reduction behind UncertaintyPlannerState::UpdateStatistics (uncertainty_planner_state.hpp:339-351):
+        dict of counts [K], any_collided [K], expectations [K, C], variance [K], si_variance [K], variances [K, V],
+        si_variances [K, V] over the particles that survive the contact filter."""
+        cfg = np.asarray(configs, dtype=np.float64)
+        n = cfg.shape[0]
+        robot = self.sim.robot
+        K, W, V = int(n_clusters), robot.width, abi.variance_width(robot.kind, robot.dof)
+        soa = np.ascontiguousarray(cfg.T)
+        lab = np.ascontiguousarray(labels, dtype=np.int32)
+        col = np.ascontiguousarray(np.asarray(collided).astype(np.uint8))
+        out = dict(counts=np.zeros(K, dtype=np.int64), any_collided=np.zeros(K, dtype=np.uint8), expectations=np.zeros((K, W)),
+                   variance=np.zeros(K), si_variance=np.zeros(K), variances=np.zeros((K, V)), si_variances=np.zeros((K, V)))
+        abi.check(self._lib.upc_cluster_statistics(self.sim.handle, n, soa.ctypes.data, lab.ctypes.data, col.ctypes.data,
+                                                   1 if allow_contacts else 0, float(step_size), K, out["counts"].ctypes.data,
+                                                   out["any_collided"].ctypes.data, out["expectations"].ctypes.data,
+                                                   out["variance"].ctypes.data, out["si_variance"].ctypes.data,
+                                                   out["variances"].ctypes.data, out["si_variances"].ctypes.data))
+        out["any_collided"] = out["any_collided"].astype(bool)
+        return out
+
     def PolicyParticleClusteringFn(self, particles, current_config):
         """Index clusters of (particles + [current_config]) as lists of indices (:1558-1578)."""
         allp = np.concatenate([np.asarray(particles, dtype=np.float64),
