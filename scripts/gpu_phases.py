@@ -3,7 +3,7 @@ import ctypes as C, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from uncertainty_planning_core_b200 import B200Simulator, abi, scenarios
-names = ["control", "estimate", "apply", "check", "resolver", "reached", "tape/misc", "-", "res:points", "res:replay", "res:solve", "-"]
+names = ["control", "estimate", "apply", "check", "resolver", "reached", "tape/misc", "-", "res:points", "res:replay", "res:solve", "contributing points (count)"]
 lib = abi.load_library()
 lib.upc_debug_phase_cycles.argtypes = [C.c_void_p, C.c_void_p]
 sc = scenarios.c2_se3()

@@ -40,7 +40,6 @@ static void fill_robot(const upc_robot_desc* r, DevRobot* d)
         d->axis[a].clamp = fabs(r->axis[a].integral_clamp); d->axis[a].vlim = fabs(r->axis[a].velocity_limit);
         d->axis[a].nb = fabs(r->axis[a].max_actuator_noise); d->weights[a] = fabs(r->distance_weights[a]);
     }
-    d->pts = r->points;
     compute_reach(r, d->reach);
     for (int l = 0; l < r->num_links; l++)
     {
@@ -82,7 +81,51 @@ static void run(const DevEnv& env, const DevRobot& rob, const DevSim& sp, int64_
 }
 
 static int g_use_cells = 1;
+static int g_use_fp32_cull = 1;
 extern "C" void emulate_set_corner_cells(int on) { g_use_cells = on; }
+extern "C" void emulate_set_fp32_cull(int on) { g_use_fp32_cull = on; }
+
+/*
+ * Conservativeness of the single-precision pre-cull, tested directly: for n_frames link poses (rows of 12 doubles)
+ * every body point the cull declares clear must be clear for the exact FP64 program at `threshold`.
+ * counts[0] = points tested, [1] = culled, [2] = violations (must be 0), [3] = exact hits.
+ */
+extern "C" int emulate_cull_check(const upc_env_desc* e, const upc_robot_desc* r, int64_t n_frames, const double* frames, double threshold, int64_t* counts)
+{
+    DevEnv env; DevRobot rob;
+    fill_env(e, &env); fill_robot(r, &rob);
+    std::vector<float> cellmin((size_t)(e->nx + 1) * (size_t)(e->ny + 1) * (size_t)(e->nz + 1));
+    build_cellmin(e->sdf, e->nx, e->ny, e->nz, cellmin.data());
+    env.cellmin = cellmin.data();
+    const std::vector<double> both = points_with_float_copy(r->points, r->num_points);
+    rob.pts = both.data();
+    rob.cull_delta = compute_cull_delta(e->nx, e->ny, e->nz, e->resolution, e->grid_from_world, r->points, r->num_points);
+    for (int k = 0; k < 4; k++) counts[k] = 0;
+    if (!(rob.cull_delta > 0.0f)) return 1;
+    const Corner4* ptsf = reinterpret_cast<const Corner4*>(rob.pts + 4 * rob.num_points);
+    for (int64_t f = 0; f < n_frames; f++)
+    {
+        double V[12];
+        voxel_from_link(env, frames + 12 * f, V);
+        for (int l = 0; l < rob.num_links; l++)
+        {
+            const float clear_above = float_round_up((rob.link_radius[l] + threshold) + UPC_CULL_MARGIN);
+            const CullFrame cf = cull_frame(env, V, rob.cull_delta, clear_above);
+            for (int k = rob.link_off[l]; k < rob.link_off[l + 1]; k++)
+            {
+                double u[3];
+                xf_point(V, rob.pts[4 * k + 0], rob.pts[4 * k + 1], rob.pts[4 * k + 2], u);
+                const bool exact_hit = (sdf_distance(env, u) - rob.pts[4 * k + 3]) < threshold;
+                const bool culled = cull_certainly_clear(env, cf, ptsf[k]);
+                counts[0]++;
+                counts[1] += culled ? 1 : 0;
+                counts[2] += (culled && exact_hit) ? 1 : 0;
+                counts[3] += exact_hit ? 1 : 0;
+            }
+        }
+    }
+    return 0;
+}
 
 extern "C" int emulate_forward_simulate(const upc_env_desc* e, const upc_robot_desc* r, const upc_sim_params* p, int64_t n,
                                         const double* starts, int64_t n_targets, const double* targets, const double* tape,
@@ -90,6 +133,9 @@ extern "C" int emulate_forward_simulate(const upc_env_desc* e, const upc_robot_d
 {
     DevEnv env; DevRobot rob; DevSim sp;
     fill_env(e, &env); fill_robot(r, &rob);
+    const std::vector<double> both = points_with_float_copy(r->points, r->num_points);
+    rob.pts = both.data();
+    rob.cull_delta = g_use_fp32_cull ? compute_cull_delta(e->nx, e->ny, e->nz, e->resolution, e->grid_from_world, r->points, r->num_points) : 0.0f;
     std::vector<float> cellmin((size_t)(e->nx + 1) * (size_t)(e->ny + 1) * (size_t)(e->nz + 1));
     build_cellmin(e->sdf, e->nx, e->ny, e->nz, cellmin.data());
     env.cellmin = cellmin.data();

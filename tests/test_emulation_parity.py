@@ -5,19 +5,61 @@ import numpy as np
 import pytest
 
 import cases
-from common import emulate_forward_simulate, max_ulp_diff
+from common import emulate_cull_check, emulate_forward_simulate, max_ulp_diff
+from uncertainty_planning_core_b200 import scenarios
 from uncertainty_planning_core_b200 import abi
 
 
+@pytest.mark.parametrize("fp32_cull", [True, False])
 @pytest.mark.parametrize("corner_cells", [True, False])
 @pytest.mark.parametrize("name", sorted(cases.GOLDEN_SIM_CASES))
-def test_device_program_matches_oracle(oracle, name, corner_cells):
+def test_device_program_matches_oracle(oracle, name, corner_cells, fp32_cull):
     sc = cases.GOLDEN_SIM_CASES[name]()
     n = sc["starts"].shape[0]
     tape = abi.fill_noise_tape(sc["seed"], sc["robot"], sc["params"], n)
     ocfg, ocoll, ostats = oracle.forward_simulate(sc["env"], sc["robot"], sc["params"], sc["starts"], sc["targets"], tape)
-    ecfg, ecoll, estats = emulate_forward_simulate(sc["env"], sc["robot"], sc["params"], sc["starts"], sc["targets"], tape, corner_cells)
+    ecfg, ecoll, estats = emulate_forward_simulate(sc["env"], sc["robot"], sc["params"], sc["starts"], sc["targets"], tape, corner_cells, fp32_cull)
     assert np.array_equal(ocoll, ecoll)
     assert max_ulp_diff(ocfg, ecfg) == 0
     for k in cases.SIM_STAT_KEYS:
         assert ostats[k] == estats[k], k
+
+
+def _random_frames(rng, n, lo, hi, snap=None):
+    frames = np.zeros((n, 12))
+    for i in range(n):
+        R = scenarios.rotation_from_axis_angle(rng.normal(size=3), rng.uniform(0.0, np.pi))
+        t = rng.uniform(lo, hi, size=3)
+        if snap is not None and i % 2 == 0:
+            # adversarial: identity rotation, body origin within a few float ulps of a cell border (voxel centre planes)
+            R = np.eye(3)
+            t = (np.round(t / snap) + 0.5) * snap + rng.uniform(-3e-7, 3e-7, size=3)
+        frames[i] = np.concatenate([R, np.asarray(t, dtype=float)[:, None]], axis=1).ravel()   # row-major [R | t]
+    return frames
+
+
+def test_single_precision_pre_cull_is_conservative():
+    """every point the float pre-cull calls clear is clear for the exact FP64 test - random poses,
+    poses whose points sit on cell borders, poses reaching outside the grid, several thresholds"""
+    rng = np.random.default_rng(77)
+    sc = scenarios.c2_se3(seed=21, n=1, shape=(64, 64, 64), resolution=0.0625)
+    extent = 64 * 0.0625
+    total_culled = total_hits = 0
+    for threshold in (0.0, 0.01, 0.1):
+        for frames in (_random_frames(rng, 300, 0.3, extent - 0.3), _random_frames(rng, 300, -0.2, extent + 0.2),
+                       _random_frames(rng, 400, 0.3, extent - 0.3, snap=0.0625)):
+            tested, culled, violations, hits = emulate_cull_check(sc["env"], sc["robot"], frames, threshold)
+            assert violations == 0
+            assert tested == frames.shape[0] * sc["robot"].desc.num_points
+            total_culled += culled
+            total_hits += hits
+    assert total_culled > 0 and total_hits > 0      # both outcomes were exercised
+    # planar grid (single layer in z): SE(2) body points sit exactly on the layer's centre plane
+    s1 = scenarios.c1_se2(seed=11, n=1, shape=(128, 128, 1), resolution=0.08)
+    frames = np.zeros((500, 12))
+    for i in range(500):
+        th = rng.uniform(-np.pi, np.pi)
+        R = np.array([[np.cos(th), -np.sin(th), 0.0], [np.sin(th), np.cos(th), 0.0], [0.0, 0.0, 1.0]])
+        frames[i] = np.concatenate([R, np.array([[rng.uniform(0.2, 10.0)], [rng.uniform(0.2, 10.0)], [0.0]])], axis=1).ravel()
+    tested, culled, violations, hits = emulate_cull_check(s1["env"], s1["robot"], frames, 0.0)
+    assert violations == 0 and culled > 0 and hits > 0

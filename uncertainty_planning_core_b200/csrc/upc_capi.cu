@@ -331,9 +331,17 @@ int32_t upc_set_robot(upc_handle* h, const upc_robot_desc* r)
     UPC_CUDA_TRY(cudaSetDevice(h->device));
     if (h->d_points) cudaFree(h->d_points);
     h->d_points = nullptr;
-    UPC_CUDA_TRY(cudaMalloc(&h->d_points, (size_t)r->num_points * 4 * sizeof(double)));
-    UPC_CUDA_TRY(cudaMemcpyAsync(h->d_points, r->points, (size_t)r->num_points * 4 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    UPC_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    {
+        const std::vector<double> both = points_with_float_copy(r->points, r->num_points);
+        UPC_CUDA_TRY(cudaMalloc(&h->d_points, both.size() * sizeof(double)));
+        UPC_CUDA_TRY(cudaMemcpyAsync(h->d_points, both.data(), both.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        UPC_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    {
+        /* UPC_B200_NO_FP32_CULL=1 forces the FP64-only point passes (tests exercise both) */
+        const char* off = getenv("UPC_B200_NO_FP32_CULL");
+        d.cull_delta = (off && off[0] == '1') ? 0.0f : compute_cull_delta(h->env.nx, h->env.ny, h->env.nz, h->env.res, h->env.G, r->points, r->num_points);
+    }
     d.pts = h->d_points;
     h->robot = d;
     h->has_robot = true;

@@ -65,10 +65,11 @@ struct DevJoint
 struct DevRobot
 {
     int kind, dof, num_links, num_joints, num_points;
+    float cull_delta;      /* single-precision pre-cull: bound of the float voxel-coordinate error, 0 = pre-cull off */
     int sensor_noise_free; /* every max_sensor_noise is zero: the sensed configuration is the configuration */
     int link_off[UPC_MAX_LINKS + 1];
     int parent_joint_of_link[UPC_MAX_LINKS];
-    const double* pts; /* num_points * 4: x, y, z, radius */
+    const double* pts; /* num_points * 4 doubles: x, y, z, radius; followed by num_points * 4 floats: (float)x, y, z, 0 */
     DevAxis axis[UPC_MAX_DOF];
     double weights[UPC_MAX_DOF];
     double base[12];
@@ -470,6 +471,146 @@ UPC_D float fmin4(const Corner4& a, const Corner4& b)
     const float m2 = (b.y < b.x) ? b.y : b.x, m3 = (b.w < b.z) ? b.w : b.z;
     const float m01 = (m1 < m0) ? m1 : m0, m23 = (m3 < m2) ? m3 : m2;
     return (m23 < m01) ? m23 : m01;
+}
+
+/*
+ * Single-precision pre-cull.  The voxel coordinate of a body point is recomputed in float with an
+ * absolute error below r.cull_delta (bound derived in upc_host_prep.h: compute_cull_delta).  A point is declared clear
+ * only when (a) it is inside the grid by more than that error, (b) its cell fractions are further than that error
+ * from 0 and 1, so the float cell is the cell the FP64 program would pick, and (c) the minimum corner of that cell
+ * exceeds the rounded-up threshold - the same bound the FP64 corner test uses.  Anything else is "undecided" and
+ * goes through the exact FP64 program, so no result ever depends on this code.
+ */
+struct CullFrame
+{
+    float v[12];        /* voxel_from_link with the cell offset folded into the translation (see cull_frame) */
+    float gx, gy, gz;   /* largest |rounding residue| per axis that still pins the cell */
+    int wx, wy, wz;     /* the rounded coordinate must lie in [0, w] */
+    float clear_above;
+};
+
+/*
+ * Per axis the float coordinate q is arranged so that round-to-nearest(q) identifies the cell:
+ *   n >= 2: q = u - 1 = (cell coordinate) - 0.5; cell = round(q) when |q - round(q)| <= 0.5 - delta; only interior
+ *           cells 0..n-2 are accepted (border cells need the exact in-bounds test: undecided);
+ *   n == 1: q = u - 0.5 = cell coordinate; any in-bounds point has |q| < 0.5 and both candidate cells (-1, 0) hold the
+ *           same clamped corners, so cell 0 stands for both: accepted when round(q) = 0 and |q| <= 0.5 - 2 delta.
+ * The cell-minimum table is indexed by cell + 1.
+ */
+UPC_D CullFrame cull_frame(const DevEnv& env, const double* V, float delta, float clear_above)
+{
+    CullFrame f;
+#pragma unroll
+    for (int k = 0; k < 12; k++) f.v[k] = (float)V[k];
+    f.v[3] = (float)(V[3] - ((env.nx == 1) ? 0.5 : 1.0));
+    f.v[7] = (float)(V[7] - ((env.ny == 1) ? 0.5 : 1.0));
+    f.v[11] = (float)(V[11] - ((env.nz == 1) ? 0.5 : 1.0));
+    const float two = delta + delta;
+    f.gx = 0.5f - ((env.nx == 1) ? two : delta);
+    f.gy = 0.5f - ((env.ny == 1) ? two : delta);
+    f.gz = 0.5f - ((env.nz == 1) ? two : delta);
+    f.wx = (env.nx == 1) ? 0 : env.nx - 2;
+    f.wy = (env.ny == 1) ? 0 : env.ny - 2;
+    f.wz = (env.nz == 1) ? 0 : env.nz - 2;
+    f.clear_above = clear_above;
+    return f;
+}
+
+UPC_D float upc_fmaf(float a, float b, float c)
+{
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(a, b, c);
+#else
+    return __builtin_fmaf(a, b, c);
+#endif
+}
+
+UPC_D int float_bits(float x)
+{
+#if defined(__CUDA_ARCH__)
+    return __float_as_int(x);
+#else
+    int b;
+    __builtin_memcpy(&b, &x, sizeof(b));
+    return b;
+#endif
+}
+
+/* round-to-nearest of |q| < 2^22 without the conversion unit: the integer sits in the low mantissa bits of q + 1.5 * 2^23 */
+UPC_D int cull_round(float q, float* residue)
+{
+    const float magic = 12582912.0f;
+    const float t = q + magic;
+    *residue = q - (t - magic);
+    return float_bits(t) - 0x4B400000;
+}
+
+/* index into the cell-minimum table of the cell holding the point, or -1 when the float arithmetic cannot pin it */
+UPC_D int cull_locate(const DevEnv& env, const CullFrame& f, const Corner4& p)
+{
+    const float qx = upc_fmaf(f.v[2], p.z, upc_fmaf(f.v[1], p.y, upc_fmaf(f.v[0], p.x, f.v[3])));
+    const float qy = upc_fmaf(f.v[6], p.z, upc_fmaf(f.v[5], p.y, upc_fmaf(f.v[4], p.x, f.v[7])));
+    const float qz = upc_fmaf(f.v[10], p.z, upc_fmaf(f.v[9], p.y, upc_fmaf(f.v[8], p.x, f.v[11])));
+    float rx, ry, rz;
+    const int ix = cull_round(qx, &rx), iy = cull_round(qy, &ry), iz = cull_round(qz, &rz);
+    const bool ok = (fabsf(rx) <= f.gx) & (fabsf(ry) <= f.gy) & (fabsf(rz) <= f.gz) & ((unsigned)ix <= (unsigned)f.wx) &
+                    ((unsigned)iy <= (unsigned)f.wy) & ((unsigned)iz <= (unsigned)f.wz);
+    const int idx = ((ix + 1) * (env.ny + 1) + (iy + 1)) * (env.nz + 1) + (iz + 1);
+    return ok ? idx : -1;
+}
+
+/* phase A of a point pass: bit j set = point first + j * stride (< lim) needs the exact FP64 evaluation.  Eight
+ * independent lookups are put in flight per trip (branch-free locate, then the loads, then the tests). */
+UPC_D unsigned cull_undecided(const DevEnv& env, const CullFrame& f, const Corner4* ptsf, int first, int lim, int stride)
+{
+    unsigned undecided = 0u;
+    for (int j0 = 0; j0 < 32; j0 += 8)
+    {
+        if (first + j0 * stride >= lim) break;
+        int idx[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+        {
+            const int k = first + (j0 + q) * stride;
+            idx[q] = cull_locate(env, f, ptsf[(k < lim) ? k : first]);
+        }
+        float m[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) m[q] = ldg(env.cellmin + max(idx[q], 0));
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+        {
+            const int k = first + (j0 + q) * stride;
+            const bool clear = (idx[q] >= 0) & (m[q] > f.clear_above);
+            if ((k < lim) & !clear) undecided |= (1u << (j0 + q));
+        }
+    }
+    return undecided;
+}
+
+/* single-point form (tests) */
+UPC_D bool cull_certainly_clear(const DevEnv& env, const CullFrame& f, const Corner4& p)
+{
+    const int idx = cull_locate(env, f, p);
+    if (idx < 0) return false;
+    return ldg(env.cellmin + idx) > f.clear_above;
+}
+
+/* bits j < 32 with first + j * stride < lim */
+UPC_D unsigned valid_point_mask(int first, int lim, int stride)
+{
+    if (first >= lim) return 0u;
+    const int count = (lim - first + stride - 1) / stride;
+    return (count >= 32) ? 0xffffffffu : ((1u << count) - 1u);
+}
+
+UPC_D int lowest_bit(unsigned m)
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)m) - 1;
+#else
+    return __builtin_ctz(m);
+#endif
 }
 
 /*

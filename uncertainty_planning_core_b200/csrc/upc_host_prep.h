@@ -76,6 +76,51 @@ inline void build_corner_cells(const float* sdf, int nx, int ny, int nz, float* 
 }
 
 /*
+ * Single-precision pre-cull: bound of |float cell coordinate - FP64 cell coordinate|.
+ * c_i = t_i + sum_j V_ij p_j with V = (grid_from_world o link) / res.  Rounding V, p, t to float and three fused
+ * multiply-adds perturb c_i by at most eps * (4 |t_i| + 5 sum_j |V_ij p_j|), eps = 2^-24.  With rigid transforms
+ * sum_j |V_ij p_j| <= |p| / res, and a point the cull accepts lies inside the grid, so |t_i| <= n_i + |p| / res:
+ * the error is below 5 eps S, S = max(n) + 1 + 2 max|p| / res.  The value returned is 16 eps S (3x head-room, which
+ * also absorbs the ~1e-13 rounding of the FP64 coordinate itself and transforms that are rigid only to 1e-6), or 0 -
+ * pre-cull off - when grid_from_world is not rigid or the guard would eat a noticeable part of a cell.
+ */
+inline float compute_cull_delta(int nx, int ny, int nz, double res, const double* grid_from_world, const double* points, int num_points)
+{
+    for (int i = 0; i < 3; i++)
+    {
+        const double* row = grid_from_world + 4 * i;
+        const double norm = sqrt(row[0] * row[0] + row[1] * row[1] + row[2] * row[2]);
+        if (!(fabs(norm - 1.0) <= 1.0e-6)) return 0.0f;
+    }
+    double pmax = 0.0;
+    for (int k = 0; k < num_points; k++)
+    {
+        const double* p = points + 4 * k;
+        pmax = std::max(pmax, sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]));
+    }
+    const double S = (double)std::max(nx, std::max(ny, nz)) + 1.0 + 2.0 * pmax / res;
+    const double delta = S * (16.0 / 16777216.0);
+    if (!(delta <= 1.0 / 64.0)) return 0.0f;
+    return (float)(delta * 1.000001);
+}
+
+/* device layout of the body points: num_points * 4 doubles (x, y, z, radius) followed by num_points * 4 floats (x, y, z, 0) */
+inline std::vector<double> points_with_float_copy(const double* points, int num_points)
+{
+    std::vector<double> out((size_t)num_points * 6, 0.0);
+    memcpy(out.data(), points, (size_t)num_points * 4 * sizeof(double));
+    float* f = reinterpret_cast<float*>(out.data() + (size_t)num_points * 4);
+    for (int k = 0; k < num_points; k++)
+    {
+        f[4 * k + 0] = (float)points[4 * k + 0];
+        f[4 * k + 1] = (float)points[4 * k + 1];
+        f[4 * k + 2] = (float)points[4 * k + 2];
+        f[4 * k + 3] = 0.0f;
+    }
+    return out;
+}
+
+/*
  * reach[a]: an upper bound of |d(point)/d(axis a)| over all body points and all configurations.
  * SE2 / SE3: reach[0] = largest |p| of the body points (rotation about the body origin).
  * Linked: for active joint a, the largest distance any point of a descendant link can have from the joint's

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(kBlock, UPC_SIM_MIN_BLOCKS) forward_simulate_k
     extern __shared__ double smem[];
     __shared__ unsigned int s_cnt[4];
     double* pts = smem;
-    const int npd = a.robot.num_points * 4;
+    const int npd = a.robot.num_points * 6; /* 4 doubles + 4 floats per point */
     for (int k = threadIdx.x; k < npd; k += kBlock) pts[k] = a.robot.pts[k];
     if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0u;
     __syncthreads();
@@ -105,7 +105,7 @@ static cudaError_t launch_sim_impl(const SimArgs& a, cudaStream_t stream)
 {
     const int64_t threads = a.n * G;
     const int64_t blocks = (threads + kBlock - 1) / kBlock;
-    size_t smem = (size_t)a.robot.num_points * 4 * sizeof(double);
+    size_t smem = (size_t)a.robot.num_points * 6 * sizeof(double);
     smem += (size_t)(kBlock / G) * (2 * M::WIDTH + 2 * M::DOF + ((M::HAS_FRAMES && G >= 4) ? 2 * (size_t)a.robot.num_links * 12 : 0)) * sizeof(double);
     if (smem > 48 * 1024)
     {

@@ -254,10 +254,12 @@ UPC_DNI double estimate_motion(const DevRobot& r, const M& m, const Group<G>& g,
  *            (ballot + shuffles), accumulating J^T J and J^T c in registers - the same sequence of operations as
  *            the sequential oracle, whatever the number of lanes.
  */
-template <class M, int G>
-UPC_DNI int resolver_correction(const DevEnv& env, const DevRobot& r, const DevSim& sp, const M& m, const Group<G>& g,
+template <class M, int G, bool INDIVIDUAL>
+UPC_DNI int resolver_correction(const DevEnv& env, const DevRobot& r, const DevSim& sp, const M& m_in, const Group<G>& g,
                               const double* pts, double* x, LocalCounters& cnt)
 {
+    const double resolve_distance = sp.resolve_distance;
+    const M m = m_in; /* private copy: the caller's model sits in memory (passed by reference to an out-of-line function) */
     UPC_T0
     constexpr int N = M::DOF;
     const int n = m.dof(r);
@@ -288,7 +290,7 @@ UPC_DNI int resolver_correction(const DevEnv& env, const DevRobot& r, const DevS
             if (env.cells != nullptr)
             {
                 /* corner-cell table: phases A and B in one pass over the lane's points, two lookups in flight per trip */
-                const float clear_above = float_round_up((r.link_radius[l] + sp.resolve_distance) + UPC_CULL_MARGIN);
+                const float clear_above = float_round_up((r.link_radius[l] + resolve_distance) + UPC_CULL_MARGIN);
                 for (int j0 = 0; j0 < 32 && (first + j0 * G) < lim; j0 += 2)
                 {
                     CellRef c[2];
@@ -316,15 +318,15 @@ UPC_DNI int resolver_correction(const DevEnv& env, const DevRobot& r, const DevS
                         if (k < lim)
                         {
                             double grad[3], dist;
-                            if (cell_gradient(env, c[jj], ca[jj], cb[jj], pts[4 * k + 3], sp.resolve_distance, clear_above, &dist, grad))
+                            if (cell_gradient(env, c[jj], ca[jj], cb[jj], pts[4 * k + 3], resolve_distance, clear_above, &dist, grad))
                             {
                                 const double de = dist - pts[4 * k + 3];
-                                if (de < sp.resolve_distance)
+                                if (de < resolve_distance)
                                 {
                                     const double gn2 = dot3(grad, grad);
                                     if (gn2 > 1.0e-24)
                                     {
-                                        const double scale = (sp.resolve_distance - de) / sqrt(gn2);
+                                        const double scale = (resolve_distance - de) / sqrt(gn2);
                                         cbuf[j][0] = grad[0] * scale;
                                         cbuf[j][1] = grad[1] * scale;
                                         cbuf[j][2] = grad[2] * scale;
@@ -347,7 +349,7 @@ UPC_DNI int resolver_correction(const DevEnv& env, const DevRobot& r, const DevS
                     {
                         double u[3];
                         xf_point(V, pts[4 * k + 0], pts[4 * k + 1], pts[4 * k + 2], u);
-                        if (!sdf_certainly_clear(env, u, pts[4 * k + 3], sp.resolve_distance)) undecided |= (1u << j);
+                        if (!sdf_certainly_clear(env, u, pts[4 * k + 3], resolve_distance)) undecided |= (1u << j);
                     }
                 }
             }
@@ -365,12 +367,12 @@ UPC_DNI int resolver_correction(const DevEnv& env, const DevRobot& r, const DevS
                 double u[3], grad[3];
                 xf_point(V, pts[4 * k + 0], pts[4 * k + 1], pts[4 * k + 2], u);
                 const double de = sdf_distance_gradient(env, u, grad) - pts[4 * k + 3];
-                if (de < sp.resolve_distance)
+                if (de < resolve_distance)
                 {
                     const double gn2 = dot3(grad, grad);
                     if (gn2 > 1.0e-24)
                     {
-                        const double scale = (sp.resolve_distance - de) / sqrt(gn2);
+                        const double scale = (resolve_distance - de) / sqrt(gn2);
                         cbuf[j][0] = grad[0] * scale;
                         cbuf[j][1] = grad[1] * scale;
                         cbuf[j][2] = grad[2] * scale;
@@ -416,7 +418,7 @@ UPC_DNI int resolver_correction(const DevEnv& env, const DevRobot& r, const DevS
                     double J[3][N];
                     m.jacobian(r, l, local, world, J);
                     count++;
-                    if (sp.individual_jacobians)
+                    if (INDIVIDUAL)
                     {
                         double A[3][3];
 #pragma unroll
@@ -459,8 +461,11 @@ UPC_DNI int resolver_correction(const DevEnv& env, const DevRobot& r, const DevS
             UPC_T1(9)
         }
     }
+#if defined(UPC_PHASE_TIMING) && defined(__CUDA_ARCH__)
+    cnt.cyc[11] += count; /* contributing points per resolver pass (a count, not cycles) */
+#endif
     if (count == 0) return 0;
-    if (sp.individual_jacobians)
+    if (INDIVIDUAL)
     {
         const double inv = 1.0 / (double)count;
 #pragma unroll
@@ -654,7 +659,8 @@ UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim&
             if (resolving && in_collision && !revert)
             {
                 /* next action: a resolver correction from the current configuration */
-                const int contributing = resolver_correction(env, r, sp, m, g, pts, vec, cnt);
+                const int contributing = sp.individual_jacobians ? resolver_correction<M, G, true>(env, r, sp, m, g, pts, vec, cnt)
+                                                                 : resolver_correction<M, G, false>(env, r, sp, m, g, pts, vec, cnt);
                 UPC_T1(4)
                 if (contributing == 0)
                 {
