@@ -124,6 +124,32 @@ def test_plain_grid_path_matches_oracle_too(oracle):
         del os.environ["UPC_B200_NO_CORNER_CELLS"]
 
 
+def test_single_precision_pre_cull_changes_nothing(oracle):
+    """the float pre-cull of the collision check is a shortcut only - results with it (default, used when
+    a lane holds >= 8 points of a link) and without it are the oracle's, bit for bit; the C2-shaped case has 128 points"""
+    from uncertainty_planning_core_b200 import B200Simulator, scenarios
+    sc = scenarios.c2_se3(seed=5, n=96, num_steps=48, shape=(64, 64, 64), resolution=0.0625)
+    n = sc["starts"].shape[0]
+    tape = abi.fill_noise_tape(9, sc["robot"], sc["params"], n)
+    ocfg, ocoll, ostats = oracle.forward_simulate(sc["env"], sc["robot"], sc["params"], sc["starts"], sc["targets"], tape)
+    assert ocoll.any() and ostats["resolver_iterations"] > 0
+    for off in (False, True):
+        if off:
+            os.environ["UPC_B200_NO_FP32_CULL"] = "1"
+        try:
+            sim = B200Simulator(sc["env"], sc["robot"])
+        finally:
+            os.environ.pop("UPC_B200_NO_FP32_CULL", None)
+        for lanes in (1, 4, 16):          # 128, 32 and 8 points per lane: all take the pre-cull when it is on
+            sim.SetLanesPerParticle(lanes)
+            cfg, coll = sim.ForwardSimulateRobots(sc["starts"], sc["targets"], tape, sc["params"])
+            assert np.array_equal(coll, ocoll) and max_ulp_diff(cfg, ocfg) <= CONFIG_ULP_TOLERANCE
+            st = sim.GetStatistics()
+            sim.ResetStatistics()
+            assert st["resolver_iterations"] == ostats["resolver_iterations"]
+        sim.close()
+
+
 def test_check_config_collision_matches_oracle(oracle, simulators):
     for make in (cases.se2_contact, cases.se3_contact, cases.linked_contact):
         sc = make()

@@ -132,6 +132,57 @@ UPC_D bool check_collision(const DevEnv& env, const DevRobot& r, const M& m, con
              * single precision against (largest radius of the link + threshold + margin) rounded up - conservative for
              * every point of the link, so it never changes a result. */
             const float clear_above = float_round_up((r.link_radius[l] + threshold) + UPC_CULL_MARGIN);
+            if ((r.cull_delta > 0.0f) && (end - beg >= 8 * G))
+            {
+                /* enough points per lane for full batches: single-precision pre-cull against the 4-byte cell minimum
+                 * first (eight lookups in flight), exact FP64 evaluation of the undecided points only */
+                const CullFrame cf = cull_frame(env, V, r.cull_delta, clear_above);
+                const Corner4* ptsf = reinterpret_cast<const Corner4*>(pts + 4 * r.num_points);
+                for (int chunk = beg; chunk < end; chunk += 32 * G)
+                {
+                    const int first = chunk + g.sub;
+                    const int lim = (end < chunk + 32 * G) ? end : (chunk + 32 * G);
+                    unsigned undecided = cull_undecided(env, cf, ptsf, first, lim, G);
+                    while (undecided)
+                    {
+                        int kk[4];
+                        int valid = 0;
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                        {
+                            if (undecided)
+                            {
+                                kk[q] = first + lowest_bit(undecided) * G;
+                                undecided &= undecided - 1u;
+                                valid++;
+                            }
+                            else
+                            {
+                                kk[q] = kk[0]; /* padding repeats a valid point and is ignored below */
+                            }
+                        }
+                        CellRef c[4];
+                        Corner4 ca[4], cb[4];
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                        {
+                            double u[3];
+                            xf_point(V, pts[4 * kk[q] + 0], pts[4 * kk[q] + 1], pts[4 * kk[q] + 2], u);
+                            c[q] = cell_locate(env, u);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                        {
+                            ca[q] = ldg4(c[q].cell);
+                            cb[q] = ldg4(c[q].cell + 4);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                            if (q < valid) hit |= cell_below(env, c[q], ca[q], cb[q], pts[4 * kk[q] + 3], threshold, clear_above);
+                    }
+                }
+                continue;
+            }
             int k = beg + g.sub;
             /* four lookups in flight per trip: locate all, load all, then evaluate */
             for (; k + 3 * G < end; k += 4 * G)
