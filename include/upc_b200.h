@@ -230,6 +230,21 @@ int32_t upc_fill_noise_tape(uint64_t seed, const upc_robot_desc* robot, const up
                             int64_t n, int64_t tape_stride, double* tape);
 
 /*
+ * "Next" row: GetNearestNeighbor (uncertainty_contact_planning.hpp:1506-1542) for n_queries sampled
+ * configurations at once.  Tree state i is described by what StateDistance (:1488-1504) reads from it: its expectation
+ * (expectations [C][n_states]), feasibility_weight[i] = (1 - Pfeasibility) * alpha + (1 - alpha),
+ * variance_weight[i] = erf(|space-independent variances|_1) * alpha_v + (1 - alpha_v) - both change only when the state
+ * does, so the caller keeps them - and use_for_nn[i] (NULL = all enabled).
+ *   distance(i, q) = (feasibility_weight[i] * (ComputeConfigurationDistance(expectation_i, query_q) / step_size)) * variance_weight[i]
+ * out_index[q] = the enabled state of smallest distance (strict <, so ties keep the smallest index, as the reference's
+ * static-schedule loop does; NaN distances are never selected), -1 if there is none; out_distance[q] (may be NULL) its
+ * distance, INFINITY if none.  Host pointers; synchronises.
+ */
+int32_t upc_nearest_neighbors(upc_handle* h, int64_t n_states, const double* expectations, const double* feasibility_weight,
+                              const double* variance_weight, const uint8_t* use_for_nn, int64_t n_queries, const double* queries,
+                              double step_size, int64_t* out_index, double* out_distance);
+
+/*
  * "Next" row: the count behind ComputeReverseEdgeProbability (uncertainty_contact_planning.hpp:2073-2090)
  * and the goal-reached fraction: how many of n configurations ([C][n]) lie within `threshold` (<=) of their target
  * (targets [C][n_targets], n_targets == 1 or n) under the robot's ComputeConfigurationDistance.  Also writes the

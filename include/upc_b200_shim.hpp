@@ -34,6 +34,7 @@
 #include <stdexcept>
 #include <string>
 #include <utility>
+#include <limits>
 #include <vector>
 
 #include "upc_b200.h"
@@ -493,6 +494,42 @@ private:
     upc_handle* handle_;
     upc_cluster_params params_;
 };
+
+/*
+ * GetNearestNeighbor (uncertainty_contact_planning.hpp:1506-1542) for a batch of sampled configurations.  The caller
+ * keeps, per tree state, the expectation and the two StateDistance factors that depend on the state only (:1492-1499).
+ * Returns, per sample, the index of the nearest enabled state (-1 if none).
+ */
+template <typename Configuration>
+inline std::vector<int64_t> NearestNeighbors(upc_handle* handle, const std::vector<const Configuration*>& expectations,
+                                             const std::vector<double>& feasibility_weights, const std::vector<double>& variance_weights,
+                                             const std::vector<uint8_t>& use_for_nearest_neighbors, const std::vector<Configuration>& samples,
+                                             const double step_size, std::vector<double>* distances = nullptr)
+{
+    typedef ConfigTraits<Configuration> Traits;
+    const size_t ns = expectations.size(), nq = samples.size();
+    std::vector<int64_t> nearest(nq, -1);
+    if (distances) distances->assign(nq, std::numeric_limits<double>::infinity());
+    if (nq == 0) return nearest;
+    if (feasibility_weights.size() != ns || variance_weights.size() != ns || (!use_for_nearest_neighbors.empty() && use_for_nearest_neighbors.size() != ns))
+        throw std::invalid_argument("NearestNeighbors: one weight pair (and flag) per state");
+    const int width = Traits::width(samples[0]);
+    std::vector<double> esoa((size_t)width * ns), qsoa((size_t)width * nq), tmp((size_t)width);
+    for (size_t i = 0; i < ns; i++)
+    {
+        Traits::flatten(*expectations[i], tmp.data());
+        for (int c = 0; c < width; c++) esoa[(size_t)c * ns + i] = tmp[(size_t)c];
+    }
+    for (size_t q = 0; q < nq; q++)
+    {
+        Traits::flatten(samples[q], tmp.data());
+        for (int c = 0; c < width; c++) qsoa[(size_t)c * nq + q] = tmp[(size_t)c];
+    }
+    check(upc_nearest_neighbors(handle, (int64_t)ns, esoa.data(), feasibility_weights.data(), variance_weights.data(),
+                                use_for_nearest_neighbors.empty() ? nullptr : use_for_nearest_neighbors.data(), (int64_t)nq, qsoa.data(), step_size,
+                                nearest.data(), distances ? distances->data() : nullptr));
+    return nearest;
+}
 
 } /* namespace upc_b200 */
 

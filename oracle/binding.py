@@ -54,6 +54,8 @@ def load():
     lib.oracle_region_signatures.argtypes = [C.POINTER(abi.EnvDesc), C.POINTER(abi.RobotDesc), i64, vp, vp]
     lib.oracle_sdf_lookup.argtypes = [C.POINTER(abi.EnvDesc), i64, vp, vp, vp]
     lib.oracle_complete_link.argtypes = [vp, i64, dp, vp, vp]
+    lib.oracle_nearest_neighbors.argtypes = [C.POINTER(abi.RobotDesc), i64, vp, vp, vp, vp, i64, vp, dp, vp, vp]
+    lib.oracle_nearest_neighbors.restype = i32
     lib.oracle_cluster_statistics.argtypes = [C.POINTER(abi.RobotDesc), i64, vp, vp, vp, i32, dp, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.oracle_cluster_statistics.restype = i32
     for name in ("oracle_forward_simulate", "oracle_check_config_collision", "oracle_cluster_particles",
@@ -209,6 +211,22 @@ def cluster_statistics(robot, configs, labels, collided, allow_contacts, step_si
                                             out["variances"].ctypes.data, out["si_variances"].ctypes.data))
     out["any_collided"] = out["any_collided"].astype(bool)
     return out
+
+
+def nearest_neighbors(robot, expectations, feasibility_weight, variance_weight, queries, step_size, use_for_nn=None):
+    exp = np.asarray(expectations, dtype=np.float64).reshape(-1, robot.width)
+    qs = np.asarray(queries, dtype=np.float64).reshape(-1, robot.width)
+    ns, nq = exp.shape[0], qs.shape[0]
+    fw = np.ascontiguousarray(feasibility_weight, dtype=np.float64)
+    vw = np.ascontiguousarray(variance_weight, dtype=np.float64)
+    use = None if use_for_nn is None else np.ascontiguousarray(np.asarray(use_for_nn).astype(np.uint8))
+    esoa, qsoa = np.ascontiguousarray(exp.T), np.ascontiguousarray(qs.T)
+    idx = np.zeros(nq, dtype=np.int64)
+    dist = np.zeros(nq, dtype=np.float64)
+    _check(load().oracle_nearest_neighbors(C.byref(robot.desc), ns, esoa.ctypes.data, fw.ctypes.data, vw.ctypes.data,
+                                           None if use is None else use.ctypes.data, nq, qsoa.ctypes.data, float(step_size),
+                                           idx.ctypes.data, dist.ctypes.data))
+    return idx, dist
 
 
 def complete_link(matrix, threshold):

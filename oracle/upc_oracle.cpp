@@ -1099,7 +1099,7 @@ static void ForwardSimulateRobots(const Environment& env, const upc_robot_desc& 
     for (int64_t i = 0; i < n; i++)
     {
         Robot robot = prototype; /* every user of a robot copies it first, e.g. uncertainty_contact_planning.hpp:1599 */
-        double start[16], target[16], result[16];
+        double start[16], target[16], result[16] = {0.0};
         for (int c = 0; c < width; c++)
         {
             start[c] = starts[(int64_t)c * n + i];
@@ -1895,6 +1895,53 @@ int32_t oracle_cluster_statistics(const upc_robot_desc* robot, int64_t n, const 
         case UPC_ROBOT_SE2: ClusterStatistics<Se2Robot>(*robot, n, configs, labels, collided, allow_contacts, step_size, n_clusters, counts, any_collided, expectations, variance, si_variance, variances, si_variances); break;
         case UPC_ROBOT_SE3: ClusterStatistics<Se3Robot>(*robot, n, configs, labels, collided, allow_contacts, step_size, n_clusters, counts, any_collided, expectations, variance, si_variance, variances, si_variances); break;
         default: ClusterStatistics<LinkedRobot>(*robot, n, configs, labels, collided, allow_contacts, step_size, n_clusters, counts, any_collided, expectations, variance, si_variance, variances, si_variances); break;
+    }
+    return UPC_OK;
+    ORACLE_CATCH
+}
+
+extern "C++" {
+template <typename Robot>
+static void NearestNeighbors(const upc_robot_desc& rd, int64_t n_states, const double* expectations, const double* fw, const double* vw,
+                             const uint8_t* use, int64_t n_queries, const double* queries, double step_size, int64_t* out_index, double* out_distance)
+{
+    const Robot robot(rd);
+    const int width = upc_config_width(rd.kind, rd.dof);
+    std::vector<double> e((size_t)width), q((size_t)width);
+    for (int64_t qi = 0; qi < n_queries; qi++)
+    {
+        for (int c = 0; c < width; c++) q[(size_t)c] = queries[(int64_t)c * n_queries + qi];
+        int64_t best_index = -1;
+        double best_distance = INFINITY;
+        for (int64_t i = 0; i < n_states; i++) /* uncertainty_contact_planning.hpp:1513-1530, one thread's view */
+        {
+            if (use != nullptr && use[i] == 0) continue;
+            for (int c = 0; c < width; c++) e[(size_t)c] = expectations[(int64_t)c * n_states + i];
+            const double expectation_distance = robot.ComputeConfigurationDistance(e.data(), q.data()) / step_size; /* :1491 */
+            const double distance = (fw[i] * expectation_distance) * vw[i];                                      /* :1500 */
+            if (distance < best_distance)
+            {
+                best_index = i;
+                best_distance = distance;
+            }
+        }
+        out_index[qi] = best_index;
+        if (out_distance) out_distance[qi] = best_distance;
+    }
+}
+}
+
+int32_t oracle_nearest_neighbors(const upc_robot_desc* robot, int64_t n_states, const double* expectations, const double* feasibility_weight,
+                                 const double* variance_weight, const uint8_t* use_for_nn, int64_t n_queries, const double* queries,
+                                 double step_size, int64_t* out_index, double* out_distance)
+{
+    ORACLE_TRY
+    ValidateRobot(robot);
+    switch (robot->kind)
+    {
+        case UPC_ROBOT_SE2: NearestNeighbors<Se2Robot>(*robot, n_states, expectations, feasibility_weight, variance_weight, use_for_nn, n_queries, queries, step_size, out_index, out_distance); break;
+        case UPC_ROBOT_SE3: NearestNeighbors<Se3Robot>(*robot, n_states, expectations, feasibility_weight, variance_weight, use_for_nn, n_queries, queries, step_size, out_index, out_distance); break;
+        default: NearestNeighbors<LinkedRobot>(*robot, n_states, expectations, feasibility_weight, variance_weight, use_for_nn, n_queries, queries, step_size, out_index, out_distance); break;
     }
     return UPC_OK;
     ORACLE_CATCH

@@ -117,6 +117,10 @@ int32_t oracle_complete_link(const double* matrix, int64_t n, double threshold, 
 int32_t oracle_cluster_statistics(const upc_robot_desc* robot, int64_t n, const double* configs, const int32_t* labels, const uint8_t* collided,
                                   int32_t allow_contacts, double step_size, int32_t n_clusters, int64_t* counts, uint8_t* any_collided,
                                   double* expectations, double* variance, double* si_variance, double* variances, double* si_variances);
+/* GetNearestNeighbor / StateDistance, uncertainty_contact_planning.hpp:1488-1542 (per-state weights supplied by the caller) */
+int32_t oracle_nearest_neighbors(const upc_robot_desc* robot, int64_t n_states, const double* expectations, const double* feasibility_weight,
+                                 const double* variance_weight, const uint8_t* use_for_nn, int64_t n_queries, const double* queries,
+                                 double step_size, int64_t* out_index, double* out_distance);
 /* reference-shaped distance pass (std::function per pair + heap-allocated delta vector per pair, as at
  * uncertainty_contact_planning.hpp:1955-1960 and simple_robot_models.hpp:412,2195), for the honest CPU baseline */
 int32_t oracle_pair_distances_reference_style(const upc_robot_desc* robot, int64_t n, const double* configs, double* matrix);

@@ -196,6 +196,41 @@ def test_cluster_statistics_match_oracle(oracle, simulators):
                     assert got["counts"][1] == 0
 
 
+def test_nearest_neighbors_match_oracle(oracle, simulators):
+    """next row 8f-3: GetNearestNeighbor for a batch of samples - indices equal (ties to the smallest index, disabled and
+    NaN-weighted states never selected), distances 0 ulp"""
+    from uncertainty_planning_core_b200 import B200Simulator
+    rng = np.random.default_rng(17)
+    for case in (cases.cl_se2_random, cases.cl_se2_wrap, cases.cl_se3_random, cases.cl_linked_random_mixed):
+        c = case()
+        sim = simulators("nn_" + case.__name__, c["env"], c["robot"])
+        states = np.concatenate([c["configs"], c["configs"][:20]], axis=0)      # 20 duplicated states: exact ties
+        ns = states.shape[0]
+        pf = rng.uniform(0.0, 1.0, ns)
+        siv = rng.uniform(0.0, 0.5, size=(ns, abi.variance_width(c["robot"].kind, c["robot"].dof)))
+        fw, vw = B200Simulator.StateDistanceWeights(pf, siv, 0.75, 0.75)
+        fw[-20:], vw[-20:] = fw[:20], vw[:20]
+        use = rng.random(ns) < 0.8
+        queries = states[rng.integers(ns, size=64)] + 0.01 * rng.normal(size=(64, states.shape[1])) * (c["robot"].kind != abi.ROBOT_SE3)
+        queries[:8] = states[:8]                                                  # distance 0 to two states each
+        for mask in (None, use):
+            gi, gd = sim.NearestNeighbors(states, fw, vw, queries, 0.25, mask)
+            wi, wd = oracle.nearest_neighbors(c["robot"], states, fw, vw, queries, 0.25, mask)
+            assert np.array_equal(gi, wi)
+            assert max_ulp_diff(gd, wd) == 0
+            assert gi.min() >= 0 and (mask is None or mask[gi].all())
+        assert np.array_equal(sim.NearestNeighbors(states, fw, vw, queries[:8], 0.25)[0], np.arange(8))   # ties keep the smallest index
+        bad = fw.copy()
+        bad[::2] = np.nan
+        gi, gd = sim.NearestNeighbors(states, bad, vw, queries, 0.25)
+        wi, wd = oracle.nearest_neighbors(c["robot"], states, bad, vw, queries, 0.25)
+        assert np.array_equal(gi, wi) and (gi % 2 == 1).all() and max_ulp_diff(gd, wd) == 0
+        gi, gd = sim.NearestNeighbors(states, fw, vw, queries, 0.25, np.zeros(ns, dtype=bool))
+        assert (gi == -1).all() and np.isinf(gd).all()
+        gi, gd = sim.NearestNeighbors(states[:0], fw[:0], vw[:0], queries, 0.25)
+        assert (gi == -1).all() and np.isinf(gd).all()
+
+
 def test_count_within_and_reverse_edge_probability(oracle, simulators):
     """next row 8f-2: counts are bit-exact against the oracle's distances (<= threshold, uncertainty_contact_planning.hpp:2083)"""
     for make in (cases.se2_contact, cases.se3_contact, cases.linked_contact):

@@ -222,3 +222,24 @@ def test_cluster_statistics_properties(oracle):
         R = s3["expectations"][k][:9].reshape(3, 3)
         assert np.allclose(R @ R.T, np.eye(3), atol=1e-12) and np.linalg.det(R) > 0.999
         assert np.allclose(s3["expectations"][k][9:], c3["configs"][l3 == k][:, 9:].mean(axis=0), atol=1e-12)
+
+
+def test_nearest_neighbors_against_numpy(oracle):
+    """StateDistance / GetNearestNeighbor (uncertainty_contact_planning.hpp:1488-1542) restated in numpy for SE(2)"""
+    c = cases.cl_se2_random()
+    rng = np.random.default_rng(5)
+    states = c["configs"]
+    ns = len(states)
+    fw, vw = rng.uniform(0.3, 1.0, ns), rng.uniform(0.3, 1.0, ns)
+    use = rng.random(ns) < 0.7
+    queries = np.stack([rng.uniform(1.0, 1.6, 40), rng.uniform(1.0, 1.5, 40), rng.uniform(-3.0, 3.0, 40)], axis=1)
+    idx, dist = oracle.nearest_neighbors(c["robot"], states, fw, vw, queries, 0.125, use)
+    for q in range(40):
+        d = states - queries[q]
+        ang = np.abs((d[:, 2] + np.pi) % (2 * np.pi) - np.pi)
+        ed = (np.hypot(d[:, 0], d[:, 1]) + ang) / 0.125
+        full = np.where(use, fw * ed * vw, np.inf)
+        assert idx[q] == int(np.argmin(full))
+        assert np.isclose(dist[q], full[idx[q]], rtol=1e-12)
+    none, dn = oracle.nearest_neighbors(c["robot"], states, fw, vw, queries, 0.125, np.zeros(ns, dtype=bool))
+    assert (none == -1).all() and np.isinf(dn).all()

@@ -277,12 +277,13 @@ def load_library():
     lib.upc_cluster_particles_device.argtypes = [vp, C.POINTER(ClusterParams), i64, i64, vp, vp, vp, vp]
     lib.upc_fill_noise_tape.argtypes = [C.c_uint64, C.POINTER(RobotDesc), C.POINTER(SimParams), i64, i64, i64, vp]
     lib.upc_count_within.argtypes = [vp, i64, vp, i64, vp, dp, C.POINTER(i64), vp]
+    lib.upc_nearest_neighbors.argtypes = [vp, i64, vp, vp, vp, vp, i64, vp, dp, vp, vp]
     lib.upc_variance_width.argtypes = [i32, i32]
     lib.upc_variance_width.restype = i32
     lib.upc_cluster_statistics.argtypes = [vp, i64, vp, vp, vp, i32, dp, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.upc_measure_l2_gather_gbs.argtypes = [vp, i64, C.POINTER(dp)]
     lib.upc_measure_fp64_tflops.argtypes = [vp, C.POINTER(dp)]
-    for name in ("upc_cluster_statistics", "upc_count_within", "upc_measure_l2_gather_gbs", "upc_measure_fp64_tflops", "upc_create", "upc_destroy", "upc_set_robot", "upc_get_stats", "upc_reset_stats",
+    for name in ("upc_cluster_statistics", "upc_nearest_neighbors", "upc_count_within", "upc_measure_l2_gather_gbs", "upc_measure_fp64_tflops", "upc_create", "upc_destroy", "upc_set_robot", "upc_get_stats", "upc_reset_stats",
                  "upc_set_lanes_per_particle", "upc_host_alloc", "upc_host_free", "upc_synchronize",
                  "upc_forward_simulate", "upc_forward_simulate_device", "upc_check_config_collision",
                  "upc_cluster_particles", "upc_cluster_particles_device", "upc_fill_noise_tape"):
@@ -296,7 +297,7 @@ EXPORTED_SYMBOLS = (
     "upc_set_robot", "upc_get_stats", "upc_reset_stats", "upc_set_lanes_per_particle", "upc_host_alloc", "upc_host_free",
     "upc_forward_simulate", "upc_forward_simulate_device", "upc_check_config_collision", "upc_cluster_particles",
     "upc_cluster_particles_device", "upc_fill_noise_tape", "upc_synchronize", "upc_measure_l2_gather_gbs",
-    "upc_measure_fp64_tflops", "upc_count_within", "upc_variance_width", "upc_cluster_statistics",
+    "upc_measure_fp64_tflops", "upc_count_within", "upc_variance_width", "upc_cluster_statistics", "upc_nearest_neighbors",
 )
 
 

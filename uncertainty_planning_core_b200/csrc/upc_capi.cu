@@ -590,6 +590,61 @@ int32_t upc_cluster_statistics(upc_handle* h, int64_t n, const double* configs, 
     return UPC_OK;
 }
 
+int32_t upc_nearest_neighbors(upc_handle* h, int64_t n_states, const double* expectations, const double* feasibility_weight,
+                              const double* variance_weight, const uint8_t* use_for_nn, int64_t n_queries, const double* queries,
+                              double step_size, int64_t* out_index, double* out_distance)
+{
+    if (!h) return fail_arg("null handle");
+    if (!h->has_robot)
+    {
+        set_error("upc_set_robot has not been called");
+        return UPC_ERR_NO_ROBOT;
+    }
+    if (n_states < 0 || n_queries < 0) return fail_arg("negative size");
+    if (n_queries == 0) return UPC_OK;
+    if (n_queries > 2147483647) return fail_arg("at most 2^31-1 queries per call");
+    if (!queries || !out_index) return fail_arg("null buffer");
+    if (!(step_size > 0.0)) return fail_arg("step_size must be > 0");
+    if (n_states == 0)
+    {
+        for (int64_t q = 0; q < n_queries; q++)
+        {
+            out_index[q] = -1;
+            if (out_distance) out_distance[q] = INFINITY;
+        }
+        return UPC_OK;
+    }
+    if (!expectations || !feasibility_weight || !variance_weight) return fail_arg("null buffer");
+    UPC_CUDA_TRY(cudaSetDevice(h->device));
+    const size_t width = (size_t)upc_config_width(h->robot.kind, h->robot.dof);
+    const size_t ns = (size_t)n_states, nq = (size_t)n_queries;
+    /* st_starts: expectations | fw | vw ; st_targets: queries ; st_coll: use ; st_out: index | distance */
+    UPC_CUDA_TRY(h->st_starts.reserve((width + 2) * ns * sizeof(double)));
+    UPC_CUDA_TRY(h->st_targets.reserve(width * nq * sizeof(double)));
+    UPC_CUDA_TRY(h->st_coll.reserve(ns + 64));
+    UPC_CUDA_TRY(h->st_out.reserve(nq * 16));
+    double* d_exp = (double*)h->st_starts.ptr;
+    double* d_fw = d_exp + width * ns;
+    double* d_vw = d_fw + ns;
+    UPC_CUDA_TRY(cudaMemcpyAsync(d_exp, expectations, width * ns * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(d_fw, feasibility_weight, ns * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(d_vw, variance_weight, ns * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(h->st_targets.ptr, queries, width * nq * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (use_for_nn) UPC_CUDA_TRY(cudaMemcpyAsync(h->st_coll.ptr, use_for_nn, ns, cudaMemcpyHostToDevice, h->stream));
+    h->stats.h2d_bytes += (int64_t)((width + 2) * ns * 8 + width * nq * 8 + (use_for_nn ? ns : 0));
+    long long* d_index = (long long*)h->st_out.ptr;
+    double* d_dist = (double*)((uint8_t*)h->st_out.ptr + nq * 8);
+    UPC_CUDA_TRY(launch_nearest_states(h, n_states, d_exp, d_fw, d_vw, use_for_nn ? (const uint8_t*)h->st_coll.ptr : nullptr, n_queries,
+                                       (const double*)h->st_targets.ptr, step_size, d_index, d_dist, h->stream));
+    h->stats.kernel_launches++;
+    static_assert(sizeof(long long) == sizeof(int64_t), "index width");
+    UPC_CUDA_TRY(cudaMemcpyAsync(out_index, d_index, nq * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (out_distance) UPC_CUDA_TRY(cudaMemcpyAsync(out_distance, d_dist, nq * 8, cudaMemcpyDeviceToHost, h->stream));
+    UPC_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->stats.d2h_bytes += (int64_t)(nq * (out_distance ? 16 : 8));
+    return UPC_OK;
+}
+
 int32_t upc_count_within(upc_handle* h, int64_t n, const double* configs, int64_t n_targets, const double* targets, double threshold,
                          int64_t* out_count, uint8_t* within)
 {

@@ -77,6 +77,9 @@ int choose_lanes(const upc_handle* h, int64_t n);
 cudaError_t launch_forward_simulate(upc_handle* h, const DevSim& sp, int64_t n, const double* starts, int64_t n_targets,
                                     const double* targets, const double* tape, double* out_configs, uint8_t* out_collided,
                                     cudaStream_t stream);
+cudaError_t launch_nearest_states(upc_handle* h, int64_t n_states, const double* d_expectations, const double* d_fw, const double* d_vw,
+                                  const uint8_t* d_use, int64_t n_queries, const double* d_queries, double step_size, long long* d_index,
+                                  double* d_distance, cudaStream_t stream);
 cudaError_t launch_count_within(upc_handle* h, int64_t n, const double* d_configs, int64_t n_targets, const double* d_targets, double threshold,
                                 unsigned long long* d_count, uint8_t* d_within, cudaStream_t stream);
 cudaError_t launch_check_collision(upc_handle* h, const double* d_config, double threshold, int* d_out, cudaStream_t stream);

@@ -234,6 +234,99 @@ cudaError_t launch_count_within(upc_handle* h, int64_t n, const double* d_config
     return cudaGetLastError();
 }
 
+/* ------------------------------------------------------------------ nearest tree state */
+
+struct NearestArgs
+{
+    DevRobot robot;
+    int64_t n_states, n_queries;
+    const double* expectations; /* [C][n_states] */
+    const double* fw;
+    const double* vw;
+    const uint8_t* use;
+    const double* queries;      /* [C][n_queries] */
+    double step_size;
+    long long* out_index;
+    double* out_distance;
+};
+
+/* uncertainty_contact_planning.hpp:1488-1542: one CTA per query, threads stride over the states in ascending order
+ * (strict < keeps the first = smallest index per thread), then a lexicographic (distance, index) minimum over the CTA */
+template <class M>
+__global__ void __launch_bounds__(256) nearest_state_kernel(const __grid_constant__ NearestArgs a)
+{
+    __shared__ double s_d[8];
+    __shared__ long long s_i[8];
+    const int64_t q = blockIdx.x;
+    const int width = (M::HAS_FRAMES) ? a.robot.dof : M::WIDTH;
+    double qc[M::WIDTH];
+    for (int k = 0; k < width; k++) qc[k] = a.queries[(int64_t)k * a.n_queries + q];
+    double best = INFINITY;
+    long long best_i = -1;
+    for (int64_t i = threadIdx.x; i < a.n_states; i += blockDim.x)
+    {
+        if (a.use != nullptr && a.use[i] == 0) continue;
+        double e[M::WIDTH];
+        for (int k = 0; k < width; k++) e[k] = a.expectations[(int64_t)k * a.n_states + i];
+        const double ed = M::distance(a.robot, e, qc) / a.step_size;
+        const double d = (a.fw[i] * ed) * a.vw[i];
+        if (d < best)
+        {
+            best = d;
+            best_i = i;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+    {
+        const double od = __shfl_xor_sync(0xffffffffu, best, off);
+        const long long oi = __shfl_xor_sync(0xffffffffu, best_i, off);
+        if (oi >= 0 && (best_i < 0 || od < best || (od == best && oi < best_i)))
+        {
+            best = od;
+            best_i = oi;
+        }
+    }
+    if ((threadIdx.x & 31) == 0)
+    {
+        s_d[threadIdx.x >> 5] = best;
+        s_i[threadIdx.x >> 5] = best_i;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++)
+        {
+            const double od = s_d[w];
+            const long long oi = s_i[w];
+            if (oi >= 0 && (best_i < 0 || od < best || (od == best && oi < best_i)))
+            {
+                best = od;
+                best_i = oi;
+            }
+        }
+        a.out_index[q] = best_i;
+        if (a.out_distance) a.out_distance[q] = (best_i < 0) ? INFINITY : best;
+    }
+}
+
+cudaError_t launch_nearest_states(upc_handle* h, int64_t n_states, const double* d_expectations, const double* d_fw, const double* d_vw,
+                                  const uint8_t* d_use, int64_t n_queries, const double* d_queries, double step_size, long long* d_index,
+                                  double* d_distance, cudaStream_t stream)
+{
+    NearestArgs a;
+    a.robot = h->robot; a.n_states = n_states; a.n_queries = n_queries; a.expectations = d_expectations; a.fw = d_fw; a.vw = d_vw; a.use = d_use;
+    a.queries = d_queries; a.step_size = step_size; a.out_index = d_index; a.out_distance = d_distance;
+    const unsigned blocks = (unsigned)n_queries;
+    switch (h->robot.kind)
+    {
+        case UPC_ROBOT_SE2: nearest_state_kernel<Se2Model><<<blocks, 256, 0, stream>>>(a); break;
+        case UPC_ROBOT_SE3: nearest_state_kernel<Se3Model><<<blocks, 256, 0, stream>>>(a); break;
+        default: nearest_state_kernel<LinkedModel><<<blocks, 256, 0, stream>>>(a); break;
+    }
+    return cudaGetLastError();
+}
+
 /* ------------------------------------------------------------------ CheckConfigCollision (single configuration) */
 
 struct CheckArgs

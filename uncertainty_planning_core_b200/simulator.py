@@ -110,6 +110,39 @@ class B200Simulator:
                                              C.byref(count), flags.ctypes.data))
         return int(count.value), flags.astype(bool)
 
+    @staticmethod
+    def StateDistanceWeights(motion_pfeasibility, space_independent_variances, feasibility_alpha, variance_alpha):
+        """The two per-state factors of StateDistance (uncertainty_contact_planning.hpp:1492-1499):
+        feasibility_weight = (1 - Pfeasibility) * alpha + (1 - alpha); variance_weight = erf(|variances|_1) * alpha_v + (1 - alpha_v)."""
+        import math
+        pf = np.asarray(motion_pfeasibility, dtype=np.float64)
+        var = np.abs(np.asarray(space_independent_variances, dtype=np.float64)).reshape(pf.shape[0], -1)
+        raw = np.zeros(pf.shape[0])
+        for k in range(var.shape[1]):
+            raw = raw + var[:, k]
+        fw = (1.0 - pf) * feasibility_alpha + (1.0 - feasibility_alpha)
+        vw = np.array([math.erf(v) for v in raw]) * variance_alpha + (1.0 - variance_alpha)
+        return fw, vw
+
+    def NearestNeighbors(self, expectations, feasibility_weight, variance_weight, queries, step_size, use_for_nn=None):
+        """GetNearestNeighbor (uncertainty_contact_planning.hpp:1506-1542) for a batch of sampled configurations:
+        returns (index [Q] int64, -1 when no state is enabled; distance [Q])."""
+        exp = np.asarray(expectations, dtype=np.float64).reshape(-1, self.robot.width)
+        qs = np.asarray(queries, dtype=np.float64).reshape(-1, self.robot.width)
+        ns, nq = exp.shape[0], qs.shape[0]
+        fw = np.ascontiguousarray(feasibility_weight, dtype=np.float64)
+        vw = np.ascontiguousarray(variance_weight, dtype=np.float64)
+        if fw.shape != (ns,) or vw.shape != (ns,):
+            raise ValueError("one feasibility and one variance weight per state")
+        use = None if use_for_nn is None else np.ascontiguousarray(np.asarray(use_for_nn).astype(np.uint8))
+        esoa, qsoa = np.ascontiguousarray(exp.T), np.ascontiguousarray(qs.T)
+        idx = np.zeros(nq, dtype=np.int64)
+        dist = np.zeros(nq, dtype=np.float64)
+        abi.check(self._lib.upc_nearest_neighbors(self._h, ns, esoa.ctypes.data, fw.ctypes.data, vw.ctypes.data,
+                                                  None if use is None else use.ctypes.data, nq, qsoa.ctypes.data, float(step_size),
+                                                  idx.ctypes.data, dist.ctypes.data))
+        return idx, dist
+
     def ComputeReverseEdgeProbability(self, child_particles, parent_expectation, noise_tape, params, goal_distance_threshold):
         """(attempts, reached): simulate the child's particles back towards the parent with contacts allowed and count those
         that end within goal_distance_threshold of it (uncertainty_contact_planning.hpp:2073-2090)."""
