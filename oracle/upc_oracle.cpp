@@ -452,9 +452,14 @@ public:
     Pid controllers_[3];
     Actuator actuators_[3];
     std::shared_ptr<PointSet> points_;
+    bool sensor_noise_free_;
+    bool SensorNoiseFree() const { return sensor_noise_free_; }
 
     explicit Se2Robot(const upc_robot_desc& d) : points_(MakePointSet(d))
     {
+        sensor_noise_free_ = true;
+        for (int i = 0; i < 3; i++)
+            if (d.axis[i].max_sensor_noise != 0.0) sensor_noise_free_ = false;
         for (int i = 0; i < 3; i++)
         {
             controllers_[i].Initialize(d.axis[i].kp, d.axis[i].ki, d.axis[i].kd, d.axis[i].integral_clamp);
@@ -558,6 +563,7 @@ public:
         config_ = Identity34();
     }
     int Dof() const { return 6; }
+    bool SensorNoiseFree() const { return sensor_noise_free_; }
     int NumLinks() const { return 1; }
     const Mat34& LinkTransform(int) const { return config_; }
     const PointSet& Points() const { return *points_; }
@@ -661,6 +667,9 @@ public:
     explicit LinkedRobot(const upc_robot_desc& d) : points_(MakePointSet(d))
     {
         dof_ = d.dof;
+        sensor_noise_free_ = true;
+        for (int i = 0; i < d.dof; i++)
+            if (d.axis[i].max_sensor_noise != 0.0) sensor_noise_free_ = false;
         width_ = d.dof;
         base_ = FromRowMajor34(d.base_transform);
         link_transforms_.assign((size_t)d.num_links, Identity34());
@@ -700,6 +709,8 @@ public:
         UpdateTransforms();
     }
     int Dof() const { return dof_; }
+    bool sensor_noise_free_;
+    bool SensorNoiseFree() const { return sensor_noise_free_; }
     int NumLinks() const { return (int)link_transforms_.size(); }
     const Mat34& LinkTransform(int l) const { return link_transforms_[(size_t)l]; }
     const PointSet& Points() const { return *points_; }
@@ -1028,7 +1039,8 @@ static bool SimulateParticle(const Environment& env, Robot& robot, const upc_sim
     {
         stats.particle_steps++;
         double draws[UPC_MAX_DOF];
-        for (int d = 0; d < dof; d++) draws[d] = tape[(((int64_t)step * slots + 0) * dof + d) * tape_stride];
+        /* with every sensor noise bound zero the sensor slot of the tape holds exact zeros by construction and is not read */
+        for (int d = 0; d < dof; d++) draws[d] = robot.SensorNoiseFree() ? 0.0 : tape[(((int64_t)step * slots + 0) * dof + d) * tape_stride];
         double u[UPC_MAX_DOF];
         robot.GenerateControlAction(target, sp.controller_interval, draws, u);
         double real[UPC_MAX_DOF];

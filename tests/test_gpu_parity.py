@@ -124,6 +124,26 @@ def test_plain_grid_path_matches_oracle_too(oracle):
         del os.environ["UPC_B200_NO_CORNER_CELLS"]
 
 
+def test_sensor_slot_is_not_read_for_noise_free_sensors(oracle):
+    """with every max_sensor_noise zero the sensor slot of the tape (exact zeros by construction) is neither
+    uploaded nor read - poisoning it changes nothing, on the oracle and on the GPU (host-pointer path, sliced upload)"""
+    from uncertainty_planning_core_b200 import B200Simulator, scenarios
+    for sc in (scenarios.c2_se3(seed=5, n=4096, num_steps=32, shape=(64, 64, 64), resolution=0.0625), cases.se2_contact(), cases.linked_contact()):
+        assert all(sc["robot"].desc.axis[a].max_sensor_noise == 0.0 for a in range(sc["robot"].dof))
+        n = sc["starts"].shape[0]
+        tape = abi.fill_noise_tape(3, sc["robot"], sc["params"], n)
+        assert not tape[:, 0].any()
+        poisoned = tape.copy()
+        poisoned[:, 0] = np.nan
+        ocfg, ocoll, _ = oracle.forward_simulate(sc["env"], sc["robot"], sc["params"], sc["starts"], sc["targets"], tape)
+        pcfg, pcoll, _ = oracle.forward_simulate(sc["env"], sc["robot"], sc["params"], sc["starts"], sc["targets"], poisoned)
+        assert np.array_equal(ocfg, pcfg) and np.array_equal(ocoll, pcoll)
+        sim = B200Simulator(sc["env"], sc["robot"])
+        cfg, coll = sim.ForwardSimulateRobots(sc["starts"], sc["targets"], poisoned, sc["params"])
+        assert np.array_equal(coll, ocoll) and max_ulp_diff(cfg, ocfg) <= CONFIG_ULP_TOLERANCE
+        sim.close()
+
+
 def test_single_precision_pre_cull_changes_nothing(oracle):
     """the float pre-cull of the collision check is a shortcut only - results with it (default, used when
     a lane holds >= 8 points of a link) and without it are the oracle's, bit for bit; the C2-shaped case has 128 points"""

@@ -232,7 +232,7 @@ int32_t upc_destroy(upc_handle* h)
     if (h->copy_stream)
     {
         cudaStreamDestroy(h->copy_stream);
-        for (int c = 0; c < 4; c++) cudaEventDestroy(h->copy_done[c]);
+        for (int c = 0; c < 8; c++) cudaEventDestroy(h->copy_done[c]);
         cudaEventDestroy(h->compute_done);
     }
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -460,17 +460,38 @@ int32_t upc_forward_simulate(upc_handle* h, const upc_sim_params* params, int64_
     UPC_CUDA_TRY(h->st_coll.reserve((size_t)n));
     UPC_CUDA_TRY(cudaMemcpyAsync(h->st_starts.ptr, starts, cfg_bytes, cudaMemcpyHostToDevice, h->stream));
     UPC_CUDA_TRY(cudaMemcpyAsync(h->st_targets.ptr, targets, tgt_bytes, cudaMemcpyHostToDevice, h->stream));
-    h->stats.h2d_bytes += (int64_t)(cfg_bytes + tgt_bytes + tape_bytes);
+    h->stats.h2d_bytes += (int64_t)(cfg_bytes + tgt_bytes);
     DevSim sp;
     {
         const int32_t prc = to_dev_sim(params, &sp);
         if (prc != UPC_OK) return prc;
     }
-    /* The tape dominates the upload (C2: 61 MB of 63 MB).  It is step-major, so the edge is simulated as up to four
-     * launches over consecutive step ranges while the next slices are still in flight on a second stream. */
+    /* The tape dominates the upload (C2: 61 MB of 63 MB).  It is step-major, so the edge is simulated as several
+     * launches over consecutive step ranges while the next slices are still in flight on a second stream.  Only the
+     * first slice's upload is exposed, so the slices start small: 1/32, 1/32, 1/16, 1/8, 1/4, 1/2 of the steps (doubling
+     * keeps up as long as uploading a step takes at most half the time of simulating it; a slower link only delays the
+     * later launches).  When every sensor noise bound is zero the kernels do not read the sensor slot and it
+     * is not uploaded either: a pitched copy moves the actuator slots only - half of the tape for max_microsteps = 1. */
     int chunks = 1;
-    if (tape_bytes >= ((size_t)8 << 20) && params->num_steps >= 8) chunks = 4;
+    int bounds[8] = {0, params->num_steps, 0, 0, 0, 0, 0, 0};
+    if (tape_bytes >= ((size_t)8 << 20) && params->num_steps >= 8)
+    {
+        int len = params->num_steps / 32;
+        if (len < 1) len = 1;
+        int at = len;
+        chunks = 1;
+        bounds[1] = at;
+        while (at < params->num_steps && chunks < 6)
+        {
+            at = (params->num_steps - (at + len) < len) ? params->num_steps : at + len; /* a short tail joins the last slice */
+            bounds[++chunks] = at;
+            if (chunks >= 2) len *= 2;
+        }
+        bounds[chunks] = params->num_steps;
+    }
     const size_t step_bytes = tape_bytes / (size_t)params->num_steps;
+    const size_t slot_bytes = (size_t)h->robot.dof * (size_t)n * sizeof(double);
+    const bool skip_sensor_slot = (h->robot.sensor_noise_free != 0);
     if (chunks > 1)
     {
         UPC_CUDA_TRY(h->st_carry.reserve((size_t)2 * h->robot.dof * (size_t)n * sizeof(double) + (size_t)2 * n + 64));
@@ -479,7 +500,7 @@ int32_t upc_forward_simulate(upc_handle* h, const upc_sim_params* params, int64_
         if (!h->copy_stream)
         {
             UPC_CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-            for (int c = 0; c < 4; c++) UPC_CUDA_TRY(cudaEventCreateWithFlags(&h->copy_done[c], cudaEventDisableTiming));
+            for (int c = 0; c < 8; c++) UPC_CUDA_TRY(cudaEventCreateWithFlags(&h->copy_done[c], cudaEventDisableTiming));
             UPC_CUDA_TRY(cudaEventCreateWithFlags(&h->compute_done, cudaEventDisableTiming));
         }
         /* the previous call's kernels may still be reading the staging tape */
@@ -488,10 +509,20 @@ int32_t upc_forward_simulate(upc_handle* h, const upc_sim_params* params, int64_
     }
     for (int c = 0; c < chunks; c++)
     {
-        const int s0 = (int)(((int64_t)params->num_steps * c) / chunks), s1 = (int)(((int64_t)params->num_steps * (c + 1)) / chunks);
+        const int s0 = bounds[c], s1 = bounds[c + 1];
         const size_t off = (size_t)s0 * step_bytes, len = (size_t)(s1 - s0) * step_bytes;
         cudaStream_t cs = (chunks > 1) ? h->copy_stream : h->stream;
-        UPC_CUDA_TRY(cudaMemcpyAsync((uint8_t*)h->st_tape.ptr + off, (const uint8_t*)tape + off, len, cudaMemcpyHostToDevice, cs));
+        if (skip_sensor_slot)
+        {
+            UPC_CUDA_TRY(cudaMemcpy2DAsync((uint8_t*)h->st_tape.ptr + off + slot_bytes, step_bytes, (const uint8_t*)tape + off + slot_bytes, step_bytes,
+                                           step_bytes - slot_bytes, (size_t)(s1 - s0), cudaMemcpyHostToDevice, cs));
+            h->stats.h2d_bytes += (int64_t)((step_bytes - slot_bytes) * (size_t)(s1 - s0));
+        }
+        else
+        {
+            UPC_CUDA_TRY(cudaMemcpyAsync((uint8_t*)h->st_tape.ptr + off, (const uint8_t*)tape + off, len, cudaMemcpyHostToDevice, cs));
+            h->stats.h2d_bytes += (int64_t)len;
+        }
         if (chunks > 1)
         {
             UPC_CUDA_TRY(cudaEventRecord(h->copy_done[c], h->copy_stream));

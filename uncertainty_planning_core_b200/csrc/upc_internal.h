@@ -65,7 +65,7 @@ struct upc_handle
     /* staging for the host-pointer entry points */
     upc::DeviceBuffer st_starts, st_targets, st_tape, st_out, st_coll, st_labels, st_ncl, st_carry;
     cudaStream_t copy_stream = nullptr; /* tape slices of the host-pointer entry point */
-    cudaEvent_t copy_done[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t copy_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t compute_done = nullptr;
     upc::ClusterWorkspace cw;
 };

@@ -600,7 +600,7 @@ UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim&
             double draws[N];
 #pragma unroll
             for (int d = 0; d < N; d++)
-                if (d < dof) draws[d] = tape[(((int64_t)step * slots) * dof + d) * n + i];
+                if (d < dof) draws[d] = r.sensor_noise_free ? 0.0 : tape[(((int64_t)step * slots) * dof + d) * n + i]; /* zeros by construction: not read */
 #ifdef UPC_PHASE_TIMING
             if (draws[0] == 123.456) cnt.particle_steps++; /* force the loads to complete inside this phase */
 #endif
