@@ -53,9 +53,14 @@ def test_forward_simulation_matches_oracle_for_every_lane_count(oracle, simulato
     sim.SetLanesPerParticle(0)
 
 
+@pytest.mark.parametrize("pivot_pass", [True, False])
 @pytest.mark.parametrize("name", sorted(cases.GOLDEN_CLUSTER_CASES))
-def test_clustering_matches_oracle(oracle, simulators, name):
+def test_clustering_matches_oracle(oracle, simulators, name, pivot_pass, monkeypatch):
+    """every golden clustering case through the default pipeline (pivot pass first) and with the pivot pass
+    forced off (adjacency / root-check / exact paths only)"""
     from uncertainty_planning_core_b200 import OutcomeClustering
+    if not pivot_pass:
+        monkeypatch.setenv("UPC_B200_NO_PIVOT_PASS", "1")
     c = cases.GOLDEN_CLUSTER_CASES[name]()
     n_sets = c.get("n_sets", 1)
     olabels, oncl, ostats = oracle.cluster_particles(c["env"], c["robot"], c["cparams"], c["configs"], n_sets)
@@ -70,6 +75,42 @@ def test_clustering_matches_oracle(oracle, simulators, name):
     labels, ncl = oc.ClusterIndices(c["configs"], n_sets)
     assert np.array_equal(ncl, oncl), name
     assert np.array_equal(labels, olabels), name
+
+
+def test_pivot_pass_boundaries(oracle, simulators):
+    """the pivot pass may only settle what the adjacency pass would settle identically - blobs whose radius sits just
+    inside / outside threshold/2, pivots just inside / outside 2*threshold, more clusters than pivots, several sets per call"""
+    from uncertainty_planning_core_b200 import OutcomeClustering
+    c = cases.cl_se2_blobs()
+    sim = simulators("cl_pivot", c["env"], c["robot"])
+    thr = 0.1
+    oc = OutcomeClustering(sim, abi.FEATURE_NONE, 0.125, thr)
+    cp = abi.ClusterParams()
+    cp.feature_type = abi.FEATURE_NONE
+    cp.distance_clustering_threshold = thr
+    rng = np.random.default_rng(23)
+
+    def ring(centre, radius, m):
+        ang = rng.uniform(0, 2 * np.pi, m)
+        return np.stack([centre[0] + radius * np.cos(ang), centre[1] + radius * np.sin(ang), np.zeros(m)], axis=1)
+
+    sets = []
+    for radius in (0.049, 0.0499995, 0.0500005, 0.051, 0.08):                 # points on a circle around the pivot (first particle)
+        sets.append(np.concatenate([[[1.0, 1.0, 0.0]], ring((1.0, 1.0), radius, 199)], axis=0))
+    for gap in (0.19, 0.1999995, 0.2000005, 0.21, 0.3):                       # two tight blobs whose pivots are `gap` apart
+        a = np.concatenate([[[1.0, 1.0, 0.0]], ring((1.0, 1.0), 0.01, 99)], axis=0)
+        b = np.concatenate([[[1.0 + gap, 1.0, 0.0]], ring((1.0 + gap, 1.0), 0.01, 99)], axis=0)
+        sets.append(np.concatenate([a, b], axis=0))
+    many = np.stack([1.0 + 0.5 * np.arange(200), np.full(200, 1.0), np.zeros(200)], axis=1)   # 200 singleton clusters > 64 pivots
+    sets.append(many)
+    for cfg in sets:
+        labels, ncl = oc.ClusterIndices(cfg)
+        olabels, oncl, _ = oracle.cluster_particles(c["env"], c["robot"], cp, cfg)
+        assert np.array_equal(ncl, oncl) and np.array_equal(labels, olabels)
+    batch = np.concatenate(sets, axis=0)
+    labels, ncl = oc.ClusterIndices(batch, n_sets=len(sets))
+    olabels, oncl, _ = oracle.cluster_particles(c["env"], c["robot"], cp, batch, len(sets))
+    assert np.array_equal(ncl, oncl) and np.array_equal(labels, olabels)
 
 
 def test_cluster_particles_assembly_and_edge_cases(oracle, simulators):

@@ -753,6 +753,111 @@ __global__ void __launch_bounds__(1024) label_kernel(const int32_t* __restrict__
     if (threadIdx.x == 0) n_clusters[blockIdx.x] = s_running;
 }
 
+/* ------------------------------------------------------------------ pivot pass: blob-shaped outcomes in O(n * clusters) */
+
+struct PivotArgs
+{
+    DevRobot robot;
+    const double* feat; /* [F][total] */
+    int nfeat;
+    int64_t total, set_size;
+    const int32_t* group; /* optional first-pass roots (in-set indices) */
+    double radius;        /* threshold / 2 - margin */
+    double separation;    /* 2 * threshold + margin */
+    int32_t* root;        /* out: in-set index of the pivot = smallest member of the particle's cluster */
+    uint8_t* ok;          /* out, per set: 1 = the partition written to root is the complete-link result */
+};
+
+constexpr int kMaxPivots = 64;
+
+/*
+ * One CTA per set.  Repeat: the smallest unassigned particle becomes a pivot and takes every unassigned particle of its
+ * first-pass group whose distance to it is <= threshold/2 - margin.  The configuration distances are metrics, so all
+ * pairs inside such a group are within the threshold (a clique); if, in addition, pivots of the same first-pass group
+ * are further than 2 * threshold + margin apart, no pair across groups is, the threshold graph is exactly the disjoint
+ * union of these cliques and complete link returns them.  The margin (1e-6) covers the rounding of the
+ * evaluated distances (<= 2e-8: the arccosine of the SE(3) rotation part near zero angle).  Anything else - more than
+ * kMaxPivots groups, pivots too close - reports ok = 0 and the adjacency pass decides.
+ */
+template <int KIND>
+__global__ void __launch_bounds__(1024) pivot_pass_kernel(const __grid_constant__ PivotArgs a)
+{
+    constexpr int MAXF = PairDistance<KIND>::MAXF;
+    __shared__ int s_warp_min[32];
+    __shared__ int s_next;
+    __shared__ int s_pivots[kMaxPivots];
+    __shared__ int s_fail;
+    const int64_t base = (int64_t)blockIdx.x * a.set_size;
+    const int n = (int)a.set_size;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) a.root[base + i] = -1;
+    if (threadIdx.x == 0)
+    {
+        s_next = (n > 0) ? 0 : 0x7fffffff;
+        s_fail = 0;
+    }
+    __syncthreads();
+    int npiv = 0;
+    for (int k = 0; k < kMaxPivots; k++)
+    {
+        const int pivot = s_next;
+        if (pivot == 0x7fffffff) break;
+        double fp[MAXF];
+#pragma unroll
+        for (int f = 0; f < MAXF; f++) fp[f] = (f < a.nfeat) ? a.feat[(int64_t)f * a.total + base + pivot] : 0.0;
+        const int gp = a.group ? a.group[base + pivot] : 0;
+        int local_min = 0x7fffffff;
+        for (int i = threadIdx.x; i < n; i += blockDim.x)
+        {
+            if (a.root[base + i] >= 0) continue;
+            bool take = (i == pivot);
+            if (!take && (!a.group || a.group[base + i] == gp))
+            {
+                double fi[MAXF];
+#pragma unroll
+                for (int f = 0; f < MAXF; f++) fi[f] = (f < a.nfeat) ? a.feat[(int64_t)f * a.total + base + i] : 0.0;
+                take = PairDistance<KIND>::eval(a.robot, fp, fi) <= a.radius; /* pivot < i always: smaller index first */
+            }
+            if (take) a.root[base + i] = pivot;
+            else local_min = min(local_min, i);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) local_min = min(local_min, __shfl_xor_sync(0xffffffffu, local_min, off));
+        __syncthreads(); /* everybody has read s_next */
+        if (lane == 0) s_warp_min[warp] = local_min;
+        if (threadIdx.x == 0) s_pivots[k] = pivot;
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            int m = 0x7fffffff;
+            for (int w = 0; w < (int)(blockDim.x >> 5); w++) m = min(m, s_warp_min[w]);
+            s_next = m;
+        }
+        npiv = k + 1;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && s_next != 0x7fffffff) s_fail = 1; /* more clusters than pivots */
+    __syncthreads();
+    /* pivots of the same first-pass group must be clearly separated */
+    for (int pair = threadIdx.x; pair < npiv * npiv; pair += blockDim.x)
+    {
+        const int ia = pair / npiv, ib = pair % npiv;
+        if (ia >= ib) continue;
+        const int pa = s_pivots[ia], pb = s_pivots[ib];
+        if (a.group && a.group[base + pa] != a.group[base + pb]) continue;
+        double fa[MAXF], fb[MAXF];
+#pragma unroll
+        for (int f = 0; f < MAXF; f++)
+        {
+            fa[f] = (f < a.nfeat) ? a.feat[(int64_t)f * a.total + base + pa] : 0.0;
+            fb[f] = (f < a.nfeat) ? a.feat[(int64_t)f * a.total + base + pb] : 0.0;
+        }
+        if (!(PairDistance<KIND>::eval(a.robot, fa, fb) > a.separation)) s_fail = 1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) a.ok[blockIdx.x] = s_fail ? 0 : 1;
+}
+
 /* ------------------------------------------------------------------ exact complete link for sets that are not unions of cliques */
 
 /*
@@ -1759,10 +1864,42 @@ int32_t run_cluster(upc_handle* h, const upc_cluster_params& cp, int64_t n_sets,
     in.nfeat = nfeat;
     in.group = group;
     in.threshold = cp.distance_clustering_threshold;
-    int64_t fallback = 0;
-    const int32_t rc = cluster_pass(h, in, n_sets, set_size, root2, stream, &fallback);
-    if (rc != UPC_OK) return rc;
-    h->stats.cluster_fallback_calls += fallback;
+    /* blob-shaped outcomes (the common case after a contact edge): the pivot pass settles the distance clustering in
+     * O(n * clusters); UPC_B200_NO_PIVOT_PASS=1 forces the adjacency pass (tests exercise both) */
+    bool settled = false;
+    {
+        const char* off = getenv("UPC_B200_NO_PIVOT_PASS");
+        if (!(off && off[0] == '1') && set_size >= 2 && set_size < ((int64_t)1 << 31) && cp.distance_clustering_threshold > 1.0e-5)
+        {
+            uint8_t* ok = buf<uint8_t>(h->cw.link_scratch, (size_t)n_sets);
+            UPC_NULLCHECK(ok);
+            PivotArgs pa;
+            pa.robot = h->robot; pa.feat = feat; pa.nfeat = nfeat; pa.total = total; pa.set_size = set_size; pa.group = group;
+            pa.radius = 0.5 * cp.distance_clustering_threshold - 1.0e-6;
+            pa.separation = 2.0 * cp.distance_clustering_threshold + 1.0e-6;
+            pa.root = root2; pa.ok = ok;
+            const int threads = (set_size >= 1024) ? 1024 : ((set_size >= 256) ? 256 : 64);
+            if (kind == UPC_ROBOT_SE2) pivot_pass_kernel<UPC_ROBOT_SE2><<<(unsigned)n_sets, threads, 0, stream>>>(pa);
+            else if (kind == UPC_ROBOT_SE3) pivot_pass_kernel<UPC_ROBOT_SE3><<<(unsigned)n_sets, threads, 0, stream>>>(pa);
+            else pivot_pass_kernel<UPC_ROBOT_LINKED><<<(unsigned)n_sets, threads, 0, stream>>>(pa);
+            h->stats.kernel_launches++;
+            UPC_CUDA_TRY(cudaGetLastError());
+            std::vector<uint8_t> flags((size_t)n_sets);
+            UPC_CUDA_TRY(cudaMemcpyAsync(flags.data(), ok, (size_t)n_sets, cudaMemcpyDeviceToHost, stream));
+            UPC_CUDA_TRY(cudaStreamSynchronize(stream));
+            h->stats.d2h_bytes += n_sets;
+            settled = true;
+            for (uint8_t f : flags)
+                if (!f) settled = false;
+        }
+    }
+    if (!settled)
+    {
+        int64_t fallback = 0;
+        const int32_t rc = cluster_pass(h, in, n_sets, set_size, root2, stream, &fallback);
+        if (rc != UPC_OK) return rc;
+        h->stats.cluster_fallback_calls += fallback;
+    }
     label_kernel<<<(unsigned)n_sets, 1024, 0, stream>>>(root2, set_size, rank, d_labels, d_n_clusters);
     h->stats.kernel_launches++;
     UPC_CUDA_TRY(cudaGetLastError());
