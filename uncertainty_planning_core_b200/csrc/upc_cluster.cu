@@ -358,7 +358,20 @@ __global__ void dedupe_resolve_kernel(const __grid_constant__ DedupeArgs a)
     int r = reps[slot];
     /* equal hashes are only a hint: the vectors themselves decide */
     bool same = true;
-    for (int k = 0; k < a.num_points && same; k++) same = a.sig[(int64_t)k * a.total + base + i] == a.sig[(int64_t)k * a.total + base + r];
+    int k = 0;
+    for (; k + 8 <= a.num_points && same; k += 8) /* eight independent load pairs in flight per trip */
+    {
+        uint32_t x[8], y[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+        {
+            x[q] = a.sig[(int64_t)(k + q) * a.total + base + i];
+            y[q] = a.sig[(int64_t)(k + q) * a.total + base + r];
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) same = same && (x[q] == y[q]);
+    }
+    for (; k < a.num_points && same; k++) same = a.sig[(int64_t)k * a.total + base + i] == a.sig[(int64_t)k * a.total + base + r];
     if (!same) r = i;
     a.urep[p] = r;
     if (r == i)
