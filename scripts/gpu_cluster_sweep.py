@@ -25,6 +25,11 @@ for kind, case, name in ((abi.ROBOT_SE2, cases.cl_se2_blobs, "SE2"), (abi.ROBOT_
         d_cfg = torch.from_numpy(np.ascontiguousarray(cfg.T)).to(dev)
         d_labels = torch.zeros(n, dtype=torch.int32, device=dev); d_ncl = torch.zeros(1, dtype=torch.int32, device=dev)
         for feat in ((abi.FEATURE_NONE, abi.FEATURE_CRS) if kind == abi.ROBOT_SE2 else (abi.FEATURE_NONE,)):
+          for path in ("pivot pass (default)", "adjacency pass (UPC_B200_NO_PIVOT_PASS=1)"):
+            if path.startswith("adjacency"):
+                os.environ["UPC_B200_NO_PIVOT_PASS"] = "1"
+            else:
+                os.environ.pop("UPC_B200_NO_PIVOT_PASS", None)
             cp = cases._cparams(feat, 0.125, 0.1)
             best = 1e9
             for rep in range(4):
@@ -35,7 +40,8 @@ for kind, case, name in ((abi.ROBOT_SE2, cases.cl_se2_blobs, "SE2"), (abi.ROBOT_
                 if rep: best = min(best, e0.elapsed_time(e1))
             ok = int(d_ncl.item()) == 8 and (n > 16384 or canonical_partition(d_labels.cpu().numpy()) == canonical_partition(owner))
             pairs = n * (n - 1) / 2
-            rec = dict(robot=name, n=n, feature="CRS+distance" if feat else "distance", ms=best, particles_per_s=n / best * 1e3, pair_distances_per_s=pairs / best * 1e3, clusters=int(d_ncl.item()), partition_ok=bool(ok))
+            rec = dict(robot=name, n=n, feature="CRS+distance" if feat else "distance", path=path, ms=best, particles_per_s=n / best * 1e3, pair_distances_per_s=pairs / best * 1e3, clusters=int(d_ncl.item()), partition_ok=bool(ok))
             out.append(rec); print(json.dumps(rec), flush=True)
     sim.close()
+os.environ.pop("UPC_B200_NO_PIVOT_PASS", None)
 json.dump(out, open("gpurun_out/cluster_sweep.json", "w"), indent=1)

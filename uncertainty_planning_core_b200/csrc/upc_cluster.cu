@@ -810,7 +810,6 @@ __global__ void __launch_bounds__(1024) pivot_pass_kernel(const __grid_constant_
         s_fail = 0;
     }
     __syncthreads();
-    int npiv = 0;
     for (int k = 0; k < kMaxPivots; k++)
     {
         const int pivot = s_next;
@@ -819,6 +818,20 @@ __global__ void __launch_bounds__(1024) pivot_pass_kernel(const __grid_constant_
 #pragma unroll
         for (int f = 0; f < MAXF; f++) fp[f] = (f < a.nfeat) ? a.feat[(int64_t)f * a.total + base + pivot] : 0.0;
         const int gp = a.group ? a.group[base + pivot] : 0;
+        /* fail fast: a new pivot must be clearly separated from the earlier pivots of its first-pass group */
+        if ((int)threadIdx.x < k)
+        {
+            const int pb = s_pivots[threadIdx.x];
+            if (!a.group || a.group[base + pb] == gp)
+            {
+                double fb[MAXF];
+#pragma unroll
+                for (int f = 0; f < MAXF; f++) fb[f] = (f < a.nfeat) ? a.feat[(int64_t)f * a.total + base + pb] : 0.0;
+                if (!(PairDistance<KIND>::eval(a.robot, fb, fp) > a.separation)) s_fail = 1;
+            }
+        }
+        __syncthreads();
+        if (s_fail) break;
         int local_min = 0x7fffffff;
         for (int i = threadIdx.x; i < n; i += blockDim.x)
         {
@@ -846,27 +859,9 @@ __global__ void __launch_bounds__(1024) pivot_pass_kernel(const __grid_constant_
             for (int w = 0; w < (int)(blockDim.x >> 5); w++) m = min(m, s_warp_min[w]);
             s_next = m;
         }
-        npiv = k + 1;
         __syncthreads();
     }
-    if (threadIdx.x == 0 && s_next != 0x7fffffff) s_fail = 1; /* more clusters than pivots */
-    __syncthreads();
-    /* pivots of the same first-pass group must be clearly separated */
-    for (int pair = threadIdx.x; pair < npiv * npiv; pair += blockDim.x)
-    {
-        const int ia = pair / npiv, ib = pair % npiv;
-        if (ia >= ib) continue;
-        const int pa = s_pivots[ia], pb = s_pivots[ib];
-        if (a.group && a.group[base + pa] != a.group[base + pb]) continue;
-        double fa[MAXF], fb[MAXF];
-#pragma unroll
-        for (int f = 0; f < MAXF; f++)
-        {
-            fa[f] = (f < a.nfeat) ? a.feat[(int64_t)f * a.total + base + pa] : 0.0;
-            fb[f] = (f < a.nfeat) ? a.feat[(int64_t)f * a.total + base + pb] : 0.0;
-        }
-        if (!(PairDistance<KIND>::eval(a.robot, fa, fb) > a.separation)) s_fail = 1;
-    }
+    if (threadIdx.x == 0 && s_next != 0x7fffffff) s_fail = 1; /* more clusters than pivots (or stopped early) */
     __syncthreads();
     if (threadIdx.x == 0) a.ok[blockIdx.x] = s_fail ? 0 : 1;
 }
