@@ -53,14 +53,16 @@ def test_forward_simulation_matches_oracle_for_every_lane_count(oracle, simulato
     sim.SetLanesPerParticle(0)
 
 
-@pytest.mark.parametrize("pivot_pass", [True, False])
+@pytest.mark.parametrize("pivot_pass", ["forced", "auto", "off"])
 @pytest.mark.parametrize("name", sorted(cases.GOLDEN_CLUSTER_CASES))
 def test_clustering_matches_oracle(oracle, simulators, name, pivot_pass, monkeypatch):
     """every golden clustering case through the default pipeline (pivot pass first) and with the pivot pass
-    forced off (adjacency / root-check / exact paths only)"""
+    forced off (adjacency / root-check / exact paths only); "forced" tries the pivot pass on these small sets too"""
     from uncertainty_planning_core_b200 import OutcomeClustering
-    if not pivot_pass:
+    if pivot_pass == "off":
         monkeypatch.setenv("UPC_B200_NO_PIVOT_PASS", "1")
+    elif pivot_pass == "forced":
+        monkeypatch.setenv("UPC_B200_FORCE_PIVOT_PASS", "1")
     c = cases.GOLDEN_CLUSTER_CASES[name]()
     n_sets = c.get("n_sets", 1)
     olabels, oncl, ostats = oracle.cluster_particles(c["env"], c["robot"], c["cparams"], c["configs"], n_sets)
@@ -77,10 +79,11 @@ def test_clustering_matches_oracle(oracle, simulators, name, pivot_pass, monkeyp
     assert np.array_equal(labels, olabels), name
 
 
-def test_pivot_pass_boundaries(oracle, simulators):
+def test_pivot_pass_boundaries(oracle, simulators, monkeypatch):
     """the pivot pass may only settle what the adjacency pass would settle identically - blobs whose radius sits just
     inside / outside threshold/2, pivots just inside / outside 2*threshold, more clusters than pivots, several sets per call"""
     from uncertainty_planning_core_b200 import OutcomeClustering
+    monkeypatch.setenv("UPC_B200_FORCE_PIVOT_PASS", "1")
     c = cases.cl_se2_blobs()
     sim = simulators("cl_pivot", c["env"], c["robot"])
     thr = 0.1
@@ -103,6 +106,14 @@ def test_pivot_pass_boundaries(oracle, simulators):
         sets.append(np.concatenate([a, b], axis=0))
     many = np.stack([1.0 + 0.5 * np.arange(200), np.full(200, 1.0), np.zeros(200)], axis=1)   # 200 singleton clusters > 64 pivots
     sets.append(many)
+    # wide blobs whose smallest member sits on the rim: a filled disc (a central member exists: settled through the centre search),
+    # the same disc with diameter above the threshold, and an empty ring (no member is central)
+    for rad, filled in ((0.044, True), (0.047, True), (0.06, True), (0.044, False)):
+        m = 199
+        ang = rng.uniform(0, 2 * np.pi, m)
+        rr = rad * np.sqrt(rng.uniform(0, 1, m)) if filled else np.full(m, rad)
+        disc = np.stack([1.0 + rr * np.cos(ang), 1.0 + rr * np.sin(ang), np.zeros(m)], axis=1)
+        sets.append(np.concatenate([[[1.0 + rad, 1.0, 0.0]], disc], axis=0))
     for cfg in sets:
         labels, ncl = oc.ClusterIndices(cfg)
         olabels, oncl, _ = oracle.cluster_particles(c["env"], c["robot"], cp, cfg)

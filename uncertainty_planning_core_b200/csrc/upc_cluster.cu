@@ -775,95 +775,200 @@ struct PivotArgs
     int nfeat;
     int64_t total, set_size;
     const int32_t* group; /* optional first-pass roots (in-set indices) */
+    double threshold;
     double radius;        /* threshold / 2 - margin */
     double separation;    /* 2 * threshold + margin */
-    int32_t* root;        /* out: in-set index of the pivot = smallest member of the particle's cluster */
+    double* scratch;      /* [2][total]: distances to the current pivot; largest distance to the extreme points */
+    int32_t* root;        /* out: in-set index of the smallest member of the particle's cluster */
     uint8_t* ok;          /* out, per set: 1 = the partition written to root is the complete-link result */
 };
 
 constexpr int kMaxPivots = 64;
 
+/* CTA-wide minimum of (key, index) pairs, smaller index on equal keys; every thread receives the result */
+__device__ __forceinline__ void block_min_pair(double& key, int& idx, double* s_key, int* s_idx)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+    {
+        const double ok = __shfl_xor_sync(0xffffffffu, key, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, off);
+        if (ok < key || (ok == key && oi < idx)) { key = ok; idx = oi; }
+    }
+    __syncthreads(); /* previous users of the scratch are done */
+    if (lane == 0) { s_key[warp] = key; s_idx[warp] = idx; }
+    __syncthreads();
+    key = s_key[0]; idx = s_idx[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++)
+        if (s_key[w] < key || (s_key[w] == key && s_idx[w] < idx)) { key = s_key[w]; idx = s_idx[w]; }
+}
+
 /*
- * One CTA per set.  Repeat: the smallest unassigned particle becomes a pivot and takes every unassigned particle of its
- * first-pass group whose distance to it is <= threshold/2 - margin.  The configuration distances are metrics, so all
- * pairs inside such a group are within the threshold (a clique); if, in addition, pivots of the same first-pass group
- * are further than 2 * threshold + margin apart, no pair across groups is, the threshold graph is exactly the disjoint
- * union of these cliques and complete link returns them.  The margin (1e-6) covers the rounding of the
- * evaluated distances (<= 2e-8: the arccosine of the SE(3) rotation part near zero angle).  Anything else - more than
- * kMaxPivots groups, pivots too close - reports ok = 0 and the adjacency pass decides.
+ * One CTA per set.  Repeat: the smallest unassigned particle p opens a group.  If every unassigned particle of its
+ * first-pass group that lies within the threshold of p lies within threshold/2 - margin, p is the group's centre;
+ * otherwise a more central member is looked for (the candidate minimising its largest distance to p, to the candidate
+ * farthest from p and to the candidates farthest from the centres tried so far).  The group takes every unassigned particle of the first-pass group within
+ * threshold/2 - margin of the centre, and must contain p.  The configuration distances are metrics, so all pairs inside
+ * a group are within the threshold (a clique); if, in addition, centres of the same first-pass group are further than
+ * 2 * threshold + margin apart, no pair across groups is, the threshold graph is exactly the disjoint union of these
+ * cliques and complete link returns them, numbered by their smallest members p.  The margin (1e-6)
+ * covers the rounding of the evaluated distances (<= 2e-8: the arccosine of the SE(3) rotation part near zero angle).
+ * Anything else - more than kMaxPivots groups, centres too close, p outside its group - reports ok = 0 and the
+ * adjacency pass decides.  The choice of the centre is a heuristic: it only affects whether the set is settled here.
  */
 template <int KIND>
 __global__ void __launch_bounds__(1024) pivot_pass_kernel(const __grid_constant__ PivotArgs a)
 {
     constexpr int MAXF = PairDistance<KIND>::MAXF;
-    __shared__ int s_warp_min[32];
-    __shared__ int s_next;
-    __shared__ int s_pivots[kMaxPivots];
+    __shared__ double s_key[32];
+    __shared__ int s_idx[32];
+    __shared__ int s_centres[kMaxPivots];
     __shared__ int s_fail;
     const int64_t base = (int64_t)blockIdx.x * a.set_size;
     const int n = (int)a.set_size;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < n; i += blockDim.x) a.root[base + i] = -1;
-    if (threadIdx.x == 0)
-    {
-        s_next = (n > 0) ? 0 : 0x7fffffff;
-        s_fail = 0;
-    }
+    if (threadIdx.x == 0) s_fail = 0;
     __syncthreads();
-    for (int k = 0; k < kMaxPivots; k++)
+    int next = (n > 0) ? 0 : 0x7fffffff;
+    for (int k = 0; k < kMaxPivots && next != 0x7fffffff; k++)
     {
-        const int pivot = s_next;
-        if (pivot == 0x7fffffff) break;
+        const int p = next;
         double fp[MAXF];
 #pragma unroll
-        for (int f = 0; f < MAXF; f++) fp[f] = (f < a.nfeat) ? a.feat[(int64_t)f * a.total + base + pivot] : 0.0;
-        const int gp = a.group ? a.group[base + pivot] : 0;
-        /* fail fast: a new pivot must be clearly separated from the earlier pivots of its first-pass group */
+        for (int f = 0; f < MAXF; f++) fp[f] = (f < a.nfeat) ? a.feat[(int64_t)f * a.total + base + p] : 0.0;
+        const int gp = a.group ? a.group[base + p] : 0;
+        /* sweep 1: distances of the candidates to p; the farthest one within the threshold */
+        double far_key = 1.0; /* keys are negated distances: block_min_pair returns the largest distance */
+        int far_idx = 0x7fffffff;
+        for (int i = threadIdx.x; i < n; i += blockDim.x)
+        {
+            double d = -1.0; /* not a candidate */
+            if (a.root[base + i] < 0 && (!a.group || a.group[base + i] == gp))
+            {
+                if (i == p)
+                {
+                    d = 0.0;
+                }
+                else
+                {
+                    double fi[MAXF];
+#pragma unroll
+                    for (int f = 0; f < MAXF; f++) fi[f] = (f < a.nfeat) ? a.feat[(int64_t)f * a.total + base + i] : 0.0;
+                    d = PairDistance<KIND>::eval(a.robot, fp, fi);
+                    if (!(d >= 0.0)) d = INFINITY; /* NaN: never a member, the separation test then rejects the set */
+                }
+                if (d <= a.threshold && (-d < far_key || (-d == far_key && i < far_idx))) { far_key = -d; far_idx = i; }
+            }
+            a.scratch[base + i] = d;
+        }
+        block_min_pair(far_key, far_idx, s_key, s_idx);
+        int centre = p;
+        if (-far_key > a.radius)
+        {
+            /* a more central candidate: minimise the largest distance to a growing set of extreme points (p, the candidate
+             * farthest from p, then the candidates farthest from the successive centres) - up to six rounds */
+            double* runmax = a.scratch + a.total; /* per candidate: largest distance to the extremes so far */
+            int ext = far_idx;
+            for (int round = 0; round < 6; round++)
+            {
+                double fe[MAXF];
+#pragma unroll
+                for (int f = 0; f < MAXF; f++) fe[f] = (f < a.nfeat) ? a.feat[(int64_t)f * a.total + base + ext] : 0.0;
+                double best_key = INFINITY;
+                int best_idx = 0x7fffffff;
+                for (int i = threadIdx.x; i < n; i += blockDim.x)
+                {
+                    const double dp = a.scratch[base + i];
+                    if (dp < 0.0 || dp > a.threshold) continue;
+                    double fi[MAXF];
+#pragma unroll
+                    for (int f = 0; f < MAXF; f++) fi[f] = (f < a.nfeat) ? a.feat[(int64_t)f * a.total + base + i] : 0.0;
+                    const double de = (i == ext) ? 0.0 : PairDistance<KIND>::eval(a.robot, fe, fi);
+                    const double before = (round == 0) ? dp : runmax[base + i];
+                    const double key = (before > de) ? before : de;
+                    runmax[base + i] = key;
+                    if (key < best_key || (key == best_key && i < best_idx)) { best_key = key; best_idx = i; }
+                }
+                block_min_pair(best_key, best_idx, s_key, s_idx);
+                if (best_idx == 0x7fffffff) break;
+                centre = best_idx;
+                /* how far is the farthest candidate from this centre? */
+                double fcand[MAXF];
+#pragma unroll
+                for (int f = 0; f < MAXF; f++) fcand[f] = (f < a.nfeat) ? a.feat[(int64_t)f * a.total + base + centre] : 0.0;
+                double worst_key = 1.0;
+                int worst_idx = 0x7fffffff;
+                for (int i = threadIdx.x; i < n; i += blockDim.x)
+                {
+                    const double dp = a.scratch[base + i];
+                    if (dp < 0.0 || dp > a.threshold) continue;
+                    double fi[MAXF];
+#pragma unroll
+                    for (int f = 0; f < MAXF; f++) fi[f] = (f < a.nfeat) ? a.feat[(int64_t)f * a.total + base + i] : 0.0;
+                    const double dc = (i == centre) ? 0.0 : PairDistance<KIND>::eval(a.robot, fcand, fi);
+                    if (-dc < worst_key || (-dc == worst_key && i < worst_idx)) { worst_key = -dc; worst_idx = i; }
+                }
+                block_min_pair(worst_key, worst_idx, s_key, s_idx);
+                if (-worst_key <= a.radius || worst_idx == 0x7fffffff) break;
+                ext = worst_idx;
+            }
+        }
+        double fc[MAXF];
+#pragma unroll
+        for (int f = 0; f < MAXF; f++) fc[f] = (f < a.nfeat) ? a.feat[(int64_t)f * a.total + base + centre] : 0.0;
+        /* fail fast: a new centre must be clearly separated from the earlier centres of its first-pass group */
         if ((int)threadIdx.x < k)
         {
-            const int pb = s_pivots[threadIdx.x];
-            if (!a.group || a.group[base + pb] == gp)
+            const int cb = s_centres[threadIdx.x];
+            if (!a.group || a.group[base + cb] == gp)
             {
                 double fb[MAXF];
 #pragma unroll
-                for (int f = 0; f < MAXF; f++) fb[f] = (f < a.nfeat) ? a.feat[(int64_t)f * a.total + base + pb] : 0.0;
-                if (!(PairDistance<KIND>::eval(a.robot, fb, fp) > a.separation)) s_fail = 1;
+                for (int f = 0; f < MAXF; f++) fb[f] = (f < a.nfeat) ? a.feat[(int64_t)f * a.total + base + cb] : 0.0;
+                if (!(PairDistance<KIND>::eval(a.robot, fb, fc) > a.separation)) s_fail = 1;
             }
         }
-        __syncthreads();
-        if (s_fail) break;
-        int local_min = 0x7fffffff;
+        /* sweep 3: the group */
+        double min_key = (double)0x7fffffff;
+        int min_idx = 0x7fffffff;
         for (int i = threadIdx.x; i < n; i += blockDim.x)
         {
             if (a.root[base + i] >= 0) continue;
-            bool take = (i == pivot);
-            if (!take && (!a.group || a.group[base + i] == gp))
+            const double dp = a.scratch[base + i];
+            bool take = false;
+            if (dp >= 0.0)
             {
-                double fi[MAXF];
+                if (centre == p)
+                {
+                    take = dp <= a.radius;
+                }
+                else if (i == centre)
+                {
+                    take = true;
+                }
+                else
+                {
+                    double fi[MAXF];
 #pragma unroll
-                for (int f = 0; f < MAXF; f++) fi[f] = (f < a.nfeat) ? a.feat[(int64_t)f * a.total + base + i] : 0.0;
-                take = PairDistance<KIND>::eval(a.robot, fp, fi) <= a.radius; /* pivot < i always: smaller index first */
+                    for (int f = 0; f < MAXF; f++) fi[f] = (f < a.nfeat) ? a.feat[(int64_t)f * a.total + base + i] : 0.0;
+                    take = PairDistance<KIND>::eval(a.robot, fc, fi) <= a.radius;
+                }
             }
-            if (take) a.root[base + i] = pivot;
-            else local_min = min(local_min, i);
+            if (take) a.root[base + i] = p;
+            else if (i < min_idx) { min_idx = i; min_key = (double)i; }
         }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) local_min = min(local_min, __shfl_xor_sync(0xffffffffu, local_min, off));
-        __syncthreads(); /* everybody has read s_next */
-        if (lane == 0) s_warp_min[warp] = local_min;
-        if (threadIdx.x == 0) s_pivots[k] = pivot;
-        __syncthreads();
+        block_min_pair(min_key, min_idx, s_key, s_idx); /* also orders the root writes before the test below */
         if (threadIdx.x == 0)
         {
-            int m = 0x7fffffff;
-            for (int w = 0; w < (int)(blockDim.x >> 5); w++) m = min(m, s_warp_min[w]);
-            s_next = m;
+            s_centres[k] = centre;
+            if (a.root[base + p] != p) s_fail = 1; /* p fell outside its own group */
         }
         __syncthreads();
+        if (s_fail) break;
+        next = min_idx;
     }
-    if (threadIdx.x == 0 && s_next != 0x7fffffff) s_fail = 1; /* more clusters than pivots (or stopped early) */
-    __syncthreads();
-    if (threadIdx.x == 0) a.ok[blockIdx.x] = s_fail ? 0 : 1;
+    if (threadIdx.x == 0) a.ok[blockIdx.x] = (s_fail || next != 0x7fffffff) ? 0 : 1; /* also: more clusters than pivots */
 }
 
 /* ------------------------------------------------------------------ exact complete link for sets that are not unions of cliques */
@@ -1873,18 +1978,26 @@ int32_t run_cluster(upc_handle* h, const upc_cluster_params& cp, int64_t n_sets,
     in.group = group;
     in.threshold = cp.distance_clustering_threshold;
     /* blob-shaped outcomes (the common case after a contact edge): the pivot pass settles the distance clustering in
-     * O(n * clusters); UPC_B200_NO_PIVOT_PASS=1 forces the adjacency pass (tests exercise both) */
+     * O(n * clusters); UPC_B200_NO_PIVOT_PASS=1 forces the adjacency pass, UPC_B200_FORCE_PIVOT_PASS=1 tries the pivot pass on
+     * small inputs too (tests exercise all three) */
     bool settled = false;
     {
         const char* off = getenv("UPC_B200_NO_PIVOT_PASS");
-        if (!(off && off[0] == '1') && set_size >= 2 && set_size < ((int64_t)1 << 31) && cp.distance_clustering_threshold > 1.0e-5)
+        /* worth it once the pair pass would cost more than a few sweeps: >= 3e7 pair tests over all sets */
+        const double pair_tests = (double)n_sets * (double)set_size * (double)set_size;
+        const char* force = getenv("UPC_B200_FORCE_PIVOT_PASS"); /* tests: try it whatever the size */
+        const bool big_enough = (pair_tests >= 3.0e7) || (force && force[0] == '1');
+        if (!(off && off[0] == '1') && set_size >= 2 && set_size < ((int64_t)1 << 31) && big_enough && cp.distance_clustering_threshold > 1.0e-5)
         {
             uint8_t* ok = buf<uint8_t>(h->cw.link_scratch, (size_t)n_sets);
             UPC_NULLCHECK(ok);
             PivotArgs pa;
             pa.robot = h->robot; pa.feat = feat; pa.nfeat = nfeat; pa.total = total; pa.set_size = set_size; pa.group = group;
+            pa.threshold = cp.distance_clustering_threshold;
             pa.radius = 0.5 * cp.distance_clustering_threshold - 1.0e-6;
             pa.separation = 2.0 * cp.distance_clustering_threshold + 1.0e-6;
+            pa.scratch = buf<double>(h->cw.dist_matrix, (size_t)total * 2);
+            UPC_NULLCHECK(pa.scratch);
             pa.root = root2; pa.ok = ok;
             const int threads = (set_size >= 1024) ? 1024 : ((set_size >= 256) ? 256 : 64);
             if (kind == UPC_ROBOT_SE2) pivot_pass_kernel<UPC_ROBOT_SE2><<<(unsigned)n_sets, threads, 0, stream>>>(pa);
