@@ -37,8 +37,18 @@ struct SimArgs
     DevCounters* counters;
 };
 
+/* CTAs per SM the register budget is cut for.  One lane per particle is the big-batch mapping: the batch never fits one wave
+ * anyway, and for the SE(3) and linked programs 255 registers with two CTAs per SM beat 168 with three (fewer spills, and the
+ * resident threads' local-memory footprint - link frames, call frames - stays closer to what L2 holds): C3 42.9 -> 39.1 ms,
+ * 10^6 SE(3) particles 1.52e9 -> 1.66e9 particle-steps/s.  The SE(2) program is small and prefers three. */
 template <class M, int G>
-__global__ void __launch_bounds__(kBlock, UPC_SIM_MIN_BLOCKS) forward_simulate_kernel(const __grid_constant__ SimArgs a)
+constexpr int sim_min_blocks()
+{
+    return (G == 1 && M::DOF > 3) ? 2 : UPC_SIM_MIN_BLOCKS;
+}
+
+template <class M, int G>
+__global__ void __launch_bounds__(kBlock, sim_min_blocks<M, G>()) forward_simulate_kernel(const __grid_constant__ SimArgs a)
 {
     extern __shared__ double smem[];
     __shared__ unsigned int s_cnt[4];
