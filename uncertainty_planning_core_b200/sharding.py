@@ -36,18 +36,21 @@ def unpack_outcomes(buf, n, width):
     return labels, collided, configs
 
 
-def gather_outcomes(packed, world):
-    """The single collective of a step: every rank receives every rank's outcome records (equal shard sizes)."""
+def gather_outcomes(packed, world, async_op=False):
+    """The single collective of a step: every rank receives every rank's outcome records (equal shard sizes).
+    async_op=True returns (out, work): the collective runs on the process group's own stream and the caller's stream
+    does not wait for it until work.wait() - the next batch's simulation overlaps the exchange."""
     if world == 1:
-        return packed.unsqueeze(0)
+        return (packed.unsqueeze(0), None) if async_op else packed.unsqueeze(0)
     out = torch.empty((world, packed.numel()), dtype=torch.uint8, device=packed.device)
     try:
-        dist.all_gather_into_tensor(out, packed)
+        work = dist.all_gather_into_tensor(out, packed, async_op=async_op)
     except (RuntimeError, NotImplementedError):
         parts = [torch.empty_like(packed) for _ in range(world)]
         dist.all_gather(parts, packed)
         out = torch.stack(parts)
-    return out
+        work = None
+    return (out, work) if async_op else out
 
 
 def merge_cluster_counts(gathered, n, width, world):
