@@ -297,33 +297,45 @@ def run_b200(args):
     stream = side.cuda_stream
     assert stream != 0
 
+    # two sets of outcome buffers: while batch k simulates, the host packs and ships batch k-1 (multi-GPU runs)
+    outs = [(d_out, d_coll, d_labels, d_ncl)]
+    if world > 1:
+        outs.append((torch.zeros_like(d_out), torch.zeros_like(d_coll), torch.zeros_like(d_labels), torch.zeros_like(d_ncl)))
+    in_flight = []
+    pending = []
+
+    def ship(buf):
+        """pack + ONE all-gather of a finished batch; NCCL's own stream carries it, at most two are in flight"""
+        o, c, l, _ = outs[buf]
+        packed, _ = sharding.pack_outcomes(l, c, o)
+        gathered, work = sharding.gather_outcomes(packed, world, async_op=True)
+        in_flight.append((gathered, packed, work))
+        while len(in_flight) > 2:
+            _, _, w = in_flight.pop(0)
+            if w is not None:
+                w.wait()
+
     def device_step(k, ev=None):
         tape = d_tapes[k % ring]
+        buf = k % len(outs)
+        o, c, l, ncl = outs[buf]
         if ev:
             ev[0].record()
         abi.check(lib.upc_forward_simulate_device(h, C.byref(params), n, d_starts.data_ptr(), n_targets, d_targets.data_ptr(),
-                                                  tape.data_ptr(), d_out.data_ptr(), d_coll.data_ptr(), stream))
+                                                  tape.data_ptr(), o.data_ptr(), c.data_ptr(), stream))
         if ev:
             ev[1].record()
-        abi.check(lib.upc_cluster_particles_device(h, C.byref(cp), 1, n, d_out.data_ptr(), d_labels.data_ptr(), d_ncl.data_ptr(), stream))
+        if world > 1 and pending:
+            ship(pending.pop(0))   # host-side packing of batch k-1 overlaps the simulation of batch k just enqueued
+        abi.check(lib.upc_cluster_particles_device(h, C.byref(cp), 1, n, o.data_ptr(), l.data_ptr(), ncl.data_ptr(), stream))
         if ev:
             ev[2].record()
         if world > 1:
-            # the exchange of batch k overlaps the simulation of batch k+1 (NCCL's own stream); at most two are in flight and
-            # all of them are waited for before the timed region ends
-            packed, _ = sharding.pack_outcomes(d_labels, d_coll, d_out)
-            gathered, work = sharding.gather_outcomes(packed, world, async_op=True)
-            in_flight.append((gathered, packed, work))
-            while len(in_flight) > 2:
-                _, _, w = in_flight.pop(0)
-                if w is not None:
-                    w.wait()
-            return gathered
-        return None
-
-    in_flight = []
+            pending.append(buf)
 
     def drain():
+        while pending:
+            ship(pending.pop(0))
         while in_flight:
             _, _, w = in_flight.pop(0)
             if w is not None:
