@@ -181,7 +181,8 @@ int32_t upc_destroy(upc_handle* h);
 int32_t upc_set_robot(upc_handle* h, const upc_robot_desc* robot);
 int32_t upc_get_stats(upc_handle* h, upc_stats* out);
 int32_t upc_reset_stats(upc_handle* h);
-/* tuning: lanes cooperating on one particle (1, 2, 4, 8, 16 or 32); 0 restores the built-in choice. Results do not depend on it. */
+/* tuning: lanes cooperating on one particle (1, 2, 3, 4, 5, 6, 8, 16 or 32; counts that do not divide 32 leave the last lanes of a warp idle);
+ * 0 restores the built-in choice. Results do not depend on it. */
 int32_t upc_set_lanes_per_particle(upc_handle* h, int32_t lanes);
 
 /* pinned host memory helpers for callers that want the fast H2D/D2H path */

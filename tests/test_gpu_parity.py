@@ -40,7 +40,7 @@ def test_forward_simulation_matches_oracle_for_every_lane_count(oracle, simulato
     g = np.load(os.path.join(HERE, "golden", "sim_%s.npz" % name))
     assert np.array_equal(ocfg, g["configs"]) and np.array_equal(ocoll, g["collided"])
     sim = simulators(name, sc["env"], sc["robot"])
-    for lanes in (0, 1, 2, 4, 8, 16, 32):
+    for lanes in (0, 1, 2, 3, 4, 5, 6, 8, 16, 32):
         sim.SetLanesPerParticle(lanes)
         sim.ResetStatistics()
         cfg, coll = sim.ForwardSimulateRobots(sc["starts"], sc["targets"], tape, sc["params"])
@@ -212,7 +212,7 @@ def test_single_precision_pre_cull_changes_nothing(oracle):
             sim = B200Simulator(sc["env"], sc["robot"])
         finally:
             os.environ.pop("UPC_B200_NO_FP32_CULL", None)
-        for lanes in (1, 4, 16):          # 128, 32 and 8 points per lane: all take the pre-cull when it is on
+        for lanes in (1, 4, 5, 16):       # 128, 32, 26 and 8 points per lane: all take the pre-cull when it is on
             sim.SetLanesPerParticle(lanes)
             cfg, coll = sim.ForwardSimulateRobots(sc["starts"], sc["targets"], tape, sc["params"])
             assert np.array_equal(coll, ocoll) and max_ulp_diff(cfg, ocfg) <= CONFIG_ULP_TOLERANCE

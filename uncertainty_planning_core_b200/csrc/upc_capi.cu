@@ -381,8 +381,8 @@ int32_t upc_reset_stats(upc_handle* h)
 int32_t upc_set_lanes_per_particle(upc_handle* h, int32_t lanes)
 {
     if (!h) return fail_arg("null argument");
-    if (lanes != 0 && lanes != 1 && lanes != 2 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32)
-        return fail_arg("lanes must be 0, 1, 2, 4, 8, 16 or 32");
+    if (lanes != 0 && lanes != 1 && lanes != 2 && lanes != 3 && lanes != 4 && lanes != 5 && lanes != 6 && lanes != 8 && lanes != 16 && lanes != 32)
+        return fail_arg("lanes must be 0, 1, 2, 3, 4, 5, 6, 8, 16 or 32");
     h->lanes_override = lanes;
     return UPC_OK;
 }

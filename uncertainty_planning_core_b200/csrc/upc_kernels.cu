@@ -58,13 +58,20 @@ __global__ void __launch_bounds__(kBlock, sim_min_blocks<M, G>()) forward_simula
     if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0u;
     __syncthreads();
 
-    const int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    const int64_t i = t / G;
+    /* G lanes per particle, groups never straddle a warp: a warp holds 32 / G particles and, when G does not divide 32, leaves
+     * its last 32 % G lanes idle */
+    constexpr int kGroupsPerWarp = 32 / G;
+    constexpr int kParticlesPerBlock = (kBlock / 32) * kGroupsPerWarp;
+    const int lane = (int)(threadIdx.x & 31);
+    const int group_in_warp = lane / G;
+    const bool lane_used = group_in_warp < kGroupsPerWarp;
+    const int particle_in_block = (int)(threadIdx.x >> 5) * kGroupsPerWarp + group_in_warp;
+    const int64_t i = lane_used ? ((int64_t)blockIdx.x * kParticlesPerBlock + particle_in_block) : a.n;
     LocalCounters lc = {};
     bool collided = false;
     Group<G> g;
-    g.sub = (int)(threadIdx.x % G);
-    g.base = (int)((threadIdx.x & 31) - g.sub);
+    g.sub = lane % G;
+    g.base = lane - g.sub;
     g.mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << g.base);
     if (i < a.n)
     {
@@ -75,7 +82,7 @@ __global__ void __launch_bounds__(kBlock, sim_min_blocks<M, G>()) forward_simula
          * per-thread local memory instead: shared memory could not hold them for 64-128 particles per CTA. */
         constexpr bool kFramesInShared = M::HAS_FRAMES && (G >= 4);
         const int per = kFramesInShared ? a.robot.num_links * 12 : 0;
-        double* park = smem + npd + (size_t)(threadIdx.x / G) * (size_t)(2 * M::WIDTH + 2 * M::DOF + 2 * per);
+        double* park = smem + npd + (size_t)particle_in_block * (size_t)(2 * M::WIDTH + 2 * M::DOF + 2 * per);
         double local_frames[(M::HAS_FRAMES && !kFramesInShared) ? 2 * UPC_MAX_LINKS * 12 : 1];
         if constexpr (kFramesInShared)
         {
@@ -113,10 +120,10 @@ __global__ void __launch_bounds__(kBlock, sim_min_blocks<M, G>()) forward_simula
 template <class M, int G>
 static cudaError_t launch_sim_impl(const SimArgs& a, cudaStream_t stream)
 {
-    const int64_t threads = a.n * G;
-    const int64_t blocks = (threads + kBlock - 1) / kBlock;
+    constexpr int particles_per_block = (kBlock / 32) * (32 / G);
+    const int64_t blocks = (a.n + particles_per_block - 1) / particles_per_block;
     size_t smem = (size_t)a.robot.num_points * 6 * sizeof(double);
-    smem += (size_t)(kBlock / G) * (2 * M::WIDTH + 2 * M::DOF + ((M::HAS_FRAMES && G >= 4) ? 2 * (size_t)a.robot.num_links * 12 : 0)) * sizeof(double);
+    smem += (size_t)particles_per_block * (2 * M::WIDTH + 2 * M::DOF + ((M::HAS_FRAMES && G >= 4) ? 2 * (size_t)a.robot.num_links * 12 : 0)) * sizeof(double);
     if (smem > 48 * 1024)
     {
         cudaError_t e = cudaFuncSetAttribute(forward_simulate_kernel<M, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -133,7 +140,10 @@ static cudaError_t launch_sim_lanes(const SimArgs& a, int lanes, cudaStream_t st
     {
         case 1: return launch_sim_impl<M, 1>(a, stream);
         case 2: return launch_sim_impl<M, 2>(a, stream);
+        case 3: return launch_sim_impl<M, 3>(a, stream);
         case 4: return launch_sim_impl<M, 4>(a, stream);
+        case 5: return launch_sim_impl<M, 5>(a, stream);
+        case 6: return launch_sim_impl<M, 6>(a, stream);
         case 8: return launch_sim_impl<M, 8>(a, stream);
         case 16: return launch_sim_impl<M, 16>(a, stream);
         default: return launch_sim_impl<M, 32>(a, stream);
@@ -153,16 +163,24 @@ int choose_lanes(const upc_handle* h, int64_t n)
     }
     else
     {
-        const int64_t one_wave_threads = (int64_t)h->sm_count * UPC_SIM_MIN_BLOCKS * kBlock;
-        lanes = 1;
-        while (lanes < 32 && n * lanes * 2 <= one_wave_threads) lanes *= 2;
+        const int64_t one_wave_warps = (int64_t)h->sm_count * UPC_SIM_MIN_BLOCKS * (kBlock / 32);
         int max_pts = 1;
         for (int l = 0; l < h->robot.num_links; l++)
         {
             const int c = h->robot.link_off[l + 1] - h->robot.link_off[l];
             if (c > max_pts) max_pts = c;
         }
-        while (lanes > 1 && lanes > max_pts) lanes /= 2;
+        /* a warp holds 32 / lanes particles.  3, 5 and 6 lanes (idle lanes at the end of every warp) can be requested through
+         * upc_set_lanes_per_particle but are not chosen here: on C2 five lanes fit one wave and shorten the per-lane point loops
+         * by a fifth, yet the 33 % extra warps all repeat the replicated state math and the kernel gets slower (2.43 -> 2.56 ms) */
+        const int candidates[] = {1, 2, 4, 8, 16, 32};
+        lanes = 1;
+        for (int c : candidates)
+        {
+            const int64_t per_warp = 32 / c;
+            const int64_t warps = (n + per_warp - 1) / per_warp;
+            if (c <= max_pts && warps <= one_wave_warps) lanes = c;
+        }
     }
     return lanes;
 }

@@ -55,11 +55,22 @@ struct Group
 #if defined(__CUDA_ARCH__)
         if (G > 1)
         {
-#pragma unroll
-            for (int off = G / 2; off > 0; off >>= 1)
+            if constexpr ((G & (G - 1)) == 0)
             {
-                const double o = __shfl_xor_sync(mask, v, off);
-                v = upc_max(v, o);
+#pragma unroll
+                for (int off = G / 2; off > 0; off >>= 1)
+                {
+                    const double o = __shfl_xor_sync(mask, v, off);
+                    v = upc_max(v, o);
+                }
+            }
+            else
+            {
+                /* group sizes that are not powers of two: every lane reads every lane (max is order-free) */
+                double best = v;
+#pragma unroll
+                for (int t = 0; t < G; t++) best = upc_max(best, __shfl_sync(mask, v, base + t));
+                v = best;
             }
         }
 #endif
@@ -435,10 +446,17 @@ UPC_DNI int resolver_correction(const DevEnv& env, const DevRobot& r, const DevS
             /* phase C: rounds in ascending j, lanes in ascending rank = ascending point index */
             unsigned rounds = contributing;
 #if defined(__CUDA_ARCH__)
-            if (G > 1)
+            if constexpr (G > 1 && (G & (G - 1)) == 0)
             {
 #pragma unroll
                 for (int off = G / 2; off > 0; off >>= 1) rounds |= __shfl_xor_sync(g.mask, rounds, off);
+            }
+            else if constexpr (G > 1)
+            {
+                unsigned all = 0u;
+#pragma unroll
+                for (int t = 0; t < G; t++) all |= __shfl_sync(g.mask, contributing, g.base + t);
+                rounds = all;
             }
 #endif
             while (rounds)
