@@ -285,7 +285,29 @@ __global__ void __launch_bounds__(128) signature_kernel(const __grid_constant__ 
         double T[12], V[12];
         m.frame(a.robot, l, T);
         voxel_from_link(a.env, T, V);
-        for (int k = beg; k < end; k++)
+        int k = beg;
+        for (; k + 4 <= end; k += 4) /* four independent lookups in flight; stores and the hash keep the point order */
+        {
+            int64_t cell[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+            {
+                double u[3];
+                xf_point(V, a.robot.pts[4 * (k + q) + 0], a.robot.pts[4 * (k + q) + 1], a.robot.pts[4 * (k + q) + 2], u);
+                cell[q] = voxel_in_bounds(a.env, u) ? (int64_t)cell_index(a.env, floor_to_int(u[0]), floor_to_int(u[1]), floor_to_int(u[2])) : (int64_t)-1;
+            }
+            uint32_t sv[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) sv[q] = (cell[q] >= 0) ? ldg(a.env.seg + cell[q]) : 0u;
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+            {
+                a.sig[(int64_t)(k + q) * a.total + i] = sv[q];
+                h = (h ^ (unsigned long long)sv[q]) * 0x9E3779B97F4A7C15ull;
+                h ^= h >> 29;
+            }
+        }
+        for (; k < end; k++)
         {
             double u[3];
             xf_point(V, a.robot.pts[4 * k + 0], a.robot.pts[4 * k + 1], a.robot.pts[4 * k + 2], u);
