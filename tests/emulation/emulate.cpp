@@ -157,6 +157,7 @@ extern "C" int emulate_forward_simulate(const upc_env_desc* e, const upc_robot_d
     for (int k = 0; k < 4; k++) counters[k] = 0;
     if (r->kind == UPC_ROBOT_SE2) run<Se2Model>(env, rob, sp, n, starts, n_targets, targets, tape, out, coll, counters);
     else if (r->kind == UPC_ROBOT_SE3) run<Se3Model>(env, rob, sp, n, starts, n_targets, targets, tape, out, coll, counters);
+    else if (rob.dof <= LinkedModelSmall::DOF && rob.num_links <= LinkedModelSmall::LINKS) run<LinkedModelSmall>(env, rob, sp, n, starts, n_targets, targets, tape, out, coll, counters); /* same dispatch as launch_forward_simulate */
     else run<LinkedModel>(env, rob, sp, n, starts, n_targets, targets, tape, out, coll, counters);
     return 0;
 }

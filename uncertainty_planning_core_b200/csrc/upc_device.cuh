@@ -1105,11 +1105,16 @@ struct Se3Model
  * Linked robot: joint values and PID state live in registers/local memory; link transforms are recomputed
  * into a caller-provided frame buffer (shared memory on the GPU) by fk().
  */
-struct LinkedModel
+/* CAP = capacity in degrees of freedom: arrays sized by it (joint values here, the resolver's normal equations in
+ * upc_sim.cuh) are what the per-thread stack of the simulation program consists of; robots with dof <= 8 run the CAP = 8
+ * instantiation (C3: 8.7 KB -> about a third of it per thread) */
+template <int CAP>
+struct LinkedModelT
 {
-    static constexpr int DOF = UPC_MAX_DOF;
-    static constexpr int WIDTH = UPC_MAX_DOF;
-    double q[UPC_MAX_DOF];
+    static constexpr int DOF = CAP;
+    static constexpr int WIDTH = CAP;
+    static constexpr int LINKS = (CAP <= 8) ? 9 : UPC_MAX_LINKS; /* link-frame capacity of the per-thread frame buffers */
+    double q[CAP];
     double* pid_i;
     double* pid_e;
     double* frames; /* num_links * 12 doubles, current link transforms */
@@ -1203,7 +1208,7 @@ struct LinkedModel
     }
     UPC_D void load(const DevRobot& r, const double* c, int64_t stride, int64_t i)
     {
-        double v[UPC_MAX_DOF];
+        double v[CAP];
         for (int a = 0; a < r.dof; a++) v[a] = c[(int64_t)a * stride + i];
         set_values(r, v);
     }
@@ -1218,7 +1223,7 @@ struct LinkedModel
     UPC_D void set(const DevRobot& r, const double* c) { set_values(r, c); }
     UPC_D void reset_controllers()
     {
-        for (int i = 0; i < UPC_MAX_DOF; i++) { pid_i[i] = 0.0; pid_e[i] = 0.0; }
+        for (int i = 0; i < CAP; i++) { pid_i[i] = 0.0; pid_e[i] = 0.0; }
     }
     UPC_D static double distance(const DevRobot& r, const double* a, const double* b) /* :2191-2217 */
     {
@@ -1297,6 +1302,9 @@ struct LinkedModel
         }
     }
 };
+
+using LinkedModel = LinkedModelT<UPC_MAX_DOF>;
+using LinkedModelSmall = LinkedModelT<8>;
 
 } /* namespace upc */
 

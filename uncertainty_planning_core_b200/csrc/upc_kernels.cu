@@ -37,6 +37,14 @@ struct SimArgs
     DevCounters* counters;
 };
 
+/* per-thread link-frame storage (two sets) of robots whose frames do not live in shared memory */
+template <class M, bool IN_SHARED>
+__host__ __device__ constexpr int frame_buffer_doubles()
+{
+    if constexpr (M::HAS_FRAMES && !IN_SHARED) return 2 * M::LINKS * 12;
+    else return 2;
+}
+
 /* CTAs per SM the register budget is cut for.  One lane per particle is the big-batch mapping: the batch never fits one wave
  * anyway, and for the SE(3) and linked programs 255 registers with two CTAs per SM beat 168 with three (fewer spills, and the
  * resident threads' local-memory footprint - link frames, call frames - stays closer to what L2 holds): C3 42.9 -> 39.1 ms,
@@ -83,7 +91,7 @@ __global__ void __launch_bounds__(kBlock, sim_min_blocks<M, G>()) forward_simula
         constexpr bool kFramesInShared = M::HAS_FRAMES && (G >= 4);
         const int per = kFramesInShared ? a.robot.num_links * 12 : 0;
         double* park = smem + npd + (size_t)particle_in_block * (size_t)(2 * M::WIDTH + 2 * M::DOF + 2 * per);
-        double local_frames[(M::HAS_FRAMES && !kFramesInShared) ? 2 * UPC_MAX_LINKS * 12 : 1];
+        double local_frames[frame_buffer_doubles<M, kFramesInShared>()];
         if constexpr (kFramesInShared)
         {
             frames0 = park + 2 * M::WIDTH + 2 * M::DOF;
@@ -92,7 +100,7 @@ __global__ void __launch_bounds__(kBlock, sim_min_blocks<M, G>()) forward_simula
         else if constexpr (M::HAS_FRAMES)
         {
             frames0 = local_frames;
-            frames1 = local_frames + UPC_MAX_LINKS * 12;
+            frames1 = local_frames + frame_buffer_doubles<M, kFramesInShared>() / 2;
         }
         simulate_particle<M, G>(a.env, a.robot, a.sp, g, i, a.n, a.starts, a.n_targets, a.targets, a.tape, a.out_configs,
                                 a.out_collided, pts, frames0, frames1, park, lc, collided);
@@ -124,7 +132,7 @@ static cudaError_t launch_sim_impl(const SimArgs& a, cudaStream_t stream)
     const int64_t blocks = (a.n + particles_per_block - 1) / particles_per_block;
     size_t smem = (size_t)a.robot.num_points * 6 * sizeof(double);
     smem += (size_t)particles_per_block * (2 * M::WIDTH + 2 * M::DOF + ((M::HAS_FRAMES && G >= 4) ? 2 * (size_t)a.robot.num_links * 12 : 0)) * sizeof(double);
-    if (smem > 48 * 1024)
+    if (smem + 256 > 48 * 1024) /* the kernel also has a few bytes of static shared memory */
     {
         cudaError_t e = cudaFuncSetAttribute(forward_simulate_kernel<M, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -206,7 +214,10 @@ cudaError_t launch_forward_simulate(upc_handle* h, const DevSim& sp, int64_t n, 
     {
         case UPC_ROBOT_SE2: return launch_sim_lanes<Se2Model>(a, lanes, stream);
         case UPC_ROBOT_SE3: return launch_sim_lanes<Se3Model>(a, lanes, stream);
-        default: return launch_sim_lanes<LinkedModel>(a, lanes, stream);
+        default:
+            /* most arms fit the small instantiation (dof <= 8, <= 9 links): half-size normal equations and frame buffers */
+            if (h->robot.dof <= LinkedModelSmall::DOF && h->robot.num_links <= LinkedModelSmall::LINKS) return launch_sim_lanes<LinkedModelSmall>(a, lanes, stream);
+            return launch_sim_lanes<LinkedModel>(a, lanes, stream);
     }
 }
 
