@@ -108,6 +108,18 @@ def linked_mixed_joints():
                 seed=32, boxes=boxes)
 
 
+def linked_ten_joints():
+    """a 10-DoF arm: more than 8 degrees of freedom, so the product runs the full-capacity linked instantiation (16 / 17)"""
+    env, boxes = _arm_environment()
+    robot = scenarios.linked_arm(num_joints=10, link_length=0.2, points_per_link=8)
+    n = 36
+    q0 = np.array([0.05, 0.02, -0.03, 0.04, 0.0, 0.02, 0.0, 0.01, -0.02, 0.0])
+    q1 = np.array([0.1, 0.35, 0.0, 0.3, 0.1, 0.2, 0.0, 0.15, -0.1, 0.05])
+    params = abi.make_sim_params(40, 0.01, env.resolution, allow_contacts=True)
+    return dict(name="linked_ten_joints", env=env, robot=robot, starts=np.tile(q0, (n, 1)), targets=q1[None, :], params=params,
+                seed=37, boxes=boxes)
+
+
 GOLDEN_SIM_CASES = {
     "se2_contact": se2_contact,
     "se2_no_contacts_allowed": se2_no_contacts_allowed,
@@ -120,6 +132,7 @@ GOLDEN_SIM_CASES = {
     "se3_large_rotation": se3_large_rotation,
     "linked_contact": linked_contact,
     "linked_mixed_joints": linked_mixed_joints,
+    "linked_ten_joints": linked_ten_joints,
 }
 
 
