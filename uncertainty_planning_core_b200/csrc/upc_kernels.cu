@@ -19,6 +19,12 @@ namespace upc
 #endif
 constexpr int kBlock = UPC_SIM_BLOCK;
 /* 3 CTAs of 128 threads per SM (<= 168 registers): measured best on B200 for the latency-bound per-particle program */
+#ifndef UPC_SIM_MIN_BLOCKS_SMALL_LINKED
+#define UPC_SIM_MIN_BLOCKS_SMALL_LINKED 3
+#endif
+#ifndef UPC_SIM_MIN_BLOCKS_ONE_LANE
+#define UPC_SIM_MIN_BLOCKS_ONE_LANE 2
+#endif
 #ifndef UPC_SIM_MIN_BLOCKS
 #define UPC_SIM_MIN_BLOCKS 3
 #endif
@@ -52,7 +58,8 @@ __host__ __device__ constexpr int frame_buffer_doubles()
 template <class M, int G>
 constexpr int sim_min_blocks()
 {
-    return (G == 1 && M::DOF > 3) ? 2 : UPC_SIM_MIN_BLOCKS;
+    if (G == 1 && M::HAS_FRAMES && M::DOF <= 8) return UPC_SIM_MIN_BLOCKS_SMALL_LINKED; /* 3.9 KB of stack per thread: three CTAs again (C3 28.5 -> 25.9 ms) */
+    return (G == 1 && M::DOF > 3) ? UPC_SIM_MIN_BLOCKS_ONE_LANE : UPC_SIM_MIN_BLOCKS;
 }
 
 template <class M, int G>
