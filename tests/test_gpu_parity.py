@@ -303,6 +303,30 @@ def test_nearest_neighbors_match_oracle(oracle, simulators):
         assert (gi == -1).all() and np.isinf(gd).all()
 
 
+def test_edge_batch_equals_edge_by_edge(oracle, simulators):
+    """BASELINE config 5 in small: a batch of edges simulated and clustered in one call each gives, edge for edge, what separate
+    calls give (particles and particle sets are independent) - and what the oracle gives"""
+    from uncertainty_planning_core_b200 import OutcomeClustering, scenarios
+    sc = scenarios.c5_batch(edges=12, particles=96, num_steps=40)
+    E, P = 12, 96
+    sim = simulators("c5_small", sc["env"], sc["robot"])
+    tape = abi.fill_noise_tape(sc["seed"], sc["robot"], sc["params"], E * P)
+    cfg, coll = sim.ForwardSimulateEdgeBatch(sc["starts"][::P], sc["targets"][::P], P, tape, sc["params"])
+    assert coll.any() and not coll.all()
+    oc = OutcomeClustering(sim, abi.FEATURE_CRS, 0.125, 0.1)
+    labels, ncl = oc.ClusterIndices(cfg.reshape(E * P, -1), n_sets=E)
+    for e in range(E):
+        sl = slice(e * P, (e + 1) * P)
+        one_cfg, one_coll = sim.ForwardSimulateRobots(sc["starts"][sl], sc["targets"][sl][:1], np.ascontiguousarray(tape[..., sl]), sc["params"])
+        assert np.array_equal(one_cfg, cfg[e]) and np.array_equal(one_coll, coll[e])
+        one_labels, one_ncl = oc.ClusterIndices(one_cfg)
+        assert np.array_equal(one_labels, labels[sl]) and one_ncl[0] == ncl[e]
+        ocfg, ocoll, _ = oracle.forward_simulate(sc["env"], sc["robot"], sc["params"], sc["starts"][sl], sc["targets"][sl], np.ascontiguousarray(tape[..., sl]))
+        assert np.array_equal(ocfg, cfg[e]) and np.array_equal(ocoll, coll[e])
+        ol, on, _ = oracle.cluster_particles(sc["env"], sc["robot"], oc.params, ocfg)
+        assert np.array_equal(ol, labels[sl]) and on[0] == ncl[e]
+
+
 def test_count_within_and_reverse_edge_probability(oracle, simulators):
     """next row 8f-2: counts are bit-exact against the oracle's distances (<= threshold, uncertainty_contact_planning.hpp:2083)"""
     for make in (cases.se2_contact, cases.se3_contact, cases.linked_contact):

@@ -95,6 +95,20 @@ class B200Simulator:
                                                  collided.ctypes.data))
         return np.ascontiguousarray(out.T), collided.astype(bool)
 
+    def ForwardSimulateEdgeBatch(self, edge_starts, edge_targets, particles_per_edge, noise_tape, params):
+        """A batch of candidate edges in ONE call (BASELINE config 5): edge e contributes `particles_per_edge` particles that
+        start at edge_starts[e] and move towards edge_targets[e] - the targets.size() == starts.size() form of
+        ForwardSimulateRobots (simple_simulator_interface.hpp:623; used at uncertainty_contact_planning.hpp:1826).
+        noise_tape covers E * particles_per_edge particles, edge-major.  Returns (configs [E, P, C], collided [E, P]);
+        particles are independent, so the result equals E separate calls with the matching tape columns."""
+        es = np.asarray(edge_starts, dtype=np.float64).reshape(-1, self.robot.width)
+        et = np.asarray(edge_targets, dtype=np.float64).reshape(-1, self.robot.width)
+        if es.shape != et.shape:
+            raise ValueError("one target per start")
+        E, P = es.shape[0], int(particles_per_edge)
+        cfg, coll = self.ForwardSimulateRobots(np.repeat(es, P, axis=0), np.repeat(et, P, axis=0), noise_tape, params)
+        return cfg.reshape(E, P, self.robot.width), coll.reshape(E, P)
+
     def CountWithin(self, configs, targets, threshold):
         """How many configurations lie within `threshold` (<=) of their target, and which: the count behind
         ComputeReverseEdgeProbability / the goal-reached fraction (uncertainty_contact_planning.hpp:2079-2088)."""
