@@ -596,14 +596,6 @@ UPC_D bool cull_certainly_clear(const DevEnv& env, const CullFrame& f, const Cor
     return ldg(env.cellmin + idx) > f.clear_above;
 }
 
-/* bits j < 32 with first + j * stride < lim */
-UPC_D unsigned valid_point_mask(int first, int lim, int stride)
-{
-    if (first >= lim) return 0u;
-    const int count = (lim - first + stride - 1) / stride;
-    return (count >= 32) ? 0xffffffffu : ((1u << count) - 1u);
-}
-
 UPC_D int lowest_bit(unsigned m)
 {
 #if defined(__CUDA_ARCH__)
