@@ -51,15 +51,17 @@ __host__ __device__ constexpr int frame_buffer_doubles()
     else return 2;
 }
 
-/* CTAs per SM the register budget is cut for.  One lane per particle is the big-batch mapping: the batch never fits one wave
- * anyway, and for the SE(3) and linked programs 255 registers with two CTAs per SM beat 168 with three (fewer spills, and the
- * resident threads' local-memory footprint - link frames, call frames - stays closer to what L2 holds): C3 42.9 -> 39.1 ms,
- * 10^6 SE(3) particles 1.52e9 -> 1.66e9 particle-steps/s.  The SE(2) program is small and prefers three. */
+/* CTAs per SM the register budget is cut for: three (168 registers) everywhere except the one-lane program of big linked
+ * robots (dof > 8 or > 9 links), whose 8.7 KB of link frames and call frames per thread favour 255 registers and two CTAs
+ * (fewer spills, smaller resident local-memory footprint).  The one-lane SE(3) program also ran with two CTAs while its point
+ * loops kept 4 - 8 lookups in flight; with the leaner loops (upc_sim.cuh, kCheckInFlight) three win: 10^6 SE(3) particles
+ * 2.09e9 -> 2.27e9 particle-steps/s. */
 template <class M, int G>
 constexpr int sim_min_blocks()
 {
-    if (G == 1 && M::HAS_FRAMES && M::DOF <= 8) return UPC_SIM_MIN_BLOCKS_SMALL_LINKED; /* 3.9 KB of stack per thread: three CTAs again (C3 28.5 -> 25.9 ms) */
-    return (G == 1 && M::DOF > 3) ? UPC_SIM_MIN_BLOCKS_ONE_LANE : UPC_SIM_MIN_BLOCKS;
+    if (G == 1 && M::HAS_FRAMES && M::DOF > 8) return UPC_SIM_MIN_BLOCKS_ONE_LANE;
+    if (G == 1 && M::HAS_FRAMES) return UPC_SIM_MIN_BLOCKS_SMALL_LINKED; /* 3.9 KB of stack per thread (C3 28.5 -> 25.9 ms with three) */
+    return UPC_SIM_MIN_BLOCKS;
 }
 
 template <class M, int G>

@@ -84,6 +84,32 @@ struct Group
     }
 };
 
+/*
+ * Independent SDF lookups a lane keeps in flight per trip of its point loops.  More lookups hide more load latency but
+ * cost registers, and this program is register-bound (168 registers with three CTAs per SM and still spilling), while
+ * 91 % of the lookups hit L1: measured on C2 (4 lanes), 4 / 2 / 8 (exact check / resolver points / pre-cull) ran 2.43 ms,
+ * 1 / 1 / 8 2.15 ms, 1 / 1 / 4 2.10 ms, 4 / 4 / 8 3.22 ms (profiles/README.md).
+ */
+#ifndef UPC_CHECK_INFLIGHT
+#define UPC_CHECK_INFLIGHT 1
+#endif
+#ifndef UPC_RES_INFLIGHT
+#define UPC_RES_INFLIGHT 1
+#endif
+/* unroll factor of the conservative-test loops of the plain-grid path (grids too big for the corner-cell table) */
+#ifndef UPC_PLAIN_UNROLL
+#define UPC_PLAIN_UNROLL 1
+#endif
+#if UPC_PLAIN_UNROLL == 1
+#define UPC_PLAIN_UNROLL_PRAGMA _Pragma("unroll 1")
+#elif UPC_PLAIN_UNROLL == 2
+#define UPC_PLAIN_UNROLL_PRAGMA _Pragma("unroll 2")
+#else
+#define UPC_PLAIN_UNROLL_PRAGMA _Pragma("unroll 4")
+#endif
+constexpr int kCheckInFlight = UPC_CHECK_INFLIGHT;
+constexpr int kResolverInFlight = UPC_RES_INFLIGHT;
+
 struct LocalCounters
 {
     unsigned int particle_steps, resolver_iterations, failed_resolves;
@@ -124,7 +150,7 @@ UPC_D void refresh_frames(const DevRobot& r, M& m, const Group<G>& g)
  * Collision check of the current configuration.  Per link, each lane first runs the cheap conservative test
  * (one cell-minimum load) over all of its points - independent iterations, so the loads of several points are in
  * flight together - and records the undecided ones in a bit mask; only those get the exact trilinear evaluation,
- * two at a time.  The result (an OR over points) does not depend on the order.
+ * kCheckInFlight at a time.  The result (an OR over points) does not depend on the order.
  */
 template <class M, int G>
 UPC_D bool check_collision(const DevEnv& env, const DevRobot& r, const M& m, const Group<G>& g, const double* pts, double threshold)
@@ -146,7 +172,7 @@ UPC_D bool check_collision(const DevEnv& env, const DevRobot& r, const M& m, con
             if ((r.cull_delta > 0.0f) && (end - beg >= 8 * G))
             {
                 /* enough points per lane for full batches: single-precision pre-cull against the 4-byte cell minimum
-                 * first (eight lookups in flight), exact FP64 evaluation of the undecided points only */
+                 * first (UPC_CULL_INFLIGHT lookups in flight), exact FP64 evaluation of the undecided points only */
                 const CullFrame cf = cull_frame(env, V, r.cull_delta, clear_above);
                 const Corner4* ptsf = reinterpret_cast<const Corner4*>(pts + 4 * r.num_points);
                 for (int chunk = beg; chunk < end; chunk += 32 * G)
@@ -156,10 +182,10 @@ UPC_D bool check_collision(const DevEnv& env, const DevRobot& r, const M& m, con
                     unsigned undecided = cull_undecided(env, cf, ptsf, first, lim, G);
                     while (undecided)
                     {
-                        int kk[4];
+                        int kk[kCheckInFlight];
                         int valid = 0;
 #pragma unroll
-                        for (int q = 0; q < 4; q++)
+                        for (int q = 0; q < kCheckInFlight; q++)
                         {
                             if (undecided)
                             {
@@ -172,23 +198,23 @@ UPC_D bool check_collision(const DevEnv& env, const DevRobot& r, const M& m, con
                                 kk[q] = kk[0]; /* padding repeats a valid point and is ignored below */
                             }
                         }
-                        CellRef c[4];
-                        Corner4 ca[4], cb[4];
+                        CellRef c[kCheckInFlight];
+                        Corner4 ca[kCheckInFlight], cb[kCheckInFlight];
 #pragma unroll
-                        for (int q = 0; q < 4; q++)
+                        for (int q = 0; q < kCheckInFlight; q++)
                         {
                             double u[3];
                             xf_point(V, pts[4 * kk[q] + 0], pts[4 * kk[q] + 1], pts[4 * kk[q] + 2], u);
                             c[q] = cell_locate(env, u);
                         }
 #pragma unroll
-                        for (int q = 0; q < 4; q++)
+                        for (int q = 0; q < kCheckInFlight; q++)
                         {
                             ca[q] = ldg4(c[q].cell);
                             cb[q] = ldg4(c[q].cell + 4);
                         }
 #pragma unroll
-                        for (int q = 0; q < 4; q++)
+                        for (int q = 0; q < kCheckInFlight; q++)
                             if (q < valid) hit |= cell_below(env, c[q], ca[q], cb[q], pts[4 * kk[q] + 3], threshold, clear_above);
                     }
                 }
@@ -230,7 +256,7 @@ UPC_D bool check_collision(const DevEnv& env, const DevRobot& r, const M& m, con
             const int first = chunk + g.sub;
             const int lim = (end < chunk + 32 * G) ? end : (chunk + 32 * G);
             unsigned undecided = 0u;
-#pragma unroll 4
+UPC_PLAIN_UNROLL_PRAGMA
             for (int j = 0; j < 32; j++)
             {
                 const int k = first + j * G;
@@ -351,14 +377,14 @@ UPC_DNI int resolver_correction(const DevEnv& env, const DevRobot& r, const DevS
             unsigned undecided = 0u;
             if (env.cells != nullptr)
             {
-                /* corner-cell table: phases A and B in one pass over the lane's points, two lookups in flight per trip */
+                /* corner-cell table: phases A and B in one pass over the lane's points, kResolverInFlight lookups in flight per trip */
                 const float clear_above = float_round_up((r.link_radius[l] + resolve_distance) + UPC_CULL_MARGIN);
-                for (int j0 = 0; j0 < 32 && (first + j0 * G) < lim; j0 += 2)
+                for (int j0 = 0; j0 < 32 && (first + j0 * G) < lim; j0 += kResolverInFlight)
                 {
-                    CellRef c[2];
-                    Corner4 ca[2], cb[2];
+                    CellRef c[kResolverInFlight];
+                    Corner4 ca[kResolverInFlight], cb[kResolverInFlight];
 #pragma unroll
-                    for (int jj = 0; jj < 2; jj++)
+                    for (int jj = 0; jj < kResolverInFlight; jj++)
                     {
                         int k = first + (j0 + jj) * G;
                         if (k >= lim) k = first; /* padding lanes of the last trip repeat a valid point and are ignored below */
@@ -367,13 +393,13 @@ UPC_DNI int resolver_correction(const DevEnv& env, const DevRobot& r, const DevS
                         c[jj] = cell_locate(env, u);
                     }
 #pragma unroll
-                    for (int jj = 0; jj < 2; jj++)
+                    for (int jj = 0; jj < kResolverInFlight; jj++)
                     {
                         ca[jj] = ldg4(c[jj].cell);
                         cb[jj] = ldg4(c[jj].cell + 4);
                     }
 #pragma unroll
-                    for (int jj = 0; jj < 2; jj++)
+                    for (int jj = 0; jj < kResolverInFlight; jj++)
                     {
                         const int j = j0 + jj;
                         const int k = first + j * G;
@@ -403,7 +429,7 @@ UPC_DNI int resolver_correction(const DevEnv& env, const DevRobot& r, const DevS
             else
             {
                 /* phase A */
-#pragma unroll 4
+UPC_PLAIN_UNROLL_PRAGMA
                 for (int j = 0; j < 32; j++)
                 {
                     const int k = first + j * G;
