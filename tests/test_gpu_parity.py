@@ -197,7 +197,7 @@ def test_sensor_slot_is_not_read_for_noise_free_sensors(oracle):
 
 
 def test_single_precision_pre_cull_changes_nothing(oracle):
-    """the float pre-cull of the collision check is a shortcut only - results with it (default, used when
+    """the float pre-cull of the collision check and of the resolver's point pass is a shortcut only - results with it (default, used when
     a lane holds >= 8 points of a link) and without it are the oracle's, bit for bit; the C2-shaped case has 128 points"""
     from uncertainty_planning_core_b200 import B200Simulator, scenarios
     sc = scenarios.c2_se3(seed=5, n=96, num_steps=48, shape=(64, 64, 64), resolution=0.0625)
@@ -212,7 +212,9 @@ def test_single_precision_pre_cull_changes_nothing(oracle):
             sim = B200Simulator(sc["env"], sc["robot"])
         finally:
             os.environ.pop("UPC_B200_NO_FP32_CULL", None)
-        for lanes in (1, 4, 5, 16):       # 128, 32, 26 and 8 points per lane: all take the pre-cull when it is on
+        # 128 .. 8 points per lane: all take the pre-cull in the collision check when it is on; 2..8 lanes also in the
+        # resolver's point pass (mask-then-evaluate, upc_sim.cuh)
+        for lanes in (1, 2, 3, 4, 5, 6, 8, 16):
             sim.SetLanesPerParticle(lanes)
             cfg, coll = sim.ForwardSimulateRobots(sc["starts"], sc["targets"], tape, sc["params"])
             assert np.array_equal(coll, ocoll) and max_ulp_diff(cfg, ocfg) <= CONFIG_ULP_TOLERANCE
