@@ -22,10 +22,19 @@ using std::min;
 
 #if defined(__CUDACC__)
 #define UPC_D __host__ __device__ __forceinline__
+#ifdef UPC_ALL_INLINE
+#define UPC_DNI __host__ __device__ __forceinline__
+#else
 #define UPC_DNI inline __host__ __device__ __noinline__
+#endif
 #else
 #define UPC_D inline
 #define UPC_DNI inline
+#endif
+#ifndef UPC_SOLVE_OUT_OF_LINE
+#define UPC_SOLVE_LINKAGE UPC_D
+#else
+#define UPC_SOLVE_LINKAGE UPC_DNI
 #endif
 
 namespace upc
@@ -749,7 +758,7 @@ UPC_D double sdf_distance_gradient(const DevEnv& env, const double* u, double* g
 /* ------------------------------------------------------------------ damped normal equations */
 
 template <int N>
-UPC_DNI void solve_damped(double (&H)[N][N], const double* g, double lambda, double* x, int n)
+UPC_SOLVE_LINKAGE void solve_damped(double (&H)[N][N], const double* g, double lambda, double* x, int n)
 {
     /* (H + lambda I) x = g by an LDL^T factorisation without square roots: unit-lower L in the strict lower
      * triangle of H (the upper triangle holds the input), reciprocal pivots in rd[] - one division per column. */

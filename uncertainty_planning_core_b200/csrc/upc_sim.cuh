@@ -111,6 +111,23 @@ struct Group
 #ifndef UPC_RES_PRECULL
 #define UPC_RES_PRECULL 1
 #endif
+/*
+ * Linkage of the big helpers.  They used to be out-of-line calls (one copy of the code, smaller loop body); every call then
+ * saves and restores the caller's registers through local memory and passes the model through memory.  Inlined, the
+ * SE(3) program drops from 508 to ~ 250 B of spills and a 1.8 to a 1.2 KB stack frame: C2 2.03 -> 1.85 ms, C1 0.416 -> 0.360 ms,
+ * C3 23.0 -> 19.3 ms (profiles/README.md).  -DUPC_RESOLVER_OUT_OF_LINE / -DUPC_ESTIMATE_OUT_OF_LINE / -DUPC_SOLVE_OUT_OF_LINE
+ * bring the calls back.
+ */
+#ifndef UPC_RESOLVER_OUT_OF_LINE
+#define UPC_RESOLVER_LINKAGE UPC_D
+#else
+#define UPC_RESOLVER_LINKAGE UPC_DNI
+#endif
+#ifndef UPC_ESTIMATE_OUT_OF_LINE
+#define UPC_ESTIMATE_LINKAGE UPC_D
+#else
+#define UPC_ESTIMATE_LINKAGE UPC_DNI
+#endif
 constexpr int kCheckInFlight = UPC_CHECK_INFLIGHT;
 constexpr int kResolverInFlight = UPC_RES_INFLIGHT;
 
@@ -309,7 +326,7 @@ UPC_PLAIN_UNROLL_PRAGMA
 
 /* EstimateMaxControlInputWorkspaceMotion: largest body-point displacement caused by a noise-free input */
 template <class M, int G>
-UPC_DNI double estimate_motion(const DevRobot& r, const M& m, const Group<G>& g, const double* pts, const double* input, double* scratch_frames)
+UPC_ESTIMATE_LINKAGE double estimate_motion(const DevRobot& r, const M& m, const Group<G>& g, const double* pts, const double* input, double* scratch_frames)
 {
     M moved = m;
     if constexpr (M::HAS_FRAMES) moved.frames = scratch_frames;
@@ -347,11 +364,11 @@ UPC_DNI double estimate_motion(const DevRobot& r, const M& m, const Group<G>& g,
  *            the sequential oracle, whatever the number of lanes.
  */
 template <class M, int G, bool INDIVIDUAL>
-UPC_DNI int resolver_correction(const DevEnv& env, const DevRobot& r, const DevSim& sp, const M& m_in, const Group<G>& g,
+UPC_RESOLVER_LINKAGE int resolver_correction(const DevEnv& env, const DevRobot& r, const DevSim& sp, const M& m_in, const Group<G>& g,
                               const double* pts, double* x, LocalCounters& cnt)
 {
     const double resolve_distance = sp.resolve_distance;
-    const M m = m_in; /* private copy: the caller's model sits in memory (passed by reference to an out-of-line function) */
+    const M m = m_in; /* private copy (when the function is compiled out of line the caller's model sits in memory) */
     UPC_T0
     constexpr int N = M::DOF;
     const int n = m.dof(r);
