@@ -30,6 +30,9 @@ constexpr int kBlock = UPC_SIM_BLOCK;
 #ifndef UPC_SIM_MIN_BLOCKS
 #define UPC_SIM_MIN_BLOCKS 3
 #endif
+#ifndef UPC_SIM_MIN_BLOCKS_SE2_ONE_LANE
+#define UPC_SIM_MIN_BLOCKS_SE2_ONE_LANE 4
+#endif
 
 struct SimArgs
 {
@@ -53,7 +56,8 @@ __host__ __device__ constexpr int frame_buffer_doubles()
     else return 2;
 }
 
-/* CTAs per SM the register budget is cut for: three (168 registers) everywhere except the one-lane program of big linked
+/* CTAs per SM the register budget is cut for: three (168 registers) everywhere except the one-lane SE(2) program (four: with
+ * more lanes per particle - the latency-bound small batches - SE(2) also prefers three, C1 -6 % with four) and the one-lane program of big linked
  * robots (dof > 8 or > 9 links), whose 8.7 KB of link frames and call frames per thread favour 255 registers and two CTAs
  * (fewer spills, smaller resident local-memory footprint).  The one-lane SE(3) program also ran with two CTAs while its point
  * loops kept 4 - 8 lookups in flight; with the leaner loops (upc_sim.cuh, kCheckInFlight) three win: 10^6 SE(3) particles
@@ -62,6 +66,7 @@ template <class M, int G>
 constexpr int sim_min_blocks()
 {
     if (G == 1 && M::HAS_FRAMES && M::DOF > 8) return UPC_SIM_MIN_BLOCKS_ONE_LANE;
+    if (G == 1 && !M::HAS_FRAMES && M::DOF == 3) return UPC_SIM_MIN_BLOCKS_SE2_ONE_LANE; /* small program: 128 registers, four CTAs (C5 +3 %) */
     if (G == 1 && M::HAS_FRAMES) return UPC_SIM_MIN_BLOCKS_SMALL_LINKED; /* 3.9 KB of stack per thread (C3 28.5 -> 25.9 ms with three) */
     return UPC_SIM_MIN_BLOCKS;
 }

@@ -111,6 +111,9 @@ struct Group
 #ifndef UPC_RES_PRECULL
 #define UPC_RES_PRECULL 1
 #endif
+#ifndef UPC_RES_PRECULL_MIN_LANES
+#define UPC_RES_PRECULL_MIN_LANES 2
+#endif
 /*
  * Linkage of the big helpers.  They used to be out-of-line calls (one copy of the code, smaller loop body); every call then
  * saves and restores the caller's registers through local memory and passes the model through memory.  Inlined, the
@@ -401,7 +404,7 @@ UPC_RESOLVER_LINKAGE int resolver_correction(const DevEnv& env, const DevRobot& 
                 /* corner-cell table: phases A and B in one pass over the lane's points, kResolverInFlight lookups in flight per trip */
                 const float clear_above = float_round_up((r.link_radius[l] + resolve_distance) + UPC_CULL_MARGIN);
                 bool culled_pass = false;
-                if constexpr (UPC_RES_PRECULL && G >= 2 && G <= 8)
+                if constexpr (UPC_RES_PRECULL && G >= UPC_RES_PRECULL_MIN_LANES && G <= 8)
                 if ((r.cull_delta > 0.0f) && (end - beg >= 8 * G))
                 {
                     culled_pass = true;
