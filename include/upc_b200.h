@@ -149,7 +149,8 @@ typedef struct upc_cluster_params
     /* POINT_TO_POINT_MOVEMENT only (uncertainty_contact_planning.hpp:1801-1863) */
     double goal_distance_threshold;
     const upc_sim_params* ptpm_sim;
-    const double* ptpm_tape; /* tape for the n*(n-1) pair simulations, same layout as upc_forward_simulate */
+    const double* ptpm_tape; /* tape for the n*(n-1) pair simulations, same layout as upc_forward_simulate; NULL = seeded noise */
+    uint64_t ptpm_seed;      /* seeded noise of the pair simulations (pair simulation k is particle k of the stream) */
 } upc_cluster_params;
 
 /* counters surfaced through GetStatistics() */
@@ -191,6 +192,7 @@ int32_t upc_host_free(void* ptr);
 
 /*
  * Batched forward simulation. starts: [C][n]; targets: [C][n_targets] with n_targets == 1 or n;
+ * (n_targets may also be any divisor of n: one target per block of n / n_targets consecutive particles)
  * tape: [num_steps][1 + max_microsteps][dof][n] pre-truncated draws (slot 0 of each step = sensor draws in
  * [-max_sensor_noise, +max_sensor_noise]; slots 1.. = actuator draws in [-1, 1]); out_configs: [C][n];
  * out_collided: n bytes, 1 iff the particle touched the environment during the edge.
@@ -204,6 +206,50 @@ int32_t upc_forward_simulate(upc_handle* h, const upc_sim_params* params, int64_
 int32_t upc_forward_simulate_device(upc_handle* h, const upc_sim_params* params, int64_t n, const double* d_starts,
                                     int64_t n_targets, const double* d_targets, const double* d_tape,
                                     double* d_out_configs, uint8_t* d_out_collided, void* stream);
+
+/*
+ * Seeded forms: no tape crosses the boundary.  Draw (particle first_particle + i, controller interval,
+ * slot, axis) is a pure function of `seed` - Philox-4x32-10 bits through the inverse CDF of the normal distribution truncated
+ * to +-2 sigma - evaluated inside the kernel; this replaces the per-thread generators of
+ * uncertainty_contact_planning.hpp:343-356 and the draws of simple_uncertainty_models.hpp:38-45, 77-88.  Results do not
+ * depend on batch size, lane count or GPU count: keying is by global particle index.
+ * starts: [C][n_starts], targets: [C][n_targets]; n_starts and n_targets must each divide n, and particle i uses entry
+ * i / (n / n_x) - one entry per particle (n_x == n), one per edge of an edge batch, or a single one (n_x == 1).
+ */
+int32_t upc_forward_simulate_seeded(upc_handle* h, const upc_sim_params* params, uint64_t seed, int64_t first_particle, int64_t n,
+                                    int64_t n_starts, const double* starts, int64_t n_targets, const double* targets, double* out_configs,
+                                    uint8_t* out_collided);
+int32_t upc_forward_simulate_seeded_device(upc_handle* h, const upc_sim_params* params, uint64_t seed, int64_t first_particle, int64_t n,
+                                           int64_t n_starts, const double* d_starts, int64_t n_targets, const double* d_targets,
+                                           double* d_out_configs, uint8_t* d_out_collided, void* stream);
+/* the same draws written out as a tape (host memory, layout of upc_forward_simulate): replaying it reproduces the seeded results bit for bit */
+int32_t upc_fill_noise_tape_seeded(uint64_t seed, const upc_robot_desc* robot, const upc_sim_params* params, int64_t first_particle,
+                                   int64_t n, int64_t tape_stride, double* tape);
+
+/*
+ * Traced simulation of a small batch: ForwardSimulateRobot / ForwardSimulateMutableRobot with enable_tracing
+ * (simple_simulator_interface.hpp:619-621; trace types :40-63; consumer ExtractTrajectoryFromTrace :66-86, used at
+ * uncertainty_contact_planning.hpp:510 and :1171).  tape == NULL selects seeded noise (seed, first_particle).
+ *   trace_configs  [num_steps][C][n]      resolved configuration at the end of every controller interval
+ *   trace_controls [num_steps][2*dof][n]  control input (velocity command) and the control step applied per microstep
+ *   trace_steps    [2][n]                 controller intervals executed (early exit: < num_steps), microsteps of the last one
+ * Host pointers; synchronises.
+ */
+int32_t upc_forward_simulate_traced(upc_handle* h, const upc_sim_params* params, int64_t n, const double* starts, int64_t n_targets,
+                                    const double* targets, const double* tape, uint64_t seed, int64_t first_particle, double* out_configs,
+                                    uint8_t* out_collided, double* trace_configs, double* trace_controls, int32_t* trace_steps);
+
+/*
+ * The planner-batch step in ONE call (BASELINE config 5): n_edges candidate edges x particles_per_edge particles simulated with
+ * seeded noise (uncertainty_contact_planning.hpp:2039-2071 for every edge) and the outcome of every edge clustered (:1986-2034),
+ * outcomes staying in device memory in between.  edge_starts / edge_targets: [C][n_edges]; out_configs [C][n], out_collided [n],
+ * out_labels [n] (cluster of the particle within its edge), out_n_clusters [n_edges]; n = n_edges * particles_per_edge,
+ * particles edge-major.  Host pointers; synchronises.
+ */
+int32_t upc_simulate_and_cluster_edges(upc_handle* h, const upc_sim_params* params, const upc_cluster_params* cparams, uint64_t seed,
+                                       int64_t first_particle, int64_t n_edges, int64_t particles_per_edge, const double* edge_starts,
+                                       const double* edge_targets, double* out_configs, uint8_t* out_collided, int32_t* out_labels,
+                                       int32_t* out_n_clusters);
 
 /* CheckConfigCollision: 1 iff any body point of `config` has sdf - radius < contact_distance + inflation */
 int32_t upc_check_config_collision(upc_handle* h, const double* config, double contact_distance, double inflation,
@@ -278,6 +324,56 @@ int32_t upc_measure_fp64_tflops(upc_handle* h, double* out_tflops);
 
 /* blocks until everything queued on the handle's stream has finished */
 int32_t upc_synchronize(upc_handle* h);
+
+/*
+ * Multi-GPU (BASELINE north_star: "the batch of candidate RRT edges or particles is sharded with the SDF
+ * replicated on every GPU and a single NCCL gather of outcome clusters").  Every rank owns a complete handle (its own copy of
+ * the environment and robot); a upc_comm ties the handles of one box together through NCCL (bound at run time).
+ *   one process per GPU:   rank 0 calls upc_comm_get_unique_id, ships the 128 bytes to the other ranks by any means, every
+ *                          rank calls upc_comm_create(handle, world, rank, id)
+ *   one process, n GPUs:   upc_comm_create_all(n, handles, comms); bracket per-rank calls with upc_comm_group_start / _end
+ */
+typedef struct upc_comm upc_comm;
+#define UPC_COMM_ID_BYTES 128
+int32_t upc_comm_get_unique_id(uint8_t* id128);
+int32_t upc_comm_create(upc_handle* h, int32_t world, int32_t rank, const uint8_t* id128, upc_comm** out);
+int32_t upc_comm_create_all(int32_t n, upc_handle* const* handles, upc_comm** out);
+int32_t upc_comm_destroy(upc_comm* c);
+int32_t upc_comm_world(const upc_comm* c);
+int32_t upc_comm_rank(const upc_comm* c);
+int32_t upc_comm_nccl_version(int32_t* out);
+int32_t upc_comm_group_start(void);
+int32_t upc_comm_group_end(void);
+/* contiguous, balanced [lo, hi) range of `total` items owned by `rank` */
+void upc_shard_bounds(int64_t total, int32_t rank, int32_t world, int64_t* lo, int64_t* hi);
+
+/* Outcome block of one rank inside the gather buffer (all offsets in bytes from the block start, 256-byte aligned):
+ * labels int32[particles] | n_clusters int32[sets] | collided uint8[particles] | configs double[C][n_local] (stride = the
+ * rank's own particle count).  `particles` / `sets` are the capacities, i.e. the largest shard. */
+typedef struct upc_outcome_layout
+{
+    int64_t particles, sets;
+    int64_t labels_offset, n_clusters_offset, collided_offset, configs_offset;
+    int64_t block_bytes;
+} upc_outcome_layout;
+int32_t upc_outcome_layout_for(int32_t width, int64_t particles, int64_t sets, upc_outcome_layout* out);
+
+/* In-place all-gather of the outcome blocks (rank r's block at d_blocks + r * block_bytes on every rank), ordered after the
+ * work queued on `stream` (NULL = the handle's stream) and executed on the communicator's own stream; `stream` does not wait
+ * for it - upc_comm_wait makes a stream wait, upc_comm_synchronize blocks the host. */
+int32_t upc_comm_all_gather_outcomes(upc_comm* c, void* d_blocks, int64_t block_bytes, void* stream);
+int32_t upc_comm_wait(upc_comm* c, void* stream);
+int32_t upc_comm_synchronize(upc_comm* c);
+
+/*
+ * One sharded planner-batch step: this rank simulates (seeded, keyed by global particle index) and clusters its contiguous
+ * block of the n_edges edges straight into its slot of d_blocks, then the single all-gather runs.  d_edge_starts /
+ * d_edge_targets: [C][n_edges] in device memory, replicated; d_blocks: world * block_bytes with the layout of
+ * upc_outcome_layout_for(width, ceil(n_edges / world) * particles_per_edge, ceil(n_edges / world)).  Asynchronous.
+ */
+int32_t upc_sharded_edge_batch(upc_comm* c, const upc_sim_params* params, const upc_cluster_params* cparams, uint64_t seed,
+                               int64_t n_edges, int64_t particles_per_edge, const double* d_edge_starts, const double* d_edge_targets,
+                               void* d_blocks, void* stream);
 
 #ifdef __cplusplus
 }

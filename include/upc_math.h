@@ -195,6 +195,66 @@ UPC_HD double upc_acos(double x)
     return upc_atan2(sn, x);
 }
 
+/* raw IEEE-754 bits of a double and back (memcpy semantics on the host, register moves on the device) */
+UPC_HD uint64_t upc_double_bits(double x)
+{
+#if defined(__CUDA_ARCH__)
+    return (uint64_t)__double_as_longlong(x);
+#else
+    uint64_t b;
+    __builtin_memcpy(&b, &x, sizeof(b));
+    return b;
+#endif
+}
+
+UPC_HD double upc_bits_double(uint64_t b)
+{
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)b);
+#else
+    double x;
+    __builtin_memcpy(&x, &b, sizeof(x));
+    return x;
+#endif
+}
+
+/*
+ * Natural logarithm of a positive, finite, normal double.  The classic argument reduction x = 2^k (1 + f) with
+ * sqrt(2)/2 < 1 + f < sqrt(2), s = f / (2 + f), and the degree-14 minimax polynomial in s (the published fdlibm form);
+ * only exact IEEE operations, one division, no fused operations - identical bits on host and device.
+ * Used by the counter-based noise generator, whose arguments lie in [0.0227, 0.075].
+ */
+UPC_HD double upc_log(double x)
+{
+    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+    const double LG1 = 6.666666666666735130e-01, LG2 = 3.999999999940941908e-01, LG3 = 2.857142874366239149e-01,
+                 LG4 = 2.222219843214978396e-01, LG5 = 1.818357216161805012e-01, LG6 = 1.531383769920937332e-01,
+                 LG7 = 1.479819860511658591e-01;
+    uint64_t bits = upc_double_bits(x);
+    int k = (int)((bits >> 52) & 0x7ffu) - 1023;
+    uint64_t mant = bits & 0x000fffffffffffffull;
+    /* mantissa above sqrt(2): halve it and bump the exponent */
+    if (mant >= 0x6a09e667f3bcdull)
+    {
+        k += 1;
+        bits = mant | 0x3fe0000000000000ull;
+    }
+    else
+    {
+        bits = mant | 0x3ff0000000000000ull;
+    }
+    const double f = upc_bits_double(bits) - 1.0;
+    const double dk = (double)k;
+    const double s = f / (2.0 + f);
+    const double z = s * s;
+    const double w = z * z;
+    const double t1 = w * (LG2 + w * (LG4 + w * LG6));
+    const double t2 = z * (LG1 + w * (LG3 + w * (LG5 + w * LG7)));
+    const double r = t2 + t1;
+    const double hfsq = (0.5 * f) * f;
+    return dk * LN2_HI - ((hfsq - (s * (hfsq + r) + dk * LN2_LO)) - f);
+}
+
 /* Angle wrap into (-pi, pi]; restates EigenHelpers::EnforceContinuousRevoluteBounds as used at
  * simple_robot_models.hpp:115 and :1083 (source un-vendored; this is the normative form here). */
 UPC_HD double upc_wrap_angle(double v)

@@ -58,6 +58,19 @@ def load():
     lib.oracle_nearest_neighbors.restype = i32
     lib.oracle_cluster_statistics.argtypes = [C.POINTER(abi.RobotDesc), i64, vp, vp, vp, i32, dp, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.oracle_cluster_statistics.restype = i32
+    lib.oracle_forward_simulate_traced.argtypes = [C.POINTER(abi.EnvDesc), C.POINTER(abi.RobotDesc), C.POINTER(abi.SimParams),
+                                                   i64, vp, i64, vp, vp, vp, vp, vp, vp, vp]
+    lib.oracle_forward_simulate_traced.restype = i32
+    lib.oracle_philox4x32_10.argtypes = [vp, vp, vp]
+    lib.oracle_philox4x32_10.restype = None
+    lib.oracle_normal_quantile.argtypes = [i64, vp, vp]
+    lib.oracle_normal_quantile.restype = None
+    lib.oracle_log.argtypes = [i64, vp, vp]
+    lib.oracle_log.restype = None
+    lib.oracle_standard_draws.argtypes = [C.c_uint64, i64, i64, C.c_uint32, C.c_uint32, C.c_uint32, vp]
+    lib.oracle_standard_draws.restype = None
+    lib.oracle_fill_noise_tape_counter.argtypes = [C.c_uint64, C.POINTER(abi.RobotDesc), C.POINTER(abi.SimParams), i64, i64, i64, vp]
+    lib.oracle_fill_noise_tape_counter.restype = i32
     for name in ("oracle_forward_simulate", "oracle_check_config_collision", "oracle_cluster_particles",
                  "oracle_pair_distances", "oracle_pair_distances_reference_style", "oracle_region_signatures",
                  "oracle_sdf_lookup", "oracle_complete_link"):
@@ -84,6 +97,41 @@ def load_ref_pid():
 def _check(code):
     if code != 0:
         raise RuntimeError("oracle error %d: %s" % (code, load().oracle_last_error().decode()))
+
+
+def philox4x32_10(key, counter):
+    k = np.ascontiguousarray(key, dtype=np.uint32)
+    c = np.ascontiguousarray(counter, dtype=np.uint32)
+    out = np.zeros(4, dtype=np.uint32)
+    load().oracle_philox4x32_10(k.ctypes.data, c.ctypes.data, out.ctypes.data)
+    return out
+
+
+def normal_quantile(p):
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    out = np.zeros_like(p)
+    load().oracle_normal_quantile(p.size, p.ctypes.data, out.ctypes.data)
+    return out
+
+
+def log(x):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.zeros_like(x)
+    load().oracle_log(x.size, x.ctypes.data, out.ctypes.data)
+    return out
+
+
+def standard_draws(seed, first, n, step, slot, axis):
+    out = np.zeros(n)
+    load().oracle_standard_draws(seed, first, n, step, slot, axis, out.ctypes.data)
+    return out
+
+
+def fill_noise_tape_counter(seed, robot, params, n, first_particle=0):
+    """The oracle's own restatement of the counter-based noise as a tape for oracle.forward_simulate."""
+    tape = np.zeros(abi.tape_shape(params, robot.dof, n), dtype=np.float64)
+    _check(load().oracle_fill_noise_tape_counter(seed, C.byref(robot.desc), C.byref(params), first_particle, n, n, tape.ctypes.data))
+    return tape
 
 
 def num_threads():
@@ -145,6 +193,25 @@ def forward_simulate(env, robot, params, starts, targets, tape):
                                           targets.shape[0], t_soa.ctypes.data, tape.ctypes.data, out.ctypes.data,
                                           coll.ctypes.data, C.byref(stats)))
     return np.ascontiguousarray(out.T), coll.astype(bool), stats.as_dict()
+
+
+def forward_simulate_traced(env, robot, params, starts, targets, tape):
+    """forward_simulate plus the per-interval record: dict(configs [S, n, C], controls [S, n, 2*dof], steps [2, n])"""
+    starts = np.asarray(starts, dtype=np.float64)
+    targets = np.asarray(targets, dtype=np.float64)
+    n, width = starts.shape
+    s_soa = np.ascontiguousarray(starts.T)
+    t_soa = np.ascontiguousarray(targets.T)
+    tape = np.ascontiguousarray(tape, dtype=np.float64)
+    out = np.zeros_like(s_soa)
+    coll = np.zeros(n, dtype=np.uint8)
+    S = params.num_steps
+    tc, tu, ts = np.zeros((S, width, n)), np.zeros((S, 2 * robot.dof, n)), np.zeros((2, n), dtype=np.int32)
+    _check(load().oracle_forward_simulate_traced(C.byref(env.desc), C.byref(robot.desc), C.byref(params), n, s_soa.ctypes.data, targets.shape[0],
+                                                 t_soa.ctypes.data, tape.ctypes.data, out.ctypes.data, coll.ctypes.data, tc.ctypes.data,
+                                                 tu.ctypes.data, ts.ctypes.data))
+    return np.ascontiguousarray(out.T), coll.astype(bool), dict(configs=np.ascontiguousarray(tc.transpose(0, 2, 1)),
+                                                                controls=np.ascontiguousarray(tu.transpose(0, 2, 1)), steps=ts)
 
 
 def check_config_collision(env, robot, config, contact_distance=0.0, inflation=0.0):

@@ -469,6 +469,7 @@ public:
         ResetPosition(zero);
     }
     int Dof() const { return 3; }
+    int Kind() const { return UPC_ROBOT_SE2; }
     int NumLinks() const { return 1; }
     const Mat34& LinkTransform(int) const { return pose_; }
     const PointSet& Points() const { return *points_; }
@@ -563,6 +564,7 @@ public:
         config_ = Identity34();
     }
     int Dof() const { return 6; }
+    int Kind() const { return UPC_ROBOT_SE3; }
     bool SensorNoiseFree() const { return sensor_noise_free_; }
     int NumLinks() const { return 1; }
     const Mat34& LinkTransform(int) const { return config_; }
@@ -709,6 +711,7 @@ public:
         UpdateTransforms();
     }
     int Dof() const { return dof_; }
+    int Kind() const { return UPC_ROBOT_LINKED; }
     bool sensor_noise_free_;
     bool SensorNoiseFree() const { return sensor_noise_free_; }
     int NumLinks() const { return (int)link_transforms_.size(); }
@@ -1026,9 +1029,17 @@ static int ComputeResolverCorrection(const Environment& env, const Robot& robot,
     return count;
 }
 
+/* per-interval record of one particle, the content of ForwardSimulationStepTrace (simple_simulator_interface.hpp:40-63): the
+ * resolved configuration at the end of every controller interval, its control input and per-microstep control step */
+struct ParticleTrace
+{
+    std::vector<std::vector<double>> configs, control_input, control_input_step;
+    int32_t last_microsteps = 0;
+};
+
 template <typename Robot>
 static bool SimulateParticle(const Environment& env, Robot& robot, const upc_sim_params& sp, const double* target,
-                             const double* tape, int64_t tape_stride, SimStats& stats)
+                             const double* tape, int64_t tape_stride, SimStats& stats, ParticleTrace* trace = nullptr)
 {
     /* tape element (step, slot, dof d) of this particle is tape[((step*(1+M)+slot)*dof + d) * tape_stride] */
     const int dof = robot.Dof();
@@ -1094,6 +1105,13 @@ static bool SimulateParticle(const Environment& env, Robot& robot, const upc_sim
             }
         }
         robot.GetPosition(cfg);
+        if (trace)
+        {
+            trace->configs.push_back(std::vector<double>(cfg, cfg + upc_config_width(robot.Kind(), dof)));
+            trace->control_input.push_back(std::vector<double>(u, u + dof));
+            trace->control_input_step.push_back(std::vector<double>(ustep, ustep + dof));
+            trace->last_microsteps = (int32_t)microsteps;
+        }
         if (robot.ComputeConfigurationDistance(cfg, target) < sp.simulation_shortcut_distance) break;
     }
     return collided;
@@ -1348,8 +1366,17 @@ static void ClusterOneSet(const Environment& env, const upc_robot_desc& rd, cons
     else if (cp.feature_type == UPC_FEATURE_POINT_TO_POINT_MOVEMENT)
     {
         /* :1801-1863: N^2-N simulations, (i->j) then (j->i) for i<j, allow_contacts = true */
-        if (!cp.ptpm_sim || !cp.ptpm_tape) throw std::invalid_argument("PTPM clustering needs sim params and a tape");
+        if (!cp.ptpm_sim) throw std::invalid_argument("PTPM clustering needs sim params (and a tape or a seed)");
         const int64_t sims = n * n - n;
+        /* no tape: pair simulation k is particle k of the counter-based stream of cp.ptpm_seed */
+        std::vector<double> seeded_tape;
+        const double* pair_tape = cp.ptpm_tape;
+        if (!pair_tape && sims > 0)
+        {
+            seeded_tape.resize((size_t)(upc_tape_doubles_per_particle(cp.ptpm_sim, rd.dof) * sims));
+            oracle_fill_noise_tape_counter(cp.ptpm_seed, &rd, cp.ptpm_sim, 0, sims, sims, seeded_tape.data());
+            pair_tape = seeded_tape.data();
+        }
         std::vector<double> starts((size_t)(width * sims)), targets((size_t)(width * sims)), results((size_t)(width * sims));
         std::vector<uint8_t> coll((size_t)sims);
         int64_t cur = 0;
@@ -1367,7 +1394,7 @@ static void ClusterOneSet(const Environment& env, const upc_robot_desc& rd, cons
             }
         upc_sim_params sp = *cp.ptpm_sim;
         sp.allow_contacts = 1;
-        ForwardSimulateRobots<Robot>(env, rd, sp, sims, starts.data(), sims, targets.data(), cp.ptpm_tape, results.data(),
+        ForwardSimulateRobots<Robot>(env, rd, sp, sims, starts.data(), sims, targets.data(), pair_tape, results.data(),
                                      coll.data(), nullptr);
         std::vector<double> D((size_t)(n * n), 0.0);
         cur = 0;
@@ -1719,6 +1746,66 @@ int32_t oracle_forward_simulate(const upc_env_desc* env_desc, const upc_robot_de
         case UPC_ROBOT_SE3: ForwardSimulateRobots<Se3Robot>(env, *robot, *params, n, starts, n_targets, targets, tape, out_configs, out_collided, stats); break;
         case UPC_ROBOT_LINKED: ForwardSimulateRobots<LinkedRobot>(env, *robot, *params, n, starts, n_targets, targets, tape, out_configs, out_collided, stats); break;
         default: throw std::invalid_argument("unknown robot kind");
+    }
+    return UPC_OK;
+    ORACLE_CATCH
+}
+
+extern "C++" {
+template <typename Robot>
+static void TracedImpl(const Environment& env, const upc_robot_desc& rd, const upc_sim_params& sp, int64_t n, const double* starts, int64_t n_targets,
+                       const double* targets, const double* tape, double* out_configs, uint8_t* out_collided, double* trace_configs,
+                       double* trace_controls, int32_t* trace_steps)
+{
+    const Robot prototype(rd);
+    const int width = upc_config_width(rd.kind, rd.dof), dof = rd.dof;
+    for (int64_t i = 0; i < n; i++)
+    {
+        Robot robot = prototype;
+        double start[16], target[16], result[16] = {0.0};
+        for (int c = 0; c < width; c++)
+        {
+            start[c] = starts[(int64_t)c * n + i];
+            target[c] = targets[(int64_t)c * n_targets + ((n_targets == 1) ? 0 : i)];
+        }
+        robot.ResetPosition(start);
+        SimStats st = {0, 0, 0, 0};
+        ParticleTrace tr;
+        const bool collided = SimulateParticle(env, robot, sp, target, tape + i, n, st, &tr);
+        robot.GetPosition(result);
+        for (int c = 0; c < width; c++) out_configs[(int64_t)c * n + i] = result[c];
+        out_collided[i] = collided ? 1 : 0;
+        for (size_t s = 0; s < tr.configs.size(); s++)
+        {
+            for (int c = 0; c < width; c++) trace_configs[((int64_t)s * width + c) * n + i] = tr.configs[s][(size_t)c];
+            for (int d = 0; d < dof; d++)
+            {
+                trace_controls[((int64_t)s * 2 * dof + d) * n + i] = tr.control_input[s][(size_t)d];
+                trace_controls[((int64_t)s * 2 * dof + dof + d) * n + i] = tr.control_input_step[s][(size_t)d];
+            }
+        }
+        trace_steps[i] = (int32_t)tr.configs.size();
+        trace_steps[n + i] = tr.last_microsteps;
+    }
+}
+}
+
+/* same outputs as upc_forward_simulate_traced: trace_configs [S][C][n], trace_controls [S][2*dof][n], trace_steps [2][n]; rows
+ * of intervals a particle did not execute are left untouched (pass zeroed buffers) */
+int32_t oracle_forward_simulate_traced(const upc_env_desc* env_desc, const upc_robot_desc* robot, const upc_sim_params* params, int64_t n,
+                                       const double* starts, int64_t n_targets, const double* targets, const double* tape, double* out_configs,
+                                       uint8_t* out_collided, double* trace_configs, double* trace_controls, int32_t* trace_steps)
+{
+    ORACLE_TRY
+    ValidateRobot(robot);
+    if (!env_desc || !params) throw std::invalid_argument("null argument");
+    if (!(n_targets == 1 || n_targets == n)) throw std::invalid_argument("targets must have size 1 or n");
+    const Environment env(*env_desc);
+    switch (robot->kind)
+    {
+        case UPC_ROBOT_SE2: TracedImpl<Se2Robot>(env, *robot, *params, n, starts, n_targets, targets, tape, out_configs, out_collided, trace_configs, trace_controls, trace_steps); break;
+        case UPC_ROBOT_SE3: TracedImpl<Se3Robot>(env, *robot, *params, n, starts, n_targets, targets, tape, out_configs, out_collided, trace_configs, trace_controls, trace_steps); break;
+        default: TracedImpl<LinkedRobot>(env, *robot, *params, n, starts, n_targets, targets, tape, out_configs, out_collided, trace_configs, trace_controls, trace_steps); break;
     }
     return UPC_OK;
     ORACLE_CATCH

@@ -103,6 +103,12 @@ void oracle_se3_exp(const double* twist6, double* cfg12);
 int32_t oracle_forward_simulate(const upc_env_desc* env, const upc_robot_desc* robot, const upc_sim_params* params,
                                 int64_t n, const double* starts, int64_t n_targets, const double* targets,
                                 const double* tape, double* out_configs, uint8_t* out_collided, upc_stats* stats);
+int32_t oracle_forward_simulate_traced(const upc_env_desc* env, const upc_robot_desc* robot, const upc_sim_params* params, int64_t n,
+                                       const double* starts, int64_t n_targets, const double* targets, const double* tape, double* out_configs,
+                                       uint8_t* out_collided, double* trace_configs, double* trace_controls, int32_t* trace_steps);
+/* counter-based noise (upc_oracle_noise.cpp) */
+int32_t oracle_fill_noise_tape_counter(uint64_t seed, const upc_robot_desc* robot, const upc_sim_params* params, int64_t first_particle,
+                                       int64_t n, int64_t tape_stride, double* tape);
 int32_t oracle_check_config_collision(const upc_env_desc* env, const upc_robot_desc* robot, const double* config,
                                       double contact_distance, double inflation, int32_t* out);
 int32_t oracle_cluster_particles(const upc_env_desc* env, const upc_robot_desc* robot, const upc_cluster_params* params,

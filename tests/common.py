@@ -36,6 +36,9 @@ def emulation():
         lib.emulate_forward_simulate.argtypes = [C.POINTER(abi.EnvDesc), C.POINTER(abi.RobotDesc), C.POINTER(abi.SimParams),
                                                  i64, vp, i64, vp, vp, vp, vp, vp]
         lib.emulate_forward_simulate.restype = C.c_int
+        lib.emulate_forward_simulate_seeded.argtypes = [C.POINTER(abi.EnvDesc), C.POINTER(abi.RobotDesc), C.POINTER(abi.SimParams), C.c_uint64,
+                                                        i64, i64, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp]
+        lib.emulate_forward_simulate_seeded.restype = C.c_int
         lib.emulate_set_corner_cells.argtypes = [C.c_int]
         lib.emulate_set_fp32_cull.argtypes = [C.c_int]
         lib.emulate_cull_check.argtypes = [C.POINTER(abi.EnvDesc), C.POINTER(abi.RobotDesc), i64, vp, C.c_double, vp]
@@ -76,6 +79,38 @@ def emulate_forward_simulate(env, robot, params, starts, targets, tape, corner_c
     stats = dict(particle_steps=int(counters[0]), collided_particles=int(counters[1]),
                  resolver_iterations=int(counters[2]), failed_resolves=int(counters[3]))
     return np.ascontiguousarray(out.T), coll.astype(bool), stats
+
+
+def emulate_forward_simulate_seeded(env, robot, params, seed, starts, targets, n=None, first_particle=0, trace=False,
+                                    corner_cells=True, fp32_cull=True):
+    """Seeded form of the device program on the CPU: draws from the counter-based generator, starts / targets
+    given per particle or per block of particles (their row counts must divide n).  trace=True also returns the per-interval
+    record (configs [S, n, C], controls [S, n, 2*dof], steps [2, n])."""
+    emulation().emulate_set_corner_cells(1 if corner_cells else 0)
+    emulation().emulate_set_fp32_cull(1 if fp32_cull else 0)
+    starts = np.asarray(starts, dtype=np.float64)
+    targets = np.asarray(targets, dtype=np.float64)
+    n = starts.shape[0] if n is None else int(n)
+    s_soa = np.ascontiguousarray(starts.T)
+    t_soa = np.ascontiguousarray(targets.T)
+    width = starts.shape[1]
+    out = np.zeros((width, n))
+    coll = np.zeros(n, dtype=np.uint8)
+    counters = np.zeros(4, dtype=np.int64)
+    S = params.num_steps
+    tc = np.zeros((S, width, n)) if trace else None
+    tu = np.zeros((S, 2 * robot.dof, n)) if trace else None
+    ts = np.zeros((2, n), dtype=np.int32) if trace else None
+    emulation().emulate_forward_simulate_seeded(C.byref(env.desc), C.byref(robot.desc), C.byref(params), seed, first_particle, n, starts.shape[0],
+                                                s_soa.ctypes.data, targets.shape[0], t_soa.ctypes.data, out.ctypes.data, coll.ctypes.data,
+                                                counters.ctypes.data, None if tc is None else tc.ctypes.data,
+                                                None if tu is None else tu.ctypes.data, None if ts is None else ts.ctypes.data)
+    stats = dict(particle_steps=int(counters[0]), collided_particles=int(counters[1]),
+                 resolver_iterations=int(counters[2]), failed_resolves=int(counters[3]))
+    res = (np.ascontiguousarray(out.T), coll.astype(bool), stats)
+    if trace:
+        res = res + (dict(configs=np.ascontiguousarray(tc.transpose(0, 2, 1)), controls=np.ascontiguousarray(tu.transpose(0, 2, 1)), steps=ts),)
+    return res
 
 
 def canonical_partition(labels):

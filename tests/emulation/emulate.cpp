@@ -39,6 +39,7 @@ static void fill_robot(const upc_robot_desc* r, DevRobot* d)
         d->axis[a].kp = fabs(r->axis[a].kp); d->axis[a].ki = fabs(r->axis[a].ki); d->axis[a].kd = fabs(r->axis[a].kd);
         d->axis[a].clamp = fabs(r->axis[a].integral_clamp); d->axis[a].vlim = fabs(r->axis[a].velocity_limit);
         d->axis[a].nb = fabs(r->axis[a].max_actuator_noise); d->weights[a] = fabs(r->distance_weights[a]);
+        d->axis[a].sensor_scale = sensor_noise_scale(r->axis[a]); d->axis[a].actuator_scale = actuator_noise_scale(r->axis[a]);
     }
     compute_reach(r, d->reach);
     for (int l = 0; l < r->num_links; l++)
@@ -69,13 +70,15 @@ template <class M>
 static void run(const DevEnv& env, const DevRobot& rob, const DevSim& sp, int64_t n, const double* starts, int64_t n_targets,
                 const double* targets, const double* tape, double* out, uint8_t* coll, int64_t* counters)
 {
+    const bool seeded = (tape == nullptr);
     Group<1> g; g.mask = 1u; g.base = 0; g.sub = 0;
     std::vector<double> f0((size_t)rob.num_links * 12), f1((size_t)rob.num_links * 12), park((size_t)2 * M::WIDTH + 2 * M::DOF);
     for (int64_t i = 0; i < n; i++)
     {
         LocalCounters lc = {};
         bool c = false;
-        simulate_particle<M, 1>(env, rob, sp, g, i, n, starts, n_targets, targets, tape, out, coll, rob.pts, f0.data(), f1.data(), park.data(), lc, c);
+        if (seeded) simulate_particle<M, 1, true>(env, rob, sp, g, i, n, starts, n_targets, targets, tape, out, coll, rob.pts, f0.data(), f1.data(), park.data(), lc, c);
+        else simulate_particle<M, 1, false>(env, rob, sp, g, i, n, starts, n_targets, targets, tape, out, coll, rob.pts, f0.data(), f1.data(), park.data(), lc, c);
         counters[0] += lc.particle_steps; counters[1] += c ? 1 : 0; counters[2] += lc.resolver_iterations; counters[3] += lc.failed_resolves;
     }
 }
@@ -127,9 +130,30 @@ extern "C" int emulate_cull_check(const upc_env_desc* e, const upc_robot_desc* r
     return 0;
 }
 
+static int emulate_impl(const upc_env_desc* e, const upc_robot_desc* r, const upc_sim_params* p, int64_t n, int64_t n_starts,
+                        const double* starts, int64_t n_targets, const double* targets, const double* tape, uint64_t seed, int64_t first_particle,
+                        double* out, uint8_t* coll, int64_t* counters, double* trace_configs, double* trace_controls, int32_t* trace_steps);
+
 extern "C" int emulate_forward_simulate(const upc_env_desc* e, const upc_robot_desc* r, const upc_sim_params* p, int64_t n,
                                         const double* starts, int64_t n_targets, const double* targets, const double* tape,
                                         double* out, uint8_t* coll, int64_t* counters)
+{
+    return emulate_impl(e, r, p, n, n, starts, n_targets, targets, tape, 0, 0, out, coll, counters, nullptr, nullptr, nullptr);
+}
+
+/* seeded noise (tape == NULL inside), block-broadcast starts / targets, optional per-interval trace */
+extern "C" int emulate_forward_simulate_seeded(const upc_env_desc* e, const upc_robot_desc* r, const upc_sim_params* p, uint64_t seed,
+                                               int64_t first_particle, int64_t n, int64_t n_starts, const double* starts, int64_t n_targets,
+                                               const double* targets, double* out, uint8_t* coll, int64_t* counters, double* trace_configs,
+                                               double* trace_controls, int32_t* trace_steps)
+{
+    return emulate_impl(e, r, p, n, n_starts, starts, n_targets, targets, nullptr, seed, first_particle, out, coll, counters, trace_configs,
+                        trace_controls, trace_steps);
+}
+
+static int emulate_impl(const upc_env_desc* e, const upc_robot_desc* r, const upc_sim_params* p, int64_t n, int64_t n_starts,
+                        const double* starts, int64_t n_targets, const double* targets, const double* tape, uint64_t seed, int64_t first_particle,
+                        double* out, uint8_t* coll, int64_t* counters, double* trace_configs, double* trace_controls, int32_t* trace_steps)
 {
     DevEnv env; DevRobot rob; DevSim sp;
     fill_env(e, &env); fill_robot(r, &rob);
@@ -154,6 +178,9 @@ extern "C" int emulate_forward_simulate(const upc_env_desc* e, const upc_robot_d
     sp.contact_distance = p->contact_distance; sp.resolve_distance = p->resolve_distance; sp.microstep_distance = p->microstep_distance;
     sp.initial_scale = p->resolver_initial_scale; sp.decay_rate = p->resolver_decay_rate; sp.damping = p->resolver_damping;
     sp.step_begin = 0; sp.step_end = p->num_steps; sp.carry_pid = nullptr; sp.carry_flags = nullptr;
+    sp.n_starts = n_starts; sp.per_start = n / n_starts; sp.per_target = n / n_targets;
+    sp.seed = seed; sp.first_particle = first_particle;
+    sp.trace_configs = trace_configs; sp.trace_controls = trace_controls; sp.trace_steps = trace_steps;
     for (int k = 0; k < 4; k++) counters[k] = 0;
     if (r->kind == UPC_ROBOT_SE2) run<Se2Model>(env, rob, sp, n, starts, n_targets, targets, tape, out, coll, counters);
     else if (r->kind == UPC_ROBOT_SE3) run<Se3Model>(env, rob, sp, n, starts, n_targets, targets, tape, out, coll, counters);

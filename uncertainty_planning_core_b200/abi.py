@@ -82,7 +82,13 @@ class ClusterParams(C.Structure):
         ("goal_distance_threshold", C.c_double),
         ("ptpm_sim", C.POINTER(SimParams)),
         ("ptpm_tape", C.c_void_p),
+        ("ptpm_seed", C.c_uint64),
     ]
+
+
+class OutcomeLayout(C.Structure):
+    _fields_ = [(k, C.c_int64) for k in
+                ("particles", "sets", "labels_offset", "n_clusters_offset", "collided_offset", "configs_offset", "block_bytes")]
 
 
 class Stats(C.Structure):
@@ -283,6 +289,31 @@ def load_library():
     lib.upc_cluster_statistics.argtypes = [vp, i64, vp, vp, vp, i32, dp, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.upc_measure_l2_gather_gbs.argtypes = [vp, i64, C.POINTER(dp)]
     lib.upc_measure_fp64_tflops.argtypes = [vp, C.POINTER(dp)]
+    u64 = C.c_uint64
+    lib.upc_forward_simulate_seeded.argtypes = [vp, C.POINTER(SimParams), u64, i64, i64, i64, vp, i64, vp, vp, vp]
+    lib.upc_forward_simulate_seeded_device.argtypes = [vp, C.POINTER(SimParams), u64, i64, i64, i64, vp, i64, vp, vp, vp, vp]
+    lib.upc_fill_noise_tape_seeded.argtypes = [u64, C.POINTER(RobotDesc), C.POINTER(SimParams), i64, i64, i64, vp]
+    lib.upc_forward_simulate_traced.argtypes = [vp, C.POINTER(SimParams), i64, vp, i64, vp, vp, u64, i64, vp, vp, vp, vp, vp]
+    lib.upc_simulate_and_cluster_edges.argtypes = [vp, C.POINTER(SimParams), C.POINTER(ClusterParams), u64, i64, i64, i64, vp, vp, vp, vp, vp, vp]
+    lib.upc_comm_get_unique_id.argtypes = [vp]
+    lib.upc_comm_create.argtypes = [vp, i32, i32, vp, C.POINTER(vp)]
+    lib.upc_comm_create_all.argtypes = [i32, C.POINTER(vp), C.POINTER(vp)]
+    lib.upc_comm_destroy.argtypes = [vp]
+    lib.upc_comm_world.argtypes = [vp]
+    lib.upc_comm_rank.argtypes = [vp]
+    lib.upc_comm_nccl_version.argtypes = [C.POINTER(i32)]
+    lib.upc_shard_bounds.argtypes = [i64, i32, i32, C.POINTER(i64), C.POINTER(i64)]
+    lib.upc_shard_bounds.restype = None
+    lib.upc_outcome_layout_for.argtypes = [i32, i64, i64, C.POINTER(OutcomeLayout)]
+    lib.upc_comm_all_gather_outcomes.argtypes = [vp, vp, i64, vp]
+    lib.upc_comm_wait.argtypes = [vp, vp]
+    lib.upc_comm_synchronize.argtypes = [vp]
+    lib.upc_sharded_edge_batch.argtypes = [vp, C.POINTER(SimParams), C.POINTER(ClusterParams), u64, i64, i64, vp, vp, vp, vp]
+    for name in ("upc_forward_simulate_seeded", "upc_forward_simulate_seeded_device", "upc_fill_noise_tape_seeded", "upc_forward_simulate_traced",
+                 "upc_simulate_and_cluster_edges", "upc_comm_get_unique_id", "upc_comm_create", "upc_comm_create_all", "upc_comm_destroy",
+                 "upc_comm_world", "upc_comm_rank", "upc_comm_nccl_version", "upc_outcome_layout_for", "upc_comm_all_gather_outcomes", "upc_comm_wait",
+                 "upc_comm_synchronize", "upc_sharded_edge_batch", "upc_comm_group_start", "upc_comm_group_end"):
+        getattr(lib, name).restype = i32
     for name in ("upc_cluster_statistics", "upc_nearest_neighbors", "upc_count_within", "upc_measure_l2_gather_gbs", "upc_measure_fp64_tflops", "upc_create", "upc_destroy", "upc_set_robot", "upc_get_stats", "upc_reset_stats",
                  "upc_set_lanes_per_particle", "upc_host_alloc", "upc_host_free", "upc_synchronize",
                  "upc_forward_simulate", "upc_forward_simulate_device", "upc_check_config_collision",
@@ -298,6 +329,10 @@ EXPORTED_SYMBOLS = (
     "upc_forward_simulate", "upc_forward_simulate_device", "upc_check_config_collision", "upc_cluster_particles",
     "upc_cluster_particles_device", "upc_fill_noise_tape", "upc_synchronize", "upc_measure_l2_gather_gbs",
     "upc_measure_fp64_tflops", "upc_count_within", "upc_variance_width", "upc_cluster_statistics", "upc_nearest_neighbors",
+    "upc_forward_simulate_seeded", "upc_forward_simulate_seeded_device", "upc_fill_noise_tape_seeded", "upc_forward_simulate_traced",
+    "upc_simulate_and_cluster_edges", "upc_comm_get_unique_id", "upc_comm_create", "upc_comm_create_all", "upc_comm_destroy",
+    "upc_comm_world", "upc_comm_rank", "upc_comm_nccl_version", "upc_comm_group_start", "upc_comm_group_end", "upc_shard_bounds",
+    "upc_outcome_layout_for", "upc_comm_all_gather_outcomes", "upc_comm_wait", "upc_comm_synchronize", "upc_sharded_edge_batch",
 )
 
 
@@ -315,3 +350,23 @@ def fill_noise_tape(seed, robot, params, n, first_particle=0):
     tape = np.zeros(tape_shape(params, robot.dof, n), dtype=np.float64)
     check(lib.upc_fill_noise_tape(seed, C.byref(robot.desc), C.byref(params), first_particle, n, n, tape.ctypes.data))
     return tape
+
+
+def fill_noise_tape_seeded(seed, robot, params, n, first_particle=0):
+    """The draws of the seeded entry points (counter-based generator) written out as a tape."""
+    lib = load_library()
+    tape = np.zeros(tape_shape(params, robot.dof, n), dtype=np.float64)
+    check(lib.upc_fill_noise_tape_seeded(seed, C.byref(robot.desc), C.byref(params), first_particle, n, n, tape.ctypes.data))
+    return tape
+
+
+def shard_bounds(total, rank, world):
+    lo, hi = C.c_int64(0), C.c_int64(0)
+    load_library().upc_shard_bounds(total, rank, world, C.byref(lo), C.byref(hi))
+    return int(lo.value), int(hi.value)
+
+
+def outcome_layout(width, particles, sets):
+    lay = OutcomeLayout()
+    check(load_library().upc_outcome_layout_for(width, particles, sets, C.byref(lay)))
+    return lay

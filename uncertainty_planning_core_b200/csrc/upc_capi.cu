@@ -4,6 +4,7 @@
  */
 #include "upc_internal.h"
 #include "upc_host_prep.h"
+#include "upc_noise.cuh"
 
 #include <math.h>
 #include <string.h>
@@ -88,6 +89,26 @@ static int32_t to_dev_sim(const upc_sim_params* p, DevSim* out)
     out->step_end = p->num_steps;
     out->carry_pid = nullptr;
     out->carry_flags = nullptr;
+    out->n_starts = 0; /* filled by set_broadcast */
+    out->per_start = 1;
+    out->per_target = 1;
+    out->seed = 0;
+    out->first_particle = 0;
+    out->trace_configs = nullptr;
+    out->trace_controls = nullptr;
+    out->trace_steps = nullptr;
+    return UPC_OK;
+}
+
+/* starts / targets given per particle, per block of particles (edge batches) or once for all: n_x must divide n */
+static int32_t set_broadcast(DevSim* sp, int64_t n, int64_t n_starts, int64_t n_targets)
+{
+    if (n_starts < 1 || (n % n_starts) != 0) return fail_arg("start_positions must have size N, or a size that divides N (one start per block of particles)");
+    if (n_targets < 1 || (n % n_targets) != 0)
+        return fail_arg("target_positions must have size 1 or size start_positions.size() (or a size that divides N: one target per block of particles)");
+    sp->n_starts = n_starts;
+    sp->per_start = n / n_starts;
+    sp->per_target = n / n_targets;
     return UPC_OK;
 }
 
@@ -225,7 +246,7 @@ int32_t upc_destroy(upc_handle* h)
     cudaFree(h->d_cells);
     cudaFree(h->d_points);
     cudaFree(h->d_counters);
-    DeviceBuffer* bufs[] = {&h->st_starts, &h->st_targets, &h->st_tape, &h->st_out, &h->st_coll, &h->st_labels, &h->st_ncl, &h->st_carry,
+    DeviceBuffer* bufs[] = {&h->st_trace, &h->st_records, &h->st_starts, &h->st_targets, &h->st_tape, &h->st_out, &h->st_coll, &h->st_labels, &h->st_ncl, &h->st_carry,
                             &h->cw.features, &h->cw.adjacency, &h->cw.roots, &h->cw.comp, &h->cw.flags, &h->cw.signatures,
                             &h->cw.frames, &h->cw.dist_matrix, &h->cw.members, &h->cw.link_scratch, &h->cw.misc, &h->cw.hash, &h->cw.dedupe, &h->cw.usig, &h->cw.uroot};
     for (DeviceBuffer* b : bufs) b->release();
@@ -273,6 +294,8 @@ int32_t upc_set_robot(upc_handle* h, const upc_robot_desc* r)
         d.axis[a].clamp = fabs(r->axis[a].integral_clamp);
         d.axis[a].vlim = fabs(r->axis[a].velocity_limit);
         d.axis[a].nb = fabs(r->axis[a].max_actuator_noise);
+        d.axis[a].sensor_scale = sensor_noise_scale(r->axis[a]);
+        d.axis[a].actuator_scale = actuator_noise_scale(r->axis[a]);
         d.weights[a] = fabs(r->distance_weights[a]);
     }
     if (r->kind == UPC_ROBOT_LINKED)
@@ -422,13 +445,130 @@ int32_t upc_forward_simulate_device(upc_handle* h, const upc_sim_params* params,
     if (rc != UPC_OK) return rc;
     if (n < 0) return fail_arg("n must be >= 0");
     if (n == 0) return UPC_OK;
-    if (!(n_targets == 1 || n_targets == n)) return fail_arg("target_positions must have size 1 or size start_positions.size()");
     if (!d_starts || !d_targets || !d_tape || !d_out_configs || !d_out_collided) return fail_arg("null buffer");
+    {
+        const int32_t brc = set_broadcast(&sp, n, n, n_targets);
+        if (brc != UPC_OK) return brc;
+    }
     UPC_CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
     UPC_CUDA_TRY(launch_forward_simulate(h, sp, n, d_starts, n_targets, d_targets, d_tape, d_out_configs, d_out_collided, s));
     h->stats.kernel_launches++;
     h->stats.particles_simulated += n;
+    return UPC_OK;
+}
+
+int32_t upc_forward_simulate_seeded_device(upc_handle* h, const upc_sim_params* params, uint64_t seed, int64_t first_particle, int64_t n,
+                                           int64_t n_starts, const double* d_starts, int64_t n_targets, const double* d_targets,
+                                           double* d_out_configs, uint8_t* d_out_collided, void* stream)
+{
+    if (!h) return fail_arg("null handle");
+    if (!h->has_robot)
+    {
+        set_error("upc_set_robot has not been called");
+        return UPC_ERR_NO_ROBOT;
+    }
+    DevSim sp;
+    const int32_t rc = to_dev_sim(params, &sp);
+    if (rc != UPC_OK) return rc;
+    if (n < 0 || first_particle < 0) return fail_arg("n and first_particle must be >= 0");
+    if (n == 0) return UPC_OK;
+    if (params->max_microsteps > 65534) return fail_arg("seeded noise supports at most 65534 microsteps per controller interval");
+    if (!d_starts || !d_targets || !d_out_configs || !d_out_collided) return fail_arg("null buffer");
+    {
+        const int32_t brc = set_broadcast(&sp, n, n_starts, n_targets);
+        if (brc != UPC_OK) return brc;
+    }
+    sp.seed = seed;
+    sp.first_particle = first_particle;
+    UPC_CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+    UPC_CUDA_TRY(launch_forward_simulate(h, sp, n, d_starts, n_targets, d_targets, nullptr, d_out_configs, d_out_collided, s));
+    h->stats.kernel_launches++;
+    h->stats.particles_simulated += n;
+    return UPC_OK;
+}
+
+/* shared by the host-pointer seeded entry points: uploads the (small) inputs, runs, leaves the results in st_out / st_coll */
+static int32_t seeded_from_host(upc_handle* h, const upc_sim_params* params, uint64_t seed, int64_t first_particle, int64_t n, int64_t n_starts,
+                                const double* starts, int64_t n_targets, const double* targets)
+{
+    const int width = upc_config_width(h->robot.kind, h->robot.dof);
+    const size_t start_bytes = (size_t)width * (size_t)n_starts * sizeof(double);
+    const size_t tgt_bytes = (size_t)width * (size_t)n_targets * sizeof(double);
+    UPC_CUDA_TRY(h->st_starts.reserve(start_bytes));
+    UPC_CUDA_TRY(h->st_targets.reserve(tgt_bytes));
+    UPC_CUDA_TRY(h->st_out.reserve((size_t)width * (size_t)n * sizeof(double)));
+    UPC_CUDA_TRY(h->st_coll.reserve((size_t)n));
+    UPC_CUDA_TRY(cudaMemcpyAsync(h->st_starts.ptr, starts, start_bytes, cudaMemcpyHostToDevice, h->stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(h->st_targets.ptr, targets, tgt_bytes, cudaMemcpyHostToDevice, h->stream));
+    h->stats.h2d_bytes += (int64_t)(start_bytes + tgt_bytes);
+    return upc_forward_simulate_seeded_device(h, params, seed, first_particle, n, n_starts, (const double*)h->st_starts.ptr, n_targets,
+                                              (const double*)h->st_targets.ptr, (double*)h->st_out.ptr, (uint8_t*)h->st_coll.ptr, h->stream);
+}
+
+int32_t upc_forward_simulate_seeded(upc_handle* h, const upc_sim_params* params, uint64_t seed, int64_t first_particle, int64_t n,
+                                    int64_t n_starts, const double* starts, int64_t n_targets, const double* targets, double* out_configs,
+                                    uint8_t* out_collided)
+{
+    if (!h) return fail_arg("null handle");
+    if (!h->has_robot)
+    {
+        set_error("upc_set_robot has not been called");
+        return UPC_ERR_NO_ROBOT;
+    }
+    if (n < 0) return fail_arg("n must be >= 0");
+    if (n == 0) return UPC_OK;
+    if (n_starts < 1 || n_targets < 1) return fail_arg("start_positions / target_positions must not be empty");
+    if (!starts || !targets || !out_configs || !out_collided) return fail_arg("null buffer");
+    UPC_CUDA_TRY(cudaSetDevice(h->device));
+    const int32_t rc = seeded_from_host(h, params, seed, first_particle, n, n_starts, starts, n_targets, targets);
+    if (rc != UPC_OK) return rc;
+    const size_t cfg_bytes = (size_t)upc_config_width(h->robot.kind, h->robot.dof) * (size_t)n * sizeof(double);
+    UPC_CUDA_TRY(cudaMemcpyAsync(out_configs, h->st_out.ptr, cfg_bytes, cudaMemcpyDeviceToHost, h->stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(out_collided, h->st_coll.ptr, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    h->stats.d2h_bytes += (int64_t)(cfg_bytes + (size_t)n);
+    UPC_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return UPC_OK;
+}
+
+/*
+ * The planner-batch step in one call (BASELINE config 5; uncertainty_contact_planning.hpp:2039-2071 followed by :1986-2034 for
+ * every candidate edge): n_edges x particles_per_edge particles simulated with seeded noise, then the outcome of every edge
+ * clustered, with the outcomes staying in device memory between the two halves.
+ */
+int32_t upc_simulate_and_cluster_edges(upc_handle* h, const upc_sim_params* params, const upc_cluster_params* cparams, uint64_t seed,
+                                       int64_t first_particle, int64_t n_edges, int64_t particles_per_edge, const double* edge_starts,
+                                       const double* edge_targets, double* out_configs, uint8_t* out_collided, int32_t* out_labels,
+                                       int32_t* out_n_clusters)
+{
+    if (!h || !cparams) return fail_arg("null argument");
+    if (!h->has_robot)
+    {
+        set_error("upc_set_robot has not been called");
+        return UPC_ERR_NO_ROBOT;
+    }
+    if (n_edges < 0 || particles_per_edge < 0) return fail_arg("negative size");
+    if (n_edges == 0 || particles_per_edge == 0) return UPC_OK;
+    if (n_edges > 65535) return fail_arg("at most 65535 edges per call");
+    if (particles_per_edge > (int64_t)1 << 20) return fail_arg("at most 2^20 particles per edge");
+    if (!edge_starts || !edge_targets || !out_configs || !out_collided || !out_labels || !out_n_clusters) return fail_arg("null buffer");
+    UPC_CUDA_TRY(cudaSetDevice(h->device));
+    const int64_t n = n_edges * particles_per_edge;
+    int32_t rc = seeded_from_host(h, params, seed, first_particle, n, n_edges, edge_starts, n_edges, edge_targets);
+    if (rc != UPC_OK) return rc;
+    UPC_CUDA_TRY(h->st_labels.reserve((size_t)n * sizeof(int32_t)));
+    UPC_CUDA_TRY(h->st_ncl.reserve((size_t)n_edges * sizeof(int32_t) + 64));
+    rc = upc_cluster_particles_device(h, cparams, n_edges, particles_per_edge, (const double*)h->st_out.ptr, (int32_t*)h->st_labels.ptr,
+                                      (int32_t*)h->st_ncl.ptr, h->stream);
+    if (rc != UPC_OK) return rc;
+    const size_t cfg_bytes = (size_t)upc_config_width(h->robot.kind, h->robot.dof) * (size_t)n * sizeof(double);
+    UPC_CUDA_TRY(cudaMemcpyAsync(out_configs, h->st_out.ptr, cfg_bytes, cudaMemcpyDeviceToHost, h->stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(out_collided, h->st_coll.ptr, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(out_labels, h->st_labels.ptr, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(out_n_clusters, h->st_ncl.ptr, (size_t)n_edges * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    h->stats.d2h_bytes += (int64_t)(cfg_bytes + (size_t)n * 5 + (size_t)n_edges * 4);
+    UPC_CUDA_TRY(cudaStreamSynchronize(h->stream));
     return UPC_OK;
 }
 
@@ -445,7 +585,8 @@ int32_t upc_forward_simulate(upc_handle* h, const upc_sim_params* params, int64_
     if (n < 0) return fail_arg("n must be >= 0");
     if (n == 0) return UPC_OK;
     if (!params) return fail_arg("null sim params");
-    if (!(n_targets == 1 || n_targets == n)) return fail_arg("target_positions must have size 1 or size start_positions.size()");
+    if (n_targets < 1 || (n % n_targets) != 0)
+        return fail_arg("target_positions must have size 1 or size start_positions.size() (or a size that divides N: one target per block of particles)");
     if (!starts || !targets || !tape || !out_configs || !out_collided) return fail_arg("null buffer");
     UPC_CUDA_TRY(cudaSetDevice(h->device));
     const int width = upc_config_width(h->robot.kind, h->robot.dof);
@@ -463,7 +604,9 @@ int32_t upc_forward_simulate(upc_handle* h, const upc_sim_params* params, int64_
     h->stats.h2d_bytes += (int64_t)(cfg_bytes + tgt_bytes);
     DevSim sp;
     {
-        const int32_t prc = to_dev_sim(params, &sp);
+        int32_t prc = to_dev_sim(params, &sp);
+        if (prc != UPC_OK) return prc;
+        prc = set_broadcast(&sp, n, n, n_targets);
         if (prc != UPC_OK) return prc;
     }
     /* The tape dominates the upload (C2: 61 MB of 63 MB).  It is step-major, so the edge is simulated as several
@@ -853,6 +996,95 @@ int32_t upc_fill_noise_tape(uint64_t seed, const upc_robot_desc* robot, const up
             }
         }
     }
+    return UPC_OK;
+}
+
+/* The draws of the seeded entry points written out as a tape: replaying it through upc_forward_simulate gives
+ * the results of upc_forward_simulate_seeded bit for bit. */
+int32_t upc_fill_noise_tape_seeded(uint64_t seed, const upc_robot_desc* robot, const upc_sim_params* params, int64_t first_particle,
+                                   int64_t n, int64_t tape_stride, double* tape)
+{
+    if (!robot || !params || !tape) return fail_arg("null argument");
+    if (robot->dof < 1 || robot->dof > UPC_MAX_DOF) return fail_arg("dof out of range");
+    if (params->num_steps < 1 || params->max_microsteps < 1 || params->max_microsteps > 65534) return fail_arg("bad step counts");
+    if (tape_stride < n || first_particle < 0) return fail_arg("tape_stride must be >= n and first_particle >= 0");
+    const int dof = robot->dof;
+    const int slots = 1 + params->max_microsteps;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++)
+    {
+        for (int step = 0; step < params->num_steps; step++)
+            for (int slot = 0; slot < slots; slot++)
+                for (int pair = 0; 2 * pair < dof; pair++)
+                {
+                    const int d0 = 2 * pair, d1 = 2 * pair + 1;
+                    const double s0 = (slot == 0) ? sensor_noise_scale(robot->axis[d0]) : actuator_noise_scale(robot->axis[d0]);
+                    const double s1 = (d1 < dof) ? ((slot == 0) ? sensor_noise_scale(robot->axis[d1]) : actuator_noise_scale(robot->axis[d1])) : 0.0;
+                    double z0 = 0.0, z1 = 0.0;
+                    if (s0 != 0.0 || s1 != 0.0) noise_pair(seed, (uint64_t)(first_particle + i), (uint32_t)step, (uint32_t)slot, (uint32_t)pair, &z0, &z1);
+                    tape[(((int64_t)step * slots + slot) * dof + d0) * tape_stride + i] = (s0 != 0.0) ? (z0 * s0) : 0.0;
+                    if (d1 < dof) tape[(((int64_t)step * slots + slot) * dof + d1) * tape_stride + i] = (s1 != 0.0) ? (z1 * s1) : 0.0;
+                }
+    }
+    return UPC_OK;
+}
+
+/*
+ * ForwardSimulateRobot with enable_tracing (simple_simulator_interface.hpp:621, trace types :40-63): a (small) batch simulated
+ * with a record of every controller interval - the resolved configuration at its end (what ExtractTrajectoryFromTrace :66-86
+ * reads), the control input and the per-microstep control step.  tape == NULL selects seeded noise.
+ */
+int32_t upc_forward_simulate_traced(upc_handle* h, const upc_sim_params* params, int64_t n, const double* starts, int64_t n_targets,
+                                    const double* targets, const double* tape, uint64_t seed, int64_t first_particle, double* out_configs,
+                                    uint8_t* out_collided, double* trace_configs, double* trace_controls, int32_t* trace_steps)
+{
+    if (!h) return fail_arg("null handle");
+    if (!h->has_robot)
+    {
+        set_error("upc_set_robot has not been called");
+        return UPC_ERR_NO_ROBOT;
+    }
+    DevSim sp;
+    int32_t rc = to_dev_sim(params, &sp);
+    if (rc != UPC_OK) return rc;
+    if (n < 0 || first_particle < 0) return fail_arg("n and first_particle must be >= 0");
+    if (n == 0) return UPC_OK;
+    if (!starts || !targets || !out_configs || !out_collided || !trace_configs || !trace_controls || !trace_steps) return fail_arg("null buffer");
+    rc = set_broadcast(&sp, n, n, n_targets);
+    if (rc != UPC_OK) return rc;
+    UPC_CUDA_TRY(cudaSetDevice(h->device));
+    const int width = upc_config_width(h->robot.kind, h->robot.dof), dof = h->robot.dof;
+    const size_t S = (size_t)params->num_steps;
+    const size_t cfg_bytes = (size_t)width * (size_t)n * sizeof(double), tgt_bytes = (size_t)width * (size_t)n_targets * sizeof(double);
+    const size_t tcfg_bytes = S * cfg_bytes, tctl_bytes = S * 2 * (size_t)dof * (size_t)n * sizeof(double), tsteps_bytes = 2 * (size_t)n * sizeof(int32_t);
+    const size_t tape_bytes = tape ? (size_t)upc_tape_doubles_per_particle(params, dof) * (size_t)n * sizeof(double) : 0;
+    UPC_CUDA_TRY(h->st_starts.reserve(cfg_bytes));
+    UPC_CUDA_TRY(h->st_targets.reserve(tgt_bytes));
+    UPC_CUDA_TRY(h->st_out.reserve(cfg_bytes));
+    UPC_CUDA_TRY(h->st_coll.reserve((size_t)n));
+    UPC_CUDA_TRY(h->st_trace.reserve(tcfg_bytes + tctl_bytes + tsteps_bytes + 64));
+    if (tape) UPC_CUDA_TRY(h->st_tape.reserve(tape_bytes));
+    UPC_CUDA_TRY(cudaMemcpyAsync(h->st_starts.ptr, starts, cfg_bytes, cudaMemcpyHostToDevice, h->stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(h->st_targets.ptr, targets, tgt_bytes, cudaMemcpyHostToDevice, h->stream));
+    if (tape) UPC_CUDA_TRY(cudaMemcpyAsync(h->st_tape.ptr, tape, tape_bytes, cudaMemcpyHostToDevice, h->stream));
+    UPC_CUDA_TRY(cudaMemsetAsync(h->st_trace.ptr, 0, tcfg_bytes + tctl_bytes + tsteps_bytes, h->stream));
+    h->stats.h2d_bytes += (int64_t)(cfg_bytes + tgt_bytes + tape_bytes);
+    sp.seed = seed;
+    sp.first_particle = first_particle;
+    sp.trace_configs = (double*)h->st_trace.ptr;
+    sp.trace_controls = (double*)((uint8_t*)h->st_trace.ptr + tcfg_bytes);
+    sp.trace_steps = (int32_t*)((uint8_t*)h->st_trace.ptr + tcfg_bytes + tctl_bytes);
+    UPC_CUDA_TRY(launch_forward_simulate(h, sp, n, (const double*)h->st_starts.ptr, n_targets, (const double*)h->st_targets.ptr,
+                                         tape ? (const double*)h->st_tape.ptr : nullptr, (double*)h->st_out.ptr, (uint8_t*)h->st_coll.ptr, h->stream));
+    h->stats.kernel_launches++;
+    h->stats.particles_simulated += n;
+    UPC_CUDA_TRY(cudaMemcpyAsync(out_configs, h->st_out.ptr, cfg_bytes, cudaMemcpyDeviceToHost, h->stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(out_collided, h->st_coll.ptr, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(trace_configs, sp.trace_configs, tcfg_bytes, cudaMemcpyDeviceToHost, h->stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(trace_controls, sp.trace_controls, tctl_bytes, cudaMemcpyDeviceToHost, h->stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(trace_steps, sp.trace_steps, tsteps_bytes, cudaMemcpyDeviceToHost, h->stream));
+    h->stats.d2h_bytes += (int64_t)(cfg_bytes + (size_t)n + tcfg_bytes + tctl_bytes + tsteps_bytes);
+    UPC_CUDA_TRY(cudaStreamSynchronize(h->stream));
     return UPC_OK;
 }
 

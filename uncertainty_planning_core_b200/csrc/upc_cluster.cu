@@ -1942,9 +1942,9 @@ int32_t run_cluster(upc_handle* h, const upc_cluster_params& cp, int64_t n_sets,
             set_error("point-to-point-movement clustering handles one particle set per call");
             return UPC_ERR_UNSUPPORTED;
         }
-        if (!cp.ptpm_sim || !cp.ptpm_tape)
+        if (!cp.ptpm_sim)
         {
-            set_error("point-to-point-movement clustering needs simulation parameters and a noise tape");
+            set_error("point-to-point-movement clustering needs simulation parameters (and a noise tape or a seed)");
             return UPC_ERR_INVALID_ARGUMENT;
         }
         const int64_t n = set_size;
@@ -1970,7 +1970,9 @@ int32_t run_cluster(upc_handle* h, const upc_cluster_params& cp, int64_t n_sets,
             UPC_CUDA_TRY(cudaGetLastError());
             upc_sim_params sp = *cp.ptpm_sim;
             sp.allow_contacts = 1; /* :1826 */
-            const int32_t src = upc_forward_simulate_device(h, &sp, sims, starts, sims, targets, cp.ptpm_tape, results, coll, stream);
+            /* pair simulation k replays column k of the tape, or is particle k of the seeded stream */
+            const int32_t src = cp.ptpm_tape ? upc_forward_simulate_device(h, &sp, sims, starts, sims, targets, cp.ptpm_tape, results, coll, stream)
+                                             : upc_forward_simulate_seeded_device(h, &sp, cp.ptpm_seed, 0, sims, sims, starts, sims, targets, results, coll, stream);
             if (src != UPC_OK) return src;
             PtpmAdjArgs pa;
             pa.robot = h->robot; pa.cfg = d_configs; pa.results = results; pa.width = width; pa.n = n; pa.wpr = wpr; pa.adj = adj;

@@ -61,6 +61,9 @@ struct DevAxis
 {
     double kp, ki, kd, clamp; /* already abs()'d, simple_pid_controller.hpp:104-112 */
     double vlim, nb;          /* |actuator limit|, |noise bound|, simple_uncertainty_models.hpp:59 */
+    /* factors applied to a standard truncated-normal draw of this axis by the counter-based generator:
+     * sensor = |max_sensor_noise| / 2, actuator = 1/2 when the axis has actuator noise; 0 = noise-free axis (exact 0.0 draws) */
+    double sensor_scale, actuator_scale;
 };
 
 struct DevJoint
@@ -101,6 +104,18 @@ struct DevSim
     int step_begin, step_end;
     double* carry_pid;
     uint8_t* carry_flags;
+    /* starts [C][n_starts] and targets [C][n_targets] may hold fewer entries than particles: particle i reads entry
+     * i / per_start (i / per_target), per_x = n / n_x - one entry per particle, one per edge of an edge batch, or one for all */
+    int64_t n_starts, per_start, per_target;
+    /* seeded launches (no tape): draws are a function of (seed, first_particle + i, step, slot, axis), DESIGN.md 4.2 */
+    uint64_t seed;
+    int64_t first_particle;
+    /* optional per-interval trace of a (small) batch: configuration after every controller interval, [num_steps][C][n], and the
+     * the control inputs behind it (SimulatorInterface::ForwardSimulateRobot with enable_tracing,
+     * simple_simulator_interface.hpp:40-86, 621); NULL = no trace */
+    double* trace_configs;
+    double* trace_controls; /* [num_steps][2 * dof][n]: control input (velocity command), then the control step applied per microstep */
+    int32_t* trace_steps;   /* [2][n]: controller intervals executed, microsteps of the last one */
 };
 
 /* per-launch counters, reduced per block then added to the handle's totals */

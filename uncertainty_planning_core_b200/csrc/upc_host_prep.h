@@ -15,6 +15,11 @@
 
 namespace upc
 {
+/* factors of the counter-based noise: what a standard truncated-normal draw of the axis is multiplied by;
+ * the same scaling the tape generator applies (sensor: z * max_sensor_noise / 2, actuator: z / 2), 0 for a noise-free axis */
+inline double sensor_noise_scale(const upc_axis_params& a) { const double b = fabs(a.max_sensor_noise); return (b > 0.0) ? (b * 0.5) : 0.0; }
+inline double actuator_noise_scale(const upc_axis_params& a) { return (fabs(a.max_actuator_noise) > 0.0) ? 0.5 : 0.0; }
+
 /* out[(ix*(ny+1)+iy)*(nz+1)+iz] = min of the 8 border-clamped SDF corners of the interpolation cell whose low
  * corner is (ix-1, iy-1, iz-1) */
 inline void build_cellmin(const float* sdf, int nx, int ny, int nz, float* out)

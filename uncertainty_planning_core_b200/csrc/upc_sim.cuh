@@ -17,6 +17,7 @@
 #define UPC_SIM_CUH
 
 #include "upc_device.cuh"
+#include "upc_noise.cuh"
 
 namespace upc
 {
@@ -649,6 +650,31 @@ UPC_PLAIN_UNROLL_PRAGMA
 }
 
 /*
+ * Counter-based draws of one (particle, controller interval, slot) for all axes: slot 0 = sensor draws
+ * (standard draw * max_sensor_noise / 2), slots 1.. = actuator draws (standard draw / 2); a noise-free axis gets an exact
+ * 0.0 and, when both axes of a pair are noise-free, no Philox block is computed.
+ */
+template <int N>
+UPC_D void seeded_draws(const DevRobot& r, uint64_t seed, uint64_t particle, int step, int slot, double* out)
+{
+#pragma unroll
+    for (int p = 0; p < (N + 1) / 2; p++)
+    {
+        const int d0 = 2 * p, d1 = 2 * p + 1;
+        if (d0 < r.dof)
+        {
+            const bool has1 = (d1 < N) && (d1 < r.dof);
+            const double s0 = (slot == 0) ? r.axis[d0].sensor_scale : r.axis[d0].actuator_scale;
+            const double s1 = has1 ? ((slot == 0) ? r.axis[has1 ? d1 : d0].sensor_scale : r.axis[has1 ? d1 : d0].actuator_scale) : 0.0;
+            double z0 = 0.0, z1 = 0.0;
+            if ((s0 != 0.0) || (s1 != 0.0)) noise_pair(seed, particle, (uint32_t)step, (uint32_t)slot, (uint32_t)p, &z0, &z1);
+            out[d0] = (s0 != 0.0) ? (z0 * s0) : 0.0;
+            if (has1) out[has1 ? d1 : d0] = (s1 != 0.0) ? (z1 * s1) : 0.0;
+        }
+    }
+}
+
+/*
  * Simulate particle i for one planner edge. `pts` are the robot's body points (shared memory on the GPU),
  * frames0/frames1 are per-particle scratch for link transforms (linked robots only), `park` is per-particle
  * scratch of 2*WIDTH + 2*DOF doubles (shared memory on the GPU) holding the target, the pre-microstep
@@ -662,7 +688,7 @@ UPC_PLAIN_UNROLL_PRAGMA
  * each instantiated once (code size is instruction-cache pressure here).  The sequence of operations per
  * particle is exactly the sequential program of DESIGN.md section 3.
  */
-template <class M, int G>
+template <class M, int G, bool SEEDED>
 UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim& sp, const Group<G>& g, int64_t i, int64_t n,
                              const double* starts, int64_t n_targets, const double* targets, const double* tape,
                              double* out_configs, uint8_t* out_collided, const double* pts, double* frames0,
@@ -678,7 +704,8 @@ UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim&
     m.pid_i = park + 2 * M::WIDTH;
     m.pid_e = park + 2 * M::WIDTH + M::DOF;
     const bool resumed = sp.step_begin > 0;
-    m.load(r, resumed ? out_configs : starts, n, i);
+    if (resumed) m.load(r, out_configs, n, i);
+    else m.load(r, starts, sp.n_starts, (sp.per_start == 1) ? i : ((sp.per_start == n) ? 0 : (i / sp.per_start)));
     m.reset_controllers();
     bool collided = false;
     bool finished = false;
@@ -694,7 +721,7 @@ UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim&
     }
     refresh_frames(r, m, g);
     {
-        const int64_t ti = (n_targets == 1) ? 0 : i;
+        const int64_t ti = (sp.per_target == 1) ? i : ((sp.per_target == n) ? 0 : (i / sp.per_target));
         if (g.sub == 0)
         {
             for (int c = 0; c < width; c++) target[c] = targets[(int64_t)c * n_targets + ti];
@@ -710,9 +737,16 @@ UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim&
         double ustep[N]; /* control input per microstep */
         {
             double draws[N];
+            if (SEEDED && !r.sensor_noise_free)
+            {
+                seeded_draws<N>(r, sp.seed, (uint64_t)(sp.first_particle + i), step, 0, draws);
+            }
+            else
+            {
 #pragma unroll
-            for (int d = 0; d < N; d++)
-                if (d < dof) draws[d] = r.sensor_noise_free ? 0.0 : tape[(((int64_t)step * slots) * dof + d) * n + i]; /* zeros by construction: not read */
+                for (int d = 0; d < N; d++)
+                    if (d < dof) draws[d] = (SEEDED || r.sensor_noise_free) ? 0.0 : tape[(((int64_t)step * slots) * dof + d) * n + i]; /* zeros by construction: not read */
+            }
 #ifdef UPC_PHASE_TIMING
             if (draws[0] == 123.456) cnt.particle_steps++; /* force the loads to complete inside this phase */
 #endif
@@ -722,6 +756,12 @@ UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim&
 #pragma unroll
             for (int d = 0; d < N; d++)
                 if (d < dof) vec[d] = u[d] * sp.dt;
+            if (sp.trace_configs != nullptr && g.sub == 0)
+            {
+#pragma unroll
+                for (int d = 0; d < N; d++)
+                    if (d < dof) sp.trace_controls[((int64_t)step * 2 * dof + d) * n + i] = u[d];
+            }
             UPC_T1(0)
         }
         unsigned microsteps = 1u, ms = 0u;
@@ -751,6 +791,12 @@ UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim&
 #pragma unroll
                     for (int d = 0; d < N; d++)
                         if (d < dof) ustep[d] = vec[d] * inv_micro;
+                    if (sp.trace_configs != nullptr && g.sub == 0)
+                    {
+#pragma unroll
+                        for (int d = 0; d < N; d++)
+                            if (d < dof) sp.trace_controls[((int64_t)step * 2 * dof + dof + d) * n + i] = ustep[d];
+                    }
                 }
                 else
                 {
@@ -769,11 +815,12 @@ UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim&
                 g.sync();
                 if (g.sub == 0) m.get(r, previous);
                 g.sync();
+                if (SEEDED) seeded_draws<N>(r, sp.seed, (uint64_t)(sp.first_particle + i), step, 1 + (int)ms, draws);
 #pragma unroll
                 for (int d = 0; d < N; d++)
                     if (d < dof)
                     {
-                        draws[d] = tape[(((int64_t)step * slots + 1 + ms) * dof + d) * n + i];
+                        if (!SEEDED) draws[d] = tape[(((int64_t)step * slots + 1 + ms) * dof + d) * n + i];
                         apply_in[d] = ustep[d];
                     }
                 noise = draws;
@@ -856,6 +903,13 @@ UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim&
         const bool arrived = m.reached(r, target, sp.shortcut);
         UPC_T1(5)
         if (arrived) finished = true;
+        if (sp.trace_configs != nullptr && g.sub == 0)
+        {
+            /* tracing (single-particle path): the resolved configuration of this interval and the inputs behind it */
+            m.store(r, sp.trace_configs + (int64_t)step * width * n, n, i);
+            sp.trace_steps[i] = step + 1;
+            sp.trace_steps[n + i] = (int32_t)microsteps;
+        }
     }
     const bool last_launch = sp.step_end >= sp.num_steps;
     if (g.sub == 0)

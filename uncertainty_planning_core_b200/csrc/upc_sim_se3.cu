@@ -1,0 +1,7 @@
+/* upc_sim_se3.cu - forward_simulate_kernel instantiated for Se3Model (all lane counts, tape and seeded noise) */
+#include "upc_sim_launch.cuh"
+
+namespace upc
+{
+cudaError_t launch_sim_se3(const SimArgs& a, int lanes, bool seeded, cudaStream_t stream) { return launch_sim_lanes<Se3Model>(a, lanes, seeded, stream); }
+}
