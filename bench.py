@@ -1,22 +1,27 @@
 #!/usr/bin/env python
 """Benchmark of the particle hot path (BASELINE.json: particle-steps/sec for sim + SDF collision, and particles
-clustered/sec).
+clustered/sec, at 1/2/4/8 B200).
 
-A "step" is one pass of the hot path over one planner edge: ForwardSimulateRobots on N particles for S controller
-intervals (noisy actuation, sphere-vs-SDF collision, contact resolution) followed by ClusterParticles of the N
-outcomes.  Default workload = BASELINE config 2: SE(3) robot, 10,000 particles per edge, 128^3 SDF, 128 body
-points, 64 controller intervals.  With --gpus N every rank owns its own edge (weak scaling), the SDF is
-replicated, and the step ends with ONE NCCL all-gather of the outcome records.
+A "step" is one pass of the hot path over one planner batch.  Default workload = BASELINE config 5, the configuration the
+metric is quoted on: 4,096 candidate RRT edges x 1,000 particles on the SE(2) environment of config 1 - ONE
+ForwardSimulateRobots call over 4,096,000 particles (the targets.size() == N form, uncertainty_contact_planning.hpp:1826;
+64 controller intervals of noisy actuation, point-vs-SDF collision, contact resolution) followed by ONE clustering pass
+over the 4,096 outcome sets (ClusterParticles, :1986-2034).  Noise is drawn inside the kernel (counter-based).
+With --gpus N the edges are split into contiguous blocks (strong scaling), the SDF is replicated, every rank simulates and
+clusters its block straight into its slot of the gather buffer, and the step ends with ONE NCCL all-gather of the outcome
+records issued by the library's own communicator (upc_comm_*); torch.distributed (gloo) only carries the 128-byte NCCL id,
+the barriers and the max-over-ranks of the timings.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]            # the CUDA path
-  python bench.py --impl reference ...                           # the CPU path (oracle) on the box's host cores
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c2|c3|c1]     # the CUDA path
+  python bench.py --impl reference ...                                             # the CPU path (oracle) on the host cores
 
-Prints ONE JSON line (see DESIGN.md section 7 for every key).
+Prints ONE JSON line (DESIGN.md section 7 explains every key).
 """
 import argparse
 import ctypes as C
 import json
 import os
+import struct
 import subprocess
 import sys
 import tempfile
@@ -29,37 +34,51 @@ sys.path.insert(0, ROOT)
 
 METRIC = "particle_steps_per_sec"
 UNIT = "particle-steps/s"
-L2_BYTES = 126 * 1024 * 1024
+SEED = 20261020
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3"])
-    ap.add_argument("--particles", type=int, default=0, help="override the workload's particle count")
+    ap.add_argument("--workload", default="c5", choices=["c1", "c2", "c3", "c5"])
+    ap.add_argument("--edges", type=int, default=0, help="override the number of edges of the workload")
+    ap.add_argument("--particles", type=int, default=0, help="override the particles per edge")
     ap.add_argument("--lanes", type=int, default=0, help="lanes per particle (0 = built-in choice)")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="particles in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--cpu-edges", type=int, default=0, help="edges in the CPU sample (0 = sized for ~10 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-big-batch", action="store_true", help="skip the 10^6-particle throughput-regime measurement of the simulation kernel")
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary workloads (C2, C3) of the `also` key")
+    ap.add_argument("--no-plugin", action="store_true", help="skip the C++ plugin driver (e2e_plugin)")
     return ap.parse_args()
 
 
-def make_workload(args, edge):
+# ---------------------------------------------------------------------------------------------- workloads
+
+def make_workload(name, edges=0, particles=0):
+    """dict(env, robot, params, edge_starts [E, C], edge_targets [E, C], particles_per_edge, label): every workload is an edge
+    batch; C1 / C2 / C3 are batches of one edge."""
     from uncertainty_planning_core_b200 import scenarios
-    if args.workload == "c1":
-        sc = scenarios.c1_se2(n=args.particles or 1000)
-        name = "C1 SE(2), %d particles/edge, 256x256 SDF, P=64, S=64"
-    elif args.workload == "c3":
-        sc = scenarios.c3_linked(n=args.particles or 100000)
-        name = "C3 7-DoF arm, %d particles/edge, 256^3 SDF, P=128, S=64"
+    if name == "c5":
+        E, P = edges or 4096, particles or 1000
+        sc = scenarios.c5_batch(edges=E, particles=1)
+        label = "C5 planner batch: %d edges x %d particles, SE(2), 256x256 SDF, P=64 body points, S=64" % (E, P)
+        es, et = sc["starts"], sc["targets"]
     else:
-        sc = scenarios.c2_se3(n=args.particles or 10000, edge=edge)
-        name = "C2 SE(3), %d particles/edge, 128^3 SDF, P=128, S=64, contact resolution"
-    sc["label"] = name % sc["starts"].shape[0]
-    return sc
+        if name == "c1":
+            sc = scenarios.c1_se2(n=1)
+            P, label = particles or 1000, "C1 SE(2), %d particles/edge, 256x256 SDF, P=64, S=64"
+        elif name == "c3":
+            sc = scenarios.c3_linked(n=1)
+            P, label = particles or 100000, "C3 7-DoF arm, %d particles/edge, 256^3 SDF, P=128, S=64, contact resolution"
+        else:
+            sc = scenarios.c2_se3(n=1)
+            P, label = particles or 10000, "C2 SE(3), %d particles/edge, 128^3 SDF, P=128, S=64, contact resolution"
+        label = label % P
+        es, et = sc["starts"][:1], sc["targets"][:1]
+    return dict(name=name, env=sc["env"], robot=sc["robot"], params=sc["params"], edge_starts=np.ascontiguousarray(es),
+                edge_targets=np.ascontiguousarray(et), particles_per_edge=P, label=label)
 
 
 def cluster_params():
@@ -71,9 +90,9 @@ def cluster_params():
     return cp
 
 
-def sdf_bytes_per_point(sc):
+def sdf_bytes_per_point(wl):
     """one trilinear cell fetch = 8 corners x 4 B (4 corners for the 2-D grid)."""
-    return 16 if sc["env"].sdf.shape[2] == 1 else 32
+    return 16 if wl["env"].sdf.shape[2] == 1 else 32
 
 
 class ClockSampler:
@@ -146,57 +165,91 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def host_cores():
+    """(logical CPUs this process may use, physical cores among them)"""
+    try:
+        logical = len(os.sched_getaffinity(0))
+    except AttributeError:
+        logical = os.cpu_count() or 1
+    physical = None
+    try:
+        import psutil
+        physical = psutil.cpu_count(logical=False)
+    except Exception:
+        pass
+    return logical, physical
+
+
 # ---------------------------------------------------------------------------------------------- CPU arm
 
-def cpu_path(sc, cp, sample, tape, reps=1):
-    """The CPU path (oracle, all host threads) on the first `sample` particles of the workload: returns
-    (seconds for sim, seconds for clustering, particle-steps executed, clusters)."""
+def cpu_pass(wl, cp, n_edges):
+    """One pass of the CPU path (oracle, all host threads) over the first n_edges edges of the workload: the oracle's own
+    counter-based tape for those particles, ForwardSimulateRobots, then ClusterParticles per edge.
+    Returns (seconds sim, seconds clustering, seconds tape, particle-steps executed)."""
     from oracle import binding as oracle
-    starts = sc["starts"][:sample]
-    targets = sc["targets"] if sc["targets"].shape[0] == 1 else sc["targets"][:sample]
-    t_sim = t_cl = 0.0
-    steps = 0
-    ncl = 0
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        cfg, coll, stats = oracle.forward_simulate(sc["env"], sc["robot"], sc["params"], starts, targets, tape)
-        t1 = time.perf_counter()
-        labels, n_clusters, _ = oracle.cluster_particles(sc["env"], sc["robot"], cp, cfg)
-        t2 = time.perf_counter()
-        t_sim += t1 - t0
-        t_cl += t2 - t1
-        steps += stats["particle_steps"]
-        ncl = int(n_clusters[0])
-    return t_sim, t_cl, steps, ncl
+    P = wl["particles_per_edge"]
+    n = n_edges * P
+    starts = np.repeat(wl["edge_starts"][:n_edges], P, axis=0)
+    targets = np.repeat(wl["edge_targets"][:n_edges], P, axis=0)
+    t0 = time.perf_counter()
+    tape = oracle.fill_noise_tape_counter(SEED, wl["robot"], wl["params"], n)
+    t1 = time.perf_counter()
+    cfg, coll, stats = oracle.forward_simulate(wl["env"], wl["robot"], wl["params"], starts, targets, tape)
+    t2 = time.perf_counter()
+    oracle.cluster_particles(wl["env"], wl["robot"], cp, cfg, n_edges)
+    t3 = time.perf_counter()
+    return t2 - t1, t3 - t2, t1 - t0, stats["particle_steps"]
 
 
-def auto_cpu_sample(sc, cp, want_seconds=12.0):
-    """Size the CPU sample to roughly `want_seconds` of host work.  Simulation time is linear in the particle count;
-    the clustering half is between quadratic (one blob) and cubic (hierarchical path), so its growth is fitted from
-    two probes."""
-    from uncertainty_planning_core_b200 import abi
-    total = sc["starts"].shape[0]
-    p1, p2 = min(96, total), min(192, total)
-    tape = abi.fill_noise_tape(sc["seed"], sc["robot"], sc["params"], p2)
-    s1, c1, _, _ = cpu_path(sc, cp, p1, np.ascontiguousarray(tape[..., :p1]))
-    s2, c2, _, _ = cpu_path(sc, cp, p2, tape)
-    sim_per = max(s2 / p2, 1e-9)
-    power = 2.0
-    if p2 > p1 and c1 > 1e-5 and c2 > c1:
-        power = min(3.2, max(1.0, np.log(c2 / c1) / np.log(p2 / p1)))
-    coef = max(c2, 1e-7) / (p2 ** power)
-    cap = min(total, 8192)
-    n = p2
-    while n * 2 <= cap and sim_per * (n * 2) + coef * (n * 2) ** power <= want_seconds:
-        n *= 2
-    lo, hi = n, min(cap, n * 2)
-    while hi - lo > 16:
-        mid = (lo + hi) // 2
-        if sim_per * mid + coef * mid ** power <= want_seconds:
-            lo = mid
-        else:
-            hi = mid
-    return int(lo)
+def size_cpu_sample(wl, cp, want_seconds):
+    """Edges in the CPU sample: probe one edge (or a slice of a big single edge), scale linearly (edges are independent)."""
+    E = wl["edge_starts"].shape[0]
+    if E == 1:
+        return 1
+    threads = host_cores()[0]
+    probe = min(E, 2 * threads)      # sets are taken whole per thread from 2 x threads sets on; mixes contact and free-space edges
+    a, b, c, _ = cpu_pass(wl, cp, probe)
+    per_edge = max((a + b + c) / probe, 1e-6)
+    return int(max(probe, min(E, want_seconds / per_edge)))
+
+
+def cpu_sample_workload(wl, cp, want_seconds):
+    """A single big edge (C2 / C3) is sampled by particles instead of by edges: clustering grows faster than linearly with the
+    set size, so the sample is bounded at 4,096 particles."""
+    if wl["edge_starts"].shape[0] > 1:
+        return wl, size_cpu_sample(wl, cp, want_seconds)
+    sub = dict(wl)
+    probe = dict(wl)
+    probe["particles_per_edge"] = min(128, wl["particles_per_edge"])
+    a, b, c, _ = cpu_pass(probe, cp, 1)
+    per_particle = max((a + c) / probe["particles_per_edge"], 1e-9)
+    sub["particles_per_edge"] = int(max(128, min(wl["particles_per_edge"], 4096, want_seconds * 0.5 / per_particle)))
+    return sub, 1
+
+
+def cpu_measure(wl, cp, want_seconds, passes):
+    """`passes` passes over a bounded sample; returns the cpu_baseline dict (value = median pass)."""
+    from oracle import binding as oracle
+    logical, physical = host_cores()
+    oracle.set_num_threads(logical)
+    sample_wl, n_edges = cpu_sample_workload(wl, cp, want_seconds / max(passes, 1))
+    P, S = sample_wl["particles_per_edge"], wl["params"].num_steps
+    rows = [cpu_pass(sample_wl, cp, n_edges) for _ in range(passes)]
+    total = np.array([r[0] + r[1] for r in rows])
+    sim = np.array([r[0] for r in rows])
+    cl = np.array([r[1] for r in rows])
+    units = n_edges * P * S
+    if wl["edge_starts"].shape[0] > 1:
+        desc = "first %d of %d edges x %d particles, %d controller intervals, sim + CRS/distance clustering per edge" % (n_edges, wl["edge_starts"].shape[0], P, S)
+    else:
+        desc = "first %d of %d particles of the edge, %d controller intervals, sim + CRS/distance clustering" % (P, wl["particles_per_edge"], S)
+    return {"value": units / float(np.median(total)), "unit": UNIT, "cores": physical or logical, "logical_cpus": logical, "threads": oracle.num_threads(),
+            "kind": "port", "sample": desc + ", %d passes (value = median pass)" % passes,
+            "value_best_pass": units / float(total.min()), "value_worst_pass": units / float(total.max()),
+            "sim_value": units / float(np.median(sim)), "sim_value_best_pass": units / float(sim.min()),
+            "clustered_per_sec": n_edges * P / max(float(np.median(cl)), 1e-12),
+            "noise_generation_s_per_pass": float(np.median([r[2] for r in rows])),
+            "note": "noise tape generation (oracle, counter-based) is outside the timed part of a pass: the CPU path replays a tape"}, float(total.sum())
 
 
 def run_reference(args):
@@ -204,33 +257,33 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import binding as oracle
-    from uncertainty_planning_core_b200 import abi
     oracle.build()
-    oracle.set_num_threads(os.cpu_count() or 1)
-    sc = make_workload(args, 0)
+    wl = make_workload(args.workload, args.edges, args.particles)
     cp = cluster_params()
-    cores = oracle.num_threads()
-    sample = args.cpu_sample or auto_cpu_sample(sc, cp, want_seconds=8.0)
-    tape = abi.fill_noise_tape(sc["seed"], sc["robot"], sc["params"], sample)
-    S = sc["params"].num_steps
+    passes = max(1, args.steps)
+    logical, physical = host_cores()
+    oracle.set_num_threads(logical)
+    sample_wl, n_edges = cpu_sample_workload(wl, cp, 2.0) if not args.cpu_edges else (wl, args.cpu_edges)
     for _ in range(min(args.warmup, 1)):
-        cpu_path(sc, cp, sample, tape)
-    t0 = time.perf_counter()
-    t_sim = t_cl = 0.0
-    for _ in range(args.steps):
-        a, b, _, ncl = cpu_path(sc, cp, sample, tape)
-        t_sim += a
-        t_cl += b
-    elapsed = time.perf_counter() - t0
-    value = sample * S * args.steps / elapsed
-    desc = "first %d of %d particles of the edge, %d controller intervals, sim + CRS/distance clustering, per step" % (sample, sc["starts"].shape[0], S)
+        cpu_pass(sample_wl, cp, n_edges)
+    rows = [cpu_pass(sample_wl, cp, n_edges) for _ in range(passes)]
+    P, S = sample_wl["particles_per_edge"], wl["params"].num_steps
+    units = n_edges * P * S
+    elapsed = sum(r[0] + r[1] for r in rows)
+    value = units * passes / elapsed
+    if wl["edge_starts"].shape[0] > 1:
+        desc = "first %d of %d edges x %d particles, %d controller intervals, sim + CRS/distance clustering per edge, per step" % (n_edges, wl["edge_starts"].shape[0], P, S)
+    else:
+        desc = "first %d of %d particles of the edge, %d controller intervals, sim + CRS/distance clustering, per step" % (P, wl["particles_per_edge"], S)
+    per = np.array([r[0] + r[1] for r in rows])
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic (seeded boxes SDF, replicated start, truncated-normal noise tape)",
-        "config": {"workload": sc["label"], "sample": desc, "threads": cores},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
-                         "sim_value": sample * S * args.steps / t_sim, "clustered_per_sec": sample * args.steps / max(t_cl, 1e-12)},
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": passes,
+        "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / passes, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic (seeded boxes SDF, seeded edges, counter-based truncated-normal noise)",
+        "config": {"workload": wl["label"], "sample": desc, "threads": oracle.num_threads()},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": physical or logical, "logical_cpus": logical, "kind": "port", "sample": desc,
+                         "value_best_pass": units / float(per.min()), "value_median_pass": units / float(np.median(per)),
+                         "sim_value": units * passes / sum(r[0] for r in rows), "clustered_per_sec": n_edges * P * passes / max(sum(r[1] for r in rows), 1e-12)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -239,10 +292,174 @@ def run_reference(args):
 
 # ---------------------------------------------------------------------------------------------- GPU arm
 
+def write_workload_file(wl, cp, path):
+    """the raw POD descriptors + arrays for scripts/plugin_bench.cpp"""
+    env, robot = wl["env"], wl["robot"]
+    with open(path, "wb") as f:
+        f.write(b"UPCWL01\0")
+        f.write(bytes(env.desc))
+        f.write(bytes(robot.desc))
+        f.write(bytes(wl["params"]))
+        f.write(struct.pack("<6q", 1 if env.convex_segment is not None else 0, 1 if env.occupancy is not None else 0, wl["edge_starts"].shape[0],
+                            wl["edge_targets"].shape[0], wl["particles_per_edge"], robot.width))
+        f.write(struct.pack("<2d", cp.signature_matching_threshold, cp.distance_clustering_threshold))
+        f.write(env.sdf.tobytes())
+        if env.convex_segment is not None:
+            f.write(env.convex_segment.tobytes())
+        if env.occupancy is not None:
+            f.write(env.occupancy.tobytes())
+        f.write(robot.points.tobytes())
+        f.write(np.ascontiguousarray(wl["edge_starts"], dtype=np.float64).tobytes())
+        f.write(np.ascontiguousarray(wl["edge_targets"], dtype=np.float64).tobytes())
+
+
+def run_plugin_driver(wl, cp, mode, steps, warmup, gpus=1):
+    exe = os.path.join(ROOT, "scripts", "plugin_bench")
+    if not os.path.exists(exe):
+        return {"unavailable": "scripts/plugin_bench is not built (run __graft_entry__.build())"}
+    path = tempfile.mktemp(suffix=".upcwl")
+    try:
+        write_workload_file(wl, cp, path)
+        env = dict(os.environ)
+        env["OMP_NUM_THREADS"] = str(host_cores()[0])
+        out = subprocess.run([exe, path, mode, str(steps), str(warmup), str(gpus)], capture_output=True, text=True, timeout=900, env=env)
+        if out.returncode != 0:
+            return {"unavailable": "plugin_bench exited %d: %s" % (out.returncode, (out.stderr or out.stdout).strip()[-300:])}
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    finally:
+        if os.path.exists(path):
+            os.unlink(path)
+
+
+class DeviceBatch:
+    """Device-resident state of one rank for a workload: handle, (optional) communicator, replicated edge arrays, two gather
+    buffers.  step(k) issues one sharded planner-batch step asynchronously on the torch side stream."""
+
+    def __init__(self, wl, cp, world, rank, local_rank, nccl_id, lanes=0):
+        import torch
+        from uncertainty_planning_core_b200 import B200Simulator, abi
+        self.torch, self.abi, self.lib = torch, abi, abi.load_library()
+        self.wl, self.cp, self.world, self.rank = wl, cp, world, rank
+        self.dev = torch.device("cuda", local_rank)
+        self.sim = B200Simulator(wl["env"], wl["robot"], device=local_rank)
+        if lanes:
+            self.sim.SetLanesPerParticle(lanes)
+        self.h = self.sim.handle
+        self.E, self.P = wl["edge_starts"].shape[0], wl["particles_per_edge"]
+        self.width = wl["robot"].width
+        self.lo, self.hi = abi.shard_bounds(self.E, rank, world)
+        cap = (self.E + world - 1) // world
+        self.lay = abi.outcome_layout(self.width, cap * self.P, cap)
+        self.comm = None
+        if world > 1:
+            comm = C.c_void_p()
+            abi.check(self.lib.upc_comm_create(self.h, world, rank, nccl_id.ctypes.data, C.byref(comm)))
+            self.comm = comm
+        self.d_starts = torch.from_numpy(np.ascontiguousarray(wl["edge_starts"].T)).to(self.dev)
+        self.d_targets = torch.from_numpy(np.ascontiguousarray(wl["edge_targets"].T)).to(self.dev)
+        self.blocks = [torch.zeros(self.lay.block_bytes * world, dtype=torch.uint8, device=self.dev) for _ in range(2 if world > 1 else 1)]
+        self.stream_obj = torch.cuda.Stream(device=self.dev)
+        self.stream = self.stream_obj.cuda_stream
+        assert self.stream != 0
+
+    def local_particles(self):
+        return (self.hi - self.lo) * self.P
+
+    def step(self, k, ev=None):
+        abi, lib, lay = self.abi, self.lib, self.lay
+        blocks = self.blocks[k % len(self.blocks)]
+        if self.comm is not None:
+            abi.check(lib.upc_sharded_edge_batch(self.comm, C.byref(self.wl["params"]), C.byref(self.cp), SEED + k, self.E, self.P,
+                                                 self.d_starts.data_ptr(), self.d_targets.data_ptr(), blocks.data_ptr(), self.stream))
+            return
+        base = blocks.data_ptr()
+        n = self.E * self.P
+        if ev:
+            ev[0].record(self.stream_obj)
+        abi.check(lib.upc_forward_simulate_seeded_device(self.h, C.byref(self.wl["params"]), SEED + k, 0, n, self.E, self.d_starts.data_ptr(), self.E,
+                                                         self.d_targets.data_ptr(), base + lay.configs_offset, base + lay.collided_offset, self.stream))
+        if ev:
+            ev[1].record(self.stream_obj)
+        abi.check(lib.upc_cluster_particles_device(self.h, C.byref(self.cp), self.E, self.P, base + lay.configs_offset, base + lay.labels_offset,
+                                                   base + lay.n_clusters_offset, self.stream))
+        if ev:
+            ev[2].record(self.stream_obj)
+
+    def finish(self):
+        """everything issued so far (exchanges included) is complete when the side stream reaches this point"""
+        if self.comm is not None:
+            self.abi.check(self.lib.upc_comm_wait(self.comm, self.stream))
+
+    def cluster_counts(self, k=0):
+        lay = self.lay
+        blk = self.blocks[k % len(self.blocks)].cpu().numpy()
+        out = []
+        for r in range(self.world):
+            lo, hi = self.abi.shard_bounds(self.E, r, self.world)
+            off = r * lay.block_bytes + lay.n_clusters_offset
+            out.append(blk[off:off + 4 * (hi - lo)].view(np.int32))
+        return np.concatenate(out)
+
+    def close(self):
+        if self.comm is not None:
+            self.lib.upc_comm_destroy(self.comm)
+        self.sim.close()
+
+
+def timed_device_steps(batch, steps, warmup, barrier, sampler=None, phase_events=False):
+    """W warm-up steps, then exactly K steps between barriers; returns (total ms, sim ms, clustering ms, stats, clocks)"""
+    torch = batch.torch
+    for k in range(warmup):
+        batch.step(k)
+    batch.finish()
+    barrier()
+    batch.sim.ResetStatistics()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)] if phase_events else None
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    if sampler:
+        sampler.mark_begin()
+    t_begin.record(batch.stream_obj)
+    for k in range(steps):
+        batch.step(warmup + k, evs[k] if evs else None)
+    batch.finish()
+    t_end.record(batch.stream_obj)
+    barrier()
+    if sampler:
+        sampler.mark_end()
+    total_ms = t_begin.elapsed_time(t_end)
+    sim_ms = sum(e[0].elapsed_time(e[1]) for e in evs) if evs else None
+    cl_ms = sum(e[1].elapsed_time(e[2]) for e in evs) if evs else None
+    return total_ms, sim_ms, cl_ms, batch.sim.GetStatistics()
+
+
+def secondary_workload(name, steps, warmup, local_rank):
+    """the `also` key: another BASELINE configuration as a device-resident step (seeded noise, sim + clustering) on one GPU"""
+    import torch
+    wl = make_workload(name)
+    cp = cluster_params()
+    batch = DeviceBatch(wl, cp, 1, 0, local_rank, None)
+    try:
+        def barrier():
+            torch.cuda.synchronize()
+        total_ms, sim_ms, cl_ms, stats = timed_device_steps(batch, steps, warmup, barrier, phase_events=True)
+        n, S = wl["particles_per_edge"], wl["params"].num_steps
+        P, bpp = wl["robot"].num_points, sdf_bytes_per_point(wl)
+        alg = (stats["particle_steps"] + stats["resolver_iterations"]) / steps * P * bpp
+        return {"workload": wl["label"], "value": n * S * steps / (total_ms * 1e-3), "unit": UNIT, "ms_per_step": total_ms / steps,
+                "sim_ms": sim_ms / steps, "clustering_ms": cl_ms / steps, "clusters": int(batch.cluster_counts()[0]),
+                "sim_value": n * S * steps / (sim_ms * 1e-3), "clustered_per_sec": n * steps / (cl_ms * 1e-3),
+                "algorithmic_sdf_gather_gbs": alg / (sim_ms / steps * 1e-3) / 1e9, "lanes_per_particle": "auto",
+                "collided_fraction": stats["collided_particles"] / max(stats["particles_simulated"], 1),
+                "resolver_iterations_per_particle_step": stats["resolver_iterations"] / max(stats["particle_steps"], 1)}
+    finally:
+        batch.close()
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from uncertainty_planning_core_b200 import B200Simulator, abi, sharding
+    from uncertainty_planning_core_b200 import abi
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -250,269 +467,182 @@ def run_b200(args):
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % args.gpus
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    # every rank runs its own attempt of the same planner edge (the planner repeats an edge `edge_attempt_count` times,
-    # uncertainty_planning_core.hpp:61): same endpoints, independent noise, equal work per GPU
-    sc = make_workload(args, edge=0)
-    cp = cluster_params()
-    params = sc["params"]
-    robot, env = sc["robot"], sc["env"]
-    n = sc["starts"].shape[0]
-    S = params.num_steps
-    width, dof = robot.width, robot.dof
     lib = abi.load_library()
-    sim = B200Simulator(env, robot, device=local_rank)
-    if args.lanes:
-        sim.SetLanesPerParticle(args.lanes)
-    h = sim.handle
-
-    # ---- inputs: a ring of distinct noise tapes whose total footprint exceeds L2, so no step finds its tape cached
-    tape_bytes = int(np.prod(abi.tape_shape(params, dof, n))) * 8
-    ring = max(2, int(np.ceil(1.5 * L2_BYTES / tape_bytes)))
-    ring = min(ring, 8)
-    pinned_tapes = []
-    for r in range(ring):
-        t = torch.empty(abi.tape_shape(params, dof, n), dtype=torch.float64).pin_memory()
-        # particle keys are global: rank r, ring slot k uses particles [(r*ring+k)*n, ...)
-        abi.check(lib.upc_fill_noise_tape(sc["seed"], C.byref(robot.desc), C.byref(params), (rank * ring + r) * n, n, n, t.data_ptr()))
-        pinned_tapes.append(t)
-    d_tapes = [t.to(dev, non_blocking=True) for t in pinned_tapes]
-    h_starts = torch.from_numpy(np.ascontiguousarray(sc["starts"].T)).pin_memory()
-    h_targets = torch.from_numpy(np.ascontiguousarray(sc["targets"].T)).pin_memory()
-    n_targets = sc["targets"].shape[0]
-    d_starts, d_targets = h_starts.to(dev), h_targets.to(dev)
-    d_out = torch.zeros((width, n), dtype=torch.float64, device=dev)
-    d_coll = torch.zeros(n, dtype=torch.uint8, device=dev)
-    d_labels = torch.zeros(n, dtype=torch.int32, device=dev)
-    d_ncl = torch.zeros(1, dtype=torch.int32, device=dev)
-    h_out = torch.empty((width, n), dtype=torch.float64).pin_memory()
-    h_coll = torch.empty(n, dtype=torch.uint8).pin_memory()
-    h_labels = torch.empty(n, dtype=torch.int32).pin_memory()
-    h_ncl = torch.empty(1, dtype=torch.int32).pin_memory()
-    torch.cuda.synchronize()
-    # a side stream: its handle is non-NULL (NULL would select the library's own stream, which torch events cannot see)
-    side = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(side)
-    stream = side.cuda_stream
-    assert stream != 0
-
-    # two sets of outcome buffers: while batch k simulates, the host packs and ships batch k-1 (multi-GPU runs)
-    outs = [(d_out, d_coll, d_labels, d_ncl)]
+    nccl_id = np.zeros(128, dtype=np.uint8)
+    nccl_version = None
     if world > 1:
-        outs.append((torch.zeros_like(d_out), torch.zeros_like(d_coll), torch.zeros_like(d_labels), torch.zeros_like(d_ncl)))
-    in_flight = []
-    pending = []
-
-    def ship(buf):
-        """pack + ONE all-gather of a finished batch; NCCL's own stream carries it, at most two are in flight"""
-        o, c, l, _ = outs[buf]
-        packed, _ = sharding.pack_outcomes(l, c, o)
-        gathered, work = sharding.gather_outcomes(packed, world, async_op=True)
-        in_flight.append((gathered, packed, work))
-        while len(in_flight) > 2:
-            _, _, w = in_flight.pop(0)
-            if w is not None:
-                w.wait()
-
-    def device_step(k, ev=None):
-        tape = d_tapes[k % ring]
-        buf = k % len(outs)
-        o, c, l, ncl = outs[buf]
-        if ev:
-            ev[0].record()
-        abi.check(lib.upc_forward_simulate_device(h, C.byref(params), n, d_starts.data_ptr(), n_targets, d_targets.data_ptr(),
-                                                  tape.data_ptr(), o.data_ptr(), c.data_ptr(), stream))
-        if ev:
-            ev[1].record()
-        if world > 1 and pending:
-            ship(pending.pop(0))   # host-side packing of batch k-1 overlaps the simulation of batch k just enqueued
-        abi.check(lib.upc_cluster_particles_device(h, C.byref(cp), 1, n, o.data_ptr(), l.data_ptr(), ncl.data_ptr(), stream))
-        if ev:
-            ev[2].record()
-        if world > 1:
-            pending.append(buf)
-
-    def drain():
-        while pending:
-            ship(pending.pop(0))
-        while in_flight:
-            _, _, w = in_flight.pop(0)
-            if w is not None:
-                w.wait()
+        # plumbing only: the NCCL communicator of the data path is created by the library from this id
+        dist.init_process_group("gloo")
+        if rank == 0:
+            abi.check(lib.upc_comm_get_unique_id(nccl_id.ctypes.data))
+        t = torch.from_numpy(nccl_id)
+        dist.broadcast(t, 0)
+        v = C.c_int32(0)
+        abi.check(lib.upc_comm_nccl_version(C.byref(v)))
+        nccl_version = v.value
 
     def barrier():
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput: W warm-up steps, then exactly K timed steps
+    def max_over_ranks(values):
+        t = torch.tensor(values, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    wl = make_workload(args.workload, args.edges, args.particles)
+    cp = cluster_params()
+    params, robot, env = wl["params"], wl["robot"], wl["env"]
+    E, P, S = wl["edge_starts"].shape[0], wl["particles_per_edge"], params.num_steps
+    n_total = E * P
+    width = robot.width
+    batch = DeviceBatch(wl, cp, world, rank, local_rank, nccl_id, args.lanes)
+
+    # ---- device-resident throughput: W warm-up steps, then exactly K timed steps between barriers, max over ranks
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    for k in range(args.warmup):
-        device_step(k)
-    drain()
-    barrier()
-    sim.ResetStatistics()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    if sampler:
-        sampler.mark_begin()
-    t_begin.record()
-    for k in range(args.steps):
-        device_step(args.warmup + k, evs[k])
-    drain()
-    t_end.record()
-    barrier()
-    if sampler:
-        sampler.mark_end()
-    total_ms = t_begin.elapsed_time(t_end)
+    total_ms, sim_ms, cl_ms, stats = timed_device_steps(batch, args.steps, args.warmup, barrier, sampler, phase_events=(world == 1))
     clocks = sampler.stop() if sampler else None
-    sim_ms = sum(e[0].elapsed_time(e[1]) for e in evs)
-    cl_ms = sum(e[1].elapsed_time(e[2]) for e in evs)
-    stats = sim.GetStatistics()
-    t = torch.tensor([total_ms, sim_ms, cl_ms], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, sim_ms, cl_ms = [float(v) for v in t.tolist()]
-    particle_steps = n * S * args.steps * world
+        # per-phase times of this rank's shard, measured in a second, un-timed pass without the exchange
+        solo = DeviceBatch(dict(wl, edge_starts=wl["edge_starts"][batch.lo:batch.hi], edge_targets=wl["edge_targets"][batch.lo:batch.hi]), cp, 1, 0, local_rank, None, args.lanes)
+        _, sim_ms, cl_ms, _ = timed_device_steps(solo, min(args.steps, 3), 1, lambda: torch.cuda.synchronize(), phase_events=True)
+        sim_ms, cl_ms = sim_ms * args.steps / min(args.steps, 3), cl_ms * args.steps / min(args.steps, 3)
+        solo.close()
+    total_ms, sim_ms, cl_ms = max_over_ranks([total_ms, sim_ms, cl_ms])
+    ncl_all = batch.cluster_counts(args.warmup + args.steps - 1)
+    particle_steps = n_total * S * args.steps
     value = particle_steps / (total_ms * 1e-3)
 
-    # ---- end to end through the host-pointer C ABI: pinned host buffers in, results back on the host, every step
+    # ---- end to end through the host-pointer C ABI: pinned host buffers in, every result back on the host, every step
+    lo, hi = batch.lo, batch.hi
+    n_local = (hi - lo) * P
+    h_es = torch.from_numpy(np.ascontiguousarray(wl["edge_starts"][lo:hi].T)).pin_memory()
+    h_et = torch.from_numpy(np.ascontiguousarray(wl["edge_targets"][lo:hi].T)).pin_memory()
+    h_out = torch.empty((width, n_local), dtype=torch.float64).pin_memory()
+    h_coll = torch.empty(n_local, dtype=torch.uint8).pin_memory()
+    h_labels = torch.empty(n_local, dtype=torch.int32).pin_memory()
+    h_ncl = torch.empty(hi - lo, dtype=torch.int32).pin_memory()
+
     def e2e_step(k):
-        tape = pinned_tapes[k % ring]
-        abi.check(lib.upc_forward_simulate(h, C.byref(params), n, h_starts.data_ptr(), n_targets, h_targets.data_ptr(), tape.data_ptr(),
-                                           h_out.data_ptr(), h_coll.data_ptr()))
-        abi.check(lib.upc_cluster_particles(h, C.byref(cp), 1, n, h_out.data_ptr(), h_labels.data_ptr(), h_ncl.data_ptr()))
+        abi.check(lib.upc_simulate_and_cluster_edges(batch.h, C.byref(params), C.byref(cp), SEED + k, lo * P, hi - lo, P, h_es.data_ptr(), h_et.data_ptr(),
+                                                     h_out.data_ptr(), h_coll.data_ptr(), h_labels.data_ptr(), h_ncl.data_ptr()))
         return int(h_ncl[0])
 
     for k in range(min(args.warmup, 3)):
         e2e_step(k)
     barrier()
-    sim.ResetStatistics()
+    batch.sim.ResetStatistics()
     t0 = time.perf_counter()
     for k in range(args.steps):
         e2e_step(args.warmup + k)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    e2e_stats = sim.GetStatistics()
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.item())
+    e2e_stats = batch.sim.GetStatistics()
+    e2e_s, h2d, d2h = max_over_ranks([e2e_s, e2e_stats["h2d_bytes"] / args.steps, e2e_stats["d2h_bytes"] / args.steps])
     e2e_value = particle_steps / e2e_s
+    e2e_same = bool(np.array_equal(h_ncl.numpy(), ncl_all[lo:hi]))   # same seeds as the device-resident pass: same outcome
 
     if rank == 0:
         # ---- roofline of the dominant kernel (forward_simulate_kernel): algorithmic SDF gather bytes / measured launch time
         hbm_peak, peak_src = measured_peaks()
-        P = robot.num_points
-        bpp = sdf_bytes_per_point(sc)
+        Pn = robot.num_points
+        bpp = sdf_bytes_per_point(wl)
         ps_launch = stats["particle_steps"] / args.steps
         ri_launch = stats["resolver_iterations"] / args.steps
-        alg_bytes = (ps_launch + ri_launch) * P * bpp            # SURVEY 8d: M*P*corners*4 per particle-step + R_used*P*32
+        alg_bytes = (ps_launch + ri_launch) * Pn * bpp            # M*P*corners*4 per particle-step + R_used*P*corners*4 per resolver iteration
         sim_ms_launch = sim_ms / args.steps
         achieved = alg_bytes / (sim_ms_launch * 1e-3) / 1e9
+        table_bytes = 8 * 4 * (env.sdf.shape[0] + 1) * (env.sdf.shape[1] + 1) * (env.sdf.shape[2] + 1)
+        gather_buffer = table_bytes if table_bytes <= 80 * 2 ** 20 else env.sdf.nbytes
         l2_gbs = C.c_double(0.0)
         fp64 = C.c_double(0.0)
-        abi.check(lib.upc_measure_l2_gather_gbs(h, env.sdf.nbytes, C.byref(l2_gbs)))
-        abi.check(lib.upc_measure_fp64_tflops(h, C.byref(fp64)))
-        compulsory = (tape_bytes + 2 * width * n * 8 + n) / (sim_ms_launch * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_sim_kernel_traffic.json")
-        if args.workload == "c2" and not args.particles and os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("traffic")   # dram bytes of one launch of this kernel, from the committed ncu capture
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": traffic, "kernel": "forward_simulate_kernel", "kernel_ms": sim_ms_launch, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": alg_bytes, "l2_gather_peak_gbs": l2_gbs.value, "frac_of_l2_gather": achieved / max(l2_gbs.value, 1e-9),
+        abi.check(lib.upc_measure_l2_gather_gbs(batch.h, gather_buffer, C.byref(l2_gbs)))
+        abi.check(lib.upc_measure_fp64_tflops(batch.h, C.byref(fp64)))
+        # compulsory HBM traffic of a seeded launch: edge endpoints in, one configuration + one flag per particle out
+        compulsory = (2 * width * (hi - lo) * 8 + (width * 8 + 1) * n_local) / (sim_ms_launch * 1e-3) / 1e9
+        model = {abi.ROBOT_SE2: "Se2Model", abi.ROBOT_SE3: "Se3Model"}.get(robot.kind, "LinkedModelSmall")
+        traffic, traffic_source = None, None
+        tpath = os.path.join(ROOT, "profiles", "r02_sim_kernel_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                tj = json.load(open(tpath)).get(args.workload)
+                if tj and not args.edges and not args.particles:
+                    traffic, traffic_source = tj["traffic"], "committed ncu capture (%s), not measured in this run" % tj.get("source", tpath)
+            except Exception:
+                pass
+        roofline = {"bound": "l2_gather", "achieved": achieved, "peak": l2_gbs.value, "unit": "GB/s", "frac": achieved / max(l2_gbs.value, 1e-9),
+                    "traffic": traffic, "traffic_source": traffic_source,
+                    "kernel": "forward_simulate_kernel<%s, lanes=%s, seeded>" % (model, args.lanes or "auto"), "kernel_ms": sim_ms_launch,
+                    "peak_source": "random 32-byte-sector gather over a %.1f MiB buffer (the size of the SDF table the kernel reads), measured live on this GPU (upc_measure_l2_gather_gbs)" % (gather_buffer / 2 ** 20),
+                    "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes_per_particle_step": Pn * bpp,
+                    "hbm_peak_gbs": hbm_peak, "hbm_peak_source": peak_src, "frac_of_hbm_peak": achieved / hbm_peak,
                     "compulsory_hbm_gbs": compulsory, "fp64_fma_peak_tflops": fp64.value,
-                    "note": "SDF (%.0f MiB) is L2/L1-resident by design, so the gather rate may exceed the HBM copy peak" % (env.sdf.nbytes / 2 ** 20)}
-        # ---- the same kernel with the machine full (rank 0, N = 1, default workload): 10^6 particles of the same edge, one lane each,
-        # first 16 controller intervals - the throughput regime, where the SDF gathers are the bound (north_star: >= 60 % of the L2 roofline)
-        if world == 1 and args.workload == "c2" and not args.particles and not args.no_big_batch:
-            nb, sb = 1000000, 16
-            pb = abi.make_sim_params(sb, params.controller_interval, env.resolution, allow_contacts=True, max_microsteps=params.max_microsteps)
-            tb = torch.from_numpy(abi.fill_noise_tape(sc["seed"] + 99, robot, pb, nb)).to(dev)
-            sbig = torch.from_numpy(np.ascontiguousarray(np.tile(sc["starts"][:1], (nb, 1)).T)).to(dev)
-            obig = torch.zeros_like(sbig)
-            cbig = torch.zeros(nb, dtype=torch.uint8, device=dev)
-            best = 1e30
-            for rep in range(4):
-                sim.ResetStatistics()
-                b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                b0.record()
-                abi.check(lib.upc_forward_simulate_device(h, C.byref(pb), nb, sbig.data_ptr(), n_targets, d_targets.data_ptr(), tb.data_ptr(),
-                                                          obig.data_ptr(), cbig.data_ptr(), stream))
-                b1.record()
-                torch.cuda.synchronize()
-                if rep:
-                    best = min(best, b0.elapsed_time(b1))
-            bst = sim.GetStatistics()
-            big_bytes = (bst["particle_steps"] + bst["resolver_iterations"]) * P * bpp
-            big_gbs = big_bytes / (best * 1e-3) / 1e9
-            roofline["big_batch"] = {"particles": nb, "controller_intervals": sb, "kernel_ms": best, "particle_steps_per_s": nb * sb / (best * 1e-3),
-                                     "achieved": big_gbs, "unit": "GB/s", "frac": big_gbs / hbm_peak, "frac_of_l2_gather": big_gbs / max(l2_gbs.value, 1e-9),
-                                     "tape_gbs": tb.numel() * 8 / (best * 1e-3) / 1e9}
-            del tb, sbig, obig, cbig
+                    "note": "algorithmic gathers = SURVEY 8d nominal bytes; conservative culls skip most of them, so `achieved` is a work rate (see DESIGN.md 7)"}
         # ---- CPU baseline on a bounded sample (rank 0, N = 1 only)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            from oracle import binding as oracle
-            oracle.set_num_threads(os.cpu_count() or 1)
-            sample = args.cpu_sample or auto_cpu_sample(sc, cp)
-            ctape = abi.fill_noise_tape(sc["seed"], robot, params, sample)
-            t_sim, t_cl, steps_done, ncl = cpu_path(sc, cp, sample, ctape)
-            cpu = {"value": sample * S / (t_sim + t_cl), "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
-                   "sample": "first %d of %d particles of the same edge, %d controller intervals, sim + clustering, 1 pass" % (sample, n, S),
-                   "sim_value": sample * S / t_sim, "clustered_per_sec": sample / max(t_cl, 1e-12)}
-            # SURVEY 8d extras: a 1-thread figure, and the distance pass in the reference's own shape (std::function per pair +
-            # a heap-allocated delta vector per pair, uncertainty_contact_planning.hpp:1955-1960) next to the plain loop
-            all_threads = oracle.num_threads()
-            oracle.set_num_threads(1)
-            small = min(256, sample)
-            t1 = time.perf_counter()
-            cfg1, _, _ = oracle.forward_simulate(env, robot, params, sc["starts"][:small], sc["targets"], np.ascontiguousarray(ctape[..., :small]))
-            cpu["sim_value_1_thread"] = small * S / (time.perf_counter() - t1)
-            oracle.set_num_threads(all_threads)
-            m = min(2048, sample)
-            fin = oracle.forward_simulate(env, robot, params, sc["starts"][:m], sc["targets"], np.ascontiguousarray(ctape[..., :m]))[0]
-            t1 = time.perf_counter(); oracle.pair_distances(robot, fin); t2 = time.perf_counter()
-            oracle.pair_distances(robot, fin, reference_style=True); t3 = time.perf_counter()
-            cpu["distance_matrix_pairs_per_sec"] = {"plain_loop": m * (m - 1) / 2 / (t2 - t1), "reference_style": m * (m - 1) / 2 / (t3 - t2), "n": m}
-        h2d = e2e_stats["h2d_bytes"] / args.steps
-        d2h = e2e_stats["d2h_bytes"] / args.steps
+            cpu, _ = cpu_measure(wl, cp, want_seconds=20.0, passes=5)
+        # ---- secondary workloads and the C++ plugin driver (rank 0, N = 1 only)
+        also, e2e_plugin = None, None
+        if world == 1 and not args.no_also and args.workload == "c5" and not args.edges and not args.particles:
+            also = {}
+            for name, st, wu in (("c2", 10, 3), ("c3", 3, 1)):
+                try:
+                    also[name] = secondary_workload(name, st, wu, local_rank)
+                except Exception as exc:  # a secondary measurement must not cost the headline line
+                    also[name] = {"unavailable": repr(exc)[:200]}
+        if world == 1 and not args.no_plugin:
+            e2e_plugin = run_plugin_driver(wl, cp, "edges" if E > 1 else "single", max(2, min(args.steps, 5)), 1)
+            if isinstance(e2e_plugin, dict) and "ms_per_step" in e2e_plugin:
+                e2e_plugin["unit"] = UNIT
+                e2e_plugin["ratio_to_device_step"] = e2e_plugin["ms_per_step"] / (total_ms / args.steps)
+            if also is not None and "c2" in also and "value" in also["c2"]:
+                c2 = make_workload("c2")
+                p2 = run_plugin_driver(c2, cp, "single", 10, 3)
+                if isinstance(p2, dict) and "ms_per_step" in p2:
+                    p2["ratio_to_device_step"] = p2["ms_per_step"] / also["c2"]["ms_per_step"]
+                also["c2"]["e2e_plugin"] = p2
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic (seeded boxes SDF, replicated start, truncated-normal noise tape)",
-            "config": {"workload": sc["label"], "edges_per_step": world, "particles_per_gpu": n,
-                       "sharding": "one attempt of the edge per GPU (same endpoints, independent noise), SDF replicated, one all-gather of outcome records per step, overlapped with the next step's simulation",
-                       "clustering": "CRS signatures (thr 0.125) + distance pass (thr 0.1)",
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic (seeded boxes SDF, seeded edges, counter-based truncated-normal noise drawn in the kernel)",
+            "config": {"workload": wl["label"], "edges": E, "particles_per_edge": P, "edges_per_gpu": hi - lo,
+                       "sharding": "contiguous blocks of edges per GPU (upc_shard_bounds), SDF + robot tables replicated, ONE in-place NCCL all-gather of outcome records per step "
+                                   "issued by the library's communicator (two gather buffers: the exchange of step k overlaps the simulation of step k+1)" if world > 1 else "single GPU",
+                       "nccl_version": nccl_version,
+                       "clustering": "CRS signatures (thr 0.125) + distance pass (thr 0.1), one pass over all edges",
                        "lanes_per_particle": args.lanes or "auto",
-                       "l2": "ring of %d distinct %.0f MB noise tapes (%.0f MB > 126 MB L2) so the streamed input is never cached; the %.0f MiB SDF is "
-                             "deliberately L2-resident across steps, as it is across the edges of a planner run" % (ring, tape_bytes / 1e6, ring * tape_bytes / 1e6, env.sdf.nbytes / 2 ** 20)},
-            "sim": {"value": particle_steps / (sim_ms * 1e-3), "unit": UNIT, "ms_per_step": sim_ms / args.steps},
-            "clustering": {"value": n * args.steps * world / (cl_ms * 1e-3), "unit": "particles clustered/s", "ms_per_step": cl_ms / args.steps,
-                           "clusters": int(d_ncl.item()), "fallback_sets": int(stats["cluster_fallback_calls"])},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps},
+                       "l2": "inputs larger than L2 where they stream: every step writes %.0f MB of outcome records and re-reads them for clustering (126 MB L2); the %.1f MiB SDF table is "
+                             "deliberately cache-resident across steps, as it is across the batches of a planner run; every step uses a new noise seed" % (batch.lay.block_bytes * world / 1e6, gather_buffer / 2 ** 20)},
+            "sim": {"value": particle_steps / (sim_ms * 1e-3), "unit": UNIT, "ms_per_step": sim_ms / args.steps,
+                    "scope": "whole batch on this GPU" if world == 1 else "slowest rank's shard, measured without the exchange"},
+            "clustering": {"value": n_total * args.steps / (cl_ms * 1e-3), "unit": "particles clustered/s", "ms_per_step": cl_ms / args.steps,
+                           "sets_per_sec": E * args.steps / (cl_ms * 1e-3), "clusters_total": int(ncl_all.sum()), "clusters_max_per_edge": int(ncl_all.max()),
+                           "fallback_sets": int(stats["cluster_fallback_calls"])},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "call": "upc_simulate_and_cluster_edges (host pointers, pinned): edge endpoints up, configurations + flags + labels + cluster counts down, every step",
+                    "same_outcome_as_device_pass": e2e_same},
+            "e2e_plugin": e2e_plugin,
             "gpu_launches": int(stats["kernel_launches"]),
             "contact": {"collided_fraction": stats["collided_particles"] / max(stats["particles_simulated"], 1),
                         "resolver_iterations_per_particle_step": stats["resolver_iterations"] / max(stats["particle_steps"], 1)},
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "also": also, "clocks": clocks,
         }
         print(json.dumps(line))
     barrier()
-    sim.close()
+    batch.close()
     if world > 1:
         dist.destroy_process_group()
 
 
 if __name__ == "__main__":
     a = parse_args()
-    # torchrun exports OMP_NUM_THREADS=1; the host-side pieces (tape generation, the CPU arm) are OpenMP code and the
-    # CPU arm is meant to use every host core ("with all the host threads it can use")
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is OpenMP code and is meant to use every host core
     _world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
-    _cores = os.cpu_count() or 1
+    _cores = host_cores()[0]
     os.environ["OMP_NUM_THREADS"] = str(_cores if a.impl == "reference" else max(1, _cores // max(1, _world)))
     if a.impl == "reference":
         run_reference(a)

@@ -322,6 +322,12 @@ int32_t upc_cluster_statistics(upc_handle* h, int64_t n, const double* configs, 
 int32_t upc_measure_l2_gather_gbs(upc_handle* h, int64_t buffer_bytes, double* out_gbs);
 int32_t upc_measure_fp64_tflops(upc_handle* h, double* out_tflops);
 
+/* Device memory for hosts that do not link the CUDA runtime themselves (the C++ shim's multi-GPU path): four grow-only scratch
+ * buffers per handle (slot 0..3; contents are lost when a slot grows) and blocking copies ordered on the handle's stream. */
+int32_t upc_device_scratch(upc_handle* h, int32_t slot, int64_t bytes, void** out);
+int32_t upc_memcpy_to_device(upc_handle* h, void* d_dst, const void* src, int64_t bytes);
+int32_t upc_memcpy_to_host(upc_handle* h, void* dst, const void* d_src, int64_t bytes);
+
 /* blocks until everything queued on the handle's stream has finished */
 int32_t upc_synchronize(upc_handle* h);
 
@@ -331,7 +337,7 @@ int32_t upc_synchronize(upc_handle* h);
  * the environment and robot); a upc_comm ties the handles of one box together through NCCL (bound at run time).
  *   one process per GPU:   rank 0 calls upc_comm_get_unique_id, ships the 128 bytes to the other ranks by any means, every
  *                          rank calls upc_comm_create(handle, world, rank, id)
- *   one process, n GPUs:   upc_comm_create_all(n, handles, comms); bracket per-rank calls with upc_comm_group_start / _end
+ *   one process, n GPUs:   upc_comm_create_all(n, handles, comms) and the *_all entry point below
  */
 typedef struct upc_comm upc_comm;
 #define UPC_COMM_ID_BYTES 128
@@ -342,8 +348,6 @@ int32_t upc_comm_destroy(upc_comm* c);
 int32_t upc_comm_world(const upc_comm* c);
 int32_t upc_comm_rank(const upc_comm* c);
 int32_t upc_comm_nccl_version(int32_t* out);
-int32_t upc_comm_group_start(void);
-int32_t upc_comm_group_end(void);
 /* contiguous, balanced [lo, hi) range of `total` items owned by `rank` */
 void upc_shard_bounds(int64_t total, int32_t rank, int32_t world, int64_t* lo, int64_t* hi);
 
@@ -360,7 +364,10 @@ int32_t upc_outcome_layout_for(int32_t width, int64_t particles, int64_t sets, u
 
 /* In-place all-gather of the outcome blocks (rank r's block at d_blocks + r * block_bytes on every rank), ordered after the
  * work queued on `stream` (NULL = the handle's stream) and executed on the communicator's own stream; `stream` does not wait
- * for it - upc_comm_wait makes a stream wait, upc_comm_synchronize blocks the host. */
+ * for it - upc_comm_wait makes a stream wait, upc_comm_synchronize blocks the host.  Work queued on `stream` after the call
+ * does wait for the exchange issued by the PREVIOUS call, so a caller that alternates between two gather buffers may issue
+ * the next step straight away (the exchange then overlaps the next step's simulation); with a single buffer call
+ * upc_comm_wait before the next step. */
 int32_t upc_comm_all_gather_outcomes(upc_comm* c, void* d_blocks, int64_t block_bytes, void* stream);
 int32_t upc_comm_wait(upc_comm* c, void* stream);
 int32_t upc_comm_synchronize(upc_comm* c);
@@ -374,6 +381,11 @@ int32_t upc_comm_synchronize(upc_comm* c);
 int32_t upc_sharded_edge_batch(upc_comm* c, const upc_sim_params* params, const upc_cluster_params* cparams, uint64_t seed,
                                int64_t n_edges, int64_t particles_per_edge, const double* d_edge_starts, const double* d_edge_targets,
                                void* d_blocks, void* stream);
+/* the same step for all n ranks of a single-process communicator set: one entry per rank in every array (device pointers on
+ * that rank's GPU; streams may be NULL) */
+int32_t upc_sharded_edge_batch_all(int32_t n, upc_comm* const* comms, const upc_sim_params* params, const upc_cluster_params* cparams, uint64_t seed,
+                                   int64_t n_edges, int64_t particles_per_edge, const double* const* d_edge_starts,
+                                   const double* const* d_edge_targets, void* const* d_blocks, void* const* streams);
 
 #ifdef __cplusplus
 }

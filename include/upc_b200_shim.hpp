@@ -27,6 +27,7 @@
 #define UPC_B200_SHIM_HPP
 
 #include <array>
+#include <cstddef>
 #include <cstdint>
 #include <map>
 #include <memory>
@@ -42,6 +43,7 @@
 #ifdef UPC_SHIM_WITH_REFERENCE
 #include <uncertainty_planning_core/simple_simulator_interface.hpp>
 #include <uncertainty_planning_core/simple_robot_models.hpp>
+#include <uncertainty_planning_core/uncertainty_contact_planning.hpp>
 #endif
 
 namespace upc_b200
@@ -52,6 +54,71 @@ inline void check(int32_t code)
     const std::string msg = std::string("upc_b200: ") + upc_last_error();
     if (code == UPC_ERR_INVALID_ARGUMENT) throw std::invalid_argument(msg);
     throw std::runtime_error(msg);
+}
+
+/* ---- reference types mirrored for the stand-alone build ------------------------------------------------------- */
+
+#ifdef UPC_SHIM_WITH_REFERENCE
+using uncertainty_contact_planning::SPATIAL_FEATURE_CLUSTERING_TYPE;
+using uncertainty_contact_planning::CONVEX_REGION_SIGNATURE;
+using uncertainty_contact_planning::ACTUATION_CENTER_CONNECTIVITY;
+using uncertainty_contact_planning::POINT_TO_POINT_MOVEMENT;
+using uncertainty_contact_planning::COMPARE;
+template <typename Configuration, typename ConfigAlloc = std::allocator<Configuration>>
+using ForwardSimulationContactResolverStepTrace = simple_simulator_interface::ForwardSimulationContactResolverStepTrace<Configuration, ConfigAlloc>;
+template <typename Configuration, typename ConfigAlloc = std::allocator<Configuration>>
+using ForwardSimulationResolverTrace = simple_simulator_interface::ForwardSimulationResolverTrace<Configuration, ConfigAlloc>;
+template <typename Configuration, typename ConfigAlloc = std::allocator<Configuration>>
+using ForwardSimulationStepTrace = simple_simulator_interface::ForwardSimulationStepTrace<Configuration, ConfigAlloc>;
+typedef Eigen::VectorXd ControlVector;
+inline ControlVector MakeControlVector(const double* v, int n) { ControlVector out(n); for (int i = 0; i < n; i++) out(i) = v[i]; return out; }
+#else
+/* uncertainty_contact_planning.hpp:52, same enumerators in the same order (CRS = 0, AC = 1, PTPM = 2, COMPARE = 3) */
+enum SPATIAL_FEATURE_CLUSTERING_TYPE {CONVEX_REGION_SIGNATURE, ACTUATION_CENTER_CONNECTIVITY, POINT_TO_POINT_MOVEMENT, COMPARE};
+/* simple_simulator_interface.hpp:40-63, with std::vector<double> standing in for Eigen::VectorXd */
+typedef std::vector<double> ControlVector;
+inline ControlVector MakeControlVector(const double* v, int n) { return ControlVector(v, v + n); }
+template <typename Configuration, typename ConfigAlloc = std::allocator<Configuration>>
+struct ForwardSimulationContactResolverStepTrace
+{
+    std::vector<Configuration, ConfigAlloc> contact_resolution_steps;
+};
+template <typename Configuration, typename ConfigAlloc = std::allocator<Configuration>>
+struct ForwardSimulationResolverTrace
+{
+    ControlVector control_input;
+    ControlVector control_input_step;
+    std::vector<ForwardSimulationContactResolverStepTrace<Configuration, ConfigAlloc>> contact_resolver_steps;
+};
+template <typename Configuration, typename ConfigAlloc = std::allocator<Configuration>>
+struct ForwardSimulationStepTrace
+{
+    std::vector<ForwardSimulationResolverTrace<Configuration, ConfigAlloc>> resolver_steps;
+    inline void Reset() { resolver_steps.clear(); }
+};
+/* simple_simulator_interface.hpp:66-86 */
+template <typename Configuration, typename ConfigAlloc = std::allocator<Configuration>>
+inline std::vector<Configuration, ConfigAlloc> ExtractTrajectoryFromTrace(const ForwardSimulationStepTrace<Configuration, ConfigAlloc>& trace)
+{
+    std::vector<Configuration, ConfigAlloc> execution_trajectory;
+    execution_trajectory.reserve(trace.resolver_steps.size());
+    for (size_t step_idx = 0; step_idx < trace.resolver_steps.size(); step_idx++)
+        execution_trajectory.push_back(trace.resolver_steps[step_idx].contact_resolver_steps.back().contact_resolution_steps.back());
+    return execution_trajectory;
+}
+#endif
+
+/*
+ * SPATIAL_FEATURE_CLUSTERING_TYPE (uncertainty_contact_planning.hpp:52: CRS = 0, AC = 1, PTPM = 2, COMPARE = 3) -> UPC_FEATURE_*
+ * (NONE = 0, CRS = 1, AC = 2, PTPM = 3).  COMPARE runs all three and prints a comparison (uncertainty_contact_planning.hpp:1915-1945):
+ * a diagnostic mode, not offered here.
+ */
+inline int32_t FromReferenceClusteringType(const SPATIAL_FEATURE_CLUSTERING_TYPE clustering_type)
+{
+    if (clustering_type == CONVEX_REGION_SIGNATURE) return UPC_FEATURE_CONVEX_REGION_SIGNATURE;
+    if (clustering_type == ACTUATION_CENTER_CONNECTIVITY) return UPC_FEATURE_ACTUATION_CENTER_CONNECTIVITY;
+    if (clustering_type == POINT_TO_POINT_MOVEMENT) return UPC_FEATURE_POINT_TO_POINT_MOVEMENT;
+    throw std::invalid_argument("upc_b200: spatial feature clustering type must be CRS, AC or PTPM (COMPARE is not supported)");
 }
 
 /* ---- configuration marshalling ------------------------------------------------------------------------- */
@@ -192,14 +259,18 @@ public:
                   const simple_simulator_interface::SurfaceNormalGrid& surface_normals_grid, const int32_t debug_level,
                   const EnvironmentDescription& env_desc, const RobotDescription& robot_desc, const SolverConfig& solver = SolverConfig(), int device = 0)
         : simple_simulator_interface::SimulatorInterface<Robot, Configuration, RNG, ConfigAlloc>(environment, environment_sdf, surface_normals_grid, debug_level),
-          env_(env_desc), robot_(robot_desc), solver_(solver), handle_(new Handle(env_desc, robot_desc, device)) {}
+          env_(env_desc), robot_(robot_desc), solver_(solver), handle_(new Handle(env_desc, robot_desc, device)) { env_.finalize(); robot_.finalize(); }
 #define UPC_SHIM_OVERRIDE override
 #define UPC_SHIM_PUBLISHER , ros::Publisher& display_debug_publisher
 #define UPC_SHIM_UNUSED_PUBLISHER (void)display_debug_publisher;
 #else
     B200Simulator(const EnvironmentDescription& env_desc, const RobotDescription& robot_desc, const int32_t debug_level = 0,
                   const SolverConfig& solver = SolverConfig(), int device = 0)
-        : env_(env_desc), robot_(robot_desc), solver_(solver), handle_(new Handle(env_desc, robot_desc, device)), debug_level_(debug_level) {}
+        : env_(env_desc), robot_(robot_desc), solver_(solver), handle_(new Handle(env_desc, robot_desc, device)), debug_level_(debug_level)
+    {
+        env_.finalize(); /* the copies point into their own storage, not the caller's */
+        robot_.finalize();
+    }
 #define UPC_SHIM_OVERRIDE
 #define UPC_SHIM_PUBLISHER
 #define UPC_SHIM_UNUSED_PUBLISHER
@@ -259,90 +330,118 @@ public:
         const int width = Traits::width(start_positions[0]);
         const upc_sim_params params = MakeParams(forward_simulation_time, simulation_shortcut_distance, use_individual_jacobians, allow_contacts);
         /* structure-of-arrays staging */
-        std::vector<double> starts((size_t)width * n), targets((size_t)width * target_positions.size()), out((size_t)width * n);
-        std::vector<double> tmp((size_t)width);
-        for (size_t i = 0; i < n; i++)
-        {
-            Traits::flatten(start_positions[i], tmp.data());
-            for (int c = 0; c < width; c++) starts[(size_t)c * n + i] = tmp[(size_t)c];
-        }
-        for (size_t i = 0; i < target_positions.size(); i++)
-        {
-            Traits::flatten(target_positions[i], tmp.data());
-            for (int c = 0; c < width; c++) targets[(size_t)c * target_positions.size() + i] = tmp[(size_t)c];
-        }
-        /* Noise: the caller's generator is advanced by ONE draw per call (a 64-bit tape seed), and particle i then
-         * draws from its own stream keyed by (seed, i) - results are independent of OpenMP thread counts, which the
-         * reference's per-thread generators (uncertainty_contact_planning.hpp:349-356) are not. */
-        std::uniform_int_distribution<uint64_t> seed_dist(0, std::numeric_limits<uint64_t>::max());
-        const uint64_t seed = seed_dist(rng[0]);
-        std::vector<double> tape((size_t)upc_tape_doubles_per_particle(&params, robot_.desc.dof) * n);
-        check(upc_fill_noise_tape(seed, &robot_.desc, &params, 0, (int64_t)n, (int64_t)n, tape.data()));
+        const size_t nt = target_positions.size();
+        std::vector<double> starts((size_t)width * n), targets((size_t)width * nt), out((size_t)width * n);
+        FlattenToSoa(start_positions, width, starts.data());
+        FlattenToSoa(target_positions, width, targets.data());
+        /* Noise: the caller's generator is advanced by ONE draw per call (a 64-bit seed); particle i then draws from the
+         * counter-based stream (seed, i) inside the kernel - no tape is generated or shipped, and results are
+         * independent of OpenMP thread counts, which the reference's per-thread generators
+         * (uncertainty_contact_planning.hpp:349-356) are not. */
+        const uint64_t seed = NextSeed(rng[0]);
         std::vector<uint8_t> collided(n);
-        check(upc_forward_simulate(handle_->get(), &params, (int64_t)n, starts.data(), (int64_t)target_positions.size(), targets.data(), tape.data(),
-                                   out.data(), collided.data()));
-        results.reserve(n);
-        for (size_t i = 0; i < n; i++)
+        check(upc_forward_simulate_seeded(handle_->get(), &params, seed, 0, (int64_t)n, (int64_t)n, starts.data(), (int64_t)nt, targets.data(),
+                                          out.data(), collided.data()));
+        results.resize(n, std::make_pair(start_positions[0], false));
+        const double* outp = out.data();
+#pragma omp parallel for schedule(static) if (n > 4096)
+        for (int64_t i = 0; i < (int64_t)n; i++)
         {
-            for (int c = 0; c < width; c++) tmp[(size_t)c] = out[(size_t)c * n + i];
-            results.push_back(std::make_pair(Traits::inflate(tmp.data(), start_positions[i]), collided[i] != 0));
+            double tmp[16];
+            for (int c = 0; c < width; c++) tmp[c] = outp[(size_t)c * n + (size_t)i];
+            results[(size_t)i] = std::make_pair(Traits::inflate(tmp, start_positions[(size_t)i]), collided[(size_t)i] != 0);
         }
         return results;
     }
 
-    /* simple_simulator_interface.hpp:621 (tracing is a host-side feature of the single-particle path; the batched
-     * kernels record no trace, matching the reference which passes none at uncertainty_contact_planning.hpp:2065) */
+    /* simple_simulator_interface.hpp:621 without a trace (the form the batched callers use) */
     std::pair<Configuration, bool> ForwardSimulateRobot(const Robot& immutable_robot, const Configuration& start_position, const Configuration& target_position,
                                                         RNG& rng, const double forward_simulation_time, const double simulation_shortcut_distance,
                                                         const bool use_individual_jacobians, const bool allow_contacts UPC_SHIM_PUBLISHER) const
     {
         UPC_SHIM_UNUSED_PUBLISHER
-        std::vector<Configuration, ConfigAlloc> s(1, start_position), t(1, target_position);
-        std::vector<RNG> rngs(1, rng);
-        std::vector<std::pair<Configuration, bool>> r = ForwardSimulateRobots(immutable_robot, s, t, rngs, forward_simulation_time, simulation_shortcut_distance,
-                                                                              use_individual_jacobians, allow_contacts
-#ifdef UPC_SHIM_WITH_REFERENCE
-                                                                              , display_debug_publisher
-#endif
-        );
-        rng = rngs[0];
-        return r[0];
+        ForwardSimulationStepTrace<Configuration, ConfigAlloc> unused;
+        return SimulateOne(immutable_robot, start_position, target_position, rng, forward_simulation_time, simulation_shortcut_distance,
+                           use_individual_jacobians, allow_contacts, unused, false);
     }
 
-#ifdef UPC_SHIM_WITH_REFERENCE
+    /* simple_simulator_interface.hpp:621 - one particle with an optional trace: one ForwardSimulationResolverTrace per controller
+     * interval executed, carrying the control input, the control step per microstep and the resolved configuration of the interval
+     * (the entry ExtractTrajectoryFromTrace :66-86 reads; callers uncertainty_contact_planning.hpp:510, :1171) */
     std::pair<Configuration, bool> ForwardSimulateRobot(const Robot& immutable_robot, const Configuration& start_position, const Configuration& target_position,
                                                         RNG& rng, const double forward_simulation_time, const double simulation_shortcut_distance,
                                                         const bool use_individual_jacobians, const bool allow_contacts,
-                                                        simple_simulator_interface::ForwardSimulationStepTrace<Configuration, ConfigAlloc>& trace,
-                                                        const bool enable_tracing, ros::Publisher& display_debug_publisher) const override
+                                                        ForwardSimulationStepTrace<Configuration, ConfigAlloc>& trace,
+                                                        const bool enable_tracing UPC_SHIM_PUBLISHER) const UPC_SHIM_OVERRIDE
     {
-        const std::pair<Configuration, bool> r = ForwardSimulateRobot(immutable_robot, start_position, target_position, rng, forward_simulation_time,
-                                                                      simulation_shortcut_distance, use_individual_jacobians, allow_contacts, display_debug_publisher);
-        if (enable_tracing)
-        {
-            /* the trace contract (simple_simulator_interface.hpp:66-86) only needs the resolved configuration per step; the
-             * device path reports the end of the edge */
-            simple_simulator_interface::ForwardSimulationResolverTrace<Configuration, ConfigAlloc> step;
-            simple_simulator_interface::ForwardSimulationContactResolverStepTrace<Configuration, ConfigAlloc> contact;
-            contact.contact_resolution_steps.push_back(r.first);
-            step.contact_resolver_steps.push_back(contact);
-            trace.resolver_steps.push_back(step);
-        }
-        return r;
+        UPC_SHIM_UNUSED_PUBLISHER
+        return SimulateOne(immutable_robot, start_position, target_position, rng, forward_simulation_time, simulation_shortcut_distance,
+                           use_individual_jacobians, allow_contacts, trace, enable_tracing);
     }
+
+#ifdef UPC_SHIM_WITH_REFERENCE
+    /* simple_simulator_interface.hpp:619 */
     std::pair<Configuration, bool> ForwardSimulateMutableRobot(Robot& mutable_robot, const Configuration& target_position, RNG& rng,
                                                                const double forward_simulation_time, const double simulation_shortcut_distance,
                                                                const bool use_individual_jacobians, const bool allow_contacts,
-                                                               simple_simulator_interface::ForwardSimulationStepTrace<Configuration, ConfigAlloc>& trace,
+                                                               ForwardSimulationStepTrace<Configuration, ConfigAlloc>& trace,
                                                                const bool enable_tracing, ros::Publisher& display_debug_publisher) const override
     {
-        const std::pair<Configuration, bool> r = ForwardSimulateRobot(mutable_robot, mutable_robot.GetPosition(), target_position, rng, forward_simulation_time,
-                                                                      simulation_shortcut_distance, use_individual_jacobians, allow_contacts, trace,
-                                                                      enable_tracing, display_debug_publisher);
+        (void)display_debug_publisher;
+        const std::pair<Configuration, bool> r = SimulateOne(mutable_robot, mutable_robot.GetPosition(), target_position, rng, forward_simulation_time,
+                                                             simulation_shortcut_distance, use_individual_jacobians, allow_contacts, trace, enable_tracing);
         mutable_robot.UpdatePosition(r.first);
         return r;
     }
 #endif
+
+    /*
+     * The planner-batch step (BASELINE config 5; what a speculative multi-edge extension of
+     * uncertainty_contact_planning.hpp:2301-2409 would issue): for every candidate edge e, particles_per_edge particles from
+     * edge_starts[e] towards edge_targets[e] (ForwardSimulateParticles :2039-2071), then the edge's outcome clustered
+     * (ClusterParticles :1986-2034).  ONE simulation launch and ONE clustering pass on the device; result[e] = the clusters of
+     * edge e in the shape ClusterParticles returns them.
+     */
+    template <typename Clustering>
+    std::vector<std::vector<std::vector<std::pair<Configuration, bool>>>> SimulateAndClusterEdges(
+        const Robot& immutable_robot, const std::vector<Configuration, ConfigAlloc>& edge_starts, const std::vector<Configuration, ConfigAlloc>& edge_targets,
+        const size_t particles_per_edge, std::vector<RNG>& rng, const double forward_simulation_time, const double simulation_shortcut_distance,
+        const bool use_individual_jacobians, const bool allow_contacts, const Clustering& clustering) const
+    {
+        (void)immutable_robot;
+        const size_t E = edge_starts.size(), P = particles_per_edge, n = E * P;
+        if (edge_targets.size() != E) throw std::invalid_argument("one target per edge");
+        if (rng.empty()) throw std::invalid_argument("at least one PRNG is required");
+        std::vector<std::vector<std::vector<std::pair<Configuration, bool>>>> result(E);
+        if (n == 0) return result;
+        const int width = Traits::width(edge_starts[0]);
+        const upc_sim_params params = MakeParams(forward_simulation_time, simulation_shortcut_distance, use_individual_jacobians, allow_contacts);
+        std::vector<double> starts((size_t)width * E), targets((size_t)width * E), out((size_t)width * n);
+        FlattenToSoa(edge_starts, width, starts.data());
+        FlattenToSoa(edge_targets, width, targets.data());
+        std::vector<uint8_t> collided(n);
+        std::vector<int32_t> labels(n), n_clusters(E);
+        const uint64_t seed = NextSeed(rng[0]);
+        check(upc_simulate_and_cluster_edges(handle_->get(), &params, &clustering.params(), seed, 0, (int64_t)E, (int64_t)P, starts.data(), targets.data(),
+                                             out.data(), collided.data(), labels.data(), n_clusters.data()));
+        const double* outp = out.data();
+#pragma omp parallel for schedule(static) if (E > 16)
+        for (int64_t e = 0; e < (int64_t)E; e++)
+        {
+            std::vector<std::vector<std::pair<Configuration, bool>>>& clusters = result[(size_t)e];
+            clusters.resize((size_t)n_clusters[(size_t)e]);
+            double tmp[16];
+            for (size_t k = 0; k < P; k++)
+            {
+                const size_t i = (size_t)e * P + k;
+                const bool hit = collided[i] != 0;
+                if (hit && !allow_contacts) continue; /* uncertainty_contact_planning.hpp:2019 */
+                for (int c = 0; c < width; c++) tmp[c] = outp[(size_t)c * n + i];
+                clusters[(size_t)labels[i]].push_back(std::make_pair(Traits::inflate(tmp, edge_starts[(size_t)e]), hit));
+            }
+        }
+        return result;
+    }
 
     upc_sim_params MakeParams(const double forward_simulation_time, const double simulation_shortcut_distance, const bool use_individual_jacobians,
                               const bool allow_contacts) const
@@ -366,7 +465,66 @@ public:
         return p;
     }
 
+    const RobotDescription& robot_description() const { return robot_; }
+    const EnvironmentDescription& environment_description() const { return env_; }
+
+    /* one 64-bit draw from the caller's generator: the key of a call's noise streams */
+    static uint64_t NextSeed(RNG& generator)
+    {
+        std::uniform_int_distribution<uint64_t> seed_dist(0, std::numeric_limits<uint64_t>::max());
+        return seed_dist(generator);
+    }
+
+    /* vector of configurations -> [C][n] doubles */
+    static void FlattenToSoa(const std::vector<Configuration, ConfigAlloc>& configs, const int width, double* soa)
+    {
+        const size_t n = configs.size();
+#pragma omp parallel for schedule(static) if (n > 4096)
+        for (int64_t i = 0; i < (int64_t)n; i++)
+        {
+            double tmp[16];
+            Traits::flatten(configs[(size_t)i], tmp);
+            for (int c = 0; c < width; c++) soa[(size_t)c * n + (size_t)i] = tmp[c];
+        }
+    }
+
 protected:
+    std::pair<Configuration, bool> SimulateOne(const Robot& immutable_robot, const Configuration& start_position, const Configuration& target_position, RNG& rng,
+                                               const double forward_simulation_time, const double simulation_shortcut_distance,
+                                               const bool use_individual_jacobians, const bool allow_contacts,
+                                               ForwardSimulationStepTrace<Configuration, ConfigAlloc>& trace, const bool enable_tracing) const
+    {
+        (void)immutable_robot;
+        const int width = Traits::width(start_position), dof = robot_.desc.dof;
+        const upc_sim_params params = MakeParams(forward_simulation_time, simulation_shortcut_distance, use_individual_jacobians, allow_contacts);
+        std::vector<double> start((size_t)width), target((size_t)width), out((size_t)width);
+        Traits::flatten(start_position, start.data());
+        Traits::flatten(target_position, target.data());
+        const uint64_t seed = NextSeed(rng);
+        uint8_t collided = 0;
+        if (!enable_tracing)
+        {
+            check(upc_forward_simulate_seeded(handle_->get(), &params, seed, 0, 1, 1, start.data(), 1, target.data(), out.data(), &collided));
+            return std::make_pair(Traits::inflate(out.data(), start_position), collided != 0);
+        }
+        const size_t S = (size_t)params.num_steps;
+        std::vector<double> trace_configs(S * (size_t)width), trace_controls(S * 2 * (size_t)dof);
+        int32_t trace_steps[2] = {0, 0};
+        check(upc_forward_simulate_traced(handle_->get(), &params, 1, start.data(), 1, target.data(), nullptr, seed, 0, out.data(), &collided,
+                                          trace_configs.data(), trace_controls.data(), trace_steps));
+        for (int32_t step = 0; step < trace_steps[0]; step++)
+        {
+            ForwardSimulationResolverTrace<Configuration, ConfigAlloc> step_trace;
+            step_trace.control_input = MakeControlVector(&trace_controls[(size_t)step * 2 * (size_t)dof], dof);
+            step_trace.control_input_step = MakeControlVector(&trace_controls[(size_t)step * 2 * (size_t)dof + (size_t)dof], dof);
+            ForwardSimulationContactResolverStepTrace<Configuration, ConfigAlloc> resolved;
+            resolved.contact_resolution_steps.push_back(Traits::inflate(&trace_configs[(size_t)step * (size_t)width], start_position));
+            step_trace.contact_resolver_steps.push_back(resolved);
+            trace.resolver_steps.push_back(step_trace);
+        }
+        return std::make_pair(Traits::inflate(out.data(), start_position), collided != 0);
+    }
+
     EnvironmentDescription env_;
     RobotDescription robot_;
     SolverConfig solver_;
@@ -384,13 +542,54 @@ class B200OutcomeClustering
 public:
     typedef ConfigTraits<Configuration> Traits;
 
-    B200OutcomeClustering(upc_handle* handle, const int32_t clustering_type, const double signature_matching_threshold, const double distance_clustering_threshold)
+    /* clustering_type is the reference's enum (uncertainty_contact_planning.hpp:52, the value the planner holds in
+     * spatial_feature_clustering_type_, :144); thresholds as at :150-151 */
+    B200OutcomeClustering(upc_handle* handle, const SPATIAL_FEATURE_CLUSTERING_TYPE clustering_type, const double signature_matching_threshold,
+                          const double distance_clustering_threshold)
         : handle_(handle)
     {
         params_ = upc_cluster_params{};
-        params_.feature_type = clustering_type;
+        params_.feature_type = FromReferenceClusteringType(clustering_type);
         params_.signature_matching_threshold = signature_matching_threshold;
         params_.distance_clustering_threshold = distance_clustering_threshold;
+    }
+
+    /* distance pass only (no spatial-feature first pass): not a mode of the reference, used for the clustering sweep */
+    static B200OutcomeClustering DistanceOnly(upc_handle* handle, const double distance_clustering_threshold)
+    {
+        B200OutcomeClustering c(handle, CONVEX_REGION_SIGNATURE, 0.0, distance_clustering_threshold);
+        c.params_.feature_type = UPC_FEATURE_NONE;
+        return c;
+    }
+
+    /*
+     * POINT_TO_POINT_MOVEMENT needs the simulator (uncertainty_contact_planning.hpp:1801-1863: n*(n-1) pair simulations of
+     * step_duration_ with shortcut goal_distance_threshold_ / 2, contacts allowed, :1826): pair_params as the simulator's
+     * MakeParams(step_duration, goal_distance_threshold * 0.5, use_individual_jacobians, true); every ClusterParticles call draws
+     * the pair simulations' seeded noise from `seed`.
+     */
+    void EnablePointToPointMovement(const upc_sim_params& pair_params, const double goal_distance_threshold, const uint64_t seed)
+    {
+        ptpm_params_ = pair_params;
+        ptpm_params_.allow_contacts = 1;
+        params_.goal_distance_threshold = goal_distance_threshold;
+        params_.ptpm_seed = seed;
+        params_.ptpm_tape = nullptr;
+        has_ptpm_ = true;
+    }
+
+    B200OutcomeClustering(const B200OutcomeClustering& o) : handle_(o.handle_), params_(o.params_), ptpm_params_(o.ptpm_params_), has_ptpm_(o.has_ptpm_) {}
+    B200OutcomeClustering& operator=(const B200OutcomeClustering& o)
+    {
+        handle_ = o.handle_; params_ = o.params_; ptpm_params_ = o.ptpm_params_; has_ptpm_ = o.has_ptpm_;
+        return *this;
+    }
+
+    /* the POD parameter block handed to the C ABI (ptpm_sim points into this object) */
+    const upc_cluster_params& params() const
+    {
+        params_.ptpm_sim = has_ptpm_ ? &ptpm_params_ : nullptr;
+        return params_;
     }
 
     /* index clusters of one particle set, numbered by smallest member */
@@ -408,7 +607,7 @@ public:
         }
         std::vector<int32_t> labels(n);
         int32_t n_clusters = 0;
-        check(upc_cluster_particles(handle_, &params_, 1, (int64_t)n, soa.data(), labels.data(), &n_clusters));
+        check(upc_cluster_particles(handle_, &params(), 1, (int64_t)n, soa.data(), labels.data(), &n_clusters));
         clusters.resize((size_t)n_clusters);
         for (size_t i = 0; i < n; i++) clusters[(size_t)labels[i]].push_back(i);
         return clusters;
@@ -490,9 +689,170 @@ public:
         return r;
     }
 
+    /* ClusterParticles for many equally sized particle sets in ONE device pass (the per-edge outcomes of an edge batch):
+     * result[s] = ClusterParticles(sets[s], allow_contacts) */
+    std::vector<std::vector<std::vector<std::pair<Configuration, bool>>>> ClusterParticleSets(
+        const std::vector<std::vector<std::pair<Configuration, bool>>>& sets, const bool allow_contacts) const
+    {
+        const size_t S = sets.size();
+        std::vector<std::vector<std::vector<std::pair<Configuration, bool>>>> result(S);
+        if (S == 0) return result;
+        const size_t P = sets[0].size();
+        for (size_t k = 0; k < S; k++)
+            if (sets[k].size() != P) throw std::invalid_argument("ClusterParticleSets: all particle sets must have the same size");
+        if (P == 0) return result;
+        if (P == 1)
+        {
+            for (size_t k = 0; k < S; k++) result[k].push_back(sets[k]); /* :1988-1995: a single particle is its own cluster */
+            return result;
+        }
+        const int width = Traits::width(sets[0][0].first);
+        const size_t n = S * P;
+        std::vector<double> soa((size_t)width * n);
+#pragma omp parallel for schedule(static) if (S > 16)
+        for (int64_t k = 0; k < (int64_t)S; k++)
+        {
+            double tmp[16];
+            for (size_t e = 0; e < P; e++)
+            {
+                Traits::flatten(sets[(size_t)k][e].first, tmp);
+                for (int c = 0; c < width; c++) soa[(size_t)c * n + (size_t)k * P + e] = tmp[c];
+            }
+        }
+        std::vector<int32_t> labels(n), n_clusters(S);
+        check(upc_cluster_particles(handle_, &params(), (int64_t)S, (int64_t)P, soa.data(), labels.data(), n_clusters.data()));
+#pragma omp parallel for schedule(static) if (S > 16)
+        for (int64_t k = 0; k < (int64_t)S; k++)
+        {
+            result[(size_t)k].resize((size_t)n_clusters[(size_t)k]);
+            for (size_t e = 0; e < P; e++)
+            {
+                const std::pair<Configuration, bool>& particle = sets[(size_t)k][e];
+                if ((particle.second == false) || allow_contacts) result[(size_t)k][(size_t)labels[(size_t)k * P + e]].push_back(particle);
+            }
+        }
+        return result;
+    }
+
 private:
     upc_handle* handle_;
-    upc_cluster_params params_;
+    mutable upc_cluster_params params_;
+    upc_sim_params ptpm_params_{};
+    bool has_ptpm_ = false;
+};
+
+/* ---- one box, several GPUs ------------------------------------------------------------------------------------------ */
+
+/*
+ * The planner-batch step sharded over the GPUs of one box: every device holds its own copy of the
+ * environment and the robot (a complete simulator), candidate edges are split into contiguous blocks, each device simulates
+ * and clusters its block, and ONE NCCL all-gather leaves the outcome records of the whole batch on every device; the host
+ * reads them from the first.  Noise is keyed by global particle index, so the result does not depend on the number of devices.
+ */
+template <typename Robot, typename Configuration, typename RNG, typename ConfigAlloc = std::allocator<Configuration>>
+class ShardedSimulator
+{
+public:
+    typedef B200Simulator<Robot, Configuration, RNG, ConfigAlloc> Simulator;
+    typedef ConfigTraits<Configuration> Traits;
+
+    ShardedSimulator(const EnvironmentDescription& env_desc, const RobotDescription& robot_desc, const std::vector<int>& devices,
+                     const SolverConfig& solver = SolverConfig())
+    {
+        if (devices.empty()) throw std::invalid_argument("ShardedSimulator needs at least one device");
+        for (size_t r = 0; r < devices.size(); r++) simulators_.push_back(std::shared_ptr<Simulator>(new Simulator(env_desc, robot_desc, 0, solver, devices[r])));
+        std::vector<upc_handle*> handles;
+        for (size_t r = 0; r < devices.size(); r++) handles.push_back(simulators_[r]->handle());
+        comms_.assign(devices.size(), nullptr);
+        check(upc_comm_create_all((int32_t)devices.size(), handles.data(), comms_.data()));
+    }
+    ~ShardedSimulator()
+    {
+        for (size_t r = 0; r < comms_.size(); r++) upc_comm_destroy(comms_[r]);
+    }
+    ShardedSimulator(const ShardedSimulator&) = delete;
+    ShardedSimulator& operator=(const ShardedSimulator&) = delete;
+
+    size_t world() const { return simulators_.size(); }
+    const Simulator& simulator(size_t rank) const { return *simulators_[rank]; }
+
+    /* same contract as B200Simulator::SimulateAndClusterEdges */
+    template <typename Clustering>
+    std::vector<std::vector<std::vector<std::pair<Configuration, bool>>>> SimulateAndClusterEdges(
+        const Robot& immutable_robot, const std::vector<Configuration, ConfigAlloc>& edge_starts, const std::vector<Configuration, ConfigAlloc>& edge_targets,
+        const size_t particles_per_edge, std::vector<RNG>& rng, const double forward_simulation_time, const double simulation_shortcut_distance,
+        const bool use_individual_jacobians, const bool allow_contacts, const Clustering& clustering)
+    {
+        (void)immutable_robot;
+        const size_t E = edge_starts.size(), P = particles_per_edge, W = world();
+        if (edge_targets.size() != E) throw std::invalid_argument("one target per edge");
+        if (rng.empty()) throw std::invalid_argument("at least one PRNG is required");
+        std::vector<std::vector<std::vector<std::pair<Configuration, bool>>>> result(E);
+        if (E * P == 0) return result;
+        const int width = Traits::width(edge_starts[0]);
+        const upc_sim_params params = simulators_[0]->MakeParams(forward_simulation_time, simulation_shortcut_distance, use_individual_jacobians, allow_contacts);
+        std::vector<double> starts((size_t)width * E), targets((size_t)width * E);
+        Simulator::FlattenToSoa(edge_starts, width, starts.data());
+        Simulator::FlattenToSoa(edge_targets, width, targets.data());
+        const uint64_t seed = Simulator::NextSeed(rng[0]);
+        const size_t cap_edges = (E + W - 1) / W;
+        upc_outcome_layout lay;
+        check(upc_outcome_layout_for(width, (int64_t)(cap_edges * P), (int64_t)cap_edges, &lay));
+        std::vector<const double*> d_starts(W), d_targets(W);
+        std::vector<void*> d_blocks(W);
+        for (size_t r = 0; r < W; r++)
+        {
+            double* ds = nullptr;
+            double* dt = nullptr;
+            void* db = nullptr;
+            check(upc_device_scratch(simulators_[r]->handle(), 0, (int64_t)(starts.size() * sizeof(double)), (void**)&ds));
+            check(upc_device_scratch(simulators_[r]->handle(), 1, (int64_t)(targets.size() * sizeof(double)), (void**)&dt));
+            check(upc_device_scratch(simulators_[r]->handle(), 2, (int64_t)((size_t)lay.block_bytes * W), &db));
+            check(upc_memcpy_to_device(simulators_[r]->handle(), ds, starts.data(), (int64_t)(starts.size() * sizeof(double))));
+            check(upc_memcpy_to_device(simulators_[r]->handle(), dt, targets.data(), (int64_t)(targets.size() * sizeof(double))));
+            d_starts[r] = ds; d_targets[r] = dt; d_blocks[r] = db;
+        }
+        check(upc_sharded_edge_batch_all((int32_t)W, comms_.data(), &params, &clustering.params(), seed, (int64_t)E, (int64_t)P, d_starts.data(),
+                                         d_targets.data(), d_blocks.data(), nullptr));
+        for (size_t r = 0; r < W; r++) check(upc_comm_synchronize(comms_[r]));
+        /* every device now holds every rank's block: read them all from the first */
+        std::vector<uint8_t> host((size_t)lay.block_bytes * W);
+        check(upc_memcpy_to_host(simulators_[0]->handle(), host.data(), d_blocks[0], (int64_t)host.size()));
+#pragma omp parallel for schedule(dynamic, 8) if (E > 16)
+        for (int64_t e = 0; e < (int64_t)E; e++)
+        {
+            /* owner rank and position of edge e inside the owner's block */
+            size_t r = 0;
+            int64_t lo = 0, hi = 0;
+            for (; r < W; r++)
+            {
+                upc_shard_bounds((int64_t)E, (int32_t)r, (int32_t)W, &lo, &hi);
+                if (e >= lo && e < hi) break;
+            }
+            const uint8_t* block = host.data() + r * (size_t)lay.block_bytes;
+            const int32_t* labels = (const int32_t*)(block + lay.labels_offset);
+            const int32_t* n_clusters = (const int32_t*)(block + lay.n_clusters_offset);
+            const uint8_t* collided = block + lay.collided_offset;
+            const double* configs = (const double*)(block + lay.configs_offset);
+            const size_t n_local = (size_t)(hi - lo) * P, el = (size_t)(e - lo);
+            std::vector<std::vector<std::pair<Configuration, bool>>>& clusters = result[(size_t)e];
+            clusters.resize((size_t)n_clusters[el]);
+            double tmp[16];
+            for (size_t k = 0; k < P; k++)
+            {
+                const size_t i = el * P + k;
+                const bool hit = collided[i] != 0;
+                if (hit && !allow_contacts) continue;
+                for (int c = 0; c < width; c++) tmp[c] = configs[(size_t)c * n_local + i];
+                clusters[(size_t)labels[i]].push_back(std::make_pair(Traits::inflate(tmp, edge_starts[(size_t)e]), hit));
+            }
+        }
+        return result;
+    }
+
+private:
+    std::vector<std::shared_ptr<Simulator>> simulators_;
+    std::vector<upc_comm*> comms_;
 };
 
 /*

@@ -1445,10 +1445,36 @@ static void ClusterSets(const Environment& env, const upc_robot_desc& rd, const 
                         int64_t set_size, const double* configs, int32_t* labels, int32_t* n_clusters, upc_stats* stats)
 {
     const int64_t total = n_sets * set_size;
+    /* Particle sets are independent (one per planner edge).  The reference clusters one edge at a time and parallelises inside
+     * (the distance matrix, uncertainty_contact_planning.hpp:1674 with ENABLE_PARALLEL_DISTANCE_MATRIX); with many sets in hand
+     * the CPU path uses its threads better by taking whole sets per thread, so that is what a batch of sets does here - the
+     * per-set work (and its result) is the same either way. */
+    const bool over_sets = (n_sets >= 2 * (int64_t)omp_get_max_threads()) && !omp_in_parallel();
+    int64_t calls = 0, fallbacks = 0;
+    std::string failure; /* exceptions must not leave the parallel region */
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : calls, fallbacks) if (over_sets)
     for (int64_t s = 0; s < n_sets; s++)
     {
         upc_cluster_params local = cp;
-        ClusterOneSet<Robot>(env, rd, local, set_size, total, configs + s * set_size, labels + s * set_size, n_clusters + s, stats);
+        upc_stats st;
+        memset(&st, 0, sizeof(st));
+        try
+        {
+            ClusterOneSet<Robot>(env, rd, local, set_size, total, configs + s * set_size, labels + s * set_size, n_clusters + s, &st);
+        }
+        catch (const std::exception& e)
+        {
+#pragma omp critical
+            failure = e.what();
+        }
+        calls += st.cluster_calls;
+        fallbacks += st.cluster_fallback_calls;
+    }
+    if (!failure.empty()) throw std::invalid_argument(failure);
+    if (stats)
+    {
+        stats->cluster_calls += calls;
+        stats->cluster_fallback_calls += fallbacks;
     }
 }
 

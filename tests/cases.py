@@ -8,6 +8,9 @@ import numpy as np
 from uncertainty_planning_core_b200 import abi, scenarios
 
 SIM_STAT_KEYS = ("particle_steps", "collided_particles", "resolver_iterations", "failed_resolves")
+# seed / first particle of the committed seeded-noise fixtures (tests/golden/sim_seeded_*.npz)
+SEEDED_GOLDEN_SEED = 0x9E3779B97F4A7C15
+SEEDED_GOLDEN_FIRST = 12345
 
 
 # ------------------------------------------------------------------------------------------- simulation
@@ -371,7 +374,18 @@ def cl_se3_ptpm():
     return _with_ptpm(dict(env=env, robot=robot, configs=cfg, cparams=_cparams(dist_thr=0.1)), num_steps=25, goal=0.08)
 
 
+def cl_linked_ptpm():
+    """the 7-DoF arm, two groups of joint configurations on either side of an obstacle in the arm's sweep"""
+    env, robot = _linked_env_robot()
+    rng = np.random.default_rng(55)
+    n = 12
+    cfg = rng.uniform(-0.01, 0.01, size=(n, 7))
+    cfg[:, 1] += np.where(np.arange(n) % 2 == 0, 0.0, 0.45)
+    return _with_ptpm(dict(env=env, robot=robot, configs=cfg, cparams=_cparams(dist_thr=0.1)), num_steps=30, goal=0.05, seed=72)
+
+
 GOLDEN_CLUSTER_CASES = {
+    "linked_ptpm": cl_linked_ptpm,
     "se2_ac": cl_se2_ac,
     "se3_ac_messy": cl_se3_ac_messy,
     "linked_ac": cl_linked_ac,

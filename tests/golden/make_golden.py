@@ -2,7 +2,7 @@
 
   pid_golden.json      produced by the REFERENCE's own, unmodified simple_pid_controller.hpp
                        (compiled into oracle/_ref/libref_pid.so by oracle/Makefile; needs /root/reference)
-  sim_*.npz, cluster_*.npz   small seeded scenarios with the ORACLE's outputs, so that the GPU parity tests
+  sim_*.npz, sim_seeded_*.npz, cluster_*.npz   small seeded scenarios (tape noise / counter-based noise) with the ORACLE's outputs, so that the GPU parity tests
                        can also be checked against files that travel with the repository
 
 Run from the repository root:  python tests/golden/make_golden.py
@@ -54,6 +54,17 @@ def sim_golden():
                             tape_checksum=np.array([np.sum(tape)]))
 
 
+def seeded_sim_golden():
+    """the same scenarios with the counter-based noise of DESIGN.md 4.2 (the oracle's own generator)"""
+    for name, make in cases.GOLDEN_SIM_CASES.items():
+        sc = make()
+        tape = ob.fill_noise_tape_counter(cases.SEEDED_GOLDEN_SEED, sc["robot"], sc["params"], sc["starts"].shape[0], first_particle=cases.SEEDED_GOLDEN_FIRST)
+        cfg, coll, stats = ob.forward_simulate(sc["env"], sc["robot"], sc["params"], sc["starts"], sc["targets"], tape)
+        np.savez_compressed(os.path.join(HERE, "sim_seeded_%s.npz" % name), configs=cfg, collided=coll,
+                            stats=np.array([stats[k] for k in cases.SIM_STAT_KEYS], dtype=np.int64),
+                            tape_head=tape[:2, :, :, :4].copy())
+
+
 def cluster_golden():
     for name, make in cases.GOLDEN_CLUSTER_CASES.items():
         c = make()
@@ -65,5 +76,6 @@ def cluster_golden():
 if __name__ == "__main__":
     pid_golden()
     sim_golden()
+    seeded_sim_golden()
     cluster_golden()
     print("golden fixtures written to", HERE)

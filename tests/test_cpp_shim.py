@@ -15,7 +15,7 @@ def _build(oracle):
     if not os.path.exists(EXE) or any(os.path.getmtime(f) > os.path.getmtime(EXE) for f in (src, hdr)):
         pkg = os.path.join(ROOT, "uncertainty_planning_core_b200")
         orc = os.path.join(ROOT, "oracle")
-        subprocess.check_call(["g++", "-std=c++14", "-O1", "-Wall", "-Wextra", "-I" + os.path.join(ROOT, "include"), src, "-o", EXE,
+        subprocess.check_call(["g++", "-std=c++14", "-O1", "-fopenmp", "-Wall", "-Wextra", "-I" + os.path.join(ROOT, "include"), src, "-o", EXE,
                                "-L" + pkg, "-L" + orc, "-lupc_b200", "-loracle", "-Wl,-rpath," + pkg, "-Wl,-rpath," + orc])
 
 
@@ -30,3 +30,15 @@ def test_shim_round_trip_matches_oracle(oracle):
     out = subprocess.run([EXE], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "shim ok" in out.stdout
+
+
+@pytest.mark.gpu
+def test_sharded_simulator_matches_single_gpu(oracle):
+    """ShardedSimulator (edges split over the GPUs of the box, NCCL all-gather issued by the library) == one GPU, bit for bit"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least two GPUs")
+    _build(oracle)
+    out = subprocess.run([EXE, "sharded", str(min(torch.cuda.device_count(), 8))], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "sharded ok" in out.stdout

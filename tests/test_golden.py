@@ -22,6 +22,17 @@ def test_oracle_simulation_matches_fixture(oracle, name):
     assert [stats[k] for k in cases.SIM_STAT_KEYS] == g["stats"].tolist()
 
 
+@pytest.mark.parametrize("name", sorted(cases.GOLDEN_SIM_CASES))
+def test_oracle_seeded_simulation_matches_fixture(oracle, name):
+    g = np.load(os.path.join(HERE, "golden", "sim_seeded_%s.npz" % name))
+    sc = cases.GOLDEN_SIM_CASES[name]()
+    tape = oracle.fill_noise_tape_counter(cases.SEEDED_GOLDEN_SEED, sc["robot"], sc["params"], sc["starts"].shape[0], first_particle=cases.SEEDED_GOLDEN_FIRST)
+    assert np.array_equal(tape[:2, :, :, :4], g["tape_head"])
+    cfg, coll, stats = oracle.forward_simulate(sc["env"], sc["robot"], sc["params"], sc["starts"], sc["targets"], tape)
+    assert np.array_equal(cfg, g["configs"]) and np.array_equal(coll, g["collided"])
+    assert [stats[k] for k in cases.SIM_STAT_KEYS] == g["stats"].tolist()
+
+
 @pytest.mark.parametrize("name", sorted(cases.GOLDEN_CLUSTER_CASES))
 def test_oracle_clustering_matches_fixture(oracle, name):
     g = np.load(os.path.join(HERE, "golden", "cluster_%s.npz" % name))

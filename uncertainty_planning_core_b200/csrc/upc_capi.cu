@@ -246,7 +246,7 @@ int32_t upc_destroy(upc_handle* h)
     cudaFree(h->d_cells);
     cudaFree(h->d_points);
     cudaFree(h->d_counters);
-    DeviceBuffer* bufs[] = {&h->st_trace, &h->st_records, &h->st_starts, &h->st_targets, &h->st_tape, &h->st_out, &h->st_coll, &h->st_labels, &h->st_ncl, &h->st_carry,
+    DeviceBuffer* bufs[] = {&h->user[0], &h->user[1], &h->user[2], &h->user[3], &h->st_trace, &h->st_records, &h->st_starts, &h->st_targets, &h->st_tape, &h->st_out, &h->st_coll, &h->st_labels, &h->st_ncl, &h->st_carry,
                             &h->cw.features, &h->cw.adjacency, &h->cw.roots, &h->cw.comp, &h->cw.flags, &h->cw.signatures,
                             &h->cw.frames, &h->cw.dist_matrix, &h->cw.members, &h->cw.link_scratch, &h->cw.misc, &h->cw.hash, &h->cw.dedupe, &h->cw.usig, &h->cw.uroot};
     for (DeviceBuffer* b : bufs) b->release();
@@ -420,6 +420,37 @@ int32_t upc_host_alloc(void** ptr, int64_t bytes)
 int32_t upc_host_free(void* ptr)
 {
     if (ptr) UPC_CUDA_TRY(cudaFreeHost(ptr));
+    return UPC_OK;
+}
+
+/* device memory for hosts that do not link the CUDA runtime themselves (the C++ shim): four grow-only scratch buffers owned by
+ * the handle, and copies ordered on the handle's stream (both copies return when the data has arrived) */
+int32_t upc_device_scratch(upc_handle* h, int32_t slot, int64_t bytes, void** out)
+{
+    if (!h || !out || slot < 0 || slot >= 4 || bytes < 0) return fail_arg("bad argument");
+    UPC_CUDA_TRY(cudaSetDevice(h->device));
+    UPC_CUDA_TRY(h->user[slot].reserve((size_t)bytes));
+    *out = h->user[slot].ptr;
+    return UPC_OK;
+}
+
+int32_t upc_memcpy_to_device(upc_handle* h, void* d_dst, const void* src, int64_t bytes)
+{
+    if (!h || !d_dst || !src || bytes < 0) return fail_arg("bad argument");
+    UPC_CUDA_TRY(cudaSetDevice(h->device));
+    UPC_CUDA_TRY(cudaMemcpyAsync(d_dst, src, (size_t)bytes, cudaMemcpyHostToDevice, h->stream));
+    UPC_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->stats.h2d_bytes += bytes;
+    return UPC_OK;
+}
+
+int32_t upc_memcpy_to_host(upc_handle* h, void* dst, const void* d_src, int64_t bytes)
+{
+    if (!h || !dst || !d_src || bytes < 0) return fail_arg("bad argument");
+    UPC_CUDA_TRY(cudaSetDevice(h->device));
+    UPC_CUDA_TRY(cudaMemcpyAsync(dst, d_src, (size_t)bytes, cudaMemcpyDeviceToHost, h->stream));
+    UPC_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->stats.d2h_bytes += bytes;
     return UPC_OK;
 }
 

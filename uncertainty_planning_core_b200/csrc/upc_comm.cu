@@ -102,6 +102,7 @@ struct upc_comm
     int world = 1, rank = 0;
     cudaStream_t stream = nullptr;   /* the exchange runs on its own stream, ordered after the compute stream by events */
     cudaEvent_t ready = nullptr, done = nullptr;
+    bool exchanged = false;
 };
 
 using namespace upc;
@@ -240,19 +241,40 @@ int32_t upc_comm_nccl_version(int32_t* out)
     return UPC_OK;
 }
 
-int32_t upc_comm_group_start(void)
+/* the exchange of n communicators driven by this thread (n = 1: one process per GPU; n > 1: one process, several GPUs - the
+ * NCCL calls of the ranks must then sit in one group).  Each exchange is ordered after the work queued on its rank's compute
+ * stream and runs on the communicator's own stream. */
+static int32_t all_gather_blocks(int n, upc_comm* const* cs, void* const* d_blocks, int64_t block_bytes, void* const* streams)
 {
-    const int32_t rc = nccl_ready();
-    if (rc != UPC_OK) return rc;
-    UPC_NCCL_TRY(nccl()->GroupStart());
-    return UPC_OK;
-}
-
-int32_t upc_comm_group_end(void)
-{
-    const int32_t rc = nccl_ready();
-    if (rc != UPC_OK) return rc;
-    UPC_NCCL_TRY(nccl()->GroupEnd());
+    for (int i = 0; i < n; i++)
+    {
+        upc_comm* c = cs[i];
+        UPC_CUDA_TRY(cudaSetDevice(c->h->device));
+        cudaStream_t s = (streams && streams[i]) ? (cudaStream_t)streams[i] : c->h->stream;
+        UPC_CUDA_TRY(cudaEventRecord(c->ready, s));
+        UPC_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ready, 0));
+        /* work queued on the compute stream from here on waits for the PREVIOUS exchange: a caller alternating between two
+         * gather buffers can issue step k + 1 while the exchange of step k is in flight, and step k + 1 will not overwrite the
+         * buffer the exchange of step k - 1 was still using */
+        if (c->exchanged) UPC_CUDA_TRY(cudaStreamWaitEvent(s, c->done, 0));
+    }
+    if (cs[0]->world > 1)
+    {
+        if (n > 1) UPC_NCCL_TRY(nccl()->GroupStart());
+        for (int i = 0; i < n; i++)
+        {
+            upc_comm* c = cs[i];
+            const uint8_t* mine = (const uint8_t*)d_blocks[i] + (size_t)c->rank * (size_t)block_bytes;
+            UPC_NCCL_TRY(nccl()->AllGather(mine, d_blocks[i], (size_t)block_bytes, kNcclUint8, c->comm, c->stream));
+        }
+        if (n > 1) UPC_NCCL_TRY(nccl()->GroupEnd());
+    }
+    for (int i = 0; i < n; i++)
+    {
+        UPC_CUDA_TRY(cudaSetDevice(cs[i]->h->device));
+        UPC_CUDA_TRY(cudaEventRecord(cs[i]->done, cs[i]->stream));
+        cs[i]->exchanged = true;
+    }
     return UPC_OK;
 }
 
@@ -262,17 +284,7 @@ int32_t upc_comm_group_end(void)
 int32_t upc_comm_all_gather_outcomes(upc_comm* c, void* d_blocks, int64_t block_bytes, void* stream)
 {
     if (!c || !d_blocks || block_bytes <= 0) return fail_comm("bad argument");
-    UPC_CUDA_TRY(cudaSetDevice(c->h->device));
-    cudaStream_t s = stream ? (cudaStream_t)stream : c->h->stream;
-    UPC_CUDA_TRY(cudaEventRecord(c->ready, s));
-    UPC_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ready, 0));
-    if (c->world > 1)
-    {
-        const uint8_t* mine = (const uint8_t*)d_blocks + (size_t)c->rank * (size_t)block_bytes;
-        UPC_NCCL_TRY(nccl()->AllGather(mine, d_blocks, (size_t)block_bytes, kNcclUint8, c->comm, c->stream));
-    }
-    UPC_CUDA_TRY(cudaEventRecord(c->done, c->stream));
-    return UPC_OK;
+    return all_gather_blocks(1, &c, &d_blocks, block_bytes, &stream);
 }
 
 /* make `stream` (NULL = the handle's compute stream) wait for the last exchange */
@@ -301,9 +313,9 @@ int32_t upc_comm_synchronize(upc_comm* c)
  * (replicated on every rank, device memory).  d_blocks: world * layout.block_bytes bytes with
  * layout = upc_outcome_layout_for(width, max shard particles, max shard edges).  Asynchronous; see upc_comm_all_gather_outcomes.
  */
-int32_t upc_sharded_edge_batch(upc_comm* c, const upc_sim_params* params, const upc_cluster_params* cparams, uint64_t seed,
-                               int64_t n_edges, int64_t particles_per_edge, const double* d_edge_starts, const double* d_edge_targets,
-                               void* d_blocks, void* stream)
+static int32_t sharded_local(upc_comm* c, const upc_sim_params* params, const upc_cluster_params* cparams, uint64_t seed, int64_t n_edges,
+                             int64_t particles_per_edge, const double* d_edge_starts, const double* d_edge_targets, void* d_blocks, void* stream,
+                             upc_outcome_layout* lay)
 {
     if (!c || !params || !cparams || !d_edge_starts || !d_edge_targets || !d_blocks) return fail_comm("null argument");
     if (n_edges < 1 || particles_per_edge < 1) return fail_comm("n_edges and particles_per_edge must be >= 1");
@@ -312,30 +324,52 @@ int32_t upc_sharded_edge_batch(upc_comm* c, const upc_sim_params* params, const 
     int64_t lo, hi;
     upc_shard_bounds(n_edges, c->rank, c->world, &lo, &hi);
     const int64_t cap_edges = (n_edges + c->world - 1) / c->world;
-    upc_outcome_layout lay;
-    upc_outcome_layout_for(width, cap_edges * particles_per_edge, cap_edges, &lay);
-    uint8_t* block = (uint8_t*)d_blocks + (size_t)c->rank * (size_t)lay.block_bytes;
+    upc_outcome_layout_for(width, cap_edges * particles_per_edge, cap_edges, lay);
+    uint8_t* block = (uint8_t*)d_blocks + (size_t)c->rank * (size_t)lay->block_bytes;
     const int64_t e = hi - lo, n = e * particles_per_edge;
-    if (e > 0)
+    if (e == 0) return UPC_OK;
+    UPC_CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+    /* this rank's columns [lo, hi) of the replicated edge arrays, compacted to [C][e] (tiny: e * C doubles) */
+    UPC_CUDA_TRY(h->st_starts.reserve((size_t)width * (size_t)e * sizeof(double)));
+    UPC_CUDA_TRY(h->st_targets.reserve((size_t)width * (size_t)e * sizeof(double)));
+    UPC_CUDA_TRY(cudaMemcpy2DAsync(h->st_starts.ptr, (size_t)e * sizeof(double), d_edge_starts + lo, (size_t)n_edges * sizeof(double),
+                                   (size_t)e * sizeof(double), (size_t)width, cudaMemcpyDeviceToDevice, s));
+    UPC_CUDA_TRY(cudaMemcpy2DAsync(h->st_targets.ptr, (size_t)e * sizeof(double), d_edge_targets + lo, (size_t)n_edges * sizeof(double),
+                                   (size_t)e * sizeof(double), (size_t)width, cudaMemcpyDeviceToDevice, s));
+    int32_t rc = upc_forward_simulate_seeded_device(h, params, seed, lo * particles_per_edge, n, e, (const double*)h->st_starts.ptr, e,
+                                                    (const double*)h->st_targets.ptr, (double*)(block + lay->configs_offset),
+                                                    block + lay->collided_offset, s);
+    if (rc != UPC_OK) return rc;
+    return upc_cluster_particles_device(h, cparams, e, particles_per_edge, (const double*)(block + lay->configs_offset),
+                                        (int32_t*)(block + lay->labels_offset), (int32_t*)(block + lay->n_clusters_offset), s);
+}
+
+int32_t upc_sharded_edge_batch(upc_comm* c, const upc_sim_params* params, const upc_cluster_params* cparams, uint64_t seed,
+                               int64_t n_edges, int64_t particles_per_edge, const double* d_edge_starts, const double* d_edge_targets,
+                               void* d_blocks, void* stream)
+{
+    upc_outcome_layout lay;
+    const int32_t rc = sharded_local(c, params, cparams, seed, n_edges, particles_per_edge, d_edge_starts, d_edge_targets, d_blocks, stream, &lay);
+    if (rc != UPC_OK) return rc;
+    return all_gather_blocks(1, &c, &d_blocks, lay.block_bytes, &stream);
+}
+
+/* the same step for all n ranks of a single-process communicator set (upc_comm_create_all): every array argument has one entry
+ * per rank (device pointers on that rank's GPU); streams may be NULL */
+int32_t upc_sharded_edge_batch_all(int32_t n, upc_comm* const* comms, const upc_sim_params* params, const upc_cluster_params* cparams, uint64_t seed,
+                                   int64_t n_edges, int64_t particles_per_edge, const double* const* d_edge_starts,
+                                   const double* const* d_edge_targets, void* const* d_blocks, void* const* streams)
+{
+    if (n < 1 || !comms || !d_edge_starts || !d_edge_targets || !d_blocks) return fail_comm("bad argument");
+    upc_outcome_layout lay;
+    for (int i = 0; i < n; i++)
     {
-        UPC_CUDA_TRY(cudaSetDevice(h->device));
-        cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
-        /* this rank's columns [lo, hi) of the replicated edge arrays, compacted to [C][e] (tiny: e * C doubles) */
-        UPC_CUDA_TRY(h->st_starts.reserve((size_t)width * (size_t)e * sizeof(double)));
-        UPC_CUDA_TRY(h->st_targets.reserve((size_t)width * (size_t)e * sizeof(double)));
-        UPC_CUDA_TRY(cudaMemcpy2DAsync(h->st_starts.ptr, (size_t)e * sizeof(double), d_edge_starts + lo, (size_t)n_edges * sizeof(double),
-                                       (size_t)e * sizeof(double), (size_t)width, cudaMemcpyDeviceToDevice, s));
-        UPC_CUDA_TRY(cudaMemcpy2DAsync(h->st_targets.ptr, (size_t)e * sizeof(double), d_edge_targets + lo, (size_t)n_edges * sizeof(double),
-                                       (size_t)e * sizeof(double), (size_t)width, cudaMemcpyDeviceToDevice, s));
-        int32_t rc = upc_forward_simulate_seeded_device(h, params, seed, lo * particles_per_edge, n, e, (const double*)h->st_starts.ptr, e,
-                                                        (const double*)h->st_targets.ptr, (double*)(block + lay.configs_offset),
-                                                        block + lay.collided_offset, s);
-        if (rc != UPC_OK) return rc;
-        rc = upc_cluster_particles_device(h, cparams, e, particles_per_edge, (const double*)(block + lay.configs_offset),
-                                          (int32_t*)(block + lay.labels_offset), (int32_t*)(block + lay.n_clusters_offset), s);
+        const int32_t rc = sharded_local(comms[i], params, cparams, seed, n_edges, particles_per_edge, d_edge_starts[i], d_edge_targets[i], d_blocks[i],
+                                         streams ? streams[i] : nullptr, &lay);
         if (rc != UPC_OK) return rc;
     }
-    return upc_comm_all_gather_outcomes(c, d_blocks, lay.block_bytes, stream);
+    return all_gather_blocks(n, comms, d_blocks, lay.block_bytes, streams);
 }
 
 } /* extern "C" */

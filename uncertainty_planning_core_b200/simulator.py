@@ -95,6 +95,66 @@ class B200Simulator:
                                                  collided.ctypes.data))
         return np.ascontiguousarray(out.T), collided.astype(bool)
 
+    def ForwardSimulateRobotsSeeded(self, start_positions, target_positions, seed, params, first_particle=0, n=None):
+        """Batched forward simulation with the counter-based noise of DESIGN.md 4.2 (no tape crosses the boundary).
+        start_positions / target_positions hold one row per particle, one row per block of particles (their row counts must
+        divide n: edge batches) or a single row; particle i draws from the stream (seed, first_particle + i).
+        Returns (configs [n, C], collided [n] bool)."""
+        starts = np.asarray(start_positions, dtype=np.float64).reshape(-1, self.robot.width)
+        targets = np.asarray(target_positions, dtype=np.float64).reshape(-1, self.robot.width)
+        n = starts.shape[0] if n is None else int(n)
+        starts_soa = np.ascontiguousarray(starts.T)
+        targets_soa = np.ascontiguousarray(targets.T)
+        out = np.zeros((self.robot.width, n))
+        collided = np.zeros(n, dtype=np.uint8)
+        abi.check(self._lib.upc_forward_simulate_seeded(self._h, C.byref(params), int(seed), int(first_particle), n, starts.shape[0],
+                                                        starts_soa.ctypes.data, targets.shape[0], targets_soa.ctypes.data,
+                                                        out.ctypes.data, collided.ctypes.data))
+        return np.ascontiguousarray(out.T), collided.astype(bool)
+
+    def ForwardSimulateRobotTraced(self, start_positions, target_positions, params, noise_tape=None, seed=0, first_particle=0):
+        """ForwardSimulateRobot with enable_tracing (simple_simulator_interface.hpp:621; trace types :40-63) for a small batch:
+        returns (configs [n, C], collided [n], trace) with trace = dict(configs [S, n, C] - the resolved configuration at the
+        end of every controller interval, what ExtractTrajectoryFromTrace (:66-86) reads -, controls [S, n, 2*dof] - control
+        input, then the control step per microstep -, steps [2, n] - intervals executed, microsteps of the last one).
+        noise_tape=None selects seeded noise."""
+        starts = np.asarray(start_positions, dtype=np.float64).reshape(-1, self.robot.width)
+        targets = np.asarray(target_positions, dtype=np.float64).reshape(-1, self.robot.width)
+        n, S, W, dof = starts.shape[0], params.num_steps, self.robot.width, self.robot.dof
+        if targets.shape[0] not in (1, n):
+            raise ValueError("target_positions must have size 1 or size start_positions.size()")
+        tape = None
+        if noise_tape is not None:
+            tape = np.ascontiguousarray(noise_tape, dtype=np.float64)
+            if tape.shape != abi.tape_shape(params, dof, n):
+                raise ValueError("noise tape has shape %s, expected %s" % (tape.shape, abi.tape_shape(params, dof, n)))
+        s_soa, t_soa = np.ascontiguousarray(starts.T), np.ascontiguousarray(targets.T)
+        out, coll = np.zeros((W, n)), np.zeros(n, dtype=np.uint8)
+        tc, tu, ts = np.zeros((S, W, n)), np.zeros((S, 2 * dof, n)), np.zeros((2, n), dtype=np.int32)
+        abi.check(self._lib.upc_forward_simulate_traced(self._h, C.byref(params), n, s_soa.ctypes.data, targets.shape[0], t_soa.ctypes.data,
+                                                        None if tape is None else tape.ctypes.data, int(seed), int(first_particle),
+                                                        out.ctypes.data, coll.ctypes.data, tc.ctypes.data, tu.ctypes.data, ts.ctypes.data))
+        trace = dict(configs=np.ascontiguousarray(tc.transpose(0, 2, 1)), controls=np.ascontiguousarray(tu.transpose(0, 2, 1)), steps=ts)
+        return np.ascontiguousarray(out.T), coll.astype(bool), trace
+
+    def SimulateAndClusterEdges(self, edge_starts, edge_targets, particles_per_edge, seed, params, cluster_params, first_particle=0):
+        """The planner-batch step in one call (BASELINE config 5): E candidate edges x particles_per_edge particles simulated
+        with seeded noise (uncertainty_contact_planning.hpp:2039-2071 per edge), each edge's outcome clustered (:1986-2034).
+        Returns (configs [E, P, C], collided [E, P], labels [E, P], n_clusters [E])."""
+        es = np.asarray(edge_starts, dtype=np.float64).reshape(-1, self.robot.width)
+        et = np.asarray(edge_targets, dtype=np.float64).reshape(-1, self.robot.width)
+        if es.shape != et.shape:
+            raise ValueError("one target per start")
+        E, P, W = es.shape[0], int(particles_per_edge), self.robot.width
+        n = E * P
+        s_soa, t_soa = np.ascontiguousarray(es.T), np.ascontiguousarray(et.T)
+        out, coll = np.zeros((W, n)), np.zeros(n, dtype=np.uint8)
+        labels, ncl = np.zeros(n, dtype=np.int32), np.zeros(E, dtype=np.int32)
+        abi.check(self._lib.upc_simulate_and_cluster_edges(self._h, C.byref(params), C.byref(cluster_params), int(seed), int(first_particle), E, P,
+                                                           s_soa.ctypes.data, t_soa.ctypes.data, out.ctypes.data, coll.ctypes.data,
+                                                           labels.ctypes.data, ncl.ctypes.data))
+        return np.ascontiguousarray(out.T).reshape(E, P, W), coll.astype(bool).reshape(E, P), labels.reshape(E, P), ncl
+
     def ForwardSimulateEdgeBatch(self, edge_starts, edge_targets, particles_per_edge, noise_tape, params):
         """A batch of candidate edges in ONE call (BASELINE config 5): edge e contributes `particles_per_edge` particles that
         start at edge_starts[e] and move towards edge_targets[e] - the targets.size() == starts.size() form of
@@ -177,9 +237,10 @@ class OutcomeClustering:
     """ClusterParticles / PolicyParticleClusteringFn over a B200Simulator's handle."""
 
     def __init__(self, simulator, clustering_type=abi.FEATURE_CRS, signature_matching_threshold=0.125,
-                 distance_clustering_threshold=0.1, goal_distance_threshold=0.0, ptpm_params=None, ptpm_tape=None):
+                 distance_clustering_threshold=0.1, goal_distance_threshold=0.0, ptpm_params=None, ptpm_tape=None, ptpm_seed=0):
         """ptpm_params / ptpm_tape: simulation parameters and noise tape [S, 1+M, dof, n*(n-1)] for the
-        POINT_TO_POINT_MOVEMENT first pass (uncertainty_contact_planning.hpp:1801-1863)."""
+        POINT_TO_POINT_MOVEMENT first pass (uncertainty_contact_planning.hpp:1801-1863); without a tape the pair
+        simulations draw seeded noise from ptpm_seed."""
         self.sim = simulator
         self._lib = simulator._lib
         self.params = abi.ClusterParams()
@@ -188,9 +249,10 @@ class OutcomeClustering:
         self.params.distance_clustering_threshold = distance_clustering_threshold
         self.params.goal_distance_threshold = goal_distance_threshold
         self._keep = (ptpm_params, None if ptpm_tape is None else np.ascontiguousarray(ptpm_tape, dtype=np.float64))
+        self.params.ptpm_seed = int(ptpm_seed)
         if ptpm_params is not None:
             self.params.ptpm_sim = C.pointer(ptpm_params)
-            self.params.ptpm_tape = self._keep[1].ctypes.data
+            self.params.ptpm_tape = None if self._keep[1] is None else self._keep[1].ctypes.data
 
     def ClusterIndices(self, configs, n_sets=1):
         """Index clustering of n_sets equally sized particle sets stacked in configs [n_sets*set_size, C].
