@@ -44,6 +44,8 @@ def load():
     lib.oracle_math.argtypes = [i32, i64, vp, vp, vp]
     lib.oracle_se3_log.argtypes = [vp, vp]
     lib.oracle_se3_exp.argtypes = [vp, vp]
+    lib.oracle_quaternion_from_rotation.argtypes = [vp, vp]
+    lib.oracle_quaternion_from_rotation.restype = None
     lib.oracle_forward_simulate.argtypes = [C.POINTER(abi.EnvDesc), C.POINTER(abi.RobotDesc), C.POINTER(abi.SimParams),
                                             i64, vp, i64, vp, vp, vp, vp, C.POINTER(abi.Stats)]
     lib.oracle_check_config_collision.argtypes = [C.POINTER(abi.EnvDesc), C.POINTER(abi.RobotDesc), vp, dp, dp, C.POINTER(i32)]
@@ -61,6 +63,10 @@ def load():
     lib.oracle_forward_simulate_traced.argtypes = [C.POINTER(abi.EnvDesc), C.POINTER(abi.RobotDesc), C.POINTER(abi.SimParams),
                                                    i64, vp, i64, vp, vp, vp, vp, vp, vp, vp]
     lib.oracle_forward_simulate_traced.restype = i32
+    lib.oracle_sensor_values.argtypes = [i64, vp, vp, vp]
+    lib.oracle_sensor_values.restype = None
+    lib.oracle_actuator_values.argtypes = [dp, dp, i64, vp, vp, vp, vp]
+    lib.oracle_actuator_values.restype = None
     lib.oracle_philox4x32_10.argtypes = [vp, vp, vp]
     lib.oracle_philox4x32_10.restype = None
     lib.oracle_normal_quantile.argtypes = [i64, vp, vp]
@@ -92,6 +98,45 @@ def load_ref_pid():
     lib.ref_pid_sequence.restype = C.c_double
     _REF = lib
     return lib
+
+
+_REF_UNC = None
+
+
+def load_ref_unc():
+    """The reference's own simple_uncertainty_models.hpp compiled unmodified against the stand-in arc_utilities headers
+    (None when oracle/_ref was never built)."""
+    global _REF_UNC
+    if _REF_UNC is not None:
+        return _REF_UNC
+    so = os.path.join(_HERE, "_ref", "libref_unc.so")
+    if not os.path.exists(so):
+        return None
+    lib = C.CDLL(so)
+    lib.ref_sensor_values.argtypes = [C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ref_sensor_values.restype = None
+    lib.ref_actuator_values.argtypes = [C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ref_actuator_values.restype = None
+    lib.ref_actuator_max_velocity_noise.argtypes = [C.c_double, C.c_double]
+    lib.ref_actuator_max_velocity_noise.restype = C.c_double
+    _REF_UNC = lib
+    return lib
+
+
+def sensor_values(process_values, draws):
+    p = np.ascontiguousarray(process_values, dtype=np.float64)
+    d = np.ascontiguousarray(draws, dtype=np.float64)
+    out = np.zeros_like(p)
+    load().oracle_sensor_values(p.size, p.ctypes.data, d.ctypes.data, out.ctypes.data)
+    return out
+
+
+def actuator_values(noise_bound, actuator_limit, inputs, draws):
+    u = np.ascontiguousarray(inputs, dtype=np.float64)
+    d = np.ascontiguousarray(draws, dtype=np.float64)
+    out, noiseless = np.zeros_like(u), np.zeros_like(u)
+    load().oracle_actuator_values(noise_bound, actuator_limit, u.size, u.ctypes.data, d.ctypes.data, out.ctypes.data, noiseless.ctypes.data)
+    return out, noiseless
 
 
 def _check(code):
@@ -174,6 +219,13 @@ def se3_exp(twist6):
     twist6 = np.ascontiguousarray(twist6, dtype=np.float64)
     out = np.zeros(12)
     load().oracle_se3_exp(twist6.ctypes.data, out.ctypes.data)
+    return out
+
+
+def quaternion_from_rotation(cfg12):
+    cfg12 = np.ascontiguousarray(cfg12, dtype=np.float64)
+    out = np.zeros(4)
+    load().oracle_quaternion_from_rotation(cfg12.ctypes.data, out.ctypes.data)
     return out
 
 

@@ -1752,7 +1752,25 @@ void oracle_math(int32_t which, int64_t n, const double* a, const double* b, dou
     }
 }
 
+/* sensor / actuator arithmetic on replayed draws (pinned against the reference's own header by tests/test_oracle_unc.py) */
+void oracle_sensor_values(int64_t n, const double* process_values, const double* draws, double* out)
+{
+    for (int64_t i = 0; i < n; i++) out[i] = SensorValue(process_values[i], draws[i]);
+}
+
+void oracle_actuator_values(double noise_bound, double actuator_limit, int64_t n, const double* inputs, const double* draws, double* out, double* noiseless)
+{
+    Actuator a;
+    a.Initialize(noise_bound, actuator_limit);
+    for (int64_t i = 0; i < n; i++)
+    {
+        out[i] = a.GetControlValue(inputs[i], draws[i]);
+        noiseless[i] = a.GetControlValue(inputs[i]);
+    }
+}
+
 void oracle_se3_log(const double* cfg12, double* twist6) { Se3Log(FromRows12(cfg12), twist6); }
+void oracle_quaternion_from_rotation(const double* cfg12, double* q4) { QuaternionFromRotation(FromRows12(cfg12), q4); }
 void oracle_se3_exp(const double* twist6, double* cfg12) { ToRows12(Se3Exp(twist6), cfg12); }
 
 int32_t oracle_forward_simulate(const upc_env_desc* env_desc, const upc_robot_desc* robot, const upc_sim_params* params,

@@ -98,8 +98,11 @@ double oracle_pid_sequence(double kp, double ki, double kd, double clamp, const 
                            int32_t n, double* out_terms);
 /* elementary functions, vectorised, for tests/test_math.py; which: 0 sin 1 cos 2 atan2(a,b) 3 acos 4 wrap 5 signed angle distance(a,b) */
 void oracle_math(int32_t which, int64_t n, const double* a, const double* b, double* out);
+void oracle_sensor_values(int64_t n, const double* process_values, const double* draws, double* out);
+void oracle_actuator_values(double noise_bound, double actuator_limit, int64_t n, const double* inputs, const double* draws, double* out, double* noiseless);
 void oracle_se3_log(const double* cfg12, double* twist6);
 void oracle_se3_exp(const double* twist6, double* cfg12);
+void oracle_quaternion_from_rotation(const double* cfg12, double* q4); /* x, y, z, w */
 int32_t oracle_forward_simulate(const upc_env_desc* env, const upc_robot_desc* robot, const upc_sim_params* params,
                                 int64_t n, const double* starts, int64_t n_targets, const double* targets,
                                 const double* tape, double* out_configs, uint8_t* out_collided, upc_stats* stats);
