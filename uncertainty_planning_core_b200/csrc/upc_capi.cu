@@ -9,6 +9,7 @@
 #include <math.h>
 #include <string.h>
 #include <stdlib.h>
+#include <memory>
 #include <random>
 
 namespace upc
@@ -166,7 +167,9 @@ int32_t upc_create(const upc_env_desc* env, int32_t device, upc_handle** out)
     UPC_CUDA_TRY(cudaGetDeviceCount(&count));
     if (device < 0 || device >= count) return fail_arg("no such CUDA device");
     UPC_CUDA_TRY(cudaSetDevice(device));
-    upc_handle* h = new upc_handle();
+    /* owned until the end: every early return below releases the stream and the allocations made so far */
+    std::unique_ptr<upc_handle, int32_t (*)(upc_handle*)> owner(new upc_handle(), upc_destroy);
+    upc_handle* h = owner.get();
     h->device = device;
     cudaDeviceProp prop;
     UPC_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -230,7 +233,7 @@ int32_t upc_create(const upc_env_desc* env, int32_t device, upc_handle** out)
     e.occ = h->d_occ;
     e.cellmin = h->d_cellmin;
     e.cells = h->d_cells;
-    *out = h;
+    *out = owner.release();
     return UPC_OK;
 }
 
@@ -385,6 +388,7 @@ int32_t upc_get_stats(upc_handle* h, upc_stats* out)
 int32_t upc_debug_phase_cycles(upc_handle* h, int64_t* out8)
 {
     if (!h || !out8) return fail_arg("null argument");
+    UPC_CUDA_TRY(cudaSetDevice(h->device));
     const int32_t rc = pull_counters(h);
     if (rc != UPC_OK) return rc;
     for (int k = 0; k < 12; k++) { out8[k] = h->phase_cycles[k]; h->phase_cycles[k] = 0; }
@@ -923,6 +927,8 @@ int32_t upc_cluster_particles(upc_handle* h, const upc_cluster_params* params, i
         return UPC_ERR_NO_ROBOT;
     }
     if (n_sets < 0 || set_size < 0) return fail_arg("negative size");
+    if (n_sets > 65535) return fail_arg("at most 65535 particle sets per call");
+    if (set_size > (int64_t)1 << 20) return fail_arg("at most 2^20 particles per set");
     if (n_sets == 0) return UPC_OK;
     if (!n_clusters) return fail_arg("null buffer");
     if (set_size == 0)
