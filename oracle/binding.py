@@ -69,8 +69,10 @@ def load():
     lib.oracle_actuator_values.restype = None
     lib.oracle_philox4x32_10.argtypes = [vp, vp, vp]
     lib.oracle_philox4x32_10.restype = None
-    lib.oracle_normal_quantile.argtypes = [i64, vp, vp]
-    lib.oracle_normal_quantile.restype = None
+    lib.oracle_truncated_normal_quantile.argtypes = [i64, vp, vp]
+    lib.oracle_truncated_normal_quantile.restype = None
+    lib.oracle_centered_uniform52.argtypes = [i64, vp, vp, vp]
+    lib.oracle_centered_uniform52.restype = None
     lib.oracle_log.argtypes = [i64, vp, vp]
     lib.oracle_log.restype = None
     lib.oracle_standard_draws.argtypes = [C.c_uint64, i64, i64, C.c_uint32, C.c_uint32, C.c_uint32, vp]
@@ -152,10 +154,19 @@ def philox4x32_10(key, counter):
     return out
 
 
-def normal_quantile(p):
-    p = np.ascontiguousarray(p, dtype=np.float64)
-    out = np.zeros_like(p)
-    load().oracle_normal_quantile(p.size, p.ctypes.data, out.ctypes.data)
+def truncated_normal_quantile(t):
+    """z(t) = Phi^-1(1/2 + t (Phi(2) - Phi(-2))) for centred uniforms t in (-1/2, 1/2)"""
+    t = np.ascontiguousarray(t, dtype=np.float64)
+    out = np.zeros_like(t)
+    load().oracle_truncated_normal_quantile(t.size, t.ctypes.data, out.ctypes.data)
+    return out
+
+
+def centered_uniform52(hi, lo):
+    hi = np.ascontiguousarray(hi, dtype=np.uint32)
+    lo = np.ascontiguousarray(lo, dtype=np.uint32)
+    out = np.zeros(hi.size)
+    load().oracle_centered_uniform52(hi.size, hi.ctypes.data, lo.ctypes.data, out.ctypes.data)
     return out
 
 

@@ -1,9 +1,10 @@
 /*
  * upc_oracle_noise.cpp - CPU restatement of the counter-based noise of DESIGN.md section 4.2.  TEST INFRASTRUCTURE ONLY.
  *
- * Follows the published algorithms, not the product's source: Philox-4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random
- * numbers: as easy as 1, 2, 3", SC'11; pinned by the Random123 known-answer vectors in tests/test_noise.py) and the inverse
- * normal CDF AS 241 / PPND16 (Wichura, Applied Statistics 37, 1988; pinned against scipy.special.ndtri).  The role of the
+ * Follows the published algorithm and the specification, not the product's source: Philox-4x32-10 (Salmon, Moraes, Dror,
+ * Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11; pinned by the Random123 known-answer vectors in
+ * tests/test_noise.py) and the rational approximation of the truncated normal quantile specified in DESIGN.md 4.2 (pinned
+ * against scipy.special.ndtri).  The role of the
  * draws is that of simple_uncertainty_models.hpp:38-45 (sensor: value + draw) and :77-88 (actuator: draw in [-1, 1] scaled
  * by the commanded value), with the truncation bounds of :29 and :59 (mean 0, +-2 sigma).
  *
@@ -51,49 +52,39 @@ Block128 Philox4x32_10(Block128 ctr, uint32_t key0, uint32_t key1)
     return ctr;
 }
 
-double Horner8(const double* c, double r)
-{
-    double acc = c[7];
-    for (int i = 6; i >= 0; i--) acc = acc * r + c[i];
-    return acc;
-}
+/*
+ * Quantile of the standard normal truncated to +-2 sigma at the centred uniform t in (-1/2, 1/2): Phi^-1(1/2 + q) with
+ * q = t (Phi(2) - Phi(-2)), by the degree-8 / degree-8 rational approximation q P(r) / Q(r), r = 0.228 - q^2, that DESIGN.md 4.2
+ * specifies (coefficient table produced by scripts/fit_truncated_quantile.py; Horner steps fused, as the specification says).
+ * tests/test_noise.py pins it against scipy.special.ndtri to 1e-13.
+ */
+const double kQuantileP[9] = {4.19803057674432534e+00, 4.98914924494953766e+02, 2.23256080577635075e+04, 4.73334579451213649e+05, 4.94985450103831850e+06,
+                              2.44404971329663284e+07, 5.03468522432988584e+07, 3.29915794812198505e+07, 3.04619464759342372e+06};
+const double kQuantileQ[9] = {1.0, 1.26415601550449168e+02, 6.10854034951519316e+03, 1.42817358525897551e+05, 1.69745287590994616e+06,
+                              9.97100045574528910e+06, 2.63619050062270910e+07, 2.58257609111968540e+07, 5.87769839876705315e+06};
 
-/* AS 241 PPND16 restricted to 0.02 < p < 0.98 (its third branch, r > 5, needs p < 1.4e-11) */
-double NormalQuantile(double p)
+double TruncatedNormalQuantile(double t)
 {
-    static const double A[8] = {3.3871328727963666080e0, 1.3314166789178437745e+2, 1.9715909503065514427e+3, 1.3731693765509461125e+4,
-                                4.5921953931549871457e+4, 6.7265770927008700853e+4, 3.3430575583588128105e+4, 2.5090809287301226727e+3};
-    static const double B[8] = {1.0, 4.2313330701600911252e+1, 6.8718700749205790830e+2, 5.3941960214247511077e+3,
-                                2.1213794301586595867e+4, 3.9307895800092710610e+4, 2.8729085735721942674e+4, 5.2264952788528545610e+3};
-    static const double C[8] = {1.42343711074968357734e0, 4.63033784615654529590e0, 5.76949722146069140550e0, 3.64784832476320460504e0,
-                                1.27045825245236838258e0, 2.41780725177450611770e-1, 2.27238449892691845833e-2, 7.74545014278341407640e-4};
-    static const double D[8] = {1.0, 2.05319162663775882187e0, 1.67638483018380384940e0, 6.89767334985100004550e-1,
-                                1.48103976427480074590e-1, 1.51986665636164571966e-2, 5.47593808499534494600e-4, 1.05075007164441684324e-9};
-    const double q = p - 0.5;
-    if (fabs(q) <= 0.425)
+    const double q = t * 9.544997361036415856e-01;
+    const double r = upc_fma(-q, q, 0.228);
+    double numerator = kQuantileP[8], denominator = kQuantileQ[8];
+    for (int i = 7; i >= 0; i--)
     {
-        const double r = 0.180625 - q * q;
-        return (q * Horner8(A, r)) / Horner8(B, r);
+        numerator = upc_fma(numerator, r, kQuantileP[i]);
+        denominator = upc_fma(denominator, r, kQuantileQ[i]);
     }
-    double r = (q < 0.0) ? p : (1.0 - p);
-    r = sqrt(-upc_log(r)) - 1.6;
-    const double val = Horner8(C, r) / Horner8(D, r);
-    return (q < 0.0) ? -val : val;
-}
-
-double UniformOpen52(uint32_t hi, uint32_t lo)
-{
-    const uint64_t k = ((uint64_t)hi << 20) | (uint64_t)(lo >> 12);
-    return ((double)k + 0.5) * ldexp(1.0, -52);
-}
-
-double TruncatedStandardNormal(double u)
-{
-    const double p = 2.275013194817920720e-02 + u * 9.544997361036415856e-01;
-    const double z = NormalQuantile(p);
+    const double z = (q * numerator) / denominator;
     if (z < -2.0) return -2.0;
     if (z > 2.0) return 2.0;
     return z;
+}
+
+/* 52 random bits -> (k + 1/2) 2^-52 - 1/2, exactly (k + 1/2 - 2^51 is a half-integer below 2^51: 52 significant bits) */
+double CenteredUniform52(uint32_t hi, uint32_t lo)
+{
+    const uint64_t k = ((uint64_t)hi << 20) | (uint64_t)(lo >> 12);
+    const int64_t twice = 2 * (int64_t)k + 1 - ((int64_t)1 << 52); /* 2 (k + 1/2 - 2^51) */
+    return ldexp((double)twice, -53);
 }
 
 /* standard draw of (seed, particle, step, slot, axis) */
@@ -105,8 +96,8 @@ double StandardDraw(uint64_t seed, uint64_t particle, uint32_t step, uint32_t sl
     ctr.v[2] = step;
     ctr.v[3] = (slot << 16) | (axis >> 1);
     const Block128 bits = Philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
-    const double u = (axis & 1u) ? UniformOpen52(bits.v[2], bits.v[3]) : UniformOpen52(bits.v[0], bits.v[1]);
-    return TruncatedStandardNormal(u);
+    const double t = (axis & 1u) ? CenteredUniform52(bits.v[2], bits.v[3]) : CenteredUniform52(bits.v[0], bits.v[1]);
+    return TruncatedNormalQuantile(t);
 }
 } /* namespace */
 
@@ -120,9 +111,15 @@ void oracle_philox4x32_10(const uint32_t* key2, const uint32_t* counter4, uint32
     memcpy(out4, r.v, sizeof(r.v));
 }
 
-void oracle_normal_quantile(int64_t n, const double* p, double* out)
+/* z(t) for centred uniforms t in (-1/2, 1/2) */
+void oracle_truncated_normal_quantile(int64_t n, const double* t, double* out)
 {
-    for (int64_t i = 0; i < n; i++) out[i] = NormalQuantile(p[i]);
+    for (int64_t i = 0; i < n; i++) out[i] = TruncatedNormalQuantile(t[i]);
+}
+
+void oracle_centered_uniform52(int64_t n, const uint32_t* hi, const uint32_t* lo, double* out)
+{
+    for (int64_t i = 0; i < n; i++) out[i] = CenteredUniform52(hi[i], lo[i]);
 }
 
 void oracle_log(int64_t n, const double* x, double* out)

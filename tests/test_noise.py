@@ -21,12 +21,32 @@ def test_philox_known_answers(oracle, counter, key, expected):
     assert oracle.philox4x32_10(key, counter).tolist() == expected
 
 
-def test_normal_quantile_matches_scipy(oracle):
+def test_truncated_quantile_matches_scipy(oracle):
+    """the degree-8 / degree-8 rational approximation of DESIGN.md 4.2 against scipy's inverse normal CDF on the whole truncated range"""
     from scipy.special import ndtri
-    p = np.concatenate([np.linspace(0.0227501319481792, 0.9772498680518208, 400001), 0.5 + np.array([-0.425, 0.425, -0.4250001, 0.4250001, 0.0])])
-    q, r = oracle.normal_quantile(p), ndtri(p)
-    assert np.max(np.abs(q - r)) < 4e-15
-    assert abs(oracle.normal_quantile([0.0227501319481792])[0] + 2.0) < 1e-13
+    W = 0.9544997361036415856
+    t = np.concatenate([np.linspace(-0.5, 0.5, 400001)[1:-1], [2.0 ** -53, -2.0 ** -53, 0.5 - 2.0 ** -53, -0.5 + 2.0 ** -53]])
+    z = oracle.truncated_normal_quantile(t)
+    assert np.max(np.abs(z - np.clip(ndtri(0.5 + t * W), -2.0, 2.0))) < 1e-13
+    assert np.all(np.diff(z[:-4]) >= 0) and z.min() >= -2.0 and z.max() <= 2.0       # monotone, bounded
+    assert np.array_equal(z, -oracle.truncated_normal_quantile(-t))                        # odd
+    assert abs(oracle.truncated_normal_quantile([0.5 - 2.0 ** -53])[0] - 2.0) < 1e-12
+
+
+def test_centered_uniform_is_exact(oracle):
+    rng = np.random.default_rng(5)
+    hi = rng.integers(0, 2 ** 32, 100000, dtype=np.uint64).astype(np.uint32)
+    lo = rng.integers(0, 2 ** 32, 100000, dtype=np.uint64).astype(np.uint32)
+    hi[:4] = [0, 0xffffffff, 0x80000000, 0x7fffffff]
+    lo[:4] = [0, 0xffffffff, 0, 0xffffffff]
+    t = oracle.centered_uniform52(hi, lo)
+    k = (hi.astype(np.uint64) << np.uint64(20)) | (lo.astype(np.uint64) >> np.uint64(12))
+    import fractions
+    for i in list(range(8)) + [17, 999]:
+        want = fractions.Fraction(2 * int(k[i]) + 1, 2 ** 53) - fractions.Fraction(1, 2)
+        assert fractions.Fraction(float(t[i])) == want
+    assert t.min() > -0.5 and t.max() < 0.5 and not np.any(t == 0.0)
+    assert t[0] == -0.5 + 2.0 ** -53 and t[1] == 0.5 - 2.0 ** -53
 
 
 def test_log_is_within_one_ulp_of_libm(oracle):

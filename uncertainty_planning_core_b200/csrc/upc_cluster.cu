@@ -1242,6 +1242,134 @@ __global__ void __launch_bounds__(256) exact_roots_kernel(const __grid_constant_
     root[a.members[r]] = (int32_t)(a.members[q.base + k] % a.set_size);
 }
 
+/*
+ * The reciprocal-nearest-neighbour rounds of one component inside ONE CTA (components of at most kFusedExactMax members): the same
+ * five phases as the kernels above - nearest, mark, row merge, column merge, retire - separated by CTA barriers instead of kernel
+ * boundaries, repeated until a round merges nothing.  Components are independent, so every CTA runs its own number of rounds and
+ * the host does not take part (the multi-kernel loop with its device-to-host flag per round remains for bigger components).
+ */
+constexpr int kFusedExactMax = 4096;
+
+__global__ void __launch_bounds__(1024) exact_rounds_fused_kernel(const __grid_constant__ ExactArgs a, int ncomp)
+{
+    __shared__ int s_merged;
+    for (int c = blockIdx.x; c < ncomp; c += gridDim.x)
+    {
+        const int64_t base = a.comp_off[c];
+        const int m = (int)(a.comp_off[c + 1] - base);
+        if (m > kFusedExactMax) continue;
+        double* D = a.D + a.matrix_off[c];
+        uint8_t* active = a.active + base;
+        int32_t* nn = a.nn + base;
+        int32_t* partner = a.partner + base;
+        int32_t* into = a.into + base;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+        __syncthreads(); /* exact_matrix_kernel's writes are visible (previous launch); separates components handled by this CTA */
+        while (true)
+        {
+            /* nearest active neighbour of every active row: key (distance, min(row, col), max(row, col)) */
+            for (int row = warp; row < m; row += warps)
+            {
+                if (!active[row])
+                {
+                    if (lane == 0) nn[row] = -1;
+                    continue;
+                }
+                const double* Drow = D + (int64_t)row * m;
+                double bv = INFINITY;
+                int bi = -1;
+                for (int col = lane; col < m; col += 32)
+                {
+                    if (col == row || !active[col]) continue;
+                    const double d = Drow[col];
+                    bool better;
+                    if (bi < 0) better = true;
+                    else if (d != bv) better = d < bv;
+                    else
+                    {
+                        const int lo1 = min(row, col), hi1 = max(row, col), lo0 = min(row, bi), hi0 = max(row, bi);
+                        better = (lo1 < lo0) || (lo1 == lo0 && hi1 < hi0);
+                    }
+                    if (better) { bv = d; bi = col; }
+                }
+                for (int o = 16; o > 0; o >>= 1)
+                {
+                    const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    bool better = false;
+                    if (oi >= 0)
+                    {
+                        if (bi < 0) better = true;
+                        else if (ov != bv) better = ov < bv;
+                        else
+                        {
+                            const int lo1 = min(row, oi), hi1 = max(row, oi), lo0 = min(row, bi), hi0 = max(row, bi);
+                            better = (lo1 < lo0) || (lo1 == lo0 && hi1 < hi0);
+                        }
+                    }
+                    if (better) { bv = ov; bi = oi; }
+                }
+                if (lane == 0) nn[row] = bi;
+            }
+            if (threadIdx.x == 0) s_merged = 0;
+            __syncthreads();
+            /* reciprocal nearest pairs within the threshold: the smaller representative absorbs the larger */
+            for (int row = threadIdx.x; row < m; row += blockDim.x)
+            {
+                int pr = -1;
+                const int b = nn[row];
+                if (b > row && nn[b] == row && D[(int64_t)row * m + b] <= a.threshold)
+                {
+                    pr = b;
+                    s_merged = 1;
+                }
+                partner[row] = pr;
+            }
+            __syncthreads();
+            if (!s_merged) break;
+            /* Lance-Williams, rows then columns: D[a][k] = max(D[a][k], D[b][k]); D[k][a] = max(D[k][a], D[k][b]) */
+            for (int row = warp; row < m; row += warps)
+            {
+                const int b = partner[row];
+                if (b < 0) continue;
+                double* Da = D + (int64_t)row * m;
+                const double* Db = D + (int64_t)b * m;
+                for (int k = lane; k < m; k += 32)
+                {
+                    const double x = Da[k], y = Db[k];
+                    Da[k] = (x < y) ? y : x;
+                }
+            }
+            __syncthreads();
+            for (int row = warp; row < m; row += warps)
+            {
+                if (!active[row]) continue;
+                double* Dk = D + (int64_t)row * m;
+                for (int col = lane; col < m; col += 32)
+                {
+                    const int b = partner[col];
+                    if (b >= 0 && col != row)
+                    {
+                        const double x = Dk[col], y = Dk[b];
+                        Dk[col] = (x < y) ? y : x;
+                    }
+                }
+            }
+            __syncthreads();
+            for (int row = threadIdx.x; row < m; row += blockDim.x)
+            {
+                const int b = partner[row];
+                if (b >= 0)
+                {
+                    active[b] = 0;
+                    into[b] = row;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 /* connected components of the threshold graph by min-label propagation + pointer jumping (exact path only) */
 __global__ void __launch_bounds__(256) propagate_kernel(const uint32_t* __restrict__ adj, int64_t total, int64_t set_size, int wpr,
                                                         const int32_t* __restrict__ set_bad, int32_t* __restrict__ comp,
@@ -1537,6 +1665,31 @@ cudaError_t launch_cluster_stats(upc_handle* h, int64_t n, const double* cfg, co
     return cudaGetLastError();
 }
 
+/* ------------------------------------------------------------------ compaction of the sets the pivot pass left unsettled */
+
+/* features (and first-pass groups) of the listed sets, packed as a batch of n_list sets */
+__global__ void __launch_bounds__(256) gather_sets_kernel(const double* __restrict__ feat, int nfeat, int64_t total, int64_t set_size,
+                                                          const int32_t* __restrict__ set_list, int64_t n_list, double* __restrict__ cfeat,
+                                                          const int32_t* __restrict__ group, int32_t* __restrict__ cgroup)
+{
+    const int64_t ctotal = n_list * set_size;
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= ctotal) return;
+    const int64_t k = p / set_size;
+    const int64_t src = (int64_t)set_list[k] * set_size + (p - k * set_size);
+    for (int f = 0; f < nfeat; f++) cfeat[(int64_t)f * ctotal + p] = feat[(int64_t)f * total + src];
+    if (group) cgroup[p] = group[src];
+}
+
+__global__ void __launch_bounds__(256) scatter_roots_kernel(const int32_t* __restrict__ croot, const int32_t* __restrict__ set_list, int64_t n_list,
+                                                            int64_t set_size, int32_t* __restrict__ root)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_list * set_size) return;
+    const int64_t k = p / set_size;
+    root[(int64_t)set_list[k] * set_size + (p - k * set_size)] = croot[p];
+}
+
 /* ------------------------------------------------------------------ host orchestration */
 
 struct PassInput
@@ -1736,7 +1889,15 @@ static int32_t cluster_pass(upc_handle* h, const PassInput& in, int64_t n_sets, 
     UPC_CUDA_TRY(cudaGetLastError());
     const unsigned row_blocks = (unsigned)((rows + 255) / 256);
     const unsigned warp_blocks = (unsigned)((rows * 32 + 255) / 256);
-    for (int round = 0; round < 1 << 20; round++)
+    int64_t largest = 0;
+    for (int c = 0; c < ncomp; c++) largest = std::max(largest, comp_off[(size_t)c + 1] - comp_off[(size_t)c]);
+    {
+        /* components of at most kFusedExactMax members: all rounds inside one CTA each, no host round trips */
+        exact_rounds_fused_kernel<<<(unsigned)std::min(ncomp, 65535), 1024, 0, stream>>>(ea, ncomp);
+        h->stats.kernel_launches++;
+        UPC_CUDA_TRY(cudaGetLastError());
+    }
+    for (int round = 0; largest > kFusedExactMax && round < 1 << 20; round++)
     {
         UPC_CUDA_TRY(cudaMemsetAsync(ea.merged_flag, 0, sizeof(int), stream));
         exact_nearest_kernel<<<warp_blocks, 256, 0, stream>>>(ea);
@@ -2034,8 +2195,44 @@ int32_t run_cluster(upc_handle* h, const upc_cluster_params& cp, int64_t n_sets,
             UPC_CUDA_TRY(cudaStreamSynchronize(stream));
             h->stats.d2h_bytes += n_sets;
             settled = true;
-            for (uint8_t f : flags)
-                if (!f) settled = false;
+            std::vector<int32_t> unsettled;
+            for (int64_t k = 0; k < n_sets; k++)
+                if (!flags[(size_t)k])
+                {
+                    settled = false;
+                    unsettled.push_back((int32_t)k);
+                }
+            if (!settled && (int64_t)unsettled.size() * 2 <= n_sets)
+            {
+                /* a minority of the sets is left: run the pair pass on those only, packed as their own batch (the settled sets'
+                 * roots stay as the pivot pass wrote them) */
+                const int64_t nl = (int64_t)unsettled.size(), ctotal = nl * set_size;
+                /* [set list | packed groups | packed roots] and the packed features */
+                int32_t* ibuf = buf<int32_t>(h->cw.comp_list, (size_t)nl + 2 * (size_t)ctotal);
+                UPC_NULLCHECK(ibuf);
+                double* cfeat = buf<double>(h->cw.comp_feat, (size_t)nfeat * (size_t)ctotal);
+                UPC_NULLCHECK(cfeat);
+                int32_t* d_list = ibuf;
+                int32_t* cgroup = ibuf + nl;
+                int32_t* croot = cgroup + ctotal;
+                UPC_CUDA_TRY(cudaMemcpyAsync(d_list, unsettled.data(), (size_t)nl * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+                h->stats.h2d_bytes += nl * (int64_t)sizeof(int32_t);
+                const unsigned gblocks = (unsigned)((ctotal + 255) / 256);
+                gather_sets_kernel<<<gblocks, 256, 0, stream>>>(feat, nfeat, total, set_size, d_list, nl, cfeat, group, group ? cgroup : nullptr);
+                h->stats.kernel_launches++;
+                UPC_CUDA_TRY(cudaGetLastError());
+                PassInput cin = in;
+                cin.feat = cfeat;
+                cin.group = group ? cgroup : nullptr;
+                int64_t fallback = 0;
+                const int32_t rc = cluster_pass(h, cin, nl, set_size, croot, stream, &fallback);
+                if (rc != UPC_OK) return rc;
+                h->stats.cluster_fallback_calls += fallback;
+                scatter_roots_kernel<<<gblocks, 256, 0, stream>>>(croot, d_list, nl, set_size, root2);
+                h->stats.kernel_launches++;
+                UPC_CUDA_TRY(cudaGetLastError());
+                settled = true;
+            }
         }
     }
     if (!settled)

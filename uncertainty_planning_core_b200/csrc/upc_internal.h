@@ -40,6 +40,8 @@ struct ClusterWorkspace
     DeviceBuffer dedupe;       /* hash table + representative bookkeeping */
     DeviceBuffer usig;         /* compact signatures of the distinct vectors */
     DeviceBuffer uroot;        /* roots of the distinct vectors */
+    DeviceBuffer comp_list;    /* sets the pivot pass left unsettled: list, packed groups, packed roots */
+    DeviceBuffer comp_feat;    /* their packed features */
 };
 
 } /* namespace upc */

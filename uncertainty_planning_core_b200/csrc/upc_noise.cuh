@@ -9,17 +9,17 @@
  *
  *   bits    Philox-4x32-10 (Salmon et al., SC'11): key = the 64-bit seed, counter = (particle lo, particle hi,
  *           controller interval, slot << 16 | axis pair); one block of 128 bits serves axes 2j and 2j + 1
- *   uniform u = (k + 1/2) 2^-52 from 52 of the 64 bits of an axis: strictly inside (0, 1), exactly representable
- *   normal  z = Phi^-1(Phi(-2) + u (Phi(2) - Phi(-2))): the inverse-CDF transform of the normal distribution truncated
- *           to +-2 sigma (the reference's distributions are mean 0, bounds +-2 sigma: simple_uncertainty_models.hpp:29, 59),
- *           Phi^-1 by Wichura's AS 241 (PPND16) rational approximations - central branch for |p - 1/2| <= 0.425, the
- *           first tail branch otherwise (its r = sqrt(-log p) stays below 1.95 here; the far-tail branch cannot occur);
+ *   uniform t = (k + 1/2) 2^-52 - 1/2 from 52 of the 64 bits of an axis: strictly inside (-1/2, 1/2), never 0, exact
+ *   normal  z = Phi^-1(1/2 + t (Phi(2) - Phi(-2))): the inverse-CDF transform of the normal distribution truncated to +-2 sigma
+ *           (the reference's distributions are mean 0, bounds +-2 sigma: simple_uncertainty_models.hpp:29, 59), evaluated by one
+ *           rational approximation of degree 8 / 8 valid on the whole truncated range (|error| <= 4e-14; Wichura's AS 241 needs
+ *           a logarithm and a square root beyond |p - 1/2| = 0.425, a second branch that nearly every warp would execute);
  *           no rejection loop: one Philox block per axis pair, always
  *   draw    sensor slot: z * (max_sensor_noise / 2); actuator slots: z / 2  (the scaling of the tape generator, section 4.1);
  *           a zero noise bound yields an exact 0.0
  *
- * Written once as __host__ __device__; only exact IEEE operations and upc_log (include/upc_math.h), so host and device
- * produce identical bits.
+ * Written once as __host__ __device__; only exact IEEE operations (explicit fused multiply-adds, one division), so host and
+ * device produce identical bits.
  */
 #ifndef UPC_NOISE_CUH
 #define UPC_NOISE_CUH
@@ -61,100 +61,74 @@ UPC_NOISE_HD void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t 
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-/* (k + 1/2) 2^-52 from the top 52 bits of (hi, lo) */
-UPC_NOISE_HD double uniform_open52(uint32_t hi, uint32_t lo)
+/* (k + 1/2) 2^-52 - 1/2 for the 52-bit integer k = top 52 bits of (hi, lo): a uniform variate in (-1/2, 1/2), never 0, exact.
+ * k is placed in the mantissa of a double in [1, 2) - no integer-to-double conversion; both subtractions are exact. */
+UPC_NOISE_HD double uniform_centered52(uint32_t hi, uint32_t lo)
 {
     const uint64_t k = ((uint64_t)hi << 20) | (uint64_t)(lo >> 12);
-    return ((double)k + 0.5) * 2.220446049250313080847e-16; /* 2^-52 */
-}
-
-/* inverse of the standard normal CDF for 0.02 < p < 0.98 (AS 241, PPND16, branches 1 and 2) */
-UPC_NOISE_HD double normal_quantile_central(double p)
-{
-    const double q = p - 0.5;
-    if (fabs(q) <= 0.425)
-    {
-        const double r = 0.180625 - q * q;
-        double num = 2.5090809287301226727e+3;
-        num = num * r + 3.3430575583588128105e+4;
-        num = num * r + 6.7265770927008700853e+4;
-        num = num * r + 4.5921953931549871457e+4;
-        num = num * r + 1.3731693765509461125e+4;
-        num = num * r + 1.9715909503065514427e+3;
-        num = num * r + 1.3314166789178437745e+2;
-        num = num * r + 3.3871328727963666080e+0;
-        double den = 5.2264952788528545610e+3;
-        den = den * r + 2.8729085735721942674e+4;
-        den = den * r + 3.9307895800092710610e+4;
-        den = den * r + 2.1213794301586595867e+4;
-        den = den * r + 5.3941960214247511077e+3;
-        den = den * r + 6.8718700749205790830e+2;
-        den = den * r + 4.2313330701600911252e+1;
-        den = den * r + 1.0;
-        return (q * num) / den;
-    }
-    const double tail = (q < 0.0) ? p : (1.0 - p);
-    const double r = sqrt(-upc_log(tail)) - 1.6;
-    double num = 7.74545014278341407640e-4;
-    num = num * r + 2.27238449892691845833e-2;
-    num = num * r + 2.41780725177450611770e-1;
-    num = num * r + 1.27045825245236838258e+0;
-    num = num * r + 3.64784832476320460504e+0;
-    num = num * r + 5.76949722146069140550e+0;
-    num = num * r + 4.63033784615654529590e+0;
-    num = num * r + 1.42343711074968357734e+0;
-    double den = 1.05075007164441684324e-9;
-    den = den * r + 5.47593808499534494600e-4;
-    den = den * r + 1.51986665636164571966e-2;
-    den = den * r + 1.48103976427480074590e-1;
-    den = den * r + 6.89767334985100004550e-1;
-    den = den * r + 1.67638483018380384940e+0;
-    den = den * r + 2.05319162663775882187e+0;
-    den = den * r + 1.0;
-    const double z = num / den;
-    return (q < 0.0) ? -z : z;
-}
-
-/* standard normal truncated to [-2, 2] from one uniform in (0, 1) */
-UPC_NOISE_HD double truncated_normal_from_uniform(double u)
-{
-    const double P_LO = 2.275013194817920720e-02;  /* Phi(-2) */
-    const double P_W = 9.544997361036415856e-01;   /* Phi(2) - Phi(-2) */
-    const double z = normal_quantile_central(P_LO + u * P_W);
-    return upc_max(-2.0, upc_min(2.0, z));
-}
-
-/* the two standard truncated normals of axis pair `pair` (axes 2 pair, 2 pair + 1) */
-UPC_NOISE_HD void noise_pair(uint64_t seed, uint64_t particle, uint32_t step, uint32_t slot, uint32_t pair, double* z0, double* z1)
-{
-    uint32_t r[4];
-    philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)particle, (uint32_t)(particle >> 32), step, (slot << 16) | pair, r);
-    *z0 = truncated_normal_from_uniform(uniform_open52(r[0], r[1]));
-    *z1 = truncated_normal_from_uniform(uniform_open52(r[2], r[3]));
+    const double one_to_two = upc_bits_double(0x3ff0000000000000ull | k); /* 1 + k 2^-52 */
+    return (one_to_two - 1.5) + 1.1102230246251565404e-16;                  /* + 2^-53 */
 }
 
 /*
- * All draws of one (particle, controller interval, slot): out[d] for d < dof.  scale[d] is the factor applied to the
- * standard draw of axis d (sensor: max_sensor_noise / 2, actuator: 1/2 when the axis has actuator noise) and 0 for a
- * noise-free axis, which yields an exact 0.0.  N is the compile-time capacity of `out`.
+ * Standard normal truncated to [-2, 2] from a centred uniform t in (-1/2, 1/2): z = Phi^-1(1/2 + q), q = t (Phi(2) - Phi(-2)).
+ * On |q| <= 0.47725 the quantile is evaluated by ONE rational approximation z = q P(r) / Q(r), r = 0.228 - q^2, of degree 8 / 8
+ * (coefficients fitted in 60-digit arithmetic by scripts/fit_truncated_quantile.py; all positive, so the fused Horner steps do
+ * not cancel): maximum absolute error 4e-14 against the exact quantile.  No branch, no logarithm, one division.
  */
-template <int N>
-UPC_NOISE_HD void noise_draws(uint64_t seed, uint64_t particle, uint32_t step, uint32_t slot, int dof, const double* scale, double* out)
+UPC_NOISE_HD double truncated_normal_from_centered(double t)
 {
-#pragma unroll
-    for (int p = 0; p < (N + 1) / 2; p++)
-    {
-        const int d0 = 2 * p, d1 = 2 * p + 1;
-        if (d0 < dof)
-        {
-            const double s0 = scale[d0];
-            const double s1 = (d1 < N && d1 < dof) ? scale[d1] : 0.0;
-            double z0 = 0.0, z1 = 0.0;
-            if ((s0 != 0.0) || (s1 != 0.0)) noise_pair(seed, particle, step, slot, (uint32_t)p, &z0, &z1);
-            out[d0] = (s0 != 0.0) ? z0 * s0 : 0.0;
-            if (d1 < N && d1 < dof) out[d1] = (s1 != 0.0) ? z1 * s1 : 0.0;
-        }
-    }
+    const double q = t * 9.544997361036415856e-01;
+    const double r = upc_fma(-q, q, 0.228);
+    double num = 3.04619464759342372e+06;
+    num = upc_fma(num, r, 3.29915794812198505e+07);
+    num = upc_fma(num, r, 5.03468522432988584e+07);
+    num = upc_fma(num, r, 2.44404971329663284e+07);
+    num = upc_fma(num, r, 4.94985450103831850e+06);
+    num = upc_fma(num, r, 4.73334579451213649e+05);
+    num = upc_fma(num, r, 2.23256080577635075e+04);
+    num = upc_fma(num, r, 4.98914924494953766e+02);
+    num = upc_fma(num, r, 4.19803057674432534e+00);
+    double den = 5.87769839876705315e+06;
+    den = upc_fma(den, r, 2.58257609111968540e+07);
+    den = upc_fma(den, r, 2.63619050062270910e+07);
+    den = upc_fma(den, r, 9.97100045574528910e+06);
+    den = upc_fma(den, r, 1.69745287590994616e+06);
+    den = upc_fma(den, r, 1.42817358525897551e+05);
+    den = upc_fma(den, r, 6.10854034951519316e+03);
+    den = upc_fma(den, r, 1.26415601550449168e+02);
+    den = upc_fma(den, r, 1.0);
+    const double z = (q * num) / den;
+    return upc_max(-2.0, upc_min(2.0, z));
+}
+
+struct NoisePair
+{
+    double z0, z1;
+};
+
+/* the two standard truncated normals of axis pair `pair` (axes 2 pair, 2 pair + 1).  One out-of-line copy per kernel: inlined at
+ * every use the generator made the simulation program 30 - 35 % longer, past the instruction cache (profiles/README.md). */
+#if defined(__CUDACC__)
+inline __host__ __device__ __noinline__
+#else
+inline
+#endif
+NoisePair noise_pair_values(uint64_t seed, uint64_t particle, uint32_t step, uint32_t slot_pair)
+{
+    uint32_t r[4];
+    philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)particle, (uint32_t)(particle >> 32), step, slot_pair, r);
+    NoisePair out;
+    out.z0 = truncated_normal_from_centered(uniform_centered52(r[0], r[1]));
+    out.z1 = truncated_normal_from_centered(uniform_centered52(r[2], r[3]));
+    return out;
+}
+
+UPC_NOISE_HD void noise_pair(uint64_t seed, uint64_t particle, uint32_t step, uint32_t slot, uint32_t pair, double* z0, double* z1)
+{
+    const NoisePair v = noise_pair_values(seed, particle, step, (slot << 16) | pair);
+    *z0 = v.z0;
+    *z1 = v.z1;
 }
 
 } /* namespace upc */
