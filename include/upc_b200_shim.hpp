@@ -31,6 +31,7 @@
 #include <cstdint>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <random>
 #include <stdexcept>
 #include <string>
@@ -242,6 +243,45 @@ private:
     upc_handle* h_;
 };
 
+/* Grow-only page-locked host staging (upc_host_alloc): transfers from pinned memory run at full PCIe speed and need no driver-side
+ * staging copy; the buffers are reused from call to call, so nothing is allocated or zero-filled per call. */
+class PinnedBuffer
+{
+public:
+    PinnedBuffer() : ptr_(nullptr), bytes_(0) {}
+    ~PinnedBuffer() { if (ptr_) upc_host_free(ptr_); }
+    PinnedBuffer(const PinnedBuffer&) = delete;
+    PinnedBuffer& operator=(const PinnedBuffer&) = delete;
+    template <typename T>
+    T* get(const size_t count)
+    {
+        const size_t want = count * sizeof(T);
+        if (want > bytes_)
+        {
+            if (ptr_) upc_host_free(ptr_);
+            ptr_ = nullptr;
+            bytes_ = 0;
+            size_t cap = 4096;
+            while (cap < want) cap *= 2;
+            check(upc_host_alloc(&ptr_, (int64_t)cap));
+            bytes_ = cap;
+        }
+        return static_cast<T*>(ptr_);
+    }
+
+private:
+    void* ptr_;
+    size_t bytes_;
+};
+
+/* staging of one simulator: inputs, outputs, flags, labels, cluster counts; guarded by a mutex because the interface methods are
+ * const and may be called from several threads (threading) */
+struct Staging
+{
+    std::mutex mutex;
+    PinnedBuffer starts, targets, out, collided, labels, counts;
+};
+
 /* ---- SimulatorInterface ---------------------------------------------------------------------------------------------- */
 
 template <typename Robot, typename Configuration, typename RNG, typename ConfigAlloc = std::allocator<Configuration>>
@@ -331,19 +371,21 @@ public:
         const upc_sim_params params = MakeParams(forward_simulation_time, simulation_shortcut_distance, use_individual_jacobians, allow_contacts);
         /* structure-of-arrays staging */
         const size_t nt = target_positions.size();
-        std::vector<double> starts((size_t)width * n), targets((size_t)width * nt), out((size_t)width * n);
-        FlattenToSoa(start_positions, width, starts.data());
-        FlattenToSoa(target_positions, width, targets.data());
+        std::lock_guard<std::mutex> guard(staging_->mutex);
+        double* starts = staging_->starts.template get<double>((size_t)width * n);
+        double* targets = staging_->targets.template get<double>((size_t)width * nt);
+        double* out = staging_->out.template get<double>((size_t)width * n);
+        uint8_t* collided = staging_->collided.template get<uint8_t>(n);
+        FlattenToSoa(start_positions, width, starts);
+        FlattenToSoa(target_positions, width, targets);
         /* Noise: the caller's generator is advanced by ONE draw per call (a 64-bit seed); particle i then draws from the
          * counter-based stream (seed, i) inside the kernel - no tape is generated or shipped, and results are
          * independent of OpenMP thread counts, which the reference's per-thread generators
          * (uncertainty_contact_planning.hpp:349-356) are not. */
         const uint64_t seed = NextSeed(rng[0]);
-        std::vector<uint8_t> collided(n);
-        check(upc_forward_simulate_seeded(handle_->get(), &params, seed, 0, (int64_t)n, (int64_t)n, starts.data(), (int64_t)nt, targets.data(),
-                                          out.data(), collided.data()));
+        check(upc_forward_simulate_seeded(handle_->get(), &params, seed, 0, (int64_t)n, (int64_t)n, starts, (int64_t)nt, targets, out, collided));
         results.resize(n, std::make_pair(start_positions[0], false));
-        const double* outp = out.data();
+        const double* outp = out;
 #pragma omp parallel for schedule(static) if (n > 4096)
         for (int64_t i = 0; i < (int64_t)n; i++)
         {
@@ -416,30 +458,19 @@ public:
         if (n == 0) return result;
         const int width = Traits::width(edge_starts[0]);
         const upc_sim_params params = MakeParams(forward_simulation_time, simulation_shortcut_distance, use_individual_jacobians, allow_contacts);
-        std::vector<double> starts((size_t)width * E), targets((size_t)width * E), out((size_t)width * n);
-        FlattenToSoa(edge_starts, width, starts.data());
-        FlattenToSoa(edge_targets, width, targets.data());
-        std::vector<uint8_t> collided(n);
-        std::vector<int32_t> labels(n), n_clusters(E);
+        std::lock_guard<std::mutex> guard(staging_->mutex);
+        double* starts = staging_->starts.template get<double>((size_t)width * E);
+        double* targets = staging_->targets.template get<double>((size_t)width * E);
+        double* out = staging_->out.template get<double>((size_t)width * n);
+        uint8_t* collided = staging_->collided.template get<uint8_t>(n);
+        int32_t* labels = staging_->labels.template get<int32_t>(n);
+        int32_t* n_clusters = staging_->counts.template get<int32_t>(E);
+        FlattenToSoa(edge_starts, width, starts);
+        FlattenToSoa(edge_targets, width, targets);
         const uint64_t seed = NextSeed(rng[0]);
-        check(upc_simulate_and_cluster_edges(handle_->get(), &params, &clustering.params(), seed, 0, (int64_t)E, (int64_t)P, starts.data(), targets.data(),
-                                             out.data(), collided.data(), labels.data(), n_clusters.data()));
-        const double* outp = out.data();
-#pragma omp parallel for schedule(static) if (E > 16)
-        for (int64_t e = 0; e < (int64_t)E; e++)
-        {
-            std::vector<std::vector<std::pair<Configuration, bool>>>& clusters = result[(size_t)e];
-            clusters.resize((size_t)n_clusters[(size_t)e]);
-            double tmp[16];
-            for (size_t k = 0; k < P; k++)
-            {
-                const size_t i = (size_t)e * P + k;
-                const bool hit = collided[i] != 0;
-                if (hit && !allow_contacts) continue; /* uncertainty_contact_planning.hpp:2019 */
-                for (int c = 0; c < width; c++) tmp[c] = outp[(size_t)c * n + i];
-                clusters[(size_t)labels[i]].push_back(std::make_pair(Traits::inflate(tmp, edge_starts[(size_t)e]), hit));
-            }
-        }
+        check(upc_simulate_and_cluster_edges(handle_->get(), &params, &clustering.params(), seed, 0, (int64_t)E, (int64_t)P, starts, targets, out, collided, labels,
+                                             n_clusters));
+        AssembleEdgeClusters(edge_starts, P, n, width, allow_contacts, out, collided, labels, n_clusters, n, 0, E, result);
         return result;
     }
 
@@ -488,6 +519,39 @@ public:
         }
     }
 
+    /* clusters of edges [first_edge, first_edge + count) from flat outcome arrays (configs [C][stride], edge-major particles starting
+     * at column 0 for first_edge): sizes are counted first so that every cluster is allocated once */
+    static void AssembleEdgeClusters(const std::vector<Configuration, ConfigAlloc>& edge_starts, const size_t P, const size_t n_columns, const int width,
+                                     const bool allow_contacts, const double* configs, const uint8_t* collided, const int32_t* labels,
+                                     const int32_t* n_clusters, const size_t stride, const size_t first_edge, const size_t count,
+                                     std::vector<std::vector<std::vector<std::pair<Configuration, bool>>>>& result)
+    {
+        (void)n_columns;
+#pragma omp parallel for schedule(static) if (count > 16)
+        for (int64_t el = 0; el < (int64_t)count; el++)
+        {
+            std::vector<std::vector<std::pair<Configuration, bool>>>& clusters = result[first_edge + (size_t)el];
+            const size_t K = (size_t)n_clusters[el];
+            clusters.resize(K);
+            std::vector<size_t> sizes(K, 0);
+            for (size_t k = 0; k < P; k++)
+            {
+                const size_t i = (size_t)el * P + k;
+                if (collided[i] == 0 || allow_contacts) sizes[(size_t)labels[i]]++; /* uncertainty_contact_planning.hpp:2019 */
+            }
+            for (size_t c = 0; c < K; c++) clusters[c].reserve(sizes[c]);
+            double tmp[16];
+            for (size_t k = 0; k < P; k++)
+            {
+                const size_t i = (size_t)el * P + k;
+                const bool hit = collided[i] != 0;
+                if (hit && !allow_contacts) continue;
+                for (int c = 0; c < width; c++) tmp[c] = configs[(size_t)c * stride + i];
+                clusters[(size_t)labels[i]].push_back(std::make_pair(Traits::inflate(tmp, edge_starts[first_edge + (size_t)el]), hit));
+            }
+        }
+    }
+
 protected:
     std::pair<Configuration, bool> SimulateOne(const Robot& immutable_robot, const Configuration& start_position, const Configuration& target_position, RNG& rng,
                                                const double forward_simulation_time, const double simulation_shortcut_distance,
@@ -529,6 +593,7 @@ protected:
     RobotDescription robot_;
     SolverConfig solver_;
     std::shared_ptr<Handle> handle_;
+    std::shared_ptr<Staging> staging_ = std::shared_ptr<Staging>(new Staging());
 #ifndef UPC_SHIM_WITH_REFERENCE
     int32_t debug_level_;
 #endif
@@ -578,10 +643,10 @@ public:
         has_ptpm_ = true;
     }
 
-    B200OutcomeClustering(const B200OutcomeClustering& o) : handle_(o.handle_), params_(o.params_), ptpm_params_(o.ptpm_params_), has_ptpm_(o.has_ptpm_) {}
+    B200OutcomeClustering(const B200OutcomeClustering& o) : handle_(o.handle_), params_(o.params_), ptpm_params_(o.ptpm_params_), has_ptpm_(o.has_ptpm_), staging_(o.staging_) {}
     B200OutcomeClustering& operator=(const B200OutcomeClustering& o)
     {
-        handle_ = o.handle_; params_ = o.params_; ptpm_params_ = o.ptpm_params_; has_ptpm_ = o.has_ptpm_;
+        handle_ = o.handle_; params_ = o.params_; ptpm_params_ = o.ptpm_params_; has_ptpm_ = o.has_ptpm_; staging_ = o.staging_;
         return *this;
     }
 
@@ -599,16 +664,22 @@ public:
         std::vector<std::vector<size_t>> clusters;
         if (n == 0) return clusters;
         const int width = Traits::width(*configs[0]);
-        std::vector<double> soa((size_t)width * n), tmp((size_t)width);
-        for (size_t i = 0; i < n; i++)
+        std::lock_guard<std::mutex> guard(staging_->mutex);
+        double* soa = staging_->starts.template get<double>((size_t)width * n);
+        int32_t* labels = staging_->labels.template get<int32_t>(n);
+        int32_t* n_clusters = staging_->counts.template get<int32_t>(1);
+#pragma omp parallel for schedule(static) if (n > 4096)
+        for (int64_t i = 0; i < (int64_t)n; i++)
         {
-            Traits::flatten(*configs[i], tmp.data());
-            for (int c = 0; c < width; c++) soa[(size_t)c * n + i] = tmp[(size_t)c];
+            double tmp[16];
+            Traits::flatten(*configs[(size_t)i], tmp);
+            for (int c = 0; c < width; c++) soa[(size_t)c * n + (size_t)i] = tmp[c];
         }
-        std::vector<int32_t> labels(n);
-        int32_t n_clusters = 0;
-        check(upc_cluster_particles(handle_, &params(), 1, (int64_t)n, soa.data(), labels.data(), &n_clusters));
-        clusters.resize((size_t)n_clusters);
+        check(upc_cluster_particles(handle_, &params(), 1, (int64_t)n, soa, labels, n_clusters));
+        clusters.resize((size_t)n_clusters[0]);
+        std::vector<size_t> sizes((size_t)n_clusters[0], 0);
+        for (size_t i = 0; i < n; i++) sizes[(size_t)labels[i]]++;
+        for (size_t k = 0; k < clusters.size(); k++) clusters[k].reserve(sizes[k]);
         for (size_t i = 0; i < n; i++) clusters[(size_t)labels[i]].push_back(i);
         return clusters;
     }
@@ -739,6 +810,7 @@ private:
     mutable upc_cluster_params params_;
     upc_sim_params ptpm_params_{};
     bool has_ptpm_ = false;
+    std::shared_ptr<Staging> staging_ = std::shared_ptr<Staging>(new Staging());
 };
 
 /* ---- one box, several GPUs ------------------------------------------------------------------------------------------ */
@@ -816,36 +888,18 @@ public:
                                          d_targets.data(), d_blocks.data(), nullptr));
         for (size_t r = 0; r < W; r++) check(upc_comm_synchronize(comms_[r]));
         /* every device now holds every rank's block: read them all from the first */
-        std::vector<uint8_t> host((size_t)lay.block_bytes * W);
-        check(upc_memcpy_to_host(simulators_[0]->handle(), host.data(), d_blocks[0], (int64_t)host.size()));
-#pragma omp parallel for schedule(dynamic, 8) if (E > 16)
-        for (int64_t e = 0; e < (int64_t)E; e++)
+        uint8_t* host = host_blocks_.template get<uint8_t>((size_t)lay.block_bytes * W);
+        check(upc_memcpy_to_host(simulators_[0]->handle(), host, d_blocks[0], (int64_t)((size_t)lay.block_bytes * W)));
+        for (size_t r = 0; r < W; r++)
         {
-            /* owner rank and position of edge e inside the owner's block */
-            size_t r = 0;
             int64_t lo = 0, hi = 0;
-            for (; r < W; r++)
-            {
-                upc_shard_bounds((int64_t)E, (int32_t)r, (int32_t)W, &lo, &hi);
-                if (e >= lo && e < hi) break;
-            }
-            const uint8_t* block = host.data() + r * (size_t)lay.block_bytes;
-            const int32_t* labels = (const int32_t*)(block + lay.labels_offset);
-            const int32_t* n_clusters = (const int32_t*)(block + lay.n_clusters_offset);
-            const uint8_t* collided = block + lay.collided_offset;
-            const double* configs = (const double*)(block + lay.configs_offset);
-            const size_t n_local = (size_t)(hi - lo) * P, el = (size_t)(e - lo);
-            std::vector<std::vector<std::pair<Configuration, bool>>>& clusters = result[(size_t)e];
-            clusters.resize((size_t)n_clusters[el]);
-            double tmp[16];
-            for (size_t k = 0; k < P; k++)
-            {
-                const size_t i = el * P + k;
-                const bool hit = collided[i] != 0;
-                if (hit && !allow_contacts) continue;
-                for (int c = 0; c < width; c++) tmp[c] = configs[(size_t)c * n_local + i];
-                clusters[(size_t)labels[i]].push_back(std::make_pair(Traits::inflate(tmp, edge_starts[(size_t)e]), hit));
-            }
+            upc_shard_bounds((int64_t)E, (int32_t)r, (int32_t)W, &lo, &hi);
+            if (hi == lo) continue;
+            const uint8_t* block = host + r * (size_t)lay.block_bytes;
+            const size_t n_local = (size_t)(hi - lo) * P;
+            Simulator::AssembleEdgeClusters(edge_starts, P, n_local, width, allow_contacts, (const double*)(block + lay.configs_offset), block + lay.collided_offset,
+                                            (const int32_t*)(block + lay.labels_offset), (const int32_t*)(block + lay.n_clusters_offset), n_local, (size_t)lo,
+                                            (size_t)(hi - lo), result);
         }
         return result;
     }
@@ -853,6 +907,7 @@ public:
 private:
     std::vector<std::shared_ptr<Simulator>> simulators_;
     std::vector<upc_comm*> comms_;
+    PinnedBuffer host_blocks_;
 };
 
 /*
