@@ -38,7 +38,9 @@ def run(mode):
         d_full_t = torch.from_numpy(np.ascontiguousarray(np.repeat(et, P, axis=0).T)).to(dev)
         d_out = torch.zeros((robot.width, n), dtype=torch.float64, device=dev)
         d_coll = torch.zeros(n, dtype=torch.uint8, device=dev)
-        stream = torch.cuda.current_stream().cuda_stream
+        side = torch.cuda.Stream(device=dev)      # a non-NULL handle: NULL would select the library's own stream, which torch events do not see
+        torch.cuda.set_stream(side)
+        stream = side.cuda_stream
         res = {}
         variants = [("seeded", None)]
         tape_bytes = int(np.prod(abi.tape_shape(params, robot.dof, n))) * 8

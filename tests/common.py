@@ -41,6 +41,7 @@ def emulation():
         lib.emulate_forward_simulate_seeded.restype = C.c_int
         lib.emulate_set_corner_cells.argtypes = [C.c_int]
         lib.emulate_set_fp32_cull.argtypes = [C.c_int]
+        lib.emulate_set_link_cull.argtypes = [C.c_int]
         lib.emulate_cull_check.argtypes = [C.POINTER(abi.EnvDesc), C.POINTER(abi.RobotDesc), i64, vp, C.c_double, vp]
         lib.emulate_cull_check.restype = C.c_int
         _EMU = lib
@@ -49,21 +50,22 @@ def emulation():
 
 def emulate_cull_check(env, robot, frames, threshold):
     """Single-precision pre-cull against the exact program for link poses `frames` [F, 12]:
-    returns (tested, culled, violations, exact_hits); violations must be 0."""
+    returns (tested, culled, violations, exact_hits, links_cleared, link_violations); both violation counts must be 0."""
     frames = np.ascontiguousarray(frames, dtype=np.float64)
-    counts = np.zeros(4, dtype=np.int64)
+    counts = np.zeros(6, dtype=np.int64)
     rc = emulation().emulate_cull_check(C.byref(env.desc), C.byref(robot.desc), frames.shape[0], frames.ctypes.data, float(threshold), counts.ctypes.data)
     if rc != 0:
         raise RuntimeError("pre-cull disabled for this environment / robot")
     return tuple(int(c) for c in counts)
 
 
-def emulate_forward_simulate(env, robot, params, starts, targets, tape, corner_cells=True, fp32_cull=True):
+def emulate_forward_simulate(env, robot, params, starts, targets, tape, corner_cells=True, fp32_cull=True, link_cull=True):
     """The product's per-thread program run on the CPU with one lane per particle.
     corner_cells selects the SDF layout the collision passes read (corner-cell table vs plain grid + cell-minimum cull);
     fp32_cull switches the single-precision pre-cull of the point passes."""
     emulation().emulate_set_corner_cells(1 if corner_cells else 0)
     emulation().emulate_set_fp32_cull(1 if fp32_cull else 0)
+    emulation().emulate_set_link_cull(1 if link_cull else 0)
     starts = np.asarray(starts, dtype=np.float64)
     targets = np.asarray(targets, dtype=np.float64)
     n = starts.shape[0]

@@ -85,13 +85,29 @@ static void run(const DevEnv& env, const DevRobot& rob, const DevSim& sp, int64_
 
 static int g_use_cells = 1;
 static int g_use_fp32_cull = 1;
+static int g_use_link_cull = 1;
 extern "C" void emulate_set_corner_cells(int on) { g_use_cells = on; }
 extern "C" void emulate_set_fp32_cull(int on) { g_use_fp32_cull = on; }
+extern "C" void emulate_set_link_cull(int on) { g_use_link_cull = on; }
+
+/* link boxes + dilated cell minima, as upc_set_robot prepares them */
+static void fill_link_cull(const upc_env_desc* e, const upc_robot_desc* r, const std::vector<float>& cellmin, DevRobot* rob, std::vector<float>* dil)
+{
+    rob->dil_radius = g_use_link_cull ? compute_link_boxes(r, e->resolution, e->grid_from_world, rob->link_center, rob->link_half) : 0;
+    rob->dilmin = nullptr;
+    if (rob->dil_radius > 0)
+    {
+        dil->resize(cellmin.size());
+        build_dilated_cellmin(cellmin.data(), e->nx, e->ny, e->nz, rob->dil_radius, dil->data());
+        rob->dilmin = dil->data();
+    }
+}
 
 /*
  * Conservativeness of the single-precision pre-cull, tested directly: for n_frames link poses (rows of 12 doubles)
  * every body point the cull declares clear must be clear for the exact FP64 program at `threshold`.
- * counts[0] = points tested, [1] = culled, [2] = violations (must be 0), [3] = exact hits.
+ * counts[0] = points tested, [1] = culled, [2] = violations (must be 0), [3] = exact hits, [4] = links cleared by the link-level
+ * cull, [5] = violations of the link-level cull (must be 0).
  */
 extern "C" int emulate_cull_check(const upc_env_desc* e, const upc_robot_desc* r, int64_t n_frames, const double* frames, double threshold, int64_t* counts)
 {
@@ -103,7 +119,14 @@ extern "C" int emulate_cull_check(const upc_env_desc* e, const upc_robot_desc* r
     const std::vector<double> both = points_with_float_copy(r->points, r->num_points);
     rob.pts = both.data();
     rob.cull_delta = compute_cull_delta(e->nx, e->ny, e->nz, e->resolution, e->grid_from_world, r->points, r->num_points);
-    for (int k = 0; k < 4; k++) counts[k] = 0;
+    std::vector<float> dil;
+    {
+        const int saved = g_use_link_cull; /* this check always looks at the link-level cull, whatever the simulation switch says */
+        g_use_link_cull = 1;
+        fill_link_cull(e, r, cellmin, &rob, &dil);
+        g_use_link_cull = saved;
+    }
+    for (int k = 0; k < 6; k++) counts[k] = 0;
     if (!(rob.cull_delta > 0.0f)) return 1;
     const Corner4* ptsf = reinterpret_cast<const Corner4*>(rob.pts + 4 * rob.num_points);
     for (int64_t f = 0; f < n_frames; f++)
@@ -113,6 +136,19 @@ extern "C" int emulate_cull_check(const upc_env_desc* e, const upc_robot_desc* r
         for (int l = 0; l < rob.num_links; l++)
         {
             const float clear_above = float_round_up((rob.link_radius[l] + threshold) + UPC_CULL_MARGIN);
+            /* link-level cull: counts[4] = links declared clear, counts[5] = of those, links with a point the exact program hits (must be 0) */
+            if (link_certainly_clear(env, rob, l, V, clear_above))
+            {
+                counts[4]++;
+                bool any = false;
+                for (int k = rob.link_off[l]; k < rob.link_off[l + 1]; k++)
+                {
+                    double u[3];
+                    xf_point(V, rob.pts[4 * k + 0], rob.pts[4 * k + 1], rob.pts[4 * k + 2], u);
+                    any |= (sdf_distance(env, u) - rob.pts[4 * k + 3]) < threshold;
+                }
+                counts[5] += any ? 1 : 0;
+            }
             const CullFrame cf = cull_frame(env, V, rob.cull_delta, clear_above);
             for (int k = rob.link_off[l]; k < rob.link_off[l + 1]; k++)
             {
@@ -163,6 +199,8 @@ static int emulate_impl(const upc_env_desc* e, const upc_robot_desc* r, const up
     std::vector<float> cellmin((size_t)(e->nx + 1) * (size_t)(e->ny + 1) * (size_t)(e->nz + 1));
     build_cellmin(e->sdf, e->nx, e->ny, e->nz, cellmin.data());
     env.cellmin = cellmin.data();
+    std::vector<float> dil;
+    fill_link_cull(e, r, cellmin, &rob, &dil);
     std::vector<float> cells;
     if (g_use_cells)
     {

@@ -224,6 +224,37 @@ def test_single_precision_pre_cull_changes_nothing(oracle):
         sim.close()
 
 
+def test_link_level_cull_changes_nothing(oracle):
+    """the link-level cull (one dilated-minimum lookup per link) is a shortcut only - results with it (default) and
+    without it (UPC_B200_NO_LINK_CULL=1) are the oracle's, for every robot kind, both SDF layouts and several lane counts"""
+    from uncertainty_planning_core_b200 import B200Simulator
+    for make in (cases.se2_contact, cases.se3_contact, cases.linked_contact, cases.linked_mixed_joints):
+        sc = make()
+        n = sc["starts"].shape[0]
+        tape = abi.fill_noise_tape(sc["seed"], sc["robot"], sc["params"], n)
+        ocfg, ocoll, ostats = oracle.forward_simulate(sc["env"], sc["robot"], sc["params"], sc["starts"], sc["targets"], tape)
+        for off in (False, True):
+            for plain in (False, True):
+                if off:
+                    os.environ["UPC_B200_NO_LINK_CULL"] = "1"
+                if plain:
+                    os.environ["UPC_B200_NO_CORNER_CELLS"] = "1"
+                try:
+                    sim = B200Simulator(sc["env"], sc["robot"])
+                finally:
+                    os.environ.pop("UPC_B200_NO_LINK_CULL", None)
+                    os.environ.pop("UPC_B200_NO_CORNER_CELLS", None)
+                for lanes in (1, 4, 32):
+                    sim.SetLanesPerParticle(lanes)
+                    sim.ResetStatistics()
+                    cfg, coll = sim.ForwardSimulateRobots(sc["starts"], sc["targets"], tape, sc["params"])
+                    assert np.array_equal(coll, ocoll) and max_ulp_diff(cfg, ocfg) <= CONFIG_ULP_TOLERANCE, (make.__name__, off, plain, lanes)
+                    st = sim.GetStatistics()
+                    for k in cases.SIM_STAT_KEYS:
+                        assert int(st[k]) == ostats[k], (make.__name__, off, plain, lanes, k)
+                sim.close()
+
+
 def test_check_config_collision_matches_oracle(oracle, simulators):
     for make in (cases.se2_contact, cases.se3_contact, cases.linked_contact):
         sc = make()

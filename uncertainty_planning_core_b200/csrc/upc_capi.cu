@@ -194,7 +194,8 @@ int32_t upc_create(const upc_env_desc* env, int32_t device, upc_handle** out)
     {
         /* cell-minimum grid for the conservative SDF cull */
         const size_t mcells = (size_t)(env->nx + 1) * (size_t)(env->ny + 1) * (size_t)(env->nz + 1);
-        std::vector<float> cellmin(mcells);
+        std::vector<float>& cellmin = h->host_cellmin; /* kept: upc_set_robot dilates it by the robot's link size (link-level cull) */
+        cellmin.resize(mcells);
         build_cellmin(env->sdf, env->nx, env->ny, env->nz, cellmin.data());
         UPC_CUDA_TRY(cudaMalloc(&h->d_cellmin, mcells * sizeof(float)));
         UPC_CUDA_TRY(cudaMemcpyAsync(h->d_cellmin, cellmin.data(), mcells * sizeof(float), cudaMemcpyHostToDevice, h->stream));
@@ -246,6 +247,7 @@ int32_t upc_destroy(upc_handle* h)
     cudaFree(h->d_seg);
     cudaFree(h->d_occ);
     cudaFree(h->d_cellmin);
+    cudaFree(h->d_dilmin);
     cudaFree(h->d_cells);
     cudaFree(h->d_points);
     cudaFree(h->d_counters);
@@ -369,6 +371,25 @@ int32_t upc_set_robot(upc_handle* h, const upc_robot_desc* r)
         d.cull_delta = (off && off[0] == '1') ? 0.0f : compute_cull_delta(h->env.nx, h->env.ny, h->env.nz, h->env.res, h->env.G, r->points, r->num_points);
     }
     d.pts = h->d_points;
+    {
+        /* link-level cull: bounding boxes of the links and the cell-minimum grid dilated by the largest link;
+         * UPC_B200_NO_LINK_CULL=1 switches it off (tests exercise both) */
+        const char* off = getenv("UPC_B200_NO_LINK_CULL");
+        d.dil_radius = (off && off[0] == '1') ? 0 : compute_link_boxes(r, h->env.res, h->env.G, d.link_center, d.link_half);
+        if (h->d_dilmin) cudaFree(h->d_dilmin);
+        h->d_dilmin = nullptr;
+        d.dilmin = nullptr;
+        if (d.dil_radius > 0)
+        {
+            std::vector<float> dil(h->host_cellmin.size());
+            build_dilated_cellmin(h->host_cellmin.data(), h->env.nx, h->env.ny, h->env.nz, d.dil_radius, dil.data());
+            UPC_CUDA_TRY(cudaMalloc(&h->d_dilmin, dil.size() * sizeof(float)));
+            UPC_CUDA_TRY(cudaMemcpyAsync(h->d_dilmin, dil.data(), dil.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+            UPC_CUDA_TRY(cudaStreamSynchronize(h->stream));
+            h->stats.h2d_bytes += (int64_t)(dil.size() * sizeof(float));
+            d.dilmin = h->d_dilmin;
+        }
+    }
     h->robot = d;
     h->has_robot = true;
     return UPC_OK;

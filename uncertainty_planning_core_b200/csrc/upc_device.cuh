@@ -90,6 +90,12 @@ struct DevRobot
     double reach[UPC_MAX_DOF];
     double link_radius[UPC_MAX_LINKS]; /* largest body-sphere radius of each link (conservative single-precision cull) */
     int axis_continuous[UPC_MAX_DOF];  /* linked robots: 1 when the active joint wraps (SimpleJointModel::IsContinuous) */
+    /* link-level cull: bounding box of every link's body points in its frame, and the cell-minimum grid dilated by
+     * dil_radius cells (same indexing as DevEnv::cellmin); dil_radius == 0 switches the cull off */
+    int dil_radius;
+    const float* dilmin;
+    double link_center[UPC_MAX_LINKS][3];
+    double link_half[UPC_MAX_LINKS][3];
     DevJoint joints[UPC_MAX_JOINTS];
 };
 
@@ -453,6 +459,32 @@ UPC_D bool sdf_certainly_clear(const DevEnv& env, const double* u, double radius
     const int ix = floor_to_int(u[0] - 0.5) + 1, iy = floor_to_int(u[1] - 0.5) + 1, iz = floor_to_int(u[2] - 0.5) + 1;
     const double m = (double)ldg(env.cellmin + ((ix * (env.ny + 1) + iy) * (env.nz + 1) + iz));
     return ((m - radius) - limit) > UPC_CULL_MARGIN;
+}
+
+/*
+ * Link-level cull: true when EVERY body point of link l is certainly at distance >= limit + its radius, decided from ONE lookup.
+ * V is the link's voxel-from-link transform.  The link's points lie in the box centre +- half of the link frame, hence - axis by
+ * axis - within c_a +- e_a in voxel coordinates, c = V centre, e_a = sum_j |V_aj| half_j.  When that interval is inside the grid
+ * on every axis all points are in bounds, and the cell every point interpolates in lies within dil_radius cells of the centre's
+ * cell (dil_radius >= half diagonal in cells + 1.5), so the dilated cell minimum at the centre's cell bounds all their
+ * interpolated distances from below (to the few ulps the cull margin covers).  Conservative: anything else returns false and the
+ * per-point passes decide.  clear_above is the rounded-up single-precision threshold the per-point cull uses.
+ */
+UPC_D bool link_certainly_clear(const DevEnv& env, const DevRobot& r, int l, const double* V, float clear_above)
+{
+    if (r.dil_radius == 0) return false;
+    double c[3];
+    xf_point(V, r.link_center[l][0], r.link_center[l][1], r.link_center[l][2], c);
+    const double hx = r.link_half[l][0], hy = r.link_half[l][1], hz = r.link_half[l][2];
+    /* 1e-6 cells of slack absorb the rounding of V, c and e (coordinates are below 2^31 cells) */
+    const double ex = (fabs(V[0]) * hx + fabs(V[1]) * hy) + (fabs(V[2]) * hz + 1.0e-6);
+    const double ey = (fabs(V[4]) * hx + fabs(V[5]) * hy) + (fabs(V[6]) * hz + 1.0e-6);
+    const double ez = (fabs(V[8]) * hx + fabs(V[9]) * hy) + (fabs(V[10]) * hz + 1.0e-6);
+    const bool inside = (c[0] - ex >= 0.0) & (c[0] + ex < env.dnx) & (c[1] - ey >= 0.0) & (c[1] + ey < env.dny) & (c[2] - ez >= 0.0) & (c[2] + ez < env.dnz);
+    if (!inside) return false;
+    const int ix = floor_to_int(c[0] - 0.5) + 1, iy = floor_to_int(c[1] - 0.5) + 1, iz = floor_to_int(c[2] - 0.5) + 1;
+    const float m = ldg(r.dilmin + ((ix * (env.ny + 1) + iy) * (env.nz + 1) + iz));
+    return m > clear_above;
 }
 
 /* smallest float >= v (v finite): a single-precision value may be compared against it instead of against v */

@@ -109,6 +109,86 @@ inline float compute_cull_delta(int nx, int ny, int nz, double res, const double
     return (float)(delta * 1.000001);
 }
 
+/*
+ * Link-level cull: per link the centre and half extents of the bounding box of its body points in the link frame,
+ * and a cell-minimum grid dilated by `radius` cells - dilated[c] = min of cellmin over the cube of cells within `radius` of c
+ * (clamped at the grid border) - so that ONE lookup at the cell of a link's box centre bounds the SDF at every point of the
+ * link from below.  radius must cover the farthest a body point's cell can lie from the centre's cell: ceil(half diagonal /
+ * resolution + 1.5), maximised over the links.  Returns 0 (cull off) when the window would be larger than 32 cells or the grid
+ * transform is not rigid.
+ */
+inline int compute_link_boxes(const upc_robot_desc* r, double res, const double* grid_from_world, double (*center)[3], double (*half)[3])
+{
+    for (int i = 0; i < 3; i++)
+    {
+        const double* row = grid_from_world + 4 * i;
+        const double norm = sqrt(row[0] * row[0] + row[1] * row[1] + row[2] * row[2]);
+        if (!(fabs(norm - 1.0) <= 1.0e-6)) return 0;
+    }
+    double worst = 0.0;
+    for (int l = 0; l < r->num_links; l++)
+    {
+        double lo[3] = {0.0, 0.0, 0.0}, hi[3] = {0.0, 0.0, 0.0};
+        for (int k = r->link_point_offset[l]; k < r->link_point_offset[l + 1]; k++)
+        {
+            const double* p = r->points + 4 * k;
+            for (int a = 0; a < 3; a++)
+            {
+                if (k == r->link_point_offset[l] || p[a] < lo[a]) lo[a] = p[a];
+                if (k == r->link_point_offset[l] || p[a] > hi[a]) hi[a] = p[a];
+            }
+        }
+        double diag2 = 0.0;
+        for (int a = 0; a < 3; a++)
+        {
+            center[l][a] = 0.5 * (lo[a] + hi[a]);
+            /* a hair more than half the span, so that rounding of the centre never leaves a point outside the box */
+            half[l][a] = (0.5 * (hi[a] - lo[a])) * (1.0 + 1.0e-12) + 1.0e-12;
+            diag2 += half[l][a] * half[l][a];
+        }
+        worst = std::max(worst, sqrt(diag2));
+    }
+    const double cells = ceil(worst / res + 1.5 + 1.0e-3);
+    if (!(cells <= 32.0)) return 0;
+    return (int)cells;
+}
+
+inline void build_dilated_cellmin(const float* cellmin, int nx, int ny, int nz, int radius, float* out)
+{
+    /* separable minimum filter over the (nx+1)(ny+1)(nz+1) cell-minimum grid: z, then y, then x */
+    const int64_t X = nx + 1, Y = ny + 1, Z = nz + 1;
+    std::vector<float> tmp((size_t)(X * Y * Z));
+#pragma omp parallel for schedule(static)
+    for (int64_t xy = 0; xy < X * Y; xy++)
+    {
+        const float* src = cellmin + xy * Z;
+        float* dst = out + xy * Z;
+        for (int64_t z = 0; z < Z; z++)
+        {
+            float m = src[z];
+            for (int64_t d = std::max<int64_t>(0, z - radius); d <= std::min<int64_t>(Z - 1, z + radius); d++) m = std::min(m, src[d]);
+            dst[z] = m;
+        }
+    }
+#pragma omp parallel for schedule(static)
+    for (int64_t x = 0; x < X; x++)
+        for (int64_t y = 0; y < Y; y++)
+            for (int64_t z = 0; z < Z; z++)
+            {
+                float m = out[(x * Y + y) * Z + z];
+                for (int64_t d = std::max<int64_t>(0, y - radius); d <= std::min<int64_t>(Y - 1, y + radius); d++) m = std::min(m, out[(x * Y + d) * Z + z]);
+                tmp[(size_t)((x * Y + y) * Z + z)] = m;
+            }
+#pragma omp parallel for schedule(static)
+    for (int64_t x = 0; x < X; x++)
+        for (int64_t yz = 0; yz < Y * Z; yz++)
+        {
+            float m = tmp[(size_t)(x * Y * Z + yz)];
+            for (int64_t d = std::max<int64_t>(0, x - radius); d <= std::min<int64_t>(X - 1, x + radius); d++) m = std::min(m, tmp[(size_t)(d * Y * Z + yz)]);
+            out[x * Y * Z + yz] = m;
+        }
+}
+
 /* device layout of the body points: num_points * 4 doubles (x, y, z, radius) followed by num_points * 4 floats (x, y, z, 0) */
 inline std::vector<double> points_with_float_copy(const double* points, int num_points)
 {

@@ -59,6 +59,8 @@ struct upc_handle
     uint32_t* d_seg = nullptr;
     float* d_occ = nullptr;
     float* d_cellmin = nullptr;
+    float* d_dilmin = nullptr;          /* cell minima dilated by the robot's largest link (link-level cull) */
+    std::vector<float> host_cellmin;    /* host copy of the cell-minimum grid, dilated again whenever the robot changes */
     float* d_cells = nullptr;
     double* d_points = nullptr;
     upc::DevCounters* d_counters = nullptr; /* device-side running totals */

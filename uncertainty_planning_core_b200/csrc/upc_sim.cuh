@@ -188,12 +188,14 @@ UPC_D bool check_collision(const DevEnv& env, const DevRobot& r, const M& m, con
         double T[12], V[12];
         m.frame(r, l, T);
         voxel_from_link(env, T, V);
+        /* single-precision clear threshold: (largest radius of the link + threshold + margin) rounded up - conservative for
+         * every point of the link, so it never changes a result */
+        const float clear_above = float_round_up((r.link_radius[l] + threshold) + UPC_CULL_MARGIN);
+        /* link-level cull: one lookup of the dilated cell minimum clears the whole link when it is far from every obstacle */
+        if (link_certainly_clear(env, r, l, V, clear_above)) continue;
         if (env.cells != nullptr)
         {
-            /* corner-cell table: one sector per point decides (and, if needed, evaluates) it.  The clear test runs in
-             * single precision against (largest radius of the link + threshold + margin) rounded up - conservative for
-             * every point of the link, so it never changes a result. */
-            const float clear_above = float_round_up((r.link_radius[l] + threshold) + UPC_CULL_MARGIN);
+            /* corner-cell table: one sector per point decides (and, if needed, evaluates) it */
             if ((r.cull_delta > 0.0f) && (end - beg >= 8 * G))
             {
                 /* enough points per lane for full batches: single-precision pre-cull against the 4-byte cell minimum
@@ -394,6 +396,9 @@ UPC_RESOLVER_LINKAGE int resolver_correction(const DevEnv& env, const DevRobot& 
         double T[12], V[12];
         m.frame(r, l, T);
         voxel_from_link(env, T, V);
+        const float clear_above = float_round_up((r.link_radius[l] + resolve_distance) + UPC_CULL_MARGIN);
+        /* link-level cull: a link farther than resolve_distance from every obstacle contributes nothing */
+        if (link_certainly_clear(env, r, l, V, clear_above)) continue;
         for (int chunk = beg; chunk < end; chunk += 32 * G)
         {
             const int first = chunk + g.sub;
@@ -403,7 +408,6 @@ UPC_RESOLVER_LINKAGE int resolver_correction(const DevEnv& env, const DevRobot& 
             if (env.cells != nullptr)
             {
                 /* corner-cell table: phases A and B in one pass over the lane's points, kResolverInFlight lookups in flight per trip */
-                const float clear_above = float_round_up((r.link_radius[l] + resolve_distance) + UPC_CULL_MARGIN);
                 bool culled_pass = false;
                 if constexpr (UPC_RES_PRECULL && G >= UPC_RES_PRECULL_MIN_LANES && G <= 8)
                 if ((r.cull_delta > 0.0f) && (end - beg >= 8 * G))
