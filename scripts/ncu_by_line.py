@@ -61,7 +61,8 @@ def main():
     n = min(len(body), len(lines))
     import glob
     import os
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    # UPC_SRC_ROOT: the checkout the profiled binary was built from (line numbers must match), default = this tree
+    root = os.environ.get("UPC_SRC_ROOT") or os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     path_by_name = {os.path.basename(p): p for p in glob.glob(root + "/uncertainty_planning_core_b200/csrc/*") + glob.glob(root + "/include/*")}
     by_fn, by_line = collections.Counter(), collections.Counter()
     s_fn, s_line = collections.Counter(), collections.Counter()

@@ -6,6 +6,7 @@
  */
 #include <string.h>
 #include <math.h>
+#include <cmath>
 #include <vector>
 #include "upc_sim.cuh"
 #include "upc_host_prep.h"
@@ -15,6 +16,13 @@ using namespace upc;
 static void fill_env(const upc_env_desc* e, DevEnv* d)
 {
     d->nx = e->nx; d->ny = e->ny; d->nz = e->nz;
+    d->planar = 0;
+    if (e->nz == 1)
+    {
+        d->planar = 1;
+        for (int64_t k = 0; k < (int64_t)e->nx * e->ny; k++)
+            if (!std::isfinite(e->sdf[k])) d->planar = 0;
+    }
     d->sdf_oob = e->sdf_oob_value; d->occ_oob = e->occupancy_oob_value;
     d->res = e->resolution; d->inv_res = 1.0 / e->resolution;
     d->dnx = (double)e->nx; d->dny = (double)e->ny; d->dnz = (double)e->nz;

@@ -223,6 +223,13 @@ int32_t upc_create(const upc_env_desc* env, int32_t device, upc_handle** out)
     UPC_CUDA_TRY(cudaStreamSynchronize(h->stream));
     DevEnv& e = h->env;
     e.nx = env->nx; e.ny = env->ny; e.nz = env->nz;
+    e.planar = 0;
+    if (env->nz == 1)
+    {
+        e.planar = 1;
+        for (size_t k = 0; k < cells; k++)
+            if (!isfinite(env->sdf[k])) e.planar = 0;
+    }
     e.sdf_oob = env->sdf_oob_value;
     e.occ_oob = env->occupancy_oob_value;
     e.res = env->resolution;

@@ -42,6 +42,7 @@ namespace upc
 struct DevEnv
 {
     int nx, ny, nz;
+    int planar; /* nz == 1 and every SDF value finite: the z interpolations are exact identities and are skipped */
     float sdf_oob, occ_oob;
     double res, inv_res;
     double dnx, dny, dnz; /* grid dimensions as doubles (bounds tests) */
@@ -695,16 +696,28 @@ UPC_D CellRef cell_locate(const DevEnv& env, const double* u)
     return c;
 }
 
+/* Single-layer grids (nz == 1, the 2-D worlds of the SE(2) robot) with finite values: both z corners of every cell are the same
+ * clamped voxel, so the four z interpolations fma(fz, v - v, v) return v exactly and the z derivative is exactly +0 - skipped, bit
+ * for bit the same result (DevEnv::planar is set by the host only when every SDF value is finite: inf - inf would be NaN) */
+#ifndef UPC_PLANAR_SHORTCUT
+#define UPC_PLANAR_SHORTCUT 1
+#endif
+
 UPC_D bool cell_below(const DevEnv& env, const CellRef& c, const Corner4& a, const Corner4& b, double radius, double limit, float clear_above)
 {
     if (!c.inb) return ((double)env.sdf_oob - radius) < limit;
     if (fmin4(a, b) > clear_above) return false;
-    const double v000 = (double)a.x, v001 = (double)a.y, v010 = (double)a.z, v011 = (double)a.w;
-    const double v100 = (double)b.x, v101 = (double)b.y, v110 = (double)b.z, v111 = (double)b.w;
-    const double c00 = upc_fma(c.fz, v001 - v000, v000);
-    const double c01 = upc_fma(c.fz, v011 - v010, v010);
-    const double c10 = upc_fma(c.fz, v101 - v100, v100);
-    const double c11 = upc_fma(c.fz, v111 - v110, v110);
+    const double v000 = (double)a.x, v010 = (double)a.z;
+    const double v100 = (double)b.x, v110 = (double)b.z;
+    double c00 = v000, c01 = v010, c10 = v100, c11 = v110;
+    if (!(UPC_PLANAR_SHORTCUT && env.planar))
+    {
+        const double v001 = (double)a.y, v011 = (double)a.w, v101 = (double)b.y, v111 = (double)b.w;
+        c00 = upc_fma(c.fz, v001 - v000, v000);
+        c01 = upc_fma(c.fz, v011 - v010, v010);
+        c10 = upc_fma(c.fz, v101 - v100, v100);
+        c11 = upc_fma(c.fz, v111 - v110, v110);
+    }
     const double c0 = upc_fma(c.fy, c01 - c00, c00);
     const double c1 = upc_fma(c.fy, c11 - c10, c10);
     const double d = upc_fma(c.fx, c1 - c0, c0);
@@ -731,8 +744,26 @@ UPC_D bool cell_gradient(const DevEnv& env, const CellRef& c, const Corner4& a, 
     }
     if (fmin4(a, b) > clear_above) return false;
     const double fx = c.fx, fy = c.fy, fz = c.fz;
-    const double v000 = (double)a.x, v001 = (double)a.y, v010 = (double)a.z, v011 = (double)a.w;
-    const double v100 = (double)b.x, v101 = (double)b.y, v110 = (double)b.z, v111 = (double)b.w;
+    const double v000 = (double)a.x, v010 = (double)a.z;
+    const double v100 = (double)b.x, v110 = (double)b.z;
+    if (UPC_PLANAR_SHORTCUT && env.planar)
+    {
+        /* z corners equal: c00 = v000 etc. and ddz = 0 exactly; fma(G, 0, x) = x, so the gradient keeps its two in-plane terms */
+        const double dy0 = v010 - v000, dy1 = v110 - v100;
+        const double c0 = upc_fma(fy, dy0, v000);
+        const double c1 = upc_fma(fy, dy1, v100);
+        const double ddx = c1 - c0;
+        *dist = upc_fma(fx, ddx, c0);
+        const double ddy = upc_fma(fx, dy1 - dy0, dy0);
+        const double g0 = ddx * env.inv_res, g1 = ddy * env.inv_res, g2 = 0.0 * env.inv_res;
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+        {
+            grad[j] = upc_fma(env.G[8 + j], g2, upc_fma(env.G[4 + j], g1, env.G[j] * g0));
+        }
+        return true;
+    }
+    const double v001 = (double)a.y, v011 = (double)a.w, v101 = (double)b.y, v111 = (double)b.w;
     const double dz00 = v001 - v000, dz01 = v011 - v010, dz10 = v101 - v100, dz11 = v111 - v110;
     const double c00 = upc_fma(fz, dz00, v000);
     const double c01 = upc_fma(fz, dz01, v010);

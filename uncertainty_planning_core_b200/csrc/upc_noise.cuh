@@ -102,33 +102,51 @@ UPC_NOISE_HD double truncated_normal_from_centered(double t)
     return upc_max(-2.0, upc_min(2.0, z));
 }
 
-struct NoisePair
+struct NoiseQuad
 {
-    double z0, z1;
+    double z[4];
 };
 
-/* the two standard truncated normals of axis pair `pair` (axes 2 pair, 2 pair + 1).  One out-of-line copy per kernel: inlined at
- * every use the generator made the simulation program 30 - 35 % longer, past the instruction cache (profiles/README.md). */
+/*
+ * The standard truncated normals of axis pairs `pair` and `pair + 1` of one (particle, step, slot): z[0], z[1] = axes 2 pair,
+ * 2 pair + 1; z[2], z[3] = axes 2 pair + 2, 2 pair + 3 (zeros when `two_blocks` is false).  The two Philox blocks and the four
+ * quantiles are independent chains evaluated side by side, which is what hides their latency (a warp runs alone on its
+ * scheduler for long stretches of this program).  One out-of-line copy per kernel: inlined at every use the generator made the
+ * simulation program 30 - 35 % longer, past the instruction cache (profiles/README.md).
+ */
+#ifndef UPC_NOISE_QUAD
+#define UPC_NOISE_QUAD 1
+#endif
 #if defined(__CUDACC__)
 inline __host__ __device__ __noinline__
 #else
 inline
 #endif
-NoisePair noise_pair_values(uint64_t seed, uint64_t particle, uint32_t step, uint32_t slot_pair)
+NoiseQuad noise_quad_values(uint64_t seed, uint64_t particle, uint32_t step, uint32_t slot, uint32_t pair, bool two_blocks)
 {
-    uint32_t r[4];
-    philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)particle, (uint32_t)(particle >> 32), step, slot_pair, r);
-    NoisePair out;
-    out.z0 = truncated_normal_from_centered(uniform_centered52(r[0], r[1]));
-    out.z1 = truncated_normal_from_centered(uniform_centered52(r[2], r[3]));
+    uint32_t a[4], b[4] = {0u, 0u, 0u, 0u};
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32), c0 = (uint32_t)particle, c1 = (uint32_t)(particle >> 32);
+    philox4x32_10(k0, k1, c0, c1, step, (slot << 16) | pair, a);
+    if (two_blocks) philox4x32_10(k0, k1, c0, c1, step, (slot << 16) | (pair + 1u), b);
+    NoiseQuad out;
+    out.z[0] = truncated_normal_from_centered(uniform_centered52(a[0], a[1]));
+    out.z[1] = truncated_normal_from_centered(uniform_centered52(a[2], a[3]));
+    out.z[2] = 0.0;
+    out.z[3] = 0.0;
+    if (two_blocks)
+    {
+        out.z[2] = truncated_normal_from_centered(uniform_centered52(b[0], b[1]));
+        out.z[3] = truncated_normal_from_centered(uniform_centered52(b[2], b[3]));
+    }
     return out;
 }
 
+/* one pair (host-side tape generation and tests) */
 UPC_NOISE_HD void noise_pair(uint64_t seed, uint64_t particle, uint32_t step, uint32_t slot, uint32_t pair, double* z0, double* z1)
 {
-    const NoisePair v = noise_pair_values(seed, particle, step, (slot << 16) | pair);
-    *z0 = v.z0;
-    *z1 = v.z1;
+    const NoiseQuad v = noise_quad_values(seed, particle, step, slot, pair, false);
+    *z0 = v.z[0];
+    *z1 = v.z[1];
 }
 
 } /* namespace upc */

@@ -132,6 +132,17 @@ struct Group
 #else
 #define UPC_ESTIMATE_LINKAGE UPC_DNI
 #endif
+/* the resolver's point pass runs the single-precision pre-cull from this many lanes per particle on: 2 for the SE(3) / linked
+ * programs (the one-lane big-batch program lost 3 % carrying it), 1 for the small SE(2) program, whose one-lane form is the planner-batch
+ * workhorse (BASELINE config 5: a third of its time was the exact evaluation of all 64 points per resolver pass) */
+#ifndef UPC_RES_PRECULL_SE2_ONE_LANE
+#define UPC_RES_PRECULL_SE2_ONE_LANE 1
+#endif
+template <class M>
+constexpr int resolver_precull_min_lanes()
+{
+    return (UPC_RES_PRECULL_SE2_ONE_LANE && !M::HAS_FRAMES && M::DOF == 3) ? 1 : UPC_RES_PRECULL_MIN_LANES;
+}
 constexpr int kCheckInFlight = UPC_CHECK_INFLIGHT;
 constexpr int kResolverInFlight = UPC_RES_INFLIGHT;
 
@@ -409,7 +420,7 @@ UPC_RESOLVER_LINKAGE int resolver_correction(const DevEnv& env, const DevRobot& 
             {
                 /* corner-cell table: phases A and B in one pass over the lane's points, kResolverInFlight lookups in flight per trip */
                 bool culled_pass = false;
-                if constexpr (UPC_RES_PRECULL && G >= UPC_RES_PRECULL_MIN_LANES && G <= 8)
+                if constexpr (UPC_RES_PRECULL && G >= resolver_precull_min_lanes<M>() && G <= 8)
                 if ((r.cull_delta > 0.0f) && (end - beg >= 8 * G))
                 {
                     culled_pass = true;
@@ -661,19 +672,31 @@ UPC_PLAIN_UNROLL_PRAGMA
 template <int N>
 UPC_D void seeded_draws(const DevRobot& r, uint64_t seed, uint64_t particle, int step, int slot, double* out)
 {
+    constexpr int kPairs = (N + 1) / 2;
+    constexpr int kStride = UPC_NOISE_QUAD ? 2 : 1; /* pairs per generator call */
 #pragma unroll
-    for (int p = 0; p < (N + 1) / 2; p++)
+    for (int p = 0; p < kPairs; p += kStride)
     {
-        const int d0 = 2 * p, d1 = 2 * p + 1;
-        if (d0 < r.dof)
+        if (2 * p < r.dof)
         {
-            const bool has1 = (d1 < N) && (d1 < r.dof);
-            const double s0 = (slot == 0) ? r.axis[d0].sensor_scale : r.axis[d0].actuator_scale;
-            const double s1 = has1 ? ((slot == 0) ? r.axis[has1 ? d1 : d0].sensor_scale : r.axis[has1 ? d1 : d0].actuator_scale) : 0.0;
-            double z0 = 0.0, z1 = 0.0;
-            if ((s0 != 0.0) || (s1 != 0.0)) noise_pair(seed, particle, (uint32_t)step, (uint32_t)slot, (uint32_t)p, &z0, &z1);
-            out[d0] = (s0 != 0.0) ? (z0 * s0) : 0.0;
-            if (has1) out[has1 ? d1 : d0] = (s1 != 0.0) ? (z1 * s1) : 0.0;
+            double s[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+            {
+                const int d = 2 * p + k;
+                const bool used = (k < 2 * kStride) && (d < N) && (d < r.dof);
+                s[k] = used ? ((slot == 0) ? r.axis[(d < N) ? d : 0].sensor_scale : r.axis[(d < N) ? d : 0].actuator_scale) : 0.0;
+            }
+            const bool first = (s[0] != 0.0) || (s[1] != 0.0), second = (s[2] != 0.0) || (s[3] != 0.0);
+            NoiseQuad v;
+            v.z[0] = 0.0; v.z[1] = 0.0; v.z[2] = 0.0; v.z[3] = 0.0;
+            if (first || second) v = noise_quad_values(seed, particle, (uint32_t)step, (uint32_t)slot, (uint32_t)p, second);
+#pragma unroll
+            for (int k = 0; k < 2 * kStride; k++)
+            {
+                const int d = 2 * p + k;
+                if ((d < N) && (d < r.dof)) out[(d < N) ? d : 0] = (s[k] != 0.0) ? (v.z[k] * s[k]) : 0.0;
+            }
         }
     }
 }
