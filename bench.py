@@ -527,7 +527,7 @@ def run_b200(args):
     h_ncl = torch.empty(hi - lo, dtype=torch.int32).pin_memory()
 
     def e2e_step(k):
-        abi.check(lib.upc_simulate_and_cluster_edges(batch.h, C.byref(params), C.byref(cp), SEED + k, lo * P, hi - lo, P, h_es.data_ptr(), h_et.data_ptr(),
+        abi.check(lib.upc_simulate_and_cluster_edges(batch.h, C.byref(params), C.byref(cp), SEED + k, lo * P, hi - lo, P, hi - lo, h_es.data_ptr(), h_et.data_ptr(),
                                                      h_out.data_ptr(), h_coll.data_ptr(), h_labels.data_ptr(), h_ncl.data_ptr()))
         return int(h_ncl[0])
 

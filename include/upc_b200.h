@@ -242,12 +242,14 @@ int32_t upc_forward_simulate_traced(upc_handle* h, const upc_sim_params* params,
 /*
  * The planner-batch step in ONE call (BASELINE config 5): n_edges candidate edges x particles_per_edge particles simulated with
  * seeded noise (uncertainty_contact_planning.hpp:2039-2071 for every edge) and the outcome of every edge clustered (:1986-2034),
- * outcomes staying in device memory in between.  edge_starts / edge_targets: [C][n_edges]; out_configs [C][n], out_collided [n],
- * out_labels [n] (cluster of the particle within its edge), out_n_clusters [n_edges]; n = n_edges * particles_per_edge,
- * particles edge-major.  Host pointers; synchronises.
+ * outcomes staying in device memory in between.  edge_starts: [C][n_starts] with n_starts == n_edges (every particle of an edge
+ * starts at the edge's start: a fresh node, uncertainty_planner_state.hpp:527-529) or n_starts == n (the parent state's own
+ * particles, uncertainty_contact_planning.hpp:2046-2055, edge-major); edge_targets: [C][n_edges]; out_configs [C][n],
+ * out_collided [n], out_labels [n] (cluster of the particle within its edge), out_n_clusters [n_edges];
+ * n = n_edges * particles_per_edge, particles edge-major.  Host pointers; synchronises.
  */
 int32_t upc_simulate_and_cluster_edges(upc_handle* h, const upc_sim_params* params, const upc_cluster_params* cparams, uint64_t seed,
-                                       int64_t first_particle, int64_t n_edges, int64_t particles_per_edge, const double* edge_starts,
+                                       int64_t first_particle, int64_t n_edges, int64_t particles_per_edge, int64_t n_starts, const double* edge_starts,
                                        const double* edge_targets, double* out_configs, uint8_t* out_collided, int32_t* out_labels,
                                        int32_t* out_n_clusters);
 

@@ -468,8 +468,8 @@ public:
         FlattenToSoa(edge_starts, width, starts);
         FlattenToSoa(edge_targets, width, targets);
         const uint64_t seed = NextSeed(rng[0]);
-        check(upc_simulate_and_cluster_edges(handle_->get(), &params, &clustering.params(), seed, 0, (int64_t)E, (int64_t)P, starts, targets, out, collided, labels,
-                                             n_clusters));
+        check(upc_simulate_and_cluster_edges(handle_->get(), &params, &clustering.params(), seed, 0, (int64_t)E, (int64_t)P, (int64_t)E, starts, targets, out, collided,
+                                             labels, n_clusters));
         AssembleEdgeClusters(edge_starts, P, n, width, allow_contacts, out, collided, labels, n_clusters, n, 0, E, result);
         return result;
     }

@@ -294,7 +294,7 @@ def load_library():
     lib.upc_forward_simulate_seeded_device.argtypes = [vp, C.POINTER(SimParams), u64, i64, i64, i64, vp, i64, vp, vp, vp, vp]
     lib.upc_fill_noise_tape_seeded.argtypes = [u64, C.POINTER(RobotDesc), C.POINTER(SimParams), i64, i64, i64, vp]
     lib.upc_forward_simulate_traced.argtypes = [vp, C.POINTER(SimParams), i64, vp, i64, vp, vp, u64, i64, vp, vp, vp, vp, vp]
-    lib.upc_simulate_and_cluster_edges.argtypes = [vp, C.POINTER(SimParams), C.POINTER(ClusterParams), u64, i64, i64, i64, vp, vp, vp, vp, vp, vp]
+    lib.upc_simulate_and_cluster_edges.argtypes = [vp, C.POINTER(SimParams), C.POINTER(ClusterParams), u64, i64, i64, i64, i64, vp, vp, vp, vp, vp, vp]
     lib.upc_device_scratch.argtypes = [vp, i32, i64, C.POINTER(vp)]
     lib.upc_memcpy_to_device.argtypes = [vp, vp, vp, i64]
     lib.upc_memcpy_to_host.argtypes = [vp, vp, vp, i64]

@@ -601,7 +601,7 @@ int32_t upc_forward_simulate_seeded(upc_handle* h, const upc_sim_params* params,
  * clustered, with the outcomes staying in device memory between the two halves.
  */
 int32_t upc_simulate_and_cluster_edges(upc_handle* h, const upc_sim_params* params, const upc_cluster_params* cparams, uint64_t seed,
-                                       int64_t first_particle, int64_t n_edges, int64_t particles_per_edge, const double* edge_starts,
+                                       int64_t first_particle, int64_t n_edges, int64_t particles_per_edge, int64_t n_starts, const double* edge_starts,
                                        const double* edge_targets, double* out_configs, uint8_t* out_collided, int32_t* out_labels,
                                        int32_t* out_n_clusters)
 {
@@ -618,7 +618,8 @@ int32_t upc_simulate_and_cluster_edges(upc_handle* h, const upc_sim_params* para
     if (!edge_starts || !edge_targets || !out_configs || !out_collided || !out_labels || !out_n_clusters) return fail_arg("null buffer");
     UPC_CUDA_TRY(cudaSetDevice(h->device));
     const int64_t n = n_edges * particles_per_edge;
-    int32_t rc = seeded_from_host(h, params, seed, first_particle, n, n_edges, edge_starts, n_edges, edge_targets);
+    if (n_starts != n_edges && n_starts != n) return fail_arg("starts must hold one configuration per edge or one per particle");
+    int32_t rc = seeded_from_host(h, params, seed, first_particle, n, n_starts, edge_starts, n_edges, edge_targets);
     if (rc != UPC_OK) return rc;
     UPC_CUDA_TRY(h->st_labels.reserve((size_t)n * sizeof(int32_t)));
     UPC_CUDA_TRY(h->st_ncl.reserve((size_t)n_edges * sizeof(int32_t) + 64));

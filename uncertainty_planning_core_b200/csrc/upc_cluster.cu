@@ -1244,15 +1244,22 @@ __global__ void __launch_bounds__(256) exact_roots_kernel(const __grid_constant_
 
 /*
  * The reciprocal-nearest-neighbour rounds of one component inside ONE CTA (components of at most kFusedExactMax members): the same
- * five phases as the kernels above - nearest, mark, row merge, column merge, retire - separated by CTA barriers instead of kernel
+ * phases as the kernels above - nearest, mark, row merge, column merge, retire - separated by CTA barriers instead of kernel
  * boundaries, repeated until a round merges nothing.  Components are independent, so every CTA runs its own number of rounds and
  * the host does not take part (the multi-kernel loop with its device-to-host flag per round remains for bigger components).
+ *
+ * Work per round follows the merges, not the component size: the pairs merged in a round are listed in shared memory, the
+ * column update D[k][a] = max(D[k][a], D[k][b]) visits those pairs only, and a row's nearest neighbour is recomputed only when it
+ * can have changed - the row absorbed another one, or its nearest neighbour took part in a merge.  (For any other row k every
+ * entry D[k][j] either stayed or grew, so the minimum of its keys (distance, min(k, j), max(k, j)) is where it was.)
  */
 constexpr int kFusedExactMax = 4096;
 
 __global__ void __launch_bounds__(1024) exact_rounds_fused_kernel(const __grid_constant__ ExactArgs a, int ncomp)
 {
-    __shared__ int s_merged;
+    __shared__ int s_npairs;
+    __shared__ short2 s_pairs[kFusedExactMax / 2];
+    __shared__ uint8_t s_dirty[kFusedExactMax];
     for (int c = blockIdx.x; c < ncomp; c += gridDim.x)
     {
         const int64_t base = a.comp_off[c];
@@ -1264,12 +1271,15 @@ __global__ void __launch_bounds__(1024) exact_rounds_fused_kernel(const __grid_c
         int32_t* partner = a.partner + base;
         int32_t* into = a.into + base;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-        __syncthreads(); /* exact_matrix_kernel's writes are visible (previous launch); separates components handled by this CTA */
+        __syncthreads(); /* separates the components handled by this CTA */
+        for (int row = threadIdx.x; row < m; row += blockDim.x) s_dirty[row] = 1;
+        __syncthreads();
         while (true)
         {
-            /* nearest active neighbour of every active row: key (distance, min(row, col), max(row, col)) */
+            /* nearest active neighbour of the rows that may have changed: key (distance, min(row, col), max(row, col)) */
             for (int row = warp; row < m; row += warps)
             {
+                if (!s_dirty[row]) continue;
                 if (!active[row])
                 {
                     if (lane == 0) nn[row] = -1;
@@ -1311,29 +1321,31 @@ __global__ void __launch_bounds__(1024) exact_rounds_fused_kernel(const __grid_c
                 }
                 if (lane == 0) nn[row] = bi;
             }
-            if (threadIdx.x == 0) s_merged = 0;
+            if (threadIdx.x == 0) s_npairs = 0;
             __syncthreads();
             /* reciprocal nearest pairs within the threshold: the smaller representative absorbs the larger */
             for (int row = threadIdx.x; row < m; row += blockDim.x)
             {
+                s_dirty[row] = 0;
                 int pr = -1;
                 const int b = nn[row];
                 if (b > row && nn[b] == row && D[(int64_t)row * m + b] <= a.threshold)
                 {
                     pr = b;
-                    s_merged = 1;
+                    const int slot = atomicAdd(&s_npairs, 1);
+                    s_pairs[slot] = make_short2((short)row, (short)b);
                 }
                 partner[row] = pr;
             }
             __syncthreads();
-            if (!s_merged) break;
-            /* Lance-Williams, rows then columns: D[a][k] = max(D[a][k], D[b][k]); D[k][a] = max(D[k][a], D[k][b]) */
-            for (int row = warp; row < m; row += warps)
+            const int npairs = s_npairs;
+            if (npairs == 0) break;
+            /* Lance-Williams, rows: D[a][k] = max(D[a][k], D[b][k]) for every merged pair */
+            for (int p = warp; p < npairs; p += warps)
             {
-                const int b = partner[row];
-                if (b < 0) continue;
-                double* Da = D + (int64_t)row * m;
-                const double* Db = D + (int64_t)b * m;
+                const int ra = s_pairs[p].x, rb = s_pairs[p].y;
+                double* Da = D + (int64_t)ra * m;
+                const double* Db = D + (int64_t)rb * m;
                 for (int k = lane; k < m; k += 32)
                 {
                     const double x = Da[k], y = Db[k];
@@ -1341,29 +1353,31 @@ __global__ void __launch_bounds__(1024) exact_rounds_fused_kernel(const __grid_c
                 }
             }
             __syncthreads();
+            /* columns: D[k][a] = max(D[k][a], D[k][b]) for every active row k; rows whose nearest neighbour merged are marked */
             for (int row = warp; row < m; row += warps)
             {
                 if (!active[row]) continue;
                 double* Dk = D + (int64_t)row * m;
-                for (int col = lane; col < m; col += 32)
+                const int my_nn = nn[row];
+                bool touched = false;
+                for (int p = lane; p < npairs; p += 32)
                 {
-                    const int b = partner[col];
-                    if (b >= 0 && col != row)
+                    const int ca = s_pairs[p].x, cb = s_pairs[p].y;
+                    if (ca != row)
                     {
-                        const double x = Dk[col], y = Dk[b];
-                        Dk[col] = (x < y) ? y : x;
+                        const double x = Dk[ca], y = Dk[cb];
+                        Dk[ca] = (x < y) ? y : x;
                     }
+                    touched |= (my_nn == ca) | (my_nn == cb) | (row == ca);
                 }
+                if (__any_sync(0xffffffffu, touched) && lane == 0) s_dirty[row] = 1;
             }
             __syncthreads();
-            for (int row = threadIdx.x; row < m; row += blockDim.x)
+            for (int p = threadIdx.x; p < npairs; p += blockDim.x)
             {
-                const int b = partner[row];
-                if (b >= 0)
-                {
-                    active[b] = 0;
-                    into[b] = row;
-                }
+                const int rb = s_pairs[p].y;
+                active[rb] = 0;
+                into[rb] = s_pairs[p].x;
             }
             __syncthreads();
         }
@@ -1403,6 +1417,55 @@ __global__ void __launch_bounds__(256) propagate_kernel(const uint32_t* __restri
             comp[p] = rr;
             *changed = 1;
         }
+    }
+}
+
+/* the same propagation for sets of at most kFusedPropagateMax particles, iterated to its fixed point inside one CTA per set (no
+ * host round trip per sweep): the fixed point - every particle labelled with the smallest index of its component - does not depend
+ * on the order in which the labels improve */
+constexpr int64_t kFusedPropagateMax = 8192;
+
+__global__ void __launch_bounds__(1024) propagate_fused_kernel(const uint32_t* __restrict__ adj, int64_t set_size, int wpr,
+                                                               const int32_t* __restrict__ set_bad, int32_t* __restrict__ comp)
+{
+    __shared__ int s_changed;
+    const int64_t set = blockIdx.x;
+    if (!set_bad[set]) return;
+    volatile int32_t* sc = comp + set * set_size;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    while (true)
+    {
+        __syncthreads();
+        if (threadIdx.x == 0) s_changed = 0;
+        __syncthreads();
+        for (int64_t i = warp; i < set_size; i += warps)
+        {
+            const uint32_t* row = adj + (set * set_size + i) * wpr;
+            int32_t best = sc[i];
+            for (int w = lane; w < wpr; w += 32)
+            {
+                uint32_t v = row[w];
+                while (v)
+                {
+                    const int b = __ffs((int)v) - 1;
+                    v &= v - 1u;
+                    best = min(best, sc[w * 32 + b]);
+                }
+            }
+            for (int off = 16; off > 0; off >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, off));
+            if (lane == 0)
+            {
+                int32_t rr = best;
+                while (sc[rr] < rr) rr = sc[rr];
+                if (rr < sc[i])
+                {
+                    sc[i] = rr;
+                    s_changed = 1;
+                }
+            }
+        }
+        __syncthreads();
+        if (!s_changed) break;
     }
 }
 
@@ -1798,7 +1861,13 @@ static int32_t cluster_pass(upc_handle* h, const PassInput& in, int64_t n_sets, 
     iota_in_set_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(comp, total, set_size);
     int* d_flag = (int*)buf<int>(h->cw.misc, 16);
     UPC_NULLCHECK(d_flag);
-    for (int iter = 0; iter < 1 << 20; iter++)
+    if (set_size <= kFusedPropagateMax)
+    {
+        propagate_fused_kernel<<<(unsigned)n_sets, 1024, 0, stream>>>(adj, set_size, wpr, set_bad, comp);
+        h->stats.kernel_launches++;
+        UPC_CUDA_TRY(cudaGetLastError());
+    }
+    for (int iter = 0; set_size > kFusedPropagateMax && iter < 1 << 20; iter++)
     {
         UPC_CUDA_TRY(cudaMemsetAsync(d_flag, 0, sizeof(int), stream));
         propagate_kernel<<<(unsigned)((total * 32 + 255) / 256), 256, 0, stream>>>(adj, total, set_size, wpr, set_bad, comp, d_flag);

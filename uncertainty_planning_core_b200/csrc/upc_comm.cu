@@ -14,6 +14,7 @@
 #include <dlfcn.h>
 #include <string.h>
 #include <mutex>
+#include <thread>
 
 namespace upc
 {
@@ -361,15 +362,29 @@ int32_t upc_sharded_edge_batch_all(int32_t n, upc_comm* const* comms, const upc_
                                    int64_t n_edges, int64_t particles_per_edge, const double* const* d_edge_starts,
                                    const double* const* d_edge_targets, void* const* d_blocks, void* const* streams)
 {
-    if (n < 1 || !comms || !d_edge_starts || !d_edge_targets || !d_blocks) return fail_comm("bad argument");
-    upc_outcome_layout lay;
+    if (n < 1 || n > 64 || !comms || !d_edge_starts || !d_edge_targets || !d_blocks) return fail_comm("bad argument");
+    /* one host thread per rank: the clustering half reads small decision flags back from its device, which would otherwise
+     * serialise the ranks behind one another */
+    upc_outcome_layout lays[64];
+    int32_t codes[64];
+    std::string messages[64];
+    std::vector<std::thread> workers;
     for (int i = 0; i < n; i++)
     {
-        const int32_t rc = sharded_local(comms[i], params, cparams, seed, n_edges, particles_per_edge, d_edge_starts[i], d_edge_targets[i], d_blocks[i],
-                                         streams ? streams[i] : nullptr, &lay);
-        if (rc != UPC_OK) return rc;
+        workers.emplace_back([&, i]() {
+            codes[i] = sharded_local(comms[i], params, cparams, seed, n_edges, particles_per_edge, d_edge_starts[i], d_edge_targets[i], d_blocks[i],
+                                     streams ? streams[i] : nullptr, &lays[i]);
+            if (codes[i] != UPC_OK) messages[i] = upc_last_error(); /* the error text is thread-local */
+        });
     }
-    return all_gather_blocks(n, comms, d_blocks, lay.block_bytes, streams);
+    for (std::thread& w : workers) w.join();
+    for (int i = 0; i < n; i++)
+        if (codes[i] != UPC_OK)
+        {
+            set_error(messages[i]);
+            return codes[i];
+        }
+    return all_gather_blocks(n, comms, d_blocks, lays[0].block_bytes, streams);
 }
 
 } /* extern "C" */

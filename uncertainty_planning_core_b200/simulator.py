@@ -140,18 +140,19 @@ class B200Simulator:
     def SimulateAndClusterEdges(self, edge_starts, edge_targets, particles_per_edge, seed, params, cluster_params, first_particle=0):
         """The planner-batch step in one call (BASELINE config 5): E candidate edges x particles_per_edge particles simulated
         with seeded noise (uncertainty_contact_planning.hpp:2039-2071 per edge), each edge's outcome clustered (:1986-2034).
+        edge_starts: [E, C] (one start per edge) or [E * P, C] (the parent states' own particles, edge-major).
         Returns (configs [E, P, C], collided [E, P], labels [E, P], n_clusters [E])."""
         es = np.asarray(edge_starts, dtype=np.float64).reshape(-1, self.robot.width)
         et = np.asarray(edge_targets, dtype=np.float64).reshape(-1, self.robot.width)
-        if es.shape != et.shape:
-            raise ValueError("one target per start")
-        E, P, W = es.shape[0], int(particles_per_edge), self.robot.width
+        E, P, W = et.shape[0], int(particles_per_edge), self.robot.width
         n = E * P
+        if es.shape[0] not in (E, n):
+            raise ValueError("edge_starts must hold one configuration per edge or one per particle (edge-major)")
         s_soa, t_soa = np.ascontiguousarray(es.T), np.ascontiguousarray(et.T)
         out, coll = np.zeros((W, n)), np.zeros(n, dtype=np.uint8)
         labels, ncl = np.zeros(n, dtype=np.int32), np.zeros(E, dtype=np.int32)
         abi.check(self._lib.upc_simulate_and_cluster_edges(self._h, C.byref(params), C.byref(cluster_params), int(seed), int(first_particle), E, P,
-                                                           s_soa.ctypes.data, t_soa.ctypes.data, out.ctypes.data, coll.ctypes.data,
+                                                           es.shape[0], s_soa.ctypes.data, t_soa.ctypes.data, out.ctypes.data, coll.ctypes.data,
                                                            labels.ctypes.data, ncl.ctypes.data))
         return np.ascontiguousarray(out.T).reshape(E, P, W), coll.astype(bool).reshape(E, P), labels.reshape(E, P), ncl
 
