@@ -20,7 +20,9 @@ _REF = None
 def build(force=False):
     """Compile liboracle.so (and oracle/_ref when the reference tree is present)."""
     so = os.path.join(_HERE, "liboracle.so")
-    if force or not os.path.exists(so):
+    if force:
+        subprocess.check_call(["make", "-B", "-C", _HERE, "liboracle.so"], stdout=sys.stderr)
+    elif not os.path.exists(so) or os.path.exists(os.path.join(_HERE, "upc_oracle.cpp")):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=sys.stderr)
     if os.path.isdir("/root/reference"):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=sys.stderr)
@@ -79,6 +81,14 @@ def load():
     lib.oracle_standard_draws.restype = None
     lib.oracle_fill_noise_tape_counter.argtypes = [C.c_uint64, C.POINTER(abi.RobotDesc), C.POINTER(abi.SimParams), i64, i64, i64, vp]
     lib.oracle_fill_noise_tape_counter.restype = i32
+    rp = C.POINTER(abi.RobotDesc)
+    lib.oracle_rob_sequence.argtypes = [rp, i32, i32, dp, i32, vp, vp, vp, vp, vp, vp]
+    lib.oracle_rob_kinematics.argtypes = [rp, i32, vp, vp, vp]
+    lib.oracle_rob_distances.argtypes = [rp, i32, vp, vp, vp, vp]
+    lib.oracle_rob_average.argtypes = [rp, i32, vp, vp]
+    lib.upc_variance_width.argtypes = [i32, i32]
+    for name in ("oracle_rob_sequence", "oracle_rob_kinematics", "oracle_rob_distances", "oracle_rob_average", "upc_variance_width"):
+        getattr(lib, name).restype = i32
     for name in ("oracle_forward_simulate", "oracle_check_config_collision", "oracle_cluster_particles",
                  "oracle_pair_distances", "oracle_pair_distances_reference_style", "oracle_region_signatures",
                  "oracle_sdf_lookup", "oracle_complete_link"):
@@ -123,6 +133,98 @@ def load_ref_unc():
     lib.ref_actuator_max_velocity_noise.restype = C.c_double
     _REF_UNC = lib
     return lib
+
+
+_REF_ROB = None
+
+
+def load_ref_rob():
+    """The reference's own simple_robot_models.hpp compiled unmodified against the stand-in Eigen / arc_utilities headers of
+    oracle/ref_standins (None when oracle/_ref was never built)."""
+    global _REF_ROB
+    if _REF_ROB is not None:
+        return _REF_ROB
+    so = os.path.join(_HERE, "_ref", "libref_rob.so")
+    if not os.path.exists(so):
+        return None
+    lib = C.CDLL(so)
+    rp, vp, ci, cd = C.POINTER(abi.RobotDesc), C.c_void_p, C.c_int, C.c_double
+    lib.ref_rob_sequence.argtypes = [rp, ci, ci, cd, ci, vp, vp, vp, vp, vp]
+    lib.ref_rob_kinematics.argtypes = [rp, ci, vp, vp, vp]
+    lib.ref_rob_distances.argtypes = [rp, ci, vp, vp, vp, vp, ci]
+    lib.ref_rob_average.argtypes = [rp, ci, vp, vp]
+    _REF_ROB = lib
+    return lib
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def rob_sequence(robot, starts, targets, dt, n_steps, z=None, reference=False):
+    """ResetPosition(start); n_steps x {u = GenerateControlAction(target, dt, draws); ApplyControlInput(u * dt, draws)} for every
+    (start, target) row.  z = standard draws [n_seq][n_steps][2][dof] in standard deviations (None = the noise-free forms).
+    reference=True runs the reference's own robot classes (oracle/_ref/libref_rob.so), else the oracle's.
+    Returns (controls [n_seq][n_steps][dof], configs [n_seq][n_steps][width])."""
+    starts, targets = _f64(starts), _f64(targets)
+    n_seq, width = starts.shape
+    d = robot.desc
+    noisy = z is not None
+    z = _f64(z if noisy else np.zeros((n_seq, n_steps, 2, d.dof)))
+    assert z.shape == (n_seq, n_steps, 2, d.dof)
+    controls = np.zeros((n_seq, n_steps, d.dof))
+    configs = np.zeros((n_seq, n_steps, width))
+    if reference:
+        rc = load_ref_rob().ref_rob_sequence(C.byref(d), n_seq, n_steps, dt, int(noisy), starts.ctypes.data, targets.ctypes.data, z.ctypes.data,
+                                             controls.ctypes.data, configs.ctypes.data)
+        assert rc == 0
+    else:
+        # the tape's draws (DESIGN.md 4): sensor z * max_sensor_noise / 2, actuator z / 2
+        bounds = np.array([d.axis[a].max_sensor_noise for a in range(d.dof)])
+        sensor = _f64(z[:, :, 0, :] * (np.abs(bounds) * 0.5))
+        actuator = _f64(z[:, :, 1, :] * 0.5)
+        _check(load().oracle_rob_sequence(C.byref(d), n_seq, n_steps, dt, int(noisy), starts.ctypes.data, targets.ctypes.data, sensor.ctypes.data,
+                                          actuator.ctypes.data, controls.ctypes.data, configs.ctypes.data))
+    return controls, configs
+
+
+def rob_kinematics(robot, configs, reference=False):
+    """(link transforms [n][links][3][4], translational point Jacobians [n][points][3][dof]) at every configuration"""
+    configs = _f64(configs)
+    d = robot.desc
+    n = configs.shape[0]
+    transforms = np.zeros((n, d.num_links, 3, 4))
+    jac = np.zeros((n, d.num_points, 3, d.dof))
+    if reference:
+        assert load_ref_rob().ref_rob_kinematics(C.byref(d), n, configs.ctypes.data, transforms.ctypes.data, jac.ctypes.data) == 0
+    else:
+        _check(load().oracle_rob_kinematics(C.byref(d), n, configs.ctypes.data, transforms.ctypes.data, jac.ctypes.data))
+    return transforms, jac
+
+
+def rob_distances(robot, a, b, reference=False):
+    """(ComputeConfigurationDistance, ComputePerDimensionConfigurationDistance) of the row pairs of a and b"""
+    a, b = _f64(a), _f64(b)
+    d = robot.desc
+    n = a.shape[0]
+    dim_width = load().upc_variance_width(d.kind, d.dof)
+    dist = np.zeros(n)
+    dims = np.zeros((n, dim_width))
+    if reference:
+        assert load_ref_rob().ref_rob_distances(C.byref(d), n, a.ctypes.data, b.ctypes.data, dist.ctypes.data, dims.ctypes.data, dim_width) == 0
+    else:
+        _check(load().oracle_rob_distances(C.byref(d), n, a.ctypes.data, b.ctypes.data, dist.ctypes.data, dims.ctypes.data))
+    return dist, dims
+
+
+def rob_average(robot, configs, reference=False):
+    configs = _f64(configs)
+    out = np.zeros(configs.shape[1])
+    if reference:
+        assert load_ref_rob().ref_rob_average(C.byref(robot.desc), configs.shape[0], configs.ctypes.data, out.ctypes.data) == 0
+    else:
+        _check(load().oracle_rob_average(C.byref(robot.desc), configs.shape[0], configs.ctypes.data, out.ctypes.data))
+    return out
 
 
 def sensor_values(process_values, draws):

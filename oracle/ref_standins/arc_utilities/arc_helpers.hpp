@@ -1,7 +1,8 @@
 /*
  * Stand-in for arc_utilities/arc_helpers.hpp (UM-ARM-Lab/arc_utilities is not vendored in the reference and not present in
  * this container) with the ONE name the reference's simple_uncertainty_models.hpp uses from it:
- * arc_helpers::TruncatedNormalDistribution (simple_uncertainty_models.hpp:25, :53).  TEST INFRASTRUCTURE ONLY - it exists so
+ * arc_helpers::TruncatedNormalDistribution (simple_uncertainty_models.hpp:25, :53), plus the two small helpers
+ * simple_robot_models.hpp takes from it (UNUSED, RetrieveOrDefault).  TEST INFRASTRUCTURE ONLY - it exists so
  * that the reference header can be compiled UNMODIFIED into oracle/_ref/libref_unc.so and the oracle's sensor / actuator
  * arithmetic (everything the reference does with a draw) can be pinned against it.
  *
@@ -21,6 +22,16 @@
 #include <algorithm>
 #include <map>
 #include <memory>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <iostream>
+#include <vector>
+
+/* arc_helpers.hpp's unused-argument marker (simple_robot_models.hpp:147, 574) */
+#ifndef UNUSED
+#define UNUSED(x) (void)(x)
+#endif
 
 namespace arc_helpers
 {
@@ -35,6 +46,14 @@ struct StandardDrawTape
         return draws[next++];
     }
 };
+
+/* map lookup with a default (simple_robot_models.hpp:1496) */
+template <typename Key, typename Value>
+inline Value RetrieveOrDefault(const std::map<Key, Value>& map, const Key& key, const Value& default_value)
+{
+    const typename std::map<Key, Value>::const_iterator found = map.find(key);
+    return (found != map.end()) ? found->second : default_value;
+}
 
 class TruncatedNormalDistribution
 {

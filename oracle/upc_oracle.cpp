@@ -2101,4 +2101,122 @@ int32_t oracle_complete_link(const double* matrix, int64_t n, double threshold, 
     return UPC_OK;
     ORACLE_CATCH
 }
+
+/* ---- robot-model pieces exposed one call at a time, for tests/test_oracle_rob.py (the reference's simple_robot_models.hpp,
+ * compiled unmodified into oracle/_ref/libref_rob.so, answers the same questions through oracle/ref_rob_shim.cpp) */
+extern "C++" {
+template <typename Robot>
+static void RobSequence(const upc_robot_desc& rd, int32_t n_seq, int32_t n_steps, double dt, int32_t noisy, const double* starts, const double* targets,
+                        const double* sensor_draws, const double* actuator_draws, double* controls, double* configs)
+{
+    const int width = upc_config_width(rd.kind, rd.dof);
+    Robot robot(rd);
+    const double zeros[UPC_MAX_DOF] = {0.0};
+    for (int32_t s = 0; s < n_seq; s++)
+    {
+        robot.ResetPosition(starts + (size_t)s * width);
+        for (int32_t k = 0; k < n_steps; k++)
+        {
+            const size_t at = ((size_t)s * n_steps + k) * rd.dof;
+            double* u = controls + at;
+            robot.GenerateControlAction(targets + (size_t)s * width, dt, noisy ? sensor_draws + at : zeros, u);
+            double input[UPC_MAX_DOF];
+            for (int a = 0; a < rd.dof; a++) input[a] = u[a] * dt;
+            robot.ApplyControlInput(input, noisy ? actuator_draws + at : nullptr);
+            robot.GetPosition(configs + ((size_t)s * n_steps + k) * width);
+        }
+    }
+}
+
+template <typename Robot>
+static void RobKinematics(const upc_robot_desc& rd, int32_t n, const double* configs, double* link_transforms, double* jacobians)
+{
+    const int width = upc_config_width(rd.kind, rd.dof);
+    Robot robot(rd);
+    for (int32_t i = 0; i < n; i++)
+    {
+        robot.UpdatePosition(configs + (size_t)i * width);
+        for (int l = 0; l < rd.num_links; l++)
+        {
+            const Mat34& T = robot.LinkTransform(l);
+            double* out = link_transforms + ((size_t)i * rd.num_links + l) * 12;
+            for (int r = 0; r < 3; r++)
+                for (int c = 0; c < 4; c++) out[4 * r + c] = T.m[r][c];
+            for (int p = rd.link_point_offset[l]; p < rd.link_point_offset[l + 1]; p++)
+            {
+                const double local[3] = {rd.points[4 * p + 0], rd.points[4 * p + 1], rd.points[4 * p + 2]};
+                double world[3];
+                TransformPoint(T, local, world);
+                double J[3][UPC_MAX_DOF];
+                robot.PointJacobian(l, local, world, J);
+                for (int r = 0; r < 3; r++)
+                    for (int a = 0; a < rd.dof; a++) jacobians[(((size_t)i * rd.num_points + p) * 3 + r) * rd.dof + a] = J[r][a];
+            }
+        }
+    }
+}
+
+template <typename Robot>
+static void RobDistances(const upc_robot_desc& rd, int32_t n, const double* a, const double* b, double* dist, double* dim_dist)
+{
+    const int width = upc_config_width(rd.kind, rd.dof);
+    const int dim_width = upc_variance_width(rd.kind, rd.dof);
+    const Robot robot(rd);
+    for (int32_t i = 0; i < n; i++)
+    {
+        dist[i] = robot.ComputeConfigurationDistance(a + (size_t)i * width, b + (size_t)i * width);
+        PerDimensionDistance(rd, a + (size_t)i * width, b + (size_t)i * width, dim_dist + (size_t)i * dim_width);
+    }
+}
+}
+
+#define ROB_DISPATCH(fn, ...)                                         \
+    switch (robot->kind)                                              \
+    {                                                                 \
+        case UPC_ROBOT_SE2: fn<Se2Robot>(*robot, __VA_ARGS__); break; \
+        case UPC_ROBOT_SE3: fn<Se3Robot>(*robot, __VA_ARGS__); break; \
+        default: fn<LinkedRobot>(*robot, __VA_ARGS__); break;         \
+    }
+
+/* n_seq independent edges: ResetPosition(start); n_steps x { u = GenerateControlAction(target, dt, sensor draws); ApplyControlInput(u * dt, actuator draws) };
+ * draws [n_seq][n_steps][dof] each, already scaled as on a tape; noisy = 0 uses the noise-free forms */
+int32_t oracle_rob_sequence(const upc_robot_desc* robot, int32_t n_seq, int32_t n_steps, double dt, int32_t noisy, const double* starts, const double* targets,
+                            const double* sensor_draws, const double* actuator_draws, double* controls, double* configs)
+{
+    ORACLE_TRY
+    ValidateRobot(robot);
+    ROB_DISPATCH(RobSequence, n_seq, n_steps, dt, noisy, starts, targets, sensor_draws, actuator_draws, controls, configs)
+    return UPC_OK;
+    ORACLE_CATCH
+}
+
+int32_t oracle_rob_kinematics(const upc_robot_desc* robot, int32_t n, const double* configs, double* link_transforms, double* jacobians)
+{
+    ORACLE_TRY
+    ValidateRobot(robot);
+    ROB_DISPATCH(RobKinematics, n, configs, link_transforms, jacobians)
+    return UPC_OK;
+    ORACLE_CATCH
+}
+
+int32_t oracle_rob_distances(const upc_robot_desc* robot, int32_t n, const double* a, const double* b, double* dist, double* dim_dist)
+{
+    ORACLE_TRY
+    ValidateRobot(robot);
+    ROB_DISPATCH(RobDistances, n, a, b, dist, dim_dist)
+    return UPC_OK;
+    ORACLE_CATCH
+}
+
+int32_t oracle_rob_average(const upc_robot_desc* robot, int32_t n, const double* configs, double* out)
+{
+    ORACLE_TRY
+    ValidateRobot(robot);
+    const int width = upc_config_width(robot->kind, robot->dof);
+    std::vector<const double*> members;
+    for (int32_t i = 0; i < n; i++) members.push_back(configs + (size_t)i * width);
+    AverageConfigurations(*robot, members, out);
+    return UPC_OK;
+    ORACLE_CATCH
+}
 }
