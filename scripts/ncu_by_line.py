@@ -57,6 +57,7 @@ def main():
     hdr = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
     h = rows[hdr]
     ci, si = h.index("Instructions Executed"), h.index("# Samples")
+    src_i = h.index("Source")
     body = rows[hdr + 1:]
     n = min(len(body), len(lines))
     import glob
@@ -65,6 +66,8 @@ def main():
     root = os.environ.get("UPC_SRC_ROOT") or os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     path_by_name = {os.path.basename(p): p for p in glob.glob(root + "/uncertainty_planning_core_b200/csrc/*") + glob.glob(root + "/include/*")}
     by_fn, by_line = collections.Counter(), collections.Counter()
+    local_fn = collections.Counter()   # executed local-memory loads / stores (LDL / STL) per function
+    tot_local = 0
     s_fn, s_line = collections.Counter(), collections.Counter()
     cache = {}
     tot_i = tot_s = 0
@@ -78,14 +81,20 @@ def main():
         fn = "%s:%s" % (f, function_of(cache, path_by_name, f, l))
         by_fn[fn] += cnt
         s_fn[fn] += smp
+        op = body[k][src_i].strip().split()
+        op = op[1] if op and op[0].startswith("@") and len(op) > 1 else (op[0] if op else "")
+        if op.startswith("LDL") or op.startswith("STL"):
+            local_fn[fn] += cnt
+            tot_local += cnt
         by_line[(f, l)] += cnt
         s_line[(f, l)] += smp
         tot_i += cnt
         tot_s += smp
     print("instructions %d, samples %d, sass rows %d / disasm rows %d" % (tot_i, tot_s, len(body), len(lines)))
-    print("%-55s %8s %8s" % ("function", "instr %", "stall %"))
+    print("local-memory instructions (LDL + STL) %d = %.1f %% of all" % (tot_local, 100.0 * tot_local / max(tot_i, 1)))
+    print("%-55s %8s %8s %9s" % ("function", "instr %", "stall %", "LDL+STL %"))
     for fn, c in by_fn.most_common(top):
-        print("%-55s %7.1f%% %7.1f%%" % (fn, 100.0 * c / max(tot_i, 1), 100.0 * s_fn[fn] / max(tot_s, 1)))
+        print("%-55s %7.1f%% %7.1f%% %8.1f%%" % (fn, 100.0 * c / max(tot_i, 1), 100.0 * s_fn[fn] / max(tot_s, 1), 100.0 * local_fn[fn] / max(tot_local, 1)))
     print("\n%-40s %8s %8s" % ("line", "instr %", "stall %"))
     for (f, l), c in by_line.most_common(top):
         print("%-40s %7.1f%% %7.1f%%" % ("%s:%d" % (f, l), 100.0 * c / max(tot_i, 1), 100.0 * s_line[(f, l)] / max(tot_s, 1)))

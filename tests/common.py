@@ -22,7 +22,8 @@ def build_emulation(force=False):
     deps = [src] + [os.path.join(ROOT, "uncertainty_planning_core_b200", "csrc", f) for f in ("upc_sim.cuh", "upc_device.cuh", "upc_host_prep.h")] + \
            [os.path.join(ROOT, "include", f) for f in ("upc_math.h", "upc_b200.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-mfma",
+        # -DUPC_GROUP_CULL=1: the group-level cull is compiled out of the shipped kernels (measured slower) but stays parity-tested here
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-mfma", "-DUPC_GROUP_CULL=1",
                                "-I" + os.path.join(ROOT, "include"),
                                "-I" + os.path.join(ROOT, "uncertainty_planning_core_b200", "csrc"), src, "-o", so])
     return so
@@ -42,6 +43,9 @@ def emulation():
         lib.emulate_set_corner_cells.argtypes = [C.c_int]
         lib.emulate_set_fp32_cull.argtypes = [C.c_int]
         lib.emulate_set_link_cull.argtypes = [C.c_int]
+        lib.emulate_set_group_cull.argtypes = [C.c_int]
+        lib.emulate_group_cull_check.argtypes = [C.POINTER(abi.EnvDesc), C.POINTER(abi.RobotDesc), i64, vp, C.c_double, vp]
+        lib.emulate_group_cull_check.restype = C.c_int
         lib.emulate_cull_check.argtypes = [C.POINTER(abi.EnvDesc), C.POINTER(abi.RobotDesc), i64, vp, C.c_double, vp]
         lib.emulate_cull_check.restype = C.c_int
         _EMU = lib
@@ -59,13 +63,25 @@ def emulate_cull_check(env, robot, frames, threshold):
     return tuple(int(c) for c in counts)
 
 
-def emulate_forward_simulate(env, robot, params, starts, targets, tape, corner_cells=True, fp32_cull=True, link_cull=True):
+def emulate_group_cull_check(env, robot, frames, threshold):
+    """Group-level cull against the exact program for link poses `frames` [F, 12]:
+    returns (groups_tested, groups_cleared, violations, points_in_cleared_groups); violations must be 0."""
+    frames = np.ascontiguousarray(frames, dtype=np.float64)
+    counts = np.zeros(4, dtype=np.int64)
+    rc = emulation().emulate_group_cull_check(C.byref(env.desc), C.byref(robot.desc), frames.shape[0], frames.ctypes.data, float(threshold), counts.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("group-level cull disabled for this environment / robot")
+    return tuple(int(c) for c in counts)
+
+
+def emulate_forward_simulate(env, robot, params, starts, targets, tape, corner_cells=True, fp32_cull=True, link_cull=True, group_cull=True):
     """The product's per-thread program run on the CPU with one lane per particle.
     corner_cells selects the SDF layout the collision passes read (corner-cell table vs plain grid + cell-minimum cull);
     fp32_cull switches the single-precision pre-cull of the point passes."""
     emulation().emulate_set_corner_cells(1 if corner_cells else 0)
     emulation().emulate_set_fp32_cull(1 if fp32_cull else 0)
     emulation().emulate_set_link_cull(1 if link_cull else 0)
+    emulation().emulate_set_group_cull(1 if group_cull else 0)
     starts = np.asarray(starts, dtype=np.float64)
     targets = np.asarray(targets, dtype=np.float64)
     n = starts.shape[0]

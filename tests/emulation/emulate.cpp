@@ -50,6 +50,7 @@ static void fill_robot(const upc_robot_desc* r, DevRobot* d)
         d->axis[a].sensor_scale = sensor_noise_scale(r->axis[a]); d->axis[a].actuator_scale = actuator_noise_scale(r->axis[a]);
     }
     compute_reach(r, d->reach);
+    compute_link_flat_z(r, d->link_flat_z, d->link_z);
     for (int l = 0; l < r->num_links; l++)
     {
         d->link_radius[l] = 0.0;
@@ -94,9 +95,11 @@ static void run(const DevEnv& env, const DevRobot& rob, const DevSim& sp, int64_
 static int g_use_cells = 1;
 static int g_use_fp32_cull = 1;
 static int g_use_link_cull = 1;
+static int g_use_group_cull = 1;
 extern "C" void emulate_set_corner_cells(int on) { g_use_cells = on; }
 extern "C" void emulate_set_fp32_cull(int on) { g_use_fp32_cull = on; }
 extern "C" void emulate_set_link_cull(int on) { g_use_link_cull = on; }
+extern "C" void emulate_set_group_cull(int on) { g_use_group_cull = on; }
 
 /* link boxes + dilated cell minima, as upc_set_robot prepares them */
 static void fill_link_cull(const upc_env_desc* e, const upc_robot_desc* r, const std::vector<float>& cellmin, DevRobot* rob, std::vector<float>* dil)
@@ -109,6 +112,79 @@ static void fill_link_cull(const upc_env_desc* e, const upc_robot_desc* r, const
         build_dilated_cellmin(cellmin.data(), e->nx, e->ny, e->nz, rob->dil_radius, dil->data());
         rob->dilmin = dil->data();
     }
+}
+
+/* point groups + the cell minima dilated by the largest group, as upc_set_robot prepares them */
+static void fill_group_cull(const upc_env_desc* e, const upc_robot_desc* r, const std::vector<float>& cellmin, DevRobot* rob, std::vector<float>* dil,
+                            std::vector<HostPointGroup>* groups)
+{
+    rob->grp_radius = g_use_group_cull ? compute_point_groups(r, e->resolution, e->grid_from_world, rob->link_chunk_off, groups) : 0;
+    rob->grpmin = nullptr;
+    rob->groups = nullptr;
+    if (rob->grp_radius > 0)
+    {
+        dil->resize(cellmin.size());
+        build_dilated_cellmin(cellmin.data(), e->nx, e->ny, e->nz, rob->grp_radius, dil->data());
+        rob->grpmin = dil->data();
+        rob->groups = reinterpret_cast<const DevPointGroup*>(groups->data());
+    }
+}
+
+/*
+ * Conservativeness of the group-level cull, tested directly: for n_frames link poses every point of a group the dilated lookup
+ * declares clear must be clear for the exact FP64 program at `threshold`.  counts[0] = groups tested, [1] = groups cleared,
+ * [2] = cleared groups holding a point the exact program flags (must be 0), [3] = points in cleared groups.
+ */
+extern "C" int emulate_group_cull_check(const upc_env_desc* e, const upc_robot_desc* r, int64_t n_frames, const double* frames, double threshold, int64_t* counts)
+{
+    DevEnv env; DevRobot rob;
+    fill_env(e, &env); fill_robot(r, &rob);
+    std::vector<float> cellmin((size_t)(e->nx + 1) * (size_t)(e->ny + 1) * (size_t)(e->nz + 1));
+    build_cellmin(e->sdf, e->nx, e->ny, e->nz, cellmin.data());
+    env.cellmin = cellmin.data();
+    const std::vector<double> both = points_with_float_copy(r->points, r->num_points);
+    rob.pts = both.data();
+    std::vector<float> dil;
+    std::vector<HostPointGroup> groups;
+    const int saved = g_use_group_cull;
+    g_use_group_cull = 1;
+    fill_group_cull(e, r, cellmin, &rob, &dil, &groups);
+    g_use_group_cull = saved;
+    for (int k = 0; k < 4; k++) counts[k] = 0;
+    if (rob.grp_radius == 0) return 1;
+    for (int64_t f = 0; f < n_frames; f++)
+    {
+        double V[12];
+        voxel_from_link(env, frames + 12 * f, V);
+        for (int l = 0; l < rob.num_links; l++)
+        {
+            const float clear_above = float_round_up((rob.link_radius[l] + threshold) + UPC_CULL_MARGIN);
+            for (int chunk = rob.link_off[l]; chunk < rob.link_off[l + 1]; chunk += 32)
+            {
+                const int chunk_index = (chunk - rob.link_off[l]) >> 5;
+                const unsigned candidates = group_candidates(env, rob, l, chunk_index, V, clear_above);
+                const DevPointGroup* grp = rob.groups + (int64_t)(rob.link_chunk_off[l] + chunk_index) * 4;
+                for (int q = 0; q < 4 && grp[q].mask != 0u; q++)
+                {
+                    counts[0]++;
+                    if ((candidates & grp[q].mask) != 0u) continue;
+                    counts[1]++;
+                    bool any = false;
+                    for (int j = 0; j < 32; j++)
+                    {
+                        if (!((grp[q].mask >> j) & 1u)) continue;
+                        const int k = chunk + j;
+                        double u[3];
+                        xf_point(V, rob.pts[4 * k + 0], rob.pts[4 * k + 1], rob.pts[4 * k + 2], u);
+                        any |= (sdf_distance(env, u) - rob.pts[4 * k + 3]) < threshold;
+                        counts[3]++;
+                    }
+                    counts[2] += any ? 1 : 0;
+                }
+            }
+        }
+    }
+    return 0;
 }
 
 /*
@@ -136,7 +212,7 @@ extern "C" int emulate_cull_check(const upc_env_desc* e, const upc_robot_desc* r
     }
     for (int k = 0; k < 6; k++) counts[k] = 0;
     if (!(rob.cull_delta > 0.0f)) return 1;
-    const Corner4* ptsf = reinterpret_cast<const Corner4*>(rob.pts + 4 * rob.num_points);
+    const CullPoint* ptsf = reinterpret_cast<const CullPoint*>(rob.pts + 4 * rob.num_points);
     for (int64_t f = 0; f < n_frames; f++)
     {
         double V[12];
@@ -157,7 +233,7 @@ extern "C" int emulate_cull_check(const upc_env_desc* e, const upc_robot_desc* r
                 }
                 counts[5] += any ? 1 : 0;
             }
-            const CullFrame cf = cull_frame(env, V, rob.cull_delta, clear_above);
+            const CullFrame cf = cull_frame(env, rob, l, V, rob.cull_delta, clear_above);
             for (int k = rob.link_off[l]; k < rob.link_off[l + 1]; k++)
             {
                 double u[3];
@@ -209,6 +285,9 @@ static int emulate_impl(const upc_env_desc* e, const upc_robot_desc* r, const up
     env.cellmin = cellmin.data();
     std::vector<float> dil;
     fill_link_cull(e, r, cellmin, &rob, &dil);
+    std::vector<float> group_dil;
+    std::vector<HostPointGroup> groups;
+    fill_group_cull(e, r, cellmin, &rob, &group_dil, &groups);
     std::vector<float> cells;
     if (g_use_cells)
     {

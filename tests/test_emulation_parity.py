@@ -5,22 +5,23 @@ import numpy as np
 import pytest
 
 import cases
-from common import emulate_cull_check, emulate_forward_simulate, max_ulp_diff
+from common import emulate_cull_check, emulate_forward_simulate, emulate_group_cull_check, max_ulp_diff
 from uncertainty_planning_core_b200 import scenarios
 from uncertainty_planning_core_b200 import abi
 
 
-@pytest.mark.parametrize("culls", ["all", "no_fp32", "no_link", "none"])
+@pytest.mark.parametrize("culls", ["all", "no_fp32", "no_link", "no_group", "group_only", "none"])
 @pytest.mark.parametrize("corner_cells", [True, False])
 @pytest.mark.parametrize("name", sorted(cases.GOLDEN_SIM_CASES))
 def test_device_program_matches_oracle(oracle, name, corner_cells, culls):
-    """every combination of the three shortcuts (corner-cell table, single-precision pre-cull, link-level cull) gives the oracle's bits"""
+    """the shortcuts (corner-cell table, single-precision pre-cull, link-level cull, group-level cull) in their combinations give the oracle's bits"""
     sc = cases.GOLDEN_SIM_CASES[name]()
     n = sc["starts"].shape[0]
     tape = abi.fill_noise_tape(sc["seed"], sc["robot"], sc["params"], n)
     ocfg, ocoll, ostats = oracle.forward_simulate(sc["env"], sc["robot"], sc["params"], sc["starts"], sc["targets"], tape)
     ecfg, ecoll, estats = emulate_forward_simulate(sc["env"], sc["robot"], sc["params"], sc["starts"], sc["targets"], tape, corner_cells,
-                                                   fp32_cull=culls in ("all", "no_link"), link_cull=culls in ("all", "no_fp32"))
+                                                   fp32_cull=culls in ("all", "no_link", "no_group"), link_cull=culls in ("all", "no_fp32", "no_group"),
+                                                   group_cull=culls in ("all", "no_fp32", "no_link", "group_only"))
     assert np.array_equal(ocoll, ecoll)
     assert max_ulp_diff(ocfg, ecfg) == 0
     for k in cases.SIM_STAT_KEYS:
@@ -86,3 +87,33 @@ def test_link_level_cull_is_conservative_for_the_arm():
             cleared += links_cleared
             hits += point_hits
     assert cleared > 100 and hits > 0
+
+
+def test_group_level_cull_is_conservative():
+    """a point group the dilated-minimum lookup calls clear holds no body point the exact FP64 test would flag - the
+    SE(3) lattice (128 points: four chunks of four groups), one arm link (16 spheres with radius: four groups of four) and the planar
+    SE(2) lattice, poses all over and beyond the grid and on cell borders, several thresholds"""
+    rng = np.random.default_rng(79)
+    sc = scenarios.c2_se3(seed=21, n=1, shape=(64, 64, 64), resolution=0.0625)
+    arm = cases.linked_contact()
+    link = abi.Robot(abi.ROBOT_SE3, [arm["robot"].points[:16].copy()], [abi.make_axis() for _ in range(6)])
+    extent = 64 * 0.0625
+    cleared_total = tested_total = 0
+    for env, robot in ((sc["env"], sc["robot"]), (arm["env"], link)):
+        for threshold in (0.0, 0.00625, 0.05):
+            for frames in (_random_frames(rng, 400, 0.2, extent - 0.2), _random_frames(rng, 300, -0.3, extent + 0.3),
+                           _random_frames(rng, 300, 0.2, extent - 0.2, snap=0.0625)):
+                tested, cleared, violations, points = emulate_group_cull_check(env, robot, frames, threshold)
+                assert violations == 0
+                assert tested == frames.shape[0] * 4 * (robot.desc.num_points // 32 if robot.desc.num_points >= 32 else 1)
+                cleared_total += cleared
+                tested_total += tested
+    assert 0 < cleared_total < tested_total                                 # both outcomes were exercised
+    s1 = scenarios.c1_se2(seed=11, n=1, shape=(128, 128, 1), resolution=0.08)
+    frames = np.zeros((600, 12))
+    for i in range(600):
+        th = rng.uniform(-np.pi, np.pi)
+        R = np.array([[np.cos(th), -np.sin(th), 0.0], [np.sin(th), np.cos(th), 0.0], [0.0, 0.0, 1.0]])
+        frames[i] = np.concatenate([R, np.array([[rng.uniform(0.2, 10.0)], [rng.uniform(0.2, 10.0)], [0.0]])], axis=1).ravel()
+    tested, cleared, violations, points = emulate_group_cull_check(s1["env"], s1["robot"], frames, 0.0)
+    assert violations == 0 and 0 < cleared < tested and tested == 600 * 8

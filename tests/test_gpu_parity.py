@@ -255,6 +255,41 @@ def test_link_level_cull_changes_nothing(oracle):
                 sim.close()
 
 
+def test_group_level_cull_changes_nothing(oracle):
+    """the group-level cull of the one-lane programs (one dilated-minimum lookup per point group) is a shortcut only -
+    results with it (default) and without it (UPC_B200_NO_GROUP_CULL=1) are the oracle's, for every robot kind, both SDF layouts,
+    with and without the link-level cull in front of it.  (The shipped build compiles the group tests out - measured slower on
+    B200, upc_device.cuh: UPC_GROUP_CULL - so there the switch changes nothing by construction; -DUPC_GROUP_CULL=1 builds are what
+    this test is for, next to the emulation parity suite which always compiles them in.)"""
+    from uncertainty_planning_core_b200 import B200Simulator, scenarios
+    c2 = scenarios.c2_se3(seed=5, n=96, num_steps=48, shape=(64, 64, 64), resolution=0.0625)     # 128 points: four chunks of four groups
+    c2["seed"] = 9
+    for sc in (cases.se2_contact(), cases.se3_contact(), cases.linked_contact(), cases.linked_mixed_joints(), c2):
+        n = sc["starts"].shape[0]
+        tape = abi.fill_noise_tape(sc["seed"], sc["robot"], sc["params"], n)
+        ocfg, ocoll, ostats = oracle.forward_simulate(sc["env"], sc["robot"], sc["params"], sc["starts"], sc["targets"], tape)
+        for off in ("", "GROUP", "LINK"):
+            for plain in (False, True):
+                if off:
+                    os.environ["UPC_B200_NO_%s_CULL" % off] = "1"
+                if plain:
+                    os.environ["UPC_B200_NO_CORNER_CELLS"] = "1"
+                try:
+                    sim = B200Simulator(sc["env"], sc["robot"])
+                finally:
+                    os.environ.pop("UPC_B200_NO_GROUP_CULL", None)
+                    os.environ.pop("UPC_B200_NO_LINK_CULL", None)
+                    os.environ.pop("UPC_B200_NO_CORNER_CELLS", None)
+                sim.SetLanesPerParticle(1)
+                sim.ResetStatistics()
+                cfg, coll = sim.ForwardSimulateRobots(sc["starts"], sc["targets"], tape, sc["params"])
+                assert np.array_equal(coll, ocoll) and max_ulp_diff(cfg, ocfg) <= CONFIG_ULP_TOLERANCE, (sc.get("name"), off, plain)
+                st = sim.GetStatistics()
+                for k in cases.SIM_STAT_KEYS:
+                    assert int(st[k]) == ostats[k], (sc.get("name"), off, plain, k)
+                sim.close()
+
+
 def test_check_config_collision_matches_oracle(oracle, simulators):
     for make in (cases.se2_contact, cases.se3_contact, cases.linked_contact):
         sc = make()

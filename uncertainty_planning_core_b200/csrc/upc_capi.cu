@@ -255,6 +255,8 @@ int32_t upc_destroy(upc_handle* h)
     cudaFree(h->d_occ);
     cudaFree(h->d_cellmin);
     cudaFree(h->d_dilmin);
+    cudaFree(h->d_grpmin);
+    cudaFree(h->d_groups);
     cudaFree(h->d_cells);
     cudaFree(h->d_points);
     cudaFree(h->d_counters);
@@ -358,6 +360,7 @@ int32_t upc_set_robot(upc_handle* h, const upc_robot_desc* r)
             if (!placed[(size_t)l]) return fail_arg("every link except the root needs a parent joint");
     }
     compute_reach(r, d.reach);
+    compute_link_flat_z(r, d.link_flat_z, d.link_z);
     for (int l = 0; l < r->num_links; l++)
     {
         d.link_radius[l] = 0.0;
@@ -395,6 +398,34 @@ int32_t upc_set_robot(upc_handle* h, const upc_robot_desc* r)
             UPC_CUDA_TRY(cudaStreamSynchronize(h->stream));
             h->stats.h2d_bytes += (int64_t)(dil.size() * sizeof(float));
             d.dilmin = h->d_dilmin;
+        }
+    }
+    {
+        /* group-level cull of the one-lane programs: point groups per 32-point chunk and the cell-minimum grid dilated by the largest
+         * group; UPC_B200_NO_GROUP_CULL=1 switches it off (tests exercise both) */
+        const char* off = getenv("UPC_B200_NO_GROUP_CULL");
+        std::vector<HostPointGroup> groups;
+        d.grp_radius = (off && off[0] == '1') ? 0 : compute_point_groups(r, h->env.res, h->env.G, d.link_chunk_off, &groups);
+        if (d.dil_radius > 0 && d.grp_radius >= d.dil_radius) d.grp_radius = 0; /* no finer than the link-level test: nothing to gain */
+        if (h->d_grpmin) cudaFree(h->d_grpmin);
+        if (h->d_groups) cudaFree(h->d_groups);
+        h->d_grpmin = nullptr;
+        h->d_groups = nullptr;
+        d.grpmin = nullptr;
+        d.groups = nullptr;
+        if (d.grp_radius > 0)
+        {
+            static_assert(sizeof(HostPointGroup) == sizeof(DevPointGroup), "group record layout");
+            std::vector<float> dil(h->host_cellmin.size());
+            build_dilated_cellmin(h->host_cellmin.data(), h->env.nx, h->env.ny, h->env.nz, d.grp_radius, dil.data());
+            UPC_CUDA_TRY(cudaMalloc(&h->d_grpmin, dil.size() * sizeof(float)));
+            UPC_CUDA_TRY(cudaMalloc(&h->d_groups, groups.size() * sizeof(HostPointGroup)));
+            UPC_CUDA_TRY(cudaMemcpyAsync(h->d_grpmin, dil.data(), dil.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+            UPC_CUDA_TRY(cudaMemcpyAsync(h->d_groups, groups.data(), groups.size() * sizeof(HostPointGroup), cudaMemcpyHostToDevice, h->stream));
+            UPC_CUDA_TRY(cudaStreamSynchronize(h->stream));
+            h->stats.h2d_bytes += (int64_t)(dil.size() * sizeof(float) + groups.size() * sizeof(HostPointGroup));
+            d.grpmin = h->d_grpmin;
+            d.groups = reinterpret_cast<const DevPointGroup*>(h->d_groups);
         }
     }
     h->robot = d;

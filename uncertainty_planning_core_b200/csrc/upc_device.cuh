@@ -75,6 +75,15 @@ struct DevJoint
     double T[12];
 };
 
+/* bounding box (link frame) and chunk-relative point mask of one point group; layout shared with upc_host_prep.h: HostPointGroup */
+struct DevPointGroup
+{
+    double c[3];
+    double h[3];
+    unsigned mask;
+    unsigned pad;
+};
+
 struct DevRobot
 {
     int kind, dof, num_links, num_joints, num_points;
@@ -82,7 +91,9 @@ struct DevRobot
     int sensor_noise_free; /* every max_sensor_noise is zero: the sensed configuration is the configuration */
     int link_off[UPC_MAX_LINKS + 1];
     int parent_joint_of_link[UPC_MAX_LINKS];
-    const double* pts; /* num_points * 4 doubles: x, y, z, radius; followed by num_points * 4 floats: (float)x, y, z, 0 */
+    const double* pts; /* num_points * 4 doubles: x, y, z, radius; followed by num_points * 8 floats: (float) x, x, y, y, z, z, 0, 0 */
+    int link_flat_z[UPC_MAX_LINKS];   /* 1: every body point of the link has the same single-precision z (planar robots) */
+    float link_z[UPC_MAX_LINKS];      /* that z */
     DevAxis axis[UPC_MAX_DOF];
     double weights[UPC_MAX_DOF];
     double base[12];
@@ -97,6 +108,13 @@ struct DevRobot
     const float* dilmin;
     double link_center[UPC_MAX_LINKS][3];
     double link_half[UPC_MAX_LINKS][3];
+    /* group-level cull of the one-lane programs: every chunk of 32 consecutive points of a link is split into up to
+     * four compact groups (upc_host_prep.h: compute_point_groups); grpmin = cell minima dilated by grp_radius cells, the radius that
+     * covers the largest group; chunk j of link l is record link_chunk_off[l] + j; grp_radius == 0 switches the cull off */
+    int grp_radius;
+    const float* grpmin;
+    const DevPointGroup* groups; /* 4 records per chunk, unused ones have an empty mask */
+    int link_chunk_off[UPC_MAX_LINKS + 1];
     DevJoint joints[UPC_MAX_JOINTS];
 };
 
@@ -488,6 +506,48 @@ UPC_D bool link_certainly_clear(const DevEnv& env, const DevRobot& r, int l, con
     return m > clear_above;
 }
 
+/*
+ * Group-level cull (one-lane programs): the points of chunk `chunk_index` of link l that are NOT proven clear by one dilated
+ * lookup per point group - same test and same proof as link_certainly_clear, with the group's box and the grid dilated by the
+ * largest group's radius.  Bit j = point chunk + j still needs the per-point passes.  All ones when the cull is off.
+ */
+/* compiled out by default: measured on B200 the group tests cost more than they save (C5 25.4 -> 26.3 ms, C3 +-0: when a link is
+ * not clear as a whole, most of its groups are not either at these robot / cell sizes); -DUPC_GROUP_CULL=1 builds it in, and the
+ * host emulation of the test suite always does */
+#ifndef UPC_GROUP_CULL
+#define UPC_GROUP_CULL 0
+#endif
+UPC_D unsigned group_candidates(const DevEnv& env, const DevRobot& r, int l, int chunk_index, const double* V, float clear_above)
+{
+    if (!UPC_GROUP_CULL || r.grp_radius == 0) return 0xffffffffu;
+    const DevPointGroup* grp = r.groups + (int64_t)(r.link_chunk_off[l] + chunk_index) * 4;
+    const double a00 = fabs(V[0]), a01 = fabs(V[1]), a02 = fabs(V[2]);
+    const double a10 = fabs(V[4]), a11 = fabs(V[5]), a12 = fabs(V[6]);
+    const double a20 = fabs(V[8]), a21 = fabs(V[9]), a22 = fabs(V[10]);
+    unsigned candidates = 0u;
+#pragma unroll 1
+    for (int q = 0; q < 4; q++)
+    {
+        const unsigned mask = ldg(&grp[q].mask);
+        if (mask == 0u) break;
+        const double hx = ldg(&grp[q].h[0]), hy = ldg(&grp[q].h[1]), hz = ldg(&grp[q].h[2]);
+        double c[3];
+        xf_point(V, ldg(&grp[q].c[0]), ldg(&grp[q].c[1]), ldg(&grp[q].c[2]), c);
+        const double ex = (a00 * hx + a01 * hy) + (a02 * hz + 1.0e-6);
+        const double ey = (a10 * hx + a11 * hy) + (a12 * hz + 1.0e-6);
+        const double ez = (a20 * hx + a21 * hy) + (a22 * hz + 1.0e-6);
+        const bool inside = (c[0] - ex >= 0.0) & (c[0] + ex < env.dnx) & (c[1] - ey >= 0.0) & (c[1] + ey < env.dny) & (c[2] - ez >= 0.0) & (c[2] + ez < env.dnz);
+        bool clear = false;
+        if (inside)
+        {
+            const int ix = floor_to_int(c[0] - 0.5) + 1, iy = floor_to_int(c[1] - 0.5) + 1, iz = floor_to_int(c[2] - 0.5) + 1;
+            clear = ldg(r.grpmin + ((ix * (env.ny + 1) + iy) * (env.nz + 1) + iz)) > clear_above;
+        }
+        if (!clear) candidates |= mask;
+    }
+    return candidates;
+}
+
 /* smallest float >= v (v finite): a single-precision value may be compared against it instead of against v */
 UPC_D float float_round_up(double v)
 {
@@ -538,40 +598,63 @@ UPC_D float fmin4(const Corner4& a, const Corner4& b)
  * exceeds the rounded-up threshold - the same bound the FP64 corner test uses.  Anything else is "undecided" and
  * goes through the exact FP64 program, so no result ever depends on this code.
  */
+/* a body point as the pre-cull reads it: every coordinate twice, so that one packed multiply-add (FFMA2, sm_100) serves the x and
+ * the y voxel axis */
+struct alignas(16) CullPoint
+{
+    float xx[2], yy[2], zz[2], pad[2];
+};
+
+struct Float2
+{
+    float x, y;
+};
+
+/* two single-precision fused multiply-adds / additions in one instruction on sm_100 (FFMA2 / FADD2: crt/sm_100_rt.h); each half
+ * rounds exactly like the scalar operation, which is what the host build executes */
+UPC_D Float2 fma2(const Float2& a, const Float2& b, const Float2& c)
+{
+    Float2 out;
+#if defined(__CUDA_ARCH__)
+    const float2 v = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(c.x, c.y));
+    out.x = v.x; out.y = v.y;
+#else
+    out.x = __builtin_fmaf(a.x, b.x, c.x);
+    out.y = __builtin_fmaf(a.y, b.y, c.y);
+#endif
+    return out;
+}
+
+UPC_D Float2 add2(const Float2& a, const Float2& b)
+{
+    Float2 out;
+#if defined(__CUDA_ARCH__)
+    const float2 v = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+    out.x = v.x; out.y = v.y;
+#else
+    out.x = a.x + b.x;
+    out.y = a.y + b.y;
+#endif
+    return out;
+}
+
+#ifndef UPC_CULL_PIN_FRAME
+#define UPC_CULL_PIN_FRAME 1
+#endif
+
 struct CullFrame
 {
-    float v[12];        /* voxel_from_link with the cell offset folded into the translation (see cull_frame) */
+    Float2 vxy[3], txy; /* rows x and y of voxel_from_link, column by column, with the cell offset folded into the translation */
+    float vz[3], tz;    /* row z */
     float gx, gy, gz;   /* largest |rounding residue| per axis that still pins the cell */
     int wx, wy, wz;     /* the rounded coordinate must lie in [0, w] */
     float clear_above;
+    int sy, sx;         /* cell-minimum table strides of the x and y index: index = ix * sx + iy * sy + iz + base */
+    int base;
+    /* z handled once per link: every point of the link has the same z and the z row of the transform ignores x and y (planar
+     * robots in axis-aligned grids).  z_index already holds iz; z_fail = the z axis cannot be pinned, nothing can be culled */
+    bool z_uniform, z_fail;
 };
-
-/*
- * Per axis the float coordinate q is arranged so that round-to-nearest(q) identifies the cell:
- *   n >= 2: q = u - 1 = (cell coordinate) - 0.5; cell = round(q) when |q - round(q)| <= 0.5 - delta; only interior
- *           cells 0..n-2 are accepted (border cells need the exact in-bounds test: undecided);
- *   n == 1: q = u - 0.5 = cell coordinate; any in-bounds point has |q| < 0.5 and both candidate cells (-1, 0) hold the
- *           same clamped corners, so cell 0 stands for both: accepted when round(q) = 0 and |q| <= 0.5 - 2 delta.
- * The cell-minimum table is indexed by cell + 1.
- */
-UPC_D CullFrame cull_frame(const DevEnv& env, const double* V, float delta, float clear_above)
-{
-    CullFrame f;
-#pragma unroll
-    for (int k = 0; k < 12; k++) f.v[k] = (float)V[k];
-    f.v[3] = (float)(V[3] - ((env.nx == 1) ? 0.5 : 1.0));
-    f.v[7] = (float)(V[7] - ((env.ny == 1) ? 0.5 : 1.0));
-    f.v[11] = (float)(V[11] - ((env.nz == 1) ? 0.5 : 1.0));
-    const float two = delta + delta;
-    f.gx = 0.5f - ((env.nx == 1) ? two : delta);
-    f.gy = 0.5f - ((env.ny == 1) ? two : delta);
-    f.gz = 0.5f - ((env.nz == 1) ? two : delta);
-    f.wx = (env.nx == 1) ? 0 : env.nx - 2;
-    f.wy = (env.ny == 1) ? 0 : env.ny - 2;
-    f.wz = (env.nz == 1) ? 0 : env.nz - 2;
-    f.clear_above = clear_above;
-    return f;
-}
 
 UPC_D float upc_fmaf(float a, float b, float c)
 {
@@ -602,17 +685,75 @@ UPC_D int cull_round(float q, float* residue)
     return float_bits(t) - 0x4B400000;
 }
 
-/* index into the cell-minimum table of the cell holding the point, or -1 when the float arithmetic cannot pin it */
-UPC_D int cull_locate(const DevEnv& env, const CullFrame& f, const Corner4& p)
+/*
+ * Per axis the float coordinate q is arranged so that round-to-nearest(q) identifies the cell:
+ *   n >= 2: q = u - 1 = (cell coordinate) - 0.5; cell = round(q) when |q - round(q)| <= 0.5 - delta; only interior
+ *           cells 0..n-2 are accepted (border cells need the exact in-bounds test: undecided);
+ *   n == 1: q = u - 0.5 = cell coordinate; any in-bounds point has |q| < 0.5 and both candidate cells (-1, 0) hold the
+ *           same clamped corners, so cell 0 stands for both: accepted when round(q) = 0 and |q| <= 0.5 - 2 delta.
+ * The cell-minimum table is indexed by cell + 1.
+ */
+UPC_D CullFrame cull_frame(const DevEnv& env, const DevRobot& r, int l, const double* V, float delta, float clear_above)
 {
-    const float qx = upc_fmaf(f.v[2], p.z, upc_fmaf(f.v[1], p.y, upc_fmaf(f.v[0], p.x, f.v[3])));
-    const float qy = upc_fmaf(f.v[6], p.z, upc_fmaf(f.v[5], p.y, upc_fmaf(f.v[4], p.x, f.v[7])));
-    const float qz = upc_fmaf(f.v[10], p.z, upc_fmaf(f.v[9], p.y, upc_fmaf(f.v[8], p.x, f.v[11])));
-    float rx, ry, rz;
-    const int ix = cull_round(qx, &rx), iy = cull_round(qy, &ry), iz = cull_round(qz, &rz);
-    const bool ok = (fabsf(rx) <= f.gx) & (fabsf(ry) <= f.gy) & (fabsf(rz) <= f.gz) & ((unsigned)ix <= (unsigned)f.wx) &
-                    ((unsigned)iy <= (unsigned)f.wy) & ((unsigned)iz <= (unsigned)f.wz);
-    const int idx = ((ix + 1) * (env.ny + 1) + (iy + 1)) * (env.nz + 1) + (iz + 1);
+    CullFrame f;
+    f.vxy[0].x = (float)V[0]; f.vxy[1].x = (float)V[1]; f.vxy[2].x = (float)V[2];
+    f.vxy[0].y = (float)V[4]; f.vxy[1].y = (float)V[5]; f.vxy[2].y = (float)V[6];
+    f.vz[0] = (float)V[8]; f.vz[1] = (float)V[9]; f.vz[2] = (float)V[10];
+    f.txy.x = (float)(V[3] - ((env.nx == 1) ? 0.5 : 1.0));
+    f.txy.y = (float)(V[7] - ((env.ny == 1) ? 0.5 : 1.0));
+    f.tz = (float)(V[11] - ((env.nz == 1) ? 0.5 : 1.0));
+    const float two = delta + delta;
+    f.gx = 0.5f - ((env.nx == 1) ? two : delta);
+    f.gy = 0.5f - ((env.ny == 1) ? two : delta);
+    f.gz = 0.5f - ((env.nz == 1) ? two : delta);
+    f.wx = (env.nx == 1) ? 0 : env.nx - 2;
+    f.wy = (env.ny == 1) ? 0 : env.ny - 2;
+    f.wz = (env.nz == 1) ? 0 : env.nz - 2;
+    f.clear_above = clear_above;
+    f.sy = env.nz + 1;
+    f.sx = (env.ny + 1) * (env.nz + 1);
+    f.base = f.sx + f.sy + 1; /* the table is indexed by cell + 1 on every axis */
+    /* the z coordinate of every point of the link is the same number when the points share their z and the row has no x / y part:
+     * fma(0, p, t) = t exactly, so the value below is the value the per-point chain would produce */
+    f.z_uniform = (r.link_flat_z[l] != 0) && (f.vz[0] == 0.0f) && (f.vz[1] == 0.0f);
+    f.z_fail = false;
+    if (f.z_uniform)
+    {
+        const float qz = upc_fmaf(f.vz[2], r.link_z[l], f.tz);
+        float rz;
+        const int iz = cull_round(qz, &rz);
+        f.z_fail = !((fabsf(rz) <= f.gz) & ((unsigned)iz <= (unsigned)f.wz));
+        f.base += iz;
+    }
+#if defined(__CUDA_ARCH__) && UPC_CULL_PIN_FRAME
+    /* keep the frame in registers: left alone ptxas rematerialises these conversions (F2F, constant loads, selects) for every
+     * point of the pass instead of holding ~ 16 values across the loop */
+    asm volatile("" : "+f"(f.vxy[0].x), "+f"(f.vxy[0].y), "+f"(f.vxy[1].x), "+f"(f.vxy[1].y), "+f"(f.vxy[2].x), "+f"(f.vxy[2].y), "+f"(f.txy.x), "+f"(f.txy.y));
+    asm volatile("" : "+f"(f.gx), "+f"(f.gy), "+r"(f.wx), "+r"(f.wy), "+r"(f.sx), "+r"(f.sy), "+r"(f.base), "+f"(f.clear_above));
+    if (!f.z_uniform) asm volatile("" : "+f"(f.vz[0]), "+f"(f.vz[1]), "+f"(f.vz[2]), "+f"(f.tz), "+f"(f.gz), "+r"(f.wz));
+#endif
+    return f;
+}
+
+/* index into the cell-minimum table of the cell holding the point, or -1 when the float arithmetic cannot pin it */
+UPC_D int cull_locate(const CullFrame& f, const CullPoint& p)
+{
+    const Float2 px = {p.xx[0], p.xx[1]}, py = {p.yy[0], p.yy[1]}, pz = {p.zz[0], p.zz[1]};
+    const Float2 q = fma2(f.vxy[2], pz, fma2(f.vxy[1], py, fma2(f.vxy[0], px, f.txy)));
+    const Float2 magic = {12582912.0f, 12582912.0f}, minus_magic = {-12582912.0f, -12582912.0f}, minus_one = {-1.0f, -1.0f};
+    const Float2 t = add2(q, magic);
+    const Float2 res = fma2(add2(t, minus_magic), minus_one, q); /* q - (t - magic): the product with -1 is exact */
+    const int ix = float_bits(t.x) - 0x4B400000, iy = float_bits(t.y) - 0x4B400000;
+    bool ok = (fabsf(res.x) <= f.gx) & (fabsf(res.y) <= f.gy) & ((unsigned)ix <= (unsigned)f.wx) & ((unsigned)iy <= (unsigned)f.wy);
+    int idx = ix * f.sx + iy * f.sy + f.base;
+    if (!f.z_uniform)
+    {
+        const float qz = upc_fmaf(f.vz[2], p.zz[0], upc_fmaf(f.vz[1], p.yy[0], upc_fmaf(f.vz[0], p.xx[0], f.tz)));
+        float rz;
+        const int iz = cull_round(qz, &rz);
+        ok = ok & (fabsf(rz) <= f.gz) & ((unsigned)iz <= (unsigned)f.wz);
+        idx += iz;
+    }
     return ok ? idx : -1;
 }
 
@@ -622,18 +763,27 @@ UPC_D int cull_locate(const DevEnv& env, const CullFrame& f, const Corner4& p)
 #ifndef UPC_CULL_INFLIGHT
 #define UPC_CULL_INFLIGHT 4
 #endif
-UPC_D unsigned cull_undecided(const DevEnv& env, const CullFrame& f, const Corner4* ptsf, int first, int lim, int stride)
+UPC_D unsigned cull_undecided(const DevEnv& env, const CullFrame& f, const CullPoint* ptsf, int first, int lim, int stride, unsigned candidates = 0xffffffffu)
 {
     unsigned undecided = 0u;
+    if (f.z_fail)
+    {
+        /* the link's common z cannot be pinned to a cell layer: every point goes through the exact program */
+        for (int j = 0; j < 32; j++)
+            if (first + j * stride < lim) undecided |= (1u << j);
+        return undecided & candidates;
+    }
+    constexpr unsigned kTrip = (UPC_CULL_INFLIGHT >= 32) ? 0xffffffffu : ((1u << UPC_CULL_INFLIGHT) - 1u);
     for (int j0 = 0; j0 < 32; j0 += UPC_CULL_INFLIGHT)
     {
         if (first + j0 * stride >= lim) break;
+        if (((candidates >> j0) & kTrip) == 0u) continue; /* every point of this trip was cleared by the group-level cull */
         int idx[UPC_CULL_INFLIGHT];
 #pragma unroll
         for (int q = 0; q < UPC_CULL_INFLIGHT; q++)
         {
             const int k = first + (j0 + q) * stride;
-            idx[q] = cull_locate(env, f, ptsf[(k < lim) ? k : first]);
+            idx[q] = cull_locate(f, ptsf[(k < lim) ? k : first]);
         }
         float m[UPC_CULL_INFLIGHT];
 #pragma unroll
@@ -646,13 +796,14 @@ UPC_D unsigned cull_undecided(const DevEnv& env, const CullFrame& f, const Corne
             if ((k < lim) & !clear) undecided |= (1u << (j0 + q));
         }
     }
-    return undecided;
+    return undecided & candidates;
 }
 
 /* single-point form (tests) */
-UPC_D bool cull_certainly_clear(const DevEnv& env, const CullFrame& f, const Corner4& p)
+UPC_D bool cull_certainly_clear(const DevEnv& env, const CullFrame& f, const CullPoint& p)
 {
-    const int idx = cull_locate(env, f, p);
+    if (f.z_fail) return false;
+    const int idx = cull_locate(f, p);
     if (idx < 0) return false;
     return ldg(env.cellmin + idx) > f.clear_above;
 }

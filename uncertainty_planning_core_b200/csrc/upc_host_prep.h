@@ -153,6 +153,113 @@ inline int compute_link_boxes(const upc_robot_desc* r, double res, const double*
     return (int)cells;
 }
 
+/*
+ * Group-level cull: between the link-level test and the per-point passes.  The one-lane programs walk a link's points
+ * in chunks of 32 consecutive points; every chunk is split here into up to four spatially compact groups (two rounds of bisection
+ * along the longest axis of the bounding box, at the median), each with the centre / half extents of its bounding box in the link
+ * frame and the mask of its points inside the chunk.  A second cell-minimum grid, dilated by the radius that covers the LARGEST
+ * GROUP instead of the largest link, lets one lookup at a group's centre clear all of its points - by the inequality of the
+ * link-level cull (compute_link_boxes).  Returns the dilation radius in cells, 0 = off (non-rigid grid transform, window above 32
+ * cells, or no link with more than one group).
+ */
+struct HostPointGroup
+{
+    double c[3];
+    double h[3];
+    unsigned mask;
+    unsigned pad;
+};
+constexpr int kGroupsPerChunk = 4;
+
+inline int compute_point_groups(const upc_robot_desc* r, double res, const double* grid_from_world, int* link_chunk_off, std::vector<HostPointGroup>* groups)
+{
+    groups->clear();
+    for (int l = 0; l <= r->num_links; l++) link_chunk_off[l] = 0;
+    for (int i = 0; i < 3; i++)
+    {
+        const double* row = grid_from_world + 4 * i;
+        const double norm = sqrt(row[0] * row[0] + row[1] * row[1] + row[2] * row[2]);
+        if (!(fabs(norm - 1.0) <= 1.0e-6)) return 0;
+    }
+    double worst = 0.0;
+    bool any_split = false;
+    int chunks = 0;
+    for (int l = 0; l < r->num_links; l++)
+    {
+        link_chunk_off[l] = chunks;
+        const int beg = r->link_point_offset[l], end = r->link_point_offset[l + 1];
+        for (int chunk = beg; chunk < end; chunk += 32)
+        {
+            const int lim = std::min(end, chunk + 32);
+            std::vector<std::vector<int>> parts(1);
+            for (int k = chunk; k < lim; k++) parts[0].push_back(k);
+            for (int round = 0; round < 2; round++)
+            {
+                std::vector<std::vector<int>> next;
+                for (auto& part : parts)
+                {
+                    if (part.size() <= 4)
+                    {
+                        next.push_back(part);
+                        continue;
+                    }
+                    double lo[3], hi[3];
+                    for (int a = 0; a < 3; a++) lo[a] = hi[a] = r->points[4 * part[0] + a];
+                    for (int k : part)
+                        for (int a = 0; a < 3; a++)
+                        {
+                            lo[a] = std::min(lo[a], r->points[4 * k + a]);
+                            hi[a] = std::max(hi[a], r->points[4 * k + a]);
+                        }
+                    int axis = 0;
+                    for (int a = 1; a < 3; a++)
+                        if (hi[a] - lo[a] > hi[axis] - lo[axis]) axis = a;
+                    std::stable_sort(part.begin(), part.end(), [&](int x, int y) { return r->points[4 * x + axis] < r->points[4 * y + axis]; });
+                    const size_t half = part.size() / 2;
+                    next.emplace_back(part.begin(), part.begin() + (long)half);
+                    next.emplace_back(part.begin() + (long)half, part.end());
+                }
+                parts.swap(next);
+            }
+            if (parts.size() > 1) any_split = true;
+            for (int gidx = 0; gidx < kGroupsPerChunk; gidx++)
+            {
+                HostPointGroup g = {};
+                if (gidx < (int)parts.size())
+                {
+                    const std::vector<int>& part = parts[(size_t)gidx];
+                    double lo[3], hi[3];
+                    for (int a = 0; a < 3; a++) lo[a] = hi[a] = r->points[4 * part[0] + a];
+                    for (int k : part)
+                    {
+                        g.mask |= 1u << (k - chunk);
+                        for (int a = 0; a < 3; a++)
+                        {
+                            lo[a] = std::min(lo[a], r->points[4 * k + a]);
+                            hi[a] = std::max(hi[a], r->points[4 * k + a]);
+                        }
+                    }
+                    double diag2 = 0.0;
+                    for (int a = 0; a < 3; a++)
+                    {
+                        g.c[a] = 0.5 * (lo[a] + hi[a]);
+                        g.h[a] = (0.5 * (hi[a] - lo[a])) * (1.0 + 1.0e-12) + 1.0e-12;
+                        diag2 += g.h[a] * g.h[a];
+                    }
+                    worst = std::max(worst, sqrt(diag2));
+                }
+                groups->push_back(g);
+            }
+            chunks++;
+        }
+    }
+    link_chunk_off[r->num_links] = chunks;
+    if (!any_split) return 0;
+    const double cells = ceil(worst / res + 1.5 + 1.0e-3);
+    if (!(cells <= 32.0)) return 0;
+    return (int)cells;
+}
+
 inline void build_dilated_cellmin(const float* cellmin, int nx, int ny, int nz, int radius, float* out)
 {
     /* separable minimum filter over the (nx+1)(ny+1)(nz+1) cell-minimum grid: z, then y, then x */
@@ -189,20 +296,39 @@ inline void build_dilated_cellmin(const float* cellmin, int nx, int ny, int nz, 
         }
 }
 
-/* device layout of the body points: num_points * 4 doubles (x, y, z, radius) followed by num_points * 4 floats (x, y, z, 0) */
+/* device layout of the body points: num_points * 4 doubles (x, y, z, radius) followed by num_points * 8 floats
+ * (x, x, y, y, z, z, 0, 0): every coordinate twice, the operand shape of the packed single-precision pre-cull (upc_device.cuh: CullPoint) */
+constexpr int kPointDoubles = 8; /* doubles of device storage per body point */
 inline std::vector<double> points_with_float_copy(const double* points, int num_points)
 {
-    std::vector<double> out((size_t)num_points * 6, 0.0);
+    std::vector<double> out((size_t)num_points * kPointDoubles, 0.0);
     memcpy(out.data(), points, (size_t)num_points * 4 * sizeof(double));
     float* f = reinterpret_cast<float*>(out.data() + (size_t)num_points * 4);
     for (int k = 0; k < num_points; k++)
     {
-        f[4 * k + 0] = (float)points[4 * k + 0];
-        f[4 * k + 1] = (float)points[4 * k + 1];
-        f[4 * k + 2] = (float)points[4 * k + 2];
-        f[4 * k + 3] = 0.0f;
+        for (int a = 0; a < 3; a++)
+        {
+            f[8 * k + 2 * a + 0] = (float)points[4 * k + a];
+            f[8 * k + 2 * a + 1] = (float)points[4 * k + a];
+        }
+        f[8 * k + 6] = 0.0f;
+        f[8 * k + 7] = 0.0f;
     }
     return out;
+}
+
+/* links whose body points all share one (single-precision) z coordinate - the planar robots: the pre-cull then handles the z axis
+ * once per link instead of once per point (upc_device.cuh: cull_frame) */
+inline void compute_link_flat_z(const upc_robot_desc* r, int* flat, float* z)
+{
+    for (int l = 0; l < r->num_links; l++)
+    {
+        const int beg = r->link_point_offset[l], end = r->link_point_offset[l + 1];
+        flat[l] = (end > beg) ? 1 : 0;
+        z[l] = (end > beg) ? (float)r->points[4 * beg + 2] : 0.0f;
+        for (int k = beg; k < end; k++)
+            if ((float)r->points[4 * k + 2] != z[l]) flat[l] = 0;
+    }
 }
 
 /*

@@ -60,6 +60,8 @@ struct upc_handle
     float* d_occ = nullptr;
     float* d_cellmin = nullptr;
     float* d_dilmin = nullptr;          /* cell minima dilated by the robot's largest link (link-level cull) */
+    float* d_grpmin = nullptr;          /* cell minima dilated by the robot's largest point group (group-level cull) */
+    void* d_groups = nullptr;           /* point-group records (DevPointGroup), four per 32-point chunk */
     std::vector<float> host_cellmin;    /* host copy of the cell-minimum grid, dilated again whenever the robot changes */
     float* d_cells = nullptr;
     double* d_points = nullptr;

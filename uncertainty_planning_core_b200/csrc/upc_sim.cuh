@@ -139,12 +139,24 @@ struct Group
 #define UPC_RES_PRECULL_SE2_ONE_LANE 1
 #endif
 template <class M>
-constexpr int resolver_precull_min_lanes()
+UPC_D constexpr int resolver_precull_min_lanes()
 {
     return (UPC_RES_PRECULL_SE2_ONE_LANE && !M::HAS_FRAMES && M::DOF == 3) ? 1 : UPC_RES_PRECULL_MIN_LANES;
 }
 constexpr int kCheckInFlight = UPC_CHECK_INFLIGHT;
 constexpr int kResolverInFlight = UPC_RES_INFLIGHT;
+
+/* 1: the warps of a CTA enter every controller interval together (one __syncthreads per interval).  Measured on B200
+ * (profiles/README.md): C5 25.4 -> 21.7 ms (20.9 ms with 256-thread CTAs for the one-lane SE(2) program), C2 1.98 -> 1.80 ms,
+ * C3 14.5 -> 13.1 ms; a second barrier per apply / check / resolve action inside the interval: 21.3 ms, not kept. */
+#ifndef UPC_STEP_BARRIER
+#define UPC_STEP_BARRIER 1
+#endif
+/* one-lane programs accumulate a contributing point as soon as it has been evaluated (ascending order either way) instead of
+ * parking its correction vector in a per-thread buffer for the replay phase: no dynamically indexed local array */
+#ifndef UPC_ONE_LANE_IMMEDIATE
+#define UPC_ONE_LANE_IMMEDIATE 1
+#endif
 
 struct LocalCounters
 {
@@ -211,13 +223,16 @@ UPC_D bool check_collision(const DevEnv& env, const DevRobot& r, const M& m, con
             {
                 /* enough points per lane for full batches: single-precision pre-cull against the 4-byte cell minimum
                  * first (UPC_CULL_INFLIGHT lookups in flight), exact FP64 evaluation of the undecided points only */
-                const CullFrame cf = cull_frame(env, V, r.cull_delta, clear_above);
-                const Corner4* ptsf = reinterpret_cast<const Corner4*>(pts + 4 * r.num_points);
+                const CullFrame cf = cull_frame(env, r, l, V, r.cull_delta, clear_above);
+                const CullPoint* ptsf = reinterpret_cast<const CullPoint*>(pts + 4 * r.num_points);
                 for (int chunk = beg; chunk < end; chunk += 32 * G)
                 {
                     const int first = chunk + g.sub;
                     const int lim = (end < chunk + 32 * G) ? end : (chunk + 32 * G);
-                    unsigned undecided = cull_undecided(env, cf, ptsf, first, lim, G);
+                    /* group-level cull (one-lane programs): only the points of groups that are not provably clear go on */
+                    unsigned group_mask = 0xffffffffu;
+                    if constexpr (G == 1) group_mask = group_candidates(env, r, l, (chunk - beg) >> 5, V, clear_above);
+                    unsigned undecided = cull_undecided(env, cf, ptsf, first, lim, G, group_mask);
                     while (undecided)
                     {
                         int kk[kCheckInFlight];
@@ -294,11 +309,13 @@ UPC_D bool check_collision(const DevEnv& env, const DevRobot& r, const M& m, con
             const int first = chunk + g.sub;
             const int lim = (end < chunk + 32 * G) ? end : (chunk + 32 * G);
             unsigned undecided = 0u;
+            unsigned group_mask = 0xffffffffu;
+            if constexpr (G == 1) group_mask = group_candidates(env, r, l, (chunk - beg) >> 5, V, clear_above);
 UPC_PLAIN_UNROLL_PRAGMA
             for (int j = 0; j < 32; j++)
             {
                 const int k = first + j * G;
-                if (k < lim)
+                if ((k < lim) && ((group_mask >> j) & 1u))
                 {
                     double u[3];
                     xf_point(V, pts[4 * k + 0], pts[4 * k + 1], pts[4 * k + 2], u);
@@ -410,12 +427,62 @@ UPC_RESOLVER_LINKAGE int resolver_correction(const DevEnv& env, const DevRobot& 
         const float clear_above = float_round_up((r.link_radius[l] + resolve_distance) + UPC_CULL_MARGIN);
         /* link-level cull: a link farther than resolve_distance from every obstacle contributes nothing */
         if (link_certainly_clear(env, r, l, V, clear_above)) continue;
+        /* accumulate the contribution (b0, b1, b2) of body point kk of this link; called in ascending point order */
+        auto accumulate = [&](int kk, double b0, double b1, double b2)
+        {
+            const double local[3] = {pts[4 * kk + 0], pts[4 * kk + 1], pts[4 * kk + 2]};
+            double world[3];
+            xf_point(T, local[0], local[1], local[2], world);
+            double J[3][N];
+            m.jacobian(r, l, local, world, J);
+            count++;
+            if (INDIVIDUAL)
+            {
+                double A[3][3];
+#pragma unroll
+                for (int rr = 0; rr < 3; rr++)
+#pragma unroll
+                    for (int qq = 0; qq < 3; qq++)
+                    {
+                        double s = 0.0;
+#pragma unroll
+                        for (int a = 0; a < N; a++)
+                            if (a < n) s = upc_fma(J[rr][a], J[qq][a], s);
+                        A[rr][qq] = s;
+                    }
+                const double cv[3] = {b0, b1, b2};
+                double yv[3];
+                solve_damped<3>(A, cv, sp.damping, yv, 3);
+#pragma unroll
+                for (int a = 0; a < N; a++)
+                    if (a < n) xs[a] = upc_fma(J[2][a], yv[2], upc_fma(J[1][a], yv[1], upc_fma(J[0][a], yv[0], xs[a])));
+            }
+            else
+            {
+#pragma unroll
+                for (int a = 0; a < N; a++)
+                {
+                    if (a < n)
+                    {
+#pragma unroll
+                        for (int b = 0; b < N; b++)
+                        {
+                            if (b >= a && b < n)
+                                H[a][b] = upc_fma(J[2][a], J[2][b], upc_fma(J[1][a], J[1][b], upc_fma(J[0][a], J[0][b], H[a][b])));
+                        }
+                        gv[a] = upc_fma(J[2][a], b2, upc_fma(J[1][a], b1, upc_fma(J[0][a], b0, gv[a])));
+                    }
+                }
+            }
+        };
         for (int chunk = beg; chunk < end; chunk += 32 * G)
         {
             const int first = chunk + g.sub;
             const int lim = (end < chunk + 32 * G) ? end : (chunk + 32 * G);
             unsigned contributing = 0u;
             unsigned undecided = 0u;
+            unsigned group_mask = 0xffffffffu;
+            if constexpr (G == 1) group_mask = group_candidates(env, r, l, (chunk - beg) >> 5, V, clear_above);
             if (env.cells != nullptr)
             {
                 /* corner-cell table: phases A and B in one pass over the lane's points, kResolverInFlight lookups in flight per trip */
@@ -430,9 +497,9 @@ UPC_RESOLVER_LINKAGE int resolver_correction(const DevEnv& env, const DevRobot& 
                      * candidates instead of one per point slot (some lane of the warp is near a surface at almost every slot).
                      * Compiled for 2..8 lanes only: measured C2 (4 lanes) 2.11 -> 2.03 ms, but the one-lane big-batch program
                      * (-3 %) and the 32-lane SE(2) program (+5 % on C1, where the pass never runs) lose by carrying it. */
-                    const CullFrame cf = cull_frame(env, V, r.cull_delta, clear_above);
-                    const Corner4* ptsf = reinterpret_cast<const Corner4*>(pts + 4 * r.num_points);
-                    unsigned candidates = cull_undecided(env, cf, ptsf, first, lim, G);
+                    const CullFrame cf = cull_frame(env, r, l, V, r.cull_delta, clear_above);
+                    const CullPoint* ptsf = reinterpret_cast<const CullPoint*>(pts + 4 * r.num_points);
+                    unsigned candidates = cull_undecided(env, cf, ptsf, first, lim, G, group_mask);
                     while (candidates)
                     {
                         const int j = lowest_bit(candidates);
@@ -453,10 +520,17 @@ UPC_RESOLVER_LINKAGE int resolver_correction(const DevEnv& env, const DevRobot& 
                                 if (gn2 > 1.0e-24)
                                 {
                                     const double scale = (resolve_distance - de) / sqrt(gn2);
-                                    cbuf[j][0] = grad[0] * scale;
-                                    cbuf[j][1] = grad[1] * scale;
-                                    cbuf[j][2] = grad[2] * scale;
-                                    contributing |= (1u << j);
+                                    if constexpr (G == 1 && UPC_ONE_LANE_IMMEDIATE)
+                                    {
+                                        accumulate(k, grad[0] * scale, grad[1] * scale, grad[2] * scale);
+                                    }
+                                    else
+                                    {
+                                        cbuf[j][0] = grad[0] * scale;
+                                        cbuf[j][1] = grad[1] * scale;
+                                        cbuf[j][2] = grad[2] * scale;
+                                        contributing |= (1u << j);
+                                    }
                                 }
                             }
                         }
@@ -465,6 +539,7 @@ UPC_RESOLVER_LINKAGE int resolver_correction(const DevEnv& env, const DevRobot& 
                 if (!culled_pass)
                 for (int j0 = 0; j0 < 32 && (first + j0 * G) < lim; j0 += kResolverInFlight)
                 {
+                    if (((group_mask >> j0) & ((1u << kResolverInFlight) - 1u)) == 0u) continue; /* cleared by the group-level cull */
                     CellRef c[kResolverInFlight];
                     Corner4 ca[kResolverInFlight], cb[kResolverInFlight];
 #pragma unroll
@@ -487,7 +562,7 @@ UPC_RESOLVER_LINKAGE int resolver_correction(const DevEnv& env, const DevRobot& 
                     {
                         const int j = j0 + jj;
                         const int k = first + j * G;
-                        if (k < lim)
+                        if ((k < lim) && ((group_mask >> j) & 1u))
                         {
                             double grad[3], dist;
                             if (cell_gradient(env, c[jj], ca[jj], cb[jj], pts[4 * k + 3], resolve_distance, clear_above, &dist, grad))
@@ -499,10 +574,17 @@ UPC_RESOLVER_LINKAGE int resolver_correction(const DevEnv& env, const DevRobot& 
                                     if (gn2 > 1.0e-24)
                                     {
                                         const double scale = (resolve_distance - de) / sqrt(gn2);
-                                        cbuf[j][0] = grad[0] * scale;
-                                        cbuf[j][1] = grad[1] * scale;
-                                        cbuf[j][2] = grad[2] * scale;
-                                        contributing |= (1u << j);
+                                        if constexpr (G == 1 && UPC_ONE_LANE_IMMEDIATE)
+                                        {
+                                            accumulate(k, grad[0] * scale, grad[1] * scale, grad[2] * scale);
+                                        }
+                                        else
+                                        {
+                                            cbuf[j][0] = grad[0] * scale;
+                                            cbuf[j][1] = grad[1] * scale;
+                                            cbuf[j][2] = grad[2] * scale;
+                                            contributing |= (1u << j);
+                                        }
                                     }
                                 }
                             }
@@ -517,7 +599,7 @@ UPC_PLAIN_UNROLL_PRAGMA
                 for (int j = 0; j < 32; j++)
                 {
                     const int k = first + j * G;
-                    if (k < lim)
+                    if ((k < lim) && ((group_mask >> j) & 1u))
                     {
                         double u[3];
                         xf_point(V, pts[4 * k + 0], pts[4 * k + 1], pts[4 * k + 2], u);
@@ -545,10 +627,17 @@ UPC_PLAIN_UNROLL_PRAGMA
                     if (gn2 > 1.0e-24)
                     {
                         const double scale = (resolve_distance - de) / sqrt(gn2);
-                        cbuf[j][0] = grad[0] * scale;
-                        cbuf[j][1] = grad[1] * scale;
-                        cbuf[j][2] = grad[2] * scale;
-                        contributing |= (1u << j);
+                        if constexpr (G == 1 && UPC_ONE_LANE_IMMEDIATE)
+                        {
+                            accumulate(k, grad[0] * scale, grad[1] * scale, grad[2] * scale);
+                        }
+                        else
+                        {
+                            cbuf[j][0] = grad[0] * scale;
+                            cbuf[j][1] = grad[1] * scale;
+                            cbuf[j][2] = grad[2] * scale;
+                            contributing |= (1u << j);
+                        }
                     }
                 }
             }
@@ -591,50 +680,7 @@ UPC_PLAIN_UNROLL_PRAGMA
                     todo &= todo - 1u;
                     const double b0 = g.bcast(c0, src), b1 = g.bcast(c1, src), b2 = g.bcast(c2, src);
                     const int kk = chunk + src + j * G;
-                    const double local[3] = {pts[4 * kk + 0], pts[4 * kk + 1], pts[4 * kk + 2]};
-                    double world[3];
-                    xf_point(T, local[0], local[1], local[2], world);
-                    double J[3][N];
-                    m.jacobian(r, l, local, world, J);
-                    count++;
-                    if (INDIVIDUAL)
-                    {
-                        double A[3][3];
-#pragma unroll
-                        for (int rr = 0; rr < 3; rr++)
-#pragma unroll
-                            for (int qq = 0; qq < 3; qq++)
-                            {
-                                double s = 0.0;
-#pragma unroll
-                                for (int a = 0; a < N; a++)
-                                    if (a < n) s = upc_fma(J[rr][a], J[qq][a], s);
-                                A[rr][qq] = s;
-                            }
-                        const double cv[3] = {b0, b1, b2};
-                        double yv[3];
-                        solve_damped<3>(A, cv, sp.damping, yv, 3);
-#pragma unroll
-                        for (int a = 0; a < N; a++)
-                            if (a < n) xs[a] = upc_fma(J[2][a], yv[2], upc_fma(J[1][a], yv[1], upc_fma(J[0][a], yv[0], xs[a])));
-                    }
-                    else
-                    {
-#pragma unroll
-                        for (int a = 0; a < N; a++)
-                        {
-                            if (a < n)
-                            {
-#pragma unroll
-                                for (int b = 0; b < N; b++)
-                                {
-                                    if (b >= a && b < n)
-                                        H[a][b] = upc_fma(J[2][a], J[2][b], upc_fma(J[1][a], J[1][b], upc_fma(J[0][a], J[0][b], H[a][b])));
-                                }
-                                gv[a] = upc_fma(J[2][a], b2, upc_fma(J[1][a], b1, upc_fma(J[0][a], b0, gv[a])));
-                            }
-                        }
-                    }
+                    accumulate(kk, b0, b1, b2);
                 }
             }
             UPC_T1(9)
@@ -719,8 +765,11 @@ template <class M, int G, bool SEEDED>
 UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim& sp, const Group<G>& g, int64_t i, int64_t n,
                              const double* starts, int64_t n_targets, const double* targets, const double* tape,
                              double* out_configs, uint8_t* out_collided, const double* pts, double* frames0,
-                             double* frames1, double* park, LocalCounters& cnt, bool& collided_out)
+                             double* frames1, double* park, LocalCounters& cnt, bool& collided_out, const bool exists = true)
 {
+    /* exists == false: a lane without a particle (tail of the batch, lanes a group size leaves over).  It runs the same control flow
+     * on particle i (a valid index) with `finished` set from the start and writes nothing to global memory, so that every thread of
+     * a CTA executes the SAME per-interval barrier instruction - an aligned barrier must not be reached divergently inside a warp. */
     constexpr int N = M::DOF;
     const int dof = r.dof;
     const int width = (M::HAS_FRAMES) ? dof : M::WIDTH;
@@ -735,7 +784,7 @@ UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim&
     else m.load(r, starts, sp.n_starts, (sp.per_start == 1) ? i : ((sp.per_start == n) ? 0 : (i / sp.per_start)));
     m.reset_controllers();
     bool collided = false;
-    bool finished = false;
+    bool finished = !exists;
     if (resumed)
     {
         for (int d = 0; d < dof; d++)
@@ -744,7 +793,7 @@ UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim&
             m.pid_e[d] = sp.carry_pid[(int64_t)(dof + d) * n + i];
         }
         collided = sp.carry_flags[i] != 0;
-        finished = sp.carry_flags[n + i] != 0;
+        finished = (sp.carry_flags[n + i] != 0) || !exists;
     }
     refresh_frames(r, m, g);
     {
@@ -756,9 +805,22 @@ UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim&
         g.sync();
     }
     const int slots = 1 + sp.max_microsteps;
+#if UPC_STEP_BARRIER && defined(__CUDA_ARCH__)
+    /* the warps of a CTA enter every controller interval together, so that they run through the same stretch of the program at
+     * about the same time and share its instruction-cache lines: without the barrier the SM instruction cache hits 78 % and its
+     * refills keep the GPC instruction cache at 95 % of its request rate (profiles/r02g_sim_c5_metrics.txt) - the per-particle
+     * program is 140 KB of SASS against 32 KB of SM instruction cache.  Every thread of the CTA passes the barrier once per
+     * interval, finished particles included. */
+    for (int step = sp.step_begin; step < sp.step_end; step++)
+    {
+        __syncthreads();
+        if (finished) continue;
+        cnt.particle_steps++;
+#else
     for (int step = sp.step_begin; step < sp.step_end && !finished; step++)
     {
         cnt.particle_steps++;
+#endif
         UPC_T0
         double vec[N];   /* the input about to be estimated / applied: control step, then resolver corrections */
         double ustep[N]; /* control input per microstep */
@@ -806,7 +868,8 @@ UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim&
             {
                 /* a static upper bound decides the common case (motion <= microstep_distance => one microstep, no
                  * down-scaling) without touching the body points; otherwise the exact estimate runs */
-                const bool small = (m.motion_bound(r, vec) * 1.000001) <= sp.microstep_distance;
+                /* with a single microstep slot the clamp below yields one microstep whatever the estimate says (BASELINE configs: M = 1) */
+                const bool small = (!resolving && sp.max_microsteps == 1) || ((m.motion_bound(r, vec) * 1.000001) <= sp.microstep_distance);
                 double est = 0.0;
                 if (!small) est = estimate_motion(r, m, g, pts, vec, frames1);
                 if (!resolving)
@@ -939,7 +1002,7 @@ UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim&
         }
     }
     const bool last_launch = sp.step_end >= sp.num_steps;
-    if (g.sub == 0)
+    if (g.sub == 0 && exists)
     {
         m.store(r, out_configs, n, i);
         out_collided[i] = collided ? 1 : 0;

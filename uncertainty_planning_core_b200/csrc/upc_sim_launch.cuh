@@ -17,6 +17,7 @@
 #include <cstring>
 #include "upc_sim_args.h"
 #include "upc_sim.cuh"
+#include "upc_host_prep.h" /* kPointDoubles */
 
 namespace upc
 {
@@ -27,7 +28,7 @@ namespace upc
 #define UPC_SIM_MIN_BLOCKS_ONE_LANE 2
 #endif
 #ifndef UPC_SIM_MIN_BLOCKS_SE2_ONE_LANE
-#define UPC_SIM_MIN_BLOCKS_SE2_ONE_LANE 4
+#define UPC_SIM_MIN_BLOCKS_SE2_ONE_LANE 2
 #endif
 
 /* per-thread link-frame storage (two sets) of robots whose frames do not live in shared memory */
@@ -48,18 +49,32 @@ template <class M, int G>
 constexpr int sim_min_blocks()
 {
     if (G == 1 && M::HAS_FRAMES && M::DOF > 8) return UPC_SIM_MIN_BLOCKS_ONE_LANE;
-    if (G == 1 && !M::HAS_FRAMES && M::DOF == 3) return UPC_SIM_MIN_BLOCKS_SE2_ONE_LANE; /* small program: 128 registers, four CTAs (C5 +3 %) */
+    if (G == 1 && !M::HAS_FRAMES && M::DOF == 3) return UPC_SIM_MIN_BLOCKS_SE2_ONE_LANE; /* small program: 128 registers, 16 warps per SM (C5 +3 % against 168 / 12) */
     if (G == 1 && M::HAS_FRAMES) return UPC_SIM_MIN_BLOCKS_SMALL_LINKED; /* 3.9 KB of stack per thread (C3 28.5 -> 25.9 ms with three) */
     return UPC_SIM_MIN_BLOCKS;
 }
 
-template <class M, int G, bool SEEDED>
-__global__ void __launch_bounds__(kBlock, sim_min_blocks<M, G>()) forward_simulate_kernel(const __grid_constant__ SimArgs a)
+/* threads per CTA: 128, except the one-lane SE(2) program (the planner-batch workhorse): 256 threads x 2 CTAs per SM - the same 16
+ * warps and 128 registers as 128 x 4, but with the per-interval barrier (UPC_STEP_BARRIER) eight warps instead of four run through
+ * the same stretch of the program together: C5 21.7 -> 20.9 ms (512 x 1: 23.8 ms) */
+#ifndef UPC_SIM_BLOCK_SE2_ONE_LANE
+#define UPC_SIM_BLOCK_SE2_ONE_LANE 256
+#endif
+template <class M, int G>
+__host__ __device__ constexpr int sim_block()
 {
+    if (G == 1 && !M::HAS_FRAMES && M::DOF == 3) return UPC_SIM_BLOCK_SE2_ONE_LANE;
+    return UPC_SIM_BLOCK;
+}
+
+template <class M, int G, bool SEEDED>
+__global__ void __launch_bounds__((sim_block<M, G>()), (sim_min_blocks<M, G>())) forward_simulate_kernel(const __grid_constant__ SimArgs a)
+{
+    constexpr int kBlock = sim_block<M, G>();
     extern __shared__ double smem[];
     __shared__ unsigned int s_cnt[4];
     double* pts = smem;
-    const int npd = a.robot.num_points * 6; /* 4 doubles + 4 floats per point */
+    const int npd = a.robot.num_points * kPointDoubles; /* 4 doubles + 8 floats per point */
     for (int k = threadIdx.x; k < npd; k += kBlock) pts[k] = a.robot.pts[k];
     if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0u;
     __syncthreads();
@@ -71,15 +86,20 @@ __global__ void __launch_bounds__(kBlock, sim_min_blocks<M, G>()) forward_simula
     const int lane = (int)(threadIdx.x & 31);
     const int group_in_warp = lane / G;
     const bool lane_used = group_in_warp < kGroupsPerWarp;
-    const int particle_in_block = (int)(threadIdx.x >> 5) * kGroupsPerWarp + group_in_warp;
-    const int64_t i = lane_used ? ((int64_t)blockIdx.x * kParticlesPerBlock + particle_in_block) : a.n;
+    const int particle_slot = (int)(threadIdx.x >> 5) * kGroupsPerWarp + group_in_warp;
+    const int64_t i_raw = (int64_t)blockIdx.x * kParticlesPerBlock + particle_slot;
+    /* lanes without a particle (tail of the batch, lanes the group size leaves over) walk the program on particle 0 with nothing to
+     * do, so that every thread of the CTA meets the same per-interval barrier (simulate_particle: exists); their scratch is the
+     * spare slot behind the CTA's particles */
+    const bool exists = lane_used && (i_raw < a.n);
+    const int64_t i = exists ? i_raw : 0;
+    const int particle_in_block = exists ? particle_slot : kParticlesPerBlock;
     LocalCounters lc = {};
     bool collided = false;
     Group<G> g;
     g.sub = lane % G;
     g.base = lane - g.sub;
     g.mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << g.base);
-    if (i < a.n)
     {
         double* frames0 = nullptr;
         double* frames1 = nullptr;
@@ -101,8 +121,8 @@ __global__ void __launch_bounds__(kBlock, sim_min_blocks<M, G>()) forward_simula
             frames1 = local_frames + frame_buffer_doubles<M, kFramesInShared>() / 2;
         }
         simulate_particle<M, G, SEEDED>(a.env, a.robot, a.sp, g, i, a.n, a.starts, a.n_targets, a.targets, a.tape, a.out_configs,
-                                a.out_collided, pts, frames0, frames1, park, lc, collided);
-        if (g.sub == 0)
+                                a.out_collided, pts, frames0, frames1, park, lc, collided, exists);
+        if (g.sub == 0 && exists)
         {
             atomicAdd(&s_cnt[0], lc.particle_steps);
             atomicAdd(&s_cnt[1], collided ? 1u : 0u);
@@ -126,10 +146,11 @@ __global__ void __launch_bounds__(kBlock, sim_min_blocks<M, G>()) forward_simula
 template <class M, int G, bool SEEDED>
 static cudaError_t launch_sim_impl(const SimArgs& a, cudaStream_t stream)
 {
+    constexpr int kBlock = sim_block<M, G>();
     constexpr int particles_per_block = (kBlock / 32) * (32 / G);
     const int64_t blocks = (a.n + particles_per_block - 1) / particles_per_block;
-    size_t smem = (size_t)a.robot.num_points * 6 * sizeof(double);
-    smem += (size_t)particles_per_block * (2 * M::WIDTH + 2 * M::DOF + ((M::HAS_FRAMES && G >= 4) ? 2 * (size_t)a.robot.num_links * 12 : 0)) * sizeof(double);
+    size_t smem = (size_t)a.robot.num_points * kPointDoubles * sizeof(double);
+    smem += (size_t)(particles_per_block + 1) * (2 * M::WIDTH + 2 * M::DOF + ((M::HAS_FRAMES && G >= 4) ? 2 * (size_t)a.robot.num_links * 12 : 0)) * sizeof(double);
     if (smem + 256 > 48 * 1024) /* the kernel also has a few bytes of static shared memory */
     {
         cudaError_t e = cudaFuncSetAttribute(forward_simulate_kernel<M, G, SEEDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
