@@ -9,7 +9,7 @@ if [ -n "$3" ]; then
   echo "pytest exit $?" >> gpurun_out/${TAG}_gputests.log
   tail -3 gpurun_out/${TAG}_gputests.log
 fi
-for rep in 1 2; do
+for rep in ${REPS:-1 2}; do
 for L in $VARIANTS; do
   unset UPC_B200_LIBRARY
   if [ $L != base ]; then export UPC_B200_LIBRARY=$PWD/uncertainty_planning_core_b200/libupc_b200_$L.so; fi

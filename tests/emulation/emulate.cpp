@@ -233,13 +233,17 @@ extern "C" int emulate_cull_check(const upc_env_desc* e, const upc_robot_desc* r
                 }
                 counts[5] += any ? 1 : 0;
             }
-            const CullFrame cf = cull_frame(env, rob, l, V, rob.cull_delta, clear_above);
+            /* both forms of the point test: the packed planar one (taken only when the link's z is uniform) and the scalar 3-D one */
+            const CullFrame cf = cull_frame<true>(env, rob, l, V, rob.cull_delta, clear_above);
+            const CullFrame cf3 = cull_frame<false>(env, rob, l, V, rob.cull_delta, clear_above);
             for (int k = rob.link_off[l]; k < rob.link_off[l + 1]; k++)
             {
                 double u[3];
                 xf_point(V, rob.pts[4 * k + 0], rob.pts[4 * k + 1], rob.pts[4 * k + 2], u);
                 const bool exact_hit = (sdf_distance(env, u) - rob.pts[4 * k + 3]) < threshold;
-                const bool culled = cull_certainly_clear(env, cf, ptsf[k]);
+                const bool culled_planar = cull_certainly_clear<true>(env, cf, ptsf[k]);
+                const bool culled_3d = cull_certainly_clear<false>(env, cf3, ptsf[k]);
+                const bool culled = culled_planar || culled_3d;
                 counts[0]++;
                 counts[1] += culled ? 1 : 0;
                 counts[2] += (culled && exact_hit) ? 1 : 0;

@@ -17,9 +17,12 @@
  */
 #include "upc_internal.h"
 #include "upc_sim.cuh"
+#include <cooperative_groups.h>
 
 #include <algorithm>
 #include <map>
+
+namespace cg = cooperative_groups;
 
 namespace upc
 {
@@ -806,6 +809,7 @@ struct PivotArgs
 };
 
 constexpr int kMaxPivots = 64;
+constexpr int kPivotCtas = 8; /* thread blocks per cluster when a cluster shares one set (portable maximum) */
 
 /* CTA-wide minimum of (key, index) pairs, smaller index on equal keys; every thread receives the result */
 __device__ __forceinline__ void block_min_pair(double& key, int& idx, double* s_key, int* s_idx)
@@ -827,7 +831,39 @@ __device__ __forceinline__ void block_min_pair(double& key, int& idx, double* s_
 }
 
 /*
- * One CTA per set.  Repeat: the smallest unassigned particle p opens a group.  If every unassigned particle of its
+ * The same minimum over the CTAS thread blocks of a cluster (distributed shared memory): every CTA reduces its own threads, publishes
+ * the result in its slot `parity` and reads the slots of all ranks after ONE cluster barrier.  Slots alternate between calls: a CTA
+ * can only overwrite slot `parity` two calls later, i.e. after the barrier of the call in between, which every CTA passes only after
+ * it has finished reading.  Every thread of every CTA receives the same result.
+ */
+template <int CTAS>
+__device__ __forceinline__ void team_min_pair(double& key, int& idx, double* s_key, int* s_idx, double* s_ckey, int* s_cidx, int& parity)
+{
+    block_min_pair(key, idx, s_key, s_idx);
+    if constexpr (CTAS > 1)
+    {
+        cg::cluster_group cluster = cg::this_cluster();
+        if (threadIdx.x == 0) { s_ckey[parity] = key; s_cidx[parity] = idx; }
+        cluster.sync();
+        double best = INFINITY;
+        int best_idx = 0x7fffffff;
+#pragma unroll
+        for (int r = 0; r < CTAS; r++)
+        {
+            const double* rk = cluster.map_shared_rank(s_ckey, r);
+            const int* ri = cluster.map_shared_rank(s_cidx, r);
+            const double k2 = rk[parity];
+            const int i2 = ri[parity];
+            if (r == 0 || k2 < best || (k2 == best && i2 < best_idx)) { best = k2; best_idx = i2; }
+        }
+        key = best; idx = best_idx;
+        parity ^= 1;
+    }
+}
+
+/*
+ * One CTA per set, or - for a few large sets - one cluster of CTAS thread blocks per set (thread-block clusters: the blocks
+ * share the sweeps over the set and exchange their partial minima through distributed shared memory).  Repeat: the smallest unassigned particle p opens a group.  If every unassigned particle of its
  * first-pass group that lies within the threshold of p lies within threshold/2 - margin, p is the group's centre;
  * otherwise a more central member is looked for (the candidate minimising its largest distance to p, to the candidate
  * farthest from p and to the candidates farthest from the centres tried so far).  The group takes every unassigned particle of the first-pass group within
@@ -839,7 +875,7 @@ __device__ __forceinline__ void block_min_pair(double& key, int& idx, double* s_
  * Anything else - more than kMaxPivots groups, centres too close, p outside its group - reports ok = 0 and the
  * adjacency pass decides.  The choice of the centre is a heuristic: it only affects whether the set is settled here.
  */
-template <int KIND>
+template <int KIND, int CTAS>
 __global__ void __launch_bounds__(1024) pivot_pass_kernel(const __grid_constant__ PivotArgs a)
 {
     constexpr int MAXF = PairDistance<KIND>::MAXF;
@@ -847,9 +883,18 @@ __global__ void __launch_bounds__(1024) pivot_pass_kernel(const __grid_constant_
     __shared__ int s_idx[32];
     __shared__ int s_centres[kMaxPivots];
     __shared__ int s_fail;
-    const int64_t base = (int64_t)blockIdx.x * a.set_size;
+    __shared__ double s_ckey[2];
+    __shared__ int s_cidx[2];
+    int parity = 0;
+    /* the set's thread team: one CTA, or the CTAS blocks of a cluster; particle i always belongs to the same thread of the team, so
+     * root / scratch entries are private to their owner between the team-wide reductions */
+    const int set = (int)(blockIdx.x / CTAS);
+    const int crank = (CTAS > 1) ? (int)(blockIdx.x % CTAS) : 0;
+    const int tid = crank * (int)blockDim.x + (int)threadIdx.x;
+    const int tstride = CTAS * (int)blockDim.x;
+    const int64_t base = (int64_t)set * a.set_size;
     const int n = (int)a.set_size;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) a.root[base + i] = -1;
+    for (int i = tid; i < n; i += tstride) a.root[base + i] = -1;
     if (threadIdx.x == 0) s_fail = 0;
     __syncthreads();
     int next = (n > 0) ? 0 : 0x7fffffff;
@@ -863,7 +908,7 @@ __global__ void __launch_bounds__(1024) pivot_pass_kernel(const __grid_constant_
         /* sweep 1: distances of the candidates to p; the farthest one within the threshold */
         double far_key = 1.0; /* keys are negated distances: block_min_pair returns the largest distance */
         int far_idx = 0x7fffffff;
-        for (int i = threadIdx.x; i < n; i += blockDim.x)
+        for (int i = tid; i < n; i += tstride)
         {
             double d = -1.0; /* not a candidate */
             if (a.root[base + i] < 0 && (!a.group || a.group[base + i] == gp))
@@ -884,7 +929,7 @@ __global__ void __launch_bounds__(1024) pivot_pass_kernel(const __grid_constant_
             }
             a.scratch[base + i] = d;
         }
-        block_min_pair(far_key, far_idx, s_key, s_idx);
+        team_min_pair<CTAS>(far_key, far_idx, s_key, s_idx, s_ckey, s_cidx, parity);
         int centre = p;
         if (-far_key > a.radius)
         {
@@ -899,7 +944,7 @@ __global__ void __launch_bounds__(1024) pivot_pass_kernel(const __grid_constant_
                 for (int f = 0; f < MAXF; f++) fe[f] = (f < a.nfeat) ? a.feat[(int64_t)f * a.total + base + ext] : 0.0;
                 double best_key = INFINITY;
                 int best_idx = 0x7fffffff;
-                for (int i = threadIdx.x; i < n; i += blockDim.x)
+                for (int i = tid; i < n; i += tstride)
                 {
                     const double dp = a.scratch[base + i];
                     if (dp < 0.0 || dp > a.threshold) continue;
@@ -912,7 +957,7 @@ __global__ void __launch_bounds__(1024) pivot_pass_kernel(const __grid_constant_
                     runmax[base + i] = key;
                     if (key < best_key || (key == best_key && i < best_idx)) { best_key = key; best_idx = i; }
                 }
-                block_min_pair(best_key, best_idx, s_key, s_idx);
+                team_min_pair<CTAS>(best_key, best_idx, s_key, s_idx, s_ckey, s_cidx, parity);
                 if (best_idx == 0x7fffffff) break;
                 centre = best_idx;
                 /* how far is the farthest candidate from this centre? */
@@ -921,7 +966,7 @@ __global__ void __launch_bounds__(1024) pivot_pass_kernel(const __grid_constant_
                 for (int f = 0; f < MAXF; f++) fcand[f] = (f < a.nfeat) ? a.feat[(int64_t)f * a.total + base + centre] : 0.0;
                 double worst_key = 1.0;
                 int worst_idx = 0x7fffffff;
-                for (int i = threadIdx.x; i < n; i += blockDim.x)
+                for (int i = tid; i < n; i += tstride)
                 {
                     const double dp = a.scratch[base + i];
                     if (dp < 0.0 || dp > a.threshold) continue;
@@ -931,7 +976,7 @@ __global__ void __launch_bounds__(1024) pivot_pass_kernel(const __grid_constant_
                     const double dc = (i == centre) ? 0.0 : PairDistance<KIND>::eval(a.robot, fcand, fi);
                     if (-dc < worst_key || (-dc == worst_key && i < worst_idx)) { worst_key = -dc; worst_idx = i; }
                 }
-                block_min_pair(worst_key, worst_idx, s_key, s_idx);
+                team_min_pair<CTAS>(worst_key, worst_idx, s_key, s_idx, s_ckey, s_cidx, parity);
                 if (-worst_key <= a.radius || worst_idx == 0x7fffffff) break;
                 ext = worst_idx;
             }
@@ -954,7 +999,7 @@ __global__ void __launch_bounds__(1024) pivot_pass_kernel(const __grid_constant_
         /* sweep 3: the group */
         double min_key = (double)0x7fffffff;
         int min_idx = 0x7fffffff;
-        for (int i = threadIdx.x; i < n; i += blockDim.x)
+        for (int i = tid; i < n; i += tstride)
         {
             if (a.root[base + i] >= 0) continue;
             const double dp = a.scratch[base + i];
@@ -980,7 +1025,7 @@ __global__ void __launch_bounds__(1024) pivot_pass_kernel(const __grid_constant_
             if (take) a.root[base + i] = p;
             else if (i < min_idx) { min_idx = i; min_key = (double)i; }
         }
-        block_min_pair(min_key, min_idx, s_key, s_idx); /* also orders the root writes before the test below */
+        team_min_pair<CTAS>(min_key, min_idx, s_key, s_idx, s_ckey, s_cidx, parity); /* also orders the root writes before the test below */
         if (threadIdx.x == 0)
         {
             s_centres[k] = centre;
@@ -990,7 +1035,8 @@ __global__ void __launch_bounds__(1024) pivot_pass_kernel(const __grid_constant_
         if (s_fail) break;
         next = min_idx;
     }
-    if (threadIdx.x == 0) a.ok[blockIdx.x] = (s_fail || next != 0x7fffffff) ? 0 : 1; /* also: more clusters than pivots */
+    if (threadIdx.x == 0 && crank == 0) a.ok[set] = (s_fail || next != 0x7fffffff) ? 0 : 1; /* also: more clusters than pivots */
+    if constexpr (CTAS > 1) cg::this_cluster().sync(); /* no block may exit while another still reads its slots */
 }
 
 /* ------------------------------------------------------------------ exact complete link for sets that are not unions of cliques */
@@ -2254,9 +2300,31 @@ int32_t run_cluster(upc_handle* h, const upc_cluster_params& cp, int64_t n_sets,
             UPC_NULLCHECK(pa.scratch);
             pa.root = root2; pa.ok = ok;
             const int threads = (set_size >= 1024) ? 1024 : ((set_size >= 256) ? 256 : 64);
-            if (kind == UPC_ROBOT_SE2) pivot_pass_kernel<UPC_ROBOT_SE2><<<(unsigned)n_sets, threads, 0, stream>>>(pa);
-            else if (kind == UPC_ROBOT_SE3) pivot_pass_kernel<UPC_ROBOT_SE3><<<(unsigned)n_sets, threads, 0, stream>>>(pa);
-            else pivot_pass_kernel<UPC_ROBOT_LINKED><<<(unsigned)n_sets, threads, 0, stream>>>(pa);
+            /* a few large sets (the single 10^4 .. 10^5-particle outcome of one edge): one CTA per set leaves 147 SMs idle, so a
+             * cluster of eight thread blocks shares each set (UPC_B200_NO_PIVOT_CLUSTER=1: one CTA per set, tests compare both) */
+            const char* no_cluster = getenv("UPC_B200_NO_PIVOT_CLUSTER");
+            const bool clustered = set_size >= 8192 && n_sets * kPivotCtas <= 2 * (int64_t)h->sm_count && !(no_cluster && no_cluster[0] == '1');
+            if (clustered)
+            {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned)(n_sets * kPivotCtas), 1, 1);
+                cfg.blockDim = dim3(1024, 1, 1);
+                cfg.dynamicSmemBytes = 0;
+                cfg.stream = stream;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = kPivotCtas;
+                attr[0].val.clusterDim.y = 1;
+                attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+                if (kind == UPC_ROBOT_SE2) UPC_CUDA_TRY(cudaLaunchKernelEx(&cfg, pivot_pass_kernel<UPC_ROBOT_SE2, kPivotCtas>, pa));
+                else if (kind == UPC_ROBOT_SE3) UPC_CUDA_TRY(cudaLaunchKernelEx(&cfg, pivot_pass_kernel<UPC_ROBOT_SE3, kPivotCtas>, pa));
+                else UPC_CUDA_TRY(cudaLaunchKernelEx(&cfg, pivot_pass_kernel<UPC_ROBOT_LINKED, kPivotCtas>, pa));
+            }
+            else if (kind == UPC_ROBOT_SE2) pivot_pass_kernel<UPC_ROBOT_SE2, 1><<<(unsigned)n_sets, threads, 0, stream>>>(pa);
+            else if (kind == UPC_ROBOT_SE3) pivot_pass_kernel<UPC_ROBOT_SE3, 1><<<(unsigned)n_sets, threads, 0, stream>>>(pa);
+            else pivot_pass_kernel<UPC_ROBOT_LINKED, 1><<<(unsigned)n_sets, threads, 0, stream>>>(pa);
             h->stats.kernel_launches++;
             UPC_CUDA_TRY(cudaGetLastError());
             std::vector<uint8_t> flags((size_t)n_sets);

@@ -612,12 +612,18 @@ struct Float2
 
 /* two single-precision fused multiply-adds / additions in one instruction on sm_100 (FFMA2 / FADD2: crt/sm_100_rt.h); each half
  * rounds exactly like the scalar operation, which is what the host build executes */
+#ifndef UPC_CULL_PACKED
+#define UPC_CULL_PACKED 1
+#endif
 UPC_D Float2 fma2(const Float2& a, const Float2& b, const Float2& c)
 {
     Float2 out;
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && UPC_CULL_PACKED
     const float2 v = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(c.x, c.y));
     out.x = v.x; out.y = v.y;
+#elif defined(__CUDA_ARCH__)
+    out.x = __fmaf_rn(a.x, b.x, c.x);
+    out.y = __fmaf_rn(a.y, b.y, c.y);
 #else
     out.x = __builtin_fmaf(a.x, b.x, c.x);
     out.y = __builtin_fmaf(a.y, b.y, c.y);
@@ -628,9 +634,12 @@ UPC_D Float2 fma2(const Float2& a, const Float2& b, const Float2& c)
 UPC_D Float2 add2(const Float2& a, const Float2& b)
 {
     Float2 out;
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && UPC_CULL_PACKED
     const float2 v = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
     out.x = v.x; out.y = v.y;
+#elif defined(__CUDA_ARCH__)
+    out.x = __fadd_rn(a.x, b.x);
+    out.y = __fadd_rn(a.y, b.y);
 #else
     out.x = a.x + b.x;
     out.y = a.y + b.y;
@@ -693,6 +702,7 @@ UPC_D int cull_round(float q, float* residue)
  *           same clamped corners, so cell 0 stands for both: accepted when round(q) = 0 and |q| <= 0.5 - 2 delta.
  * The cell-minimum table is indexed by cell + 1.
  */
+template <bool PLANAR>
 UPC_D CullFrame cull_frame(const DevEnv& env, const DevRobot& r, int l, const double* V, float delta, float clear_above)
 {
     CullFrame f;
@@ -715,7 +725,7 @@ UPC_D CullFrame cull_frame(const DevEnv& env, const DevRobot& r, int l, const do
     f.base = f.sx + f.sy + 1; /* the table is indexed by cell + 1 on every axis */
     /* the z coordinate of every point of the link is the same number when the points share their z and the row has no x / y part:
      * fma(0, p, t) = t exactly, so the value below is the value the per-point chain would produce */
-    f.z_uniform = (r.link_flat_z[l] != 0) && (f.vz[0] == 0.0f) && (f.vz[1] == 0.0f);
+    f.z_uniform = PLANAR && (r.link_flat_z[l] != 0) && (f.vz[0] == 0.0f) && (f.vz[1] == 0.0f);
     f.z_fail = false;
     if (f.z_uniform)
     {
@@ -726,35 +736,57 @@ UPC_D CullFrame cull_frame(const DevEnv& env, const DevRobot& r, int l, const do
         f.base += iz;
     }
 #if defined(__CUDA_ARCH__) && UPC_CULL_PIN_FRAME
-    /* keep the frame in registers: left alone ptxas rematerialises these conversions (F2F, constant loads, selects) for every
-     * point of the pass instead of holding ~ 16 values across the loop */
-    asm volatile("" : "+f"(f.vxy[0].x), "+f"(f.vxy[0].y), "+f"(f.vxy[1].x), "+f"(f.vxy[1].y), "+f"(f.vxy[2].x), "+f"(f.vxy[2].y), "+f"(f.txy.x), "+f"(f.txy.y));
-    asm volatile("" : "+f"(f.gx), "+f"(f.gy), "+r"(f.wx), "+r"(f.wy), "+r"(f.sx), "+r"(f.sy), "+r"(f.base), "+f"(f.clear_above));
-    if (!f.z_uniform) asm volatile("" : "+f"(f.vz[0]), "+f"(f.vz[1]), "+f"(f.vz[2]), "+f"(f.tz), "+f"(f.gz), "+r"(f.wz));
+    /* planar programs keep the frame in registers: left alone ptxas rematerialises these conversions (F2F, constant loads, selects)
+     * for every point of the pass instead of holding 16 values across the loop (C5 21.9 -> 21.3 ms).  The 3-D programs (SE(3),
+     * linked: 168 registers, already spilling) are better off without: C2 1.80 ms against 1.95 ms with the frame pinned. */
+    if constexpr (PLANAR)
+    {
+        asm volatile("" : "+f"(f.vxy[0].x), "+f"(f.vxy[0].y), "+f"(f.vxy[1].x), "+f"(f.vxy[1].y), "+f"(f.vxy[2].x), "+f"(f.vxy[2].y), "+f"(f.txy.x), "+f"(f.txy.y));
+        asm volatile("" : "+f"(f.gx), "+f"(f.gy), "+r"(f.wx), "+r"(f.wy), "+r"(f.sx), "+r"(f.sy), "+r"(f.base), "+f"(f.clear_above));
+    }
 #endif
     return f;
 }
 
-/* index into the cell-minimum table of the cell holding the point, or -1 when the float arithmetic cannot pin it */
+/* index into the cell-minimum table of the cell holding the point, or -1 when the float arithmetic cannot pin it.
+ * PLANAR programs (SE(2)): x and y axes in packed instructions, z already folded into the frame when the link's z is uniform;
+ * the 3-D programs: three scalar chains (the form they were tuned with: packing them cost C2 8 %) */
+template <bool PLANAR>
 UPC_D int cull_locate(const CullFrame& f, const CullPoint& p)
 {
-    const Float2 px = {p.xx[0], p.xx[1]}, py = {p.yy[0], p.yy[1]}, pz = {p.zz[0], p.zz[1]};
-    const Float2 q = fma2(f.vxy[2], pz, fma2(f.vxy[1], py, fma2(f.vxy[0], px, f.txy)));
-    const Float2 magic = {12582912.0f, 12582912.0f}, minus_magic = {-12582912.0f, -12582912.0f}, minus_one = {-1.0f, -1.0f};
-    const Float2 t = add2(q, magic);
-    const Float2 res = fma2(add2(t, minus_magic), minus_one, q); /* q - (t - magic): the product with -1 is exact */
-    const int ix = float_bits(t.x) - 0x4B400000, iy = float_bits(t.y) - 0x4B400000;
-    bool ok = (fabsf(res.x) <= f.gx) & (fabsf(res.y) <= f.gy) & ((unsigned)ix <= (unsigned)f.wx) & ((unsigned)iy <= (unsigned)f.wy);
-    int idx = ix * f.sx + iy * f.sy + f.base;
-    if (!f.z_uniform)
+    if constexpr (PLANAR)
     {
-        const float qz = upc_fmaf(f.vz[2], p.zz[0], upc_fmaf(f.vz[1], p.yy[0], upc_fmaf(f.vz[0], p.xx[0], f.tz)));
-        float rz;
-        const int iz = cull_round(qz, &rz);
-        ok = ok & (fabsf(rz) <= f.gz) & ((unsigned)iz <= (unsigned)f.wz);
-        idx += iz;
+        const Float2 px = {p.xx[0], p.xx[1]}, py = {p.yy[0], p.yy[1]}, pz = {p.zz[0], p.zz[1]};
+        const Float2 q = fma2(f.vxy[2], pz, fma2(f.vxy[1], py, fma2(f.vxy[0], px, f.txy)));
+        const Float2 magic = {12582912.0f, 12582912.0f}, minus_magic = {-12582912.0f, -12582912.0f}, minus_one = {-1.0f, -1.0f};
+        const Float2 t = add2(q, magic);
+        const Float2 res = fma2(add2(t, minus_magic), minus_one, q); /* q - (t - magic): the product with -1 is exact */
+        const int ix = float_bits(t.x) - 0x4B400000, iy = float_bits(t.y) - 0x4B400000;
+        bool ok = (fabsf(res.x) <= f.gx) & (fabsf(res.y) <= f.gy) & ((unsigned)ix <= (unsigned)f.wx) & ((unsigned)iy <= (unsigned)f.wy);
+        int idx = ix * f.sx + iy * f.sy + f.base;
+        if (!f.z_uniform)
+        {
+            const float qz = upc_fmaf(f.vz[2], p.zz[0], upc_fmaf(f.vz[1], p.yy[0], upc_fmaf(f.vz[0], p.xx[0], f.tz)));
+            float rz;
+            const int iz = cull_round(qz, &rz);
+            ok = ok & (fabsf(rz) <= f.gz) & ((unsigned)iz <= (unsigned)f.wz);
+            idx += iz;
+        }
+        return ok ? idx : -1;
     }
-    return ok ? idx : -1;
+    else
+    {
+        const float x = p.xx[0], y = p.yy[0], z = p.zz[0];
+        const float qx = upc_fmaf(f.vxy[2].x, z, upc_fmaf(f.vxy[1].x, y, upc_fmaf(f.vxy[0].x, x, f.txy.x)));
+        const float qy = upc_fmaf(f.vxy[2].y, z, upc_fmaf(f.vxy[1].y, y, upc_fmaf(f.vxy[0].y, x, f.txy.y)));
+        const float qz = upc_fmaf(f.vz[2], z, upc_fmaf(f.vz[1], y, upc_fmaf(f.vz[0], x, f.tz)));
+        float rx, ry, rz;
+        const int ix = cull_round(qx, &rx), iy = cull_round(qy, &ry), iz = cull_round(qz, &rz);
+        const bool ok = (fabsf(rx) <= f.gx) & (fabsf(ry) <= f.gy) & (fabsf(rz) <= f.gz) & ((unsigned)ix <= (unsigned)f.wx) &
+                        ((unsigned)iy <= (unsigned)f.wy) & ((unsigned)iz <= (unsigned)f.wz);
+        const int idx = ix * f.sx + iy * f.sy + iz + f.base;
+        return ok ? idx : -1;
+    }
 }
 
 /* phase A of a point pass: bit j set = point first + j * stride (< lim) needs the exact FP64 evaluation.
@@ -763,6 +795,7 @@ UPC_D int cull_locate(const CullFrame& f, const CullPoint& p)
 #ifndef UPC_CULL_INFLIGHT
 #define UPC_CULL_INFLIGHT 4
 #endif
+template <bool PLANAR>
 UPC_D unsigned cull_undecided(const DevEnv& env, const CullFrame& f, const CullPoint* ptsf, int first, int lim, int stride, unsigned candidates = 0xffffffffu)
 {
     unsigned undecided = 0u;
@@ -783,7 +816,7 @@ UPC_D unsigned cull_undecided(const DevEnv& env, const CullFrame& f, const CullP
         for (int q = 0; q < UPC_CULL_INFLIGHT; q++)
         {
             const int k = first + (j0 + q) * stride;
-            idx[q] = cull_locate(f, ptsf[(k < lim) ? k : first]);
+            idx[q] = cull_locate<PLANAR>(f, ptsf[(k < lim) ? k : first]);
         }
         float m[UPC_CULL_INFLIGHT];
 #pragma unroll
@@ -800,10 +833,11 @@ UPC_D unsigned cull_undecided(const DevEnv& env, const CullFrame& f, const CullP
 }
 
 /* single-point form (tests) */
+template <bool PLANAR>
 UPC_D bool cull_certainly_clear(const DevEnv& env, const CullFrame& f, const CullPoint& p)
 {
     if (f.z_fail) return false;
-    const int idx = cull_locate(f, p);
+    const int idx = cull_locate<PLANAR>(f, p);
     if (idx < 0) return false;
     return ldg(env.cellmin + idx) > f.clear_above;
 }
@@ -1138,6 +1172,7 @@ struct Se2Model
         set_config(x + n0, y + n1, th + n2);
     }
     static constexpr bool HAS_FRAMES = false;
+    static constexpr bool PLANAR = true; /* body points usually share one z: the pre-cull may locate the z axis once per link */
     UPC_D void frame(const DevRobot&, int, double* T) const /* :363-371 */
     {
         T[0] = cs;  T[1] = -sn; T[2] = 0.0;  T[3] = x;
@@ -1314,6 +1349,7 @@ struct Se3Model
         for (int k = 0; k < 12; k++) T[k] = next[k];
     }
     static constexpr bool HAS_FRAMES = false;
+    static constexpr bool PLANAR = false;
     UPC_D void frame(const DevRobot&, int, double* out) const
     {
 #pragma unroll
@@ -1353,6 +1389,7 @@ struct LinkedModelT
     double* pid_e;
     double* frames; /* num_links * 12 doubles, current link transforms */
     static constexpr bool HAS_FRAMES = true;
+    static constexpr bool PLANAR = false;
     UPC_D void frame(const DevRobot&, int l, double* out) const
     {
 #pragma unroll

@@ -154,6 +154,9 @@ constexpr int kResolverInFlight = UPC_RES_INFLIGHT;
 #endif
 /* one-lane programs accumulate a contributing point as soon as it has been evaluated (ascending order either way) instead of
  * parking its correction vector in a per-thread buffer for the replay phase: no dynamically indexed local array */
+#ifndef UPC_STEP_BARRIER_EVERY
+#define UPC_STEP_BARRIER_EVERY 1
+#endif
 #ifndef UPC_ONE_LANE_IMMEDIATE
 #define UPC_ONE_LANE_IMMEDIATE 1
 #endif
@@ -223,7 +226,7 @@ UPC_D bool check_collision(const DevEnv& env, const DevRobot& r, const M& m, con
             {
                 /* enough points per lane for full batches: single-precision pre-cull against the 4-byte cell minimum
                  * first (UPC_CULL_INFLIGHT lookups in flight), exact FP64 evaluation of the undecided points only */
-                const CullFrame cf = cull_frame(env, r, l, V, r.cull_delta, clear_above);
+                const CullFrame cf = cull_frame<M::PLANAR>(env, r, l, V, r.cull_delta, clear_above);
                 const CullPoint* ptsf = reinterpret_cast<const CullPoint*>(pts + 4 * r.num_points);
                 for (int chunk = beg; chunk < end; chunk += 32 * G)
                 {
@@ -232,7 +235,7 @@ UPC_D bool check_collision(const DevEnv& env, const DevRobot& r, const M& m, con
                     /* group-level cull (one-lane programs): only the points of groups that are not provably clear go on */
                     unsigned group_mask = 0xffffffffu;
                     if constexpr (G == 1) group_mask = group_candidates(env, r, l, (chunk - beg) >> 5, V, clear_above);
-                    unsigned undecided = cull_undecided(env, cf, ptsf, first, lim, G, group_mask);
+                    unsigned undecided = cull_undecided<M::PLANAR>(env, cf, ptsf, first, lim, G, group_mask);
                     while (undecided)
                     {
                         int kk[kCheckInFlight];
@@ -497,9 +500,9 @@ UPC_RESOLVER_LINKAGE int resolver_correction(const DevEnv& env, const DevRobot& 
                      * candidates instead of one per point slot (some lane of the warp is near a surface at almost every slot).
                      * Compiled for 2..8 lanes only: measured C2 (4 lanes) 2.11 -> 2.03 ms, but the one-lane big-batch program
                      * (-3 %) and the 32-lane SE(2) program (+5 % on C1, where the pass never runs) lose by carrying it. */
-                    const CullFrame cf = cull_frame(env, r, l, V, r.cull_delta, clear_above);
+                    const CullFrame cf = cull_frame<M::PLANAR>(env, r, l, V, r.cull_delta, clear_above);
                     const CullPoint* ptsf = reinterpret_cast<const CullPoint*>(pts + 4 * r.num_points);
-                    unsigned candidates = cull_undecided(env, cf, ptsf, first, lim, G, group_mask);
+                    unsigned candidates = cull_undecided<M::PLANAR>(env, cf, ptsf, first, lim, G, group_mask);
                     while (candidates)
                     {
                         const int j = lowest_bit(candidates);
@@ -813,7 +816,7 @@ UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim&
      * interval, finished particles included. */
     for (int step = sp.step_begin; step < sp.step_end; step++)
     {
-        __syncthreads();
+        if (((step - sp.step_begin) % UPC_STEP_BARRIER_EVERY) == 0) __syncthreads();
         if (finished) continue;
         cnt.particle_steps++;
 #else
