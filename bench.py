@@ -580,7 +580,10 @@ def run_b200(args):
                     "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes_per_particle_step": Pn * bpp,
                     "hbm_peak_gbs": hbm_peak, "hbm_peak_source": peak_src, "frac_of_hbm_peak": achieved / hbm_peak,
                     "compulsory_hbm_gbs": compulsory, "fp64_fma_peak_tflops": fp64.value,
-                    "note": "algorithmic gathers = SURVEY 8d nominal bytes; conservative culls skip most of them, so `achieved` is a work rate (see DESIGN.md 7)"}
+                    "note": "algorithmic gathers = SURVEY 8d nominal bytes; conservative culls skip most of them, so `achieved` is a work rate (see DESIGN.md 7)",
+                    "limiter": "not bandwidth: ncu of this kernel (profiles/r02l_sim_c5_metrics.txt, r02g_* before) - the 140 KB per-particle program is bound by "
+                               "instruction fetch (SM instruction cache 78 % -> 92 % hits with the per-interval barrier) and, after that, by fixed-latency dependencies at "
+                               "16 warps per SM; L1 serves 99 % of the SDF sectors, DRAM carries a few MB per launch"}
         # ---- CPU baseline on a bounded sample (rank 0, N = 1 only)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:

@@ -946,6 +946,56 @@ inline std::vector<int64_t> NearestNeighbors(upc_handle* handle, const std::vect
     return nearest;
 }
 
+/*
+ * Speculative multi-edge extension: the RRT-Extend branch of PerformForwardPropagation (uncertainty_contact_planning.hpp:2320-2340)
+ * for a whole batch of sampled configurations in ONE nearest-neighbour launch, ONE simulation launch and ONE clustering pass - the
+ * shape that makes planner batches (BASELINE config 5) exist inside a planner.  Per sample q, exactly what the reference does for
+ * one: nearest[q] = GetNearestNeighbor(sample) (:1506-1542); target = the sample itself when it lies within step_size of the nearest
+ * state's expectation, else InterpolateBetweenConfigurations(expectation, sample, step_size / distance) (:2322-2334, evaluated by
+ * the caller's own robot object, so the arithmetic is the reference's); then ForwardSimulateParticles (:2039-2071) from the
+ * expectation towards the target and ClusterParticles (:1986-2034) of the outcome.  Which of the speculative edges the planner
+ * commits - and in which order their child states enter the tree - stays the planner's decision.  Samples without an enabled
+ * state (nearest = -1) get no edge: their entry of `clusters` is empty.
+ */
+template <typename Configuration, typename ConfigAlloc = std::allocator<Configuration>>
+struct ExtensionBatch
+{
+    std::vector<int64_t> nearest;                                                     /* per sample: index of the state it extends from */
+    std::vector<Configuration, ConfigAlloc> targets;                                  /* per sample: the configuration simulated towards */
+    std::vector<std::vector<std::vector<std::pair<Configuration, bool>>>> clusters;   /* per sample: what ClusterParticles returns */
+};
+
+template <typename Simulator, typename Robot, typename Configuration, typename RNG, typename Clustering, typename ConfigAlloc = std::allocator<Configuration>>
+inline ExtensionBatch<Configuration, ConfigAlloc> ExtendTowardsSamples(
+    const Simulator& simulator, upc_handle* handle, const Robot& robot, const std::vector<const Configuration*>& expectations,
+    const std::vector<double>& feasibility_weights, const std::vector<double>& variance_weights, const std::vector<uint8_t>& use_for_nearest_neighbors,
+    const std::vector<Configuration>& samples, const double step_size, const size_t particles_per_edge, std::vector<RNG>& rng,
+    const double step_duration, const double simulation_shortcut_distance, const bool use_individual_jacobians, const bool allow_contacts,
+    const Clustering& clustering)
+{
+    ExtensionBatch<Configuration, ConfigAlloc> batch;
+    batch.nearest = NearestNeighbors<Configuration>(handle, expectations, feasibility_weights, variance_weights, use_for_nearest_neighbors, samples, step_size);
+    batch.targets.assign(samples.begin(), samples.end());
+    batch.clusters.resize(samples.size());
+    std::vector<Configuration, ConfigAlloc> edge_starts, edge_targets;
+    std::vector<size_t> edge_sample;
+    for (size_t q = 0; q < samples.size(); q++)
+    {
+        if (batch.nearest[q] < 0) continue;
+        const Configuration& from = *expectations[(size_t)batch.nearest[q]];
+        const double target_distance = robot.ComputeConfigurationDistance(from, samples[q]);
+        if (target_distance > step_size) batch.targets[q] = robot.InterpolateBetweenConfigurations(from, samples[q], step_size / target_distance);
+        edge_starts.push_back(from);
+        edge_targets.push_back(batch.targets[q]);
+        edge_sample.push_back(q);
+    }
+    if (edge_starts.empty()) return batch;
+    auto edge_clusters = simulator.SimulateAndClusterEdges(robot, edge_starts, edge_targets, particles_per_edge, rng, step_duration, simulation_shortcut_distance,
+                                                           use_individual_jacobians, allow_contacts, clustering);
+    for (size_t e = 0; e < edge_sample.size(); e++) batch.clusters[edge_sample[e]] = std::move(edge_clusters[e]);
+    return batch;
+}
+
 } /* namespace upc_b200 */
 
 #endif /* UPC_B200_SHIM_HPP */

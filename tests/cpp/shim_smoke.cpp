@@ -23,9 +23,26 @@ extern "C" int32_t oracle_cluster_statistics(const upc_robot_desc*, int64_t, con
 extern "C" int32_t oracle_cluster_particles(const upc_env_desc*, const upc_robot_desc*, const upc_cluster_params*, int64_t, int64_t, const double*,
                                             int32_t*, int32_t*, upc_stats*);
 
+extern "C" int32_t oracle_nearest_neighbors(const upc_robot_desc*, int64_t, const double*, const double*, const double*, const uint8_t*, int64_t, const double*,
+                                            double, int64_t*, double*);
+
 typedef std::array<double, 3> SE2Config;
 typedef std::pair<SE2Config, bool> Particle;
-struct StubRobot {}; /* the planner's robot object is only borrowed by the simulator */
+typedef std::array<double, 3> SE2ConfigFwd;
+/* the planner's robot object is only borrowed by the simulator; the extension-batch helper asks it for SimpleSE2Robot's distance and
+ * interpolation (simple_robot_models.hpp:401-430) */
+struct StubRobot
+{
+    static double wrap(double a) { while (a > M_PI) a -= 2.0 * M_PI; while (a <= -M_PI) a += 2.0 * M_PI; return a; }
+    double ComputeConfigurationDistance(const SE2ConfigFwd& a, const SE2ConfigFwd& b) const
+    {
+        return std::sqrt((b[0] - a[0]) * (b[0] - a[0]) + (b[1] - a[1]) * (b[1] - a[1])) + std::fabs(wrap(b[2] - a[2]));
+    }
+    SE2ConfigFwd InterpolateBetweenConfigurations(const SE2ConfigFwd& a, const SE2ConfigFwd& b, const double ratio) const
+    {
+        return SE2ConfigFwd{a[0] + (b[0] - a[0]) * ratio, a[1] + (b[1] - a[1]) * ratio, wrap(a[2] + wrap(b[2] - a[2]) * ratio)};
+    }
+};
 
 using namespace upc_b200;
 
@@ -308,6 +325,52 @@ int main(int argc, char** argv)
         for (size_t i = 0; i < m; i++) psz[(size_t)pl[i]]++;
         for (size_t k = 0; k < pc.size(); k++)
             if (pc[k].size() != psz[k]) { std::printf("PTPM cluster %zu size differs\n", k); return 19; }
+    }
+    {
+        /* speculative multi-edge extension (RRT-Extend branch, uncertainty_contact_planning.hpp:2320-2340) for a batch of samples:
+         * nearest states == the oracle's, targets == the reference's interpolation rule, clusters == the edge batch issued by hand */
+        const StubRobot& planner_robot = stub;
+        const std::vector<SE2Config> tree = {{2.6, 2.4, 0.1}, {3.0, 2.5, 0.0}, {3.4, 2.4, -0.2}, {2.8, 2.9, 0.3}, {3.8, 2.6, 0.0}, {2.2, 2.2, 0.0}};
+        std::vector<const SE2Config*> expectations;
+        for (const SE2Config& c : tree) expectations.push_back(&c);
+        const std::vector<double> fw = {1.0, 1.0, 1.2, 1.0, 0.9, 1.0}, vw = {1.0, 1.1, 1.0, 1.0, 1.0, 1.0};
+        const std::vector<uint8_t> use = {1, 1, 1, 1, 1, 0};
+        std::vector<SE2Config> samples;
+        for (int q = 0; q < 10; q++) samples.push_back(SE2Config{2.3 + 0.17 * q, 2.2 + 0.09 * ((q * 7) % 10), -0.4 + 0.09 * q});
+        samples[3] = SE2Config{3.02, 2.52, 0.01}; /* closer than the step size: the sample itself is the target */
+        const double step_size = 0.3;
+        const size_t P = 64;
+        std::vector<std::mt19937_64> g(1, std::mt19937_64(4321)), g_copy = g;
+        const auto ext = ExtendTowardsSamples(simulator, simulator.handle(), planner_robot, expectations, fw, vw, use, samples, step_size, P, g, 0.5, 0.01, false,
+                                              true, clustering);
+        std::vector<double> esoa(3 * tree.size()), qsoa(3 * samples.size()), odist(samples.size());
+        for (size_t i = 0; i < tree.size(); i++)
+            for (int c = 0; c < 3; c++) esoa[(size_t)c * tree.size() + i] = tree[i][(size_t)c];
+        for (size_t q = 0; q < samples.size(); q++)
+            for (int c = 0; c < 3; c++) qsoa[(size_t)c * samples.size() + q] = samples[q][(size_t)c];
+        std::vector<int64_t> onear(samples.size());
+        if (oracle_nearest_neighbors(&robot.desc, (int64_t)tree.size(), esoa.data(), fw.data(), vw.data(), use.data(), (int64_t)samples.size(), qsoa.data(), step_size,
+                                     onear.data(), odist.data()) != 0) return 20;
+        if (ext.nearest != onear) { std::printf("extension batch: nearest states differ from the oracle\n"); return 20; }
+        std::vector<SE2Config> es, et;
+        bool interpolated = false, direct = false;
+        for (size_t q = 0; q < samples.size(); q++)
+        {
+            if (ext.nearest[q] == 5) { std::printf("extension batch: a disabled state was selected\n"); return 20; }
+            const SE2Config& from = tree[(size_t)ext.nearest[q]];
+            const double d = planner_robot.ComputeConfigurationDistance(from, samples[q]);
+            const SE2Config want = (d > step_size) ? planner_robot.InterpolateBetweenConfigurations(from, samples[q], step_size / d) : samples[q];
+            if (ext.targets[q] != want) { std::printf("extension batch: target %zu differs\n", q); return 20; }
+            interpolated |= d > step_size;
+            direct |= !(d > step_size);
+            if (std::fabs(planner_robot.ComputeConfigurationDistance(from, want) - std::min(d, step_size)) > 1e-12) { std::printf("extension batch: step length\n"); return 20; }
+            es.push_back(from);
+            et.push_back(want);
+        }
+        if (!interpolated || !direct) { std::printf("extension batch: both target rules must be exercised\n"); return 20; }
+        const auto by_hand = simulator.SimulateAndClusterEdges(stub, es, et, P, g_copy, 0.5, 0.01, false, true, clustering);
+        if (ext.clusters != by_hand) { std::printf("extension batch: clusters differ from the edge batch issued by hand\n"); return 20; }
+        if (g[0] != g_copy[0]) { std::printf("extension batch: generator advanced differently\n"); return 20; }
     }
     const auto stats = simulator.GetStatistics();
     std::printf("shim ok: %zu particles, %zu collided, %zu clusters, %.0f kernel launches\n", n, collided, clusters.size(), stats.at("kernel_launches"));
