@@ -10,7 +10,9 @@ over the 4,096 outcome sets (ClusterParticles, :1986-2034).  Noise is drawn insi
 With --gpus N the edges are split into contiguous blocks (strong scaling), the SDF is replicated, every rank simulates and
 clusters its block straight into its slot of the gather buffer, and the step ends with ONE NCCL all-gather of the outcome
 records issued by the library's own communicator (upc_comm_*); torch.distributed (gloo) only carries the 128-byte NCCL id,
-the barriers and the max-over-ranks of the timings.
+the barriers and the max-over-ranks of the timings.  Batches are pipelined over two streams: the simulation of batch k overlaps
+the clustering (and exchange) of batch k - 1 - K simulations and K clusterings inside the timed region, pipeline drained at both
+ends; `sim` / `clustering` / `pipeline.ms_per_step_back_to_back` come from a second pass without the overlap.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c2|c3|c1]     # the CUDA path
   python bench.py --impl reference ...                                             # the CPU path (oracle) on the host cores
@@ -332,14 +334,19 @@ def run_plugin_driver(wl, cp, mode, steps, warmup, gpus=1):
 
 
 class DeviceBatch:
-    """Device-resident state of one rank for a workload: handle, (optional) communicator, replicated edge arrays, two gather
-    buffers.  step(k) issues one sharded planner-batch step asynchronously on the torch side stream."""
+    """Device-resident state of one rank for a workload: handle, (optional) communicator, replicated edge arrays, two outcome
+    buffers, two streams.  step(k) issues one planner-batch step asynchronously.  Pipelined (default): the simulation of batch k
+    runs on stream A while the clustering (and, with several GPUs, the exchange) of batch k - 1 runs on stream B - the
+    simulation fills the machine, the clustering is a handful of small latency-bound launches with host decisions in between, so
+    the two overlap almost for free; finish() drains the pipeline.  step(k, ev) with timing events runs the two halves back to back
+    on stream A instead (the per-phase breakdown)."""
 
-    def __init__(self, wl, cp, world, rank, local_rank, nccl_id, lanes=0):
+    def __init__(self, wl, cp, world, rank, local_rank, nccl_id, lanes=0, pipelined=True):
         import torch
         from uncertainty_planning_core_b200 import B200Simulator, abi
         self.torch, self.abi, self.lib = torch, abi, abi.load_library()
         self.wl, self.cp, self.world, self.rank = wl, cp, world, rank
+        self.pipelined = pipelined
         self.dev = torch.device("cuda", local_rank)
         self.sim = B200Simulator(wl["env"], wl["robot"], device=local_rank)
         if lanes:
@@ -357,42 +364,90 @@ class DeviceBatch:
             self.comm = comm
         self.d_starts = torch.from_numpy(np.ascontiguousarray(wl["edge_starts"].T)).to(self.dev)
         self.d_targets = torch.from_numpy(np.ascontiguousarray(wl["edge_targets"].T)).to(self.dev)
-        self.blocks = [torch.zeros(self.lay.block_bytes * world, dtype=torch.uint8, device=self.dev) for _ in range(2 if world > 1 else 1)]
-        self.stream_obj = torch.cuda.Stream(device=self.dev)
-        self.stream = self.stream_obj.cuda_stream
-        assert self.stream != 0
+        self.blocks = [torch.zeros(self.lay.block_bytes * world, dtype=torch.uint8, device=self.dev) for _ in range(2)]
+        self.stream_obj = torch.cuda.Stream(device=self.dev)        # A: simulation
+        self.stream_b_obj = torch.cuda.Stream(device=self.dev)      # B: clustering + exchange of the batch before
+        self.stream, self.stream_b = self.stream_obj.cuda_stream, self.stream_b_obj.cuda_stream
+        assert self.stream != 0 and self.stream_b != 0
+        self.ev_sim = [torch.cuda.Event() for _ in range(2)]        # simulation of the batch in buffer i has finished
+        self.ev_done = [torch.cuda.Event() for _ in range(2)]       # clustering of the batch in buffer i has finished
+        self.pending = None                                          # batch simulated but not yet clustered
+        self.issued = 0
 
     def local_particles(self):
         return (self.hi - self.lo) * self.P
 
-    def step(self, k, ev=None):
+    def _simulate(self, k, stream_obj):
         abi, lib, lay = self.abi, self.lib, self.lay
-        blocks = self.blocks[k % len(self.blocks)]
+        blocks = self.blocks[k % 2]
         if self.comm is not None:
-            abi.check(lib.upc_sharded_edge_batch(self.comm, C.byref(self.wl["params"]), C.byref(self.cp), SEED + k, self.E, self.P,
-                                                 self.d_starts.data_ptr(), self.d_targets.data_ptr(), blocks.data_ptr(), self.stream))
+            abi.check(lib.upc_sharded_edge_batch_simulate(self.comm, C.byref(self.wl["params"]), SEED + k, self.E, self.P, self.d_starts.data_ptr(),
+                                                          self.d_targets.data_ptr(), blocks.data_ptr(), stream_obj.cuda_stream))
             return
         base = blocks.data_ptr()
-        n = self.E * self.P
-        if ev:
-            ev[0].record(self.stream_obj)
-        abi.check(lib.upc_forward_simulate_seeded_device(self.h, C.byref(self.wl["params"]), SEED + k, 0, n, self.E, self.d_starts.data_ptr(), self.E,
-                                                         self.d_targets.data_ptr(), base + lay.configs_offset, base + lay.collided_offset, self.stream))
-        if ev:
-            ev[1].record(self.stream_obj)
+        abi.check(lib.upc_forward_simulate_seeded_device(self.h, C.byref(self.wl["params"]), SEED + k, 0, self.E * self.P, self.E, self.d_starts.data_ptr(), self.E,
+                                                         self.d_targets.data_ptr(), base + lay.configs_offset, base + lay.collided_offset, stream_obj.cuda_stream))
+
+    def _cluster(self, k, stream_obj):
+        abi, lib, lay = self.abi, self.lib, self.lay
+        blocks = self.blocks[k % 2]
+        if self.comm is not None:
+            abi.check(lib.upc_sharded_edge_batch_finish(self.comm, C.byref(self.cp), self.E, self.P, blocks.data_ptr(), stream_obj.cuda_stream))
+            return
+        base = blocks.data_ptr()
         abi.check(lib.upc_cluster_particles_device(self.h, C.byref(self.cp), self.E, self.P, base + lay.configs_offset, base + lay.labels_offset,
-                                                   base + lay.n_clusters_offset, self.stream))
-        if ev:
-            ev[2].record(self.stream_obj)
+                                                   base + lay.n_clusters_offset, stream_obj.cuda_stream))
+
+    def step(self, k, ev=None):
+        A, B = self.stream_obj, self.stream_b_obj
+        if ev or not self.pipelined:
+            # the two halves back to back on stream A (events around each: the per-phase breakdown)
+            self._drain()
+            if ev:
+                ev[0].record(A)
+            self._simulate(k, A)
+            if ev:
+                ev[1].record(A)
+            self._cluster(k, A)
+            if ev:
+                ev[2].record(A)
+            return
+        # buffer k % 2 was last used by batch k - 2: its clustering (and exchange) must be over before it is overwritten
+        if self.issued >= 2:
+            A.wait_event(self.ev_done[k % 2])
+            if self.comm is not None:
+                self.abi.check(self.lib.upc_comm_wait(self.comm, A.cuda_stream))
+        self._simulate(k, A)
+        self.ev_sim[k % 2].record(A)
+        self.issued += 1
+        if self.pending is not None:
+            self._finish_pending()
+        self.pending = k
+
+    def _finish_pending(self):
+        k, B = self.pending, self.stream_b_obj
+        B.wait_event(self.ev_sim[k % 2])
+        self._cluster(k, B)          # host decisions inside only ever wait for stream B
+        self.ev_done[k % 2].record(B)
+        self.pending = None
+
+    def _drain(self):
+        if self.pending is not None:
+            self._finish_pending()
+        if self.issued:
+            self.stream_obj.wait_event(self.ev_done[0])
+            self.stream_obj.wait_event(self.ev_done[1])
+            self.issued = 0
 
     def finish(self):
-        """everything issued so far (exchanges included) is complete when the side stream reaches this point"""
+        """everything issued so far (clustering and exchanges included) is complete when stream A reaches this point"""
+        self._drain()
         if self.comm is not None:
             self.abi.check(self.lib.upc_comm_wait(self.comm, self.stream))
 
     def cluster_counts(self, k=0):
         lay = self.lay
-        blk = self.blocks[k % len(self.blocks)].cpu().numpy()
+        blk = self.blocks[k % 2].cpu().numpy()
         out = []
         for r in range(self.world):
             lo, hi = self.abi.shard_bounds(self.E, r, self.world)
@@ -442,12 +497,13 @@ def secondary_workload(name, steps, warmup, local_rank):
     try:
         def barrier():
             torch.cuda.synchronize()
-        total_ms, sim_ms, cl_ms, stats = timed_device_steps(batch, steps, warmup, barrier, phase_events=True)
+        total_ms, _, _, stats = timed_device_steps(batch, steps, warmup, barrier)                       # pipelined: what `value` is
+        b2b_ms, sim_ms, cl_ms, _ = timed_device_steps(batch, steps, 1, barrier, phase_events=True)     # back to back: the breakdown
         n, S = wl["particles_per_edge"], wl["params"].num_steps
         P, bpp = wl["robot"].num_points, sdf_bytes_per_point(wl)
         alg = (stats["particle_steps"] + stats["resolver_iterations"]) / steps * P * bpp
         return {"workload": wl["label"], "value": n * S * steps / (total_ms * 1e-3), "unit": UNIT, "ms_per_step": total_ms / steps,
-                "sim_ms": sim_ms / steps, "clustering_ms": cl_ms / steps, "clusters": int(batch.cluster_counts()[0]),
+                "ms_per_step_back_to_back": b2b_ms / steps, "sim_ms": sim_ms / steps, "clustering_ms": cl_ms / steps, "clusters": int(batch.cluster_counts()[0]),
                 "sim_value": n * S * steps / (sim_ms * 1e-3), "clustered_per_sec": n * steps / (cl_ms * 1e-3),
                 "algorithmic_sdf_gather_gbs": alg / (sim_ms / steps * 1e-3) / 1e9, "lanes_per_particle": "auto",
                 "collided_fraction": stats["collided_particles"] / max(stats["particles_simulated"], 1),
@@ -503,8 +559,14 @@ def run_b200(args):
 
     # ---- device-resident throughput: W warm-up steps, then exactly K timed steps between barriers, max over ranks
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    total_ms, sim_ms, cl_ms, stats = timed_device_steps(batch, args.steps, args.warmup, barrier, sampler, phase_events=(world == 1))
+    total_ms, _, _, stats = timed_device_steps(batch, args.steps, args.warmup, barrier, sampler)
     clocks = sampler.stop() if sampler else None
+    b2b_ms = None
+    if world == 1:
+        # per-phase times: a second, shorter pass with the two halves back to back on one stream and events around each
+        kb = min(args.steps, 5)
+        b2b_ms, sim_ms, cl_ms, _ = timed_device_steps(batch, kb, 1, barrier, phase_events=True)
+        b2b_ms, sim_ms, cl_ms = b2b_ms * args.steps / kb, sim_ms * args.steps / kb, cl_ms * args.steps / kb
     if world > 1:
         # per-phase times of this rank's shard, measured in a second, un-timed pass without the exchange
         solo = DeviceBatch(dict(wl, edge_starts=wl["edge_starts"][batch.lo:batch.hi], edge_targets=wl["edge_targets"][batch.lo:batch.hi]), cp, 1, 0, local_rank, None, args.lanes)
@@ -614,14 +676,17 @@ def run_b200(args):
             "dtype": "f64", "data": "synthetic (seeded boxes SDF, seeded edges, counter-based truncated-normal noise drawn in the kernel)",
             "config": {"workload": wl["label"], "edges": E, "particles_per_edge": P, "edges_per_gpu": hi - lo,
                        "sharding": "contiguous blocks of edges per GPU (upc_shard_bounds), SDF + robot tables replicated, ONE in-place NCCL all-gather of outcome records per step "
-                                   "issued by the library's communicator (two gather buffers: the exchange of step k overlaps the simulation of step k+1)" if world > 1 else "single GPU",
+                                   "issued by the library's communicator (two gather buffers: clustering + exchange of step k overlap the simulation of step k+1)" if world > 1 else "single GPU",
                        "nccl_version": nccl_version,
                        "clustering": "CRS signatures (thr 0.125) + distance pass (thr 0.1), one pass over all edges",
                        "lanes_per_particle": args.lanes or "auto",
                        "l2": "inputs larger than L2 where they stream: every step writes %.0f MB of outcome records and re-reads them for clustering (126 MB L2); the %.1f MiB SDF table is "
                              "deliberately cache-resident across steps, as it is across the batches of a planner run; every step uses a new noise seed" % (batch.lay.block_bytes * world / 1e6, gather_buffer / 2 ** 20)},
+            "pipeline": {"overlap": "the simulation of batch k (stream A) overlaps the clustering%s of batch k - 1 (stream B); K simulations and K clusterings inside the timed region, "
+                                    "the pipeline drained at both ends" % (" and the exchange" if world > 1 else ""),
+                         "ms_per_step_back_to_back": (b2b_ms / args.steps) if b2b_ms else None},
             "sim": {"value": particle_steps / (sim_ms * 1e-3), "unit": UNIT, "ms_per_step": sim_ms / args.steps,
-                    "scope": "whole batch on this GPU" if world == 1 else "slowest rank's shard, measured without the exchange"},
+                    "scope": "whole batch on this GPU, measured back to back (not overlapped)" if world == 1 else "slowest rank's shard, measured back to back without the exchange"},
             "clustering": {"value": n_total * args.steps / (cl_ms * 1e-3), "unit": "particles clustered/s", "ms_per_step": cl_ms / args.steps,
                            "sets_per_sec": E * args.steps / (cl_ms * 1e-3), "clusters_total": int(ncl_all.sum()), "clusters_max_per_edge": int(ncl_all.max()),
                            "fallback_sets": int(stats["cluster_fallback_calls"])},

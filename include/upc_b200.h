@@ -383,6 +383,18 @@ int32_t upc_comm_synchronize(upc_comm* c);
 int32_t upc_sharded_edge_batch(upc_comm* c, const upc_sim_params* params, const upc_cluster_params* cparams, uint64_t seed,
                                int64_t n_edges, int64_t particles_per_edge, const double* d_edge_starts, const double* d_edge_targets,
                                void* d_blocks, void* stream);
+/*
+ * The two halves of that step as separate calls, for callers that pipeline batches with two streams: the simulation of batch
+ * k + 1 (stream A: fills the machine) overlaps the clustering and the exchange of batch k (stream B: small latency-bound
+ * launches and the host decisions between them).  _simulate is asynchronous and never waits on the host; _finish clusters this
+ * rank's block on `stream` - order it after the simulation of the same batch with an event - and issues the all-gather behind
+ * it.  Simulation and clustering of one handle touch disjoint device state, so both may be in flight, issued from one host
+ * thread; the d_blocks of batches in flight must be distinct buffers (call upc_comm_wait on stream A before a buffer is reused).
+ */
+int32_t upc_sharded_edge_batch_simulate(upc_comm* c, const upc_sim_params* params, uint64_t seed, int64_t n_edges, int64_t particles_per_edge,
+                                        const double* d_edge_starts, const double* d_edge_targets, void* d_blocks, void* stream);
+int32_t upc_sharded_edge_batch_finish(upc_comm* c, const upc_cluster_params* cparams, int64_t n_edges, int64_t particles_per_edge, void* d_blocks,
+                                      void* stream);
 /* the same step for all n ranks of a single-process communicator set: one entry per rank in every array (device pointers on
  * that rank's GPU; streams may be NULL) */
 int32_t upc_sharded_edge_batch_all(int32_t n, upc_comm* const* comms, const upc_sim_params* params, const upc_cluster_params* cparams, uint64_t seed,

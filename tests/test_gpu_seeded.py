@@ -228,6 +228,70 @@ def test_sharded_edge_batch_through_the_library_communicator(oracle, simulators)
                 lib.upc_comm_destroy(c)
 
 
+def test_pipelined_halves_of_the_sharded_step_equal_the_one_call_form(oracle, simulators):
+    """upc_sharded_edge_batch_simulate / _finish: batch k + 1 simulated on stream A while batch k is clustered (and exchanged) on
+    stream B, two outcome buffers, one host thread - what bench.py times.  Six batches with different seeds in flight back to back
+    must each equal upc_sharded_edge_batch issued alone."""
+    import torch
+    lib = abi.load_library()
+    E, P = 40, 96
+    sc = scenarios.c5_batch(edges=E, particles=P, num_steps=32)
+    cp = cases._cparams(abi.FEATURE_CRS, 0.125, 0.1)
+    sim = simulators("c5_pipe", sc["env"], sc["robot"])
+    handles = (C.c_void_p * 1)(sim.handle.value)
+    comms = (C.c_void_p * 1)()
+    abi.check(lib.upc_comm_create_all(1, handles, comms))
+    comm = C.c_void_p(comms[0])
+    try:
+        width = sim.robot.width
+        lay = abi.outcome_layout(width, E * P, E)
+        dev = torch.device("cuda", 0)
+        d_s = torch.from_numpy(np.ascontiguousarray(sc["starts"][::P].T)).to(dev)
+        d_t = torch.from_numpy(np.ascontiguousarray(sc["targets"][::P].T)).to(dev)
+        K = 6
+        want = []
+        ref = torch.zeros(lay.block_bytes, dtype=torch.uint8, device=dev)
+        for k in range(K):
+            abi.check(lib.upc_sharded_edge_batch(comm, C.byref(sc["params"]), C.byref(cp), 900 + k, E, P, d_s.data_ptr(), d_t.data_ptr(), ref.data_ptr(), None))
+            abi.check(lib.upc_comm_synchronize(comm))
+            torch.cuda.synchronize()
+            want.append(ref.cpu().numpy().copy())
+        A, B = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        bufs = [torch.zeros(lay.block_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+        ev_sim = [torch.cuda.Event() for _ in range(2)]
+        ev_done = [torch.cuda.Event() for _ in range(2)]
+        got = [None] * K
+
+        def finish(k):
+            B.wait_event(ev_sim[k % 2])
+            abi.check(lib.upc_sharded_edge_batch_finish(comm, C.byref(cp), E, P, bufs[k % 2].data_ptr(), B.cuda_stream))
+            ev_done[k % 2].record(B)
+
+        for k in range(K):
+            if k >= 2:
+                ev_done[k % 2].synchronize()                      # batch k - 2 is complete: read it back before its buffer is reused
+                got[k - 2] = bufs[k % 2].cpu().numpy().copy()
+                A.wait_event(ev_done[k % 2])
+                abi.check(lib.upc_comm_wait(comm, A.cuda_stream))
+            abi.check(lib.upc_sharded_edge_batch_simulate(comm, C.byref(sc["params"]), 900 + k, E, P, d_s.data_ptr(), d_t.data_ptr(), bufs[k % 2].data_ptr(),
+                                                          A.cuda_stream))
+            ev_sim[k % 2].record(A)
+            if k >= 1:
+                finish(k - 1)
+        finish(K - 1)
+        torch.cuda.synchronize()
+        abi.check(lib.upc_comm_synchronize(comm))
+        got[K - 2] = bufs[(K - 2) % 2].cpu().numpy().copy()
+        got[K - 1] = bufs[(K - 1) % 2].cpu().numpy().copy()
+        n = E * P
+        for k in range(K):
+            for off, size in ((lay.configs_offset, 8 * width * n), (lay.collided_offset, n), (lay.labels_offset, 4 * n), (lay.n_clusters_offset, 4 * E)):
+                assert np.array_equal(got[k][off:off + size], want[k][off:off + size]), (k, off)
+        assert not np.array_equal(want[0][lay.configs_offset:lay.configs_offset + 64], want[1][lay.configs_offset:lay.configs_offset + 64])
+    finally:
+        lib.upc_comm_destroy(comm)
+
+
 # ------------------------------------------------------------------ BASELINE.json sizes
 
 def test_full_size_c3_subsample_matches_oracle(oracle, simulators):

@@ -1474,10 +1474,15 @@ constexpr int64_t kFusedPropagateMax = 8192;
 __global__ void __launch_bounds__(1024) propagate_fused_kernel(const uint32_t* __restrict__ adj, int64_t set_size, int wpr,
                                                                const int32_t* __restrict__ set_bad, int32_t* __restrict__ comp)
 {
+    /* the labels of the set live in shared memory while they are iterated (the sweeps chase them through dependent loads: ~ 30
+     * cycles each here against an L2 round trip per hop in global memory) and are written back once */
+    extern __shared__ int32_t s_labels[];
     __shared__ int s_changed;
     const int64_t set = blockIdx.x;
     if (!set_bad[set]) return;
-    volatile int32_t* sc = comp + set * set_size;
+    int32_t* gc = comp + set * set_size;
+    volatile int32_t* sc = s_labels;
+    for (int64_t i = threadIdx.x; i < set_size; i += blockDim.x) s_labels[i] = gc[i];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
     while (true)
     {
@@ -1513,6 +1518,7 @@ __global__ void __launch_bounds__(1024) propagate_fused_kernel(const uint32_t* _
         __syncthreads();
         if (!s_changed) break;
     }
+    for (int64_t i = threadIdx.x; i < set_size; i += blockDim.x) gc[i] = s_labels[i];
 }
 
 /* ------------------------------------------------------------------ per-cluster statistics */
@@ -1909,7 +1915,7 @@ static int32_t cluster_pass(upc_handle* h, const PassInput& in, int64_t n_sets, 
     UPC_NULLCHECK(d_flag);
     if (set_size <= kFusedPropagateMax)
     {
-        propagate_fused_kernel<<<(unsigned)n_sets, 1024, 0, stream>>>(adj, set_size, wpr, set_bad, comp);
+        propagate_fused_kernel<<<(unsigned)n_sets, 1024, (size_t)set_size * sizeof(int32_t), stream>>>(adj, set_size, wpr, set_bad, comp);
         h->stats.kernel_launches++;
         UPC_CUDA_TRY(cudaGetLastError());
     }

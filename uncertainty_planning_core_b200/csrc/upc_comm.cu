@@ -314,11 +314,10 @@ int32_t upc_comm_synchronize(upc_comm* c)
  * (replicated on every rank, device memory).  d_blocks: world * layout.block_bytes bytes with
  * layout = upc_outcome_layout_for(width, max shard particles, max shard edges).  Asynchronous; see upc_comm_all_gather_outcomes.
  */
-static int32_t sharded_local(upc_comm* c, const upc_sim_params* params, const upc_cluster_params* cparams, uint64_t seed, int64_t n_edges,
-                             int64_t particles_per_edge, const double* d_edge_starts, const double* d_edge_targets, void* d_blocks, void* stream,
-                             upc_outcome_layout* lay)
+static int32_t sharded_simulate(upc_comm* c, const upc_sim_params* params, uint64_t seed, int64_t n_edges, int64_t particles_per_edge,
+                                const double* d_edge_starts, const double* d_edge_targets, void* d_blocks, void* stream, upc_outcome_layout* lay)
 {
-    if (!c || !params || !cparams || !d_edge_starts || !d_edge_targets || !d_blocks) return fail_comm("null argument");
+    if (!c || !params || !d_edge_starts || !d_edge_targets || !d_blocks) return fail_comm("null argument");
     if (n_edges < 1 || particles_per_edge < 1) return fail_comm("n_edges and particles_per_edge must be >= 1");
     upc_handle* h = c->h;
     const int width = upc_config_width(h->robot.kind, h->robot.dof);
@@ -338,12 +337,37 @@ static int32_t sharded_local(upc_comm* c, const upc_sim_params* params, const up
                                    (size_t)e * sizeof(double), (size_t)width, cudaMemcpyDeviceToDevice, s));
     UPC_CUDA_TRY(cudaMemcpy2DAsync(h->st_targets.ptr, (size_t)e * sizeof(double), d_edge_targets + lo, (size_t)n_edges * sizeof(double),
                                    (size_t)e * sizeof(double), (size_t)width, cudaMemcpyDeviceToDevice, s));
-    int32_t rc = upc_forward_simulate_seeded_device(h, params, seed, lo * particles_per_edge, n, e, (const double*)h->st_starts.ptr, e,
-                                                    (const double*)h->st_targets.ptr, (double*)(block + lay->configs_offset),
-                                                    block + lay->collided_offset, s);
-    if (rc != UPC_OK) return rc;
-    return upc_cluster_particles_device(h, cparams, e, particles_per_edge, (const double*)(block + lay->configs_offset),
+    return upc_forward_simulate_seeded_device(h, params, seed, lo * particles_per_edge, n, e, (const double*)h->st_starts.ptr, e,
+                                              (const double*)h->st_targets.ptr, (double*)(block + lay->configs_offset),
+                                              block + lay->collided_offset, s);
+}
+
+static int32_t sharded_cluster(upc_comm* c, const upc_cluster_params* cparams, int64_t n_edges, int64_t particles_per_edge, void* d_blocks, void* stream,
+                               upc_outcome_layout* lay)
+{
+    if (!c || !cparams || !d_blocks) return fail_comm("null argument");
+    if (n_edges < 1 || particles_per_edge < 1) return fail_comm("n_edges and particles_per_edge must be >= 1");
+    upc_handle* h = c->h;
+    const int width = upc_config_width(h->robot.kind, h->robot.dof);
+    int64_t lo, hi;
+    upc_shard_bounds(n_edges, c->rank, c->world, &lo, &hi);
+    const int64_t cap_edges = (n_edges + c->world - 1) / c->world;
+    upc_outcome_layout_for(width, cap_edges * particles_per_edge, cap_edges, lay);
+    uint8_t* block = (uint8_t*)d_blocks + (size_t)c->rank * (size_t)lay->block_bytes;
+    if (hi == lo) return UPC_OK;
+    UPC_CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+    return upc_cluster_particles_device(h, cparams, hi - lo, particles_per_edge, (const double*)(block + lay->configs_offset),
                                         (int32_t*)(block + lay->labels_offset), (int32_t*)(block + lay->n_clusters_offset), s);
+}
+
+static int32_t sharded_local(upc_comm* c, const upc_sim_params* params, const upc_cluster_params* cparams, uint64_t seed, int64_t n_edges,
+                             int64_t particles_per_edge, const double* d_edge_starts, const double* d_edge_targets, void* d_blocks, void* stream,
+                             upc_outcome_layout* lay)
+{
+    const int32_t rc = sharded_simulate(c, params, seed, n_edges, particles_per_edge, d_edge_starts, d_edge_targets, d_blocks, stream, lay);
+    if (rc != UPC_OK) return rc;
+    return sharded_cluster(c, cparams, n_edges, particles_per_edge, d_blocks, stream, lay);
 }
 
 int32_t upc_sharded_edge_batch(upc_comm* c, const upc_sim_params* params, const upc_cluster_params* cparams, uint64_t seed,
@@ -352,6 +376,30 @@ int32_t upc_sharded_edge_batch(upc_comm* c, const upc_sim_params* params, const 
 {
     upc_outcome_layout lay;
     const int32_t rc = sharded_local(c, params, cparams, seed, n_edges, particles_per_edge, d_edge_starts, d_edge_targets, d_blocks, stream, &lay);
+    if (rc != UPC_OK) return rc;
+    return all_gather_blocks(1, &c, &d_blocks, lay.block_bytes, &stream);
+}
+
+/*
+ * The two halves of upc_sharded_edge_batch as separate calls, for callers that pipeline batches: the simulation of batch k + 1
+ * (stream A, fills the machine) overlaps the clustering and the exchange of batch k (stream B: a handful of small, latency-bound
+ * launches and the host decisions between them).  upc_sharded_edge_batch_simulate is asynchronous and never waits on the host;
+ * upc_sharded_edge_batch_finish clusters this rank's block on `stream` - the caller orders it after the simulation of the same
+ * batch with an event - and issues the all-gather behind it.  The two calls of one handle touch disjoint device state (simulation:
+ * edge staging + counters; clustering: its workspace), so batch k + 1 may be simulated while batch k is finished, from ONE host
+ * thread.  d_blocks of batches in flight must be distinct buffers.
+ */
+int32_t upc_sharded_edge_batch_simulate(upc_comm* c, const upc_sim_params* params, uint64_t seed, int64_t n_edges, int64_t particles_per_edge,
+                                        const double* d_edge_starts, const double* d_edge_targets, void* d_blocks, void* stream)
+{
+    upc_outcome_layout lay;
+    return sharded_simulate(c, params, seed, n_edges, particles_per_edge, d_edge_starts, d_edge_targets, d_blocks, stream, &lay);
+}
+
+int32_t upc_sharded_edge_batch_finish(upc_comm* c, const upc_cluster_params* cparams, int64_t n_edges, int64_t particles_per_edge, void* d_blocks, void* stream)
+{
+    upc_outcome_layout lay;
+    const int32_t rc = sharded_cluster(c, cparams, n_edges, particles_per_edge, d_blocks, stream, &lay);
     if (rc != UPC_OK) return rc;
     return all_gather_blocks(1, &c, &d_blocks, lay.block_bytes, &stream);
 }
