@@ -366,7 +366,9 @@ class DeviceBatch:
         self.d_targets = torch.from_numpy(np.ascontiguousarray(wl["edge_targets"].T)).to(self.dev)
         self.blocks = [torch.zeros(self.lay.block_bytes * world, dtype=torch.uint8, device=self.dev) for _ in range(2)]
         self.stream_obj = torch.cuda.Stream(device=self.dev)        # A: simulation
-        self.stream_b_obj = torch.cuda.Stream(device=self.dev)      # B: clustering + exchange of the batch before
+        # B: clustering + exchange of the batch before.  High priority: the simulation kernel holds every register of every SM, and the
+        # clustering's small CTAs must get the slots that free up as simulation CTAs retire instead of queueing behind the whole launch
+        self.stream_b_obj = torch.cuda.Stream(device=self.dev, priority=-1)
         self.stream, self.stream_b = self.stream_obj.cuda_stream, self.stream_b_obj.cuda_stream
         assert self.stream != 0 and self.stream_b != 0
         self.ev_sim = [torch.cuda.Event() for _ in range(2)]        # simulation of the batch in buffer i has finished

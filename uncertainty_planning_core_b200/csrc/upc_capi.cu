@@ -260,7 +260,7 @@ int32_t upc_destroy(upc_handle* h)
     cudaFree(h->d_cells);
     cudaFree(h->d_points);
     cudaFree(h->d_counters);
-    DeviceBuffer* bufs[] = {&h->user[0], &h->user[1], &h->user[2], &h->user[3], &h->st_trace, &h->st_records, &h->st_starts, &h->st_targets, &h->st_tape, &h->st_out, &h->st_coll, &h->st_labels, &h->st_ncl, &h->st_carry,
+    DeviceBuffer* bufs[] = {&h->user[0], &h->user[1], &h->user[2], &h->user[3], &h->st_trace, &h->st_records, &h->st_order, &h->st_starts, &h->st_targets, &h->st_tape, &h->st_out, &h->st_coll, &h->st_labels, &h->st_ncl, &h->st_carry,
                             &h->cw.features, &h->cw.adjacency, &h->cw.roots, &h->cw.comp, &h->cw.flags, &h->cw.signatures,
                             &h->cw.frames, &h->cw.dist_matrix, &h->cw.members, &h->cw.link_scratch, &h->cw.misc, &h->cw.hash, &h->cw.dedupe, &h->cw.usig, &h->cw.uroot, &h->cw.comp_list, &h->cw.comp_feat};
     for (DeviceBuffer* b : bufs) b->release();

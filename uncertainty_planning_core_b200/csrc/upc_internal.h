@@ -69,7 +69,7 @@ struct upc_handle
     upc_stats stats{};
     int64_t phase_cycles[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     /* staging for the host-pointer entry points */
-    upc::DeviceBuffer st_starts, st_targets, st_tape, st_out, st_coll, st_labels, st_ncl, st_carry, st_trace, st_records;
+    upc::DeviceBuffer st_starts, st_targets, st_tape, st_out, st_coll, st_labels, st_ncl, st_carry, st_trace, st_records, st_order;
     upc::DeviceBuffer user[4]; /* upc_device_scratch */
     cudaStream_t copy_stream = nullptr; /* tape slices of the host-pointer entry point */
     cudaEvent_t copy_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

@@ -48,6 +48,48 @@ int choose_lanes(const upc_handle* h, int64_t n)
 }
 
 /* tape == nullptr selects the seeded kernels (sp.seed / sp.first_particle) */
+/*
+ * Heavy-first schedule of an edge batch.  Edges that start or end near an obstacle are the ones whose particles go through contact
+ * resolution - several times the work of a free-space edge - and CTAs are scheduled in launch order, so a contact-heavy edge at the
+ * end of the launch drains the machine at its own pace (a 512-edge shard of C5: 11.9 ms in natural order, 10.0 ms with the edges
+ * sorted by the clearance of their end points; 4,096 edges: 77.5 -> 75 ms).  Key = the smaller SDF value at the body origin of the
+ * edge's start and target (nearest voxel), in cells, 64 buckets; one CTA: histogram, scan, scatter.  The order inside a bucket is
+ * whatever the atomics give - it only affects WHEN an edge is simulated, never its result.
+ */
+__global__ void __launch_bounds__(1024) edge_order_kernel(const DevEnv env, int position_offset, int64_t E, const double* __restrict__ starts,
+                                                          const double* __restrict__ targets, int32_t* __restrict__ order)
+{
+    __shared__ int s_count[64];
+    __shared__ int s_off[64];
+    if (threadIdx.x < 64) s_count[threadIdx.x] = 0;
+    __syncthreads();
+    auto bucket = [&](int64_t e) {
+        float key = INFINITY;
+        for (int end = 0; end < 2; end++)
+        {
+            const double* c = end ? targets : starts;
+            const double px = c[(int64_t)(position_offset + 0) * E + e], py = c[(int64_t)(position_offset + 1) * E + e];
+            const double pz = (position_offset == 0) ? 0.0 : c[(int64_t)(position_offset + 2) * E + e];
+            double u[3];
+            xf_point(env.G, px, py, pz, u);
+            int ix = (int)floor(u[0] * env.inv_res), iy = (int)floor(u[1] * env.inv_res), iz = (int)floor(u[2] * env.inv_res);
+            ix = max(0, min(ix, env.nx - 1)); iy = max(0, min(iy, env.ny - 1)); iz = max(0, min(iz, env.nz - 1));
+            key = fminf(key, env.sdf[((int64_t)ix * env.ny + iy) * env.nz + iz]);
+        }
+        const float cells = key * (float)env.inv_res;
+        return (cells > 0.0f) ? min((int)cells, 63) : 0;
+    };
+    for (int64_t e = threadIdx.x; e < E; e += blockDim.x) atomicAdd(&s_count[bucket(e)], 1);
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        int run = 0;
+        for (int b = 0; b < 64; b++) { s_off[b] = run; run += s_count[b]; }
+    }
+    __syncthreads();
+    for (int64_t e = threadIdx.x; e < E; e += blockDim.x) order[atomicAdd(&s_off[bucket(e)], 1)] = (int32_t)e;
+}
+
 cudaError_t launch_forward_simulate(upc_handle* h, const DevSim& sp, int64_t n, const double* starts, int64_t n_targets,
                                     const double* targets, const double* tape, double* out_configs, uint8_t* out_collided,
                                     cudaStream_t stream)
@@ -64,8 +106,25 @@ cudaError_t launch_forward_simulate(upc_handle* h, const DevSim& sp, int64_t n, 
     a.out_configs = out_configs;
     a.out_collided = out_collided;
     a.counters = h->d_counters;
+    a.edge_order = nullptr;
+    a.edge_particles = 1;
     const int lanes = choose_lanes(h, n);
     const bool seeded = (tape == nullptr);
+    {
+        /* edge batch in one launch (one start and one target per block of particles), free-flying robot: heavy edges first
+         * (UPC_B200_NO_EDGE_ORDER=1: natural order) */
+        static const bool off = []() { const char* e = getenv("UPC_B200_NO_EDGE_ORDER"); return e != nullptr && e[0] == '1'; }();
+        const int64_t E = sp.n_starts;
+        if (!off && seeded && h->robot.kind != UPC_ROBOT_LINKED && E >= 8 && E == n_targets && sp.per_start > 1 && sp.per_start == sp.per_target &&
+            E * sp.per_start == n && E < ((int64_t)1 << 31) && sp.step_begin == 0 && sp.step_end >= sp.num_steps && sp.trace_configs == nullptr)
+        {
+            if (h->st_order.reserve((size_t)E * sizeof(int32_t)) != cudaSuccess) return cudaErrorMemoryAllocation;
+            edge_order_kernel<<<1, 1024, 0, stream>>>(h->env, (h->robot.kind == UPC_ROBOT_SE3) ? 9 : 0, E, starts, targets, (int32_t*)h->st_order.ptr);
+            h->stats.kernel_launches++;
+            a.edge_order = (const int32_t*)h->st_order.ptr;
+            a.edge_particles = sp.per_start;
+        }
+    }
     switch (h->robot.kind)
     {
         case UPC_ROBOT_SE2: return launch_sim_se2(a, lanes, seeded, stream);

@@ -32,6 +32,10 @@ struct SimArgs
     double* out_configs;
     uint8_t* out_collided;
     DevCounters* counters;
+    /* edge batches (one start / target per block of edge_particles particles): the order in which the blocks are worked through.
+     * Slot j of the launch simulates edge edge_order[j]; results land where they always do.  NULL = natural order. */
+    const int32_t* edge_order;
+    int64_t edge_particles;
 };
 
 /* lanes: 1, 2, 3, 4, 5, 6, 8, 16 or 32 lanes per particle; seeded: draws from the counter-based generator instead of a.tape */

@@ -92,7 +92,13 @@ __global__ void __launch_bounds__((sim_block<M, G>()), (sim_min_blocks<M, G>()))
      * do, so that every thread of the CTA meets the same per-interval barrier (simulate_particle: exists); their scratch is the
      * spare slot behind the CTA's particles */
     const bool exists = lane_used && (i_raw < a.n);
-    const int64_t i = exists ? i_raw : 0;
+    int64_t i = exists ? i_raw : 0;
+    if (a.edge_order != nullptr && exists)
+    {
+        /* heavy-first schedule of an edge batch: this slot's edge is edge_order[slot / P] */
+        const int64_t slot_edge = i_raw / a.edge_particles;
+        i = (int64_t)a.edge_order[slot_edge] * a.edge_particles + (i_raw - slot_edge * a.edge_particles);
+    }
     const int particle_in_block = exists ? particle_slot : kParticlesPerBlock;
     LocalCounters lc = {};
     bool collided = false;
