@@ -44,6 +44,7 @@ def emulation():
         lib.emulate_set_fp32_cull.argtypes = [C.c_int]
         lib.emulate_set_link_cull.argtypes = [C.c_int]
         lib.emulate_set_group_cull.argtypes = [C.c_int]
+        lib.emulate_set_shared_masks.argtypes = [C.c_int]
         lib.emulate_group_cull_check.argtypes = [C.POINTER(abi.EnvDesc), C.POINTER(abi.RobotDesc), i64, vp, C.c_double, vp]
         lib.emulate_group_cull_check.restype = C.c_int
         lib.emulate_cull_check.argtypes = [C.POINTER(abi.EnvDesc), C.POINTER(abi.RobotDesc), i64, vp, C.c_double, vp]
@@ -74,7 +75,7 @@ def emulate_group_cull_check(env, robot, frames, threshold):
     return tuple(int(c) for c in counts)
 
 
-def emulate_forward_simulate(env, robot, params, starts, targets, tape, corner_cells=True, fp32_cull=True, link_cull=True, group_cull=True):
+def emulate_forward_simulate(env, robot, params, starts, targets, tape, corner_cells=True, fp32_cull=True, link_cull=True, group_cull=True, shared_masks=True):
     """The product's per-thread program run on the CPU with one lane per particle.
     corner_cells selects the SDF layout the collision passes read (corner-cell table vs plain grid + cell-minimum cull);
     fp32_cull switches the single-precision pre-cull of the point passes."""
@@ -82,6 +83,7 @@ def emulate_forward_simulate(env, robot, params, starts, targets, tape, corner_c
     emulation().emulate_set_fp32_cull(1 if fp32_cull else 0)
     emulation().emulate_set_link_cull(1 if link_cull else 0)
     emulation().emulate_set_group_cull(1 if group_cull else 0)
+    emulation().emulate_set_shared_masks(1 if shared_masks else 0)
     starts = np.asarray(starts, dtype=np.float64)
     targets = np.asarray(targets, dtype=np.float64)
     n = starts.shape[0]

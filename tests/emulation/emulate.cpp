@@ -75,6 +75,9 @@ static void fill_robot(const upc_robot_desc* r, DevRobot* d)
     }
 }
 
+static int g_use_shared_masks = 1;
+extern "C" void emulate_set_shared_masks(int on) { g_use_shared_masks = on; }
+
 template <class M>
 static void run(const DevEnv& env, const DevRobot& rob, const DevSim& sp, int64_t n, const double* starts, int64_t n_targets,
                 const double* targets, const double* tape, double* out, uint8_t* coll, int64_t* counters)
@@ -86,8 +89,10 @@ static void run(const DevEnv& env, const DevRobot& rob, const DevSim& sp, int64_
     {
         LocalCounters lc = {};
         bool c = false;
-        if (seeded) simulate_particle<M, 1, true>(env, rob, sp, g, i, n, starts, n_targets, targets, tape, out, coll, rob.pts, f0.data(), f1.data(), park.data(), lc, c);
-        else simulate_particle<M, 1, false>(env, rob, sp, g, i, n, starts, n_targets, targets, tape, out, coll, rob.pts, f0.data(), f1.data(), park.data(), lc, c);
+        unsigned masks[kMaxMaskChunks]; /* shared pre-cull masks of the collision check and the resolver pass behind it */
+        unsigned* mp = g_use_shared_masks ? masks : nullptr;
+        if (seeded) simulate_particle<M, 1, true>(env, rob, sp, g, i, n, starts, n_targets, targets, tape, out, coll, rob.pts, f0.data(), f1.data(), park.data(), lc, c, true, mp, 1);
+        else simulate_particle<M, 1, false>(env, rob, sp, g, i, n, starts, n_targets, targets, tape, out, coll, rob.pts, f0.data(), f1.data(), park.data(), lc, c, true, mp, 1);
         counters[0] += lc.particle_steps; counters[1] += c ? 1 : 0; counters[2] += lc.resolver_iterations; counters[3] += lc.failed_resolves;
     }
 }

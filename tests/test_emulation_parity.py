@@ -10,7 +10,7 @@ from uncertainty_planning_core_b200 import scenarios
 from uncertainty_planning_core_b200 import abi
 
 
-@pytest.mark.parametrize("culls", ["all", "no_fp32", "no_link", "no_group", "group_only", "none"])
+@pytest.mark.parametrize("culls", ["all", "no_fp32", "no_link", "no_group", "group_only", "no_shared_masks", "none"])
 @pytest.mark.parametrize("corner_cells", [True, False])
 @pytest.mark.parametrize("name", sorted(cases.GOLDEN_SIM_CASES))
 def test_device_program_matches_oracle(oracle, name, corner_cells, culls):
@@ -20,8 +20,10 @@ def test_device_program_matches_oracle(oracle, name, corner_cells, culls):
     tape = abi.fill_noise_tape(sc["seed"], sc["robot"], sc["params"], n)
     ocfg, ocoll, ostats = oracle.forward_simulate(sc["env"], sc["robot"], sc["params"], sc["starts"], sc["targets"], tape)
     ecfg, ecoll, estats = emulate_forward_simulate(sc["env"], sc["robot"], sc["params"], sc["starts"], sc["targets"], tape, corner_cells,
-                                                   fp32_cull=culls in ("all", "no_link", "no_group"), link_cull=culls in ("all", "no_fp32", "no_group"),
-                                                   group_cull=culls in ("all", "no_fp32", "no_link", "group_only"))
+                                                   fp32_cull=culls in ("all", "no_link", "no_group", "no_shared_masks"),
+                                                   link_cull=culls in ("all", "no_fp32", "no_group", "no_shared_masks"),
+                                                   group_cull=culls in ("all", "no_fp32", "no_link", "group_only", "no_shared_masks"),
+                                                   shared_masks=culls != "no_shared_masks")
     assert np.array_equal(ocoll, ecoll)
     assert max_ulp_diff(ocfg, ecfg) == 0
     for k in cases.SIM_STAT_KEYS:

@@ -652,14 +652,30 @@ int32_t upc_simulate_and_cluster_edges(upc_handle* h, const upc_sim_params* para
     if (n_starts != n_edges && n_starts != n) return fail_arg("starts must hold one configuration per edge or one per particle");
     int32_t rc = seeded_from_host(h, params, seed, first_particle, n, n_starts, edge_starts, n_edges, edge_targets);
     if (rc != UPC_OK) return rc;
+    /* the configurations and collision flags (five sixths of what goes back to the host) are final once the simulation has run:
+     * they travel on the copy stream while the outcome is clustered */
+    if (!h->copy_stream)
+    {
+        UPC_CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        for (int c = 0; c < 8; c++) UPC_CUDA_TRY(cudaEventCreateWithFlags(&h->copy_done[c], cudaEventDisableTiming));
+        UPC_CUDA_TRY(cudaEventCreateWithFlags(&h->compute_done, cudaEventDisableTiming));
+    }
+    const size_t cfg_bytes = (size_t)upc_config_width(h->robot.kind, h->robot.dof) * (size_t)n * sizeof(double);
+    UPC_CUDA_TRY(cudaEventRecord(h->compute_done, h->stream));
+    UPC_CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->compute_done, 0));
+    UPC_CUDA_TRY(cudaMemcpyAsync(out_configs, h->st_out.ptr, cfg_bytes, cudaMemcpyDeviceToHost, h->copy_stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(out_collided, h->st_coll.ptr, (size_t)n, cudaMemcpyDeviceToHost, h->copy_stream));
+    UPC_CUDA_TRY(cudaEventRecord(h->copy_done[0], h->copy_stream));
     UPC_CUDA_TRY(h->st_labels.reserve((size_t)n * sizeof(int32_t)));
     UPC_CUDA_TRY(h->st_ncl.reserve((size_t)n_edges * sizeof(int32_t) + 64));
     rc = upc_cluster_particles_device(h, cparams, n_edges, particles_per_edge, (const double*)h->st_out.ptr, (int32_t*)h->st_labels.ptr,
                                       (int32_t*)h->st_ncl.ptr, h->stream);
-    if (rc != UPC_OK) return rc;
-    const size_t cfg_bytes = (size_t)upc_config_width(h->robot.kind, h->robot.dof) * (size_t)n * sizeof(double);
-    UPC_CUDA_TRY(cudaMemcpyAsync(out_configs, h->st_out.ptr, cfg_bytes, cudaMemcpyDeviceToHost, h->stream));
-    UPC_CUDA_TRY(cudaMemcpyAsync(out_collided, h->st_coll.ptr, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    if (rc != UPC_OK)
+    {
+        cudaStreamSynchronize(h->copy_stream); /* the caller's buffers must not be written after the call returns */
+        return rc;
+    }
+    UPC_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->copy_done[0], 0));
     UPC_CUDA_TRY(cudaMemcpyAsync(out_labels, h->st_labels.ptr, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     UPC_CUDA_TRY(cudaMemcpyAsync(out_n_clusters, h->st_ncl.ptr, (size_t)n_edges * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     h->stats.d2h_bytes += (int64_t)(cfg_bytes + (size_t)n * 5 + (size_t)n_edges * 4);

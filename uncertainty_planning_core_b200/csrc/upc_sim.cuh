@@ -203,10 +203,35 @@ UPC_D void refresh_frames(const DevRobot& r, M& m, const Group<G>& g)
  * flight together - and records the undecided ones in a bit mask; only those get the exact trilinear evaluation,
  * kCheckInFlight at a time.  The result (an OR over points) does not depend on the order.
  */
+/*
+ * Sharing the pre-cull between the collision check and the resolver pass that follows it.  When a check finds a collision the
+ * resolver's point pass runs on the SAME configuration, and its pre-cull differs from the check's only in the threshold
+ * (resolve_distance >= contact_distance).  With share_threshold > 0 the check therefore runs its link-level and per-point culls at
+ * that larger threshold - a superset of the points it needs itself, the exact evaluation still decides at `threshold` - and leaves
+ * the undecided masks (one word per chunk of 32 * G points, links in order) in `masks`; they are exactly the masks the resolver's
+ * own cull would compute, so the resolver skips it.  *masks_state = number of words written, -1 = not recorded (a link took a path
+ * without the pre-cull, or more than kMaxMaskChunks words).
+ */
+constexpr int kMaxMaskChunks = 8;
+#ifndef UPC_SHARE_MASKS
+#define UPC_SHARE_MASKS 1
+#endif
+
+/* the programs whose resolver pass runs the single-precision pre-cull (and can therefore take it from the check before it) */
 template <class M, int G>
-UPC_D bool check_collision(const DevEnv& env, const DevRobot& r, const M& m, const Group<G>& g, const double* pts, double threshold)
+UPC_D constexpr bool shares_cull_masks()
+{
+    return UPC_SHARE_MASKS && UPC_RES_PRECULL && (G >= resolver_precull_min_lanes<M>()) && (G <= 8);
+}
+
+template <class M, int G>
+UPC_D bool check_collision(const DevEnv& env, const DevRobot& r, const M& m, const Group<G>& g, const double* pts, double threshold,
+                           double share_threshold = -1.0, unsigned* masks = nullptr, int mask_stride = 0, int* masks_state = nullptr)
 {
     bool hit = false;
+    const bool rec = (masks != nullptr) && (share_threshold >= threshold);
+    bool rec_ok = rec;
+    int rec_n = 0;
     for (int l = 0; l < r.num_links; l++)
     {
         const int beg = r.link_off[l], end = r.link_off[l + 1];
@@ -217,8 +242,20 @@ UPC_D bool check_collision(const DevEnv& env, const DevRobot& r, const M& m, con
         /* single-precision clear threshold: (largest radius of the link + threshold + margin) rounded up - conservative for
          * every point of the link, so it never changes a result */
         const float clear_above = float_round_up((r.link_radius[l] + threshold) + UPC_CULL_MARGIN);
+        /* the culls run at the shared (larger) threshold when their masks are recorded for the resolver */
+        const float clear_cull = rec ? float_round_up((r.link_radius[l] + share_threshold) + UPC_CULL_MARGIN) : clear_above;
+        const int link_chunks = (end - beg + 32 * G - 1) / (32 * G);
         /* link-level cull: one lookup of the dilated cell minimum clears the whole link when it is far from every obstacle */
-        if (link_certainly_clear(env, r, l, V, clear_above)) continue;
+        if (link_certainly_clear(env, r, l, V, clear_cull))
+        {
+            if (rec_ok)
+            {
+                if (rec_n + link_chunks > kMaxMaskChunks) rec_ok = false;
+                else
+                    for (int c = 0; c < link_chunks; c++) masks[(rec_n++) * mask_stride] = 0u;
+            }
+            continue;
+        }
         if (env.cells != nullptr)
         {
             /* corner-cell table: one sector per point decides (and, if needed, evaluates) it */
@@ -226,16 +263,18 @@ UPC_D bool check_collision(const DevEnv& env, const DevRobot& r, const M& m, con
             {
                 /* enough points per lane for full batches: single-precision pre-cull against the 4-byte cell minimum
                  * first (UPC_CULL_INFLIGHT lookups in flight), exact FP64 evaluation of the undecided points only */
-                const CullFrame cf = cull_frame<M::PLANAR>(env, r, l, V, r.cull_delta, clear_above);
+                const CullFrame cf = cull_frame<M::PLANAR>(env, r, l, V, r.cull_delta, clear_cull);
                 const CullPoint* ptsf = reinterpret_cast<const CullPoint*>(pts + 4 * r.num_points);
+                if (rec_ok && rec_n + link_chunks > kMaxMaskChunks) rec_ok = false;
                 for (int chunk = beg; chunk < end; chunk += 32 * G)
                 {
                     const int first = chunk + g.sub;
                     const int lim = (end < chunk + 32 * G) ? end : (chunk + 32 * G);
                     /* group-level cull (one-lane programs): only the points of groups that are not provably clear go on */
                     unsigned group_mask = 0xffffffffu;
-                    if constexpr (G == 1) group_mask = group_candidates(env, r, l, (chunk - beg) >> 5, V, clear_above);
+                    if constexpr (G == 1) group_mask = group_candidates(env, r, l, (chunk - beg) >> 5, V, clear_cull);
                     unsigned undecided = cull_undecided<M::PLANAR>(env, cf, ptsf, first, lim, G, group_mask);
+                    if (rec_ok) masks[(rec_n++) * mask_stride] = undecided;
                     while (undecided)
                     {
                         int kk[kCheckInFlight];
@@ -276,6 +315,7 @@ UPC_D bool check_collision(const DevEnv& env, const DevRobot& r, const M& m, con
                 }
                 continue;
             }
+            rec_ok = false; /* this link is checked without the pre-cull: nothing to share */
             int k = beg + g.sub;
             /* four lookups in flight per trip: locate all, load all, then evaluate */
             for (; k + 3 * G < end; k += 4 * G)
@@ -307,6 +347,7 @@ UPC_D bool check_collision(const DevEnv& env, const DevRobot& r, const M& m, con
             }
             continue;
         }
+        rec_ok = false; /* plain-grid path: its conservative test is not the resolver's pre-cull */
         for (int chunk = beg; chunk < end; chunk += 32 * G)
         {
             const int first = chunk + g.sub;
@@ -358,6 +399,7 @@ UPC_PLAIN_UNROLL_PRAGMA
             }
         }
     }
+    if (masks_state != nullptr) *masks_state = rec_ok ? rec_n : -1;
     return g.any(hit);
 }
 
@@ -402,8 +444,9 @@ UPC_ESTIMATE_LINKAGE double estimate_motion(const DevRobot& r, const M& m, const
  */
 template <class M, int G, bool INDIVIDUAL>
 UPC_RESOLVER_LINKAGE int resolver_correction(const DevEnv& env, const DevRobot& r, const DevSim& sp, const M& m_in, const Group<G>& g,
-                              const double* pts, double* x, LocalCounters& cnt)
+                              const double* pts, double* x, LocalCounters& cnt, const unsigned* shared_masks = nullptr, int mask_stride = 0)
 {
+    int shared_at = 0; /* next word of the masks the preceding collision check recorded (check_collision: share_threshold) */
     const double resolve_distance = sp.resolve_distance;
     const M m = m_in; /* private copy (when the function is compiled out of line the caller's model sits in memory) */
     UPC_T0
@@ -428,8 +471,21 @@ UPC_RESOLVER_LINKAGE int resolver_correction(const DevEnv& env, const DevRobot& 
         m.frame(r, l, T);
         voxel_from_link(env, T, V);
         const float clear_above = float_round_up((r.link_radius[l] + resolve_distance) + UPC_CULL_MARGIN);
+        if (shared_masks != nullptr)
+        {
+            /* the check before this pass already culled this configuration at resolve_distance: a link without candidates is done */
+            const int link_chunks = (end - beg + 32 * G - 1) / (32 * G);
+            unsigned any = 0u;
+            for (int c = 0; c < link_chunks; c++) any |= shared_masks[(shared_at + c) * mask_stride];
+            if (G > 1) any = g.any(any != 0u) ? 1u : 0u; /* the accumulation phase below is a group operation: all lanes or none */
+            if (any == 0u)
+            {
+                shared_at += link_chunks;
+                continue;
+            }
+        }
         /* link-level cull: a link farther than resolve_distance from every obstacle contributes nothing */
-        if (link_certainly_clear(env, r, l, V, clear_above)) continue;
+        else if (link_certainly_clear(env, r, l, V, clear_above)) continue;
         /* accumulate the contribution (b0, b1, b2) of body point kk of this link; called in ascending point order */
         auto accumulate = [&](int kk, double b0, double b1, double b2)
         {
@@ -500,9 +556,17 @@ UPC_RESOLVER_LINKAGE int resolver_correction(const DevEnv& env, const DevRobot& 
                      * candidates instead of one per point slot (some lane of the warp is near a surface at almost every slot).
                      * Compiled for 2..8 lanes only: measured C2 (4 lanes) 2.11 -> 2.03 ms, but the one-lane big-batch program
                      * (-3 %) and the 32-lane SE(2) program (+5 % on C1, where the pass never runs) lose by carrying it. */
-                    const CullFrame cf = cull_frame<M::PLANAR>(env, r, l, V, r.cull_delta, clear_above);
-                    const CullPoint* ptsf = reinterpret_cast<const CullPoint*>(pts + 4 * r.num_points);
-                    unsigned candidates = cull_undecided<M::PLANAR>(env, cf, ptsf, first, lim, G, group_mask);
+                    unsigned candidates;
+                    if (shared_masks != nullptr)
+                    {
+                        candidates = shared_masks[(shared_at++) * mask_stride];
+                    }
+                    else
+                    {
+                        const CullFrame cf = cull_frame<M::PLANAR>(env, r, l, V, r.cull_delta, clear_above);
+                        const CullPoint* ptsf = reinterpret_cast<const CullPoint*>(pts + 4 * r.num_points);
+                        candidates = cull_undecided<M::PLANAR>(env, cf, ptsf, first, lim, G, group_mask);
+                    }
                     while (candidates)
                     {
                         const int j = lowest_bit(candidates);
@@ -768,8 +832,13 @@ template <class M, int G, bool SEEDED>
 UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim& sp, const Group<G>& g, int64_t i, int64_t n,
                              const double* starts, int64_t n_targets, const double* targets, const double* tape,
                              double* out_configs, uint8_t* out_collided, const double* pts, double* frames0,
-                             double* frames1, double* park, LocalCounters& cnt, bool& collided_out, const bool exists = true)
+                             double* frames1, double* park, LocalCounters& cnt, bool& collided_out, const bool exists = true,
+                             unsigned* masks = nullptr, const int mask_stride = 0)
 {
+    /* masks: kMaxMaskChunks words per thread (stride mask_stride) for the pre-cull shared by a collision check and the resolver
+     * pass behind it; NULL = every pass culls for itself */
+    constexpr bool kShare = shares_cull_masks<M, G>();
+    int masks_state = -1;
     /* exists == false: a lane without a particle (tail of the batch, lanes a group size leaves over).  It runs the same control flow
      * on particle i (a valid index) with `finished` set from the start and writes nothing to global memory, so that every thread of
      * a CTA executes the SAME per-interval barrier instruction - an aligned barrier must not be reached divergently inside a warp. */
@@ -922,7 +991,10 @@ UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim&
             m.apply(r, apply_in, noise);
             refresh_frames(r, m, g);
             UPC_T1(2)
-            bool in_collision = check_collision(env, r, m, g, pts, sp.contact_distance);
+            /* one call site (the check is inlined: a second one would be a second copy of it in a program bound by instruction fetch) */
+            const bool share = kShare && (masks != nullptr) && (sp.allow_contacts != 0);
+            bool in_collision = check_collision(env, r, m, g, pts, sp.contact_distance, share ? sp.resolve_distance : -1.0, share ? masks : nullptr,
+                                                mask_stride, &masks_state);
             UPC_T1(3)
             bool revert = false;
             if (!resolving)
@@ -962,8 +1034,9 @@ UPC_D void simulate_particle(const DevEnv& env, const DevRobot& r, const DevSim&
             if (resolving && in_collision && !revert)
             {
                 /* next action: a resolver correction from the current configuration */
-                const int contributing = sp.individual_jacobians ? resolver_correction<M, G, true>(env, r, sp, m, g, pts, vec, cnt)
-                                                                 : resolver_correction<M, G, false>(env, r, sp, m, g, pts, vec, cnt);
+                const unsigned* shared = (kShare && masks_state >= 0) ? masks : nullptr;
+                const int contributing = sp.individual_jacobians ? resolver_correction<M, G, true>(env, r, sp, m, g, pts, vec, cnt, shared, mask_stride)
+                                                                 : resolver_correction<M, G, false>(env, r, sp, m, g, pts, vec, cnt, shared, mask_stride);
                 UPC_T1(4)
                 if (contributing == 0)
                 {

@@ -126,8 +126,12 @@ __global__ void __launch_bounds__((sim_block<M, G>()), (sim_min_blocks<M, G>()))
             frames0 = local_frames;
             frames1 = local_frames + frame_buffer_doubles<M, kFramesInShared>() / 2;
         }
+        /* per-thread words of the shared pre-cull masks, behind the scratch of the CTA's particles (and the spare slot) */
+        unsigned* masks = nullptr;
+        if constexpr (shares_cull_masks<M, G>())
+            masks = reinterpret_cast<unsigned*>(smem + npd + (size_t)(kParticlesPerBlock + 1) * (size_t)(2 * M::WIDTH + 2 * M::DOF + 2 * per)) + threadIdx.x;
         simulate_particle<M, G, SEEDED>(a.env, a.robot, a.sp, g, i, a.n, a.starts, a.n_targets, a.targets, a.tape, a.out_configs,
-                                a.out_collided, pts, frames0, frames1, park, lc, collided, exists);
+                                a.out_collided, pts, frames0, frames1, park, lc, collided, exists, masks, kBlock);
         if (g.sub == 0 && exists)
         {
             atomicAdd(&s_cnt[0], lc.particle_steps);
@@ -157,6 +161,7 @@ static cudaError_t launch_sim_impl(const SimArgs& a, cudaStream_t stream)
     const int64_t blocks = (a.n + particles_per_block - 1) / particles_per_block;
     size_t smem = (size_t)a.robot.num_points * kPointDoubles * sizeof(double);
     smem += (size_t)(particles_per_block + 1) * (2 * M::WIDTH + 2 * M::DOF + ((M::HAS_FRAMES && G >= 4) ? 2 * (size_t)a.robot.num_links * 12 : 0)) * sizeof(double);
+    if (shares_cull_masks<M, G>()) smem += (size_t)kBlock * kMaxMaskChunks * sizeof(unsigned); /* shared pre-cull masks, kMaxMaskChunks words per thread */
     if (smem + 256 > 48 * 1024) /* the kernel also has a few bytes of static shared memory */
     {
         cudaError_t e = cudaFuncSetAttribute(forward_simulate_kernel<M, G, SEEDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
