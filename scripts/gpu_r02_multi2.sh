@@ -4,10 +4,10 @@ N=${1:-2}
 TAG=${2:-r02q}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/${TAG}_gpus_$N.txt 2>&1
-timeout 300 python -m pytest tests/test_cpp_shim.py tests/test_gpu_seeded.py -x -q -m gpu -k "sharded" > gpurun_out/${TAG}_tests_$N.log 2>&1
+[ -n "$SKIP_TESTS" ] || timeout 300 python -m pytest tests/test_cpp_shim.py tests/test_gpu_seeded.py -x -q -m gpu -k "sharded or pipelined" > gpurun_out/${TAG}_tests_$N.log 2>&1
 echo "pytest exit $?" >> gpurun_out/${TAG}_tests_$N.log
 tail -3 gpurun_out/${TAG}_tests_$N.log
-for n in 1 2 4 8; do
+for n in ${NLIST:-1 2 4 8}; do
   if [ $n -le $N ]; then
     if [ $n -eq 1 ]; then
       timeout 300 python bench.py --gpus 1 --steps 10 --warmup 3 --no-also --no-plugin --no-cpu-baseline > gpurun_out/${TAG}_bench_${N}box_1.json 2> gpurun_out/${TAG}_bench_${N}box_1.err
