@@ -364,15 +364,19 @@ class DeviceBatch:
             self.comm = comm
         self.d_starts = torch.from_numpy(np.ascontiguousarray(wl["edge_starts"].T)).to(self.dev)
         self.d_targets = torch.from_numpy(np.ascontiguousarray(wl["edge_targets"].T)).to(self.dev)
-        self.blocks = [torch.zeros(self.lay.block_bytes * world, dtype=torch.uint8, device=self.dev) for _ in range(2)]
+        # outcome buffers: two on one GPU (simulate k + 1 while k is clustered); three with several GPUs, so that the exchange of batch
+        # k - 1 - a collective: it ends when the slowest rank has clustered - has a whole further step before its buffer is needed again
+        self.nbuf = 3 if world > 1 else 2
+        self.blocks = [torch.zeros(self.lay.block_bytes * world, dtype=torch.uint8, device=self.dev) for _ in range(self.nbuf)]
         self.stream_obj = torch.cuda.Stream(device=self.dev)        # A: simulation
         # B: clustering + exchange of the batch before.  High priority: the simulation kernel holds every register of every SM, and the
         # clustering's small CTAs must get the slots that free up as simulation CTAs retire instead of queueing behind the whole launch
         self.stream_b_obj = torch.cuda.Stream(device=self.dev, priority=-1)
         self.stream, self.stream_b = self.stream_obj.cuda_stream, self.stream_b_obj.cuda_stream
         assert self.stream != 0 and self.stream_b != 0
-        self.ev_sim = [torch.cuda.Event() for _ in range(2)]        # simulation of the batch in buffer i has finished
-        self.ev_done = [torch.cuda.Event() for _ in range(2)]       # clustering of the batch in buffer i has finished
+        self.ev_sim = [torch.cuda.Event() for _ in range(self.nbuf)]    # simulation of the batch in buffer i has finished
+        self.ev_done = [torch.cuda.Event() for _ in range(self.nbuf)]   # clustering of the batch in buffer i has finished (and, with a
+                                                                         # communicator, the exchange of the batch before it: stream B waits for it)
         self.pending = None                                          # batch simulated but not yet clustered
         self.issued = 0
 
@@ -381,7 +385,7 @@ class DeviceBatch:
 
     def _simulate(self, k, stream_obj):
         abi, lib, lay = self.abi, self.lib, self.lay
-        blocks = self.blocks[k % 2]
+        blocks = self.blocks[k % self.nbuf]
         if self.comm is not None:
             abi.check(lib.upc_sharded_edge_batch_simulate(self.comm, C.byref(self.wl["params"]), SEED + k, self.E, self.P, self.d_starts.data_ptr(),
                                                           self.d_targets.data_ptr(), blocks.data_ptr(), stream_obj.cuda_stream))
@@ -392,7 +396,7 @@ class DeviceBatch:
 
     def _cluster(self, k, stream_obj):
         abi, lib, lay = self.abi, self.lib, self.lay
-        blocks = self.blocks[k % 2]
+        blocks = self.blocks[k % self.nbuf]
         if self.comm is not None:
             abi.check(lib.upc_sharded_edge_batch_finish(self.comm, C.byref(self.cp), self.E, self.P, blocks.data_ptr(), stream_obj.cuda_stream))
             return
@@ -414,13 +418,19 @@ class DeviceBatch:
             if ev:
                 ev[2].record(A)
             return
-        # buffer k % 2 was last used by batch k - 2: its clustering (and exchange) must be over before it is overwritten
-        if self.issued >= 2:
-            A.wait_event(self.ev_done[k % 2])
+        # the buffer was last used by batch k - nbuf: its clustering must be over before it is overwritten, and so must its exchange -
+        # which stream B waited for before it recorded the `done` event of the batch AFTER it (upc_comm: an exchange is ordered behind
+        # the one before), i.e. of batch k - 2 when there are three buffers
+        nb = self.nbuf
+        if self.issued >= nb:
+            A.wait_event(self.ev_done[k % nb])
             if self.comm is not None:
-                self.abi.check(self.lib.upc_comm_wait(self.comm, A.cuda_stream))
+                if nb >= 3:
+                    A.wait_event(self.ev_done[(k - nb + 1) % nb])
+                else:
+                    self.abi.check(self.lib.upc_comm_wait(self.comm, A.cuda_stream))
         self._simulate(k, A)
-        self.ev_sim[k % 2].record(A)
+        self.ev_sim[k % nb].record(A)
         self.issued += 1
         if self.pending is not None:
             self._finish_pending()
@@ -428,17 +438,17 @@ class DeviceBatch:
 
     def _finish_pending(self):
         k, B = self.pending, self.stream_b_obj
-        B.wait_event(self.ev_sim[k % 2])
+        B.wait_event(self.ev_sim[k % self.nbuf])
         self._cluster(k, B)          # host decisions inside only ever wait for stream B
-        self.ev_done[k % 2].record(B)
+        self.ev_done[k % self.nbuf].record(B)
         self.pending = None
 
     def _drain(self):
         if self.pending is not None:
             self._finish_pending()
         if self.issued:
-            self.stream_obj.wait_event(self.ev_done[0])
-            self.stream_obj.wait_event(self.ev_done[1])
+            for ev in self.ev_done:
+                self.stream_obj.wait_event(ev)
             self.issued = 0
 
     def finish(self):
@@ -449,7 +459,7 @@ class DeviceBatch:
 
     def cluster_counts(self, k=0):
         lay = self.lay
-        blk = self.blocks[k % 2].cpu().numpy()
+        blk = self.blocks[k % self.nbuf].cpu().numpy()
         out = []
         for r in range(self.world):
             lo, hi = self.abi.shard_bounds(self.E, r, self.world)
@@ -679,7 +689,7 @@ def run_b200(args):
             "dtype": "f64", "data": "synthetic (seeded boxes SDF, seeded edges, counter-based truncated-normal noise drawn in the kernel)",
             "config": {"workload": wl["label"], "edges": E, "particles_per_edge": P, "edges_per_gpu": hi - lo,
                        "sharding": "contiguous blocks of edges per GPU (upc_shard_bounds), SDF + robot tables replicated, ONE in-place NCCL all-gather of outcome records per step "
-                                   "issued by the library's communicator (two gather buffers: clustering + exchange of step k overlap the simulation of step k+1)" if world > 1 else "single GPU",
+                                   "issued by the library's communicator (three gather buffers: clustering + exchange of step k overlap the simulation of steps k+1 and k+2)" if world > 1 else "single GPU",
                        "nccl_version": nccl_version,
                        "clustering": "CRS signatures (thr 0.125) + distance pass (thr 0.1), one pass over all edges",
                        "lanes_per_particle": args.lanes or "auto",

@@ -117,7 +117,11 @@ static int32_t fail_comm(const char* msg)
 static int32_t finish_comm(upc_comm* c)
 {
     UPC_CUDA_TRY(cudaSetDevice(c->h->device));
-    UPC_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    /* highest priority: the exchange of one batch overlaps the simulation of the next, whose kernel holds every register of every
+     * SM - NCCL's few CTAs must get the slots that free up as simulation CTAs retire instead of queueing behind the whole launch */
+    int least = 0, greatest = 0;
+    UPC_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    UPC_CUDA_TRY(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, greatest));
     UPC_CUDA_TRY(cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming));
     UPC_CUDA_TRY(cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming));
     return UPC_OK;
