@@ -253,6 +253,19 @@ int32_t upc_simulate_and_cluster_edges(upc_handle* h, const upc_sim_params* para
                                        const double* edge_targets, double* out_configs, uint8_t* out_collided, int32_t* out_labels,
                                        int32_t* out_n_clusters);
 
+/*
+ * The same step as a pair of calls, for callers that keep two batches in flight (slot = 0 / 1): upc_edge_batch_submit uploads the
+ * end points of a batch and queues its simulation - asynchronous, it returns as soon as the work is queued; the host arrays must
+ * stay valid until the batch has been collected - and upc_edge_batch_collect clusters the batch in `slot` on the handle's second,
+ * high-priority stream and brings configurations, flags, labels and cluster counts to the host (blocks until they are there).
+ * Issue submit(k + 1) before collect(k): the simulation of the next batch fills the machine while the clustering and the
+ * download of this one run underneath.  Results equal upc_simulate_and_cluster_edges for the same arguments.
+ */
+int32_t upc_edge_batch_submit(upc_handle* h, const upc_sim_params* params, uint64_t seed, int64_t first_particle, int64_t n_edges,
+                              int64_t particles_per_edge, int64_t n_starts, const double* edge_starts, const double* edge_targets, int32_t slot);
+int32_t upc_edge_batch_collect(upc_handle* h, const upc_cluster_params* cparams, int32_t slot, double* out_configs, uint8_t* out_collided,
+                               int32_t* out_labels, int32_t* out_n_clusters);
+
 /* CheckConfigCollision: 1 iff any body point of `config` has sdf - radius < contact_distance + inflation */
 int32_t upc_check_config_collision(upc_handle* h, const double* config, double contact_distance, double inflation,
                                    int32_t* out_in_collision);

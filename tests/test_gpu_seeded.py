@@ -292,6 +292,54 @@ def test_pipelined_halves_of_the_sharded_step_equal_the_one_call_form(oracle, si
         lib.upc_comm_destroy(comm)
 
 
+def test_submit_collect_pairs_equal_the_one_call_edge_batch(oracle, simulators):
+    """upc_edge_batch_submit / upc_edge_batch_collect with two batches in flight (submit k + 1 before collect k) return, batch by
+    batch, what upc_simulate_and_cluster_edges returns for the same arguments - which test_planner_batch_step_matches_oracle pins to
+    the oracle.  Both start forms: one start per edge, one start per particle."""
+    lib = abi.load_library()
+    E, P = 24, 128
+    sc = scenarios.c5_batch(edges=E, particles=P, num_steps=32)
+    cp = cases._cparams(abi.FEATURE_CRS, 0.125, 0.1)
+    sim = simulators("c5_submit", sc["env"], sc["robot"])
+    width, n = sim.robot.width, E * P
+    es = np.ascontiguousarray(sc["starts"][::P].T)
+    et = np.ascontiguousarray(sc["targets"][::P].T)
+    rng = np.random.default_rng(3)
+    per_particle = np.ascontiguousarray((sc["starts"] + rng.normal(scale=1e-3, size=sc["starts"].shape)).T)
+
+    def one_call(seed, starts):
+        out, coll = np.zeros((width, n)), np.zeros(n, dtype=np.uint8)
+        labels, ncl = np.zeros(n, dtype=np.int32), np.zeros(E, dtype=np.int32)
+        abi.check(lib.upc_simulate_and_cluster_edges(sim.handle, C.byref(sc["params"]), C.byref(cp), seed, 0, E, P, starts.shape[1], starts.ctypes.data, et.ctypes.data,
+                                                     out.ctypes.data, coll.ctypes.data, labels.ctypes.data, ncl.ctypes.data))
+        return out, coll, labels, ncl
+
+    K = 5
+    starts_of = lambda k: per_particle if k % 2 else es
+    want = [one_call(700 + k, starts_of(k)) for k in range(K)]
+    got = []
+    res = [(np.zeros((width, n)), np.zeros(n, dtype=np.uint8), np.zeros(n, dtype=np.int32), np.zeros(E, dtype=np.int32)) for _ in range(2)]
+
+    def submit(k):
+        st = starts_of(k)
+        abi.check(lib.upc_edge_batch_submit(sim.handle, C.byref(sc["params"]), 700 + k, 0, E, P, st.shape[1], st.ctypes.data, et.ctypes.data, k % 2))
+
+    submit(0)
+    for k in range(K):
+        if k + 1 < K:
+            submit(k + 1)
+        o, c, l, m = res[k % 2]
+        abi.check(lib.upc_edge_batch_collect(sim.handle, C.byref(cp), k % 2, o.ctypes.data, c.ctypes.data, l.ctypes.data, m.ctypes.data))
+        got.append((o.copy(), c.copy(), l.copy(), m.copy()))
+    for k in range(K):
+        for a, b in zip(got[k], want[k]):
+            assert np.array_equal(a, b), k
+    assert not np.array_equal(want[0][0], want[2][0])            # different seeds really give different batches
+    # a slot can only be collected once, and only after a submit
+    o, c, l, m = res[0]
+    assert lib.upc_edge_batch_collect(sim.handle, C.byref(cp), 0, o.ctypes.data, c.ctypes.data, l.ctypes.data, m.ctypes.data) != 0
+
+
 # ------------------------------------------------------------------ BASELINE.json sizes
 
 def test_full_size_c3_subsample_matches_oracle(oracle, simulators):

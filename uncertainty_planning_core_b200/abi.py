@@ -312,13 +312,16 @@ def load_library():
     lib.upc_comm_wait.argtypes = [vp, vp]
     lib.upc_comm_synchronize.argtypes = [vp]
     lib.upc_sharded_edge_batch.argtypes = [vp, C.POINTER(SimParams), C.POINTER(ClusterParams), u64, i64, i64, vp, vp, vp, vp]
+    lib.upc_edge_batch_submit.argtypes = [vp, C.POINTER(SimParams), u64, i64, i64, i64, i64, vp, vp, i32]
+    lib.upc_edge_batch_collect.argtypes = [vp, C.POINTER(ClusterParams), i32, vp, vp, vp, vp]
     lib.upc_sharded_edge_batch_simulate.argtypes = [vp, C.POINTER(SimParams), u64, i64, i64, vp, vp, vp, vp]
     lib.upc_sharded_edge_batch_finish.argtypes = [vp, C.POINTER(ClusterParams), i64, i64, vp, vp]
     lib.upc_sharded_edge_batch_all.argtypes = [i32, vp, C.POINTER(SimParams), C.POINTER(ClusterParams), u64, i64, i64, vp, vp, vp, vp]
     for name in ("upc_forward_simulate_seeded", "upc_forward_simulate_seeded_device", "upc_fill_noise_tape_seeded", "upc_forward_simulate_traced",
                  "upc_simulate_and_cluster_edges", "upc_comm_get_unique_id", "upc_comm_create", "upc_comm_create_all", "upc_comm_destroy",
                  "upc_comm_world", "upc_comm_rank", "upc_comm_nccl_version", "upc_outcome_layout_for", "upc_comm_all_gather_outcomes", "upc_comm_wait",
-                 "upc_comm_synchronize", "upc_sharded_edge_batch", "upc_sharded_edge_batch_simulate", "upc_sharded_edge_batch_finish", "upc_sharded_edge_batch_all", "upc_device_scratch", "upc_memcpy_to_device", "upc_memcpy_to_host"):
+                 "upc_comm_synchronize", "upc_sharded_edge_batch", "upc_sharded_edge_batch_simulate", "upc_sharded_edge_batch_finish", "upc_sharded_edge_batch_all",
+                 "upc_edge_batch_submit", "upc_edge_batch_collect", "upc_device_scratch", "upc_memcpy_to_device", "upc_memcpy_to_host"):
         getattr(lib, name).restype = i32
     for name in ("upc_cluster_statistics", "upc_nearest_neighbors", "upc_count_within", "upc_measure_l2_gather_gbs", "upc_measure_fp64_tflops", "upc_create", "upc_destroy", "upc_set_robot", "upc_get_stats", "upc_reset_stats",
                  "upc_set_lanes_per_particle", "upc_host_alloc", "upc_host_free", "upc_synchronize",
@@ -339,6 +342,7 @@ EXPORTED_SYMBOLS = (
     "upc_simulate_and_cluster_edges", "upc_comm_get_unique_id", "upc_comm_create", "upc_comm_create_all", "upc_comm_destroy",
     "upc_comm_world", "upc_comm_rank", "upc_comm_nccl_version", "upc_sharded_edge_batch_all", "upc_shard_bounds", "upc_device_scratch", "upc_memcpy_to_device", "upc_memcpy_to_host",
     "upc_outcome_layout_for", "upc_comm_all_gather_outcomes", "upc_comm_wait", "upc_comm_synchronize", "upc_sharded_edge_batch", "upc_sharded_edge_batch_simulate", "upc_sharded_edge_batch_finish",
+    "upc_edge_batch_submit", "upc_edge_batch_collect",
 )
 
 

@@ -260,10 +260,15 @@ int32_t upc_destroy(upc_handle* h)
     cudaFree(h->d_cells);
     cudaFree(h->d_points);
     cudaFree(h->d_counters);
-    DeviceBuffer* bufs[] = {&h->user[0], &h->user[1], &h->user[2], &h->user[3], &h->st_trace, &h->st_records, &h->st_order, &h->st_starts, &h->st_targets, &h->st_tape, &h->st_out, &h->st_coll, &h->st_labels, &h->st_ncl, &h->st_carry,
+    DeviceBuffer* bufs[] = {&h->user[0], &h->user[1], &h->user[2], &h->user[3], &h->st_trace, &h->st_records, &h->st_order, &h->eb_starts[0], &h->eb_starts[1], &h->eb_targets[0], &h->eb_targets[1], &h->eb_out[0], &h->eb_out[1], &h->eb_coll[0], &h->eb_coll[1], &h->st_starts, &h->st_targets, &h->st_tape, &h->st_out, &h->st_coll, &h->st_labels, &h->st_ncl, &h->st_carry,
                             &h->cw.features, &h->cw.adjacency, &h->cw.roots, &h->cw.comp, &h->cw.flags, &h->cw.signatures,
                             &h->cw.frames, &h->cw.dist_matrix, &h->cw.members, &h->cw.link_scratch, &h->cw.misc, &h->cw.hash, &h->cw.dedupe, &h->cw.usig, &h->cw.uroot, &h->cw.comp_list, &h->cw.comp_feat};
     for (DeviceBuffer* b : bufs) b->release();
+    if (h->aux_stream)
+    {
+        cudaStreamDestroy(h->aux_stream);
+        for (int c = 0; c < 2; c++) cudaEventDestroy(h->eb_sim_done[c]);
+    }
     if (h->copy_stream)
     {
         cudaStreamDestroy(h->copy_stream);
@@ -680,6 +685,104 @@ int32_t upc_simulate_and_cluster_edges(upc_handle* h, const upc_sim_params* para
     UPC_CUDA_TRY(cudaMemcpyAsync(out_n_clusters, h->st_ncl.ptr, (size_t)n_edges * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     h->stats.d2h_bytes += (int64_t)(cfg_bytes + (size_t)n * 5 + (size_t)n_edges * 4);
     UPC_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return UPC_OK;
+}
+
+/*
+ * The planner-batch step as a pair of calls, so that a caller can keep two batches in flight: upc_edge_batch_submit uploads the
+ * edge end points of a batch and queues its simulation (asynchronous: returns as soon as the work is queued);
+ * upc_edge_batch_collect clusters the batch submitted to `slot` on the handle's second, high-priority stream and brings its
+ * results to the host (blocks until they are there).  submit(k + 1) before collect(k): the simulation of the next batch fills the
+ * machine while this batch's clustering - small latency-bound launches with host decisions in between - and its 119 MB of
+ * results run underneath.  Same results as upc_simulate_and_cluster_edges for the same arguments.
+ */
+static int32_t ensure_edge_batch_streams(upc_handle* h)
+{
+    if (!h->aux_stream)
+    {
+        int least = 0, greatest = 0;
+        UPC_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        UPC_CUDA_TRY(cudaStreamCreateWithPriority(&h->aux_stream, cudaStreamNonBlocking, greatest));
+        for (int c = 0; c < 2; c++) UPC_CUDA_TRY(cudaEventCreateWithFlags(&h->eb_sim_done[c], cudaEventDisableTiming));
+    }
+    if (!h->copy_stream)
+    {
+        UPC_CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        for (int c = 0; c < 8; c++) UPC_CUDA_TRY(cudaEventCreateWithFlags(&h->copy_done[c], cudaEventDisableTiming));
+        UPC_CUDA_TRY(cudaEventCreateWithFlags(&h->compute_done, cudaEventDisableTiming));
+    }
+    return UPC_OK;
+}
+
+int32_t upc_edge_batch_submit(upc_handle* h, const upc_sim_params* params, uint64_t seed, int64_t first_particle, int64_t n_edges,
+                              int64_t particles_per_edge, int64_t n_starts, const double* edge_starts, const double* edge_targets, int32_t slot)
+{
+    if (!h || !params) return fail_arg("null argument");
+    if (!h->has_robot)
+    {
+        set_error("upc_set_robot has not been called");
+        return UPC_ERR_NO_ROBOT;
+    }
+    if (slot < 0 || slot > 1) return fail_arg("slot must be 0 or 1");
+    if (n_edges < 1 || particles_per_edge < 1) return fail_arg("n_edges and particles_per_edge must be >= 1");
+    if (n_edges > 65535) return fail_arg("at most 65535 edges per call");
+    if (particles_per_edge > (int64_t)1 << 20) return fail_arg("at most 2^20 particles per edge");
+    if (!edge_starts || !edge_targets) return fail_arg("null buffer");
+    const int64_t n = n_edges * particles_per_edge;
+    if (n_starts != n_edges && n_starts != n) return fail_arg("starts must hold one configuration per edge or one per particle");
+    UPC_CUDA_TRY(cudaSetDevice(h->device));
+    const int32_t src = ensure_edge_batch_streams(h);
+    if (src != UPC_OK) return src;
+    const int width = upc_config_width(h->robot.kind, h->robot.dof);
+    const size_t start_bytes = (size_t)width * (size_t)n_starts * sizeof(double);
+    const size_t tgt_bytes = (size_t)width * (size_t)n_edges * sizeof(double);
+    UPC_CUDA_TRY(h->eb_starts[slot].reserve(start_bytes));
+    UPC_CUDA_TRY(h->eb_targets[slot].reserve(tgt_bytes));
+    UPC_CUDA_TRY(h->eb_out[slot].reserve((size_t)width * (size_t)n * sizeof(double)));
+    UPC_CUDA_TRY(h->eb_coll[slot].reserve((size_t)n));
+    UPC_CUDA_TRY(cudaMemcpyAsync(h->eb_starts[slot].ptr, edge_starts, start_bytes, cudaMemcpyHostToDevice, h->stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(h->eb_targets[slot].ptr, edge_targets, tgt_bytes, cudaMemcpyHostToDevice, h->stream));
+    h->stats.h2d_bytes += (int64_t)(start_bytes + tgt_bytes);
+    const int32_t rc = upc_forward_simulate_seeded_device(h, params, seed, first_particle, n, n_starts, (const double*)h->eb_starts[slot].ptr, n_edges,
+                                                          (const double*)h->eb_targets[slot].ptr, (double*)h->eb_out[slot].ptr, (uint8_t*)h->eb_coll[slot].ptr,
+                                                          h->stream);
+    if (rc != UPC_OK) return rc;
+    UPC_CUDA_TRY(cudaEventRecord(h->eb_sim_done[slot], h->stream));
+    h->eb_edges[slot] = n_edges;
+    h->eb_particles[slot] = particles_per_edge;
+    return UPC_OK;
+}
+
+int32_t upc_edge_batch_collect(upc_handle* h, const upc_cluster_params* cparams, int32_t slot, double* out_configs, uint8_t* out_collided,
+                               int32_t* out_labels, int32_t* out_n_clusters)
+{
+    if (!h || !cparams) return fail_arg("null argument");
+    if (slot < 0 || slot > 1) return fail_arg("slot must be 0 or 1");
+    if (h->eb_edges[slot] < 1) return fail_arg("nothing was submitted to this slot");
+    if (!out_configs || !out_collided || !out_labels || !out_n_clusters) return fail_arg("null buffer");
+    UPC_CUDA_TRY(cudaSetDevice(h->device));
+    const int64_t n_edges = h->eb_edges[slot], particles_per_edge = h->eb_particles[slot], n = n_edges * particles_per_edge;
+    h->eb_edges[slot] = 0;
+    const size_t cfg_bytes = (size_t)upc_config_width(h->robot.kind, h->robot.dof) * (size_t)n * sizeof(double);
+    /* configurations and flags are final once the simulation has run: they travel on the copy stream while the outcome is clustered */
+    UPC_CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->eb_sim_done[slot], 0));
+    UPC_CUDA_TRY(cudaMemcpyAsync(out_configs, h->eb_out[slot].ptr, cfg_bytes, cudaMemcpyDeviceToHost, h->copy_stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(out_collided, h->eb_coll[slot].ptr, (size_t)n, cudaMemcpyDeviceToHost, h->copy_stream));
+    UPC_CUDA_TRY(cudaStreamWaitEvent(h->aux_stream, h->eb_sim_done[slot], 0));
+    UPC_CUDA_TRY(h->st_labels.reserve((size_t)n * sizeof(int32_t)));
+    UPC_CUDA_TRY(h->st_ncl.reserve((size_t)n_edges * sizeof(int32_t) + 64));
+    const int32_t rc = upc_cluster_particles_device(h, cparams, n_edges, particles_per_edge, (const double*)h->eb_out[slot].ptr, (int32_t*)h->st_labels.ptr,
+                                                    (int32_t*)h->st_ncl.ptr, h->aux_stream);
+    if (rc != UPC_OK)
+    {
+        cudaStreamSynchronize(h->copy_stream); /* the caller's buffers must not be written after the call returns */
+        return rc;
+    }
+    UPC_CUDA_TRY(cudaMemcpyAsync(out_labels, h->st_labels.ptr, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->aux_stream));
+    UPC_CUDA_TRY(cudaMemcpyAsync(out_n_clusters, h->st_ncl.ptr, (size_t)n_edges * sizeof(int32_t), cudaMemcpyDeviceToHost, h->aux_stream));
+    h->stats.d2h_bytes += (int64_t)(cfg_bytes + (size_t)n * 5 + (size_t)n_edges * 4);
+    UPC_CUDA_TRY(cudaStreamSynchronize(h->aux_stream));
+    UPC_CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
     return UPC_OK;
 }
 

@@ -70,6 +70,11 @@ struct upc_handle
     int64_t phase_cycles[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     /* staging for the host-pointer entry points */
     upc::DeviceBuffer st_starts, st_targets, st_tape, st_out, st_coll, st_labels, st_ncl, st_carry, st_trace, st_records, st_order;
+    /* upc_edge_batch_submit / _collect: two batches in flight (device-side staging per slot), clustering on its own stream */
+    upc::DeviceBuffer eb_starts[2], eb_targets[2], eb_out[2], eb_coll[2];
+    cudaEvent_t eb_sim_done[2] = {nullptr, nullptr};
+    int64_t eb_edges[2] = {0, 0}, eb_particles[2] = {0, 0};
+    cudaStream_t aux_stream = nullptr; /* highest priority: its small CTAs take the slots retiring simulation CTAs free */
     upc::DeviceBuffer user[4]; /* upc_device_scratch */
     cudaStream_t copy_stream = nullptr; /* tape slices of the host-pointer entry point */
     cudaEvent_t copy_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
