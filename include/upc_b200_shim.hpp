@@ -474,6 +474,59 @@ public:
         return result;
     }
 
+    /*
+     * The same step as a pair of calls for planners that keep two batches in flight (upc_edge_batch_submit / _collect): submit batch
+     * k + 1, then collect batch k - the next batch is simulated while this one is clustered, downloaded and assembled into clusters
+     * on the host.  `slot` is 0 or 1; the edge vectors given to SubmitEdgeBatch must stay alive until the slot has been collected
+     * (their start configurations are read again when the clusters are assembled).  CollectEdgeBatch returns what
+     * SimulateAndClusterEdges would have returned for the same arguments.
+     */
+    void SubmitEdgeBatch(const Robot& immutable_robot, const std::vector<Configuration, ConfigAlloc>& edge_starts, const std::vector<Configuration, ConfigAlloc>& edge_targets,
+                         const size_t particles_per_edge, std::vector<RNG>& rng, const double forward_simulation_time, const double simulation_shortcut_distance,
+                         const bool use_individual_jacobians, const bool allow_contacts, const int slot) const
+    {
+        (void)immutable_robot;
+        if (slot < 0 || slot > 1) throw std::invalid_argument("slot must be 0 or 1");
+        const size_t E = edge_starts.size();
+        if (E == 0 || particles_per_edge == 0) throw std::invalid_argument("an edge batch needs at least one edge and one particle");
+        if (edge_targets.size() != E) throw std::invalid_argument("one target per edge");
+        if (rng.empty()) throw std::invalid_argument("at least one PRNG is required");
+        const int width = Traits::width(edge_starts[0]);
+        const upc_sim_params params = MakeParams(forward_simulation_time, simulation_shortcut_distance, use_individual_jacobians, allow_contacts);
+        std::lock_guard<std::mutex> guard(staging_->mutex);
+        PendingBatch& pb = pending_[slot];
+        double* starts = pb.starts.template get<double>((size_t)width * E);
+        double* targets = pb.targets.template get<double>((size_t)width * E);
+        FlattenToSoa(edge_starts, width, starts);
+        FlattenToSoa(edge_targets, width, targets);
+        const uint64_t seed = NextSeed(rng[0]);
+        check(upc_edge_batch_submit(handle_->get(), &params, seed, 0, (int64_t)E, (int64_t)particles_per_edge, (int64_t)E, starts, targets, slot));
+        pb.edge_starts = &edge_starts;
+        pb.particles = particles_per_edge;
+        pb.allow_contacts = allow_contacts;
+    }
+
+    template <typename Clustering>
+    std::vector<std::vector<std::vector<std::pair<Configuration, bool>>>> CollectEdgeBatch(const Clustering& clustering, const int slot) const
+    {
+        if (slot < 0 || slot > 1) throw std::invalid_argument("slot must be 0 or 1");
+        std::lock_guard<std::mutex> guard(staging_->mutex);
+        PendingBatch& pb = pending_[slot];
+        if (pb.edge_starts == nullptr) throw std::invalid_argument("nothing was submitted to this slot");
+        const std::vector<Configuration, ConfigAlloc>& edge_starts = *pb.edge_starts;
+        const size_t E = edge_starts.size(), P = pb.particles, n = E * P;
+        const int width = Traits::width(edge_starts[0]);
+        double* out = pb.out.template get<double>((size_t)width * n);
+        uint8_t* collided = pb.collided.template get<uint8_t>(n);
+        int32_t* labels = pb.labels.template get<int32_t>(n);
+        int32_t* n_clusters = pb.counts.template get<int32_t>(E);
+        pb.edge_starts = nullptr;
+        check(upc_edge_batch_collect(handle_->get(), &clustering.params(), slot, out, collided, labels, n_clusters));
+        std::vector<std::vector<std::vector<std::pair<Configuration, bool>>>> result(E);
+        AssembleEdgeClusters(edge_starts, P, n, width, pb.allow_contacts, out, collided, labels, n_clusters, n, 0, E, result);
+        return result;
+    }
+
     upc_sim_params MakeParams(const double forward_simulation_time, const double simulation_shortcut_distance, const bool use_individual_jacobians,
                               const bool allow_contacts) const
     {
@@ -594,6 +647,16 @@ protected:
     SolverConfig solver_;
     std::shared_ptr<Handle> handle_;
     std::shared_ptr<Staging> staging_ = std::shared_ptr<Staging>(new Staging());
+    /* SubmitEdgeBatch / CollectEdgeBatch: page-locked staging and bookkeeping of the two batches in flight */
+    struct PendingBatch
+    {
+        PinnedBuffer starts, targets, out, collided, labels, counts;
+        const std::vector<Configuration, ConfigAlloc>* edge_starts = nullptr;
+        size_t particles = 0;
+        bool allow_contacts = true;
+    };
+    mutable std::shared_ptr<std::array<PendingBatch, 2>> pending_store_ = std::shared_ptr<std::array<PendingBatch, 2>>(new std::array<PendingBatch, 2>());
+    std::array<PendingBatch, 2>& pending_ = *pending_store_;
 #ifndef UPC_SHIM_WITH_REFERENCE
     int32_t debug_level_;
 #endif

@@ -113,6 +113,7 @@ static int run(const Workload& w, const std::string& mode, int steps, int warmup
     upc_stats before{}, after{};
     if (mode == "edges")
     {
+        std::string call_name;
         std::shared_ptr<Simulator> one;
         std::shared_ptr<ShardedSimulator<StubRobot, Config, std::mt19937_64>> many;
         std::vector<int> devs;
@@ -121,15 +122,28 @@ static int run(const Workload& w, const std::string& mode, int steps, int warmup
         else one.reset(new Simulator(w.env, w.robot, 0, solver, 0));
         upc_handle* h0 = many ? many->simulator(0).handle() : one->handle();
         B200OutcomeClustering<StubRobot, Config> clustering(h0, CONVEX_REGION_SIGNATURE, w.signature_threshold, w.distance_threshold);
+        /* one GPU: two batches in flight (SubmitEdgeBatch k + 1, then CollectEdgeBatch k); several GPUs: one blocking call per batch */
+        const bool pipelined = !many && std::getenv("UPC_PLUGIN_BENCH_ONE_CALL") == nullptr;
+        call_name = pipelined ? "SubmitEdgeBatch / CollectEdgeBatch (two batches in flight)" : "SimulateAndClusterEdges";
         for (int k = 0; k < warmup + steps; k++)
         {
             if (k == warmup)
             {
                 check(upc_get_stats(h0, &before));
                 t0 = std::chrono::steady_clock::now();
+                if (pipelined) one->SubmitEdgeBatch(stub, starts, targets, P, rngs, sim_time, shortcut, false, true, k % 2);
             }
-            const auto result = many ? many->SimulateAndClusterEdges(stub, starts, targets, P, rngs, sim_time, shortcut, false, true, clustering)
-                                     : one->SimulateAndClusterEdges(stub, starts, targets, P, rngs, sim_time, shortcut, false, true, clustering);
+            std::vector<std::vector<std::vector<std::pair<Config, bool>>>> result;
+            if (pipelined && k >= warmup)
+            {
+                if (k + 1 < warmup + steps) one->SubmitEdgeBatch(stub, starts, targets, P, rngs, sim_time, shortcut, false, true, (k + 1) % 2);
+                result = one->CollectEdgeBatch(clustering, k % 2);
+            }
+            else
+            {
+                result = many ? many->SimulateAndClusterEdges(stub, starts, targets, P, rngs, sim_time, shortcut, false, true, clustering)
+                              : one->SimulateAndClusterEdges(stub, starts, targets, P, rngs, sim_time, shortcut, false, true, clustering);
+            }
             if (k == warmup + steps - 1)
                 for (const auto& edge : result)
                 {
@@ -140,9 +154,9 @@ static int run(const Workload& w, const std::string& mode, int steps, int warmup
         const double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         check(upc_get_stats(h0, &after));
         const double particle_steps = (double)w.n_starts * (double)P * (double)w.params.num_steps * steps;
-        std::printf("{\"mode\": \"edges\", \"call\": \"%s::SimulateAndClusterEdges\", \"gpus\": %d, \"ms_per_step\": %.6f, \"value\": %.6e, \"edges\": %lld, \"particles_per_edge\": %zu, "
+        std::printf("{\"mode\": \"edges\", \"call\": \"%s::%s\", \"gpus\": %d, \"ms_per_step\": %.6f, \"value\": %.6e, \"edges\": %lld, \"particles_per_edge\": %zu, "
                     "\"clusters\": %zu, \"particles_returned\": %zu, \"h2d_bytes_per_step\": %.1f, \"d2h_bytes_per_step\": %.1f, \"checksum\": %.17g}\n",
-                    many ? "ShardedSimulator" : "B200Simulator", gpus, 1e3 * seconds / steps, particle_steps / seconds, (long long)w.n_starts, P, clusters_total, particles_out,
+                    many ? "ShardedSimulator" : "B200Simulator", call_name.c_str(), gpus, 1e3 * seconds / steps, particle_steps / seconds, (long long)w.n_starts, P, clusters_total, particles_out,
                     (double)(after.h2d_bytes - before.h2d_bytes) / steps, (double)(after.d2h_bytes - before.d2h_bytes) / steps, checksum);
         return 0;
     }

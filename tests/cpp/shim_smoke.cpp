@@ -298,6 +298,20 @@ int main(int argc, char** argv)
         std::vector<std::vector<Particle>> sets(E);
         for (size_t i = 0; i < bn; i++) sets[i / P].push_back(Particle(SE2Config{bout[i], bout[bn + i], bout[2 * bn + i]}, bcoll[i] != 0));
         if (clustering.ClusterParticleSets(sets, false) != expect) { std::printf("ClusterParticleSets differs from the oracle\n"); return 18; }
+        /* the same step as submit / collect pairs, two batches in flight: batch by batch what the blocking call returns */
+        std::vector<std::mt19937_64> ga(1, std::mt19937_64(99)), gb = ga;
+        std::vector<std::vector<std::vector<std::vector<Particle>>>> blocking;
+        for (int k = 0; k < 3; k++) blocking.push_back(simulator.SimulateAndClusterEdges(stub, es, et, P, ga, 0.5, 0.01, false, false, clustering));
+        simulator.SubmitEdgeBatch(stub, es, et, P, gb, 0.5, 0.01, false, false, 0);
+        for (int k = 0; k < 3; k++)
+        {
+            if (k + 1 < 3) simulator.SubmitEdgeBatch(stub, es, et, P, gb, 0.5, 0.01, false, false, (k + 1) % 2);
+            if (simulator.CollectEdgeBatch(clustering, k % 2) != blocking[(size_t)k]) { std::printf("submit / collect batch %d differs from the blocking call\n", k); return 18; }
+        }
+        if (blocking[0] == blocking[1]) { std::printf("batches with different seeds must differ\n"); return 18; }
+        bool empty_slot_throws = false;
+        try { simulator.CollectEdgeBatch(clustering, 0); } catch (const std::invalid_argument&) { empty_slot_throws = true; }
+        if (!empty_slot_throws) { std::printf("collecting an empty slot did not throw\n"); return 18; }
     }
 
     {
