@@ -153,6 +153,7 @@ def load_ref_rob():
     lib.ref_rob_kinematics.argtypes = [rp, ci, vp, vp, vp]
     lib.ref_rob_distances.argtypes = [rp, ci, vp, vp, vp, vp, ci]
     lib.ref_rob_average.argtypes = [rp, ci, vp, vp]
+    lib.ref_state_statistics.argtypes = [rp, ci, vp, cd, ci, vp, vp, vp, vp]
     _REF_ROB = lib
     return lib
 
@@ -225,6 +226,18 @@ def rob_average(robot, configs, reference=False):
     else:
         _check(load().oracle_rob_average(C.byref(robot.desc), configs.shape[0], configs.ctypes.data, out.ctypes.data))
     return out
+
+
+def ref_state_statistics(robot, configs, step_size):
+    """UncertaintyPlannerState(particles)::UpdateStatistics(robot) of the reference (oracle/_ref/libref_rob.so): dict with the keys of one
+    cluster of cluster_statistics()"""
+    configs = _f64(configs)
+    d = robot.desc
+    V = load().upc_variance_width(d.kind, d.dof)
+    expectation, scalars, variances, si_variances = np.zeros(configs.shape[1]), np.zeros(2), np.zeros(V), np.zeros(V)
+    assert load_ref_rob().ref_state_statistics(C.byref(d), configs.shape[0], configs.ctypes.data, float(step_size), V, expectation.ctypes.data, scalars.ctypes.data,
+                                               variances.ctypes.data, si_variances.ctypes.data) == 0
+    return dict(expectation=expectation, variance=scalars[0], si_variance=scalars[1], variances=variances, si_variances=si_variances)
 
 
 def sensor_values(process_values, draws):

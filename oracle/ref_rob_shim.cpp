@@ -5,13 +5,17 @@
  * here; the stand-ins follow the libraries' documented semantics with libm, independently of the oracle's arithmetic).
  * Built by oracle/Makefile into oracle/_ref/libref_rob.so from the header where it lies under $(REFERENCE)/include; used by
  * tests/test_oracle_rob.py to pin the oracle's robot models (sense -> PID -> clamp -> noisy apply sequences, forward
- * kinematics, point Jacobians, configuration distances, averages) against the reference's code.  TEST INFRASTRUCTURE ONLY.
+ * kinematics, point Jacobians, configuration distances, averages) against the reference's code, and - through the reference's
+ * own, UNMODIFIED uncertainty_planner_state.hpp (UncertaintyPlannerState::UpdateStatistics :339-351, ComputeExpectation /
+ * ComputeVariance / ComputeDirectionalVariance / the space-independent forms :591-714) - the per-cluster statistics of the child
+ * states (oracle_cluster_statistics, the product's upc_cluster_statistics).  TEST INFRASTRUCTURE ONLY.
  *
  * Robots are described by the product's POD upc_robot_desc (include/upc_b200.h) so that the same Python fixtures drive both
  * sides.  The reference's SE(2) / SE(3) robots take ONE parameter set for the translational axes and one for the rotational
  * axes (SE2_ROBOT_CONFIG :38-90, SE3_ROBOT_CONFIG :453-505); this shim reads them from axis 0 and from the last axis.
  */
 #include <uncertainty_planning_core/simple_robot_models.hpp>
+#include <uncertainty_planning_core/uncertainty_planner_state.hpp>
 #include "upc_b200.h"
 
 #include <string>
@@ -284,6 +288,53 @@ int ref_rob_distances(const upc_robot_desc* d, int n, const double* a, const dou
     if (d->kind == UPC_ROBOT_SE2) Distances<Se2Adapter>(*d, n, a, b, dist, dim_dist, dim_width);
     else if (d->kind == UPC_ROBOT_SE3) Distances<Se3Adapter>(*d, n, a, b, dist, dim_dist, dim_width);
     else Distances<LinkedAdapter>(*d, n, a, b, dist, dim_dist, dim_width);
+    return 0;
+}
+
+/*
+ * UncertaintyPlannerState(state_id, particles, ...)::UpdateStatistics(robot) (uncertainty_planner_state.hpp:339-351): expectation,
+ * variance, space-independent variance and the two per-dimension variance vectors of one particle set (a child state's cluster)
+ */
+extern "C++" {
+namespace
+{
+template <typename A, typename Serializer, typename Alloc>
+void StateStatistics(const upc_robot_desc& d, int n, const double* configs, double step_size, int dim_width, double* expectation, double* scalars, double* variances,
+                     double* si_variances)
+{
+    const int width = Width(d);
+    const typename A::Robot robot = A::Make(d);
+    std::vector<typename A::Config, Alloc> particles;
+    for (int i = 0; i < n; i++) particles.push_back(A::In(d, configs + (size_t)i * width));
+    uncertainty_planning_tools::UncertaintyPlannerState<typename A::Config, Serializer, Alloc> state(1u, particles, 1u, 1u, 1.0, 1u, 1u, 1.0, step_size,
+                                                                                                  particles.front(), 0u, 0u, 0u);
+    state.UpdateStatistics(robot);
+    A::Out(state.GetExpectation(), expectation);
+    scalars[0] = state.GetVariance();
+    scalars[1] = state.GetSpaceIndependentVariance();
+    const Eigen::VectorXd v = state.GetVariances(), sv = state.GetSpaceIndependentVariances();
+    assert(v.size() == dim_width && sv.size() == dim_width);
+    for (int k = 0; k < dim_width; k++)
+    {
+        variances[k] = v(k);
+        si_variances[k] = sv(k);
+    }
+}
+}
+}
+
+int ref_state_statistics(const upc_robot_desc* d, int n, const double* configs, double step_size, int dim_width, double* expectation, double* scalars,
+                         double* variances, double* si_variances)
+{
+    if (d->kind == UPC_ROBOT_SE2)
+        StateStatistics<Se2Adapter, simple_robot_models::EigenMatrixD31Serializer, std::allocator<Eigen::Matrix<double, 3, 1>>>(*d, n, configs, step_size, dim_width, expectation,
+                                                                                                                              scalars, variances, si_variances);
+    else if (d->kind == UPC_ROBOT_SE3)
+        StateStatistics<Se3Adapter, simple_robot_models::EigenIsometry3dSerializer, Eigen::aligned_allocator<Eigen::Isometry3d>>(*d, n, configs, step_size, dim_width, expectation,
+                                                                                                                               scalars, variances, si_variances);
+    else
+        StateStatistics<LinkedAdapter, simple_robot_models::SimpleLinkedConfigurationSerializer, std::allocator<simple_robot_models::SimpleLinkedConfiguration>>(
+            *d, n, configs, step_size, dim_width, expectation, scalars, variances, si_variances);
     return 0;
 }
 

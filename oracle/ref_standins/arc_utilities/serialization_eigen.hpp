@@ -13,6 +13,7 @@
 #include <cstring>
 #include <functional>
 #include <stdexcept>
+#include <string>
 #include <utility>
 #include <vector>
 
@@ -63,6 +64,30 @@ inline std::pair<std::vector<T, Allocator>, uint64_t> DeserializeVector(const st
     return std::make_pair(out, position - current);
 }
 
+template <typename CharType>
+inline uint64_t SerializeString(const std::basic_string<CharType>& str, std::vector<uint8_t>& buffer)
+{
+    uint64_t written = SerializeFixedSizePOD<uint64_t>((uint64_t)str.size(), buffer);
+    for (size_t i = 0; i < str.size(); i++) written += SerializeFixedSizePOD<CharType>(str[i], buffer);
+    return written;
+}
+
+template <typename CharType>
+inline std::pair<std::basic_string<CharType>, uint64_t> DeserializeString(const std::vector<uint8_t>& buffer, const uint64_t current)
+{
+    uint64_t position = current;
+    const std::pair<uint64_t, uint64_t> size = DeserializeFixedSizePOD<uint64_t>(buffer, position);
+    position += size.second;
+    std::basic_string<CharType> out;
+    for (uint64_t i = 0; i < size.first; i++)
+    {
+        const std::pair<CharType, uint64_t> c = DeserializeFixedSizePOD<CharType>(buffer, position);
+        out.push_back(c.first);
+        position += c.second;
+    }
+    return std::make_pair(out, position - current);
+}
+
 /* fixed-size matrices: coefficients, column-major */
 template <int R, int C>
 inline uint64_t SerializeEigenType(const Eigen::Matrix<double, R, C>& value, std::vector<uint8_t>& buffer)
@@ -94,6 +119,25 @@ struct EigenTypeDeserializer<Eigen::Matrix<double, R, C>>
                 out(i, j) = v.first;
                 position += v.second;
             }
+        return std::make_pair(out, position - current);
+    }
+};
+
+template <>
+struct EigenTypeDeserializer<Eigen::VectorXd>
+{
+    static std::pair<Eigen::VectorXd, uint64_t> Run(const std::vector<uint8_t>& buffer, const uint64_t current)
+    {
+        uint64_t position = current;
+        const std::pair<uint64_t, uint64_t> size = DeserializeFixedSizePOD<uint64_t>(buffer, position);
+        position += size.second;
+        Eigen::VectorXd out((long)size.first);
+        for (uint64_t i = 0; i < size.first; i++)
+        {
+            const std::pair<double, uint64_t> v = DeserializeFixedSizePOD<double>(buffer, position);
+            out((long)i) = v.first;
+            position += v.second;
+        }
         return std::make_pair(out, position - current);
     }
 };

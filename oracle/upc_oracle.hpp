@@ -4,14 +4,15 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may build, link or
  * call anything under oracle/.  The product (uncertainty_planning_core_b200/, include/) never does.
  *
- * PARITY STATUS: *partially pinned*.  The reference (UM-ARM-Lab/uncertainty_planning_core) ships no tests and
- * no golden vectors, its simulator is pure virtual (simple_simulator_interface.hpp:613-623) and the heavy
- * arithmetic lives in un-vendored, un-pinned arc_utilities / sdf_tools (package.xml:11-19).  The only piece of
- * the reference that compiles here is simple_pid_controller.hpp; oracle/_ref builds it unmodified and
- * tests/test_oracle_pid.py pins Pid::ComputeFeedbackTerm against it.  Everything else is "parity unpinned":
- * the robot models, noise models and clustering pipeline restate the cited reference lines operation by
- * operation, and the pieces the reference does not contain (SDF lookup, contact resolver, SE(3) log/exp,
- * complete-link clustering tie-breaks) follow the normative spec in DESIGN.md.
+ * PARITY STATUS: *partially pinned*.  The reference (UM-ARM-Lab/uncertainty_planning_core) ships no tests and no golden vectors,
+ * its simulator is pure virtual (simple_simulator_interface.hpp:613-623) and the heavy arithmetic lives in un-vendored, un-pinned
+ * arc_utilities / sdf_tools (package.xml:11-19).  What CAN be compiled from the reference is compiled UNMODIFIED into oracle/_ref
+ * (oracle/Makefile) and this oracle is tested against it: simple_pid_controller.hpp (tests/test_oracle_pid.py),
+ * simple_uncertainty_models.hpp (tests/test_oracle_unc.py), simple_robot_models.hpp and uncertainty_planner_state.hpp on the stand-in
+ * Eigen / arc_utilities headers of oracle/ref_standins (tests/test_oracle_rob.py: control / apply sequences, kinematics, Jacobians,
+ * distances, averages, per-cluster statistics of all three robots).  "Parity unpinned" remains for what the reference does not
+ * contain or cannot compile: the simulator loop, SDF lookup and contact resolver, complete-link clustering and the clustering member
+ * functions of UncertaintyPlanningSpace - restated from the cited lines / specified in DESIGN.md.
  *
  * Style: sequential, one robot object per particle, array-of-structs configurations - the shape of the
  * reference's CPU path (OpenMP parallel-for over particles / pairs as at uncertainty_contact_planning.hpp:1509,

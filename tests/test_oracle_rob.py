@@ -184,3 +184,41 @@ def test_average_configuration_matches_reference_header(oracle, ref, name, robot
     want = oracle.rob_average(robot, members, reference=True)
     got = oracle.rob_average(robot, members)
     assert np.allclose(got, want, rtol=0, atol=1e-13), np.abs(got - want).max()
+
+
+@pytest.mark.parametrize("name,robot,gen", ROBOTS, ids=[r[0] for r in ROBOTS])
+def test_child_state_statistics_match_reference_planner_state(oracle, ref, name, robot, gen):
+    """The per-cluster statistics (next row (f)-1): the reference's OWN uncertainty_planner_state.hpp, compiled unmodified next to its
+    robot models - UncertaintyPlannerState(particles)::UpdateStatistics(robot) (:339-351): ComputeExpectation, ComputeVariance,
+    ComputeSpaceIndependentVariance and the two directional forms (:591-714) - against the oracle's cluster statistics (which the
+    product's upc_cluster_statistics reproduces to 0 ulp on the GPU) for one cluster: many members, two members, a single member."""
+    rng = np.random.default_rng(505)
+    centre = gen(rng)
+    step_size = 0.35
+    for count in (41, 2, 1):
+        if robot.desc.kind == abi.ROBOT_SE3:
+            members = []
+            for _ in range(count):
+                R = centre[:9].reshape(3, 3) @ scenarios.rotation_from_axis_angle(rng.normal(size=3), rng.uniform(0.01, 0.2))
+                members.append(scenarios.se3_config(R, centre[9:] + rng.normal(scale=0.05, size=3)))
+            members = np.stack(members)
+        else:
+            members = centre[None, :] + rng.normal(scale=0.03, size=(count, centre.size))
+            if name.startswith("se2"):
+                members[:, 2] = -3.12 + rng.normal(scale=0.03, size=count)     # headings straddling +-pi
+            if name == "arm_mixed_joints":
+                # joint values are configurations only inside their limits (SimpleJointModel clamps on construction, :903-916);
+                # active joints 0 and 4 are continuous
+                limited = [1, 2, 3, 5]
+                members[:, limited] = np.clip(members[:, limited], -0.25, 0.25)
+        want = oracle.ref_state_statistics(robot, members, step_size)
+        got = oracle.cluster_statistics(robot, members, np.zeros(count, dtype=np.int32), np.zeros(count, dtype=bool), True, step_size, 1)
+        tol = 2e-9 if robot.desc.kind == abi.ROBOT_SE3 else 1e-13          # SE(3): arccos near zero angle, two closed forms of the quaternion
+        assert int(got["counts"][0]) == count
+        assert np.allclose(got["expectations"][0], want["expectation"], rtol=0, atol=1e-13), (count, np.abs(got["expectations"][0] - want["expectation"]).max())
+        assert abs(got["variance"][0] - want["variance"]) <= tol, count
+        assert abs(got["si_variance"][0] - want["si_variance"]) <= tol * 10, count
+        assert np.allclose(got["variances"][0], want["variances"], rtol=0, atol=tol), count
+        assert np.allclose(got["si_variances"][0], want["si_variances"], rtol=0, atol=tol * 10), count
+        if count > 2:
+            assert want["variance"] > 1e-5 and np.all(want["variances"] >= 0.0)
